@@ -1,0 +1,259 @@
+"""Python front-end of the CHECKERS.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product (lidar_transfer_b200) never does.
+
+Two families of checkers live here:
+
+* ``oracle.*``   -- oracle/liboracle.so, our C restatement (oracle/vl_oracle.c) plus the
+                    numpy restatements below.  Builds anywhere gcc exists.
+* ``oracle.ref_*`` -- oracle/_ref/*.so, the reference itself compiled from its own
+                    sources (oracle/Makefile `ref` target; only buildable where
+                    /root/reference exists, the binaries travel to the GPU box).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REF_DIR = os.path.join(_HERE, "_ref")
+REFERENCE_ROOT = "/root/reference"
+
+NORMALIZE_SSE = 1  # Vector3.h:73-89 rsqrtps + Newton step (bit-exact vs the reference on x86)
+BRUTE_FORCE = 2    # every triangle, tie-break (min t, min triangle index)
+MIN_ID_TIES = 4    # reference BVH, exact-t ties to the smaller triangle index
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_f64p = ctypes.POINTER(ctypes.c_double)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i64p = ctypes.POINTER(ctypes.c_longlong)
+
+
+def build(ref=None):
+  """Compile liboracle.so and -- when the reference checkout is present -- oracle/_ref."""
+  if ref is None:
+    ref = os.path.isdir(REFERENCE_ROOT)
+  subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+  if ref:
+    subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+
+
+_libs = {}
+
+
+def _lib(path):
+  if path not in _libs:
+    if not os.path.exists(path):
+      raise FileNotFoundError(
+          "%s missing: run `make -C oracle` (oracle) / `make -C oracle ref` (reference build)" % path)
+    _libs[path] = ctypes.CDLL(path)
+  return _libs[path]
+
+
+def have_ref(name="libref_raytracer_nofma.so"):
+  return os.path.exists(os.path.join(_REF_DIR, name))
+
+
+def _p(a, t):
+  return a.ctypes.data_as(t)
+
+
+def _prep_trace(rays, origin, verts, faces, colors, rem):
+  rays = np.ascontiguousarray(rays, np.float32).reshape(-1)
+  origin = np.ascontiguousarray(origin, np.float32).reshape(-1)
+  verts = np.ascontiguousarray(verts, np.float32).reshape(-1)
+  faces = np.ascontiguousarray(faces, np.int32).reshape(-1)
+  colors = np.ascontiguousarray(colors, np.int32).reshape(-1)
+  rem = np.ascontiguousarray(rem, np.float32).reshape(-1)
+  n_rays = rays.size // 3
+  out = dict(endpoints=np.zeros(n_rays * 3, np.float32), endcolors=np.zeros(n_rays * 3, np.int32),
+             range=np.zeros(n_rays, np.float32), endrem=np.zeros(n_rays, np.float32),
+             tri_id=np.full(n_rays, -1, np.int32))
+  return rays, origin, verts, faces, colors, rem, n_rays, out
+
+
+def trace(rays, origin, verts, faces, colors, rem, height, flags=0):
+  """vlo_trace: restatement of trace()/ctrace, auxiliary/raytracer/RayTracer.cpp:19-124."""
+  lib = _lib(os.path.join(_HERE, "liboracle.so"))
+  rays, origin, verts, faces, colors, rem, n_rays, out = _prep_trace(rays, origin, verts, faces, colors, rem)
+  stats = np.zeros(4, np.int32)
+  lib.vlo_trace(_p(rays, _f32p), _p(origin, _f32p), _p(verts, _f32p), _p(faces, _i32p), _p(colors, _i32p),
+                _p(rem, _f32p), ctypes.c_int(n_rays), ctypes.c_int(verts.size // 3),
+                ctypes.c_int(faces.size // 3), ctypes.c_int(height),
+                _p(out["endpoints"], _f32p), _p(out["endcolors"], _i32p), _p(out["range"], _f32p),
+                _p(out["endrem"], _f32p), _p(out["tri_id"], _i32p), ctypes.c_uint(flags), _p(stats, _i32p))
+  out["n_nodes"] = int(stats[0])
+  return out
+
+
+def ref_ctrace(rays, origin, verts, faces, colors, rem, height, variant="nofma", ids=False):
+  """The reference's own extern "C" ctrace (RayTracer.cpp:116-124) compiled from its sources.
+
+  variant "nofma" = canonical parity build (-ffp-contract=off), "fma" = reference flags as shipped.
+  ids=True uses the triangle-id harness (oracle/ref_ids_harness.cpp, nofma only).
+  """
+  rays, origin, verts, faces, colors, rem, n_rays, out = _prep_trace(rays, origin, verts, faces, colors, rem)
+  args = [_p(rays, _f32p), _p(origin, _f32p), _p(verts, _f32p), _p(faces, _i32p), _p(colors, _i32p),
+          _p(rem, _f32p), ctypes.c_int(n_rays), ctypes.c_int(verts.size // 3), ctypes.c_int(faces.size // 3),
+          ctypes.c_int(height), _p(out["endpoints"], _f32p), _p(out["endcolors"], _i32p),
+          _p(out["range"], _f32p), _p(out["endrem"], _f32p)]
+  if ids:
+    lib = _lib(os.path.join(_REF_DIR, "libref_ids_nofma.so"))
+    lib.ctrace_ids(*args, _p(out["tri_id"], _i32p))
+  else:
+    name = "libref_raytracer_nofma.so" if variant == "nofma" else "libref_raytracer.so"
+    lib = _lib(os.path.join(_REF_DIR, name))
+    lib.ctrace(*args)
+    out.pop("tri_id")
+  return out
+
+
+def create_rays(fov_up, fov_down, H, W):
+  """Restates MultiSemLaserScan.create_rays, auxiliary/laserscan.py:1092-1119."""
+  initial = 180
+  yaw_angles = (np.linspace(0, 360, W) + initial)
+  larger = yaw_angles > 360
+  yaw_angles[larger] -= 360
+  yaw = yaw_angles / 180. * np.pi
+  pitch = np.linspace(fov_up, fov_down, H) / 180. * np.pi
+  pitch = np.pi / 2 - pitch
+  beams = np.empty((H, W, 3), np.float64)
+  for i, p in enumerate(pitch):
+    beams[i, :, 0] = np.sin(p) * np.cos(-yaw)
+    beams[i, :, 1] = np.sin(p) * np.sin(-yaw)
+    beams[i, :, 2] = np.cos(p) * np.ones(yaw.shape)
+  return np.ascontiguousarray(beams.reshape(W * H, -1).astype(np.float32))
+
+
+def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True):
+  """vlo_project: do_range_projection_new('depth') + do_label_projection_new,
+  auxiliary/laserscan.py:294-391, 672-676."""
+  lib = _lib(os.path.join(_HERE, "liboracle.so"))
+  lib.vlo_project.restype = ctypes.c_long
+  points = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+  n = points.shape[0]
+  remissions = np.ascontiguousarray(remissions, np.float32)
+  labels = np.ascontiguousarray(labels, np.uint32)
+  out = dict(range_image=np.empty(H * W, np.float32), index=np.empty(H * W, np.int32),
+             proj_label=np.empty(H * W, np.int32), proj_remissions=np.empty(H * W, np.float32),
+             keep=np.empty(n, np.uint8))
+  kept = lib.vlo_project(_p(points, _f64p), _p(remissions, _f32p), _p(labels, _u32p), ctypes.c_long(n),
+                         ctypes.c_double(fov_up), ctypes.c_double(fov_down), ctypes.c_int(H), ctypes.c_int(W),
+                         ctypes.c_int(1 if remove else 0), _p(out["range_image"], _f32p), _p(out["index"], _i32p),
+                         _p(out["proj_label"], _i32p), _p(out["proj_remissions"], _f32p), _p(out["keep"], _u8p))
+  for k in ("range_image", "index", "proj_label", "proj_remissions"):
+    out[k] = out[k].reshape(H, W)
+  out["n_kept"] = int(kept)
+  out["keep"] = out["keep"].astype(bool)
+  return out
+
+
+def project_numpy(points, remissions, labels, fov_up, fov_down, H, W, remove=True):
+  """Pure-numpy/Python-loop restatement of the same projection (small inputs only);
+  line-for-line semantics of auxiliary/laserscan.py:294-391 used to cross-check vlo_project."""
+  points = np.asarray(points, np.float64).reshape(-1, 3)
+  remissions = np.asarray(remissions, np.float32)
+  labels = np.asarray(labels, np.uint32)
+  fu = fov_up / 180.0 * np.pi
+  fd = fov_down / 180.0 * np.pi
+  fov = abs(fd) + abs(fu)
+  depth = np.linalg.norm(points, 2, axis=1)
+  k0 = depth != 0
+  depth, points, remissions, labels = depth[k0], points[k0], remissions[k0], labels[k0]
+  yaw = -np.arctan2(points[:, 1], points[:, 0])
+  pitch = np.arcsin(points[:, 2] / depth)
+  proj_x = 0.5 * (yaw / np.pi + 1.0)
+  proj_y = 1.0 - (pitch + abs(fd)) / fov
+  keep = k0.copy()
+  if remove:
+    k1 = (proj_y >= 0) & (proj_y <= 1)
+    depth, proj_x, proj_y, remissions, labels = depth[k1], proj_x[k1], proj_y[k1], remissions[k1], labels[k1]
+    keep[np.flatnonzero(k0)[~k1]] = False
+  proj_x = proj_x * W
+  proj_y = proj_y * H
+  px = np.maximum(0, np.minimum(W - 1, np.floor(proj_x))).astype(np.int32)
+  py = np.maximum(0, np.minimum(H - 1, np.floor(proj_y))).astype(np.int32)
+  index = np.full((H, W), -1, np.int32)
+  range_image = np.zeros((H, W), np.float32)
+  proj_rem = np.full((H, W), -1, np.float32)
+  for i in range(len(depth)):
+    if depth[i] < range_image[py[i], px[i]] or index[py[i], px[i]] == -1:
+      range_image[py[i], px[i]] = depth[i]
+      index[py[i], px[i]] = i
+      proj_rem[py[i], px[i]] = remissions[i]
+  proj_label = np.zeros((H, W), np.int32)
+  mask = index >= 0
+  proj_label[mask] = labels[index[mask]]
+  return dict(range_image=range_image, index=index, proj_label=proj_label, proj_remissions=proj_rem,
+              keep=keep, n_kept=int(len(depth)))
+
+
+def _tsdf_args(vol_dim, vol_origin, voxel_size, im_h, im_w, trunc, obs_weight, fov_up, fov_down):
+  vd = np.asarray(vol_dim, np.float32).copy()
+  vo = np.asarray(vol_origin, np.float32).copy()
+  other = np.asarray([0, voxel_size, im_h, im_w, trunc, obs_weight, fov_up, fov_down], np.float32)
+  return vd, vo, other
+
+
+def tsdf_new_volume(vol_dim):
+  """Fresh volumes as TSDFVolume.__init__ makes them, auxiliary/fusion_lidar.py:48-52."""
+  vol_dim = tuple(int(v) for v in vol_dim)
+  return dict(tsdf=np.ones(vol_dim, np.float32), weight=np.zeros(vol_dim, np.float32),
+              color=np.zeros(vol_dim, np.float32), rem=np.zeros(vol_dim, np.float32))
+
+
+def label_to_color_im(proj_label):
+  """integrate()'s fold of the 3-channel image, fusion_lidar.py:259-264, for
+  proj_label3[:, :, 0] = label (laserscan.py:970-971)."""
+  lab = np.asarray(proj_label).astype(np.float32)
+  return np.floor(lab * 256 * 256 + np.float32(0) * 256 + np.float32(0)).astype(np.float32)
+
+
+def tsdf_integrate(vol, vol_origin, voxel_size, color_im, depth_im, rem_im, fov_up, fov_down,
+                   obs_weight=1.0, use_ref=False):
+  """In-place integrate of one range image into vol (dict from tsdf_new_volume).
+
+  use_ref=False: vlo_tsdf_integrate (restatement); use_ref=True: the reference's CUDA kernel
+  string compiled for the CPU (oracle/_ref/libref_tsdf.so)."""
+  im_h, im_w = depth_im.shape
+  trunc = voxel_size * 5  # fusion_lidar.py:31
+  vd, vo, other = _tsdf_args(vol["tsdf"].shape, vol_origin, voxel_size, im_h, im_w, trunc, obs_weight,
+                             fov_up, fov_down)
+  color_im = np.ascontiguousarray(color_im, np.float32).reshape(-1)
+  depth_im = np.ascontiguousarray(depth_im, np.float32).reshape(-1)
+  rem_im = np.ascontiguousarray(rem_im, np.float32).reshape(-1)
+  for k in ("tsdf", "weight", "color", "rem"):
+    assert vol[k].flags["C_CONTIGUOUS"] and vol[k].dtype == np.float32
+  counters = np.zeros(2, np.int64)
+  if use_ref:
+    lib = _lib(os.path.join(_REF_DIR, "libref_tsdf.so"))
+    cam_pose = np.eye(4, dtype=np.float32).reshape(-1)
+    lib.ref_tsdf_integrate(_p(vol["tsdf"], _f32p), _p(vol["weight"], _f32p), _p(vol["color"], _f32p),
+                           _p(vol["rem"], _f32p), _p(vd, _f32p), _p(vo, _f32p), _p(cam_pose, _f32p),
+                           _p(other, _f32p), _p(color_im, _f32p), _p(depth_im, _f32p), _p(rem_im, _f32p))
+  else:
+    lib = _lib(os.path.join(_HERE, "liboracle.so"))
+    lib.vlo_tsdf_integrate(_p(vol["tsdf"], _f32p), _p(vol["weight"], _f32p), _p(vol["color"], _f32p),
+                           _p(vol["rem"], _f32p), _p(vd, _f32p), _p(vo, _f32p), _p(other, _f32p),
+                           _p(color_im, _f32p), _p(depth_im, _f32p), _p(rem_im, _f32p), _p(counters, _i64p))
+  return dict(n_vis=int(counters[0]), n_written=int(counters[1]))
+
+
+def mesh_attributes(verts_vox, color_vol, rem_vol, voxel_size, vol_origin):
+  """Vertex world coords / colours / remission lookup of TSDFVolume.get_mesh,
+  auxiliary/fusion_lidar.py:408-423 (numpy, verbatim order)."""
+  verts_vox = np.asarray(verts_vox, np.float32)
+  verts_ind = np.round(verts_vox).astype(int)
+  verts = verts_vox * voxel_size + np.asarray(vol_origin, np.float32)
+  rgb_vals = color_vol[verts_ind[:, 0], verts_ind[:, 1], verts_ind[:, 2]]
+  rem = rem_vol[verts_ind[:, 0], verts_ind[:, 1], verts_ind[:, 2]]
+  colors_b = np.floor(rgb_vals / (256 * 256))
+  colors_g = np.floor((rgb_vals - colors_b * 256 * 256) / 256)
+  colors_r = rgb_vals - colors_b * 256 * 256 - colors_g * 256
+  colors = np.floor(np.asarray([colors_r, colors_g, colors_b])).T
+  colors = colors.astype(np.int64).astype(np.uint8)
+  return verts.astype(np.float32), colors, rem
