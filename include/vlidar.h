@@ -1,0 +1,143 @@
+/*
+ * vlidar.h -- C ABI of libvlidar.so, the B200 (sm_100a) virtual-LiDAR hot path.
+ *
+ * Drop-in boundary for PRBonn/lidar_transfer (reference file:line in each comment).
+ * Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * Two layers:
+ *   1. `ctrace`  -- the reference's own extern "C" entry point, HOST pointers, same
+ *                   signature and semantics (auxiliary/raytracer/RayTracer.cpp:116-124,
+ *                   bound by auxiliary/raytracer/RayTracerCython.pyx:5-7).
+ *   2. `vl_*`    -- the device-pointer API the Python host side (torch tensors) calls:
+ *                   stream-ordered, no hidden allocation, never throws.  Returns 0 on
+ *                   success or a negative VL_E* code; vl_last_error() has the text.
+ *
+ * There is no CPU fallback: every entry point fails loudly when no CUDA device is usable.
+ */
+#ifndef VLIDAR_H_
+#define VLIDAR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VL_ABI_VERSION 1
+
+#define VL_OK            0
+#define VL_EINVAL       -1   /* bad argument (null pointer, negative size, misaligned blob) */
+#define VL_ENOSPACE     -2   /* caller-provided workspace too small */
+#define VL_ECUDA        -3   /* CUDA runtime / launch error (text in vl_last_error) */
+#define VL_EBADMESH     -4   /* face index outside [0, n_verts) detected on device */
+
+/* cudaStream_t passed as an opaque pointer (torch.cuda.current_stream().cuda_stream). */
+typedef void* vl_stream;
+
+int         vl_abi_version(void);
+const char* vl_last_error(void);   /* thread-local, never NULL */
+int         vl_device_count(void); /* >0 or VL_ECUDA */
+
+/* ------------------------------------------------------------------------------------
+ * (0) reference-compatible host entry point.
+ *
+ * Replaces: void ctrace(...)  auxiliary/raytracer/RayTracer.cpp:116-124 (-> trace(), :19-114).
+ * All pointers are HOST pointers to caller-owned contiguous buffers.  Builds the BVH over
+ * the indexed mesh, casts n_rays rays (width = n_rays / height, RayTracer.cpp:56) from
+ * origin[3] and, for HITS ONLY, writes endpoints[3r..], endcolors[3r..] (= colours of the
+ * hit triangle's vertex 0), endrem[r] (= mean remission of its three vertices) and
+ * range[r]; entries of missing rays are left untouched (the caller zero-fills,
+ * auxiliary/fusion_lidar.py:440-447).  n_verts is used to validate face indices (the
+ * reference ignores it; a bad index there is undefined behaviour).  Synchronous.
+ * Like the reference it returns void; failures are reported through vl_last_error() and
+ * vl_ctrace_status().  Unlike the reference it prints nothing to stdout.
+ * ---------------------------------------------------------------------------------- */
+void ctrace(float* rays, float* origin, float* verts, int* faces, int* colors, float* rem,
+            int n_rays, int n_verts, int n_faces, int height,
+            float* endpoints, int* endcolors, float* range, float* endrem);
+int  vl_ctrace_status(void);       /* status of this thread's most recent ctrace() */
+
+/* Same as ctrace plus a nullable per-ray triangle-id output (-1 = miss, written for every
+ * ray) and an explicit return code. */
+int vl_ctrace_ids(const float* rays, const float* origin, const float* verts, const int* faces,
+                  const int* colors, const float* rem, int n_rays, int n_verts, int n_faces,
+                  int height, float* endpoints, int* endcolors, float* range, float* endrem,
+                  int* tri_id);
+
+/* ------------------------------------------------------------------------------------
+ * (i) LBVH build over the per-scan triangle mesh.
+ *
+ * Replaces: Triangle construction RayTracer.cpp:32-51 + BVH::BVH/build BVH.cpp:112-243.
+ * d_* are DEVICE pointers.  The BVH (nodes, sorted triangle records, per-triangle vertex-0
+ * colours) and all build temporaries live in ONE caller-provided device blob of at least
+ * vl_bvh_blob_bytes(n_faces) bytes, 256-byte aligned.  Input arrays are not referenced
+ * after the build kernels finish.
+ * ---------------------------------------------------------------------------------- */
+size_t vl_bvh_blob_bytes(int n_faces);
+int vl_bvh_build(const float* d_verts, const int* d_faces, const int* d_colors, const float* d_rem,
+                 int n_verts, int n_faces, void* d_blob, size_t blob_bytes, vl_stream stream);
+/* Synchronises the stream and reads the build status word: VL_OK or VL_EBADMESH.
+ * info (nullable, int[8]): [0] n_tris [1] root ref [2] n_bad_faces [3] max climb depth. */
+int vl_bvh_status(const void* d_blob, int n_faces, vl_stream stream, int* info);
+
+/* ------------------------------------------------------------------------------------
+ * (ii) closest-hit traversal + Moller-Trumbore.
+ *
+ * Replaces: the ray loop RayTracer.cpp:62-92, BVH::getIntersection BVH.cpp:19-110,
+ * BBox::intersect BBox.cpp:52-100, Triangle::getIntersection Triangle.h:27-50,
+ * normalize Vector3.h:73-89 (IEEE 1/sqrt instead of rsqrtps+NR).
+ * d_rays float32[3*n_rays] (not normalised), d_origin float32[3] on the device.
+ * Outputs as in ctrace (hits only) except d_tri_id (nullable): written for every ray,
+ * original face index or -1.  Exact-t ties go to the smaller face index.
+ * ---------------------------------------------------------------------------------- */
+int vl_trace(const void* d_blob, int n_faces, const float* d_rays, const float* d_origin,
+             int n_rays, int height, float* d_endpoints, int* d_endcolors, float* d_range,
+             float* d_endrem, int* d_tri_id, vl_stream stream);
+
+/* Test aid: same outputs by testing every triangle per ray (no BVH). */
+int vl_trace_bruteforce(const float* d_verts, const int* d_faces, const int* d_colors,
+                        const float* d_rem, int n_verts, int n_faces, const float* d_rays,
+                        const float* d_origin, int n_rays, int height, float* d_endpoints,
+                        int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id,
+                        vl_stream stream);
+
+/* ------------------------------------------------------------------------------------
+ * (iii) spherical range-image projection (atomicMin-on-depth scatter).
+ *
+ * Replaces: LaserScan.do_range_projection_new(method="depth") auxiliary/laserscan.py:294-391
+ * and SemLaserScan.do_label_projection_new :672-676.
+ * d_points float64[3*n] (the reference holds float64 after the pose round trip),
+ * d_remissions float32[n], d_labels uint32[n].  fov in degrees.  remove != 0 applies the
+ * vertical-FOV filter.  Outputs: d_range f32[H*W] (0 empty), d_index i32[H*W] (-1 empty;
+ * index into the KEPT point list, like the reference after remove_points), d_label
+ * i32[H*W] (0 empty), d_rem f32[H*W] (-1 empty), d_keep u8[n] (nullable), d_n_kept
+ * int[1] (nullable).  Workspace: vl_project_workspace_bytes(n, H, W) device bytes.
+ * ---------------------------------------------------------------------------------- */
+size_t vl_project_workspace_bytes(long n_points, int H, int W);
+int vl_project(const double* d_points, const float* d_remissions, const uint32_t* d_labels,
+               long n_points, double fov_up_deg, double fov_down_deg, int H, int W, int remove,
+               float* d_range, int32_t* d_index, int32_t* d_label, float* d_rem,
+               uint8_t* d_keep, int* d_n_kept, void* d_workspace, size_t workspace_bytes,
+               vl_stream stream);
+
+/* ------------------------------------------------------------------------------------
+ * (iv) class-aware TSDF voxel integration.
+ *
+ * Replaces: the pycuda `integrate` kernel auxiliary/fusion_lidar.py:66-229 and its launch
+ * :252-287; vl_tsdf_init replaces the host-side volume initialisation + upload :48-63.
+ * Volumes are float32[dx*dy*dz], C order (z fastest).  d_color_im is the folded single
+ * channel image (label * 65536, fusion_lidar.py:259-264).
+ * ---------------------------------------------------------------------------------- */
+int vl_tsdf_init(float* d_tsdf, float* d_weight, float* d_color, float* d_rem,
+                 long long n_voxels, vl_stream stream);
+int vl_tsdf_integrate(float* d_tsdf, float* d_weight, float* d_color, float* d_rem,
+                      int dx, int dy, int dz, const float vol_origin[3], float voxel_size,
+                      float trunc_margin, float obs_weight, float fov_up_deg, float fov_down_deg,
+                      const float* d_color_im, const float* d_depth_im, const float* d_rem_im,
+                      int im_h, int im_w, vl_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLIDAR_H_ */

@@ -1,0 +1,175 @@
+// vl_project.cu -- (iii) spherical range-image projection as an atomicMin-on-depth scatter, sm_100a.
+//
+// Replaces LaserScan.do_range_projection_new(method="depth") (auxiliary/laserscan.py:294-391,
+// a per-point PYTHON loop) and SemLaserScan.do_label_projection_new (:672-676).
+//
+// The reference loop is sequential and compares the float64 depth of point i against the
+// float32 value already stored in the image (:376-378):   depth[i] < range_image[py,px].
+// Let R(i) = float32(depth[i]).  Per pixel the loop's final winner is (proof):
+//   R* = min_i R(i);  among points with R(i) == R*:
+//     the LAST  index with depth[i] <  R*  (such a point always displaces the incumbent), else
+//     the FIRST index (all have depth[i] >= R*, none can displace the first entrant).
+// One 64-bit atomicMin reproduces that exactly:
+//   key = R bits << 32 | (depth < R ? 0x7fffffff - i : 0x80000000 | i).
+// Compile with -fmad=false: the float64 expressions must round like numpy's.
+#include "vl_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct ProjParams {
+  double fov_down_abs, fov, pi;
+  int H, W, remove;
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_project_scatter(const double* __restrict__ pts, long n, ProjParams P, unsigned long long* __restrict__ keys,
+                  unsigned int* __restrict__ masks, unsigned int* __restrict__ warp_counts,
+                  uint8_t* __restrict__ keep_out) {
+  const long i = (long)blockIdx.x * kThreads + threadIdx.x;
+  bool keep = false;
+  if (i < n) {
+    const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    const double depth = sqrt((x * x + y * y) + z * z);  // np.linalg.norm(points, 2, axis=1), :304
+    if (depth != 0.0) {                                   // :307-309
+      const double yaw = -atan2(y, x);
+      const double pitch = asin(z / depth);
+      double proj_x = 0.5 * (yaw / P.pi + 1.0);           // :329-330
+      double proj_y = 1.0 - (pitch + P.fov_down_abs) / P.fov;
+      if (!P.remove || (proj_y >= 0.0 && proj_y <= 1.0)) {  // :337-345
+        proj_x *= P.W;
+        proj_y *= P.H;
+        double fx = fmax(0.0, fmin((double)(P.W - 1), floor(proj_x)));  // :355-360
+        double fy = fmax(0.0, fmin((double)(P.H - 1), floor(proj_y)));
+        const int pix = (int)fy * P.W + (int)fx;
+        const float R = (float)depth;
+        const unsigned int lo = (depth < (double)R) ? (0x7fffffffu - (unsigned int)i) : (0x80000000u | (unsigned int)i);
+        atomicMin(keys + pix, ((unsigned long long)__float_as_uint(R) << 32) | lo);
+        keep = true;
+      }
+    }
+    if (keep_out) keep_out[i] = keep ? 1 : 0;
+  }
+  const unsigned int m = __ballot_sync(0xffffffffu, keep);
+  if ((threadIdx.x & 31) == 0) {
+    const long w = i >> 5;
+    if (w * 32 < n) { masks[w] = m; warp_counts[w] = __popc(m); }
+  }
+}
+
+// single-CTA exclusive scan of the per-warp kept counts (n/32 entries); total -> n_kept
+__global__ void __launch_bounds__(1024) k_scan_counts(unsigned int* __restrict__ counts, long total, int* n_kept) {
+  __shared__ unsigned int warp_sums[32];
+  __shared__ unsigned int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  constexpr int kPer = 4;
+  for (long base = 0; base < total; base += 1024 * kPer) {
+    unsigned int v[kPer], sum = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      long idx = base + (long)tid * kPer + k;
+      v[k] = idx < total ? counts[idx] : 0u;
+      sum += v[k];
+    }
+    unsigned int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned int t = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned int ws = warp_sums[lane], wi = ws;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        unsigned int t = __shfl_up_sync(0xffffffffu, wi, off);
+        if (lane >= off) wi += t;
+      }
+      warp_sums[lane] = wi - ws;
+    }
+    __syncthreads();
+    unsigned int run = carry_s + warp_sums[wid] + (incl - sum);
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      long idx = base + (long)tid * kPer + k;
+      if (idx < total) counts[idx] = run;
+      run += v[k];
+    }
+    __syncthreads();
+    if (tid == 1023) carry_s = run;
+    __syncthreads();
+  }
+  if (tid == 0 && n_kept) *n_kept = (int)carry_s;
+}
+
+// per pixel: decode the winner, translate its index into the kept-point numbering, gather
+__global__ void __launch_bounds__(kThreads)
+k_project_gather(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ masks,
+                 const unsigned int* __restrict__ warp_prefix, const float* __restrict__ remissions,
+                 const uint32_t* __restrict__ labels, int n_pix, float* __restrict__ range, int32_t* __restrict__ index,
+                 int32_t* __restrict__ label, float* __restrict__ rem) {
+  const int p = blockIdx.x * kThreads + threadIdx.x;
+  if (p >= n_pix) return;
+  const unsigned long long key = keys[p];
+  if (key == ~0ull) {  // :362-367 initial values
+    range[p] = 0.0f; index[p] = -1; label[p] = 0; rem[p] = -1.0f;
+    return;
+  }
+  const unsigned int lo = (unsigned int)key;
+  const unsigned int i = (lo & 0x80000000u) ? (lo & 0x7fffffffu) : (0x7fffffffu - lo);
+  range[p] = __uint_as_float((unsigned int)(key >> 32));
+  index[p] = (int)(warp_prefix[i >> 5] + __popc(masks[i >> 5] & ((1u << (i & 31)) - 1u)));
+  label[p] = (int32_t)labels[i];   // :672-676
+  rem[p] = remissions[i];
+}
+
+}  // namespace
+
+extern "C" size_t vl_project_workspace_bytes(long n_points, int H, int W) {
+  size_t nw = (size_t)((n_points + 31) / 32) + 1;
+  return vl_align256(8 * (size_t)H * W) + 2 * vl_align256(4 * nw);
+}
+
+extern "C" int vl_project(const double* d_points, const float* d_remissions, const uint32_t* d_labels, long n_points,
+                          double fov_up_deg, double fov_down_deg, int H, int W, int remove, float* d_range,
+                          int32_t* d_index, int32_t* d_label, float* d_rem, uint8_t* d_keep, int* d_n_kept,
+                          void* d_workspace, size_t workspace_bytes, vl_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (H <= 0 || W <= 0 || n_points < 0 || n_points >= 0x7fffffffL || !d_range || !d_index || !d_label || !d_rem ||
+      !d_workspace || (n_points > 0 && (!d_points || !d_remissions || !d_labels))) {
+    vl_set_error("vl_project: invalid argument");
+    return VL_EINVAL;
+  }
+  if (workspace_bytes < vl_project_workspace_bytes(n_points, H, W)) {
+    vl_set_error("vl_project: workspace too small (%zu < %zu)", workspace_bytes, vl_project_workspace_bytes(n_points, H, W));
+    return VL_ENOSPACE;
+  }
+  const size_t nw = (size_t)((n_points + 31) / 32);
+  char* ws = static_cast<char*>(d_workspace);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws);
+  unsigned int* masks = reinterpret_cast<unsigned int*>(ws + vl_align256(8 * (size_t)H * W));
+  unsigned int* counts = reinterpret_cast<unsigned int*>(ws + vl_align256(8 * (size_t)H * W) + vl_align256(4 * (nw + 1)));
+  ProjParams P;
+  P.pi = 3.141592653589793;  // np.pi
+  const double fov_up = fov_up_deg / 180.0 * P.pi, fov_down = fov_down_deg / 180.0 * P.pi;  // :299-301
+  P.fov_down_abs = fabs(fov_down);
+  P.fov = fabs(fov_down) + fabs(fov_up);
+  P.H = H; P.W = W; P.remove = remove;
+  VL_CUDA_CHECK(cudaMemsetAsync(keys, 0xff, 8 * (size_t)H * W, stream));
+  if (n_points > 0) {
+    const int nb = (int)((n_points + kThreads - 1) / kThreads);
+    k_project_scatter<<<nb, kThreads, 0, stream>>>(d_points, n_points, P, keys, masks, counts, d_keep);
+    VL_LAUNCH_CHECK("k_project_scatter");
+  }
+  k_scan_counts<<<1, 1024, 0, stream>>>(counts, (long)nw, d_n_kept);
+  VL_LAUNCH_CHECK("k_scan_counts");
+  const int n_pix = H * W;
+  k_project_gather<<<(n_pix + kThreads - 1) / kThreads, kThreads, 0, stream>>>(keys, masks, counts, d_remissions, d_labels,
+                                                                             n_pix, d_range, d_index, d_label, d_rem);
+  VL_LAUNCH_CHECK("k_project_gather");
+  return VL_OK;
+}

@@ -1,0 +1,243 @@
+// vl_trace.cu -- (ii) per-ray closest-hit BVH traversal + Moller-Trumbore, sm_100a.
+//
+// Replaces the reference's hot loop: RayTracer.cpp:62-92 (per-pixel loop and write-back),
+// BVH::getIntersection BVH.cpp:19-110, BBox::intersect BBox.cpp:52-100,
+// Triangle::getIntersection Triangle.h:27-50, normalize Vector3.h:73-89.
+//
+// Result contract: the closest hit under the reference's Moller-Trumbore
+// arithmetic over ALL triangles -- the tree only prunes.  The slab test is conservative
+// (padded leaf boxes + relaxed far bound) so it can never cull a triangle the triangle test
+// would accept; exact-t ties go to the smaller original face index.
+#include "vl_common.cuh"
+
+namespace {
+
+constexpr int kTraceThreads = 128;
+constexpr int kSmemStack = 24;   // per-thread stack entries held in shared memory
+constexpr int kLocalStack = 48;  // overflow (LBVH height is bounded by 64 key bits)
+
+struct Hit {
+  float t;
+  int pos;     // sorted triangle position
+  int orig;    // original face index
+  float rem;
+};
+
+// slab test of one box; lanes with NaN (0 * inf) impose no constraint, like the reference's
+// min/max ordering (BBox.cpp:70-80).  `exact_nan` is only needed when a direction component is 0.
+template <bool kNanFilter>
+__device__ __forceinline__ void slab(const float bminx, const float bminy, const float bminz, const float bmaxx,
+                                     const float bmaxy, const float bmaxz, const float3 o, const float3 inv_d,
+                                     float* tnear, float* tfar) {
+  float l1x = (bminx - o.x) * inv_d.x, l2x = (bmaxx - o.x) * inv_d.x;
+  float l1y = (bminy - o.y) * inv_d.y, l2y = (bmaxy - o.y) * inv_d.y;
+  float l1z = (bminz - o.z) * inv_d.z, l2z = (bmaxz - o.z) * inv_d.z;
+  float lox, loy, loz, hix, hiy, hiz;
+  if (kNanFilter) {
+    hix = fmaxf(fminf(l1x, INFINITY), fminf(l2x, INFINITY)); lox = fminf(fmaxf(l1x, -INFINITY), fmaxf(l2x, -INFINITY));
+    hiy = fmaxf(fminf(l1y, INFINITY), fminf(l2y, INFINITY)); loy = fminf(fmaxf(l1y, -INFINITY), fmaxf(l2y, -INFINITY));
+    hiz = fmaxf(fminf(l1z, INFINITY), fminf(l2z, INFINITY)); loz = fminf(fmaxf(l1z, -INFINITY), fmaxf(l2z, -INFINITY));
+    if (l1x != l1x || l2x != l2x) { lox = -INFINITY; hix = INFINITY; }
+    if (l1y != l1y || l2y != l2y) { loy = -INFINITY; hiy = INFINITY; }
+    if (l1z != l1z || l2z != l2z) { loz = -INFINITY; hiz = INFINITY; }
+  } else {
+    lox = fminf(l1x, l2x); hix = fmaxf(l1x, l2x);
+    loy = fminf(l1y, l2y); hiy = fmaxf(l1y, l2y);
+    loz = fminf(l1z, l2z); hiz = fmaxf(l1z, l2z);
+  }
+  *tnear = fmaxf(fmaxf(lox, loy), loz);
+  *tfar = fminf(fminf(hix, hiy), hiz);
+}
+
+template <bool kNanFilter>
+__device__ __forceinline__ void traverse(const VlNode* __restrict__ nodes, const VlTri* __restrict__ tris,
+                                         int root_ref, const float3 o, const float3 d, const float3 inv_d,
+                                         uint2 (*sstack)[kTraceThreads], Hit* best) {
+  uint2 lstack[kLocalStack];
+  int sp = 0;
+  int ref = root_ref;
+  const int tid = threadIdx.x;
+  while (true) {
+    if (ref >= 0) {
+      const float4* q = nodes[ref].q;
+      const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), e = __ldg(q + 3);
+      float tn0, tf0, tn1, tf1;
+      slab<kNanFilter>(a.x, a.y, a.z, a.w, b.x, b.y, o, inv_d, &tn0, &tf0);
+      slab<kNanFilter>(b.z, b.w, c.x, c.y, c.z, c.w, o, inv_d, &tn1, &tf1);
+      // BBox.cpp:97 `tfar >= 0 && tfar >= tnear`, with a relaxed far bound; BVH.cpp:41 prune
+      tf0 = tf0 * 1.0000004f; tf1 = tf1 * 1.0000004f;
+      const bool h0 = (tf0 >= 0.f) & (tf0 >= tn0) & (tn0 <= best->t);
+      const bool h1 = (tf1 >= 0.f) & (tf1 >= tn1) & (tn1 <= best->t);
+      const int r0 = __float_as_int(e.x), r1 = __float_as_int(e.y);
+      if (h0 & h1) {
+        const bool swap = tn1 < tn0;  // BVH.cpp:77: nearer child first
+        const int far_ref = swap ? r0 : r1;
+        const float far_t = swap ? tn0 : tn1;
+        ref = swap ? r1 : r0;
+        const uint2 ent = make_uint2((unsigned)far_ref, __float_as_uint(far_t));
+        if (sp < kSmemStack) sstack[sp][tid] = ent; else lstack[sp - kSmemStack] = ent;
+        ++sp;
+        continue;
+      }
+      if (h0) { ref = r0; continue; }
+      if (h1) { ref = r1; continue; }
+    } else {
+      const int first = vl_leaf_first(ref), count = vl_leaf_count(ref);
+      for (int k = 0; k < count; ++k) {
+        const float4* tq = reinterpret_cast<const float4*>(tris + first + k);
+        const float4 v0 = __ldg(tq), e1 = __ldg(tq + 1), e2 = __ldg(tq + 2);
+        float t;
+        if (vl_tri_hit(v0, e1, e2, o, d, &t)) {
+          const int orig = __float_as_int(v0.w);
+          if (t < best->t || (t == best->t && orig < best->orig)) {
+            best->t = t; best->pos = first + k; best->orig = orig; best->rem = e1.w;
+          }
+        }
+      }
+    }
+    // pop, skipping entries that can no longer beat the best hit (BVH.cpp:41)
+    bool found = false;
+    while (sp > 0) {
+      --sp;
+      const uint2 ent = sp < kSmemStack ? sstack[sp][tid] : lstack[sp - kSmemStack];
+      if (__uint_as_float(ent.y) <= best->t) { ref = (int)ent.x; found = true; break; }
+    }
+    if (!found) break;
+  }
+}
+
+__global__ void __launch_bounds__(kTraceThreads)
+k_trace(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ nodes, const VlTri* __restrict__ tris,
+        const int4* __restrict__ c0, const float* __restrict__ rays, const float* __restrict__ origin, int n_traced,
+        float* __restrict__ endpoints, int* __restrict__ endcolors, float* __restrict__ range,
+        float* __restrict__ endrem, int* __restrict__ tri_id) {
+  __shared__ uint2 sstack[kSmemStack][kTraceThreads];
+  const int r = blockIdx.x * kTraceThreads + threadIdx.x;
+  if (r >= n_traced) return;
+  const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
+  const float3 d = vl_normalize(__ldg(rays + 3 * (size_t)r), __ldg(rays + 3 * (size_t)r + 1), __ldg(rays + 3 * (size_t)r + 2));
+  const float3 inv_d = make_float3(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));  // Ray.h:11-12
+  Hit best;
+  best.t = 999999999.f;  // BVH.cpp:20
+  best.pos = -1; best.orig = 0x7fffffff; best.rem = 0.f;
+  const int root = hdr->root_ref;
+  if (hdr->n_tris > 0) {
+    if (d.x == 0.f || d.y == 0.f || d.z == 0.f || !(d.x == d.x))
+      traverse<true>(nodes, tris, root, o, d, inv_d, sstack, &best);
+    else
+      traverse<false>(nodes, tris, root, o, d, inv_d, sstack, &best);
+  }
+  if (best.pos >= 0) {
+    // RayTracer.cpp:73-90 write-back, BVH.cpp:106-107 hit = o + d * t
+    const int4 col = __ldg(c0 + best.pos);
+    endpoints[3 * (size_t)r + 0] = __fadd_rn(o.x, __fmul_rn(d.x, best.t));
+    endpoints[3 * (size_t)r + 1] = __fadd_rn(o.y, __fmul_rn(d.y, best.t));
+    endpoints[3 * (size_t)r + 2] = __fadd_rn(o.z, __fmul_rn(d.z, best.t));
+    endcolors[3 * (size_t)r + 0] = col.x;
+    endcolors[3 * (size_t)r + 1] = col.y;
+    endcolors[3 * (size_t)r + 2] = col.z;
+    endrem[r] = best.rem;
+    range[r] = best.t;
+  }
+  if (tri_id) tri_id[r] = best.pos >= 0 ? best.orig : -1;
+}
+
+// ---------------------------------------------------------------------------
+// test aid: every ray against every triangle, triangles staged through shared memory
+// ---------------------------------------------------------------------------
+constexpr int kBfTile = 128;
+
+__global__ void __launch_bounds__(kTraceThreads)
+k_trace_bruteforce(const float* __restrict__ verts, const int* __restrict__ faces, const int* __restrict__ colors,
+                   const float* __restrict__ rem, int n_verts, int n_faces, const float* __restrict__ rays,
+                   const float* __restrict__ origin, int n_traced, float* __restrict__ endpoints,
+                   int* __restrict__ endcolors, float* __restrict__ range, float* __restrict__ endrem,
+                   int* __restrict__ tri_id) {
+  __shared__ float4 sv0[kBfTile], se1[kBfTile], se2[kBfTile];
+  const int r = blockIdx.x * kTraceThreads + threadIdx.x;
+  const bool active = r < n_traced;
+  const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
+  float3 d = make_float3(0.f, 0.f, 0.f);
+  if (active) d = vl_normalize(__ldg(rays + 3 * (size_t)r), __ldg(rays + 3 * (size_t)r + 1), __ldg(rays + 3 * (size_t)r + 2));
+  float best_t = 999999999.f;
+  int best = -1;
+  for (int base = 0; base < n_faces; base += kBfTile) {
+    __syncthreads();
+    const int f = base + threadIdx.x;
+    if (threadIdx.x < kBfTile) {
+      float4 v0 = make_float4(0, 0, 0, 0), e1 = v0, e2 = v0;
+      if (f < n_faces) {
+        int i0 = faces[3 * (size_t)f], i1 = faces[3 * (size_t)f + 1], i2 = faces[3 * (size_t)f + 2];
+        if ((unsigned)i0 < (unsigned)n_verts && (unsigned)i1 < (unsigned)n_verts && (unsigned)i2 < (unsigned)n_verts) {
+          v0 = make_float4(verts[3 * (size_t)i0], verts[3 * (size_t)i0 + 1], verts[3 * (size_t)i0 + 2], 0.f);
+          e1 = make_float4(__fsub_rn(verts[3 * (size_t)i1], v0.x), __fsub_rn(verts[3 * (size_t)i1 + 1], v0.y),
+                           __fsub_rn(verts[3 * (size_t)i1 + 2], v0.z), 0.f);
+          e2 = make_float4(__fsub_rn(verts[3 * (size_t)i2], v0.x), __fsub_rn(verts[3 * (size_t)i2 + 1], v0.y),
+                           __fsub_rn(verts[3 * (size_t)i2 + 2], v0.z), 0.f);
+        }
+      }
+      sv0[threadIdx.x] = v0; se1[threadIdx.x] = e1; se2[threadIdx.x] = e2;
+    }
+    __syncthreads();
+    if (active) {
+      const int lim = min(kBfTile, n_faces - base);
+      for (int k = 0; k < lim; ++k) {
+        float t;
+        if (vl_tri_hit(sv0[k], se1[k], se2[k], o, d, &t) && t < best_t) { best_t = t; best = base + k; }
+      }
+    }
+  }
+  if (!active) return;
+  if (best >= 0) {
+    int i0 = faces[3 * (size_t)best], i1 = faces[3 * (size_t)best + 1], i2 = faces[3 * (size_t)best + 2];
+    endpoints[3 * (size_t)r + 0] = __fadd_rn(o.x, __fmul_rn(d.x, best_t));
+    endpoints[3 * (size_t)r + 1] = __fadd_rn(o.y, __fmul_rn(d.y, best_t));
+    endpoints[3 * (size_t)r + 2] = __fadd_rn(o.z, __fmul_rn(d.z, best_t));
+    endcolors[3 * (size_t)r + 0] = (int)(float)colors[3 * (size_t)i0];
+    endcolors[3 * (size_t)r + 1] = (int)(float)colors[3 * (size_t)i0 + 1];
+    endcolors[3 * (size_t)r + 2] = (int)(float)colors[3 * (size_t)i0 + 2];
+    endrem[r] = __fdiv_rn(__fadd_rn(__fadd_rn(rem[i0], rem[i1]), rem[i2]), 3.0f);
+    range[r] = best_t;
+  }
+  if (tri_id) tri_id[r] = best;
+}
+
+}  // namespace
+
+int vl_trace_launch(const void* d_blob, int n_faces, const float* d_rays, const float* d_origin, int n_rays,
+                    int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
+                    int* d_tri_id, cudaStream_t stream) {
+  const int width = n_rays / height;           // RayTracer.cpp:56
+  const long long n_traced = (long long)width * height;
+  if (d_tri_id && n_rays > n_traced) {         // rays beyond width*height are never cast
+    VL_CUDA_CHECK(cudaMemsetAsync(d_tri_id + n_traced, 0xff, sizeof(int) * (size_t)(n_rays - n_traced), stream));
+  }
+  if (n_traced <= 0) return VL_OK;
+  const char* blob = static_cast<const char*>(d_blob);
+  VlBlobLayout L = vl_blob_layout(n_faces);
+  const int nb = (int)((n_traced + kTraceThreads - 1) / kTraceThreads);
+  k_trace<<<nb, kTraceThreads, 0, stream>>>(reinterpret_cast<const VlHeader*>(blob),
+                                           reinterpret_cast<const VlNode*>(blob + L.off_nodes),
+                                           reinterpret_cast<const VlTri*>(blob + L.off_tris),
+                                           reinterpret_cast<const int4*>(blob + L.off_c0), d_rays, d_origin,
+                                           (int)n_traced, d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id);
+  VL_LAUNCH_CHECK("k_trace");
+  return VL_OK;
+}
+
+int vl_trace_bruteforce_launch(const float* d_verts, const int* d_faces, const int* d_colors, const float* d_rem,
+                               int n_verts, int n_faces, const float* d_rays, const float* d_origin, int n_rays,
+                               int height, float* d_endpoints, int* d_endcolors, float* d_range,
+                               float* d_endrem, int* d_tri_id, cudaStream_t stream) {
+  const int width = n_rays / height;
+  const long long n_traced = (long long)width * height;
+  if (d_tri_id && n_rays > n_traced)
+    VL_CUDA_CHECK(cudaMemsetAsync(d_tri_id + n_traced, 0xff, sizeof(int) * (size_t)(n_rays - n_traced), stream));
+  if (n_traced <= 0) return VL_OK;
+  const int nb = (int)((n_traced + kTraceThreads - 1) / kTraceThreads);
+  k_trace_bruteforce<<<nb, kTraceThreads, 0, stream>>>(d_verts, d_faces, d_colors, d_rem, n_verts, n_faces, d_rays,
+                                                      d_origin, (int)n_traced, d_endpoints, d_endcolors, d_range,
+                                                      d_endrem, d_tri_id);
+  VL_LAUNCH_CHECK("k_trace_bruteforce");
+  return VL_OK;
+}

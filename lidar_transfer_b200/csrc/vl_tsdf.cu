@@ -1,0 +1,150 @@
+// vl_tsdf.cu -- (iv) class-aware TSDF voxel integration, sm_100a.
+//
+// Replaces the reference's pycuda `integrate` kernel (auxiliary/fusion_lidar.py:66-229, the
+// class-aware branch `merge == true`, :190-227) and its launch loop (:252-287); vl_tsdf_init
+// replaces the host-side volume construction + 4 uploads (:48-63).  The volumes never leave HBM.
+//
+// Arithmetic follows the kernel string operation by operation, including its quirks
+// (SURVEY.md A.4): float-precision voxel index decode, `dist_old` read from the WEIGHT volume,
+// no weight update on a class switch, mixed float/double constants.  The reference is JIT-compiled
+// by nvcc with default -fmad=true; this file is compiled with -fmad=false and spells out the three
+// places where that contraction happens (__fmaf_rn), so the rounding is explicit.
+// The one-element out-of-bounds access of the reference's `voxel_idx > N` guard (:92) is NOT
+// reproduced: voxel_idx == N is never touched.
+#include "vl_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+#define VL_PI 3.14159265358979323846
+
+struct TsdfParams {
+  int dx, dy, dz;
+  float ox, oy, oz;
+  float voxel_size, trunc_margin, obs_weight, fov_up_deg, fov_down_deg;
+  int im_h, im_w;
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_tsdf_init(float4* __restrict__ tsdf, float4* __restrict__ weight, float4* __restrict__ color, float4* __restrict__ rem,
+            long long n4, float* tsdf_s, float* weight_s, float* color_s, float* rem_s, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    tsdf[i] = one; weight[i] = zero; color[i] = zero; rem[i] = zero;
+  }
+  // tail (n not a multiple of 4)
+  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    tsdf_s[i] = 1.f; weight_s[i] = 0.f; color_s[i] = 0.f; rem_s[i] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_tsdf_integrate(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, float* __restrict__ color_vol,
+                 float* __restrict__ rem_vol, const TsdfParams P, const float* __restrict__ color_im,
+                 const float* __restrict__ depth_im, const float* __restrict__ rem_im, long long n_vox) {
+  const long long vi = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (vi >= n_vox) return;
+  const int voxel_idx = (int)vi;
+  const int vol_dim_y = P.dy, vol_dim_z = P.dz;
+  // :96-98 (float division: can decode (x+1, -1, z) once voxel_idx exceeds 2^24)
+  float voxel_x = floorf(((float)voxel_idx) / ((float)(vol_dim_y * vol_dim_z)));
+  float voxel_y = floorf(((float)(voxel_idx - ((int)voxel_x) * vol_dim_y * vol_dim_z)) / ((float)vol_dim_z));
+  float voxel_z = (float)(voxel_idx - ((int)voxel_x) * vol_dim_y * vol_dim_z - ((int)voxel_y) * vol_dim_z);
+  // :101-104
+  float voxel_size = P.voxel_size;
+  float pt_x = __fmaf_rn(voxel_x, voxel_size, P.ox);
+  float pt_y = __fmaf_rn(voxel_y, voxel_size, P.oy);
+  float pt_z = __fmaf_rn(voxel_z, voxel_size, P.oz);
+  float cam_pt_x = pt_x, cam_pt_z = pt_z, cam_pt_y = pt_y;
+  // :119-128
+  int im_h = P.im_h, im_w = P.im_w;
+  float fov_up = P.fov_up_deg * VL_PI / 180.0;
+  float fov_down = P.fov_down_deg * VL_PI / 180.0;
+  float fov = fabsf(fov_up) + fabsf(fov_down);
+  float depth = norm3df(cam_pt_x, cam_pt_y, cam_pt_z);
+  float yaw = -atan2f(cam_pt_y, cam_pt_x);
+  float pitch = asinf(cam_pt_z / depth);
+  if (pitch > fov_up || pitch < fov_down) return;  // :131-132
+  float proj_x = 0.5 * (yaw / VL_PI + 1.0);        // :134-137
+  float proj_y = 1.0 - (pitch + fabsf(fov_down)) / fov;
+  proj_x *= im_w;
+  proj_y *= im_h;
+  int proj_x_cl = (int)floorf(proj_x);             // :139-144
+  proj_x_cl = min(im_w - 1, proj_x_cl);
+  proj_x_cl = max(0, proj_x_cl);
+  int proj_y_cl = (int)floorf(proj_y);
+  proj_y_cl = min(im_h - 1, proj_y_cl);
+  proj_y_cl = max(0, proj_y_cl);
+  int pixel_x = proj_x_cl, pixel_y = proj_y_cl;
+  float depth_value = __ldg(depth_im + pixel_y * im_w + pixel_x);  // :154-156
+  if (depth_value == 0) return;
+  // :190-227 class-aware integration
+  float trunc_margin = P.trunc_margin;
+  float depth_diff = depth_value - depth;
+  if (depth_diff < -trunc_margin) return;
+  float dist = fminf(1.0f, depth_diff / trunc_margin);
+  float dist_old = weight_vol[voxel_idx];  // sic (:197)
+  float old_color = color_vol[voxel_idx];
+  float new_color = __ldg(color_im + pixel_y * im_w + pixel_x);
+  if (old_color == new_color) {
+    float w_old = dist_old;
+    float w_new = w_old + P.obs_weight;
+    weight_vol[voxel_idx] = w_new;
+    tsdf_vol[voxel_idx] = __fmaf_rn(tsdf_vol[voxel_idx], w_old, dist) / w_new;
+    float old_rem = rem_vol[voxel_idx];
+    float new_rem = __ldg(rem_im + pixel_y * im_w + pixel_x);
+    rem_vol[voxel_idx] = __fmaf_rn(old_rem, w_old, new_rem) / w_new;
+  } else if (dist < dist_old) {
+    tsdf_vol[voxel_idx] = dist;
+    float new_b = floorf(new_color / (256 * 256));
+    float new_g = floorf((new_color - new_b * 256 * 256) / 256);
+    float new_r = new_color - new_b * 256 * 256 - new_g * 256;
+    color_vol[voxel_idx] = new_b * 256 * 256 + new_g * 256 + new_r;
+    rem_vol[voxel_idx] = __ldg(rem_im + pixel_y * im_w + pixel_x);
+  }
+}
+
+}  // namespace
+
+extern "C" int vl_tsdf_init(float* d_tsdf, float* d_weight, float* d_color, float* d_rem, long long n_voxels,
+                            vl_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_voxels < 0 || !d_tsdf || !d_weight || !d_color || !d_rem) {
+    vl_set_error("vl_tsdf_init: invalid argument");
+    return VL_EINVAL;
+  }
+  if (n_voxels == 0) return VL_OK;
+  const bool aligned = ((((uintptr_t)d_tsdf) | ((uintptr_t)d_weight) | ((uintptr_t)d_color) | ((uintptr_t)d_rem)) & 15) == 0;
+  const long long n4 = aligned ? n_voxels / 4 : 0;
+  long long want = (n_voxels / 4 + kThreads - 1) / kThreads;
+  int nb = (int)(want < 1 ? 1 : (want > 148LL * 16 ? 148LL * 16 : want));
+  k_tsdf_init<<<nb, kThreads, 0, stream>>>(reinterpret_cast<float4*>(d_tsdf), reinterpret_cast<float4*>(d_weight),
+                                          reinterpret_cast<float4*>(d_color), reinterpret_cast<float4*>(d_rem), n4,
+                                          d_tsdf, d_weight, d_color, d_rem, n_voxels);
+  VL_LAUNCH_CHECK("k_tsdf_init");
+  return VL_OK;
+}
+
+extern "C" int vl_tsdf_integrate(float* d_tsdf, float* d_weight, float* d_color, float* d_rem, int dx, int dy, int dz,
+                                 const float vol_origin[3], float voxel_size, float trunc_margin, float obs_weight,
+                                 float fov_up_deg, float fov_down_deg, const float* d_color_im, const float* d_depth_im,
+                                 const float* d_rem_im, int im_h, int im_w, vl_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long n_vox = (long long)dx * dy * dz;
+  if (dx <= 0 || dy <= 0 || dz <= 0 || n_vox > 0x7fffffffLL || im_h <= 0 || im_w <= 0 || !vol_origin || !d_tsdf ||
+      !d_weight || !d_color || !d_rem || !d_color_im || !d_depth_im || !d_rem_im) {
+    vl_set_error("vl_tsdf_integrate: invalid argument (dims %d x %d x %d, image %d x %d)", dx, dy, dz, im_h, im_w);
+    return VL_EINVAL;
+  }
+  TsdfParams P;
+  P.dx = dx; P.dy = dy; P.dz = dz;
+  P.ox = vol_origin[0]; P.oy = vol_origin[1]; P.oz = vol_origin[2];
+  P.voxel_size = voxel_size; P.trunc_margin = trunc_margin; P.obs_weight = obs_weight;
+  P.fov_up_deg = fov_up_deg; P.fov_down_deg = fov_down_deg;
+  P.im_h = im_h; P.im_w = im_w;
+  const unsigned int nb = (unsigned int)((n_vox + kThreads - 1) / kThreads);
+  k_tsdf_integrate<<<nb, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, d_color_im, d_depth_im, d_rem_im, n_vox);
+  VL_LAUNCH_CHECK("k_tsdf_integrate");
+  return VL_OK;
+}

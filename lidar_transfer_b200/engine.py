@@ -1,0 +1,248 @@
+"""Host side of the hot path: PyTorch tensors for device memory and streams, libvlidar for the work.
+
+Everything here runs on the current CUDA device and the current torch stream; nothing
+synchronises unless stated.  PyTorch is plumbing only -- no torch op computes any result.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _stream():
+  return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+  return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _dev(x, dtype, device=None):
+  """numpy / torch (any device) -> contiguous CUDA tensor of dtype."""
+  if isinstance(x, np.ndarray):
+    x = torch.from_numpy(np.ascontiguousarray(x))
+  elif not torch.is_tensor(x):
+    x = torch.as_tensor(x)
+  if device is None:
+    device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+  return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+
+
+def require_cuda():
+  if not torch.cuda.is_available():
+    raise RuntimeError("lidar_transfer_b200 needs a CUDA device: the hot path has no CPU fallback")
+  lib()
+
+
+class Bvh:
+  """(i) LBVH over an indexed triangle mesh, held in one device blob.
+
+  Replaces Triangle construction + `BVH bvh(&objects)`, auxiliary/raytracer/RayTracer.cpp:32-54.
+  verts f32[N_v,3], faces i32[N_t,3], colors i32[N_v,3], rem f32[N_v] -- the arrays
+  TSDFVolume.throw_rays_at_mesh flattens for C_Trace (auxiliary/fusion_lidar.py:434-438).
+  `blob` may be passed to reuse a previous allocation (no allocation in steady state).
+  """
+
+  def __init__(self, verts, faces, colors, rem, blob=None):
+    require_cuda()
+    self.verts = _dev(verts, torch.float32).reshape(-1)
+    dev = self.verts.device
+    self.faces = _dev(faces, torch.int32, dev).reshape(-1)
+    self.colors = _dev(colors, torch.int32, dev).reshape(-1)
+    self.rem = _dev(rem, torch.float32, dev).reshape(-1)
+    self.n_verts = self.verts.numel() // 3
+    self.n_faces = self.faces.numel() // 3
+    if self.colors.numel() != 3 * self.n_verts or self.rem.numel() != self.n_verts:
+      raise ValueError("colors must hold 3 ints and rem 1 float per vertex")
+    need = lib().vl_bvh_blob_bytes(self.n_faces)
+    if blob is None or blob.numel() < need or blob.device != dev:
+      blob = torch.empty(need, dtype=torch.uint8, device=dev)
+    self.blob = blob
+    with torch.cuda.device(dev):
+      check(lib().vl_bvh_build(_ptr(self.verts), _ptr(self.faces), _ptr(self.colors), _ptr(self.rem),
+                               self.n_verts, self.n_faces, _ptr(self.blob), self.blob.numel(), _stream()))
+
+  def status(self):
+    """Synchronises; raises VlidarError(VL_EBADMESH) on out-of-range face indices.
+    Returns dict(n_tris, root_ref, n_bad_faces, max_climb)."""
+    info = (ctypes.c_int * 8)()
+    with torch.cuda.device(self.blob.device):
+      rc = lib().vl_bvh_status(_ptr(self.blob), self.n_faces, _stream(), info)
+    out = dict(n_tris=info[0], root_ref=info[1], n_bad_faces=info[2], max_climb=info[3])
+    check(rc)
+    return out
+
+
+def _trace_outputs(n_rays, dev, out, want_ids):
+  if out is None:
+    out = {}
+  spec = (("endpoints", 3 * n_rays, torch.float32), ("endcolors", 3 * n_rays, torch.int32),
+          ("range", n_rays, torch.float32), ("endrem", n_rays, torch.float32))
+  for name, n, dt in spec:
+    if name not in out:
+      out[name] = torch.zeros(n, dtype=dt, device=dev)  # misses stay 0 (fusion_lidar.py:440-447)
+    t = out[name]
+    if t.dtype != dt or t.numel() != n or not t.is_contiguous() or t.device != dev:
+      raise ValueError("output %s must be a contiguous %s tensor of %d elements on %s" % (name, dt, n, dev))
+  if want_ids and "tri_id" not in out:
+    out["tri_id"] = torch.empty(n_rays, dtype=torch.int32, device=dev)
+  return out
+
+
+def trace(bvh, rays, origin, height, out=None, want_ids=True):
+  """(ii) closest-hit ray cast; the device-resident equivalent of C_Trace
+  (auxiliary/raytracer/RayTracerCython.pyx:15-33 -> RayTracer.cpp:56-92).
+
+  rays f32[R,3] (any length, normalised on device), origin f32[3].  Returns dict of flat CUDA
+  tensors: endpoints[3R], endcolors[3R], range[R], endrem[R] (written for hits only -- pass
+  `out` to keep previous content) and tri_id[R] (original face index, -1 = miss)."""
+  dev = bvh.blob.device
+  rays = _dev(rays, torch.float32, dev).reshape(-1)
+  origin = _dev(origin, torch.float32, dev).reshape(-1)
+  n_rays = rays.numel() // 3
+  out = _trace_outputs(n_rays, dev, out, want_ids)
+  with torch.cuda.device(dev):
+    check(lib().vl_trace(_ptr(bvh.blob), bvh.n_faces, _ptr(rays), _ptr(origin), n_rays, int(height),
+                         _ptr(out["endpoints"]), _ptr(out["endcolors"]), _ptr(out["range"]), _ptr(out["endrem"]),
+                         _ptr(out.get("tri_id")), _stream()))
+  return out
+
+
+def trace_bruteforce(verts, faces, colors, rem, rays, origin, height, out=None):
+  """Test aid: same outputs without a BVH (every triangle per ray)."""
+  require_cuda()
+  verts = _dev(verts, torch.float32).reshape(-1)
+  dev = verts.device
+  faces = _dev(faces, torch.int32, dev).reshape(-1)
+  colors = _dev(colors, torch.int32, dev).reshape(-1)
+  rem = _dev(rem, torch.float32, dev).reshape(-1)
+  rays = _dev(rays, torch.float32, dev).reshape(-1)
+  origin = _dev(origin, torch.float32, dev).reshape(-1)
+  n_rays = rays.numel() // 3
+  out = _trace_outputs(n_rays, dev, out, True)
+  with torch.cuda.device(dev):
+    check(lib().vl_trace_bruteforce(_ptr(verts), _ptr(faces), _ptr(colors), _ptr(rem), verts.numel() // 3,
+                                    faces.numel() // 3, _ptr(rays), _ptr(origin), n_rays, int(height),
+                                    _ptr(out["endpoints"]), _ptr(out["endcolors"]), _ptr(out["range"]),
+                                    _ptr(out["endrem"]), _ptr(out["tri_id"]), _stream()))
+  return out
+
+
+def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, workspace=None):
+  """(iii) spherical range-image projection, the device equivalent of
+  LaserScan.do_range_projection_new('depth') + do_label_projection_new
+  (auxiliary/laserscan.py:294-391, 672-676).
+
+  points f64[N,3], remissions f32[N], labels u32/i32[N].  Returns dict of CUDA tensors:
+  range_image f32[H,W] (0 empty), index i32[H,W] (-1 empty, into the kept points),
+  proj_label i32[H,W], proj_remissions f32[H,W] (-1 empty), keep bool[N], n_kept i32[1]."""
+  require_cuda()
+  points = _dev(points, torch.float64).reshape(-1)
+  dev = points.device
+  n = points.numel() // 3
+  remissions = _dev(remissions, torch.float32, dev).reshape(-1)
+  if torch.is_tensor(labels) and labels.dtype in (torch.int32, torch.uint32):
+    labels = labels.to(dev).contiguous().view(torch.int32)
+  else:
+    labels = _dev(np.asarray(labels.cpu() if torch.is_tensor(labels) else labels).astype(np.uint32).view(np.int32),
+                  torch.int32, dev)
+  labels = labels.reshape(-1)
+  if remissions.numel() != n or labels.numel() != n:
+    raise ValueError("points, remissions and labels disagree in length")
+  need = lib().vl_project_workspace_bytes(n, H, W)
+  if workspace is None or workspace.numel() < need:
+    workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+  out = dict(range_image=torch.empty((H, W), dtype=torch.float32, device=dev),
+             index=torch.empty((H, W), dtype=torch.int32, device=dev),
+             proj_label=torch.empty((H, W), dtype=torch.int32, device=dev),
+             proj_remissions=torch.empty((H, W), dtype=torch.float32, device=dev),
+             keep=torch.empty(max(n, 1), dtype=torch.uint8, device=dev),
+             n_kept=torch.zeros(1, dtype=torch.int32, device=dev))
+  with torch.cuda.device(dev):
+    check(lib().vl_project(_ptr(points), _ptr(remissions), _ptr(labels), n, float(fov_up), float(fov_down), H, W,
+                           1 if remove else 0, _ptr(out["range_image"]), _ptr(out["index"]), _ptr(out["proj_label"]),
+                           _ptr(out["proj_remissions"]), _ptr(out["keep"]), _ptr(out["n_kept"]), _ptr(workspace),
+                           workspace.numel(), _stream()))
+  out["keep"] = out["keep"][:n].bool()
+  out["workspace"] = workspace
+  return out
+
+
+class TsdfDevice:
+  """(iv) the four TSDF volumes resident in HBM + the integrate kernel.
+
+  Device-side core of auxiliary.fusion_lidar.TSDFVolume (auxiliary/fusion_lidar.py:23-63,
+  252-287); the reference-shaped class lives in lidar_transfer_b200/auxiliary/fusion_lidar.py."""
+
+  def __init__(self, vol_dim, vol_origin, voxel_size, fov_up, fov_down, device=None):
+    require_cuda()
+    self.dim = tuple(int(v) for v in vol_dim)
+    self.origin = np.asarray(vol_origin, np.float32).copy()
+    self.voxel_size = float(np.float32(voxel_size))
+    self.trunc_margin = float(np.float32(voxel_size * 5))  # fusion_lidar.py:31, cast at :277-280
+    self.fov_up = float(np.float32(fov_up))
+    self.fov_down = float(np.float32(fov_down))
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    n = self.dim[0] * self.dim[1] * self.dim[2]
+    if n >= 2 ** 31:
+      raise ValueError("volume of %d voxels exceeds the reference kernel's int voxel index" % n)
+    self.tsdf = torch.empty(self.dim, dtype=torch.float32, device=dev)
+    self.weight = torch.empty(self.dim, dtype=torch.float32, device=dev)
+    self.color = torch.empty(self.dim, dtype=torch.float32, device=dev)
+    self.rem = torch.empty(self.dim, dtype=torch.float32, device=dev)
+    self.reset()
+
+  def reset(self):
+    n = self.dim[0] * self.dim[1] * self.dim[2]
+    with torch.cuda.device(self.tsdf.device):
+      check(lib().vl_tsdf_init(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color), _ptr(self.rem), n, _stream()))
+
+  def integrate(self, color_im, depth_im, rem_im, obs_weight=1.0):
+    """color_im: folded single-channel image (label * 65536), depth_im, rem_im: f32[H,W]."""
+    dev = self.tsdf.device
+    color_im = _dev(color_im, torch.float32, dev)
+    depth_im = _dev(depth_im, torch.float32, dev)
+    rem_im = _dev(rem_im, torch.float32, dev)
+    im_h, im_w = depth_im.shape
+    origin = (ctypes.c_float * 3)(*[float(v) for v in self.origin])
+    with torch.cuda.device(dev):
+      check(lib().vl_tsdf_integrate(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color), _ptr(self.rem),
+                                    self.dim[0], self.dim[1], self.dim[2], origin, self.voxel_size,
+                                    self.trunc_margin, float(np.float32(obs_weight)), self.fov_up, self.fov_down,
+                                    _ptr(color_im), _ptr(depth_im), _ptr(rem_im), int(im_h), int(im_w), _stream()))
+
+
+def ctrace_host(rays, origin, verts, faces, colors, rem, height, outputs=None, want_ids=False):
+  """The reference-compatible HOST-pointer entry point (extern "C" ctrace / vl_ctrace_ids) on numpy
+  buffers: H2D, build, trace, D2H inside the call.  outputs: dict of preallocated numpy arrays
+  (endpoints, endcolors, range, endrem) updated in place for hits."""
+  require_cuda()
+  f32, i32 = np.float32, np.int32
+
+  def chk(a, dt, name):
+    if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags["C_CONTIGUOUS"]):
+      raise ValueError("%s must be a C-contiguous numpy array of %s" % (name, np.dtype(dt).name))
+    return a
+
+  rays = chk(rays, f32, "rays").reshape(-1)
+  origin = chk(origin, f32, "origin").reshape(-1)
+  verts = chk(verts, f32, "verts").reshape(-1)
+  faces = chk(faces, i32, "faces").reshape(-1)
+  colors = chk(colors, i32, "colors").reshape(-1)
+  rem = chk(rem, f32, "rem").reshape(-1)
+  n_rays = rays.size // 3
+  if outputs is None:
+    outputs = dict(endpoints=np.zeros(3 * n_rays, f32), endcolors=np.zeros(3 * n_rays, i32),
+                   range=np.zeros(n_rays, f32), endrem=np.zeros(n_rays, f32))
+  tri_id = np.empty(n_rays, i32) if want_ids else None
+  p = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
+  check(lib().vl_ctrace_ids(p(rays), p(origin), p(verts), p(faces), p(colors), p(rem), n_rays, verts.size // 3,
+                            faces.size // 3, int(height), p(chk(outputs["endpoints"], f32, "endpoints")),
+                            p(chk(outputs["endcolors"], i32, "endcolors")), p(chk(outputs["range"], f32, "range")),
+                            p(chk(outputs["endrem"], f32, "endrem")), p(tri_id)))
+  if want_ids:
+    outputs["tri_id"] = tri_id
+  return outputs
