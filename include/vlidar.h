@@ -90,10 +90,13 @@ int vl_bvh_status(const void* d_blob, int n_faces, vl_stream stream, int* info);
  * d_rays float32[3*n_rays] (not normalised), d_origin float32[3] on the device.
  * Outputs as in ctrace (hits only) except d_tri_id (nullable): written for every ray,
  * original face index or -1.  Exact-t ties go to the smaller face index.
+ * flags: VL_TRACE_ZERO_MISSES writes 0 to all four outputs of a missing ray (what the
+ * reference caller obtains by zero-filling first, auxiliary/fusion_lidar.py:440-447).
  * ---------------------------------------------------------------------------------- */
+#define VL_TRACE_ZERO_MISSES 1
 int vl_trace(const void* d_blob, int n_faces, const float* d_rays, const float* d_origin,
              int n_rays, int height, float* d_endpoints, int* d_endcolors, float* d_range,
-             float* d_endrem, int* d_tri_id, vl_stream stream);
+             float* d_endrem, int* d_tri_id, int flags, vl_stream stream);
 
 /* Test aid: same outputs by testing every triangle per ray (no BVH). */
 int vl_trace_bruteforce(const float* d_verts, const int* d_faces, const int* d_colors,
@@ -136,6 +139,18 @@ int vl_tsdf_integrate(float* d_tsdf, float* d_weight, float* d_color, float* d_r
                       float trunc_margin, float obs_weight, float fov_up_deg, float fov_down_deg,
                       const float* d_color_im, const float* d_depth_im, const float* d_rem_im,
                       int im_h, int im_w, vl_stream stream);
+
+/* ------------------------------------------------------------------------------------
+ * measurement aids (no reference counterpart): a process-wide count of kernels launched by
+ * this library, and optional per-stage device timing with CUDA events recorded on the
+ * launching stream.  vl_profile_collect synchronises the device and ACCUMULATES into
+ * stage_ms[] / stage_launches[] (vl_profile_stage_count() entries each).
+ * ---------------------------------------------------------------------------------- */
+long long   vl_launch_count(void);
+int         vl_profile_enable(int on);          /* returns the previous setting */
+int         vl_profile_stage_count(void);
+const char* vl_profile_stage_name(int stage);
+int         vl_profile_collect(double* stage_ms, long long* stage_launches);
 
 #ifdef __cplusplus
 }

@@ -32,12 +32,17 @@ SIGNATURES = {
     "vl_bvh_blob_bytes": (_sz, [_i]),
     "vl_bvh_build": (_i, [_vp] * 4 + [_i, _i, _vp, _sz, _vp]),
     "vl_bvh_status": (_i, [_vp, _i, _vp, _vp]),
-    "vl_trace": (_i, [_vp, _i, _vp, _vp, _i, _i] + [_vp] * 6),
+    "vl_trace": (_i, [_vp, _i, _vp, _vp, _i, _i] + [_vp] * 5 + [_i, _vp]),
     "vl_trace_bruteforce": (_i, [_vp] * 4 + [_i, _i, _vp, _vp, _i, _i] + [_vp] * 6),
     "vl_project_workspace_bytes": (_sz, [_l, _i, _i]),
     "vl_project": (_i, [_vp, _vp, _vp, _l, _d, _d, _i, _i, _i] + [_vp] * 7 + [_sz, _vp]),
     "vl_tsdf_init": (_i, [_vp] * 4 + [_ll, _vp]),
     "vl_tsdf_integrate": (_i, [_vp] * 4 + [_i, _i, _i, _vp] + [_f] * 5 + [_vp] * 3 + [_i, _i, _vp]),
+    "vl_launch_count": (_ll, []),
+    "vl_profile_enable": (_i, [_i]),
+    "vl_profile_stage_count": (_i, []),
+    "vl_profile_stage_name": (_c.c_char_p, [_i]),
+    "vl_profile_collect": (_i, [_vp, _vp]),
 }
 
 _lib = None

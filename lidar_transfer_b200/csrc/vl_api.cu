@@ -22,6 +22,70 @@ void vl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---------------------------------------------------------------------------
+// launch counter + optional per-stage event timing
+// ---------------------------------------------------------------------------
+#include <atomic>
+#include <vector>
+namespace {
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_prof_on{0};
+struct ProfRec { int stage; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+thread_local cudaEvent_t g_prof_open[VL_ST_COUNT];
+const char* kStageNames[VL_ST_COUNT] = {"bounds", "morton", "sort_hist", "sort_scan", "sort_scatter", "emit_climb",
+                                        "trace", "project_scatter", "project_gather", "tsdf_init", "tsdf_integrate",
+                                        "mesh_count", "mesh_scan", "mesh_emit"};
+cudaEvent_t prof_event() {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+void vl_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void vl_prof_begin(int stage, cudaStream_t stream) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, stream);
+  g_prof_open[stage] = e;
+}
+void vl_prof_end(int stage, cudaStream_t stream) {
+  if (!g_prof_on.load(std::memory_order_relaxed) || !g_prof_open[stage]) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, stream);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof_recs.push_back({stage, g_prof_open[stage], e});
+  g_prof_open[stage] = nullptr;
+}
+
+extern "C" long long vl_launch_count(void) { return g_launches.load(); }
+extern "C" int vl_profile_enable(int on) { return g_prof_on.exchange(on ? 1 : 0); }
+extern "C" int vl_profile_stage_count(void) { return VL_ST_COUNT; }
+extern "C" const char* vl_profile_stage_name(int stage) { return (stage >= 0 && stage < VL_ST_COUNT) ? kStageNames[stage] : ""; }
+// Waits for the device, then adds every finished record to stage_ms / stage_launches (arrays of
+// vl_profile_stage_count() entries, accumulated into, not cleared) and forgets the records.
+extern "C" int vl_profile_collect(double* stage_ms, long long* stage_launches) {
+  VL_CUDA_CHECK(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for (const ProfRec& r : g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      if (stage_ms) stage_ms[r.stage] += ms;
+      if (stage_launches) stage_launches[r.stage] += 1;
+    }
+    g_prof_pool.push_back(r.a);
+    g_prof_pool.push_back(r.b);
+  }
+  g_prof_recs.clear();
+  return VL_OK;
+}
+
 extern "C" int vl_abi_version(void) { return VL_ABI_VERSION; }
 extern "C" const char* vl_last_error(void) { return g_err; }
 extern "C" int vl_ctrace_status(void) { return g_ctrace_status; }
@@ -76,12 +140,12 @@ static int check_trace_args(const char* who, const float* d_rays, const float* d
 
 extern "C" int vl_trace(const void* d_blob, int n_faces, const float* d_rays, const float* d_origin, int n_rays,
                         int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
-                        int* d_tri_id, vl_stream stream) {
+                        int* d_tri_id, int flags, vl_stream stream) {
   int rc = check_trace_args("vl_trace", d_rays, d_origin, n_rays, height, d_endpoints, d_endcolors, d_range, d_endrem);
   if (rc) return rc;
   if (!d_blob || n_faces < 0) { vl_set_error("vl_trace: invalid BVH blob"); return VL_EINVAL; }
   return vl_trace_launch(d_blob, n_faces, d_rays, d_origin, n_rays, height, d_endpoints, d_endcolors, d_range,
-                         d_endrem, d_tri_id, static_cast<cudaStream_t>(stream));
+                         d_endrem, d_tri_id, flags, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vl_trace_bruteforce(const float* d_verts, const int* d_faces, const int* d_colors, const float* d_rem,
@@ -166,7 +230,7 @@ extern "C" int vl_ctrace_ids(const float* rays, const float* origin, const float
   VL_CUDA_CHECK(cudaMemcpyAsync(A + o_erem, endrem, 4 * nr, cudaMemcpyHostToDevice, s));
   rc = vl_trace_launch(A + o_blob, n_faces, (const float*)(A + o_rays), (const float*)(A + o_origin), n_rays, height,
                        (float*)(A + o_ep), (int*)(A + o_ec), (float*)(A + o_range), (float*)(A + o_erem),
-                       tri_id ? (int*)(A + o_id) : nullptr, s);
+                       tri_id ? (int*)(A + o_id) : nullptr, 0, s);
   if (rc) return rc;
   VL_CUDA_CHECK(cudaMemcpyAsync(endpoints, A + o_ep, 12 * nr, cudaMemcpyDeviceToHost, s));
   VL_CUDA_CHECK(cudaMemcpyAsync(endcolors, A + o_ec, 12 * nr, cudaMemcpyDeviceToHost, s));

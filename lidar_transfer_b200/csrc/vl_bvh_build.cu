@@ -346,10 +346,12 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
   int nb_verts = (n_verts + kThreads - 1) / kThreads;
   if (nb_verts > 148 * 8) nb_verts = 148 * 8;
   if (nb_verts < 1) nb_verts = 1;
-  k_bounds<<<nb_verts, kThreads, 0, stream>>>(d_verts, n_verts, hdr);
+  { VlProfScope ps(VL_ST_BOUNDS, stream);
+  k_bounds<<<nb_verts, kThreads, 0, stream>>>(d_verts, n_verts, hdr); }
   VL_LAUNCH_CHECK("k_bounds");
   const int nb_faces = (n_faces + kThreads - 1) / kThreads;
-  k_morton<<<nb_faces, kThreads, 0, stream>>>(d_verts, d_faces, n_verts, n_faces, hdr, keys0, flags);
+  { VlProfScope ps(VL_ST_MORTON, stream);
+  k_morton<<<nb_faces, kThreads, 0, stream>>>(d_verts, d_faces, n_verts, n_faces, hdr, keys0, flags); }
   VL_LAUNCH_CHECK("k_morton");
 
   const int nt = L.n_sort_tiles;
@@ -359,11 +361,14 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
   unsigned int* vout = vals1;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 8 * pass;
-    k_sort_hist<<<nt, kThreads, 0, stream>>>(kin, n_faces, shift, hist, nt);
+    { VlProfScope ps(VL_ST_SORT_HIST, stream);
+    k_sort_hist<<<nt, kThreads, 0, stream>>>(kin, n_faces, shift, hist, nt); }
     VL_LAUNCH_CHECK("k_sort_hist");
-    k_sort_scan<<<1, 1024, 0, stream>>>(hist, 256 * nt);
+    { VlProfScope ps(VL_ST_SORT_SCAN, stream);
+    k_sort_scan<<<1, 1024, 0, stream>>>(hist, 256 * nt); }
     VL_LAUNCH_CHECK("k_sort_scan");
-    k_sort_scatter<<<nt, kThreads, 0, stream>>>(kin, vin, kout, vout, n_faces, shift, hist, nt);
+    { VlProfScope ps(VL_ST_SORT_SCATTER, stream);
+    k_sort_scatter<<<nt, kThreads, 0, stream>>>(kin, vin, kout, vout, n_faces, shift, hist, nt); }
     VL_LAUNCH_CHECK("k_sort_scatter");
     kin = kout;
     vin = vout;
@@ -371,6 +376,7 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
     vout = (vout == vals1) ? vals0 : vals1;
   }
   // after 4 passes the sorted (key, face id) pairs are back in keys0 / vals0
+  VlProfScope ps_emit(VL_ST_EMIT_CLIMB, stream);
   k_emit_climb<<<nb_faces, kThreads, 0, stream>>>(d_verts, d_faces, d_colors, d_rem, n_verts, n_faces, keys0, vals0, hdr,
                                                  reinterpret_cast<VlNode*>(blob + L.off_nodes),
                                                  reinterpret_cast<VlTri*>(blob + L.off_tris),

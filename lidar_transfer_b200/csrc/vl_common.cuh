@@ -9,6 +9,24 @@
 // error plumbing (thread-local text behind vl_last_error())
 // ---------------------------------------------------------------------------
 void vl_set_error(const char* fmt, ...);
+void vl_count_launch();
+
+// ---------------------------------------------------------------------------
+// optional per-stage device timing (CUDA events on the launching stream), off by default.
+// bench.py switches it on to obtain the per-kernel durations behind the roofline figures.
+// ---------------------------------------------------------------------------
+enum VlStage {
+  VL_ST_BOUNDS = 0, VL_ST_MORTON, VL_ST_SORT_HIST, VL_ST_SORT_SCAN, VL_ST_SORT_SCATTER, VL_ST_EMIT_CLIMB,
+  VL_ST_TRACE, VL_ST_PROJECT_SCATTER, VL_ST_PROJECT_GATHER, VL_ST_TSDF_INIT, VL_ST_TSDF_INTEGRATE,
+  VL_ST_MESH_COUNT, VL_ST_MESH_SCAN, VL_ST_MESH_EMIT, VL_ST_COUNT
+};
+void vl_prof_begin(int stage, cudaStream_t stream);
+void vl_prof_end(int stage, cudaStream_t stream);
+struct VlProfScope {
+  int stage; cudaStream_t stream;
+  VlProfScope(int st, cudaStream_t s) : stage(st), stream(s) { vl_prof_begin(st, s); }
+  ~VlProfScope() { vl_prof_end(stage, stream); }
+};
 
 #define VL_CUDA_CHECK(expr)                                                           \
   do {                                                                                \
@@ -22,6 +40,7 @@ void vl_set_error(const char* fmt, ...);
 
 #define VL_LAUNCH_CHECK(name)                                                         \
   do {                                                                                \
+    vl_count_launch();                                                                \
     cudaError_t _e = cudaGetLastError();                                              \
     if (_e != cudaSuccess) {                                                          \
       vl_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));          \
@@ -160,7 +179,7 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
                         int n_verts, int n_faces, void* d_blob, cudaStream_t stream);
 int vl_trace_launch(const void* d_blob, int n_faces, const float* d_rays, const float* d_origin, int n_rays,
                     int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
-                    int* d_tri_id, cudaStream_t stream);
+                    int* d_tri_id, int flags, cudaStream_t stream);
 int vl_trace_bruteforce_launch(const float* d_verts, const int* d_faces, const int* d_colors, const float* d_rem,
                                int n_verts, int n_faces, const float* d_rays, const float* d_origin, int n_rays,
                                int height, float* d_endpoints, int* d_endcolors, float* d_range,

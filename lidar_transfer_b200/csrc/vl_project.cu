@@ -162,12 +162,14 @@ extern "C" int vl_project(const double* d_points, const float* d_remissions, con
   VL_CUDA_CHECK(cudaMemsetAsync(keys, 0xff, 8 * (size_t)H * W, stream));
   if (n_points > 0) {
     const int nb = (int)((n_points + kThreads - 1) / kThreads);
+    VlProfScope ps(VL_ST_PROJECT_SCATTER, stream);
     k_project_scatter<<<nb, kThreads, 0, stream>>>(d_points, n_points, P, keys, masks, counts, d_keep);
     VL_LAUNCH_CHECK("k_project_scatter");
   }
   k_scan_counts<<<1, 1024, 0, stream>>>(counts, (long)nw, d_n_kept);
   VL_LAUNCH_CHECK("k_scan_counts");
   const int n_pix = H * W;
+  VlProfScope ps(VL_ST_PROJECT_GATHER, stream);
   k_project_gather<<<(n_pix + kThreads - 1) / kThreads, kThreads, 0, stream>>>(keys, masks, counts, d_remissions, d_labels,
                                                                              n_pix, d_range, d_index, d_label, d_rem);
   VL_LAUNCH_CHECK("k_project_gather");

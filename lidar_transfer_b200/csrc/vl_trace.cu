@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kTraceThreads)
 k_trace(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ nodes, const VlTri* __restrict__ tris,
         const int4* __restrict__ c0, const float* __restrict__ rays, const float* __restrict__ origin, int n_traced,
         float* __restrict__ endpoints, int* __restrict__ endcolors, float* __restrict__ range,
-        float* __restrict__ endrem, int* __restrict__ tri_id) {
+        float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses) {
   __shared__ uint2 sstack[kSmemStack][kTraceThreads];
   const int r = blockIdx.x * kTraceThreads + threadIdx.x;
   if (r >= n_traced) return;
@@ -138,6 +138,11 @@ k_trace(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ nodes, cons
     endcolors[3 * (size_t)r + 2] = col.z;
     endrem[r] = best.rem;
     range[r] = best.t;
+  } else if (zero_misses) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { endpoints[3 * (size_t)r + k] = 0.f; endcolors[3 * (size_t)r + k] = 0; }
+    endrem[r] = 0.f;
+    range[r] = 0.f;
   }
   if (tri_id) tri_id[r] = best.pos >= 0 ? best.orig : -1;
 }
@@ -206,7 +211,7 @@ k_trace_bruteforce(const float* __restrict__ verts, const int* __restrict__ face
 
 int vl_trace_launch(const void* d_blob, int n_faces, const float* d_rays, const float* d_origin, int n_rays,
                     int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
-                    int* d_tri_id, cudaStream_t stream) {
+                    int* d_tri_id, int flags, cudaStream_t stream) {
   const int width = n_rays / height;           // RayTracer.cpp:56
   const long long n_traced = (long long)width * height;
   if (d_tri_id && n_rays > n_traced) {         // rays beyond width*height are never cast
@@ -216,11 +221,12 @@ int vl_trace_launch(const void* d_blob, int n_faces, const float* d_rays, const 
   const char* blob = static_cast<const char*>(d_blob);
   VlBlobLayout L = vl_blob_layout(n_faces);
   const int nb = (int)((n_traced + kTraceThreads - 1) / kTraceThreads);
+  VlProfScope ps(VL_ST_TRACE, stream);
   k_trace<<<nb, kTraceThreads, 0, stream>>>(reinterpret_cast<const VlHeader*>(blob),
                                            reinterpret_cast<const VlNode*>(blob + L.off_nodes),
                                            reinterpret_cast<const VlTri*>(blob + L.off_tris),
                                            reinterpret_cast<const int4*>(blob + L.off_c0), d_rays, d_origin,
-                                           (int)n_traced, d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id);
+                                           (int)n_traced, d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, (flags & VL_TRACE_ZERO_MISSES) != 0);
   VL_LAUNCH_CHECK("k_trace");
   return VL_OK;
 }

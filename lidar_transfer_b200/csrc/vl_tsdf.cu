@@ -119,6 +119,7 @@ extern "C" int vl_tsdf_init(float* d_tsdf, float* d_weight, float* d_color, floa
   const long long n4 = aligned ? n_voxels / 4 : 0;
   long long want = (n_voxels / 4 + kThreads - 1) / kThreads;
   int nb = (int)(want < 1 ? 1 : (want > 148LL * 16 ? 148LL * 16 : want));
+  VlProfScope ps(VL_ST_TSDF_INIT, stream);
   k_tsdf_init<<<nb, kThreads, 0, stream>>>(reinterpret_cast<float4*>(d_tsdf), reinterpret_cast<float4*>(d_weight),
                                           reinterpret_cast<float4*>(d_color), reinterpret_cast<float4*>(d_rem), n4,
                                           d_tsdf, d_weight, d_color, d_rem, n_voxels);
@@ -144,6 +145,7 @@ extern "C" int vl_tsdf_integrate(float* d_tsdf, float* d_weight, float* d_color,
   P.fov_up_deg = fov_up_deg; P.fov_down_deg = fov_down_deg;
   P.im_h = im_h; P.im_w = im_w;
   const unsigned int nb = (unsigned int)((n_vox + kThreads - 1) / kThreads);
+  VlProfScope ps(VL_ST_TSDF_INTEGRATE, stream);
   k_tsdf_integrate<<<nb, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, d_color_im, d_depth_im, d_rem_im, n_vox);
   VL_LAUNCH_CHECK("k_tsdf_integrate");
   return VL_OK;

@@ -76,14 +76,17 @@ class Bvh:
     return out
 
 
-def _trace_outputs(n_rays, dev, out, want_ids):
+TRACE_ZERO_MISSES = 1
+
+
+def _trace_outputs(n_rays, dev, out, want_ids, alloc=torch.zeros):
   if out is None:
     out = {}
   spec = (("endpoints", 3 * n_rays, torch.float32), ("endcolors", 3 * n_rays, torch.int32),
           ("range", n_rays, torch.float32), ("endrem", n_rays, torch.float32))
   for name, n, dt in spec:
     if name not in out:
-      out[name] = torch.zeros(n, dtype=dt, device=dev)  # misses stay 0 (fusion_lidar.py:440-447)
+      out[name] = alloc(n, dtype=dt, device=dev)  # misses stay 0 (fusion_lidar.py:440-447)
     t = out[name]
     if t.dtype != dt or t.numel() != n or not t.is_contiguous() or t.device != dev:
       raise ValueError("output %s must be a contiguous %s tensor of %d elements on %s" % (name, dt, n, dev))
@@ -92,22 +95,23 @@ def _trace_outputs(n_rays, dev, out, want_ids):
   return out
 
 
-def trace(bvh, rays, origin, height, out=None, want_ids=True):
+def trace(bvh, rays, origin, height, out=None, want_ids=True, zero_misses=False):
   """(ii) closest-hit ray cast; the device-resident equivalent of C_Trace
   (auxiliary/raytracer/RayTracerCython.pyx:15-33 -> RayTracer.cpp:56-92).
 
   rays f32[R,3] (any length, normalised on device), origin f32[3].  Returns dict of flat CUDA
   tensors: endpoints[3R], endcolors[3R], range[R], endrem[R] (written for hits only -- pass
-  `out` to keep previous content) and tri_id[R] (original face index, -1 = miss)."""
+  `out` to keep previous content, or zero_misses=True to have the kernel write 0 for misses)
+  and tri_id[R] (original face index, -1 = miss)."""
   dev = bvh.blob.device
   rays = _dev(rays, torch.float32, dev).reshape(-1)
   origin = _dev(origin, torch.float32, dev).reshape(-1)
   n_rays = rays.numel() // 3
-  out = _trace_outputs(n_rays, dev, out, want_ids)
+  out = _trace_outputs(n_rays, dev, out, want_ids, torch.empty if zero_misses else torch.zeros)
   with torch.cuda.device(dev):
     check(lib().vl_trace(_ptr(bvh.blob), bvh.n_faces, _ptr(rays), _ptr(origin), n_rays, int(height),
                          _ptr(out["endpoints"]), _ptr(out["endcolors"]), _ptr(out["range"]), _ptr(out["endrem"]),
-                         _ptr(out.get("tri_id")), _stream()))
+                         _ptr(out.get("tri_id")), TRACE_ZERO_MISSES if zero_misses else 0, _stream()))
   return out
 
 

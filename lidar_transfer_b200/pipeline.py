@@ -1,0 +1,125 @@
+"""One-scan-per-stream executor for batches of independent scans.
+
+Scans are independent units (every scan has its own mesh, so every scan pays its own LBVH build):
+a ScanRenderer owns `n_streams` CUDA streams, each with a pre-allocated BVH blob, staging and output
+buffers, and round-robins scans over them -- no allocation and no host synchronisation in steady state.
+The reference processes scans one by one in its driver loop (lidar_deform.py:393-458 ->
+TSDFVolume.throw_rays_at_mesh, auxiliary/fusion_lidar.py:426-455 -> C_Trace); this is the batch
+form of the same call, also used to shard scans across GPUs (sharding.py).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import engine
+from ._lib import check, lib
+
+
+def _ptr(t):
+  return ctypes.c_void_p(t.data_ptr())
+
+
+class _Slot:
+  def __init__(self, dev, max_verts, max_faces, n_rays, host_io):
+    f32, i32 = torch.float32, torch.int32
+    self.stream = torch.cuda.Stream(device=dev)
+    self.blob = torch.empty(lib().vl_bvh_blob_bytes(max_faces), dtype=torch.uint8, device=dev)
+    self.out = dict(endpoints=torch.empty(3 * n_rays, dtype=f32, device=dev),
+                    endcolors=torch.empty(3 * n_rays, dtype=i32, device=dev),
+                    range=torch.empty(n_rays, dtype=f32, device=dev),
+                    endrem=torch.empty(n_rays, dtype=f32, device=dev),
+                    tri_id=torch.empty(n_rays, dtype=i32, device=dev))
+    self.done = torch.cuda.Event()
+    self.busy = False
+    if host_io:
+      # device staging for host-fed meshes + pinned host buffers for the results
+      self.d_verts = torch.empty(3 * max_verts, dtype=f32, device=dev)
+      self.d_faces = torch.empty(3 * max_faces, dtype=i32, device=dev)
+      self.d_colors = torch.empty(3 * max_verts, dtype=i32, device=dev)
+      self.d_rem = torch.empty(max_verts, dtype=f32, device=dev)
+      self.h_out = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in self.out.items()}
+
+
+class ScanRenderer:
+  """rays f32[R,3] and origin f32[3] are fixed per renderer (one target sensor)."""
+
+  def __init__(self, rays, origin, height, max_verts, max_faces, n_streams=4, device=None, host_io=False):
+    engine.require_cuda()
+    self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    self.rays = engine._dev(rays, torch.float32, self.dev).reshape(-1)
+    self.origin = engine._dev(origin, torch.float32, self.dev).reshape(-1)
+    self.n_rays = self.rays.numel() // 3
+    self.height = int(height)
+    self.max_verts, self.max_faces = int(max_verts), int(max_faces)
+    self.slots = [_Slot(self.dev, max_verts, max_faces, self.n_rays, host_io) for _ in range(n_streams)]
+    self.host_io = host_io
+    self._next = 0
+    self._lib = lib()
+
+  def _acquire(self):
+    s = self.slots[self._next]
+    self._next = (self._next + 1) % len(self.slots)
+    if s.busy:
+      s.done.synchronize()  # the slot's previous scan must have drained before its buffers are reused
+      s.busy = False
+    return s
+
+  def _launch(self, s, verts, faces, colors, rem, n_verts, n_faces):
+    L = self._lib
+    st = ctypes.c_void_p(s.stream.cuda_stream)
+    check(L.vl_bvh_build(_ptr(verts), _ptr(faces), _ptr(colors), _ptr(rem), n_verts, n_faces, _ptr(s.blob),
+                         s.blob.numel(), st))
+    check(L.vl_trace(_ptr(s.blob), n_faces, _ptr(self.rays), _ptr(self.origin), self.n_rays, self.height,
+                     _ptr(s.out["endpoints"]), _ptr(s.out["endcolors"]), _ptr(s.out["range"]), _ptr(s.out["endrem"]),
+                     _ptr(s.out["tri_id"]), engine.TRACE_ZERO_MISSES, st))
+
+  def submit(self, verts, faces, colors, rem):
+    """Device-resident mesh (flat CUDA tensors: verts f32[3N_v], faces i32[3N_t], colors i32[3N_v],
+    rem f32[N_v]).  Asynchronous; returns the slot whose `.out` tensors hold the result once
+    `slot.done` has completed."""
+    n_verts, n_faces = verts.numel() // 3, faces.numel() // 3
+    if n_faces > self.max_faces:
+      raise ValueError("mesh has %d faces, renderer was sized for %d" % (n_faces, self.max_faces))
+    s = self._acquire()
+    s.stream.wait_stream(torch.cuda.current_stream(self.dev))
+    with torch.cuda.device(self.dev):
+      self._launch(s, verts, faces, colors, rem, n_verts, n_faces)
+    s.done.record(s.stream)
+    s.busy = True
+    return s
+
+  def submit_host(self, verts, faces, colors, rem):
+    """Host mesh (pinned or pageable torch CPU tensors / numpy arrays, flat, reference dtypes):
+    H2D on the slot's stream, build, trace, D2H of the five outputs into the slot's pinned buffers."""
+    if not self.host_io:
+      raise RuntimeError("renderer was created without host_io=True")
+    as_t = lambda a: torch.from_numpy(a) if isinstance(a, np.ndarray) else a
+    verts, faces, colors, rem = (as_t(a).reshape(-1) for a in (verts, faces, colors, rem))
+    n_verts, n_faces = verts.numel() // 3, faces.numel() // 3
+    if n_faces > self.max_faces or n_verts > self.max_verts:
+      raise ValueError("mesh (%d verts, %d faces) exceeds the renderer's capacity" % (n_verts, n_faces))
+    s = self._acquire()
+    with torch.cuda.device(self.dev), torch.cuda.stream(s.stream):
+      s.d_verts[:3 * n_verts].copy_(verts, non_blocking=True)
+      s.d_faces[:3 * n_faces].copy_(faces, non_blocking=True)
+      s.d_colors[:3 * n_verts].copy_(colors, non_blocking=True)
+      s.d_rem[:n_verts].copy_(rem, non_blocking=True)
+      self._launch(s, s.d_verts, s.d_faces, s.d_colors, s.d_rem, n_verts, n_faces)
+      for k, v in s.out.items():
+        s.h_out[k].copy_(v, non_blocking=True)
+    s.done.record(s.stream)
+    s.busy = True
+    return s
+
+  def wait(self):
+    for s in self.slots:
+      if s.busy:
+        s.done.synchronize()
+        s.busy = False
+
+  def fence(self):
+    """Make the current torch stream wait for everything submitted so far (device-side join)."""
+    cur = torch.cuda.current_stream(self.dev)
+    for s in self.slots:
+      cur.wait_stream(s.stream)
