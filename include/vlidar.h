@@ -94,6 +94,7 @@ int vl_bvh_status(const void* d_blob, int n_faces, vl_stream stream, int* info);
  * reference caller obtains by zero-filling first, auxiliary/fusion_lidar.py:440-447).
  * ---------------------------------------------------------------------------------- */
 #define VL_TRACE_ZERO_MISSES 1
+#define VL_TRACE_PACKET      2   /* warp-packet traversal (8x4 beam tiles share one stack) instead of per-ray stacks */
 int vl_trace(const void* d_blob, int n_faces, const float* d_rays, const float* d_origin,
              int n_rays, int height, float* d_endpoints, int* d_endcolors, float* d_range,
              float* d_endrem, int* d_tri_id, int flags, vl_stream stream);
@@ -151,6 +152,11 @@ int         vl_profile_enable(int on);          /* returns the previous setting 
 int         vl_profile_stage_count(void);
 const char* vl_profile_stage_name(int stage);
 int         vl_profile_collect(double* stage_ms, long long* stage_launches);
+/* Debug: while d_stats is non-NULL every vl_trace launch also writes, per ray, the pair
+ * {inner nodes visited, triangles tested} to d_stats[2*r .. 2*r+1] (device int[2*n_rays]). */
+void        vl_debug_trace_stats(int* d_stats);
+/* Debug: force the traversal variant: 0 auto, 1 per-thread, 4/8/16/32 = packet tile width. */
+void        vl_debug_trace_mode(int mode);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,8 @@ SIGNATURES = {
     "vl_profile_stage_count": (_i, []),
     "vl_profile_stage_name": (_c.c_char_p, [_i]),
     "vl_profile_collect": (_i, [_vp, _vp]),
+    "vl_debug_trace_stats": (None, [_vp]),
+    "vl_debug_trace_mode": (None, [_i]),
 }
 
 _lib = None

@@ -52,13 +52,14 @@ __device__ __forceinline__ void slab(const float bminx, const float bminy, const
 template <bool kNanFilter>
 __device__ __forceinline__ void traverse(const VlNode* __restrict__ nodes, const VlTri* __restrict__ tris,
                                          int root_ref, const float3 o, const float3 d, const float3 inv_d,
-                                         uint2 (*sstack)[kTraceThreads], Hit* best) {
+                                         uint2 (*sstack)[kTraceThreads], Hit* best, int* n_nodes, int* n_tris) {
   uint2 lstack[kLocalStack];
   int sp = 0;
   int ref = root_ref;
   const int tid = threadIdx.x;
   while (true) {
     if (ref >= 0) {
+      ++*n_nodes;
       const float4* q = nodes[ref].q;
       const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), e = __ldg(q + 3);
       float tn0, tf0, tn1, tf1;
@@ -83,6 +84,7 @@ __device__ __forceinline__ void traverse(const VlNode* __restrict__ nodes, const
       if (h1) { ref = r1; continue; }
     } else {
       const int first = vl_leaf_first(ref), count = vl_leaf_count(ref);
+      *n_tris += count;
       for (int k = 0; k < count; ++k) {
         const float4* tq = reinterpret_cast<const float4*>(tris + first + k);
         const float4 v0 = __ldg(tq), e1 = __ldg(tq + 1), e2 = __ldg(tq + 2);
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(kTraceThreads)
 k_trace(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ nodes, const VlTri* __restrict__ tris,
         const int4* __restrict__ c0, const float* __restrict__ rays, const float* __restrict__ origin, int n_traced,
         float* __restrict__ endpoints, int* __restrict__ endcolors, float* __restrict__ range,
-        float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses) {
+        float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses, int* __restrict__ stats) {
   __shared__ uint2 sstack[kSmemStack][kTraceThreads];
   const int r = blockIdx.x * kTraceThreads + threadIdx.x;
   if (r >= n_traced) return;
@@ -121,12 +123,14 @@ k_trace(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ nodes, cons
   best.t = 999999999.f;  // BVH.cpp:20
   best.pos = -1; best.orig = 0x7fffffff; best.rem = 0.f;
   const int root = hdr->root_ref;
+  int n_nodes = 0, n_tris = 0;
   if (hdr->n_tris > 0) {
     if (d.x == 0.f || d.y == 0.f || d.z == 0.f || !(d.x == d.x))
-      traverse<true>(nodes, tris, root, o, d, inv_d, sstack, &best);
+      traverse<true>(nodes, tris, root, o, d, inv_d, sstack, &best, &n_nodes, &n_tris);
     else
-      traverse<false>(nodes, tris, root, o, d, inv_d, sstack, &best);
+      traverse<false>(nodes, tris, root, o, d, inv_d, sstack, &best, &n_nodes, &n_tris);
   }
+  if (stats) { stats[2 * (size_t)r] = n_nodes; stats[2 * (size_t)r + 1] = n_tris; }
   if (best.pos >= 0) {
     // RayTracer.cpp:73-90 write-back, BVH.cpp:106-107 hit = o + d * t
     const int4 col = __ldg(c0 + best.pos);
@@ -207,7 +211,134 @@ k_trace_bruteforce(const float* __restrict__ verts, const int* __restrict__ face
   if (tri_id) tri_id[r] = best;
 }
 
+// ---------------------------------------------------------------------------
+// warp-packet traversal: the 32 rays of a warp are a TW x TH tile of the H x W beam grid
+// (neighbouring beams), they walk the tree TOGETHER with one shared stack:
+//   * node / triangle records are fetched with warp-uniform addresses (1 L1 wavefront per
+//     128-bit load instead of up to 32 for per-lane pointers -- the per-thread kernel above is
+//     L1TEX-wavefront bound, profiles/r01_*),
+//   * a child is entered when ANY lane's slab test passes and is not pruned by that lane's best t
+//     (ballot), the child preferred as "near" by more lanes first (BVH.cpp:77 generalised),
+//   * the far child is pushed with PER-LANE entry distances (+inf = lane does not enter), so
+//     popping prunes per lane exactly like BVH.cpp:41.
+// Every lane still sees every triangle the per-thread traversal would test (a superset), so the
+// result is the same closest hit; only the amount of work differs.
+// ---------------------------------------------------------------------------
+constexpr int kPktWarps = 4;
+constexpr int kPktStack = 64;  // LBVH height <= 32 key bits + 32 tie-break bits
+
+template <int TW>
+__global__ void __launch_bounds__(kPktWarps * 32)
+k_trace_packet(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ nodes, const VlTri* __restrict__ tris,
+               const int4* __restrict__ c0, const float* __restrict__ rays, const float* __restrict__ origin,
+               int width, int height, float* __restrict__ endpoints, int* __restrict__ endcolors,
+               float* __restrict__ range, float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses,
+               int* __restrict__ stats) {
+  constexpr int TH = 32 / TW;
+  __shared__ float s_tn[kPktWarps][kPktStack][32];
+  __shared__ int s_ref[kPktWarps][kPktStack];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int tiles_x = (width + TW - 1) / TW, tiles_y = (height + TH - 1) / TH;
+  const int tile = blockIdx.x * kPktWarps + wib;
+  if (tile >= tiles_x * tiles_y) return;  // warp-uniform
+  const int col = (tile % tiles_x) * TW + (lane % TW), row = (tile / tiles_x) * TH + (lane / TW);
+  const bool valid = col < width && row < height;
+  const size_t r = (size_t)row * width + col;
+  const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
+  float3 d = make_float3(0.f, 0.f, 0.f);
+  if (valid) d = vl_normalize(__ldg(rays + 3 * r), __ldg(rays + 3 * r + 1), __ldg(rays + 3 * r + 2));
+  const float3 inv_d = make_float3(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));
+  // a lane with a zero / NaN direction component needs the NaN-filtering slab (BBox.cpp:70-80)
+  const bool odd_lane = valid && (d.x == 0.f || d.y == 0.f || d.z == 0.f || !(d.x == d.x));
+  const bool any_odd = __any_sync(0xffffffffu, odd_lane);
+  float best_t = valid ? 999999999.f : -INFINITY;  // BVH.cpp:20; invalid lanes never enter anything
+  int best_pos = -1, best_orig = 0x7fffffff;
+  float best_rem = 0.f;
+  int n_nodes = 0, n_tris = 0;
+  int ref = hdr->root_ref;
+  int sp = 0;
+  if (hdr->n_tris > 0) {
+    while (true) {
+      if (ref >= 0) {
+        ++n_nodes;
+        const float4* q = nodes[ref].q;  // warp-uniform address
+        const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), e = __ldg(q + 3);
+        float tn0, tf0, tn1, tf1;
+        if (any_odd) {
+          slab<true>(a.x, a.y, a.z, a.w, b.x, b.y, o, inv_d, &tn0, &tf0);
+          slab<true>(b.z, b.w, c.x, c.y, c.z, c.w, o, inv_d, &tn1, &tf1);
+        } else {
+          slab<false>(a.x, a.y, a.z, a.w, b.x, b.y, o, inv_d, &tn0, &tf0);
+          slab<false>(b.z, b.w, c.x, c.y, c.z, c.w, o, inv_d, &tn1, &tf1);
+        }
+        tf0 = tf0 * 1.0000004f; tf1 = tf1 * 1.0000004f;
+        const bool h0 = (tf0 >= 0.f) & (tf0 >= tn0) & (tn0 <= best_t);
+        const bool h1 = (tf1 >= 0.f) & (tf1 >= tn1) & (tn1 <= best_t);
+        const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+        const int r0 = __float_as_int(e.x), r1 = __float_as_int(e.y);
+        if (m0 && m1) {
+          const unsigned want1 = __ballot_sync(0xffffffffu, h1 && (!h0 || tn1 < tn0));
+          const bool first1 = 2 * __popc(want1) > __popc(m0 | m1);
+          s_ref[wib][sp] = first1 ? r0 : r1;
+          s_tn[wib][sp][lane] = first1 ? (h0 ? tn0 : INFINITY) : (h1 ? tn1 : INFINITY);
+          ++sp;
+          ref = first1 ? r1 : r0;
+          continue;
+        }
+        if (m0) { ref = r0; continue; }
+        if (m1) { ref = r1; continue; }
+      } else {
+        const int first = vl_leaf_first(ref), count = vl_leaf_count(ref);
+        n_tris += count;
+        for (int k = 0; k < count; ++k) {
+          const float4* tq = reinterpret_cast<const float4*>(tris + first + k);  // warp-uniform
+          const float4 v0 = __ldg(tq), e1 = __ldg(tq + 1), e2 = __ldg(tq + 2);
+          float t;
+          if (valid && vl_tri_hit(v0, e1, e2, o, d, &t)) {
+            const int orig = __float_as_int(v0.w);
+            if (t < best_t || (t == best_t && orig < best_orig)) {
+              best_t = t; best_pos = first + k; best_orig = orig; best_rem = e1.w;
+            }
+          }
+        }
+      }
+      bool found = false;
+      while (sp > 0) {
+        --sp;
+        if (__any_sync(0xffffffffu, s_tn[wib][sp][lane] <= best_t)) { ref = s_ref[wib][sp]; found = true; break; }
+      }
+      if (!found) break;
+    }
+  }
+  if (!valid) return;
+  if (best_pos >= 0) {
+    const int4 col4 = __ldg(c0 + best_pos);
+    endpoints[3 * r + 0] = __fadd_rn(o.x, __fmul_rn(d.x, best_t));
+    endpoints[3 * r + 1] = __fadd_rn(o.y, __fmul_rn(d.y, best_t));
+    endpoints[3 * r + 2] = __fadd_rn(o.z, __fmul_rn(d.z, best_t));
+    endcolors[3 * r + 0] = col4.x;
+    endcolors[3 * r + 1] = col4.y;
+    endcolors[3 * r + 2] = col4.z;
+    endrem[r] = best_rem;
+    range[r] = best_t;
+  } else if (zero_misses) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { endpoints[3 * r + k] = 0.f; endcolors[3 * r + k] = 0; }
+    endrem[r] = 0.f;
+    range[r] = 0.f;
+  }
+  if (tri_id) tri_id[r] = best_pos >= 0 ? best_orig : -1;
+  if (stats) { stats[2 * r] = n_nodes; stats[2 * r + 1] = n_tris; }
+}
+
+int* g_debug_stats = nullptr;  // vl_debug_trace_stats(): per-ray {inner nodes visited, triangles tested}
+int g_debug_mode = 0;          // vl_debug_trace_mode(): 0 auto, 1 per-thread, 8/16/32 packet tile width
+
 }  // namespace
+
+extern "C" void vl_debug_trace_mode(int mode) { g_debug_mode = mode; }
+
+extern "C" void vl_debug_trace_stats(int* d_stats) { g_debug_stats = d_stats; }
 
 int vl_trace_launch(const void* d_blob, int n_faces, const float* d_rays, const float* d_origin, int n_rays,
                     int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
@@ -220,13 +351,31 @@ int vl_trace_launch(const void* d_blob, int n_faces, const float* d_rays, const 
   if (n_traced <= 0) return VL_OK;
   const char* blob = static_cast<const char*>(d_blob);
   VlBlobLayout L = vl_blob_layout(n_faces);
-  const int nb = (int)((n_traced + kTraceThreads - 1) / kTraceThreads);
+  const VlHeader* hdr = reinterpret_cast<const VlHeader*>(blob);
+  const VlNode* nodes = reinterpret_cast<const VlNode*>(blob + L.off_nodes);
+  const VlTri* tris = reinterpret_cast<const VlTri*>(blob + L.off_tris);
+  const int4* c0 = reinterpret_cast<const int4*>(blob + L.off_c0);
+  const bool zm = (flags & VL_TRACE_ZERO_MISSES) != 0;
+  int mode = g_debug_mode;
+  // measured on B200 (gpurun_out/trace_stats_710.txt): per-thread stacks 0.180 ms, 8x4 packets 0.185 ms per
+  // 131 072 rays over 1.05 M triangles -- packets test 1.65x the triangles, so per-thread is the default
+  if (mode == 0) mode = (flags & VL_TRACE_PACKET) ? ((height >= 4 && width >= 8) ? 8 : 32) : 1;
   VlProfScope ps(VL_ST_TRACE, stream);
-  k_trace<<<nb, kTraceThreads, 0, stream>>>(reinterpret_cast<const VlHeader*>(blob),
-                                           reinterpret_cast<const VlNode*>(blob + L.off_nodes),
-                                           reinterpret_cast<const VlTri*>(blob + L.off_tris),
-                                           reinterpret_cast<const int4*>(blob + L.off_c0), d_rays, d_origin,
-                                           (int)n_traced, d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, (flags & VL_TRACE_ZERO_MISSES) != 0);
+  if (mode == 1) {
+    const int nb = (int)((n_traced + kTraceThreads - 1) / kTraceThreads);
+    k_trace<<<nb, kTraceThreads, 0, stream>>>(hdr, nodes, tris, c0, d_rays, d_origin, (int)n_traced, d_endpoints,
+                                             d_endcolors, d_range, d_endrem, d_tri_id, zm, g_debug_stats);
+  } else {
+    const int tw = mode, th = 32 / mode;
+    const long long n_tiles = (long long)((width + tw - 1) / tw) * ((height + th - 1) / th);
+    const int nb = (int)((n_tiles + kPktWarps - 1) / kPktWarps);
+#define VL_PKT(TW_)                                                                                              \
+  k_trace_packet<TW_><<<nb, kPktWarps * 32, 0, stream>>>(hdr, nodes, tris, c0, d_rays, d_origin, width, height,   \
+                                                         d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id,  \
+                                                         zm, g_debug_stats)
+    if (tw == 8) VL_PKT(8); else if (tw == 16) VL_PKT(16); else if (tw == 4) VL_PKT(4); else VL_PKT(32);
+#undef VL_PKT
+  }
   VL_LAUNCH_CHECK("k_trace");
   return VL_OK;
 }
