@@ -286,9 +286,7 @@ def run_native(args):
   alg_bytes = {
       "bounds": 12 * nv,
       "morton": 12 * nt + 12 * nv + 4 * nt + 4 * nt,          # faces + verts(gather, once) + key + flag
-      "sort_hist": 4 * nt,
-      "sort_scan": 2 * 4 * 256 * np.ceil(nt / 4096),
-      "sort_scatter": (4 + 4) * nt * 2,                       # key+val in, key+val out
+      "sort_pass": (4 + 4) * nt * 2,                          # key+val in, key+val out (one 8-bit digit)
       "emit_climb": 8 * nt + 12 * nt + 28 * nv + 48 * nt + 16 * nt + 64 * nt,
       "trace": 112 * nt + 12 * R + 36 * R,
   }
@@ -325,7 +323,7 @@ def run_native(args):
       "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                    "alg_bytes_per_launch": alg_bytes.get(dom, 0.0), "ms_per_launch": dom_ms / dom_n,
-                   "step_alg_bytes": sum(alg_bytes[k] * (4 if k.startswith("sort") else 1) for k in alg_bytes) * S,
+                   "step_alg_bytes": sum(alg_bytes[k] * (4 if k == "sort_pass" else 1) for k in alg_bytes) * S,
                    "profiled_ms_per_step": ms_prof / K},
       "stages": stages_out,
       "cpu_baseline": cpu,

@@ -5,20 +5,34 @@
 // The tree is a different (Morton-order) tree; closest-hit results do not depend on the tree
 // (DESIGN.md "parity under a different tree").
 //
-// Pipeline (all on the caller's stream, no allocation, no host sync):
-//   k_init_header  -> k_bounds (vertex AABB, warp-reduce + ordered-uint atomics)
-//   -> k_morton (validate faces, centroid -> 32-bit cubic-cell Morton key, zero climb flags)
-//   -> 4 x { k_sort_hist, k_sort_scan, k_sort_scatter }   stable 8-bit LSD radix sort (key, face id)
-//   -> k_emit_climb (write 48 B triangle records in sorted order, then Apetrei-style bottom-up
-//      hierarchy + box refit in the same kernel; sub-trees of <= 4 triangles collapse to leaves)
+// Pipeline: 8 launches on the caller's stream, no allocation, no host sync:
+//   k_init_header  header + zeroed digit histograms / tile tickets
+//   k_bounds       vertex AABB (block reduction, 6 ordered-uint atomics per CTA)
+//   k_morton       validate faces, centroid -> 32-bit cubic-cell Morton key, the four 8-bit digit
+//                  histograms of the whole key array (shared-memory privatised), zeroed climb flags
+//                  and tile states
+//   4 x k_sort_pass  stable LSD radix sort of (key, face id), ONE kernel per 8-bit digit: tiles take
+//                  tickets, rank their keys with __match_any_sync and obtain their global offsets by
+//                  decoupled look-back over per-tile digit counts (single-pass "onesweep" scheme) --
+//                  each key/value is read once and written once per pass
+//   k_emit_climb   sorted 48 B triangle records + bottom-up hierarchy (Apetrei's formulation of the
+//                  Karras radix tree) with box refit in the same kernel.  A CTA owns a run of sorted
+//                  triangles and resolves every inner node whose two children lie inside that run
+//                  through SHARED memory (flag / sibling box / sibling ref); only the few nodes that
+//                  straddle CTA boundaries climb on through global memory + atomics.  Sub-trees of
+//                  <= 4 triangles collapse to leaves and never touch the node array.
 #include "vl_common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 
-__global__ void k_init_header(VlHeader* hdr, int n_tris) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+__global__ void __launch_bounds__(1024) k_init_header(VlHeader* hdr, int n_tris, unsigned int* ghist,
+                                                      unsigned int* tickets) {
+  const int t = threadIdx.x;
+  if (t < 256 * VL_SORT_PASSES) ghist[t] = 0u;
+  if (t < VL_SORT_PASSES) tickets[t] = 0u;
+  if (t == 0) {
     hdr->n_tris = n_tris;
     hdr->root_ref = vl_make_leaf(0, 0);
     hdr->n_bad_faces = 0;
@@ -30,13 +44,18 @@ __global__ void k_init_header(VlHeader* hdr, int n_tris) {
   }
 }
 
-// Vertex AABB: grid-stride float loads, warp shuffle reduction, one atomic pair per warp.
+// Vertex AABB: grid-stride float4-free loads (12 B stride), warp shuffle + shared-memory block
+// reduction, one atomic set per CTA.
 __global__ void __launch_bounds__(kThreads) k_bounds(const float* __restrict__ verts, int n_verts, VlHeader* hdr) {
+  __shared__ float s_mn[kThreads / 32][3], s_mx[kThreads / 32][3];
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_verts; i += gridDim.x * blockDim.x) {
+  // the flat float array is read fully coalesced: element e belongs to axis e % 3
+  const size_t total = 3 * (size_t)n_verts;
+  const size_t stride = (size_t)gridDim.x * kThreads * 3;
+  for (size_t base = ((size_t)blockIdx.x * kThreads + threadIdx.x) * 3; base < total; base += stride) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      float v = __ldg(verts + 3 * (size_t)i + k);
+      float v = __ldg(verts + base + k);
       mn[k] = fminf(mn[k], v);
       mx[k] = fmaxf(mx[k], v);
     }
@@ -49,13 +68,20 @@ __global__ void __launch_bounds__(kThreads) k_bounds(const float* __restrict__ v
       mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], off));
     }
   }
-  if ((threadIdx.x & 31) == 0) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (mn[k] <= mx[k]) {
-        atomicMin(&hdr->bounds_min[k], vl_float_to_ordered(mn[k]));
-        atomicMax(&hdr->bounds_max[k], vl_float_to_ordered(mx[k]));
-      }
+    for (int k = 0; k < 3; ++k) { s_mn[w][k] = mn[k]; s_mx[w][k] = mx[k]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int k = threadIdx.x;
+    float a = s_mn[0][k], b = s_mx[0][k];
+#pragma unroll
+    for (int ww = 1; ww < kThreads / 32; ++ww) { a = fminf(a, s_mn[ww][k]); b = fmaxf(b, s_mx[ww][k]); }
+    if (a <= b) {
+      atomicMin(&hdr->bounds_min[k], vl_float_to_ordered(a));
+      atomicMax(&hdr->bounds_max[k], vl_float_to_ordered(b));
     }
   }
 }
@@ -70,133 +96,115 @@ __device__ __forceinline__ unsigned int expand10(unsigned int v) {  // 10 bits -
 
 // 32-bit Morton key over CUBIC cells: x,y get 11 bits, z 10 bits, one common scale
 // s = 2048 / max(ext_x, ext_y, 2 ext_z) -- LiDAR scenes are flat, equal-size cells keep the
-// radix tree's implicit splits isotropic.
+// radix tree's implicit splits isotropic.  Persistent grid: every CTA also accumulates the four
+// digit histograms of its keys in shared memory and flushes the non-zero bins once.
 __global__ void __launch_bounds__(kThreads)
 k_morton(const float* __restrict__ verts, const int* __restrict__ faces, int n_verts, int n_faces,
-         VlHeader* hdr, unsigned int* __restrict__ keys, int* __restrict__ flags) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_faces) return;
-  flags[i] = 0;
-  int i0 = __ldg(faces + 3 * (size_t)i), i1 = __ldg(faces + 3 * (size_t)i + 1), i2 = __ldg(faces + 3 * (size_t)i + 2);
-  if ((unsigned)i0 >= (unsigned)n_verts || (unsigned)i1 >= (unsigned)n_verts || (unsigned)i2 >= (unsigned)n_verts) {
-    atomicAdd(&hdr->n_bad_faces, 1);
-    keys[i] = 0xffffffffu;
-    return;
-  }
+         VlHeader* hdr, unsigned int* __restrict__ keys, int* __restrict__ flags, unsigned int* __restrict__ ghist,
+         unsigned int* __restrict__ tile_state, int n_state_words) {
+  __shared__ unsigned int h[VL_SORT_PASSES][256];
+#pragma unroll
+  for (int p = 0; p < VL_SORT_PASSES; ++p) h[p][threadIdx.x] = 0u;
   float bmin[3], ext[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     bmin[k] = vl_ordered_to_float(hdr->bounds_min[k]);
     ext[k] = vl_ordered_to_float(hdr->bounds_max[k]) - bmin[k];
   }
-  float m = fmaxf(fmaxf(ext[0], ext[1]), 2.0f * ext[2]);
-  float s = m > 0.0f ? 2048.0f / m : 0.0f;
-  float c[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-    c[k] = (__ldg(verts + 3 * (size_t)i0 + k) + __ldg(verts + 3 * (size_t)i1 + k) + __ldg(verts + 3 * (size_t)i2 + k)) *
-           (1.0f / 3.0f);
-  unsigned int qx = (unsigned int)fminf(fmaxf((c[0] - bmin[0]) * s, 0.0f), 2047.0f);
-  unsigned int qy = (unsigned int)fminf(fmaxf((c[1] - bmin[1]) * s, 0.0f), 2047.0f);
-  unsigned int qz = (unsigned int)fminf(fmaxf((c[2] - bmin[2]) * s, 0.0f), 1023.0f);
-  unsigned int key = ((qx >> 10) << 31) | ((qy >> 10) << 30) | (expand10(qz) << 2) | (expand10(qx & 1023u) << 1) |
-                     expand10(qy & 1023u);
-  keys[i] = key;
-}
-
-// ---------------------------------------------------------------------------
-// stable LSD radix sort, 8-bit digits, tiles of VL_SORT_TILE keys
-// hist layout: hist[digit * n_tiles + tile]  (an exclusive scan of the flat array yields
-// the global output offset of every (digit, tile) bucket)
-// ---------------------------------------------------------------------------
-constexpr int kItems = VL_SORT_TILE / kThreads;  // 16
-
-__global__ void __launch_bounds__(kThreads)
-k_sort_hist(const unsigned int* __restrict__ keys, int n, int shift, unsigned int* __restrict__ hist, int n_tiles) {
-  __shared__ unsigned int h[256];
-  h[threadIdx.x] = 0;
+  const float m = fmaxf(fmaxf(ext[0], ext[1]), 2.0f * ext[2]);
+  const float s = m > 0.0f ? 2048.0f / m : 0.0f;
   __syncthreads();
-  int base = blockIdx.x * VL_SORT_TILE;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n_state_words; i += stride) tile_state[i] = 0u;
+  int n_bad = 0;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n_faces; i += stride) {
+    flags[i] = 0;
+    const int i0 = __ldg(faces + 3 * (size_t)i), i1 = __ldg(faces + 3 * (size_t)i + 1), i2 = __ldg(faces + 3 * (size_t)i + 2);
+    unsigned int key;
+    if ((unsigned)i0 >= (unsigned)n_verts || (unsigned)i1 >= (unsigned)n_verts || (unsigned)i2 >= (unsigned)n_verts) {
+      ++n_bad;
+      key = 0xffffffffu;
+    } else {
+      float c[3];
 #pragma unroll
-  for (int j = 0; j < kItems; ++j) {
-    int idx = base + j * kThreads + threadIdx.x;
-    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+      for (int k = 0; k < 3; ++k)
+        c[k] = (__ldg(verts + 3 * (size_t)i0 + k) + __ldg(verts + 3 * (size_t)i1 + k) + __ldg(verts + 3 * (size_t)i2 + k)) *
+               (1.0f / 3.0f);
+      const unsigned int qx = (unsigned int)fminf(fmaxf((c[0] - bmin[0]) * s, 0.0f), 2047.0f);
+      const unsigned int qy = (unsigned int)fminf(fmaxf((c[1] - bmin[1]) * s, 0.0f), 2047.0f);
+      const unsigned int qz = (unsigned int)fminf(fmaxf((c[2] - bmin[2]) * s, 0.0f), 1023.0f);
+      key = ((qx >> 10) << 31) | ((qy >> 10) << 30) | (expand10(qz) << 2) | (expand10(qx & 1023u) << 1) |
+            expand10(qy & 1023u);
+    }
+    keys[i] = key;
+#pragma unroll
+    for (int p = 0; p < VL_SORT_PASSES; ++p) atomicAdd(&h[p][(key >> (8 * p)) & 255u], 1u);
   }
+  if (n_bad) atomicAdd(&hdr->n_bad_faces, n_bad);
   __syncthreads();
-  hist[threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
-}
-
-// single-CTA exclusive scan over `total` counters (<= a few hundred thousand)
-__global__ void __launch_bounds__(1024) k_sort_scan(unsigned int* __restrict__ hist, int total) {
-  __shared__ unsigned int warp_sums[32];
-  __shared__ unsigned int carry_s;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
-  constexpr int kPer = 4;
-  for (int base = 0; base < total; base += 1024 * kPer) {
-    unsigned int v[kPer], sum = 0;
 #pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-      int idx = base + tid * kPer + k;
-      v[k] = idx < total ? hist[idx] : 0u;
-      sum += v[k];
-    }
-    unsigned int incl = sum;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      unsigned int t = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += t;
-    }
-    if (lane == 31) warp_sums[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-      unsigned int ws = warp_sums[lane], wi = ws;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        unsigned int t = __shfl_up_sync(0xffffffffu, wi, off);
-        if (lane >= off) wi += t;
-      }
-      warp_sums[lane] = wi - ws;  // exclusive
-    }
-    __syncthreads();
-    unsigned int run = carry_s + warp_sums[wid] + (incl - sum);
-#pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-      int idx = base + tid * kPer + k;
-      if (idx < total) hist[idx] = run;
-      run += v[k];
-    }
-    __syncthreads();
-    if (tid == 1023) carry_s = run;
-    __syncthreads();
+  for (int p = 0; p < VL_SORT_PASSES; ++p) {
+    const unsigned int c = h[p][threadIdx.x];
+    if (c) atomicAdd(&ghist[p * 256 + threadIdx.x], c);
   }
 }
 
-// Stable scatter.  Warp w owns the contiguous 512-key run [tile*4096 + 512 w, +512) and walks it in
-// 16 rounds of 32; __match_any_sync ranks equal digits inside a round, a per-warp digit counter in
-// shared memory carries the rank across rounds, a 256-thread column scan orders the warps.
-__global__ void __launch_bounds__(kThreads)
-k_sort_scatter(const unsigned int* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
-               unsigned int* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int n, int shift,
-               const unsigned int* __restrict__ hist, int n_tiles) {
-  __shared__ unsigned int cnt[kThreads / 32][256];
+// ---------------------------------------------------------------------------
+// stable LSD radix sort, 8-bit digits, one kernel per digit (decoupled look-back)
+//
+// tile state word (per tile, per digit): [31:30] 0 = not ready, 1 = this tile's count,
+// 2 = inclusive count of tiles 0..this;  [29:0] the count (n < 2^28).
+// Tiles are numbered by a ticket counter, so a tile only ever waits for tiles that started earlier.
+// ---------------------------------------------------------------------------
+constexpr int kItems = VL_SORT_ITEMS;
+constexpr int kSortWarps = VL_SORT_THREADS / 32;
+constexpr unsigned int kStAggregate = 1u << 30, kStPrefix = 2u << 30, kStMask = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(VL_SORT_THREADS)
+k_sort_pass(const unsigned int* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
+            unsigned int* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int n, int shift,
+            const unsigned int* __restrict__ ghist, volatile unsigned int* tile_state, unsigned int* ticket) {
+  __shared__ unsigned int cnt[kSortWarps][256];
+  __shared__ unsigned int warp_sums[kSortWarps];
+  __shared__ int s_tile;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  for (int k = tid; k < (kThreads / 32) * 256; k += kThreads) (&cnt[0][0])[k] = 0;
+  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+#pragma unroll
+  for (int ww = 0; ww < kSortWarps; ++ww) cnt[ww][tid] = 0u;
+  // exclusive scan of the global digit histogram: thread d -> first output slot of digit d
+  const unsigned int gcount = ghist[tid];
+  unsigned int incl = gcount;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += t;
+  }
+  if (lane == 31) warp_sums[w] = incl;
   __syncthreads();
-  const int base = blockIdx.x * VL_SORT_TILE + w * (32 * kItems);
+  unsigned int gbase = incl - gcount;
+#pragma unroll
+  for (int ww = 0; ww < kSortWarps; ++ww)
+    if (ww < w) gbase += warp_sums[ww];
+  const int tile = s_tile;
+
+  // rank: warp w owns the contiguous run [tile*TILE + w*32*kItems, +32*kItems), walked in kItems rounds of 32
+  const int base = tile * VL_SORT_TILE + w * (32 * kItems);
   const unsigned int lt_mask = (1u << lane) - 1u;
   unsigned int key[kItems], val[kItems];
   unsigned short rank[kItems];
 #pragma unroll
   for (int j = 0; j < kItems; ++j) {
-    int idx = base + j * 32 + lane;
-    bool valid = idx < n;
+    const int idx = base + j * 32 + lane;
+    const bool valid = idx < n;
     key[j] = valid ? keys_in[idx] : 0xffffffffu;
     val[j] = valid ? (vals_in ? vals_in[idx] : (unsigned int)idx) : 0u;
-    unsigned int d = (key[j] >> shift) & 255u;
-    unsigned int peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u);
-    int leader = __ffs(peers) - 1;
+  }
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const bool valid = base + j * 32 + lane < n;
+    const unsigned int d = (key[j] >> shift) & 255u;
+    const unsigned int peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u);
+    const int leader = __ffs(peers) - 1;
     unsigned int basecnt = 0;
     if (lane == leader && valid) {
       basecnt = cnt[w][d];
@@ -207,22 +215,41 @@ k_sort_scatter(const unsigned int* __restrict__ keys_in, const unsigned int* __r
     __syncwarp();
   }
   __syncthreads();
-  {  // thread d: exclusive scan of digit d over the 8 warps, seeded with the global bucket offset
-    unsigned int run = hist[tid * n_tiles + blockIdx.x];
+  {  // thread d: digit d's count in this tile, published; look back for the tiles before
+    unsigned int run = 0;
 #pragma unroll
-    for (int ww = 0; ww < kThreads / 32; ++ww) {
-      unsigned int c = cnt[ww][tid];
+    for (int ww = 0; ww < kSortWarps; ++ww) {
+      const unsigned int c = cnt[ww][tid];
       cnt[ww][tid] = run;
       run += c;
     }
+    volatile unsigned int* mine = tile_state + (size_t)tile * 256 + tid;
+    unsigned int before = 0;
+    if (tile == 0) {
+      *mine = kStPrefix | run;
+    } else {
+      *mine = kStAggregate | run;
+      int t = tile - 1;
+      while (true) {
+        const unsigned int st = tile_state[(size_t)t * 256 + tid];
+        if ((st >> 30) == 0u) continue;  // predecessor has not published yet
+        before += st & kStMask;
+        if ((st >> 30) == 2u) break;
+        --t;
+      }
+      *mine = kStPrefix | (before + run);
+    }
+    const unsigned int off = gbase + before;
+#pragma unroll
+    for (int ww = 0; ww < kSortWarps; ++ww) cnt[ww][tid] += off;
   }
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < kItems; ++j) {
-    int idx = base + j * 32 + lane;
+    const int idx = base + j * 32 + lane;
     if (idx < n) {
-      unsigned int d = (key[j] >> shift) & 255u;
-      unsigned int out = cnt[w][d] + rank[j];
+      const unsigned int d = (key[j] >> shift) & 255u;
+      const unsigned int out = cnt[w][d] + rank[j];
       keys_out[out] = key[j];
       vals_out[out] = val[j];
     }
@@ -233,19 +260,79 @@ k_sort_scatter(const unsigned int* __restrict__ keys_in, const unsigned int* __r
 // emit sorted triangle records + bottom-up hierarchy (Apetrei 2014 formulation of the
 // Karras radix tree: inner node i sits between sorted keys i and i+1)
 // ---------------------------------------------------------------------------
+constexpr int kClimbThreads = 512;
+constexpr int kClimbWarps = kClimbThreads / 32;
+constexpr unsigned long long kDeltaInf = ~0ull;
+
+// delta(i): the split level between sorted keys i and i+1 (larger = the two keys part ways higher up the
+// radix tree); equal keys are told apart by the index bits, so all deltas of one array are distinct.
 __device__ __forceinline__ unsigned long long key_delta(const unsigned int* __restrict__ keys, int i) {
-  return ((unsigned long long)(keys[i] ^ keys[i + 1]) << 32) | (unsigned int)(i ^ (i + 1));
+  return ((unsigned long long)(__ldg(keys + i) ^ __ldg(keys + i + 1)) << 32) | (unsigned int)(i ^ (i + 1));
 }
 
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ unsigned long long shfl_up64(unsigned long long v, int off) {
+  return ((unsigned long long)__shfl_up_sync(0xffffffffu, (unsigned int)(v >> 32), off) << 32) |
+         __shfl_up_sync(0xffffffffu, (unsigned int)v, off);
+}
+__device__ __forceinline__ unsigned long long shfl_down64(unsigned long long v, int off) {
+  return ((unsigned long long)__shfl_down_sync(0xffffffffu, (unsigned int)(v >> 32), off) << 32) |
+         __shfl_down_sync(0xffffffffu, (unsigned int)v, off);
+}
+
+__global__ void __launch_bounds__(kClimbThreads)
 k_emit_climb(const float* __restrict__ verts, const int* __restrict__ faces, const int* __restrict__ colors,
              const float* __restrict__ rem, int n_verts, int n, const unsigned int* __restrict__ keys,
              const unsigned int* __restrict__ vals, VlHeader* hdr, VlNode* nodes, VlTri* __restrict__ tris,
              int4* __restrict__ c0, int* flags) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
+  // Slot k of the CTA = inner node B0 + k (it sits between sorted keys B0+k and B0+k+1).  Node i is LOCAL
+  // when its whole key range lies inside the CTA's run [B0, B1): its range grows left / right until it
+  // meets a larger delta, so   local(i)  <=>  max delta[B0-1 .. i-1] > delta(i)  and  max delta[i+1 .. B1-1] > delta(i)
+  // (delta(-1) = delta(n-1) = +inf).  Both children of a node evaluate the same predicate, and every leaf
+  // under a local node belongs to this CTA, so the two children always meet in the same place.
+  __shared__ unsigned long long s_delta[kClimbThreads + 1];  // [0] = delta(B0-1), [1+k] = delta(B0+k)
+  __shared__ unsigned long long s_wmax[2][kClimbWarps];
+  __shared__ unsigned char s_local[kClimbThreads];
+  __shared__ int s_flag[kClimbThreads];
+  __shared__ float s_box[kClimbThreads][2][6];  // [left child | right child] box
+  __shared__ int s_ref[kClimbThreads][2];
+  __shared__ int s_bound[kClimbThreads][2];     // left child: range start, right child: range end
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int B0 = blockIdx.x * kClimbThreads;
+  const int B1 = min(B0 + kClimbThreads, n);
+  const int p = B0 + tid;
+  const bool active = p < n;
+  s_flag[tid] = 0;
+  {
+    unsigned long long dl = 0ull;  // delta(p); 0 for slots past the run never wins a max
+    if (active) dl = (p == n - 1) ? kDeltaInf : key_delta(keys, p);
+    if (tid == 0) s_delta[0] = (B0 == 0) ? kDeltaInf : key_delta(keys, B0 - 1);
+    s_delta[1 + tid] = dl;
+    // inclusive prefix / suffix max inside the warp, warp totals to shared memory
+    unsigned long long pm = dl, sm = dl;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned long long a = shfl_up64(pm, off), b = shfl_down64(sm, off);
+      if (lane >= off) pm = max(pm, a);
+      if (lane + off < 32) sm = max(sm, b);
+    }
+    if (lane == 31) s_wmax[0][wid] = pm;
+    if (lane == 0) s_wmax[1][wid] = sm;
+    __syncthreads();
+    // exclusive versions: max over [B0-1 .. p-1] and over [p+1 .. B1-1]
+    unsigned long long pre = shfl_up64(pm, 1), suf = shfl_down64(sm, 1);
+    if (lane == 0) pre = 0ull;
+    if (lane == 31) suf = 0ull;
+    pre = max(pre, s_delta[0]);
+    for (int ww = 0; ww < kClimbWarps; ++ww) {
+      if (ww < wid) pre = max(pre, s_wmax[0][ww]);
+      if (ww > wid) suf = max(suf, s_wmax[1][ww]);
+    }
+    s_local[tid] = (active && p <= B1 - 2 && pre > dl && suf > dl) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!active) return;
   const int f = (int)vals[p];
-  int i0 = __ldg(faces + 3 * (size_t)f), i1 = __ldg(faces + 3 * (size_t)f + 1), i2 = __ldg(faces + 3 * (size_t)f + 2);
+  const int i0 = __ldg(faces + 3 * (size_t)f), i1 = __ldg(faces + 3 * (size_t)f + 1), i2 = __ldg(faces + 3 * (size_t)f + 2);
   float bmin[3], bmax[3];
   if ((unsigned)i0 >= (unsigned)n_verts || (unsigned)i1 >= (unsigned)n_verts || (unsigned)i2 >= (unsigned)n_verts) {
     // invalid face: a record no ray can hit (a = 0) and an empty box
@@ -266,7 +353,7 @@ k_emit_climb(const float* __restrict__ verts, const int* __restrict__ faces, con
       v2[k] = __ldg(verts + 3 * (size_t)i2 + k);
     }
     // Triangle.h:63-70 mean remission, RayTracer.cpp:36-48 colours pass through float
-    float r = __fdiv_rn(__fadd_rn(__fadd_rn(__ldg(rem + i0), __ldg(rem + i1)), __ldg(rem + i2)), 3.0f);
+    const float r = __fdiv_rn(__fadd_rn(__fadd_rn(__ldg(rem + i0), __ldg(rem + i1)), __ldg(rem + i2)), 3.0f);
     VlTri t;
     t.v0 = make_float4(v0[0], v0[1], v0[2], __int_as_float(f));
     t.e1 = make_float4(__fsub_rn(v1[0], v0[0]), __fsub_rn(v1[1], v0[1]), __fsub_rn(v1[2], v0[2]), r);
@@ -292,31 +379,72 @@ k_emit_climb(const float* __restrict__ verts, const int* __restrict__ faces, con
   int ref = vl_make_leaf(p, 1);
   if (n == 1) { hdr->root_ref = ref; return; }
   int climb = 0;
+  bool in_cta = true;  // [l, r] still inside [B0, B1): deltas come from shared memory
   while (true) {
     bool is_left;
     if (l == 0) is_left = true;
     else if (r == n - 1) is_left = false;
+    else if (in_cta) is_left = s_delta[1 + r - B0] < s_delta[l - B0];
     else is_left = key_delta(keys, r) < key_delta(keys, l - 1);
     const int parent = is_left ? r : l - 1;
-    float* nf = reinterpret_cast<float*>(&nodes[parent]);
-    int* ni = reinterpret_cast<int*>(&nodes[parent]);
-    const int boff = is_left ? 0 : 6;
+    if (in_cta && parent >= B0 && parent < B1 && s_local[parent - B0]) {
+      // ---- the whole sub-tree of `parent` lives in this CTA: the children meet in shared memory ----
+      const int k = parent - B0, me = is_left ? 0 : 1;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { nf[boff + k] = bmin[k]; nf[boff + 3 + k] = bmax[k]; }
-    ni[is_left ? 12 : 13] = ref;
-    ni[is_left ? 14 : 15] = is_left ? l : r;
-    __threadfence();
-    if (atomicExch(&flags[parent], 1) == 0) break;  // first child to arrive stops here
-    __threadfence();
-    const int soff = is_left ? 6 : 0;
+      for (int a = 0; a < 3; ++a) { s_box[k][me][a] = bmin[a]; s_box[k][me][3 + a] = bmax[a]; }
+      s_ref[k][me] = ref;
+      s_bound[k][me] = is_left ? l : r;
+      __threadfence_block();
+      if (atomicExch(&s_flag[k], 1) == 0) break;  // first child to arrive stops here
+      __threadfence_block();
+      float smin[3], smax[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      bmin[k] = fminf(bmin[k], __ldcg(nf + soff + k));
-      bmax[k] = fmaxf(bmax[k], __ldcg(nf + soff + 3 + k));
+      for (int a = 0; a < 3; ++a) { smin[a] = s_box[k][me ^ 1][a]; smax[a] = s_box[k][me ^ 1][3 + a]; }
+      const int sref = s_ref[k][me ^ 1];
+      if (is_left) r = s_bound[k][1]; else l = s_bound[k][0];
+      const int size = r - l + 1;
+      if (size > VL_LEAF_MAX) {  // a real inner node: the whole 64 B record in one go
+        float4 q0, q1, q2, q3;
+        if (is_left) {
+          q0 = make_float4(bmin[0], bmin[1], bmin[2], bmax[0]);
+          q1 = make_float4(bmax[1], bmax[2], smin[0], smin[1]);
+          q2 = make_float4(smin[2], smax[0], smax[1], smax[2]);
+          q3 = make_float4(__int_as_float(ref), __int_as_float(sref), __int_as_float(l), __int_as_float(r));
+        } else {
+          q0 = make_float4(smin[0], smin[1], smin[2], smax[0]);
+          q1 = make_float4(smax[1], smax[2], bmin[0], bmin[1]);
+          q2 = make_float4(bmin[2], bmax[0], bmax[1], bmax[2]);
+          q3 = make_float4(__int_as_float(sref), __int_as_float(ref), __int_as_float(l), __int_as_float(r));
+        }
+        float4* q = nodes[parent].q;
+        q[0] = q0; q[1] = q1; q[2] = q2; q[3] = q3;
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { bmin[a] = fminf(bmin[a], smin[a]); bmax[a] = fmaxf(bmax[a], smax[a]); }
+      ref = size <= VL_LEAF_MAX ? vl_make_leaf(l, size) : parent;
+    } else {
+      // ---- the sub-tree of `parent` spans CTAs: the children meet in global memory ----
+      in_cta = false;
+      float* nf = reinterpret_cast<float*>(&nodes[parent]);
+      int* ni = reinterpret_cast<int*>(&nodes[parent]);
+      const int boff = is_left ? 0 : 6;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { nf[boff + a] = bmin[a]; nf[boff + 3 + a] = bmax[a]; }
+      ni[is_left ? 12 : 13] = ref;
+      ni[is_left ? 14 : 15] = is_left ? l : r;
+      __threadfence();
+      if (atomicExch(&flags[parent], 1) == 0) break;  // first child to arrive stops here
+      __threadfence();
+      const int soff = is_left ? 6 : 0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        bmin[a] = fminf(bmin[a], __ldcg(nf + soff + a));
+        bmax[a] = fmaxf(bmax[a], __ldcg(nf + soff + 3 + a));
+      }
+      if (is_left) r = __ldcg(ni + 15); else l = __ldcg(ni + 14);
+      const int size = r - l + 1;
+      ref = size <= VL_LEAF_MAX ? vl_make_leaf(l, size) : parent;
     }
-    if (is_left) r = __ldcg(ni + 15); else l = __ldcg(ni + 14);
-    const int size = r - l + 1;
-    ref = size <= VL_LEAF_MAX ? vl_make_leaf(l, size) : parent;
     ++climb;
     if (l == 0 && r == n - 1) {
       hdr->root_ref = ref;
@@ -333,43 +461,43 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
   char* blob = static_cast<char*>(d_blob);
   VlBlobLayout L = vl_blob_layout(n_faces);
   VlHeader* hdr = reinterpret_cast<VlHeader*>(blob);
-  k_init_header<<<1, 32, 0, stream>>>(hdr, n_faces);
+  unsigned int* ghist = reinterpret_cast<unsigned int*>(blob + L.off_ghist);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(blob + L.off_tickets);
+  unsigned int* tile_state = reinterpret_cast<unsigned int*>(blob + L.off_tile_state);
+  k_init_header<<<1, 1024, 0, stream>>>(hdr, n_faces, ghist, tickets);
   VL_LAUNCH_CHECK("k_init_header");
   if (n_faces <= 0) return VL_OK;
   unsigned int* keys0 = reinterpret_cast<unsigned int*>(blob + L.off_keys0);
   unsigned int* keys1 = reinterpret_cast<unsigned int*>(blob + L.off_keys1);
   unsigned int* vals0 = reinterpret_cast<unsigned int*>(blob + L.off_vals0);
   unsigned int* vals1 = reinterpret_cast<unsigned int*>(blob + L.off_vals1);
-  unsigned int* hist = reinterpret_cast<unsigned int*>(blob + L.off_hist);
   int* flags = reinterpret_cast<int*>(blob + L.off_flags);
 
+  // persistent grids: 148 SMs x 4 resident CTAs
   int nb_verts = (n_verts + kThreads - 1) / kThreads;
-  if (nb_verts > 148 * 8) nb_verts = 148 * 8;
+  if (nb_verts > 148 * 4) nb_verts = 148 * 4;
   if (nb_verts < 1) nb_verts = 1;
   { VlProfScope ps(VL_ST_BOUNDS, stream);
   k_bounds<<<nb_verts, kThreads, 0, stream>>>(d_verts, n_verts, hdr); }
   VL_LAUNCH_CHECK("k_bounds");
-  const int nb_faces = (n_faces + kThreads - 1) / kThreads;
+  const int nt = L.n_sort_tiles;
+  const int n_state_words = 256 * VL_SORT_PASSES * nt;
+  int nb_faces = (n_faces + kThreads - 1) / kThreads;
+  if (nb_faces > 148 * 4) nb_faces = 148 * 4;
   { VlProfScope ps(VL_ST_MORTON, stream);
-  k_morton<<<nb_faces, kThreads, 0, stream>>>(d_verts, d_faces, n_verts, n_faces, hdr, keys0, flags); }
+  k_morton<<<nb_faces, kThreads, 0, stream>>>(d_verts, d_faces, n_verts, n_faces, hdr, keys0, flags, ghist, tile_state,
+                                             n_state_words); }
   VL_LAUNCH_CHECK("k_morton");
 
-  const int nt = L.n_sort_tiles;
   const unsigned int* kin = keys0;
   const unsigned int* vin = nullptr;  // pass 0 generates the identity permutation on the fly
   unsigned int* kout = keys1;
   unsigned int* vout = vals1;
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 8 * pass;
-    { VlProfScope ps(VL_ST_SORT_HIST, stream);
-    k_sort_hist<<<nt, kThreads, 0, stream>>>(kin, n_faces, shift, hist, nt); }
-    VL_LAUNCH_CHECK("k_sort_hist");
-    { VlProfScope ps(VL_ST_SORT_SCAN, stream);
-    k_sort_scan<<<1, 1024, 0, stream>>>(hist, 256 * nt); }
-    VL_LAUNCH_CHECK("k_sort_scan");
-    { VlProfScope ps(VL_ST_SORT_SCATTER, stream);
-    k_sort_scatter<<<nt, kThreads, 0, stream>>>(kin, vin, kout, vout, n_faces, shift, hist, nt); }
-    VL_LAUNCH_CHECK("k_sort_scatter");
+  for (int pass = 0; pass < VL_SORT_PASSES; ++pass) {
+    { VlProfScope ps(VL_ST_SORT_PASS, stream);
+    k_sort_pass<<<nt, VL_SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, n_faces, 8 * pass, ghist + 256 * pass,
+                                                   tile_state + (size_t)256 * nt * pass, tickets + pass); }
+    VL_LAUNCH_CHECK("k_sort_pass");
     kin = kout;
     vin = vout;
     kout = (kout == keys1) ? keys0 : keys1;
@@ -377,10 +505,11 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
   }
   // after 4 passes the sorted (key, face id) pairs are back in keys0 / vals0
   VlProfScope ps_emit(VL_ST_EMIT_CLIMB, stream);
-  k_emit_climb<<<nb_faces, kThreads, 0, stream>>>(d_verts, d_faces, d_colors, d_rem, n_verts, n_faces, keys0, vals0, hdr,
-                                                 reinterpret_cast<VlNode*>(blob + L.off_nodes),
-                                                 reinterpret_cast<VlTri*>(blob + L.off_tris),
-                                                 reinterpret_cast<int4*>(blob + L.off_c0), flags);
+  const int nb_climb = (n_faces + kClimbThreads - 1) / kClimbThreads;
+  k_emit_climb<<<nb_climb, kClimbThreads, 0, stream>>>(d_verts, d_faces, d_colors, d_rem, n_verts, n_faces, keys0, vals0,
+                                                      hdr, reinterpret_cast<VlNode*>(blob + L.off_nodes),
+                                                      reinterpret_cast<VlTri*>(blob + L.off_tris),
+                                                      reinterpret_cast<int4*>(blob + L.off_c0), flags);
   VL_LAUNCH_CHECK("k_emit_climb");
   return VL_OK;
 }

@@ -16,7 +16,7 @@ void vl_count_launch();
 // bench.py switches it on to obtain the per-kernel durations behind the roofline figures.
 // ---------------------------------------------------------------------------
 enum VlStage {
-  VL_ST_BOUNDS = 0, VL_ST_MORTON, VL_ST_SORT_HIST, VL_ST_SORT_SCAN, VL_ST_SORT_SCATTER, VL_ST_EMIT_CLIMB,
+  VL_ST_BOUNDS = 0, VL_ST_MORTON, VL_ST_SORT_PASS, VL_ST_EMIT_CLIMB,
   VL_ST_TRACE, VL_ST_PROJECT_SCATTER, VL_ST_PROJECT_GATHER, VL_ST_TSDF_INIT, VL_ST_TSDF_INTEGRATE,
   VL_ST_MESH_COUNT, VL_ST_MESH_SCAN, VL_ST_MESH_EMIT, VL_ST_COUNT
 };
@@ -52,7 +52,7 @@ struct VlProfScope {
 // BVH blob layout (one caller-provided device allocation, all sections 256 B aligned)
 //
 //   [header 256 B][nodes 64 B x max(n-1,1)][tris 48 B x n][c0 16 B x n]
-//   [sort keys 2 x 4 B x n][sort vals 2 x 4 B x n][flags 4 B x n][radix hist]
+//   [sort keys 2 x 4 B x n][sort vals 2 x 4 B x n][flags 4 B x n][radix-sort scratch]
 //
 // HBM layout rationale: a node carries BOTH children's boxes so one 64 B (half-line)
 // fetch decides both descents; a triangle record is three float4 (v0, e1, e2) so a leaf
@@ -88,10 +88,15 @@ __host__ __device__ inline int vl_make_leaf(int first, int count) { return ~((fi
 __host__ __device__ inline int vl_leaf_first(int ref) { return (~ref) >> 3; }
 __host__ __device__ inline int vl_leaf_count(int ref) { return (~ref) & 7; }
 
-#define VL_SORT_TILE 4096  // keys per radix-sort tile (256 threads x 16)
+#define VL_SORT_THREADS 256
+#define VL_SORT_ITEMS 8
+#define VL_SORT_TILE (VL_SORT_THREADS * VL_SORT_ITEMS)  // keys per radix-sort tile
+#define VL_SORT_PASSES 4                                // 8-bit digits over the 32-bit Morton key
 
+// sort scratch: [digit histograms 4 x 256 u32][4 tile tickets, padded to 256 B][tile states 4 x n_tiles x 256 u32]
 struct VlBlobLayout {
-  size_t off_nodes, off_tris, off_c0, off_keys0, off_keys1, off_vals0, off_vals1, off_flags, off_hist;
+  size_t off_nodes, off_tris, off_c0, off_keys0, off_keys1, off_vals0, off_vals1, off_flags;
+  size_t off_ghist, off_tickets, off_tile_state;
   size_t total;
   int n_sort_tiles;
 };
@@ -111,7 +116,9 @@ __host__ inline VlBlobLayout vl_blob_layout(int n) {
   L.off_vals1 = off; off = vl_align256(off + 4 * nn);
   L.off_flags = off; off = vl_align256(off + 4 * nn);
   L.n_sort_tiles = (int)((nn + VL_SORT_TILE - 1) / VL_SORT_TILE);
-  L.off_hist = off;  off = vl_align256(off + 4 * 256 * (size_t)L.n_sort_tiles);
+  L.off_ghist = off;      off = vl_align256(off + 4 * 256 * VL_SORT_PASSES);
+  L.off_tickets = off;    off = vl_align256(off + 4 * VL_SORT_PASSES);
+  L.off_tile_state = off; off = vl_align256(off + 4 * 256 * (size_t)VL_SORT_PASSES * (size_t)L.n_sort_tiles);
   L.total = off;
   return L;
 }
