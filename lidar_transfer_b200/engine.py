@@ -219,6 +219,34 @@ class TsdfDevice:
                                     _ptr(color_im), _ptr(depth_im), _ptr(rem_im), int(im_h), int(im_w), _stream()))
 
 
+  def extract_mesh(self, level=0.0, want_norms=True):
+    """(v) iso-surface of the TSDF volume at `level` + per-vertex colour / remission lookup on the device;
+    the device-resident equivalent of TSDFVolume.get_mesh (auxiliary/fusion_lidar.py:403-424).
+    Returns dict(verts f32[N_v,3] world frame, faces i32[N_t,3], norms f32[N_v,3], colors u8[N_v,3],
+    rem f32[N_v]) -- a triangle soup, N_v = 3 N_t.  Synchronises once (the triangle count)."""
+    dev = self.tsdf.device
+    n = self.dim[0] * self.dim[1] * self.dim[2]
+    need = lib().vl_mesh_workspace_bytes(n)
+    ws = getattr(self, "_mesh_ws", None)
+    if ws is None or ws.numel() < need:
+      ws = self._mesh_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    origin = (ctypes.c_float * 3)(*[float(v) for v in self.origin])
+    with torch.cuda.device(dev):
+      check(lib().vl_mesh_count(_ptr(self.tsdf), self.dim[0], self.dim[1], self.dim[2], float(level), _ptr(ws),
+                                ws.numel(), _ptr(total), _stream()))
+      n_t = int(total.item())
+      out = dict(verts=torch.empty((3 * n_t, 3), dtype=torch.float32, device=dev),
+                 faces=torch.empty((n_t, 3), dtype=torch.int32, device=dev),
+                 norms=torch.empty((3 * n_t, 3), dtype=torch.float32, device=dev) if want_norms else None,
+                 colors=torch.empty((3 * n_t, 3), dtype=torch.uint8, device=dev),
+                 rem=torch.empty(3 * n_t, dtype=torch.float32, device=dev))
+      check(lib().vl_mesh_emit(_ptr(self.tsdf), _ptr(self.color), _ptr(self.rem), self.dim[0], self.dim[1], self.dim[2],
+                               float(level), self.voxel_size, origin, _ptr(ws), ws.numel(), n_t, _ptr(out["verts"]),
+                               _ptr(out["faces"]), _ptr(out["norms"]), _ptr(out["colors"]), _ptr(out["rem"]), _stream()))
+    return out
+
+
 def ctrace_host(rays, origin, verts, faces, colors, rem, height, outputs=None, want_ids=False):
   """The reference-compatible HOST-pointer entry point (extern "C" ctrace / vl_ctrace_ids) on numpy
   buffers: H2D, build, trace, D2H inside the call.  outputs: dict of preallocated numpy arrays

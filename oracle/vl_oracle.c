@@ -508,4 +508,68 @@ void vlo_mesh_attributes(const float* verts_vox, long n, const float* color_vol,
   }
 }
 
+/* ------------------------------------------------------------------ */
+/* iso-surface extraction (restates lidar_transfer_b200/csrc/vl_mesh.cu; replaces get_mesh,   */
+/* auxiliary/fusion_lidar.py:403-424, whose marching cubes lives in un-vendored scikit-image  */
+/* -- parity of the topology against skimage is UNPINNED)                     */
+/* ------------------------------------------------------------------ */
+#include "../lidar_transfer_b200/csrc/vl_mc_table.inc"
+static const signed char vlo_tri_table[256][15] = VL_MC_TRI_TABLE;
+static const unsigned char vlo_tri_count[256] = VL_MC_TRI_COUNT;
+static const unsigned char vlo_edge_corners[12][2] = VL_MC_EDGE_CORNERS;
+
+/*
+ * Cubes are visited in voxel-index order (x slowest, z fastest), triangles in table order; the
+ * output is a triangle soup (3 vertices per triangle).  Vertex = low corner + t along the edge
+ * axis with t = (level - va) / (vb - va) in float32; world = vert * voxel_size + origin (:412);
+ * label / remission from the nearest voxel (np.round, :409-415); colours split as :417-423.
+ * Returns the number of triangles; writes at most `capacity` of them (capacity 0 = count only).
+ */
+long long vlo_mesh_extract(const float* tsdf, const float* color_vol, const float* rem_vol, int dx, int dy, int dz,
+                           float level, float voxel_size, const float* vol_origin, long long capacity,
+                           float* verts, int* faces, uint8_t* colors, float* rem_out) {
+  long long n_tris = 0;
+  const long long yz = (long long)dy * dz;
+  for (int x = 0; x + 1 < dx; ++x)
+    for (int y = 0; y + 1 < dy; ++y)
+      for (int z = 0; z + 1 < dz; ++z) {
+        const long long vi = (long long)x * yz + (long long)y * dz + z;
+        float v[8];
+        int mask = 0;
+        for (int c = 0; c < 8; ++c) {
+          v[c] = tsdf[vi + (c & 1) * yz + ((c >> 1) & 1) * dz + ((c >> 2) & 1)];
+          if (v[c] < level) mask |= 1 << c;
+        }
+        const int cnt = vlo_tri_count[mask];
+        for (int t = 0; t < cnt; ++t, ++n_tris) {
+          if (n_tris >= capacity) continue;
+          for (int k = 0; k < 3; ++k) {
+            const int e = vlo_tri_table[mask][3 * t + k];
+            const int ca = vlo_edge_corners[e][0], cb = vlo_edge_corners[e][1];
+            const float tt = (level - v[ca]) / (v[cb] - v[ca]);
+            float pv[3] = {(float)(x + (ca & 1)), (float)(y + ((ca >> 1) & 1)), (float)(z + ((ca >> 2) & 1))};
+            const int axis = (ca ^ cb) == 1 ? 0 : ((ca ^ cb) == 2 ? 1 : 2);
+            pv[axis] = pv[axis] + tt;
+            long ix = (long)rint((double)pv[0]), iy = (long)rint((double)pv[1]), iz = (long)rint((double)pv[2]);
+            if (ix > dx - 1) ix = dx - 1;
+            if (iy > dy - 1) iy = dy - 1;
+            if (iz > dz - 1) iz = dz - 1;
+            const long long ni = ((long long)ix * dy + iy) * dz + iz;
+            const float rgb = color_vol[ni];
+            const float b = floorf(rgb / (256 * 256));
+            const float g = floorf((rgb - b * 256 * 256) / 256);
+            const float r = rgb - b * 256 * 256 - g * 256;
+            const long long vtx = 3 * n_tris + k;
+            colors[3 * vtx + 0] = (uint8_t)((long long)floorf(r) & 255);
+            colors[3 * vtx + 1] = (uint8_t)((long long)floorf(g) & 255);
+            colors[3 * vtx + 2] = (uint8_t)((long long)floorf(b) & 255);
+            rem_out[vtx] = rem_vol[ni];
+            for (int a = 0; a < 3; ++a) verts[3 * vtx + a] = pv[a] * voxel_size + vol_origin[a];
+            faces[vtx] = (int)vtx;
+          }
+        }
+      }
+  return n_tris;
+}
+
 int vlo_abi_version(void) { return 1; }

@@ -1,0 +1,117 @@
+"""The reference-shaped call surface (lidar_transfer_b200/auxiliary) on the GPU: same calls, same results."""
+import os
+
+import numpy as np
+import pytest
+
+from lidar_transfer_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
+
+
+@pytest.fixture(scope="module")
+def G():
+  return np.load(GOLDEN)
+
+
+def test_c_trace_matches_reference_golden(engine, G):
+  """C_Trace with the .pyx signature on the golden meshes: ids / labels equal, ranges <= 1e-4 relative
+  (the golden comes from the reference C++ build, whose normalise uses x86 rsqrtps)."""
+  from lidar_transfer_b200.auxiliary.raytracer import RayTracerCython as rtc
+  for tag in ("s", "m", "o"):
+    seed, n_side, n_boxes, H, W = (int(v) for v in G["trace_%s_args" % tag])
+    sc = synth.make_scene(seed, n_side=n_side, n_boxes=n_boxes)
+    rays = G["trace_%s_rays" % tag].reshape(-1).copy()
+    ep, ec = np.zeros(3 * H * W, np.float32), np.zeros(3 * H * W, np.int32)
+    rg, rm = np.zeros(H * W, np.float32), np.zeros(H * W, np.float32)
+    assert rtc.C_Trace(rays, G["trace_%s_origin" % tag].copy(), sc["verts"].reshape(-1), sc["faces"].reshape(-1),
+                       sc["colors"].reshape(-1), sc["rem"], ep, ec, rg, rm, H, W) is None
+    ref_r, ref_c = G["trace_%s_range" % tag], G["trace_%s_endcolors" % tag]
+    hit = ref_r > 0
+    assert np.array_equal(rg > 0, hit)
+    assert (ec == ref_c).all(axis=None) or (ec.reshape(-1, 3) == ref_c.reshape(-1, 3)).all(axis=1).mean() > 0.999
+    assert (np.abs(rg[hit] - ref_r[hit]) / ref_r[hit]).max() <= 1e-4
+    assert np.abs(ep - G["trace_%s_endpoints" % tag]).max() <= 1e-4 * max(1.0, np.abs(ep).max())
+    same_label = (ec.reshape(-1, 3) == ref_c.reshape(-1, 3)).all(axis=1)
+    assert np.allclose(rm[same_label], G["trace_%s_endrem" % tag][same_label], rtol=0, atol=0.35)
+
+
+def test_c_trace_rejects_what_cython_rejects(engine):
+  from lidar_transfer_b200.auxiliary.raytracer import RayTracerCython as rtc
+  sc = synth.make_scene(3, n_side=8, n_boxes=0)
+  H, W = 2, 4
+  f32, i32 = np.float32, np.int32
+  good = dict(rays=np.ones(3 * H * W, f32), origin=np.zeros(3, f32), verts=sc["verts"].reshape(-1),
+              faces=sc["faces"].reshape(-1), colors=sc["colors"].reshape(-1), rem=sc["rem"],
+              ep=np.zeros(3 * H * W, f32), ec=np.zeros(3 * H * W, i32), rg=np.zeros(H * W, f32), rm=np.zeros(H * W, f32))
+  call = lambda d: rtc.C_Trace(d["rays"], d["origin"], d["verts"], d["faces"], d["colors"], d["rem"], d["ep"], d["ec"],
+                               d["rg"], d["rm"], H, W)
+  call(good)
+  for key, bad in (("rays", good["rays"].astype(np.float64)), ("faces", good["faces"].astype(np.int64)),
+                   ("verts", sc["verts"]), ("ep", np.zeros(6 * H * W, f32)[::2])):
+    d = dict(good); d[key] = bad
+    with pytest.raises(ValueError):
+      call(d)
+
+
+def test_throw_rays_at_mesh_glue_matches_reference_golden(engine, G):
+  """TSDFVolume.throw_rays_at_mesh on a known mesh: the 7-tuple, shapes and dtypes of fusion_lidar.py:452-455."""
+  import torch
+  from lidar_transfer_b200.auxiliary import fusion_lidar as fl
+  seed, n_side, n_boxes, H, W = (int(v) for v in G["glue_args"])
+  sc = synth.make_scene(seed, n_side=n_side, n_boxes=n_boxes)
+  tv = fl.TSDFVolume.__new__(fl.TSDFVolume)
+  dev = "cuda"
+  tv._mesh = dict(verts=torch.from_numpy(sc["verts"]).to(dev), faces=torch.from_numpy(sc["faces"]).to(dev), norms=None,
+                  colors=torch.from_numpy(sc["colors"].astype(np.uint8)).to(dev), rem=torch.from_numpy(sc["rem"]).to(dev))
+  from lidar_transfer_b200.rays import create_rays
+  out = tv.throw_rays_at_mesh(create_rays(3.0, -25.0, H, W), np.zeros(3, np.float32), H, W, None)
+  names = ("endpoints", "ray_colors", "verts", "colors", "faces", "range_image", "rem_image")
+  for name, a in zip(names, out):
+    g = G["glue_" + name]
+    assert a.shape == g.shape and a.dtype == g.dtype, name
+  assert np.array_equal(out[1], G["glue_ray_colors"])
+  hit = G["glue_range_image"] > 0
+  assert np.array_equal(out[5] > 0, hit)
+  assert (np.abs(out[5][hit] - G["glue_range_image"][hit]) / G["glue_range_image"][hit]).max() <= 1e-4
+  assert np.array_equal(out[6].view(np.int32), G["glue_rem_image"].view(np.int32))
+
+
+def test_tsdf_volume_pipeline_vs_oracle(engine, oracle):
+  """deform('mergemesh') core: projection -> TSDFVolume -> integrate -> marching cubes -> ray cast, against the
+  same chain of oracle restatements."""
+  from lidar_transfer_b200.auxiliary import fusion_lidar as fl
+  from lidar_transfer_b200.rays import create_rays
+  pts, labels = synth.make_scan_points(11, 60000)
+  H, W, fu, fd = 64, 1024, 3.0, -25.0
+  pr = oracle.project(pts[:, :3].astype(np.float64), pts[:, 3], labels, fu, fd, H, W)
+  vox = 0.2
+  bnds = np.array([[-20, 20], [-20, 20], [-3, 2]], np.float64)
+  proj_label3 = np.zeros((H, W, 3))
+  proj_label3[:, :, 0] = pr["proj_label"]
+  tv = fl.TSDFVolume(bnds.copy(), vox, fu, fd)
+  tv.integrate(proj_label3, pr["range_image"], pr["proj_remissions"], np.eye(3), obs_weight=1.)
+  tH, tW = 32, 512
+  rays = create_rays(fu, fd, tH, tW)
+  origin = np.zeros(3, np.float32)
+  ep, rc, verts, colors, faces, rng_im, rem_im = tv.throw_rays_at_mesh(rays, origin, tH, tW, None)
+  assert ep.shape == (tH * tW, 3) and rc.shape == (tH * tW, 3) and rng_im.shape == (tH, tW) and rem_im.shape == (tH, tW)
+  assert faces.shape[0] > 20000 and verts.shape[0] == 3 * faces.shape[0] and colors.dtype == np.uint8
+  # oracle chain
+  dim = np.ceil((bnds[:, 1] - bnds[:, 0]) / vox).astype(int)
+  vol = oracle.tsdf_new_volume(dim)
+  oracle.tsdf_integrate(vol, bnds[:, 0].astype(np.float32), vox, oracle.label_to_color_im(pr["proj_label"]),
+                        pr["range_image"], pr["proj_remissions"], fu, fd)
+  om = oracle.mesh_extract(vol["tsdf"], vol["color"], vol["rem"], np.float32(vox), bnds[:, 0].astype(np.float32))
+  ot = oracle.trace(rays, origin, om["verts"], om["faces"], om["colors"].astype(np.int32), om["rem"], tH, oracle.MIN_ID_TIES)
+  # the two TSDF volumes may differ in <= 1e-4 of the voxels (libm ulps at pixel borders): compare images loosely
+  assert abs(faces.shape[0] - om["faces"].shape[0]) <= 1e-3 * om["faces"].shape[0]
+  ref_r = ot["range"].reshape(tH, tW)
+  both = (ref_r > 0) & (rng_im > 0)
+  assert ((ref_r > 0) != (rng_im > 0)).mean() < 1e-3
+  assert both.mean() > 0.3
+  close = np.abs(rng_im[both] - ref_r[both]) <= 1e-4 * ref_r[both]
+  assert close.mean() > 0.999
+  lab, ref_lab = rc[:, 2].reshape(tH, tW), ot["endcolors"].reshape(-1, 3)[:, 2].reshape(tH, tW)
+  assert (lab[both] == ref_lab[both]).mean() > 0.999
