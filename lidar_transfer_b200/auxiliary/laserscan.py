@@ -1,0 +1,507 @@
+"""Drop-in for the reference's `auxiliary.laserscan` (auxiliary/laserscan.py): LaserScan, SemLaserScan,
+MultiSemLaserScan and compare() with the attribute contract lidar_deform.py:393-452 and the visualiser read
+(SURVEY.md appendix D).  Scan files, poses and class filters stay on the host in numpy like the reference;
+the hot path runs on the device through libvlidar:
+
+  do_range_projection_new('depth') + do_label_projection_new   laserscan.py:294-391, 672-676 -> vl_project
+  deform('mesh' | 'mergemesh')                                  laserscan.py:863-1012        -> vl_tsdf_* , vl_mesh_*,
+                                                                                               vl_bvh_build, vl_trace
+  create_rays                                                   laserscan.py:1092-1119       -> rays.create_rays
+  write                                                         laserscan.py:1121-1178       -> same bytes, vectorised
+
+Host-side differences that do not change results: no per-point Python loops, no test.ply side effect unless
+`MultiSemLaserScan.write_ply` is set (the reference rewrites ./test.ply on every mergemesh scan, :1010).
+"""
+import os
+
+import numpy as np
+
+from .. import engine
+from ..rays import create_rays as _create_rays
+from . import fusion_lidar as fl
+from .np_ioueval import iouEval
+
+
+class LaserScan:
+  """Class that contains LaserScan with x,y,z,r"""
+  EXTENSIONS_SCAN = ['.bin']
+
+  def __init__(self, H, W, transformation=None, beam_angles=None):
+    self.proj_H = H
+    self.proj_W = W
+    if transformation is None or (not isinstance(transformation, np.ndarray) and not transformation):
+      transformation = np.eye(4)
+    self.transformation = np.array(transformation).reshape(4, 4)
+    self.reset()
+    self.beam_angles = beam_angles
+    self.pose = np.eye(4)
+
+  def reset(self):
+    H, W = self.proj_H, self.proj_W
+    self.points = np.zeros((0, 3), dtype=np.float32)
+    self.remissions = np.zeros((0, ), dtype=np.float32)
+    self.back_points = np.zeros((0, 3), dtype=np.float32)
+    self.proj_range = np.full((H, W), -1, dtype=np.float32)
+    self.proj_xyz = np.full((H, W, 3), -1, dtype=np.float32)
+    self.proj_remissions = np.full((H, W), -1, dtype=np.float32)
+    self.proj_idx = np.full((H, W), -1, dtype=np.int32)
+    self.proj_x = np.zeros((0, 1), dtype=np.float32)
+    self.proj_y = np.zeros((0, 1), dtype=np.float32)
+    self.unproj_range = np.zeros((0, 1), dtype=np.float32)
+    self.proj_mask = np.zeros((H, W), dtype=np.int32)
+
+  def size(self):
+    return self.points.shape[0]
+
+  def __len__(self):
+    return self.size()
+
+  # ---- IO + rigid transforms (host, float64 like the reference) -------------------------------
+  @staticmethod
+  def _read_bin(filename):
+    if not isinstance(filename, str):
+      raise TypeError("Filename should be string type, but was {type}".format(type=str(type(filename))))
+    return np.fromfile(filename, dtype=np.float32).reshape((-1, 4))
+
+  def open_scan(self, filename, fov_up, fov_down):
+    self.reset()
+    if not isinstance(filename, str):
+      raise TypeError("Filename should be string type, but was {type}".format(type=str(type(filename))))
+    if not any(filename.endswith(ext) for ext in self.EXTENSIONS_SCAN):
+      raise RuntimeError("Filename extension is not valid scan file.")
+    scan = self._read_bin(filename)
+    self.points = scan[:, 0:3]
+    self.remissions = scan[:, 3]
+
+  def open_scan_append(self, filename, pose, fov_up, fov_down):
+    scan = self._read_bin(filename)
+    hom = np.ones((scan.shape[0], 4))
+    hom[:, 0:3] = scan[:, 0:3]
+    t_points = np.matmul(self.transformation, np.matmul(pose.reshape((-1, 4)), hom.T)).T
+    if self.points.size == 0:
+      self.points, self.remissions = t_points[:, 0:3], scan[:, 3]
+    else:
+      self.points = np.concatenate((self.points, t_points[:, 0:3]))
+      self.remissions = np.concatenate((self.remissions, scan[:, 3]))
+
+  def apply_transformation(self, transformation):
+    hom = np.ones((self.points.shape[0], 4))
+    hom[:, 0:3] = self.points[:, 0:3]
+    self.points = np.matmul(transformation, hom.T).T[:, 0:3]
+
+  def apply_pose(self):
+    self.apply_transformation(self.pose)
+
+  def apply_inv_pose(self):
+    self.apply_transformation(np.linalg.inv(self.pose))
+
+  def remove_points(self, keep_index):
+    self.points = self.points[keep_index]
+    self.remissions = self.remissions[keep_index]
+    self.label = self.label[keep_index]
+    self.label_color = self.label_color[keep_index]
+
+  # ---- projections ---------------------------------------------------------------------------
+  def _angles(self, fov_up, fov_down, remove):
+    """Shared front half of both projections (laserscan.py:207-257 / 300-345): depth, image coordinates,
+    optional FOV filter.  float64 numpy, used by the host-side (comparison-only) projection."""
+    fov_up = fov_up / 180.0 * np.pi
+    fov_down = fov_down / 180.0 * np.pi
+    fov = abs(fov_down) + abs(fov_up)
+    depth = np.linalg.norm(self.points, 2, axis=1)
+    keep = depth != 0
+    if remove:
+      depth = depth[keep]
+      self.remove_points(keep)
+    yaw = -np.arctan2(self.points[:, 1], self.points[:, 0])
+    pitch = np.arcsin(self.points[:, 2] / depth)
+    if self.beam_angles:
+      ba = np.asarray(self.beam_angles)
+      pitch = ba[np.abs(pitch[:, None] - ba[None, :]).argmin(axis=1)]
+    proj_x = 0.5 * (yaw / np.pi + 1.0)
+    proj_y = 1.0 - (pitch + abs(fov_down)) / fov
+    if remove:
+      keep = (proj_y >= 0) & (proj_y <= 1)
+      self.remove_points(keep)
+      depth, proj_y, proj_x = depth[keep], proj_y[keep], proj_x[keep]
+    return depth, proj_x * self.proj_W, proj_y * self.proj_H
+
+  def _clamp(self, proj_x, proj_y):
+    px = np.maximum(0, np.minimum(self.proj_W - 1, np.floor(proj_x))).astype(np.int32)
+    py = np.maximum(0, np.minimum(self.proj_H - 1, np.floor(proj_y))).astype(np.int32)
+    return px, py
+
+  def do_range_projection(self, fov_up, fov_down, remove=False):
+    """The older sort-and-scatter projection (laserscan.py:202-292) lidar_deform.py:408 applies to the
+    single SOURCE scan that compare() measures against.  Host numpy, like the reference: it is not on the
+    synthesis path.  Far-to-near scatter: the nearest point of a pixel is written last."""
+    depth, proj_x, proj_y = self._angles(fov_up, fov_down, remove)
+    px, py = self._clamp(proj_x, proj_y)
+    self.unproj_range = np.copy(depth)
+    order = np.argsort(depth)[::-1]
+    self.depth = depth[order]
+    px, py = px[order], py[order]
+    self.proj_range[py, px] = self.depth
+    self.proj_xyz[py, px] = self.points[order]
+    self.proj_remissions[py, px] = self.remissions[order]
+    self.proj_idx[py, px] = np.arange(depth.shape[0])[order]
+    self.proj_x, self.proj_y = px, py
+    self.proj_mask = (self.proj_idx > 0).astype(np.float32)
+
+  def do_range_projection_new(self, fov_up, fov_down, remove=False, method="depth"):
+    """Nearest-point-per-pixel projection (laserscan.py:294-391) as one atomicMin scatter on the device."""
+    if method != "depth":
+      raise NotImplementedError("only method='depth' (the one deform() uses, laserscan.py:952) runs on the device")
+    if self.beam_angles:
+      raise NotImplementedError("beam_angles snapping (laserscan.py:322-327) is not on the device path yet")
+    pts = np.ascontiguousarray(self.points, np.float64)
+    out = engine.project(pts, np.ascontiguousarray(self.remissions, np.float32),
+                         np.ascontiguousarray(self.label).astype(np.uint32), fov_up, fov_down, self.proj_H, self.proj_W,
+                         remove=remove)
+    keep = out["keep"].cpu().numpy()
+    if not remove:  # the reference always drops depth == 0 points (:307-309), FOV filtering is optional
+      keep = np.linalg.norm(pts, 2, axis=1) != 0
+    self.remove_points(keep)
+    self._fov = (fov_up, fov_down)
+    self.index = out["index"].cpu().numpy()
+    self.range_image = out["range_image"].cpu().numpy()
+    self.proj_remissions = out["proj_remissions"].cpu().numpy()
+    self._proj_label_dev = out["proj_label"].cpu().numpy()
+    mask = self.index >= 0
+    self.label_image = np.zeros((self.proj_H, self.proj_W, 1))
+    self.label_image[mask, 0] = self.label[self.index[mask]]
+    self.label_color_image = np.zeros((self.proj_H, self.proj_W, 3))
+    self.label_color_image[mask] = self.label_color[self.index[mask]]
+    self.proj_range = self.range_image
+    self.unproj_range = np.linalg.norm(self.points, 2, axis=1)
+    # per-pixel image coordinates of the winning point (float and clamped), laserscan.py:384-388
+    w = self.points[self.index]  # index -1 wraps to the last point, exactly like the reference's fancy index
+    depth = np.linalg.norm(w, 2, axis=2)
+    fu, fd = fov_up / 180.0 * np.pi, fov_down / 180.0 * np.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+      self.proj_x_float = 0.5 * (-np.arctan2(w[..., 1], w[..., 0]) / np.pi + 1.0) * self.proj_W
+      self.proj_y_float = (1.0 - (np.arcsin(w[..., 2] / depth) + abs(fd)) / (abs(fd) + abs(fu))) * self.proj_H
+    self.proj_x, self.proj_y = self._clamp(self.proj_x_float, self.proj_y_float)
+
+  def do_reverse_projection_new(self, fov_up, fov_down, preserve_float=False):
+    """Pixel + depth -> xyz (laserscan.py:475-501), the `cp` adaption's back projection."""
+    fov_up = fov_up / 180.0 * np.pi
+    fov_down = fov_down / 180.0 * np.pi
+    fov = abs(fov_down) + abs(fov_up)
+    depth = self.range_image
+    if preserve_float:
+      proj_x, proj_y = self.proj_x_float / self.proj_W, self.proj_y_float / self.proj_H
+    else:
+      proj_x, proj_y = self.proj_x / self.proj_W, self.proj_y / self.proj_H
+    yaw = (proj_x * 2 - 1.0) * np.pi
+    pitch = np.pi / 2 - (1.0 * fov - proj_y * fov - abs(fov_down))
+    self.back_points = np.array([depth * np.sin(pitch) * np.cos(-yaw), depth * np.sin(pitch) * np.sin(-yaw),
+                                 depth * np.cos(pitch)]).transpose(1, 2, 0).reshape(-1, 3)
+
+
+class SemLaserScan(LaserScan):
+  """Class that contains LaserScan with x,y,z,r,label,color_label"""
+  EXTENSIONS_LABEL = ['.label']
+
+  def __init__(self, H, W, nclasses, color_dict=None, transformation=None, beam_angles=None):
+    super(SemLaserScan, self).__init__(H, W, transformation, beam_angles)
+    self.reset()
+    self.nclasses = nclasses
+    self.color_dict = color_dict
+    max_key = max([key + 1 for key in color_dict] + [0])
+    self.color_lut = np.zeros((max_key + 100, 3), dtype=np.float32)
+    for key, value in color_dict.items():
+      self.color_lut[key] = np.array(value, np.float32) / 255.0
+
+  def reset(self):
+    super(SemLaserScan, self).reset()
+    self.label = np.zeros((0, ), dtype=np.uint32)
+    self.label_image = np.zeros((0, ), dtype=np.uint32)
+    self.label_color_image = np.zeros((0, 3), dtype=np.uint32)
+    self.label_color = np.zeros((0, 3), dtype=np.float32)
+    self.proj_label = np.zeros((self.proj_H, self.proj_W), dtype=np.int32)
+    self.proj_color = np.zeros((self.proj_H, self.proj_W, 3), dtype=float)
+
+  @staticmethod
+  def _read_label(filename, extensions):
+    if not isinstance(filename, str):
+      raise TypeError("Filename should be string type, but was {type}".format(type=str(type(filename))))
+    if not any(filename.endswith(ext) for ext in extensions):
+      raise RuntimeError("Filename extension is not valid label file.")
+    return np.fromfile(filename, dtype=np.uint32).reshape((-1))
+
+  def open_label(self, filename):
+    label = self._read_label(filename, self.EXTENSIONS_LABEL)
+    if label.shape[0] != self.points.shape[0]:
+      raise ValueError("Scan and Label don't contain same number of points")
+    self.label = label & 0xFFFF  # semantic label in lower half
+
+  def open_label_append(self, filename):
+    label = self._read_label(filename, self.EXTENSIONS_LABEL)
+    self.label = label if self.label.size == 0 else np.concatenate((self.label, label))
+
+  def set_label(self, label):
+    if not isinstance(label, np.ndarray):
+      raise TypeError("Label should be numpy array")
+    if label.shape[0] != self.points.shape[0]:
+      raise ValueError("Scan and Label don't contain same number of points")
+    self.label = label
+    self.do_label_projection()
+
+  def colorize(self):
+    self.label_color = self.color_lut[self.label].reshape((-1, 3))
+
+  def do_label_projection(self):
+    mask = self.proj_idx >= 0
+    self.proj_label[mask] = self.label[self.proj_idx[mask]]
+    self.proj_color[mask] = self.color_lut[self.label[self.proj_idx[mask]]]
+
+  def do_label_projection_new(self):
+    mask = self.index >= 0
+    self.proj_label[mask] = self.label[self.index[mask]]
+    self.proj_color[mask] = self.color_lut[self.label[self.index[mask]]]
+
+  def remove_class(self, class_index):
+    self.remove_classes([class_index])
+
+  def remove_classes(self, classes):
+    keep_index = ~np.isin(self.label, np.asarray(list(classes), dtype=np.int64))
+    self.points = self.points[keep_index]
+    self.remissions = self.remissions[keep_index]
+    self.label = self.label[keep_index]
+    self.label_color = self.label_color[keep_index]
+
+  def get_bnds(self):
+    return np.concatenate((np.amin(self.points, axis=0).reshape(3, 1), np.amax(self.points, axis=0).reshape(3, 1)), axis=1)
+
+  def _label_map(self, sequential):
+    label_map = np.full(self.proj_color.shape[:2], -1, dtype=int)
+    for i, (idx, rgb) in enumerate(self.color_dict.items()):
+      label_map[((self.proj_color * 255).astype(np.uint8) == rgb).all(2)] = i if sequential else idx
+    return label_map
+
+  def get_label_map(self):
+    return self._label_map(True)
+
+  def convert_color_to_label(self):
+    return self._label_map(False)
+
+
+class MultiSemLaserScan():
+  """Class that contains multiple LaserScans with x,y,z,r,label,color_label"""
+  write_ply = False  # the reference writes ./test.ply after every mergemesh deform (laserscan.py:1010)
+
+  def __init__(self, source_config, target_config, nscans, nclasses, ignore_classes, moving_classes, color_dict=None,
+               transformation=None, preserve_float=False, voxel_size=0.1, vol_bnds=None):
+    self.H = source_config["beams"]
+    self.W = int(source_config["fov_hor"] / source_config["angle_res_hor"])
+    self.fov_up, self.fov_down = source_config["fov_up"], source_config["fov_down"]
+    self.beam_angles = sorted(source_config['beam_angles']) if source_config.get('beam_angles') else None
+    self.t_H = target_config["beams"]
+    self.t_W = int(target_config["fov_hor"] / target_config["angle_res_hor"])
+    self.t_fov_up, self.t_fov_down = target_config["fov_up"], target_config["fov_down"]
+    self.t_beam_angles = self.beam_angles  # sic: the reference reads the SOURCE config here (laserscan.py:747)
+    self.nscans, self.nclasses = nscans, nclasses
+    self.ignore_classes, self.moving_classes = ignore_classes, moving_classes
+    self.color_dict, self.transformation = color_dict, transformation
+    self.preserve_float, self.voxel_size, self.vol_bnds = preserve_float, voxel_size, vol_bnds
+    self.poses = np.zeros((nscans, 4, 4), dtype=np.float32)
+    self.scans = [SemLaserScan(self.H, self.W, nclasses, color_dict, transformation, self.beam_angles)
+                  for _ in range(self.nscans)]
+    self.reset()
+
+  def reset(self):
+    for scan in self.scans:
+      scan.reset()
+
+  def get_scan(self, idx):
+    return self.scans[idx]
+
+  def open_multiple_scans(self, scan_names, label_names, poses, idx):
+    self.reset()
+    if self.nscans > 1:
+      n_prev = self.nscans // 2
+      rel = np.arange(-n_prev, self.nscans - n_prev)
+      rel = np.insert(rel[rel != 0], 0, 0)  # primary scan first (it keeps its moving classes)
+    else:
+      rel = np.zeros(1, dtype=int)
+    for i, scan in enumerate(self.scans):
+      scan_idx = idx + rel[i]
+      if self.nscans > 1:
+        print("Open scan %d/%d %d:%d" % (i + 1, self.nscans, rel[i], scan_idx + 1))
+      scan.open_scan(scan_names[scan_idx], self.fov_up, self.fov_down)
+      scan.open_label(label_names[scan_idx])
+      scan.colorize()
+      self.poses[i] = scan.pose = poses[scan_idx]
+      scan.apply_pose()
+      if i != 0:
+        scan.remove_classes(self.moving_classes)
+      scan.remove_classes(self.ignore_classes)
+
+  def _merge(self, H, W, beam_angles, pose):
+    m = SemLaserScan(H, W, self.nclasses, self.color_dict, self.transformation, beam_angles)
+    m.reset()
+    m.pose = pose
+    m.points = np.concatenate([m.points] + [s.points for s in self.scans])
+    m.remissions = np.concatenate([m.remissions] + [s.remissions for s in self.scans])
+    m.label = np.concatenate([m.label] + [s.label for s in self.scans])
+    m.label_color = np.concatenate([m.label_color] + [s.label_color for s in self.scans])
+    return m
+
+  def _cast(self, tsdf_vol, lut):
+    """Ray-cast the target beam pattern against the fused volume and fill the attributes write()/compare() read."""
+    rays = self.create_rays(self.t_fov_up, self.t_fov_down, self.t_H, self.t_W)
+    origin = np.array([0, 0, 0]).astype(np.float32)
+    self.back_points, label_color, verts, colors, faces, self.proj_range, self.proj_remissions = \
+        tsdf_vol.throw_rays_at_mesh(rays, origin, self.t_H, self.t_W, lut)
+    self.proj_color = label_color.reshape(self.t_H, self.t_W, 3)
+    self.label_color = lut[label_color[:, 2]]
+    self.label_image = np.copy(self.proj_color[:, :, 2])
+    self.proj_color = lut[self.label_image]
+    return verts, lut[colors[:, 2]], faces
+
+  def deform(self, adaption, poses, idx):
+    """ Deforms laserscan with specified adaption method and transformation (laserscan.py:819-1021) """
+    self.adaption = adaption
+    if adaption == 'cp':  # closest point: project into the TARGET image, project back
+      self.merged = m = self._merge(self.t_H, self.t_W, self.t_beam_angles, poses[idx])
+      m.apply_inv_pose()
+      m.do_range_projection_new(self.t_fov_up, self.t_fov_down, remove=True)
+      m.do_label_projection_new()
+      m.do_reverse_projection_new(self.t_fov_up, self.t_fov_down, preserve_float=self.preserve_float)
+      self.back_points, self.proj_range, self.proj_remissions = m.back_points, m.proj_range, m.proj_remissions
+      self.proj_color, self.label_image, self.index = m.proj_color, m.label_image, m.index
+      self.label_color = m.label_color_image.reshape(-1, 3)
+      return [], [], []
+
+    elif adaption == 'mesh':  # one range image per scan, all fused into one volume
+      vol_bnds = self.vol_bnds
+      inv = np.linalg.inv(poses[idx])
+      for i, scan in enumerate(self.scans):
+        print("Create range image %d/%d" % (i + 1, self.nscans))
+        scan.apply_transformation(inv)
+        scan.do_range_projection_new(self.fov_up, self.fov_down, remove=True)
+        scan.do_label_projection_new()
+      print("Initializing voxel volume...")
+      tsdf_vol = fl.TSDFVolume(vol_bnds, voxel_size=self.voxel_size, fov_up=self.fov_up, fov_down=self.fov_down)
+      for i, scan in enumerate(self.scans):
+        print("Fusing scan %d/%d" % (i + 1, self.nscans))
+        proj_label3 = np.zeros(scan.proj_color.shape)
+        proj_label3[:, :, 0] = scan.proj_label
+        tsdf_vol.integrate(proj_label3, scan.proj_range, scan.proj_remissions, np.eye(3), obs_weight=1.)
+      return self._cast(tsdf_vol, self.scans[0].color_lut)
+
+    elif adaption == 'mergemesh':  # all scans merged into ONE range image (source size, TARGET fov), then fused
+      self.merged = m = self._merge(self.H, self.W, self.beam_angles, poses[idx])
+      m.apply_inv_pose()
+      m.do_range_projection_new(self.t_fov_up, self.t_fov_down, remove=True)
+      m.do_label_projection_new()
+      merged_bnds = np.rint(m.get_bnds()).astype(int)
+      vol_bnds = self.vol_bnds  # clipped IN PLACE like the reference (the caller's array is shared across scans)
+      vol_bnds[:, 0] = np.maximum(vol_bnds[:, 0], merged_bnds[:, 0])
+      vol_bnds[:, 1] = np.minimum(vol_bnds[:, 1], merged_bnds[:, 1])
+      print("Initializing voxel volume...")
+      tsdf_vol = fl.TSDFVolume(vol_bnds, voxel_size=self.voxel_size, fov_up=self.t_fov_up, fov_down=self.t_fov_down)
+      proj_label3 = np.zeros(m.proj_color.shape)
+      proj_label3[:, :, 0] = m.proj_label
+      tsdf_vol.integrate(proj_label3, m.proj_range, m.proj_remissions, np.eye(3), obs_weight=1.)
+      print("target dim:", self.t_H, self.t_W)
+      verts, colors, faces = self._cast(tsdf_vol, m.color_lut)
+      if self.write_ply:
+        fl.meshwrite("test.ply", verts, faces, verts, colors[..., ::-1] * 255)
+      return verts, colors, faces
+
+    elif adaption == 'catmesh':
+      raise NotImplementedError("'catmesh' is a stub in the reference too (laserscan.py:1014-1016)")
+    else:
+      raise ValueError("Adaption method not recognized or not defined: %r" % (adaption,))
+
+  def get_label_map(self):
+    proj_color = self.label_color.reshape(self.H, self.W, 3)
+    label_map = np.full(proj_color.shape[:2], -1, dtype=int)
+    for i, (idx, rgb) in enumerate(self.color_dict.items()):
+      label_map[(proj_color.astype(np.uint8) == rgb).all(2)] = i
+    return label_map
+
+  def create_rays(self, fov_up, fov_down, H, W):
+    return _create_rays(fov_up, fov_down, H, W)
+
+  def write(self, out_dir, idx, write_png=False):
+    """KITTI .bin (float32 x,y,z,remission) + .label (uint32) of the re-rendered scan; the reference's filter
+    rules (laserscan.py:1133-1158) with array writes instead of per-point struct.pack."""
+    if write_png:
+      raise NotImplementedError("write_png references an undefined name in the reference (laserscan.py:1124-1126)")
+    if self.adaption == 'cp':
+      back_points = self.merged.back_points.reshape(-1, 3)
+      label_image = self.merged.label_image.reshape(-1)
+      remissions = self.merged.proj_remissions.reshape(-1)
+      valid = self.merged.index.reshape(-1,) > 0
+      back_points, remissions = back_points[valid], remissions[valid]
+      label_image = label_image[valid].astype(np.int32)
+    else:
+      back_points = self.back_points.reshape(-1, 3)
+      label_image = self.label_image.reshape(-1)
+      remissions = self.proj_remissions.reshape(-1)
+    valid = label_image >= 0
+    back_points, remissions, label_image = back_points[valid], remissions[valid], label_image[valid].astype(np.int32)
+    keep = np.sum(back_points, axis=1) != 0  # remove points with (0, 0, 0)
+    back_points, remissions, label_image = back_points[keep], remissions[keep], label_image[keep]
+    assert back_points.shape[0] == label_image.shape[0]
+    rec = np.empty((back_points.shape[0], 4), dtype="<f4")
+    rec[:, 0:3] = back_points
+    rec[:, 3] = remissions
+    rec.tofile(os.path.join(out_dir, "velodyne", str(idx).zfill(6) + ".bin"))
+    label_image.astype("<u4").tofile(os.path.join(out_dir, "labels", str(idx).zfill(6) + ".label"))
+
+
+def compare(scan_source, scan_target):
+  """ Compare two scans by examine labels, range and remissions (laserscan.py:1181-1301): the identity
+  re-render self-check.  Returns (label_diff, range_diff, remissions_diff, m_iou, m_acc, MSE). """
+  source_color = np.copy(scan_source.proj_color)
+  source_label = np.copy(scan_source.proj_label)
+  if scan_target.adaption == 'cp':
+    target_label = np.copy(scan_target.merged.proj_label)
+    target_color = np.copy(scan_target.merged.proj_color)
+  else:
+    target_color = np.copy(scan_target.proj_color)
+    target_label = np.copy(scan_target.label_image)
+  assert source_color.size == target_color.size
+  assert source_label.size == target_label.size
+
+  # no data (black) in the source scan masks both; source background masks the target
+  black = np.sum(source_color, axis=2) == 0
+  source_label[black] = 0
+  target_label[black] = 0
+  target_color[black] = 0
+  bg_label = source_label == 0
+  target_label[bg_label] = 0
+  target_color[bg_label] = 0
+  label_diff = abs(source_color - target_color)
+
+  # compress the labels that occur to 0..k-1 (sequentially, in place, like the reference :1217-1223)
+  for i, value in enumerate(np.union1d(np.unique(source_label), np.unique(target_label))):
+    mask_source, mask_target = source_label == value, target_label == value
+    source_label[mask_source] = i
+    target_label[mask_target] = i
+  present = np.union1d(np.unique(source_label), np.unique(target_label))
+  empty = np.isin(np.arange(scan_source.nclasses), present, invert=True)
+  ev = iouEval(scan_source.nclasses, np.arange(scan_source.nclasses)[empty])
+  ev.addBatch(target_label, source_label)
+  m_iou, iou = ev.getIoU()
+  print("IoU class: ", (iou * 100).astype(int))
+  m_acc = ev.getacc()
+  print("IoU: ", m_iou)
+  print("Acc: ", m_acc)
+
+  source_range, target_range = np.copy(scan_source.proj_range), np.copy(scan_target.proj_range)
+  source_range[bg_label] = 0
+  target_range[bg_label] = 0
+  range_diff = (source_range - target_range) ** 2
+  MSE = range_diff.sum() / range_diff.size
+  print("MSE: ", MSE)
+
+  source_rem, target_rem = np.copy(scan_source.proj_remissions), np.copy(scan_target.proj_remissions)
+  source_rem[bg_label] = 0
+  target_rem[bg_label] = 0
+  remissions_diff = (source_rem - target_rem) ** 2
+  return label_diff, range_diff, remissions_diff, m_iou, m_acc, MSE

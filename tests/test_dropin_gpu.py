@@ -115,3 +115,86 @@ def test_tsdf_volume_pipeline_vs_oracle(engine, oracle):
   assert close.mean() > 0.999
   lab, ref_lab = rc[:, 2].reshape(tH, tW), ot["endcolors"].reshape(-1, 3)[:, 2].reshape(tH, tW)
   assert (lab[both] == ref_lab[both]).mean() > 0.999
+
+
+def _lut(G):
+  lut = {0: [0, 0, 0], 1: [0, 0, 255], 10: [245, 150, 100], 40: [255, 0, 255], 48: [75, 0, 75], 50: [0, 200, 255],
+         70: [0, 175, 0], 72: [80, 240, 150]}
+  for k in np.unique(G["scan_label"]):
+    lut.setdefault(int(k), [int(k) % 251 + 1, 7, 9])
+  return lut
+
+
+@pytest.mark.parametrize("tag", ["src", "tgt"])
+def test_semlaserscan_projection_matches_reference_golden(engine, G, tag):
+  """SemLaserScan.do_range_projection_new + do_label_projection_new through vl_project vs the reference's Python."""
+  from lidar_transfer_b200.auxiliary.laserscan import SemLaserScan
+  fu, fd, H, W = G["proj_%s_args" % tag]
+  s = SemLaserScan(int(H), int(W), 20, color_dict=_lut(G))
+  s.points, s.remissions = G["proj_%s_points_f64" % tag].copy(), G["proj_%s_rem_in" % tag].copy()
+  s.label = G["proj_%s_label_in" % tag].copy()
+  s.colorize()
+  s.do_range_projection_new(fu, fd, remove=True)
+  s.do_label_projection_new()
+  assert s.points.shape[0] == int(G["proj_%s_n_kept" % tag][0]) and np.array_equal(s.points, G["proj_%s_kept_points" % tag])
+  assert np.array_equal(s.index, G["proj_%s_index" % tag]) and np.array_equal(s.proj_label, G["proj_%s_label" % tag])
+  assert np.array_equal(s.range_image.view(np.int32), G["proj_%s_range" % tag].view(np.int32))
+  assert np.array_equal(s.proj_remissions.view(np.int32), G["proj_%s_rem" % tag].view(np.int32))
+  for pf in (False, True):
+    s.do_reverse_projection_new(fu, fd, preserve_float=pf)
+    assert np.allclose(s.back_points, G["proj_%s_back_%d" % (tag, int(pf))], rtol=0, atol=1e-9)
+
+
+def _dataset(G, tmp_path):
+  scan = np.concatenate([G["scan_points_f32"], G["scan_rem"][:, None]], axis=1).astype(np.float32)
+  names, labels = [], []
+  for k in range(2):
+    p, l = str(tmp_path / ("%06d.bin" % k)), str(tmp_path / ("%06d.label" % k))
+    scan.tofile(p); G["scan_label"].astype(np.uint32).tofile(l)
+    names.append(p); labels.append(l)
+  return names, labels
+
+
+def test_deform_cp_and_mergemesh_and_compare(engine, G, tmp_path):
+  """The lidar_deform.py:393-452 sequence on a small scan: SemLaserScan reference scan, MultiSemLaserScan.deform in
+  the 'cp' and 'mergemesh' adaptions, compare() for the identity re-render, write()."""
+  from lidar_transfer_b200.auxiliary.laserscan import SemLaserScan, MultiSemLaserScan, compare
+  names, labels = _dataset(G, tmp_path)
+  lut = _lut(G)
+  H, W = 64, 512
+  src = dict(name="HDL-64E", beams=H, fov_up=3.0, fov_down=-25.0, fov_hor=360.0, angle_res_hor=360.0 / W)
+  poses = [G["scan_pose"], G["scan_pose"]]
+  scan = SemLaserScan(H, W, len(lut), lut)
+  scan.open_scan(names[0], 3.0, -25.0); scan.open_label(labels[0]); scan.colorize(); scan.remove_classes([0, 1])
+  scan.do_range_projection(3.0, -25.0, remove=True); scan.do_label_projection()
+
+  # cp into the golden's target geometry: back-projected points equal the reference's
+  tgt = dict(name="HDL-32E", beams=32, fov_up=10.67, fov_down=-30.67, fov_hor=360.0, angle_res_hor=360.0 / 256)
+  ms = MultiSemLaserScan(src, tgt, 1, len(lut), [0, 1], [252, 259], lut, transformation=None, preserve_float=True,
+                         voxel_size=0.25, vol_bnds=np.array([[-30, 30], [-30, 30], [-4, 3]]))
+  ms.open_multiple_scans(names, labels, poses, 0)
+  assert ms.deform('cp', poses, 0) == ([], [], [])
+  assert np.allclose(ms.back_points, G["proj_tgt_back_1"], rtol=0, atol=1e-9)
+  assert np.array_equal(ms.proj_range.view(np.int32), G["proj_tgt_range"].view(np.int32))
+  os.makedirs(tmp_path / "velodyne"); os.makedirs(tmp_path / "labels")
+  ms.write(str(tmp_path), 3)
+  n_valid = int((G["proj_tgt_index"].reshape(-1) > 0).sum())
+  assert os.path.getsize(tmp_path / "velodyne" / "000003.bin") <= 16 * n_valid
+
+  # mergemesh, identity sensor: the synthetic scan must resemble the source scan
+  ms = MultiSemLaserScan(src, src, 1, len(lut), [0, 1], [252, 259], lut, transformation=None, preserve_float=True,
+                         voxel_size=0.25, vol_bnds=np.array([[-30, 30], [-30, 30], [-4, 3]]))
+  ms.open_multiple_scans(names, labels, poses, 0)
+  verts, vcolors, faces = ms.deform('mergemesh', poses, 0)
+  assert faces.shape[0] > 1000 and verts.shape == (3 * faces.shape[0], 3) and vcolors.shape == verts.shape
+  assert ms.back_points.shape == (H * W, 3) and ms.proj_range.shape == (H, W) and ms.label_image.shape == (H, W)
+  assert ms.proj_color.shape == (H, W, 3) and ms.label_color.shape == (H * W, 3)
+  hit = ms.proj_range > 0
+  assert hit.mean() > 0.02
+  assert set(np.unique(ms.label_image[hit])) <= set(int(v) % 256 for v in np.unique(G["scan_label"]))
+  label_diff, range_diff, rem_diff, m_iou, m_acc, mse = compare(scan, ms)
+  assert label_diff.shape == (H, W, 3) and range_diff.shape == (H, W) and np.isfinite(mse) and 0 <= m_iou <= 1 and 0 <= m_acc <= 1
+  ms.write(str(tmp_path), 4)
+  out = np.fromfile(tmp_path / "velodyne" / "000004.bin", np.float32).reshape(-1, 4)
+  lab = np.fromfile(tmp_path / "labels" / "000004.label", np.uint32)
+  assert out.shape[0] == lab.shape[0] == int(((ms.back_points.sum(axis=1) != 0)).sum())

@@ -1,0 +1,183 @@
+"""Host-side logic that needs no GPU: the C ABI library loads and exports every symbol include/vlidar.h declares,
+the reference-shaped classes keep the reference's host semantics (checked against goldens produced by the
+reference's own Python), scan sharding across ranks (gloo, world_size 2)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
+
+
+@pytest.fixture(scope="module")
+def G():
+  return np.load(GOLDEN)
+
+
+def _declared_symbols():
+  text = open(os.path.join(ROOT, "include", "vlidar.h")).read()
+  text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+  return sorted(set(re.findall(r"\b(ctrace|vl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(vl):
+  import ctypes
+  from lidar_transfer_b200 import _lib
+  names = _declared_symbols()
+  assert "ctrace" in names and "vl_trace" in names and "vl_bvh_build" in names and len(names) >= 25
+  raw = ctypes.CDLL(_lib.LIB_PATH)
+  for n in names:
+    assert hasattr(raw, n), "libvlidar.so does not export %s" % n
+  assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+  assert vl.vl_abi_version() == 1
+  assert vl.vl_bvh_blob_bytes(0) >= 256 and vl.vl_bvh_blob_bytes(1000) > 112 * 1000
+  assert vl.vl_profile_stage_count() >= 5
+
+
+def test_no_cuda_means_loud_failure_not_fallback(vl):
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip("GPU present")
+  from lidar_transfer_b200 import engine, _lib
+  with pytest.raises(RuntimeError):
+    engine.require_cuda()
+  with pytest.raises(RuntimeError):
+    engine.Bvh(np.zeros((3, 3), np.float32), np.zeros((1, 3), np.int32), np.zeros((3, 3), np.int32), np.zeros(3, np.float32))
+  # the reference-signature host entry point reports the missing device instead of computing on the CPU
+  z = np.zeros(3, np.float32)
+  with pytest.raises(_lib.VlidarError):
+    _lib.check(vl.vl_ctrace_ids(z.ctypes.data, z.ctypes.data, z.ctypes.data, np.zeros(3, np.int32).ctypes.data,
+                                np.zeros(3, np.int32).ctypes.data, z.ctypes.data, 1, 1, 1, 1, z.ctypes.data,
+                                np.zeros(3, np.int32).ctypes.data, z.ctypes.data, z.ctypes.data, None))
+
+
+def test_product_never_imports_the_oracle():
+  for dirpath, _, files in os.walk(os.path.join(ROOT, "lidar_transfer_b200")):
+    for f in files:
+      if f.endswith((".py", ".cu", ".cuh", ".h")):
+        text = open(os.path.join(dirpath, f)).read()
+        assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+def _color_map():
+  return {0: [0, 0, 0], 1: [0, 0, 255], 10: [245, 150, 100], 40: [255, 0, 255], 44: [255, 150, 255], 48: [75, 0, 75],
+          50: [0, 200, 255], 51: [50, 120, 255], 70: [0, 175, 0], 71: [0, 60, 135], 72: [80, 240, 150],
+          80: [150, 240, 255], 81: [0, 0, 255], 99: [255, 255, 50], 252: [245, 150, 100], 259: [255, 0, 0]}
+
+
+def test_old_projection_and_pose_round_trip_match_reference(G):
+  """LaserScan.do_range_projection / remove_classes / apply_pose on the host vs the reference's own Python."""
+  from lidar_transfer_b200.auxiliary.laserscan import SemLaserScan
+  lut = {k: v for k, v in _color_map().items()}
+  for k in np.unique(G["scan_label"]):
+    lut.setdefault(int(k), [1, 2, 3])
+  s = SemLaserScan(64, 512, 20, color_dict=lut)
+  s.points, s.remissions, s.label = G["scan_points_f32"].copy(), G["scan_rem"].copy(), G["scan_label"].copy()
+  s.colorize()
+  s.remove_classes([0, 1])
+  s.do_range_projection(3.0, -25.0, remove=True)
+  s.do_label_projection()
+  assert np.array_equal(s.proj_range.view(np.int32), G["oldproj_range"].view(np.int32))
+  assert np.array_equal(s.proj_label, G["oldproj_label"])
+  assert np.array_equal(s.proj_remissions.view(np.int32), G["oldproj_rem"].view(np.int32))
+  # pose round trip (open_multiple_scans :812-815 + deform :949) reproduces the float64 points fed to the projection
+  s2 = SemLaserScan(64, 512, 20, color_dict=lut)
+  s2.points, s2.remissions, s2.label = G["scan_points_f32"].copy(), G["scan_rem"].copy(), G["scan_label"].copy()
+  s2.colorize()
+  s2.pose = G["scan_pose"]
+  s2.apply_pose()
+  s2.remove_classes([0, 1])
+  s2.apply_inv_pose()
+  assert s2.points.dtype == np.float64 and np.array_equal(s2.points, G["proj_src_points_f64"])
+  assert np.array_equal(s2.label, G["proj_src_label_in"])
+
+
+def test_reverse_projection_matches_reference(G):
+  from lidar_transfer_b200.auxiliary.laserscan import LaserScan
+  for tag in ("src", "tgt"):
+    fu, fd, H, W = G["proj_%s_args" % tag]
+    H, W = int(H), int(W)
+    s = LaserScan(H, W)
+    s.range_image = G["proj_%s_range" % tag]
+    idx = G["proj_%s_index" % tag]
+    pts = G["proj_%s_kept_points" % tag]
+    w = pts[idx]
+    depth = np.linalg.norm(w, 2, axis=2)
+    s.proj_x_float = 0.5 * (-np.arctan2(w[..., 1], w[..., 0]) / np.pi + 1.0) * W
+    s.proj_y_float = (1.0 - (np.arcsin(w[..., 2] / depth) + abs(fd / 180 * np.pi)) / (abs(fd / 180 * np.pi) + abs(fu / 180 * np.pi))) * H
+    s.proj_x, s.proj_y = s._clamp(s.proj_x_float, s.proj_y_float)
+    for pf in (False, True):
+      s.do_reverse_projection_new(fu, fd, preserve_float=pf)
+      assert np.allclose(s.back_points, G["proj_%s_back_%d" % (tag, int(pf))], rtol=0, atol=1e-9), (tag, pf)
+
+
+def test_write_produces_the_reference_bytes(G, tmp_path):
+  from lidar_transfer_b200.auxiliary.laserscan import MultiSemLaserScan
+  ms = MultiSemLaserScan.__new__(MultiSemLaserScan)
+  ms.adaption = "mergemesh"
+  ms.back_points = G["glue_endpoints"].copy()
+  ms.label_image = G["glue_ray_colors"][:, 2].reshape(8, 32).copy()
+  ms.proj_remissions = G["glue_rem_image"].copy()
+  os.makedirs(tmp_path / "velodyne"); os.makedirs(tmp_path / "labels")
+  ms.write(str(tmp_path), 7)
+  assert np.array_equal(np.fromfile(tmp_path / "velodyne" / "000007.bin", np.uint8), G["write_bin"])
+  assert np.array_equal(np.fromfile(tmp_path / "labels" / "000007.label", np.uint8), G["write_label"])
+
+
+def test_meshwrite_format(tmp_path):
+  from lidar_transfer_b200.auxiliary.fusion_lidar import meshwrite
+  v = np.array([[0.5, 1.25, -2.0], [1, 2, 3], [4, 5, 6.1234567]], np.float32)
+  f = np.array([[0, 1, 2]], np.int32)
+  c = np.array([[255, 0, 10.9], [1, 2, 3], [4, 5, 6]])
+  meshwrite(str(tmp_path / "m.ply"), v, f, v, c)
+  lines = open(tmp_path / "m.ply").read().splitlines()
+  assert lines[0] == "ply" and lines[2] == "element vertex 3" and lines[12] == "element face 1" and lines[14] == "end_header"
+  assert lines[15] == "0.500000 1.250000 -2.000000 0.500000 1.250000 -2.000000 255 0 10"
+  assert lines[17].startswith("4.000000 5.000000 6.123456 ") and lines[18] == "3 0 1 2"
+
+
+def test_iou_eval_known_answer():
+  """auxiliary/np_ioueval.py:73-95: two overlapping squares."""
+  from lidar_transfer_b200.auxiliary.np_ioueval import iouEval
+  lbl = np.zeros((7, 7), dtype=np.int64); lbl[1:4, 1:4] = 1
+  prd = np.zeros((7, 7), dtype=np.int64); prd[2:5, 2:5] = 1
+  ev = iouEval(2, [])
+  ev.addBatch(prd, lbl)
+  m_iou, iou = ev.getIoU()
+  assert np.isclose(iou[1], 4 / 14) and np.isclose(iou[0], 35 / 45) and np.isclose(m_iou, (4 / 14 + 35 / 45) / 2)
+  assert np.isclose(ev.getacc(), 39 / 49)
+
+
+def test_scan_sharding_two_ranks_gloo(tmp_path):
+  """One process per GPU, scans partitioned with no collective on the data path: world_size 2 over gloo."""
+  script = tmp_path / "shard.py"
+  script.write_text('''
+import os, sys, json
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+from lidar_transfer_b200 import sharding
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+mine = sharding.scans_for_rank(23, rank, world)
+t = torch.zeros(23, dtype=torch.int64)
+t[mine] = rank + 1
+dist.all_reduce(t)
+per_rank = sharding.gather_stats({"rank": rank, "n": len(mine), "ms": 10.0 * (rank + 1)})
+if rank == 0:
+  print(json.dumps({"cover": t.tolist(), "stats": per_rank, "agg": sharding.aggregate(per_rank, rays_per_scan=100)}))
+dist.destroy_process_group()
+''' % ROOT)
+  out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                       capture_output=True, text=True, timeout=300)
+  assert out.returncode == 0, out.stderr[-2000:]
+  import json
+  line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+  d = json.loads(line)
+  assert sorted(set(d["cover"])) == [1, 2] and d["cover"].count(1) == 12 and d["cover"].count(2) == 11
+  assert [s["n"] for s in d["stats"]] == [12, 11]
+  assert d["agg"]["scans"] == 23 and d["agg"]["ms"] == 20.0 and np.isclose(d["agg"]["mrays_per_s"], 23 * 100 / 20e-3 / 1e6)
