@@ -287,7 +287,8 @@ def run_native(args):
       "bounds": 12 * nv,
       "morton": 12 * nt + 12 * nv + 4 * nt + 4 * nt,          # faces + verts(gather, once) + key + flag
       "sort_pass": (4 + 4) * nt * 2,                          # key+val in, key+val out (one 8-bit digit)
-      "emit_climb": 8 * nt + 12 * nt + 28 * nv + 48 * nt + 16 * nt + 64 * nt,
+      "emit_climb": 8 * nt + 12 * nt + 28 * nv + 48 * nt + 16 * nt + 64 * 0.3 * nt,   # ~0.3 nodes per triangle are written
+      "top_climb": 64 * 0.004 * nt,
       "trace": 112 * nt + 12 * R + 36 * R,
   }
   total_stage_ms = sum(v[0] for v in stage.values()) or 1.0
@@ -342,7 +343,7 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="native", choices=["native", "reference"])
   ap.add_argument("--scans-per-step", type=int, default=8)
-  ap.add_argument("--streams", type=int, default=4)
+  ap.add_argument("--streams", type=int, default=8)
   ap.add_argument("--cpu-scans", type=int, default=8, help="scans timed for cpu_baseline (about 1.2 s each)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   args = ap.parse_args()

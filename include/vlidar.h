@@ -176,8 +176,11 @@ int         vl_profile_collect(double* stage_ms, long long* stage_launches);
 /* Debug: while d_stats is non-NULL every vl_trace launch also writes, per ray, the pair
  * {inner nodes visited, triangles tested} to d_stats[2*r .. 2*r+1] (device int[2*n_rays]). */
 void        vl_debug_trace_stats(int* d_stats);
-/* Debug: force the traversal variant: 0 auto, 1 per-thread, 4/8/16/32 = packet tile width. */
+/* Debug: force the traversal variant: 0 auto, 1 per-ray in storage order, 2 per-ray in 16x8 beam tiles,
+ * 4/8/16/32 = warp packets of that tile width. */
 void        vl_debug_trace_mode(int mode);
+/* Debug (timing only, leaves the blob unusable): 0 full build, 1 / 2 / 3 = stop after bounds / morton / sort. */
+void        vl_debug_build_stop(int stage);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvlidar.so")
+LIB_PATH = os.environ.get("VLIDAR_LIB", os.path.join(_HERE, "libvlidar.so"))  # VLIDAR_LIB: tuning builds only
 
 VL_OK, VL_EINVAL, VL_ENOSPACE, VL_ECUDA, VL_EBADMESH = 0, -1, -2, -3, -4
 
@@ -48,6 +48,7 @@ SIGNATURES = {
     "vl_profile_collect": (_i, [_vp, _vp]),
     "vl_debug_trace_stats": (None, [_vp]),
     "vl_debug_trace_mode": (None, [_i]),
+    "vl_debug_build_stop": (None, [_i]),
 }
 
 _lib = None

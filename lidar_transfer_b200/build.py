@@ -32,6 +32,24 @@ def _newer(a, b):
   return (not os.path.exists(b)) or os.path.getmtime(a) > os.path.getmtime(b)
 
 
+def build_variant(tag, defines):
+  """Tuning aid: a separate library lidar_transfer_b200/libvlidar_<tag>.so compiled with extra -D flags
+  (select it at run time with VLIDAR_LIB=...)."""
+  out = os.path.join(HERE, "libvlidar_%s.so" % tag)
+  objdir = os.path.join(OBJ, tag)
+  os.makedirs(objdir, exist_ok=True)
+  objs = []
+  for src, extra in SOURCES.items():
+    s = os.path.join(CSRC, src)
+    if not os.path.exists(s):
+      continue
+    o = os.path.join(objdir, src.replace(".cu", ".o"))
+    objs.append(o)
+    subprocess.check_call([NVCC] + COMMON + extra + ["-D" + d for d in defines] + ["-c", s, "-o", o])
+  subprocess.check_call([NVCC, "-shared", "-o", out] + objs + ["-ccbin", "/usr/bin/g++"])
+  return out
+
+
 def build(force=False, verbose=False):
   os.makedirs(OBJ, exist_ok=True)
   objs = []

@@ -35,7 +35,7 @@ std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof_recs;
 std::vector<cudaEvent_t> g_prof_pool;
 thread_local cudaEvent_t g_prof_open[VL_ST_COUNT];
-const char* kStageNames[VL_ST_COUNT] = {"bounds", "morton", "sort_pass", "emit_climb",
+const char* kStageNames[VL_ST_COUNT] = {"bounds", "morton", "sort_pass", "emit_climb", "top_climb",
                                         "trace", "project_scatter", "project_gather", "tsdf_init", "tsdf_integrate",
                                         "mesh_count", "mesh_scan", "mesh_emit"};
 cudaEvent_t prof_event() {

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(1024) k_init_header(VlHeader* hdr, int n_tris,
     hdr->root_ref = vl_make_leaf(0, 0);
     hdr->n_bad_faces = 0;
     hdr->max_climb = 0;
+    hdr->n_pending = 0;
     for (int k = 0; k < 3; ++k) {
       hdr->bounds_min[k] = 0xffffffffu;
       hdr->bounds_max[k] = 0u;
@@ -165,26 +166,30 @@ k_sort_pass(const unsigned int* __restrict__ keys_in, const unsigned int* __rest
             unsigned int* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int n, int shift,
             const unsigned int* __restrict__ ghist, volatile unsigned int* tile_state, unsigned int* ticket) {
   __shared__ unsigned int cnt[kSortWarps][256];
-  __shared__ unsigned int warp_sums[kSortWarps];
+  __shared__ unsigned int warp_sums[8];
   __shared__ int s_tile;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  for (int k = tid; k < kSortWarps * 256; k += VL_SORT_THREADS) (&cnt[0][0])[k] = 0u;
+  // exclusive scan of the global digit histogram: thread d (< 256) -> first output slot of digit d
+  unsigned int gcount = 0, incl = 0;
+  if (tid < 256) {
+    gcount = ghist[tid];
+    incl = gcount;
 #pragma unroll
-  for (int ww = 0; ww < kSortWarps; ++ww) cnt[ww][tid] = 0u;
-  // exclusive scan of the global digit histogram: thread d -> first output slot of digit d
-  const unsigned int gcount = ghist[tid];
-  unsigned int incl = gcount;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, off);
-    if (lane >= off) incl += t;
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += t;
+    }
+    if (lane == 31) warp_sums[w] = incl;
   }
-  if (lane == 31) warp_sums[w] = incl;
   __syncthreads();
   unsigned int gbase = incl - gcount;
+  if (tid < 256) {
 #pragma unroll
-  for (int ww = 0; ww < kSortWarps; ++ww)
-    if (ww < w) gbase += warp_sums[ww];
+    for (int ww = 0; ww < 8; ++ww)
+      if (ww < w) gbase += warp_sums[ww];
+  }
   const int tile = s_tile;
 
   // rank: warp w owns the contiguous run [tile*TILE + w*32*kItems, +32*kItems), walked in kItems rounds of 32
@@ -215,7 +220,7 @@ k_sort_pass(const unsigned int* __restrict__ keys_in, const unsigned int* __rest
     __syncwarp();
   }
   __syncthreads();
-  {  // thread d: digit d's count in this tile, published; look back for the tiles before
+  if (tid < 256) {  // thread d: digit d's count in this tile, published; look back for the tiles before
     unsigned int run = 0;
 #pragma unroll
     for (int ww = 0; ww < kSortWarps; ++ww) {
@@ -232,7 +237,7 @@ k_sort_pass(const unsigned int* __restrict__ keys_in, const unsigned int* __rest
       int t = tile - 1;
       while (true) {
         const unsigned int st = tile_state[(size_t)t * 256 + tid];
-        if ((st >> 30) == 0u) continue;  // predecessor has not published yet
+        if ((st >> 30) == 0u) { __nanosleep(32); continue; }  // predecessor has not published yet
         before += st & kStMask;
         if ((st >> 30) == 2u) break;
         --t;
@@ -279,182 +284,267 @@ __device__ __forceinline__ unsigned long long shfl_down64(unsigned long long v, 
          __shfl_down_sync(0xffffffffu, (unsigned int)v, off);
 }
 
+struct __align__(16) ClimbSlot {
+  float4 a;  // box min xyz, box max x
+  float4 b;  // box max y z, child ref (bits), outer range bound (bits)
+};
+
 __global__ void __launch_bounds__(kClimbThreads)
 k_emit_climb(const float* __restrict__ verts, const int* __restrict__ faces, const int* __restrict__ colors,
              const float* __restrict__ rem, int n_verts, int n, const unsigned int* __restrict__ keys,
              const unsigned int* __restrict__ vals, VlHeader* hdr, VlNode* nodes, VlTri* __restrict__ tris,
-             int4* __restrict__ c0, int* flags) {
+             int4* __restrict__ c0, int* flags, unsigned int* __restrict__ pending) {
   // Slot k of the CTA = inner node B0 + k (it sits between sorted keys B0+k and B0+k+1).  Node i is LOCAL
   // when its whole key range lies inside the CTA's run [B0, B1): its range grows left / right until it
   // meets a larger delta, so   local(i)  <=>  max delta[B0-1 .. i-1] > delta(i)  and  max delta[i+1 .. B1-1] > delta(i)
   // (delta(-1) = delta(n-1) = +inf).  Both children of a node evaluate the same predicate, and every leaf
   // under a local node belongs to this CTA, so the two children always meet in the same place.
+  //
+  // Phases: (0) deltas + locality flags; (1) one thread per triangle emits its record and parks its box;
+  // (2) every thread finds, from the deltas alone, the maximal local sub-tree of <= 4 triangles it belongs
+  // to -- those become the leaves of the BVH; (3) the first thread of each leaf is compacted to the front of
+  // the CTA (dense warps) and climbs from there.
   __shared__ unsigned long long s_delta[kClimbThreads + 1];  // [0] = delta(B0-1), [1+k] = delta(B0+k)
   __shared__ unsigned long long s_wmax[2][kClimbWarps];
   __shared__ unsigned char s_local[kClimbThreads];
   __shared__ int s_flag[kClimbThreads];
-  __shared__ float s_box[kClimbThreads][2][6];  // [left child | right child] box
-  __shared__ int s_ref[kClimbThreads][2];
-  __shared__ int s_bound[kClimbThreads][2];     // left child: range start, right child: range end
+  __shared__ ClimbSlot s_slot[kClimbThreads][2];  // [left child | right child]; its head doubles as s_tbox until phase 3
+  __shared__ int s_lead[kClimbThreads];           // (first - B0) | count << 16 of the compacted leaves
+  __shared__ int s_wcount[kClimbWarps];
+  float(*s_tbox)[6] = reinterpret_cast<float(*)[6]>(&s_slot[0][0]);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int B0 = blockIdx.x * kClimbThreads;
   const int B1 = min(B0 + kClimbThreads, n);
   const int p = B0 + tid;
   const bool active = p < n;
   s_flag[tid] = 0;
-  {
-    unsigned long long dl = 0ull;  // delta(p); 0 for slots past the run never wins a max
-    if (active) dl = (p == n - 1) ? kDeltaInf : key_delta(keys, p);
-    if (tid == 0) s_delta[0] = (B0 == 0) ? kDeltaInf : key_delta(keys, B0 - 1);
-    s_delta[1 + tid] = dl;
-    // inclusive prefix / suffix max inside the warp, warp totals to shared memory
-    unsigned long long pm = dl, sm = dl;
+  // ---- phase 0 ----
+  unsigned long long dl = 0ull;  // delta(p); 0 for slots past the run never wins a max
+  if (active) dl = (p == n - 1) ? kDeltaInf : key_delta(keys, p);
+  if (tid == 0) s_delta[0] = (B0 == 0) ? kDeltaInf : key_delta(keys, B0 - 1);
+  s_delta[1 + tid] = dl;
+  unsigned long long pm = dl, sm = dl;  // inclusive prefix / suffix max inside the warp
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const unsigned long long a = shfl_up64(pm, off), b = shfl_down64(sm, off);
-      if (lane >= off) pm = max(pm, a);
-      if (lane + off < 32) sm = max(sm, b);
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned long long a = shfl_up64(pm, off), b = shfl_down64(sm, off);
+    if (lane >= off) pm = max(pm, a);
+    if (lane + off < 32) sm = max(sm, b);
+  }
+  if (lane == 31) s_wmax[0][wid] = pm;
+  if (lane == 0) s_wmax[1][wid] = sm;
+  __syncthreads();
+  if (wid < 2) {  // warp 0: exclusive prefix max of the warp totals, warp 1: exclusive suffix max (0 is neutral)
+    unsigned long long acc = lane < kClimbWarps ? s_wmax[wid][lane] : 0ull;
+#pragma unroll
+    for (int off = 1; off < kClimbWarps; off <<= 1) {
+      const unsigned long long up = shfl_up64(acc, off), down = shfl_down64(acc, off);
+      if (wid == 0) { if (lane >= off) acc = max(acc, up); }
+      else if (lane + off < 32) acc = max(acc, down);
     }
-    if (lane == 31) s_wmax[0][wid] = pm;
-    if (lane == 0) s_wmax[1][wid] = sm;
-    __syncthreads();
-    // exclusive versions: max over [B0-1 .. p-1] and over [p+1 .. B1-1]
+    const unsigned long long up1 = shfl_up64(acc, 1), down1 = shfl_down64(acc, 1);
+    unsigned long long ex = wid == 0 ? (lane == 0 ? 0ull : up1) : (lane == 31 ? 0ull : down1);
+    __syncwarp();
+    if (lane < kClimbWarps) s_wmax[wid][lane] = ex;
+  }
+  // ---- phase 1: triangle record + box ----
+  float bmin[3], bmax[3];
+  if (active) {
+    const int f = (int)vals[p];
+    const int i0 = __ldg(faces + 3 * (size_t)f), i1 = __ldg(faces + 3 * (size_t)f + 1), i2 = __ldg(faces + 3 * (size_t)f + 2);
+    if ((unsigned)i0 >= (unsigned)n_verts || (unsigned)i1 >= (unsigned)n_verts || (unsigned)i2 >= (unsigned)n_verts) {
+      // invalid face: a record no ray can hit (a = 0) and an empty box
+      VlTri t;
+      t.v0 = make_float4(0.f, 0.f, 0.f, __int_as_float(f));
+      t.e1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      t.e2 = make_float4(0.f, 0.f, 0.f, 0.f);
+      tris[p] = t;
+      c0[p] = make_int4(0, 0, 0, f);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { bmin[k] = INFINITY; bmax[k] = -INFINITY; }
+    } else {
+      float v0[3], v1[3], v2[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        v0[k] = __ldg(verts + 3 * (size_t)i0 + k);
+        v1[k] = __ldg(verts + 3 * (size_t)i1 + k);
+        v2[k] = __ldg(verts + 3 * (size_t)i2 + k);
+      }
+      // Triangle.h:63-70 mean remission, RayTracer.cpp:36-48 colours pass through float
+      const float r = __fdiv_rn(__fadd_rn(__fadd_rn(__ldg(rem + i0), __ldg(rem + i1)), __ldg(rem + i2)), 3.0f);
+      VlTri t;
+      t.v0 = make_float4(v0[0], v0[1], v0[2], __int_as_float(f));
+      t.e1 = make_float4(__fsub_rn(v1[0], v0[0]), __fsub_rn(v1[1], v0[1]), __fsub_rn(v1[2], v0[2]), r);
+      t.e2 = make_float4(__fsub_rn(v2[0], v0[0]), __fsub_rn(v2[1], v0[1]), __fsub_rn(v2[2], v0[2]), 0.f);
+      tris[p] = t;
+      c0[p] = make_int4((int)(float)__ldg(colors + 3 * (size_t)i0), (int)(float)__ldg(colors + 3 * (size_t)i0 + 1),
+                        (int)(float)__ldg(colors + 3 * (size_t)i0 + 2), f);
+      // conservative leaf box: pad by 2^-21 of the scene's largest |coordinate| so that rounding in
+      // the slab test can never cull a triangle the Moller-Trumbore arithmetic would accept
+      float amax = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        amax = fmaxf(amax, fmaxf(fabsf(vl_ordered_to_float(hdr->bounds_min[k])), fabsf(vl_ordered_to_float(hdr->bounds_max[k]))));
+      const float pad = amax * 4.76837158203125e-07f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        bmin[k] = fminf(v0[k], fminf(v1[k], v2[k])) - pad;
+        bmax[k] = fmaxf(v0[k], fmaxf(v1[k], v2[k])) + pad;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { s_tbox[tid][k] = bmin[k]; s_tbox[tid][3 + k] = bmax[k]; }
+  }
+  __syncthreads();
+  {  // locality flag of node p (exclusive maxima: [B0-1 .. p-1] and [p+1 .. B1-1])
     unsigned long long pre = shfl_up64(pm, 1), suf = shfl_down64(sm, 1);
     if (lane == 0) pre = 0ull;
     if (lane == 31) suf = 0ull;
-    pre = max(pre, s_delta[0]);
-    for (int ww = 0; ww < kClimbWarps; ++ww) {
-      if (ww < wid) pre = max(pre, s_wmax[0][ww]);
-      if (ww > wid) suf = max(suf, s_wmax[1][ww]);
-    }
+    pre = max(max(pre, s_delta[0]), s_wmax[0][wid]);
+    suf = max(suf, s_wmax[1][wid]);
     s_local[tid] = (active && p <= B1 - 2 && pre > dl && suf > dl) ? 1 : 0;
   }
   __syncthreads();
-  if (!active) return;
-  const int f = (int)vals[p];
-  const int i0 = __ldg(faces + 3 * (size_t)f), i1 = __ldg(faces + 3 * (size_t)f + 1), i2 = __ldg(faces + 3 * (size_t)f + 2);
-  float bmin[3], bmax[3];
-  if ((unsigned)i0 >= (unsigned)n_verts || (unsigned)i1 >= (unsigned)n_verts || (unsigned)i2 >= (unsigned)n_verts) {
-    // invalid face: a record no ray can hit (a = 0) and an empty box
-    VlTri t;
-    t.v0 = make_float4(0.f, 0.f, 0.f, __int_as_float(f));
-    t.e1 = make_float4(0.f, 0.f, 0.f, 0.f);
-    t.e2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    tris[p] = t;
-    c0[p] = make_int4(0, 0, 0, f);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { bmin[k] = INFINITY; bmax[k] = -INFINITY; }
-  } else {
-    float v0[3], v1[3], v2[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      v0[k] = __ldg(verts + 3 * (size_t)i0 + k);
-      v1[k] = __ldg(verts + 3 * (size_t)i1 + k);
-      v2[k] = __ldg(verts + 3 * (size_t)i2 + k);
-    }
-    // Triangle.h:63-70 mean remission, RayTracer.cpp:36-48 colours pass through float
-    const float r = __fdiv_rn(__fadd_rn(__fadd_rn(__ldg(rem + i0), __ldg(rem + i1)), __ldg(rem + i2)), 3.0f);
-    VlTri t;
-    t.v0 = make_float4(v0[0], v0[1], v0[2], __int_as_float(f));
-    t.e1 = make_float4(__fsub_rn(v1[0], v0[0]), __fsub_rn(v1[1], v0[1]), __fsub_rn(v1[2], v0[2]), r);
-    t.e2 = make_float4(__fsub_rn(v2[0], v0[0]), __fsub_rn(v2[1], v0[1]), __fsub_rn(v2[2], v0[2]), 0.f);
-    tris[p] = t;
-    c0[p] = make_int4((int)(float)__ldg(colors + 3 * (size_t)i0), (int)(float)__ldg(colors + 3 * (size_t)i0 + 1),
-                      (int)(float)__ldg(colors + 3 * (size_t)i0 + 2), f);
-    // conservative leaf box: pad by 2^-21 of the scene's largest |coordinate| so that rounding in
-    // the slab test can never cull a triangle the Moller-Trumbore arithmetic would accept
-    float amax = 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-      amax = fmaxf(amax, fmaxf(fabsf(vl_ordered_to_float(hdr->bounds_min[k])), fabsf(vl_ordered_to_float(hdr->bounds_max[k]))));
-    const float pad = amax * 4.76837158203125e-07f;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      bmin[k] = fminf(v0[k], fminf(v1[k], v2[k])) - pad;
-      bmax[k] = fmaxf(v0[k], fmaxf(v1[k], v2[k])) + pad;
+  // ---- phase 2: the leaf (maximal local sub-tree of <= VL_LEAF_MAX triangles) this triangle belongs to ----
+  int l = p, r = p;
+  if (active) {
+    while (r - l + 1 < VL_LEAF_MAX) {
+      const bool is_left = (l == 0) ? true : ((r == n - 1) ? false : (s_delta[1 + r - B0] < s_delta[l - B0]));
+      const int parent = is_left ? r : l - 1;
+      if (parent < B0 || parent > B1 - 2 || !s_local[parent - B0]) break;
+      const unsigned long long dp = s_delta[1 + parent - B0];
+      int nl = l, nr = r;
+      if (is_left) {
+        nr = r + 1;
+        while (nr - nl + 1 <= VL_LEAF_MAX && s_delta[1 + nr - B0] < dp) ++nr;
+      } else {
+        nl = l - 1;
+        while (nr - nl + 1 <= VL_LEAF_MAX && s_delta[nl - B0] < dp) --nl;
+      }
+      if (nr - nl + 1 > VL_LEAF_MAX) break;
+      l = nl; r = nr;
     }
   }
-
-  int l = p, r = p;
-  int ref = vl_make_leaf(p, 1);
-  if (n == 1) { hdr->root_ref = ref; return; }
-  int climb = 0;
-  bool in_cta = true;  // [l, r] still inside [B0, B1): deltas come from shared memory
-  while (true) {
-    bool is_left;
-    if (l == 0) is_left = true;
-    else if (r == n - 1) is_left = false;
-    else if (in_cta) is_left = s_delta[1 + r - B0] < s_delta[l - B0];
-    else is_left = key_delta(keys, r) < key_delta(keys, l - 1);
+  // ---- phase 3: compact the first thread of every leaf to the front of the CTA ----
+  const bool leader = active && p == l;
+  const unsigned int bal = __ballot_sync(0xffffffffu, leader);
+  if (lane == 0) s_wcount[wid] = __popc(bal);
+  __syncthreads();
+  int before = 0, n_leaders = 0;
+#pragma unroll
+  for (int ww = 0; ww < kClimbWarps; ++ww) {
+    const int c = s_wcount[ww];
+    if (ww < wid) before += c;
+    n_leaders += c;
+  }
+  if (leader) s_lead[before + __popc(bal & ((1u << lane) - 1u))] = (l - B0) | ((r - l + 1) << 16);
+  __syncthreads();
+  const bool run = tid < n_leaders;
+  int ref = 0;
+  if (run) {
+    const int packed = s_lead[tid], first = packed & 0xffff, count = packed >> 16;
+    l = B0 + first; r = l + count - 1;
+    ref = vl_make_leaf(l, count);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { bmin[k] = s_tbox[first][k]; bmax[k] = s_tbox[first][3 + k]; }
+    for (int j = 1; j < count; ++j) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        bmin[k] = fminf(bmin[k], s_tbox[first + j][k]);
+        bmax[k] = fmaxf(bmax[k], s_tbox[first + j][3 + k]);
+      }
+    }
+  }
+  __syncthreads();  // every box has been read: the slots may be written from here on
+  if (!run) return;
+  if (l == 0 && r == n - 1) { hdr->root_ref = ref; return; }
+  while (true) {  // [l, r] stays inside [B0, B1): every delta comes from shared memory
+    const bool is_left = (l == 0) ? true : ((r == n - 1) ? false : (s_delta[1 + r - B0] < s_delta[l - B0]));
     const int parent = is_left ? r : l - 1;
-    if (in_cta && parent >= B0 && parent < B1 && s_local[parent - B0]) {
+    if (parent >= B0 && parent < B1 && s_local[parent - B0]) {
       // ---- the whole sub-tree of `parent` lives in this CTA: the children meet in shared memory ----
       const int k = parent - B0, me = is_left ? 0 : 1;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) { s_box[k][me][a] = bmin[a]; s_box[k][me][3 + a] = bmax[a]; }
-      s_ref[k][me] = ref;
-      s_bound[k][me] = is_left ? l : r;
+      s_slot[k][me].a = make_float4(bmin[0], bmin[1], bmin[2], bmax[0]);
+      s_slot[k][me].b = make_float4(bmax[1], bmax[2], __int_as_float(ref), __int_as_float(is_left ? l : r));
       __threadfence_block();
       if (atomicExch(&s_flag[k], 1) == 0) break;  // first child to arrive stops here
       __threadfence_block();
-      float smin[3], smax[3];
-#pragma unroll
-      for (int a = 0; a < 3; ++a) { smin[a] = s_box[k][me ^ 1][a]; smax[a] = s_box[k][me ^ 1][3 + a]; }
-      const int sref = s_ref[k][me ^ 1];
-      if (is_left) r = s_bound[k][1]; else l = s_bound[k][0];
+      const float4 sa = s_slot[k][me ^ 1].a, sb = s_slot[k][me ^ 1].b;
+      const int sref = __float_as_int(sb.z);
+      if (is_left) r = __float_as_int(sb.w); else l = __float_as_int(sb.w);
       const int size = r - l + 1;
       if (size > VL_LEAF_MAX) {  // a real inner node: the whole 64 B record in one go
-        float4 q0, q1, q2, q3;
-        if (is_left) {
-          q0 = make_float4(bmin[0], bmin[1], bmin[2], bmax[0]);
-          q1 = make_float4(bmax[1], bmax[2], smin[0], smin[1]);
-          q2 = make_float4(smin[2], smax[0], smax[1], smax[2]);
-          q3 = make_float4(__int_as_float(ref), __int_as_float(sref), __int_as_float(l), __int_as_float(r));
-        } else {
-          q0 = make_float4(smin[0], smin[1], smin[2], smax[0]);
-          q1 = make_float4(smax[1], smax[2], bmin[0], bmin[1]);
-          q2 = make_float4(bmin[2], bmax[0], bmax[1], bmax[2]);
-          q3 = make_float4(__int_as_float(sref), __int_as_float(ref), __int_as_float(l), __int_as_float(r));
-        }
+        const float4 ma = make_float4(bmin[0], bmin[1], bmin[2], bmax[0]);
+        const float4 mb = make_float4(bmax[1], bmax[2], __int_as_float(ref), __int_as_float(is_left ? l : r));
         float4* q = nodes[parent].q;
-        q[0] = q0; q[1] = q1; q[2] = q2; q[3] = q3;
+        q[is_left ? 0 : 2] = ma; q[is_left ? 1 : 3] = mb;
+        q[is_left ? 2 : 0] = sa; q[is_left ? 3 : 1] = sb;
       }
-#pragma unroll
-      for (int a = 0; a < 3; ++a) { bmin[a] = fminf(bmin[a], smin[a]); bmax[a] = fmaxf(bmax[a], smax[a]); }
+      bmin[0] = fminf(bmin[0], sa.x); bmin[1] = fminf(bmin[1], sa.y); bmin[2] = fminf(bmin[2], sa.z);
+      bmax[0] = fmaxf(bmax[0], sa.w); bmax[1] = fmaxf(bmax[1], sb.x); bmax[2] = fmaxf(bmax[2], sb.y);
       ref = size <= VL_LEAF_MAX ? vl_make_leaf(l, size) : parent;
     } else {
-      // ---- the sub-tree of `parent` spans CTAs: the children meet in global memory ----
-      in_cta = false;
-      float* nf = reinterpret_cast<float*>(&nodes[parent]);
-      int* ni = reinterpret_cast<int*>(&nodes[parent]);
-      const int boff = is_left ? 0 : 6;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) { nf[boff + a] = bmin[a]; nf[boff + 3 + a] = bmax[a]; }
-      ni[is_left ? 12 : 13] = ref;
-      ni[is_left ? 14 : 15] = is_left ? l : r;
-      __threadfence();
-      if (atomicExch(&flags[parent], 1) == 0) break;  // first child to arrive stops here
-      __threadfence();
-      const int soff = is_left ? 6 : 0;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        bmin[a] = fminf(bmin[a], __ldcg(nf + soff + a));
-        bmax[a] = fmaxf(bmax[a], __ldcg(nf + soff + 3 + a));
-      }
-      if (is_left) r = __ldcg(ni + 15); else l = __ldcg(ni + 14);
+      // ---- the sub-tree of `parent` spans CTAs: park this half in the node record and stop; whichever child
+      // completes the pair queues the node for k_top_climb (no fence: the kernel boundary orders the data) ----
+      float4* q = nodes[parent].q + (is_left ? 0 : 2);
+      q[0] = make_float4(bmin[0], bmin[1], bmin[2], bmax[0]);
+      q[1] = make_float4(bmax[1], bmax[2], __int_as_float(ref), __int_as_float(is_left ? l : r));
+      if (atomicAdd(&flags[parent], 1) == 1) pending[atomicAdd(&hdr->n_pending, 1)] = parent;
+      break;
+    }
+    if (l == 0 && r == n - 1) { hdr->root_ref = ref; break; }  // the whole mesh fits one CTA
+  }
+}
+
+// The few nodes whose key range spans CTAs of k_emit_climb: one thread per queued node (both halves parked by
+// k_emit_climb) merges it and climbs on through global memory -- write own half, fence, count the arrival; the
+// first child to arrive at a node stops, the second carries the merged box upwards.  A few thousand threads
+// with a dependent chain of ~10-25 levels: latency-bound, but it holds next to no SM resources.
+constexpr int kTopThreads = 128;
+
+__global__ void __launch_bounds__(kTopThreads)
+k_top_climb(const unsigned int* __restrict__ keys, int n, VlHeader* hdr, VlNode* nodes, int* flags,
+            const unsigned int* __restrict__ pending) {
+  const int n_pending = hdr->n_pending;
+  for (int i = blockIdx.x * kTopThreads + threadIdx.x; i < n_pending; i += gridDim.x * kTopThreads) {
+    int parent = (int)pending[i];
+    float bmin[3], bmax[3];
+    int l, r, ref, climb = 0;
+    {
+      const float4* q = nodes[parent].q;
+      const float4 q0 = __ldcg(q), q1 = __ldcg(q + 1), q2 = __ldcg(q + 2), q3 = __ldcg(q + 3);
+      bmin[0] = fminf(q0.x, q2.x); bmin[1] = fminf(q0.y, q2.y); bmin[2] = fminf(q0.z, q2.z);
+      bmax[0] = fmaxf(q0.w, q2.w); bmax[1] = fmaxf(q1.x, q3.x); bmax[2] = fmaxf(q1.y, q3.y);
+      l = __float_as_int(q1.w); r = __float_as_int(q3.w);
+    }
+    while (true) {
       const int size = r - l + 1;
       ref = size <= VL_LEAF_MAX ? vl_make_leaf(l, size) : parent;
-    }
-    ++climb;
-    if (l == 0 && r == n - 1) {
-      hdr->root_ref = ref;
-      atomicMax(&hdr->max_climb, climb);
-      break;
+      ++climb;
+      if (l == 0 && r == n - 1) {
+        hdr->root_ref = ref;
+        atomicMax(&hdr->max_climb, climb);
+        break;
+      }
+      const bool is_left = (l == 0) ? true : ((r == n - 1) ? false : (key_delta(keys, r) < key_delta(keys, l - 1)));
+      parent = is_left ? r : l - 1;
+      float4* q = nodes[parent].q;
+      q[is_left ? 0 : 2] = make_float4(bmin[0], bmin[1], bmin[2], bmax[0]);
+      q[is_left ? 1 : 3] = make_float4(bmax[1], bmax[2], __int_as_float(ref), __int_as_float(is_left ? l : r));
+      __threadfence();
+      if (atomicAdd(&flags[parent], 1) == 0) break;  // first child to arrive stops here
+      __threadfence();
+      const float4 sa = __ldcg(q + (is_left ? 2 : 0)), sb = __ldcg(q + (is_left ? 3 : 1));
+      bmin[0] = fminf(bmin[0], sa.x); bmin[1] = fminf(bmin[1], sa.y); bmin[2] = fminf(bmin[2], sa.z);
+      bmax[0] = fmaxf(bmax[0], sa.w); bmax[1] = fmaxf(bmax[1], sb.x); bmax[2] = fmaxf(bmax[2], sb.y);
+      if (is_left) r = __float_as_int(sb.w); else l = __float_as_int(sb.w);
     }
   }
 }
 
 }  // namespace
+
+int g_debug_build_stop = 0;  // vl_debug_build_stop(): 0 full build; 1 / 2 / 3 = return after bounds / morton / sort (timing only)
+extern "C" void vl_debug_build_stop(int stage) { g_debug_build_stop = stage; }
 
 int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_colors, const float* d_rem,
                         int n_verts, int n_faces, void* d_blob, cudaStream_t stream) {
@@ -480,6 +570,7 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
   { VlProfScope ps(VL_ST_BOUNDS, stream);
   k_bounds<<<nb_verts, kThreads, 0, stream>>>(d_verts, n_verts, hdr); }
   VL_LAUNCH_CHECK("k_bounds");
+  if (g_debug_build_stop == 1) return VL_OK;
   const int nt = L.n_sort_tiles;
   const int n_state_words = 256 * VL_SORT_PASSES * nt;
   int nb_faces = (n_faces + kThreads - 1) / kThreads;
@@ -488,6 +579,7 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
   k_morton<<<nb_faces, kThreads, 0, stream>>>(d_verts, d_faces, n_verts, n_faces, hdr, keys0, flags, ghist, tile_state,
                                              n_state_words); }
   VL_LAUNCH_CHECK("k_morton");
+  if (g_debug_build_stop == 2) return VL_OK;
 
   const unsigned int* kin = keys0;
   const unsigned int* vin = nullptr;  // pass 0 generates the identity permutation on the fly
@@ -504,12 +596,21 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
     vout = (vout == vals1) ? vals0 : vals1;
   }
   // after 4 passes the sorted (key, face id) pairs are back in keys0 / vals0
-  VlProfScope ps_emit(VL_ST_EMIT_CLIMB, stream);
+  if (g_debug_build_stop == 3) return VL_OK;
   const int nb_climb = (n_faces + kClimbThreads - 1) / kClimbThreads;
+  VlNode* nodes = reinterpret_cast<VlNode*>(blob + L.off_nodes);
+  { VlProfScope ps(VL_ST_EMIT_CLIMB, stream);
+  // vals1 is free after the sort: it becomes the queue of nodes for k_top_climb (at most n / 2 entries)
   k_emit_climb<<<nb_climb, kClimbThreads, 0, stream>>>(d_verts, d_faces, d_colors, d_rem, n_verts, n_faces, keys0, vals0,
-                                                      hdr, reinterpret_cast<VlNode*>(blob + L.off_nodes),
-                                                      reinterpret_cast<VlTri*>(blob + L.off_tris),
-                                                      reinterpret_cast<int4*>(blob + L.off_c0), flags);
+                                                      hdr, nodes, reinterpret_cast<VlTri*>(blob + L.off_tris),
+                                                      reinterpret_cast<int4*>(blob + L.off_c0), flags, vals1); }
   VL_LAUNCH_CHECK("k_emit_climb");
+  if (nb_climb > 1) {
+    VlProfScope ps(VL_ST_TOP_CLIMB, stream);
+    int nb_top = (nb_climb * 16 + kTopThreads - 1) / kTopThreads;  // ~ a dozen queued nodes per CTA is typical
+    if (nb_top > 148 * 8) nb_top = 148 * 8;
+    k_top_climb<<<nb_top, kTopThreads, 0, stream>>>(keys0, n_faces, hdr, nodes, flags, vals1);
+    VL_LAUNCH_CHECK("k_top_climb");
+  }
   return VL_OK;
 }

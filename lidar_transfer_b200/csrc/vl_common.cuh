@@ -16,7 +16,7 @@ void vl_count_launch();
 // bench.py switches it on to obtain the per-kernel durations behind the roofline figures.
 // ---------------------------------------------------------------------------
 enum VlStage {
-  VL_ST_BOUNDS = 0, VL_ST_MORTON, VL_ST_SORT_PASS, VL_ST_EMIT_CLIMB,
+  VL_ST_BOUNDS = 0, VL_ST_MORTON, VL_ST_SORT_PASS, VL_ST_EMIT_CLIMB, VL_ST_TOP_CLIMB,
   VL_ST_TRACE, VL_ST_PROJECT_SCATTER, VL_ST_PROJECT_GATHER, VL_ST_TSDF_INIT, VL_ST_TSDF_INTEGRATE,
   VL_ST_MESH_COUNT, VL_ST_MESH_SCAN, VL_ST_MESH_EMIT, VL_ST_COUNT
 };
@@ -59,9 +59,9 @@ struct VlProfScope {
 // of <= 4 Morton-adjacent triangles is one contiguous <= 192 B run.
 // ---------------------------------------------------------------------------
 struct __align__(16) VlNode {
-  // words 0..5  left child box  (min xyz, max xyz)
-  // words 6..11 right child box (min xyz, max xyz)
-  // word 12 left ref, 13 right ref, 14 range-left bound, 15 range-right bound
+  // q[0], q[1]: left child   (min x y z, max x | max y z, child ref, first key of its range)
+  // q[2], q[3]: right child  (min x y z, max x | max y z, child ref, last key of its range)
+  // each half is one aligned 32 B chunk, written by the child that owns it during the build
   float4 q[4];
 };
 
@@ -78,7 +78,8 @@ struct VlHeader {
   int max_climb;
   unsigned int bounds_min[3];  // order-preserving uint encoding of float
   unsigned int bounds_max[3];
-  int pad[54];
+  int n_pending;               // nodes queued by k_emit_climb for k_top_climb
+  int pad[53];
 };
 static_assert(sizeof(VlHeader) == 256, "header is 256 B");
 
@@ -88,8 +89,12 @@ __host__ __device__ inline int vl_make_leaf(int first, int count) { return ~((fi
 __host__ __device__ inline int vl_leaf_first(int ref) { return (~ref) >> 3; }
 __host__ __device__ inline int vl_leaf_count(int ref) { return (~ref) & 7; }
 
+#ifndef VL_SORT_THREADS
 #define VL_SORT_THREADS 256
+#endif
+#ifndef VL_SORT_ITEMS
 #define VL_SORT_ITEMS 8
+#endif
 #define VL_SORT_TILE (VL_SORT_THREADS * VL_SORT_ITEMS)  // keys per radix-sort tile
 #define VL_SORT_PASSES 4                                // 8-bit digits over the 32-bit Morton key
 

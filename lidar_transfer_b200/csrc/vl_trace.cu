@@ -49,6 +49,10 @@ __device__ __forceinline__ void slab(const float bminx, const float bminy, const
   *tfar = fminf(fminf(hix, hiy), hiz);
 }
 
+// "while-while" traversal: every lane first walks inner nodes until it holds a leaf (lanes that got there early
+// idle instead of dragging the warp through both code paths), then the leaves are tested together.
+constexpr int kDoneRef = (int)0x80000000;  // not a valid leaf reference (first would be >= 2^28)
+
 template <bool kNanFilter>
 __device__ __forceinline__ void traverse(const VlNode* __restrict__ nodes, const VlTri* __restrict__ tris,
                                          int root_ref, const float3 o, const float3 d, const float3 inv_d,
@@ -57,19 +61,28 @@ __device__ __forceinline__ void traverse(const VlNode* __restrict__ nodes, const
   int sp = 0;
   int ref = root_ref;
   const int tid = threadIdx.x;
-  while (true) {
-    if (ref >= 0) {
+  // pop, skipping entries that can no longer beat the best hit (BVH.cpp:41)
+  auto pop = [&]() -> int {
+    while (sp > 0) {
+      --sp;
+      const uint2 ent = sp < kSmemStack ? sstack[sp][tid] : lstack[sp - kSmemStack];
+      if (__uint_as_float(ent.y) <= best->t) return (int)ent.x;
+    }
+    return kDoneRef;
+  };
+  while (ref != kDoneRef) {
+    while (ref >= 0) {
       ++*n_nodes;
       const float4* q = nodes[ref].q;
       const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), e = __ldg(q + 3);
       float tn0, tf0, tn1, tf1;
       slab<kNanFilter>(a.x, a.y, a.z, a.w, b.x, b.y, o, inv_d, &tn0, &tf0);
-      slab<kNanFilter>(b.z, b.w, c.x, c.y, c.z, c.w, o, inv_d, &tn1, &tf1);
+      slab<kNanFilter>(c.x, c.y, c.z, c.w, e.x, e.y, o, inv_d, &tn1, &tf1);
       // BBox.cpp:97 `tfar >= 0 && tfar >= tnear`, with a relaxed far bound; BVH.cpp:41 prune
       tf0 = tf0 * 1.0000004f; tf1 = tf1 * 1.0000004f;
       const bool h0 = (tf0 >= 0.f) & (tf0 >= tn0) & (tn0 <= best->t);
       const bool h1 = (tf1 >= 0.f) & (tf1 >= tn1) & (tn1 <= best->t);
-      const int r0 = __float_as_int(e.x), r1 = __float_as_int(e.y);
+      const int r0 = __float_as_int(b.z), r1 = __float_as_int(e.z);
       if (h0 & h1) {
         const bool swap = tn1 < tn0;  // BVH.cpp:77: nearer child first
         const int far_ref = swap ? r0 : r1;
@@ -78,44 +91,54 @@ __device__ __forceinline__ void traverse(const VlNode* __restrict__ nodes, const
         const uint2 ent = make_uint2((unsigned)far_ref, __float_as_uint(far_t));
         if (sp < kSmemStack) sstack[sp][tid] = ent; else lstack[sp - kSmemStack] = ent;
         ++sp;
-        continue;
+      } else if (h0) {
+        ref = r0;
+      } else if (h1) {
+        ref = r1;
+      } else {
+        ref = pop();
       }
-      if (h0) { ref = r0; continue; }
-      if (h1) { ref = r1; continue; }
-    } else {
-      const int first = vl_leaf_first(ref), count = vl_leaf_count(ref);
-      *n_tris += count;
-      for (int k = 0; k < count; ++k) {
-        const float4* tq = reinterpret_cast<const float4*>(tris + first + k);
-        const float4 v0 = __ldg(tq), e1 = __ldg(tq + 1), e2 = __ldg(tq + 2);
-        float t;
-        if (vl_tri_hit(v0, e1, e2, o, d, &t)) {
-          const int orig = __float_as_int(v0.w);
-          if (t < best->t || (t == best->t && orig < best->orig)) {
-            best->t = t; best->pos = first + k; best->orig = orig; best->rem = e1.w;
-          }
+    }
+    if (ref == kDoneRef) break;
+    const int first = vl_leaf_first(ref), count = vl_leaf_count(ref);
+    *n_tris += count;
+    for (int k = 0; k < count; ++k) {
+      const float4* tq = reinterpret_cast<const float4*>(tris + first + k);
+      const float4 v0 = __ldg(tq), e1 = __ldg(tq + 1), e2 = __ldg(tq + 2);
+      float t;
+      if (vl_tri_hit(v0, e1, e2, o, d, &t)) {
+        const int orig = __float_as_int(v0.w);
+        if (t < best->t || (t == best->t && orig < best->orig)) {
+          best->t = t; best->pos = first + k; best->orig = orig; best->rem = e1.w;
         }
       }
     }
-    // pop, skipping entries that can no longer beat the best hit (BVH.cpp:41)
-    bool found = false;
-    while (sp > 0) {
-      --sp;
-      const uint2 ent = sp < kSmemStack ? sstack[sp][tid] : lstack[sp - kSmemStack];
-      if (__uint_as_float(ent.y) <= best->t) { ref = (int)ent.x; found = true; break; }
-    }
-    if (!found) break;
+    ref = pop();
   }
 }
 
+// kTiled: a warp is an 8 x 4 tile of the H x W beam grid and a CTA a 16 x 8 tile (neighbouring beams walk the
+// same sub-trees, so their node fetches hit in L1 and their control flow stays together); otherwise rays are
+// taken in storage order (ray sets that are not a beam grid).
+template <bool kTiled>
 __global__ void __launch_bounds__(kTraceThreads)
 k_trace(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ nodes, const VlTri* __restrict__ tris,
         const int4* __restrict__ c0, const float* __restrict__ rays, const float* __restrict__ origin, int n_traced,
-        float* __restrict__ endpoints, int* __restrict__ endcolors, float* __restrict__ range,
+        int width, int height, float* __restrict__ endpoints, int* __restrict__ endcolors, float* __restrict__ range,
         float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses, int* __restrict__ stats) {
   __shared__ uint2 sstack[kSmemStack][kTraceThreads];
-  const int r = blockIdx.x * kTraceThreads + threadIdx.x;
-  if (r >= n_traced) return;
+  int r;
+  if (kTiled) {
+    const int tiles_x = (width + 15) >> 4;
+    const int bx = blockIdx.x % tiles_x, by = blockIdx.x / tiles_x;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = (bx << 4) + ((w & 1) << 3) + (lane & 7), row = (by << 3) + ((w >> 1) << 2) + (lane >> 3);
+    if (col >= width || row >= height) return;
+    r = row * width + col;
+  } else {
+    r = blockIdx.x * kTraceThreads + threadIdx.x;
+    if (r >= n_traced) return;
+  }
   const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
   const float3 d = vl_normalize(__ldg(rays + 3 * (size_t)r), __ldg(rays + 3 * (size_t)r + 1), __ldg(rays + 3 * (size_t)r + 2));
   const float3 inv_d = make_float3(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));  // Ray.h:11-12
@@ -266,16 +289,16 @@ k_trace_packet(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ node
         float tn0, tf0, tn1, tf1;
         if (any_odd) {
           slab<true>(a.x, a.y, a.z, a.w, b.x, b.y, o, inv_d, &tn0, &tf0);
-          slab<true>(b.z, b.w, c.x, c.y, c.z, c.w, o, inv_d, &tn1, &tf1);
+          slab<true>(c.x, c.y, c.z, c.w, e.x, e.y, o, inv_d, &tn1, &tf1);
         } else {
           slab<false>(a.x, a.y, a.z, a.w, b.x, b.y, o, inv_d, &tn0, &tf0);
-          slab<false>(b.z, b.w, c.x, c.y, c.z, c.w, o, inv_d, &tn1, &tf1);
+          slab<false>(c.x, c.y, c.z, c.w, e.x, e.y, o, inv_d, &tn1, &tf1);
         }
         tf0 = tf0 * 1.0000004f; tf1 = tf1 * 1.0000004f;
         const bool h0 = (tf0 >= 0.f) & (tf0 >= tn0) & (tn0 <= best_t);
         const bool h1 = (tf1 >= 0.f) & (tf1 >= tn1) & (tn1 <= best_t);
         const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
-        const int r0 = __float_as_int(e.x), r1 = __float_as_int(e.y);
+        const int r0 = __float_as_int(b.z), r1 = __float_as_int(e.z);
         if (m0 && m1) {
           const unsigned want1 = __ballot_sync(0xffffffffu, h1 && (!h0 || tn1 < tn0));
           const bool first1 = 2 * __popc(want1) > __popc(m0 | m1);
@@ -332,7 +355,7 @@ k_trace_packet(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ node
 }
 
 int* g_debug_stats = nullptr;  // vl_debug_trace_stats(): per-ray {inner nodes visited, triangles tested}
-int g_debug_mode = 0;          // vl_debug_trace_mode(): 0 auto, 1 per-thread, 8/16/32 packet tile width
+int g_debug_mode = 0;          // vl_debug_trace_mode(): 0 auto, 1 per-ray storage order, 2 per-ray 16x8 tiles, 4/8/16/32 packet tile width
 
 }  // namespace
 
@@ -359,12 +382,17 @@ int vl_trace_launch(const void* d_blob, int n_faces, const float* d_rays, const 
   int mode = g_debug_mode;
   // measured on B200 (gpurun_out/trace_stats_710.txt): per-thread stacks 0.180 ms, 8x4 packets 0.185 ms per
   // 131 072 rays over 1.05 M triangles -- packets test 1.65x the triangles, so per-thread is the default
-  if (mode == 0) mode = (flags & VL_TRACE_PACKET) ? ((height >= 4 && width >= 8) ? 8 : 32) : 1;
+  if (mode == 0) mode = (flags & VL_TRACE_PACKET) ? ((height >= 4 && width >= 8) ? 8 : 32) : 2;
   VlProfScope ps(VL_ST_TRACE, stream);
+  if (mode == 2 && !(height >= 4 && width >= 8)) mode = 1;
   if (mode == 1) {
     const int nb = (int)((n_traced + kTraceThreads - 1) / kTraceThreads);
-    k_trace<<<nb, kTraceThreads, 0, stream>>>(hdr, nodes, tris, c0, d_rays, d_origin, (int)n_traced, d_endpoints,
-                                             d_endcolors, d_range, d_endrem, d_tri_id, zm, g_debug_stats);
+    k_trace<false><<<nb, kTraceThreads, 0, stream>>>(hdr, nodes, tris, c0, d_rays, d_origin, (int)n_traced, width, height,
+                                                    d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, zm, g_debug_stats);
+  } else if (mode == 2) {
+    const int nb = ((width + 15) / 16) * ((height + 7) / 8);
+    k_trace<true><<<nb, kTraceThreads, 0, stream>>>(hdr, nodes, tris, c0, d_rays, d_origin, (int)n_traced, width, height,
+                                                   d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, zm, g_debug_stats);
   } else {
     const int tw = mode, th = 32 / mode;
     const long long n_tiles = (long long)((width + tw - 1) / tw) * ((height + th - 1) / th);

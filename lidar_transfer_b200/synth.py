@@ -2,8 +2,8 @@
 
 There is no network for datasets, so BASELINE.json configs 3 and 5 use this generator
 (SURVEY.md section 8d): a ground height field over x,y in [-50,50] m with a radial berm so
-every ray terminates, plus axis-aligned boxes (cars, buildings) tessellated at the grid
-pitch.  Per-vertex labels are drawn from the SemanticKITTI ids the reference's config
+every ray terminates, plus axis-aligned boxes (cars, buildings; none of them over the sensor)
+tessellated at 4x the grid pitch.  Per-vertex labels are drawn from the SemanticKITTI ids the reference's config
 lists (config/lidar_transfer.yaml:13-46) excluding 0, 1 and ids >= 256; remission U[0,1).
 
 The mesh layout is the one TSDFVolume.get_mesh hands to C_Trace
@@ -62,9 +62,12 @@ def make_scene(seed, n_side=500, n_boxes=40, extent=50.0):
       sx, sy, sz = 4.0, 1.8, 1.5
     if rng.random() < 0.5:
       sx, sy = sy, sx
-    r = rng.uniform(6.0, 38.0)
-    th = rng.uniform(0.0, 2.0 * np.pi)
-    cx, cy, z0 = r * np.cos(th), r * np.sin(th), -2.2
+    while True:  # keep the sensor (origin) outside every box, with 2.5 m clearance
+      r = rng.uniform(6.0, 38.0)
+      th = rng.uniform(0.0, 2.0 * np.pi)
+      cx, cy, z0 = r * np.cos(th), r * np.sin(th), -2.2
+      if abs(cx) > sx / 2 + 2.5 or abs(cy) > sy / 2 + 2.5:
+        break
     lo = np.array([cx - sx / 2, cy - sy / 2, z0])
     ex, ey, ez = np.array([sx, 0, 0.0]), np.array([0, sy, 0.0]), np.array([0, 0, sz + 0.5])
     # boxes are tessellated at 4x the ground pitch: 40 boxes add ~4 % to the triangle budget

@@ -14,7 +14,7 @@ L = _lib.lib()
 bvh = engine.Bvh(sc["verts"], sc["faces"], sc["colors"], sc["rem"])
 print(bvh.status())
 ref_out = None
-for mode in (1, 32, 16, 8, 4):
+for mode in (1, 2, 8):
   L.vl_debug_trace_mode(mode)
   stats = torch.zeros(2 * H * W, dtype=torch.int32, device="cuda")
   L.vl_debug_trace_stats(ctypes.c_void_p(stats.data_ptr()))
@@ -22,6 +22,8 @@ for mode in (1, 32, 16, 8, 4):
   torch.cuda.synchronize()
   L.vl_debug_trace_stats(ctypes.c_void_p(0))
   st = stats.cpu().numpy().reshape(H, W, 2)
+  if mode == 2:
+    os.makedirs('gpurun_out', exist_ok=True); np.save('gpurun_out/trace_stats_mode2.npy', st.astype(np.int16)); np.save('gpurun_out/trace_range.npy', out['range'].cpu().numpy().reshape(H, W).astype(np.float16))
   nodes, tris = st[..., 0], st[..., 1]
   pc = lambda a: [float(np.percentile(a, q)) for q in (50, 90, 99, 100)]
   ts = []
