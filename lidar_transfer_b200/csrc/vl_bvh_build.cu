@@ -114,6 +114,14 @@ k_morton(const float* __restrict__ verts, const int* __restrict__ faces, int n_v
   }
   const float m = fmaxf(fmaxf(ext[0], ext[1]), 2.0f * ext[2]);
   const float s = m > 0.0f ? 2048.0f / m : 0.0f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // conservative leaf-box padding: 2^-21 of the scene's largest |coordinate|, so that rounding in the slab
+    // test can never cull a triangle the Moller-Trumbore arithmetic would accept
+    float amax = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) amax = fmaxf(amax, fmaxf(fabsf(bmin[k]), fabsf(bmin[k] + ext[k])));
+    hdr->box_pad = amax * 4.76837158203125e-07f;
+  }
   __syncthreads();
   const int stride = gridDim.x * kThreads;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n_state_words; i += stride) tile_state[i] = 0u;
@@ -311,6 +319,7 @@ k_emit_climb(const float* __restrict__ verts, const int* __restrict__ faces, con
   __shared__ ClimbSlot s_slot[kClimbThreads][2];  // [left child | right child]; its head doubles as s_tbox until phase 3
   __shared__ int s_lead[kClimbThreads];           // (first - B0) | count << 16 of the compacted leaves
   __shared__ int s_wcount[kClimbWarps];
+  __shared__ unsigned char s_info[kClimbThreads];
   float(*s_tbox)[6] = reinterpret_cast<float(*)[6]>(&s_slot[0][0]);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int B0 = blockIdx.x * kClimbThreads;
@@ -378,13 +387,7 @@ k_emit_climb(const float* __restrict__ verts, const int* __restrict__ faces, con
       tris[p] = t;
       c0[p] = make_int4((int)(float)__ldg(colors + 3 * (size_t)i0), (int)(float)__ldg(colors + 3 * (size_t)i0 + 1),
                         (int)(float)__ldg(colors + 3 * (size_t)i0 + 2), f);
-      // conservative leaf box: pad by 2^-21 of the scene's largest |coordinate| so that rounding in
-      // the slab test can never cull a triangle the Moller-Trumbore arithmetic would accept
-      float amax = 0.f;
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        amax = fmaxf(amax, fmaxf(fabsf(vl_ordered_to_float(hdr->bounds_min[k])), fabsf(vl_ordered_to_float(hdr->bounds_max[k]))));
-      const float pad = amax * 4.76837158203125e-07f;
+      const float pad = hdr->box_pad;  // set by k_morton
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         bmin[k] = fminf(v0[k], fminf(v1[k], v2[k])) - pad;
@@ -405,23 +408,43 @@ k_emit_climb(const float* __restrict__ verts, const int* __restrict__ faces, con
   }
   __syncthreads();
   // ---- phase 2: the leaf (maximal local sub-tree of <= VL_LEAF_MAX triangles) this triangle belongs to ----
+  // Node i covers keys [i - Lx, i + 1 + Rx], Lx / Rx = how many deltas directly left / right of delta(i) are
+  // smaller than it.  Small nodes (<= 4 keys) have Lx + Rx <= 2, so three comparisons per side decide it --
+  // no loops, no divergence.  s_info[k]: 0 = not a small local node, else 0x10 | Lx | Rx << 2.
+  {
+    unsigned int info = 0;
+    if (s_local[tid]) {  // node p is local: its range ends inside the CTA, the windows never leave s_delta
+      int lx = 0, rx = 0;
+      bool go = true;
+#pragma unroll
+      for (int j = 1; j <= 3; ++j) {
+        go = go && (tid - j >= -1) && s_delta[1 + tid - j] < dl;
+        lx += go ? 1 : 0;
+      }
+      go = true;
+#pragma unroll
+      for (int j = 1; j <= 3; ++j) {
+        go = go && (tid + j < kClimbThreads) && s_delta[1 + tid + j] < dl;
+        rx += go ? 1 : 0;
+      }
+      if (lx + rx <= VL_LEAF_MAX - 2) info = 0x10u | (unsigned)lx | ((unsigned)rx << 2);
+    }
+    s_info[tid] = (unsigned char)info;
+  }
+  __syncthreads();
   int l = p, r = p;
   if (active) {
-    while (r - l + 1 < VL_LEAF_MAX) {
-      const bool is_left = (l == 0) ? true : ((r == n - 1) ? false : (s_delta[1 + r - B0] < s_delta[l - B0]));
-      const int parent = is_left ? r : l - 1;
-      if (parent < B0 || parent > B1 - 2 || !s_local[parent - B0]) break;
-      const unsigned long long dp = s_delta[1 + parent - B0];
-      int nl = l, nr = r;
-      if (is_left) {
-        nr = r + 1;
-        while (nr - nl + 1 <= VL_LEAF_MAX && s_delta[1 + nr - B0] < dp) ++nr;
-      } else {
-        nl = l - 1;
-        while (nr - nl + 1 <= VL_LEAF_MAX && s_delta[nl - B0] < dp) --nl;
+    // the small local nodes that contain key p are nested (they are ancestors of leaf p): take the largest
+    int best = 1;
+#pragma unroll
+    for (int j = -(VL_LEAF_MAX - 1); j <= VL_LEAF_MAX - 2; ++j) {
+      const int k = tid + j;  // candidate node
+      if (k >= 0 && k < kClimbThreads) {
+        const unsigned int info = s_info[k];
+        const int nl = k - (int)(info & 3u), nr = k + 1 + (int)((info >> 2) & 3u);
+        const int size = nr - nl + 1;
+        if (info && nl <= tid && tid <= nr && size > best) { best = size; l = B0 + nl; r = B0 + nr; }
       }
-      if (nr - nl + 1 > VL_LEAF_MAX) break;
-      l = nl; r = nr;
     }
   }
   // ---- phase 3: compact the first thread of every leaf to the front of the CTA ----

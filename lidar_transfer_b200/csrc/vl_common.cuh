@@ -79,7 +79,8 @@ struct VlHeader {
   unsigned int bounds_min[3];  // order-preserving uint encoding of float
   unsigned int bounds_max[3];
   int n_pending;               // nodes queued by k_emit_climb for k_top_climb
-  int pad[53];
+  float box_pad;               // conservative leaf-box padding (k_morton)
+  int pad[52];
 };
 static_assert(sizeof(VlHeader) == 256, "header is 256 B");
 
