@@ -173,12 +173,12 @@ __global__ void __launch_bounds__(VL_SORT_THREADS)
 k_sort_pass(const unsigned int* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
             unsigned int* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int n, int shift,
             const unsigned int* __restrict__ ghist, volatile unsigned int* tile_state, unsigned int* ticket) {
-  __shared__ unsigned int cnt[kSortWarps][256];
+  __shared__ __align__(16) unsigned int cnt[kSortWarps][256];
   __shared__ unsigned int warp_sums[8];
   __shared__ int s_tile;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
-  for (int k = tid; k < kSortWarps * 256; k += VL_SORT_THREADS) (&cnt[0][0])[k] = 0u;
+  for (int k = tid; k < kSortWarps * 64; k += VL_SORT_THREADS) reinterpret_cast<uint4*>(&cnt[0][0])[k] = make_uint4(0u, 0u, 0u, 0u);
   // exclusive scan of the global digit histogram: thread d (< 256) -> first output slot of digit d
   unsigned int gcount = 0, incl = 0;
   if (tid < 256) {
@@ -242,13 +242,27 @@ k_sort_pass(const unsigned int* __restrict__ keys_in, const unsigned int* __rest
       *mine = kStPrefix | run;
     } else {
       *mine = kStAggregate | run;
+      // look back over the predecessors, kLookBack tiles per round trip (the loads of one round are independent;
+      // a virtual tile -1 holds the prefix 0)
+      constexpr int kLookBack = 8;
       int t = tile - 1;
       while (true) {
-        const unsigned int st = tile_state[(size_t)t * 256 + tid];
-        if ((st >> 30) == 0u) { __nanosleep(32); continue; }  // predecessor has not published yet
-        before += st & kStMask;
-        if ((st >> 30) == 2u) break;
-        --t;
+        unsigned int st[kLookBack];
+#pragma unroll
+        for (int k = 0; k < kLookBack; ++k) st[k] = (t - k >= 0) ? tile_state[(size_t)(t - k) * 256 + tid] : (2u << 30);
+        bool done = false;
+        int used = 0;
+#pragma unroll
+        for (int k = 0; k < kLookBack; ++k) {
+          if (!done && used == k && (st[k] >> 30) != 0u) {
+            before += st[k] & kStMask;
+            ++used;
+            done = (st[k] >> 30) == 2u;
+          }
+        }
+        if (done) break;
+        t -= used;
+        if (used == 0) __nanosleep(32);  // the nearest predecessor has not published yet
       }
       *mine = kStPrefix | (before + run);
     }
