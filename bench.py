@@ -139,7 +139,7 @@ def run_reference(args):
   rays = create_rays(FOV_UP, FOV_DOWN, H, W)
   scenes = make_scenes(0, 2)
   cores = os.cpu_count()
-  os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+  os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core
   times, kind = time_reference(scenes, rays, n_calls=args.steps, warmup=min(args.warmup, 1))
   total = sum(times)
   value = args.steps * H * W / total / 1e6
@@ -163,6 +163,9 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_native(args):
+  # stdout carries exactly ONE line (the JSON): everything libraries print there (e.g. "NCCL version ...") goes to stderr
+  json_fd = os.dup(1)
+  os.dup2(2, 1)
   import torch
   import torch.distributed as dist
   rank = int(os.environ.get("RANK", "0"))
@@ -300,8 +303,9 @@ def run_native(args):
 
   # cpu baseline: the reference C++ ray tracer on a bounded sample of the same scans
   cpu = None
-  if not args.no_cpu_baseline:
+  if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
     n_calls = min(args.cpu_scans, S)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     times, kind = time_reference(scenes, rays_np, n_calls=n_calls, warmup=0)
     cpu_val = n_calls * H * W / sum(times) / 1e6
     cpu = {"value": cpu_val, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": kind,
@@ -331,7 +335,7 @@ def run_native(args):
       "clocks": clocks,
       "hit_fraction": hit_frac,
   }
-  print(json.dumps(line))
+  os.write(json_fd, (json.dumps(line) + "\n").encode())
   if world > 1:
     dist.destroy_process_group()
 

@@ -154,7 +154,7 @@ int vl_tsdf_integrate(float* d_tsdf, float* d_weight, float* d_color, float* d_r
  * flat normals), d_colors u8[9T] = (r, g, b) of the nearest voxel's folded colour with the
  * reference's uint8 wrap (:417-423), d_rem_out f32[3T].  At most capacity_tris are written.
  * ---------------------------------------------------------------------------------- */
-size_t vl_mesh_workspace_bytes(long long n_voxels);
+size_t vl_mesh_workspace_bytes(int dx, int dy, int dz);   /* ~1 byte per voxel (the cube case indices) */
 int vl_mesh_count(const float* d_tsdf, int dx, int dy, int dz, float level, void* d_workspace,
                   size_t workspace_bytes, long long* d_total, vl_stream stream);
 int vl_mesh_emit(const float* d_tsdf, const float* d_color, const float* d_rem, int dx, int dy, int dz,

@@ -226,7 +226,7 @@ class TsdfDevice:
     rem f32[N_v]) -- a triangle soup, N_v = 3 N_t.  Synchronises once (the triangle count)."""
     dev = self.tsdf.device
     n = self.dim[0] * self.dim[1] * self.dim[2]
-    need = lib().vl_mesh_workspace_bytes(n)
+    need = lib().vl_mesh_workspace_bytes(self.dim[0], self.dim[1], self.dim[2])
     ws = getattr(self, "_mesh_ws", None)
     if ws is None or ws.numel() < need:
       ws = self._mesh_ws = torch.empty(need, dtype=torch.uint8, device=dev)
