@@ -146,21 +146,23 @@ int vl_tsdf_integrate(float* d_tsdf, float* d_weight, float* d_color, float* d_r
  *
  * Replaces: TSDFVolume.get_volume + get_mesh, auxiliary/fusion_lidar.py:395-424 (D2H of three
  * volumes, scikit-image marching_cubes_lewiner at level 0 on the CPU, numpy vertex lookup).
- * Two calls because the triangle count is data dependent: vl_mesh_count sweeps the volume
- * and leaves per-chunk offsets in the workspace and the grand total in d_total (device
- * long long[1]); the caller reads it, allocates, and calls vl_mesh_emit with the SAME
+ * Two calls because the output size is data dependent: vl_mesh_count sweeps the volume,
+ * leaves per-cube case indices and per-unit offsets in the workspace and the grand totals in
+ * d_totals (device long long[2]: [0] triangles T, [1] active cubes A); the caller reads them,
+ * allocates the outputs plus an 8*A-byte scratch list, and calls vl_mesh_emit with the SAME
  * workspace.  Output is a triangle soup in cube order: d_verts f32[9T] (world frame,
  * verts * voxel_size + origin, :412), d_faces i32[3T] = 0..3T-1, d_norms f32[9T] (nullable,
  * flat normals), d_colors u8[9T] = (r, g, b) of the nearest voxel's folded colour with the
- * reference's uint8 wrap (:417-423), d_rem_out f32[3T].  At most capacity_tris are written.
+ * reference's uint8 wrap (:417-423), d_rem_out f32[3T].
  * ---------------------------------------------------------------------------------- */
 size_t vl_mesh_workspace_bytes(int dx, int dy, int dz);   /* ~1 byte per voxel (the cube case indices) */
 int vl_mesh_count(const float* d_tsdf, int dx, int dy, int dz, float level, void* d_workspace,
-                  size_t workspace_bytes, long long* d_total, vl_stream stream);
+                  size_t workspace_bytes, long long* d_totals, vl_stream stream);
 int vl_mesh_emit(const float* d_tsdf, const float* d_color, const float* d_rem, int dx, int dy, int dz,
                  float level, float voxel_size, const float vol_origin[3], const void* d_workspace,
-                 size_t workspace_bytes, long long capacity_tris, float* d_verts, int* d_faces,
-                 float* d_norms, unsigned char* d_colors, float* d_rem_out, vl_stream stream);
+                 size_t workspace_bytes, long long n_tris, long long n_active, void* d_active_list,
+                 float* d_verts, int* d_faces, float* d_norms, unsigned char* d_colors, float* d_rem_out,
+                 vl_stream stream);
 
 /* ------------------------------------------------------------------------------------
  * measurement aids (no reference counterpart): a process-wide count of kernels launched by

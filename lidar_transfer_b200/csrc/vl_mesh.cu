@@ -4,12 +4,15 @@
 // volumes to the host (3.4 GB at the default 284 M voxels), runs scikit-image's marching_cubes_lewiner on the
 // CPU (:407) and looks vertex colours / remissions up with numpy (:409-423).  Here the volumes stay in HBM:
 //
-//   k_mesh_count  one thread per cube (cube index == voxel index of its low corner): 4 corner reads + 4 from the
-//                 neighbour lane, the 256-case index stored as one byte per cube, per-chunk triangle totals
-//   k_mesh_scan   exclusive scan of the chunk totals (single CTA) -> chunk offsets + grand total
-//   k_mesh_emit   sweep over the case bytes; a CTA-wide exclusive scan per 256-cube slab gives every cube its
-//                 output slot (cube order: deterministic, no atomics), then the slab's triangles are expanded one
-//                 per thread so that every lane works and consecutive lanes write consecutive triangles
+//   k_mesh_count    a warp sweeps a unit of 2048 consecutive cubes of one yz-plane (cube index == voxel index of
+//                   its low corner): 4 corner reads per cube, the 4 corners one step up in z come from the
+//                   neighbour lane (lane 31: from the already prefetched next step); the 256-case index is kept
+//                   as one byte per cube; per-unit totals of triangles and of active cubes
+//   k_mesh_scan     exclusive scan of both unit totals (single CTA) -> unit offsets + grand totals
+//   k_mesh_compact  sweep over the case bytes: the active cubes (1-2 % of the volume) are written, in cube order,
+//                   as (voxel index, first triangle slot) -- warp ballots / shuffles only, no barriers, no atomics
+//   k_mesh_emit     one thread per ACTIVE cube writes its 1-5 triangles (dense warps, neighbouring threads write
+//                   neighbouring slots); output order = cube order, deterministic
 //
 // Output is an indexed triangle SOUP: 3 vertices per triangle, faces = (3t, 3t+1, 3t+2).  Vertex positions,
 // world transform (verts * voxel_size + origin, float32, :412), nearest-voxel lookup (np.round = half-to-even,
@@ -23,8 +26,8 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kSlabs = 64;                       // 256-cube slabs per chunk
-constexpr int kChunk = kThreads * kSlabs;        // cubes per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kUnit = 2048;                      // cubes per warp unit (64 steps of 32)
 
 __constant__ signed char c_tri_table[256][15] = VL_MC_TRI_TABLE;
 __constant__ unsigned char c_tri_count[256] = VL_MC_TRI_COUNT;
@@ -35,215 +38,216 @@ struct MeshParams {
   float level, voxel_size, ox, oy, oz;
 };
 
-// Thread mapping of both sweeps: blockIdx.y = x (one yz-plane per grid row), blockIdx.x = chunk of kChunk
-// consecutive voxels j = y * dz + z of that plane.  Chunk c of plane x has the linear chunk id x * chunks_per_plane + c;
-// chunk ids increase with the voxel index, so triangles still come out in cube order.
-
-// Case index of the cube whose low corner is voxel (x, y, z): bit c set <=> value at corner c < level; 0 when the
-// cube leaves the volume.  Every lane of the warp must call this (shuffles): lane L holds voxel j, lane L+1 voxel
-// j+1 = the same column one step up in z, so the four z+1 corners come from the neighbour lane instead of memory.
-__device__ __forceinline__ int cube_case(const float* __restrict__ plane0, const MeshParams& P, int x, int j, bool in_plane) {
-  const int yz = P.dy * P.dz;
-  const int y = j / P.dz, z = j - y * P.dz;
-  const bool x1 = x + 1 < P.dx, y1 = in_plane && (y + 1 < P.dy);
-  // corner (cx, cy, 0)
-  float v00 = 1.f, v10 = 1.f, v01 = 1.f, v11 = 1.f;
-  if (in_plane) {
-    v00 = __ldg(plane0 + j);
-    if (x1) v10 = __ldg(plane0 + yz + j);
-    if (y1) v01 = __ldg(plane0 + j + P.dz);
-    if (x1 && y1) v11 = __ldg(plane0 + yz + j + P.dz);
-  }
-  // corner (cx, cy, 1) = the neighbour lane's (cx, cy, 0)
-  float w00 = __shfl_down_sync(0xffffffffu, v00, 1), w10 = __shfl_down_sync(0xffffffffu, v10, 1);
-  float w01 = __shfl_down_sync(0xffffffffu, v01, 1), w11 = __shfl_down_sync(0xffffffffu, v11, 1);
-  const bool valid = in_plane && x1 && y1 && (z + 1 < P.dz);
-  if (valid && (threadIdx.x & 31) == 31) {  // the last lane has no neighbour
-    w00 = __ldg(plane0 + j + 1); w10 = __ldg(plane0 + yz + j + 1);
-    w01 = __ldg(plane0 + j + P.dz + 1); w11 = __ldg(plane0 + yz + j + P.dz + 1);
-  }
-  if (!valid) return 0;
-  const float L = P.level;
-  return (v00 < L ? 1 : 0) | (v10 < L ? 2 : 0) | (v01 < L ? 4 : 0) | (v11 < L ? 8 : 0) |
-         (w00 < L ? 16 : 0) | (w10 < L ? 32 : 0) | (w01 < L ? 64 : 0) | (w11 < L ? 128 : 0);
-}
+// Unit u of plane x (x = blockIdx.y) covers voxels j = y * dz + z in [u * kUnit, (u + 1) * kUnit) of that plane; the
+// linear unit id x * units_per_plane + u increases with the voxel index, so everything stays in cube order.
 
 __global__ void __launch_bounds__(kThreads)
-k_mesh_count(const float* __restrict__ tsdf, const MeshParams P, int chunks_per_plane, int* __restrict__ chunk_count,
-             unsigned char* __restrict__ cases) {
-  __shared__ int s_sum[kThreads / 32];
+k_mesh_count(const float* __restrict__ tsdf, const MeshParams P, int units_per_plane, int* __restrict__ unit_tris,
+             int* __restrict__ unit_active, unsigned char* __restrict__ cases) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int u = blockIdx.x * kWarps + wid;
+  if (u >= units_per_plane) return;  // warp-uniform
   const int x = blockIdx.y, yz = P.dy * P.dz;
   const float* plane0 = tsdf + (size_t)x * yz;
   unsigned char* cases0 = cases + (size_t)x * yz;
-  int mine = 0;
-  for (int s = 0; s < kSlabs; ++s) {
-    const int j = blockIdx.x * kChunk + s * kThreads + threadIdx.x;
-    const bool in_plane = j < yz;
-    const int m = cube_case(plane0, P, x, in_plane ? j : 0, in_plane);
-    if (in_plane) {
-      cases0[j] = (unsigned char)m;
-      mine += c_tri_count[m];
+  const bool x1 = x + 1 < P.dx;
+  const float L = P.level;
+  int j = u * kUnit + lane;
+  int y = j / P.dz, z = j - y * P.dz;
+  // the four z-low corners of voxel j: (x, y), (x+1, y), (x, y+1), (x+1, y+1); 1.0 (= empty space) outside the volume
+  auto fetch = [&](int jj, int yy, float* v) {
+    v[0] = v[1] = v[2] = v[3] = 1.f;
+    if (jj < yz) {
+      const bool y1 = yy + 1 < P.dy;
+      v[0] = __ldg(plane0 + jj);
+      if (x1) v[1] = __ldg(plane0 + yz + jj);
+      if (y1) v[2] = __ldg(plane0 + jj + P.dz);
+      if (x1 && y1) v[3] = __ldg(plane0 + yz + jj + P.dz);
     }
-    if ((blockIdx.x * kChunk + (s + 1) * kThreads) >= yz) break;  // uniform: the plane ends inside this chunk
+  };
+  float cur[4], nxt[4];
+  fetch(j, y, cur);
+  int n_tris = 0, n_active = 0;
+  for (int step = 0; step < kUnit / 32; ++step) {
+    // voxel j + 32 (the next step) is fetched before this step's cases are formed
+    int jn = j + 32, yn = y, zn = z + 32;
+    while (zn >= P.dz) { zn -= P.dz; ++yn; }
+    fetch(jn, yn, nxt);
+    int m = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float up = __shfl_down_sync(0xffffffffu, cur[c], 1);  // voxel j + 1 = one step up in z (if z + 1 < dz)
+      const float wrap = __shfl_sync(0xffffffffu, nxt[c], 0);     // lane 31: voxel j + 1 is lane 0 of the next step
+      const float w = lane == 31 ? wrap : up;
+      m |= (cur[c] < L ? (1 << c) : 0) | (w < L ? (16 << c) : 0);
+    }
+    const bool valid = j < yz && x1 && (y + 1 < P.dy) && (z + 1 < P.dz);
+    if (!valid) m = 0;
+    if (j < yz) cases0[j] = (unsigned char)m;
+    const int cnt = c_tri_count[m];
+    n_tris += cnt;
+    n_active += cnt > 0 ? 1 : 0;
+    j = jn; y = yn; z = zn;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cur[c] = nxt[c];
+    if (u * kUnit + (step + 1) * 32 >= yz) break;  // warp-uniform: the plane ends inside this unit
   }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
-  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = mine;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) t += s_sum[w];
-    chunk_count[x * chunks_per_plane + blockIdx.x] = t;
+  for (int off = 16; off > 0; off >>= 1) {
+    n_tris += __shfl_xor_sync(0xffffffffu, n_tris, off);
+    n_active += __shfl_xor_sync(0xffffffffu, n_active, off);
+  }
+  if (lane == 0) {
+    unit_tris[x * units_per_plane + u] = n_tris;
+    unit_active[x * units_per_plane + u] = n_active;
   }
 }
 
-// single CTA: chunk_offset[c] = sum of chunk_count[0..c), total[0] = grand total (long long)
+// single CTA: exclusive scans of both unit totals; totals[0] = triangles, totals[1] = active cubes
 __global__ void __launch_bounds__(1024)
-k_mesh_scan(const int* __restrict__ chunk_count, long long* __restrict__ chunk_offset, int n_chunks,
-            long long* __restrict__ total) {
-  __shared__ long long warp_sums[32];
-  __shared__ long long carry_s;
+k_mesh_scan(const int* __restrict__ unit_tris, const int* __restrict__ unit_active, long long* __restrict__ tri_offset,
+            long long* __restrict__ act_offset, int n_units, long long* __restrict__ totals) {
+  __shared__ long long warp_sums[2][32];
+  __shared__ long long carry_s[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry_s = 0;
+  if (tid < 2) carry_s[tid] = 0;
   __syncthreads();
-  for (int base = 0; base < n_chunks; base += 1024) {
+  for (int base = 0; base < n_units; base += 1024) {
     const int idx = base + tid;
-    const long long v = idx < n_chunks ? (long long)chunk_count[idx] : 0ll;
-    long long incl = v;
+    const long long v0 = idx < n_units ? (long long)unit_tris[idx] : 0ll, v1 = idx < n_units ? (long long)unit_active[idx] : 0ll;
+    long long i0 = v0, i1 = v1;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      const long long t = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += t;
+      const long long t0 = __shfl_up_sync(0xffffffffu, i0, off), t1 = __shfl_up_sync(0xffffffffu, i1, off);
+      if (lane >= off) { i0 += t0; i1 += t1; }
     }
-    if (lane == 31) warp_sums[wid] = incl;
+    if (lane == 31) { warp_sums[0][wid] = i0; warp_sums[1][wid] = i1; }
     __syncthreads();
-    if (wid == 0) {
-      const long long ws = warp_sums[lane];
+    if (wid < 2) {
+      const long long ws = warp_sums[wid][lane];
       long long wi = ws;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const long long t = __shfl_up_sync(0xffffffffu, wi, off);
         if (lane >= off) wi += t;
       }
-      warp_sums[lane] = wi - ws;
+      warp_sums[wid][lane] = wi - ws;
     }
     __syncthreads();
-    const long long excl = carry_s + warp_sums[wid] + (incl - v);
-    if (idx < n_chunks) chunk_offset[idx] = excl;
+    const long long e0 = carry_s[0] + warp_sums[0][wid] + (i0 - v0), e1 = carry_s[1] + warp_sums[1][wid] + (i1 - v1);
+    if (idx < n_units) { tri_offset[idx] = e0; act_offset[idx] = e1; }
     __syncthreads();
-    if (tid == 1023) carry_s = excl + v;
+    if (tid == 1023) { carry_s[0] = e0 + v0; carry_s[1] = e1 + v1; }
     __syncthreads();
   }
-  if (tid == 0) total[0] = carry_s;
+  if (tid == 0) { totals[0] = carry_s[0]; totals[1] = carry_s[1]; }
 }
 
-// Second sweep: reads the case byte of every cube (1 B instead of 8 floats), gives every cube its output slot with
-// a CTA-wide scan per 256-cube slab, then EXPANDS: triangle t of the slab is produced by thread t % 256 (binary
-// search of t in the slab's offsets), so all lanes work and consecutive lanes write consecutive triangles.
+// active cubes in cube order: list[i] = (voxel index, first triangle slot)
 __global__ void __launch_bounds__(kThreads)
-k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol, const float* __restrict__ rem_vol,
-            const MeshParams P, int chunks_per_plane, const unsigned char* __restrict__ cases,
-            const long long* __restrict__ chunk_offset, long long capacity, float* __restrict__ verts,
-            int* __restrict__ faces, float* __restrict__ norms, unsigned char* __restrict__ colors,
-            float* __restrict__ rem_out) {
-  __shared__ int s_warp[kThreads / 32];
-  __shared__ int s_off[kThreads + 1];       // exclusive triangle offsets of the slab's cubes
-  __shared__ unsigned char s_case[kThreads];
-  __shared__ long long s_run;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+k_mesh_compact(const MeshParams P, int units_per_plane, const unsigned char* __restrict__ cases,
+               const int* __restrict__ unit_tris, const long long* __restrict__ tri_offset,
+               const long long* __restrict__ act_offset, long long n_active, uint2* __restrict__ list) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int u = blockIdx.x * kWarps + wid;
+  if (u >= units_per_plane) return;
   const int x = blockIdx.y, yz = P.dy * P.dz;
-  const float* plane0 = tsdf + (size_t)x * yz;
+  const int unit = x * units_per_plane + u;
+  if (unit_tris[unit] == 0) return;  // nothing active in this unit
   const unsigned char* cases0 = cases + (size_t)x * yz;
-  if (tid == 0) s_run = chunk_offset[x * chunks_per_plane + blockIdx.x];
-  for (int s = 0; s < kSlabs; ++s) {
-    const int j0 = blockIdx.x * kChunk + s * kThreads;
-    if (j0 >= yz) break;
-    const int j = j0 + tid;
+  long long tri_run = tri_offset[unit], act_run = act_offset[unit];
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  for (int step = 0; step < kUnit / 32; ++step) {
+    const int j = u * kUnit + step * 32 + lane;
+    if (u * kUnit + step * 32 >= yz) break;
     const int m = j < yz ? cases0[j] : 0;
     const int cnt = c_tri_count[m];
-    if (__syncthreads_or(cnt) == 0) continue;  // nothing to emit in this slab (also orders s_run / s_off reuse)
+    const unsigned int bal = __ballot_sync(0xffffffffu, cnt > 0);
+    if (bal == 0u) continue;
     int incl = cnt;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, off);
       if (lane >= off) incl += t;
     }
-    if (lane == 31) s_warp[wid] = incl;
-    s_case[tid] = (unsigned char)m;
-    __syncthreads();
-    int before = 0, slab_total = 0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) {
-      const int t = s_warp[w];
-      if (w < wid) before += t;
-      slab_total += t;
+    if (cnt > 0) {
+      const long long slot = act_run + __popc(bal & lt_mask);
+      if (slot < n_active) list[slot] = make_uint2((unsigned int)(x * yz + j), (unsigned int)(tri_run + incl - cnt));
     }
-    s_off[tid] = before + incl - cnt;
-    if (tid == 0) s_off[kThreads] = slab_total;
-    const long long run = s_run;
-    __syncthreads();
-    if (tid == 0) s_run = run + slab_total;
-    for (int t = tid; t < slab_total; t += kThreads) {
-      const long long tri = run + t;
-      if (tri >= capacity) break;
-      // source cube: the last slot whose offset is <= t
-      int lo = 0, hi = kThreads - 1;
+    tri_run += __shfl_sync(0xffffffffu, incl, 31);
+    act_run += __popc(bal);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol, const float* __restrict__ rem_vol,
+            const MeshParams P, const unsigned char* __restrict__ cases, const uint2* __restrict__ list, long long n_active,
+            long long capacity, float* __restrict__ verts, int* __restrict__ faces, float* __restrict__ norms,
+            unsigned char* __restrict__ colors, float* __restrict__ rem_out) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n_active) return;
+  const uint2 ent = list[i];
+  const int vi = (int)ent.x, yz = P.dy * P.dz;
+  const int mc = cases[vi];
+  const int x = vi / yz, jj = vi - x * yz, y = jj / P.dz, z = jj - y * P.dz;
+  const float* cube0 = tsdf + vi;
+  float v[8];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (s_off[mid] <= t) lo = mid; else hi = mid - 1;
-      }
-      const int src = lo, local = t - s_off[src], mc = s_case[src];
-      const int jj = j0 + src, y = jj / P.dz, z = jj - y * P.dz;
-      float pw[3][3];
+  for (int c = 0; c < 8; ++c) v[c] = __ldg(cube0 + (size_t)(c & 1) * yz + ((c >> 1) & 1) * P.dz + ((c >> 2) & 1));
+  const int cnt = c_tri_count[mc];
+  for (int t = 0; t < cnt; ++t) {
+    const long long tri = (long long)ent.y + t;
+    if (tri >= capacity) break;
+    float pw[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int e = c_tri_table[mc][3 * t + k];
+      const int ca = c_edge_corners[e][0], cb = c_edge_corners[e][1];
+      // vertex on the edge ca -> cb (cb = ca + one axis step), float32 like skimage's output
+      float va = v[0], vb = v[0];
+#pragma unroll
+      for (int c = 1; c < 8; ++c) { va = ca == c ? v[c] : va; vb = cb == c ? v[c] : vb; }
+      const float tt = __fdiv_rn(__fsub_rn(P.level, va), __fsub_rn(vb, va));
+      float pv[3] = {(float)(x + (ca & 1)), (float)(y + ((ca >> 1) & 1)), (float)(z + ((ca >> 2) & 1))};
+      const int axis = (ca ^ cb) == 1 ? 0 : ((ca ^ cb) == 2 ? 1 : 2);
+      pv[0] = axis == 0 ? __fadd_rn(pv[0], tt) : pv[0];
+      pv[1] = axis == 1 ? __fadd_rn(pv[1], tt) : pv[1];
+      pv[2] = axis == 2 ? __fadd_rn(pv[2], tt) : pv[2];
+      // nearest voxel (np.round: half to even), clamped to the volume
+      const int ix = min(max(__float2int_rn(pv[0]), 0), P.dx - 1);
+      const int iy = min(max(__float2int_rn(pv[1]), 0), P.dy - 1);
+      const int iz = min(max(__float2int_rn(pv[2]), 0), P.dz - 1);
+      const long long ni = ((long long)ix * P.dy + iy) * P.dz + iz;
+      const float rgb = __ldg(color_vol + ni);
+      // fusion_lidar.py:417-423 (float32 arithmetic, then astype(uint8) wraps modulo 256)
+      const float cb_ = floorf(__fdiv_rn(rgb, 65536.0f));
+      const float cg_ = floorf(__fdiv_rn(__fsub_rn(rgb, __fmul_rn(cb_, 65536.0f)), 256.0f));
+      const float cr_ = __fsub_rn(__fsub_rn(rgb, __fmul_rn(cb_, 65536.0f)), __fmul_rn(cg_, 256.0f));
+      const long long vtx = 3 * tri + k;
+      colors[3 * vtx + 0] = (unsigned char)((long long)floorf(cr_) & 255);
+      colors[3 * vtx + 1] = (unsigned char)((long long)floorf(cg_) & 255);
+      colors[3 * vtx + 2] = (unsigned char)((long long)floorf(cb_) & 255);
+      rem_out[vtx] = __ldg(rem_vol + ni);
+      // :412 verts * voxel_size + origin
+      pw[k][0] = __fadd_rn(__fmul_rn(pv[0], P.voxel_size), P.ox);
+      pw[k][1] = __fadd_rn(__fmul_rn(pv[1], P.voxel_size), P.oy);
+      pw[k][2] = __fadd_rn(__fmul_rn(pv[2], P.voxel_size), P.oz);
+      verts[3 * vtx + 0] = pw[k][0];
+      verts[3 * vtx + 1] = pw[k][1];
+      verts[3 * vtx + 2] = pw[k][2];
+      faces[vtx] = (int)vtx;
+    }
+    if (norms) {  // flat normal of the triangle for all three vertices (only consumed by meshwrite)
+      const float ax = pw[1][0] - pw[0][0], ay = pw[1][1] - pw[0][1], az = pw[1][2] - pw[0][2];
+      const float bx = pw[2][0] - pw[0][0], by = pw[2][1] - pw[0][1], bz = pw[2][2] - pw[0][2];
+      float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+      const float nn = sqrtf(nx * nx + ny * ny + nz * nz);
+      if (nn > 0.f) { nx /= nn; ny /= nn; nz /= nn; }
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const int e = c_tri_table[mc][3 * local + k];
-        const int ca = c_edge_corners[e][0], cb = c_edge_corners[e][1];
-        // vertex on the edge ca -> cb (cb = ca + one axis step), float32 like skimage's output
-        const float va = __ldg(plane0 + (size_t)(ca & 1) * yz + jj + ((ca >> 1) & 1) * P.dz + ((ca >> 2) & 1));
-        const float vb = __ldg(plane0 + (size_t)(cb & 1) * yz + jj + ((cb >> 1) & 1) * P.dz + ((cb >> 2) & 1));
-        const float tt = __fdiv_rn(__fsub_rn(P.level, va), __fsub_rn(vb, va));
-        float pv[3] = {(float)(x + (ca & 1)), (float)(y + ((ca >> 1) & 1)), (float)(z + ((ca >> 2) & 1))};
-        const int axis = (ca ^ cb) == 1 ? 0 : ((ca ^ cb) == 2 ? 1 : 2);
-        pv[axis] = __fadd_rn(pv[axis], tt);
-        // nearest voxel (np.round: half to even), clamped to the volume
-        const int ix = min(max(__float2int_rn(pv[0]), 0), P.dx - 1);
-        const int iy = min(max(__float2int_rn(pv[1]), 0), P.dy - 1);
-        const int iz = min(max(__float2int_rn(pv[2]), 0), P.dz - 1);
-        const long long ni = ((long long)ix * P.dy + iy) * P.dz + iz;
-        const float rgb = __ldg(color_vol + ni);
-        // fusion_lidar.py:417-423 (float32 arithmetic, then astype(uint8) wraps modulo 256)
-        const float cb_ = floorf(__fdiv_rn(rgb, 65536.0f));
-        const float cg_ = floorf(__fdiv_rn(__fsub_rn(rgb, __fmul_rn(cb_, 65536.0f)), 256.0f));
-        const float cr_ = __fsub_rn(__fsub_rn(rgb, __fmul_rn(cb_, 65536.0f)), __fmul_rn(cg_, 256.0f));
-        const long long vtx = 3 * tri + k;
-        colors[3 * vtx + 0] = (unsigned char)((long long)floorf(cr_) & 255);
-        colors[3 * vtx + 1] = (unsigned char)((long long)floorf(cg_) & 255);
-        colors[3 * vtx + 2] = (unsigned char)((long long)floorf(cb_) & 255);
-        rem_out[vtx] = __ldg(rem_vol + ni);
-        // :412 verts * voxel_size + origin
-        pw[k][0] = __fadd_rn(__fmul_rn(pv[0], P.voxel_size), P.ox);
-        pw[k][1] = __fadd_rn(__fmul_rn(pv[1], P.voxel_size), P.oy);
-        pw[k][2] = __fadd_rn(__fmul_rn(pv[2], P.voxel_size), P.oz);
-        verts[3 * vtx + 0] = pw[k][0];
-        verts[3 * vtx + 1] = pw[k][1];
-        verts[3 * vtx + 2] = pw[k][2];
-        faces[vtx] = (int)vtx;
-      }
-      if (norms) {  // flat normal of the triangle for all three vertices (only consumed by meshwrite)
-        const float ax = pw[1][0] - pw[0][0], ay = pw[1][1] - pw[0][1], az = pw[1][2] - pw[0][2];
-        const float bx = pw[2][0] - pw[0][0], by = pw[2][1] - pw[0][1], bz = pw[2][2] - pw[0][2];
-        float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
-        const float nn = sqrtf(nx * nx + ny * ny + nz * nz);
-        if (nn > 0.f) { nx /= nn; ny /= nn; nz /= nn; }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          norms[3 * (3 * tri + k) + 0] = nx;
-          norms[3 * (3 * tri + k) + 1] = ny;
-          norms[3 * (3 * tri + k) + 2] = nz;
-        }
+        norms[3 * (3 * tri + k) + 0] = nx;
+        norms[3 * (3 * tri + k) + 1] = ny;
+        norms[3 * (3 * tri + k) + 2] = nz;
       }
     }
   }
@@ -251,22 +255,26 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
 
 }  // namespace
 
-static int mesh_chunks_per_plane(int dy, int dz) { return (int)(((long long)dy * dz + kChunk - 1) / kChunk); }
+static int mesh_units_per_plane(int dy, int dz) { return (int)(((long long)dy * dz + kUnit - 1) / kUnit); }
 
-// workspace: [chunk counts i32][chunk offsets i64][case byte per voxel]
-static size_t mesh_ws_layout(int dx, int dy, int dz, size_t* off_offsets, size_t* off_cases) {
-  const size_t n_chunks = (size_t)dx * mesh_chunks_per_plane(dy, dz);
-  size_t off = vl_align256(n_chunks * 4);
-  if (off_offsets) *off_offsets = off;
-  off = vl_align256(off + n_chunks * 8);
-  if (off_cases) *off_cases = off;
-  off = vl_align256(off + (size_t)dx * dy * dz);
-  return off;
+// workspace: [unit triangle counts i32][unit active counts i32][triangle offsets i64][active offsets i64][case byte per voxel]
+struct MeshWs { size_t tris, active, tri_off, act_off, cases, total; };
+static MeshWs mesh_ws_layout(int dx, int dy, int dz) {
+  const size_t n_units = (size_t)dx * mesh_units_per_plane(dy, dz);
+  MeshWs w;
+  size_t off = 0;
+  w.tris = off;    off = vl_align256(off + n_units * 4);
+  w.active = off;  off = vl_align256(off + n_units * 4);
+  w.tri_off = off; off = vl_align256(off + n_units * 8);
+  w.act_off = off; off = vl_align256(off + n_units * 8);
+  w.cases = off;   off = vl_align256(off + (size_t)dx * dy * dz);
+  w.total = off;
+  return w;
 }
 
 extern "C" size_t vl_mesh_workspace_bytes(int dx, int dy, int dz) {
   if (dx <= 0 || dy <= 0 || dz <= 0) return 256;
-  return mesh_ws_layout(dx, dy, dz, nullptr, nullptr);
+  return mesh_ws_layout(dx, dy, dz).total;
 }
 
 static int mesh_args(const char* who, const float* d_tsdf, int dx, int dy, int dz, const void* d_ws, size_t ws_bytes,
@@ -286,50 +294,56 @@ static int mesh_args(const char* who, const float* d_tsdf, int dx, int dy, int d
 }
 
 extern "C" int vl_mesh_count(const float* d_tsdf, int dx, int dy, int dz, float level, void* d_workspace,
-                             size_t workspace_bytes, long long* d_total, vl_stream stream_) {
+                             size_t workspace_bytes, long long* d_totals, vl_stream stream_) {
   MeshParams P;
   int rc = mesh_args("vl_mesh_count", d_tsdf, dx, dy, dz, d_workspace, workspace_bytes, &P, level, 1.f, nullptr);
   if (rc) return rc;
-  if (!d_total) { vl_set_error("vl_mesh_count: null d_total"); return VL_EINVAL; }
+  if (!d_totals) { vl_set_error("vl_mesh_count: null d_totals"); return VL_EINVAL; }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int cpp = mesh_chunks_per_plane(dy, dz);
-  size_t off_offsets, off_cases;
-  mesh_ws_layout(dx, dy, dz, &off_offsets, &off_cases);
+  const int upp = mesh_units_per_plane(dy, dz);
+  const MeshWs w = mesh_ws_layout(dx, dy, dz);
   char* ws = static_cast<char*>(d_workspace);
   { VlProfScope ps(VL_ST_MESH_COUNT, stream);
-  k_mesh_count<<<dim3(cpp, dx), kThreads, 0, stream>>>(d_tsdf, P, cpp, reinterpret_cast<int*>(ws),
-                                                      reinterpret_cast<unsigned char*>(ws + off_cases)); }
+  k_mesh_count<<<dim3((upp + kWarps - 1) / kWarps, dx), kThreads, 0, stream>>>(
+      d_tsdf, P, upp, reinterpret_cast<int*>(ws + w.tris), reinterpret_cast<int*>(ws + w.active),
+      reinterpret_cast<unsigned char*>(ws + w.cases)); }
   VL_LAUNCH_CHECK("k_mesh_count");
   { VlProfScope ps(VL_ST_MESH_SCAN, stream);
-  k_mesh_scan<<<1, 1024, 0, stream>>>(reinterpret_cast<const int*>(ws), reinterpret_cast<long long*>(ws + off_offsets),
-                                      cpp * dx, d_total); }
+  k_mesh_scan<<<1, 1024, 0, stream>>>(reinterpret_cast<const int*>(ws + w.tris), reinterpret_cast<const int*>(ws + w.active),
+                                      reinterpret_cast<long long*>(ws + w.tri_off), reinterpret_cast<long long*>(ws + w.act_off),
+                                      upp * dx, d_totals); }
   VL_LAUNCH_CHECK("k_mesh_scan");
   return VL_OK;
 }
 
 extern "C" int vl_mesh_emit(const float* d_tsdf, const float* d_color, const float* d_rem, int dx, int dy, int dz,
                             float level, float voxel_size, const float vol_origin[3], const void* d_workspace,
-                            size_t workspace_bytes, long long capacity_tris, float* d_verts, int* d_faces,
-                            float* d_norms, unsigned char* d_colors, float* d_rem_out, vl_stream stream_) {
+                            size_t workspace_bytes, long long n_tris, long long n_active, void* d_active_list,
+                            float* d_verts, int* d_faces, float* d_norms, unsigned char* d_colors, float* d_rem_out,
+                            vl_stream stream_) {
   MeshParams P;
   int rc = mesh_args("vl_mesh_emit", d_tsdf, dx, dy, dz, d_workspace, workspace_bytes, &P, level, voxel_size, vol_origin);
   if (rc) return rc;
-  if (!d_color || !d_rem || !vol_origin || capacity_tris < 0 ||
-      (capacity_tris > 0 && (!d_verts || !d_faces || !d_colors || !d_rem_out))) {
-    vl_set_error("vl_mesh_emit: invalid argument");
+  if (!d_color || !d_rem || !vol_origin || n_tris < 0 || n_active < 0 || n_tris >= (1ll << 31) / 3 ||
+      (n_tris > 0 && (!d_verts || !d_faces || !d_colors || !d_rem_out || !d_active_list || n_active == 0))) {
+    vl_set_error("vl_mesh_emit: invalid argument (n_tris %lld, n_active %lld)", n_tris, n_active);
     return VL_EINVAL;
   }
-  if (capacity_tris == 0) return VL_OK;
+  if (n_tris == 0) return VL_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int cpp = mesh_chunks_per_plane(dy, dz);
-  size_t off_offsets, off_cases;
-  mesh_ws_layout(dx, dy, dz, &off_offsets, &off_cases);
+  const int upp = mesh_units_per_plane(dy, dz);
+  const MeshWs w = mesh_ws_layout(dx, dy, dz);
   const char* ws = static_cast<const char*>(d_workspace);
+  const unsigned char* cases = reinterpret_cast<const unsigned char*>(ws + w.cases);
+  uint2* list = static_cast<uint2*>(d_active_list);
+  { VlProfScope ps(VL_ST_MESH_COMPACT, stream);
+  k_mesh_compact<<<dim3((upp + kWarps - 1) / kWarps, dx), kThreads, 0, stream>>>(
+      P, upp, cases, reinterpret_cast<const int*>(ws + w.tris), reinterpret_cast<const long long*>(ws + w.tri_off),
+      reinterpret_cast<const long long*>(ws + w.act_off), n_active, list); }
+  VL_LAUNCH_CHECK("k_mesh_compact");
   VlProfScope ps(VL_ST_MESH_EMIT, stream);
-  k_mesh_emit<<<dim3(cpp, dx), kThreads, 0, stream>>>(d_tsdf, d_color, d_rem, P, cpp,
-                                                     reinterpret_cast<const unsigned char*>(ws + off_cases),
-                                                     reinterpret_cast<const long long*>(ws + off_offsets), capacity_tris,
-                                                     d_verts, d_faces, d_norms, d_colors, d_rem_out);
+  k_mesh_emit<<<(unsigned)((n_active + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
+      d_tsdf, d_color, d_rem, P, cases, list, n_active, n_tris, d_verts, d_faces, d_norms, d_colors, d_rem_out);
   VL_LAUNCH_CHECK("k_mesh_emit");
   return VL_OK;
 }

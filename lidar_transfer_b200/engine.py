@@ -230,20 +230,23 @@ class TsdfDevice:
     ws = getattr(self, "_mesh_ws", None)
     if ws is None or ws.numel() < need:
       ws = self._mesh_ws = torch.empty(need, dtype=torch.uint8, device=dev)
-    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    totals = torch.zeros(2, dtype=torch.int64, device=dev)
     origin = (ctypes.c_float * 3)(*[float(v) for v in self.origin])
     with torch.cuda.device(dev):
       check(lib().vl_mesh_count(_ptr(self.tsdf), self.dim[0], self.dim[1], self.dim[2], float(level), _ptr(ws),
-                                ws.numel(), _ptr(total), _stream()))
-      n_t = int(total.item())
+                                ws.numel(), _ptr(totals), _stream()))
+      n_t, n_a = (int(v) for v in totals.tolist())  # the one host synchronisation of the extraction
       out = dict(verts=torch.empty((3 * n_t, 3), dtype=torch.float32, device=dev),
                  faces=torch.empty((n_t, 3), dtype=torch.int32, device=dev),
                  norms=torch.empty((3 * n_t, 3), dtype=torch.float32, device=dev) if want_norms else None,
                  colors=torch.empty((3 * n_t, 3), dtype=torch.uint8, device=dev),
                  rem=torch.empty(3 * n_t, dtype=torch.float32, device=dev))
+      active = torch.empty(max(n_a, 1), dtype=torch.int64, device=dev)
       check(lib().vl_mesh_emit(_ptr(self.tsdf), _ptr(self.color), _ptr(self.rem), self.dim[0], self.dim[1], self.dim[2],
-                               float(level), self.voxel_size, origin, _ptr(ws), ws.numel(), n_t, _ptr(out["verts"]),
-                               _ptr(out["faces"]), _ptr(out["norms"]), _ptr(out["colors"]), _ptr(out["rem"]), _stream()))
+                               float(level), self.voxel_size, origin, _ptr(ws), ws.numel(), n_t, n_a, _ptr(active),
+                               _ptr(out["verts"]), _ptr(out["faces"]), _ptr(out["norms"]), _ptr(out["colors"]),
+                               _ptr(out["rem"]), _stream()))
+      out["n_active_cubes"] = n_a
     return out
 
 
