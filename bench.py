@@ -41,6 +41,15 @@ WORKLOAD = "c5-synthetic-1Mtri-64x2048"
 METRIC = "Mrays/s (LBVH build + closest-hit trace per scan, 64x2048 target, ~1M-tri mesh per scan)"
 
 
+def _ncu_traffic(kernel):
+  """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
+  p = os.path.join(ROOT, "profiles", "r01_%s_ncu_full.json" % kernel)
+  try:
+    return float(json.load(open(p))["dram_bytes_per_launch"])
+  except (OSError, KeyError, ValueError):
+    return None
+
+
 def _peaks():
   p = os.path.join(ROOT, "MEASURED_PEAKS.json")
   if os.path.exists(p):
@@ -326,7 +335,7 @@ def run_native(args):
               "scans_per_s": S * world * K / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / K},
       "gpu_launches": int(launches),
       "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                   "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                   "frac": achieved / peak, "traffic": _ncu_traffic(dom), "peak_source": peak_src,
                    "alg_bytes_per_launch": alg_bytes.get(dom, 0.0), "ms_per_launch": dom_ms / dom_n,
                    "step_alg_bytes": sum(alg_bytes[k] * (4 if k == "sort_pass" else 1) for k in alg_bytes) * S,
                    "profiled_ms_per_step": ms_prof / K},

@@ -21,7 +21,8 @@ constexpr int kThreads = 256;
 struct TsdfParams {
   int dx, dy, dz;
   float ox, oy, oz;
-  float voxel_size, trunc_margin, obs_weight, fov_up_deg, fov_down_deg;
+  float voxel_size, trunc_margin, obs_weight;
+  float fov_up, fov_down;  // radians: float(deg * PI / 180.0) evaluated in double on the host, like :119-120 per thread
   int im_h, im_w;
 };
 
@@ -59,8 +60,7 @@ k_tsdf_integrate(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, f
   float cam_pt_x = pt_x, cam_pt_z = pt_z, cam_pt_y = pt_y;
   // :119-128
   int im_h = P.im_h, im_w = P.im_w;
-  float fov_up = P.fov_up_deg * VL_PI / 180.0;
-  float fov_down = P.fov_down_deg * VL_PI / 180.0;
+  const float fov_up = P.fov_up, fov_down = P.fov_down;  // :119-120, hoisted (same IEEE double expression on the host)
   float fov = fabsf(fov_up) + fabsf(fov_down);
   float depth = norm3df(cam_pt_x, cam_pt_y, cam_pt_z);
   float yaw = -atan2f(cam_pt_y, cam_pt_x);
@@ -142,7 +142,8 @@ extern "C" int vl_tsdf_integrate(float* d_tsdf, float* d_weight, float* d_color,
   P.dx = dx; P.dy = dy; P.dz = dz;
   P.ox = vol_origin[0]; P.oy = vol_origin[1]; P.oz = vol_origin[2];
   P.voxel_size = voxel_size; P.trunc_margin = trunc_margin; P.obs_weight = obs_weight;
-  P.fov_up_deg = fov_up_deg; P.fov_down_deg = fov_down_deg;
+  P.fov_up = fov_up_deg * VL_PI / 180.0;      // float * double / double -> float, exactly the kernel-string expression
+  P.fov_down = fov_down_deg * VL_PI / 180.0;
   P.im_h = im_h; P.im_w = im_w;
   const unsigned int nb = (unsigned int)((n_vox + kThreads - 1) / kThreads);
   VlProfScope ps(VL_ST_TSDF_INTEGRATE, stream);
