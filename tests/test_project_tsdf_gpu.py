@@ -48,3 +48,63 @@ def test_tsdf_integrate_matches_oracle(engine, oracle):
   for k in ("tsdf", "rem"):
     err = np.abs(g[k][ok] - vol[k][ok])
     assert (err > 1e-5).sum() <= 1e-4 * n, (k, (err > 1e-5).sum())
+
+
+def test_projection_edge_cases(engine, oracle):
+  """No points, every point outside the vertical FOV, exact depth ties (first index wins, laserscan.py:376-382) and
+  float64 depths that collapse onto one float32 value (the sequential loop's last-smaller-wins rule)."""
+  H, W, fu, fd = 8, 32, 3.0, -25.0
+  z = np.zeros((0, 3), np.float64)
+  got = engine.project(z, np.zeros(0, np.float32), np.zeros(0, np.uint32), fu, fd, H, W)
+  assert int(got["n_kept"].item()) == 0 and (got["index"].cpu().numpy() == -1).all() and (got["range_image"].cpu().numpy() == 0).all()
+  assert (got["proj_remissions"].cpu().numpy() == -1).all()
+  up = np.tile(np.array([[1.0, 0.0, 5.0]]), (50, 1))  # pitch ~ 79 deg: outside the FOV
+  ref = oracle.project(up, np.ones(50, np.float32), np.full(50, 40, np.uint32), fu, fd, H, W)
+  got = engine.project(up, np.ones(50, np.float32), np.full(50, 40, np.uint32), fu, fd, H, W)
+  assert ref["n_kept"] == 0 and int(got["n_kept"].item()) == 0 and (got["index"].cpu().numpy() == -1).all()
+  # one pixel, many points: exact float64 ties, sub-float32 differences, and a nearer straggler in the middle
+  base = np.array([10.0, 0.1, -1.0])
+  eps = np.array([0.0, 0.0, 3e-9, -3e-9, 1e-12, -1e-12, 0.0, 2e-3, -2e-3, -2e-3, 5e-10])
+  pts = base[None, :] * (1.0 + eps[:, None])
+  rem = np.arange(len(eps), dtype=np.float32) / 16
+  lab = (40 + np.arange(len(eps))).astype(np.uint32)
+  for perm_seed in range(6):
+    perm = np.random.default_rng(perm_seed).permutation(len(eps))
+    ref = oracle.project(pts[perm], rem[perm], lab[perm], fu, fd, H, W)
+    chk = oracle.project_numpy(pts[perm], rem[perm], lab[perm], fu, fd, H, W)
+    got = engine.project(pts[perm], rem[perm], lab[perm], fu, fd, H, W)
+    for k in ("index", "proj_label"):
+      assert np.array_equal(ref[k], chk[k]) and np.array_equal(got[k].cpu().numpy(), ref[k]), (k, perm_seed)
+    for k in ("range_image", "proj_remissions"):
+      assert np.array_equal(got[k].cpu().numpy().view(np.int32), ref[k].view(np.int32)), (k, perm_seed)
+    assert (ref["index"] >= 0).sum() == 1
+
+
+def test_tsdf_class_switch_and_empty_image(engine, oracle):
+  """An all-empty range image writes nothing; a second integration with OTHER labels takes the class-switch branch
+  (overwrite iff dist < weight, no weight update, fusion_lidar.py:216-227)."""
+  pts, labels = synth.make_scan_points(8, 30000)
+  H, W, fu, fd = 32, 512, 3.0, -25.0
+  pr = oracle.project(pts[:, :3].astype(np.float64), pts[:, 3], labels, fu, fd, H, W)
+  vox = 0.4
+  bnds = np.array([[-16, 16], [-16, 16], [-3, 2]], np.float64)
+  dim = np.ceil((bnds[:, 1] - bnds[:, 0]) / vox).astype(int)
+  origin = bnds[:, 0].astype(np.float32)
+  dev = engine.TsdfDevice(dim, origin, vox, fu, fd)
+  zero = np.zeros((H, W), np.float32)
+  dev.integrate(zero, zero, zero)
+  assert (dev.tsdf.cpu().numpy() == 1).all() and (dev.weight.cpu().numpy() == 0).all() and (dev.color.cpu().numpy() == 0).all()
+  vol = oracle.tsdf_new_volume(dim)
+  c1 = oracle.label_to_color_im(pr["proj_label"])
+  c2 = oracle.label_to_color_im(np.where(pr["proj_label"] > 0, 99, 0))
+  closer = (pr["range_image"] * np.float32(0.98)).astype(np.float32)
+  for color_im, depth in ((c1, pr["range_image"]), (c2, closer), (c2, closer), (c1, pr["range_image"])):
+    oracle.tsdf_integrate(vol, origin, vox, color_im, depth, pr["proj_remissions"], fu, fd)
+    dev.integrate(color_im, depth, pr["proj_remissions"])
+  assert len(np.unique(vol["color"])) >= 3 and (vol["weight"] > 1).any()
+  n = vol["tsdf"].size
+  g = {k: getattr(dev, k).cpu().numpy() for k in ("tsdf", "weight", "color", "rem")}
+  differs = (g["color"] != vol["color"]) | (g["weight"] != vol["weight"])
+  assert differs.sum() <= 1e-4 * n, differs.sum()
+  for k in ("tsdf", "rem"):
+    assert (np.abs(g[k][~differs] - vol[k][~differs]) > 1e-5).sum() <= 1e-4 * n, k
