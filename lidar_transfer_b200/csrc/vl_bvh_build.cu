@@ -172,9 +172,11 @@ constexpr unsigned int kStAggregate = 1u << 30, kStPrefix = 2u << 30, kStMask = 
 __global__ void __launch_bounds__(VL_SORT_THREADS)
 k_sort_pass(const unsigned int* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
             unsigned int* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int n, int shift,
-            const unsigned int* __restrict__ ghist, volatile unsigned int* tile_state, unsigned int* ticket) {
+            const unsigned int* __restrict__ ghist, volatile unsigned int* tile_state, unsigned int* ticket, int n_tiles) {
   __shared__ __align__(16) unsigned int cnt[kSortWarps][256];
   __shared__ unsigned int warp_sums[8];
+  __shared__ unsigned int s_texcl[256], s_gbase[256];
+  __shared__ unsigned int s_keys[VL_SORT_TILE], s_vals[VL_SORT_TILE];
   __shared__ int s_tile;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
@@ -236,50 +238,104 @@ k_sort_pass(const unsigned int* __restrict__ keys_in, const unsigned int* __rest
       cnt[ww][tid] = run;
       run += c;
     }
-    volatile unsigned int* mine = tile_state + (size_t)tile * 256 + tid;
+    // Two-level decoupled look-back.  Every tile publishes its count; the count of all tiles before tile t is
+    //   (inclusive count of the previous GROUP of kGroup tiles) + (counts of the earlier tiles of t's own group).
+    // The last tile of a group publishes the group's aggregate, looks back over GROUPS (a few steps, decoupled:
+    // aggregate or inclusive, whichever is there) and publishes the group's inclusive count.  With every tile
+    // resident at once a flat look-back walks back ~t/2 tiles; this one reads <= kGroup - 1 tile words + 1 group word.
+    constexpr int kGroup = 32, kBatch = 8;
+    volatile unsigned int* group_state = tile_state + (size_t)n_tiles * 256;
+    tile_state[(size_t)tile * 256 + tid] = kStAggregate | run;
+    const int g = tile / kGroup, first = g * kGroup;
     unsigned int before = 0;
-    if (tile == 0) {
-      *mine = kStPrefix | run;
-    } else {
-      *mine = kStAggregate | run;
-      // look back over the predecessors, kLookBack tiles per round trip (the loads of one round are independent;
-      // a virtual tile -1 holds the prefix 0)
-      constexpr int kLookBack = 8;
-      int t = tile - 1;
-      while (true) {
-        unsigned int st[kLookBack];
+    for (int t = tile - 1; t >= first;) {  // the earlier tiles of this group, kBatch independent loads per round trip
+      unsigned int st[kBatch];
 #pragma unroll
-        for (int k = 0; k < kLookBack; ++k) st[k] = (t - k >= 0) ? tile_state[(size_t)(t - k) * 256 + tid] : (2u << 30);
-        bool done = false;
-        int used = 0;
+      for (int k = 0; k < kBatch; ++k) st[k] = (t - k >= first) ? tile_state[(size_t)(t - k) * 256 + tid] : (1u << 30);
+      bool ready = true;
 #pragma unroll
-        for (int k = 0; k < kLookBack; ++k) {
-          if (!done && used == k && (st[k] >> 30) != 0u) {
-            before += st[k] & kStMask;
-            ++used;
-            done = (st[k] >> 30) == 2u;
-          }
-        }
-        if (done) break;
-        t -= used;
-        if (used == 0) __nanosleep(32);  // the nearest predecessor has not published yet
-      }
-      *mine = kStPrefix | (before + run);
+      for (int k = 0; k < kBatch; ++k) ready = ready && (st[k] >> 30) != 0u;
+      if (!ready) { __nanosleep(32); continue; }
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) before += st[k] & kStMask;
+      t -= kBatch;
     }
-    const unsigned int off = gbase + before;
+    if ((tile % kGroup) == kGroup - 1) {  // this tile completes its group
+      const unsigned int group_total = before + run;
+      unsigned int groups_before = 0;
+      if (g == 0) {
+        group_state[tid] = kStPrefix | group_total;
+      } else {
+        group_state[(size_t)g * 256 + tid] = kStAggregate | group_total;
+        int t = g - 1;
+        while (true) {  // kBatch earlier groups per round trip; a virtual group -1 holds the inclusive count 0
+          unsigned int st[kBatch];
 #pragma unroll
-    for (int ww = 0; ww < kSortWarps; ++ww) cnt[ww][tid] += off;
+          for (int k = 0; k < kBatch; ++k) st[k] = (t - k >= 0) ? group_state[(size_t)(t - k) * 256 + tid] : (2u << 30);
+          bool done = false;
+          int used = 0;
+#pragma unroll
+          for (int k = 0; k < kBatch; ++k) {
+            if (!done && used == k && (st[k] >> 30) != 0u) {
+              groups_before += st[k] & kStMask;
+              ++used;
+              done = (st[k] >> 30) == 2u;
+            }
+          }
+          if (done) break;
+          t -= used;
+          if (used == 0) __nanosleep(32);
+        }
+        group_state[(size_t)g * 256 + tid] = kStPrefix | (groups_before + group_total);
+      }
+      before += groups_before;
+    } else if (g > 0) {  // inclusive count of the previous group
+      unsigned int st;
+      while (((st = group_state[(size_t)(g - 1) * 256 + tid]) >> 30) != 2u) __nanosleep(32);
+      before += st & kStMask;
+    }
+    // position of digit d inside the tile's locally sorted order (exclusive scan of `run` over the 256 digits)
+    unsigned int tincl = run;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, tincl, off);
+      if (lane >= off) tincl += t;
+    }
+    if (lane == 31) warp_sums[w] = tincl;
+    s_texcl[tid] = tincl - run;       // + the sums of the digit warps before, added after the barrier
+    s_gbase[tid] = gbase + before;    // first global slot of this tile's digit-d keys
   }
   __syncthreads();
+  if (tid < 256) {
+    unsigned int add = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww)
+      if (ww < w) add += warp_sums[ww];
+    const unsigned int texcl = s_texcl[tid] + add;
+    s_gbase[tid] -= texcl;            // global slot = s_gbase[d] + position in the tile's sorted order
+#pragma unroll
+    for (int ww = 0; ww < kSortWarps; ++ww) cnt[ww][tid] += texcl;
+  }
+  __syncthreads();
+  // stage the tile in digit order in shared memory, then write runs of equal digits with consecutive lanes:
+  // neighbouring lanes hit neighbouring addresses instead of 32 different sectors
 #pragma unroll
   for (int j = 0; j < kItems; ++j) {
     const int idx = base + j * 32 + lane;
     if (idx < n) {
       const unsigned int d = (key[j] >> shift) & 255u;
-      const unsigned int out = cnt[w][d] + rank[j];
-      keys_out[out] = key[j];
-      vals_out[out] = val[j];
+      const unsigned int lpos = cnt[w][d] + rank[j];
+      s_keys[lpos] = key[j];
+      s_vals[lpos] = val[j];
     }
+  }
+  __syncthreads();
+  const int tile_n = min(VL_SORT_TILE, n - tile * VL_SORT_TILE);
+  for (int i = tid; i < tile_n; i += VL_SORT_THREADS) {
+    const unsigned int k = s_keys[i];
+    const unsigned int out = s_gbase[(k >> shift) & 255u] + (unsigned int)i;
+    keys_out[out] = k;
+    vals_out[out] = s_vals[i];
   }
 }
 
@@ -609,7 +665,7 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
   VL_LAUNCH_CHECK("k_bounds");
   if (g_debug_build_stop == 1) return VL_OK;
   const int nt = L.n_sort_tiles;
-  const int n_state_words = 256 * VL_SORT_PASSES * nt;
+  const int n_state_words = 256 * VL_SORT_PASSES * L.n_state_tiles;
   int nb_faces = (n_faces + kThreads - 1) / kThreads;
   if (nb_faces > 148 * 4) nb_faces = 148 * 4;
   { VlProfScope ps(VL_ST_MORTON, stream);
@@ -625,7 +681,7 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
   for (int pass = 0; pass < VL_SORT_PASSES; ++pass) {
     { VlProfScope ps(VL_ST_SORT_PASS, stream);
     k_sort_pass<<<nt, VL_SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, n_faces, 8 * pass, ghist + 256 * pass,
-                                                   tile_state + (size_t)256 * nt * pass, tickets + pass); }
+                                                   tile_state + (size_t)256 * L.n_state_tiles * pass, tickets + pass, nt); }
     VL_LAUNCH_CHECK("k_sort_pass");
     kin = kout;
     vin = vout;

@@ -99,12 +99,13 @@ __host__ __device__ inline int vl_leaf_count(int ref) { return (~ref) & 7; }
 #define VL_SORT_TILE (VL_SORT_THREADS * VL_SORT_ITEMS)  // keys per radix-sort tile
 #define VL_SORT_PASSES 4                                // 8-bit digits over the 32-bit Morton key
 
-// sort scratch: [digit histograms 4 x 256 u32][4 tile tickets, padded to 256 B][tile states 4 x n_tiles x 256 u32]
+// sort scratch: [digit histograms 4 x 256 u32][4 tile tickets, padded to 256 B][tile + group states 4 x n_state_tiles x 256 u32]
 struct VlBlobLayout {
   size_t off_nodes, off_tris, off_c0, off_keys0, off_keys1, off_vals0, off_vals1, off_flags;
   size_t off_ghist, off_tickets, off_tile_state;
   size_t total;
   int n_sort_tiles;
+  int n_state_tiles;  // state rows per pass: one per tile + one per group of 32 tiles
 };
 
 __host__ inline size_t vl_align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -124,7 +125,8 @@ __host__ inline VlBlobLayout vl_blob_layout(int n) {
   L.n_sort_tiles = (int)((nn + VL_SORT_TILE - 1) / VL_SORT_TILE);
   L.off_ghist = off;      off = vl_align256(off + 4 * 256 * VL_SORT_PASSES);
   L.off_tickets = off;    off = vl_align256(off + 4 * VL_SORT_PASSES);
-  L.off_tile_state = off; off = vl_align256(off + 4 * 256 * (size_t)VL_SORT_PASSES * (size_t)L.n_sort_tiles);
+  L.n_state_tiles = L.n_sort_tiles + (L.n_sort_tiles + 31) / 32;
+  L.off_tile_state = off; off = vl_align256(off + 4 * 256 * (size_t)VL_SORT_PASSES * (size_t)L.n_state_tiles);
   L.total = off;
   return L;
 }
