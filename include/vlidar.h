@@ -43,8 +43,8 @@ int         vl_device_count(void); /* >0 or VL_ECUDA */
  * (0) reference-compatible host entry point.
  *
  * Replaces: void ctrace(...)  auxiliary/raytracer/RayTracer.cpp:116-124 (-> trace(), :19-114).
- * All pointers are HOST pointers to caller-owned contiguous buffers.  Builds the BVH over
- * the indexed mesh, casts n_rays rays (width = n_rays / height, RayTracer.cpp:56) from
+ * All pointers are HOST pointers to caller-owned contiguous buffers.  Uploads the indexed
+ * mesh, casts n_rays rays (width = n_rays / height, RayTracer.cpp:56) from
  * origin[3] and, for HITS ONLY, writes endpoints[3r..], endcolors[3r..] (= colours of the
  * hit triangle's vertex 0), endrem[r] (= mean remission of its three vertices) and
  * range[r]; entries of missing rays are left untouched (the caller zero-fills,
@@ -98,6 +98,41 @@ int vl_bvh_status(const void* d_blob, int n_faces, vl_stream stream, int* info);
 int vl_trace(const void* d_blob, int n_faces, const float* d_rays, const float* d_origin,
              int n_rays, int height, float* d_endpoints, int* d_endcolors, float* d_range,
              float* d_endrem, int* d_tri_id, int flags, vl_stream stream);
+
+/* ------------------------------------------------------------------------------------
+ * (ii-b) beam index + scene-streaming cast: the same reference code as (i) + (ii) together
+ * (RayTracer.cpp:32-92, BVH.cpp:19-243, Triangle.h:27-50), for the case the ctrace ABI
+ * actually describes -- ALL rays share one origin (RayTracer.cpp:116-124) and every mesh is
+ * cast once.  The rays (the sensor's beams, constant across scans) are indexed once in a
+ * direction-space cell grid; each scan's triangles are then streamed through that index a
+ * single time, candidates tested with the same Moller-Trumbore arithmetic as vl_trace, the
+ * closest hit per beam kept by a 64-bit atomicMin on (t, face index).  Identical results to
+ * vl_bvh_build + vl_trace (closest hit over all triangles, exact-t ties to the smaller face
+ * index), no per-scan tree.
+ *
+ * vl_beams_build: d_rays f32[3*n_rays] (not normalised) -> d_beams, a caller-provided device
+ * blob of vl_beams_bytes(n_rays, height) bytes, 256-byte aligned; valid for every later
+ * vl_cast with the same (n_rays, height), any origin, any mesh.
+ * vl_cast: mesh arrays as in vl_bvh_build, outputs / flags as in vl_trace; d_workspace of
+ * vl_cast_workspace_bytes(n_rays, n_faces) bytes (8 B per ray + 12 B per face, 256-byte
+ * aligned) is scratch for this call.  vl_cast_status synchronises the stream and returns
+ * VL_OK, VL_EBADMESH or VL_ENOSPACE (more than 2^36 triangle-cell candidates: results
+ * invalid, use the LBVH path) for the most recent vl_cast on that workspace; info (nullable,
+ * int[8]): [0] n_bad_faces [1] triangles that can be hit [2],[3] candidate items (low 31
+ * bits, high bits).
+ * ---------------------------------------------------------------------------------- */
+size_t vl_beams_bytes(int n_rays, int height);
+int vl_beams_build(const float* d_rays, int n_rays, int height, void* d_beams, size_t beams_bytes,
+                   vl_stream stream);
+size_t vl_cast_workspace_bytes(int n_rays, int n_faces);
+int vl_cast(const void* d_beams, const float* d_verts, const int* d_faces, const int* d_colors,
+            const float* d_rem, int n_verts, int n_faces, const float* d_origin, int n_rays,
+            int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
+            int* d_tri_id, int flags, void* d_workspace, size_t workspace_bytes, vl_stream stream);
+int vl_cast_status(const void* d_workspace, vl_stream stream, int* info);
+/* Which device path the host-pointer ctrace / vl_ctrace_ids uses: 0 (default) = beam index +
+ * vl_cast, 1 = vl_bvh_build + vl_trace.  Process-wide. */
+void vl_ctrace_method(int method);
 
 /* Test aid: same outputs by testing every triangle per ray (no BVH). */
 int vl_trace_bruteforce(const float* d_verts, const int* d_faces, const int* d_colors,
@@ -181,6 +216,10 @@ void        vl_debug_trace_stats(int* d_stats);
 /* Debug: force the traversal variant: 0 auto, 1 per-ray in storage order, 2 per-ray in 16x8 beam tiles,
  * 4/8/16/32 = warp packets of that tile width. */
 void        vl_debug_trace_mode(int mode);
+/* Debug: cell rows per beam row of the beam index (default 2); changes vl_beams_bytes. */
+void        vl_debug_cast_cells(int cells_per_beam_row);
+/* Debug: persistent CTAs per SM of the item kernel (default 4). */
+void        vl_debug_cast_ctas(int ctas_per_sm);
 /* Debug (timing only, leaves the blob unusable): 0 full build, 1 / 2 / 3 = stop after bounds / morton / sort. */
 void        vl_debug_build_stop(int stage);
 

@@ -33,6 +33,14 @@ SIGNATURES = {
     "vl_bvh_build": (_i, [_vp] * 4 + [_i, _i, _vp, _sz, _vp]),
     "vl_bvh_status": (_i, [_vp, _i, _vp, _vp]),
     "vl_trace": (_i, [_vp, _i, _vp, _vp, _i, _i] + [_vp] * 5 + [_i, _vp]),
+    "vl_beams_bytes": (_sz, [_i, _i]),
+    "vl_beams_build": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
+    "vl_cast_workspace_bytes": (_sz, [_i, _i]),
+    "vl_cast": (_i, [_vp] * 5 + [_i, _i, _vp, _i, _i] + [_vp] * 5 + [_i, _vp, _sz, _vp]),
+    "vl_cast_status": (_i, [_vp, _vp, _vp]),
+    "vl_ctrace_method": (None, [_i]),
+    "vl_debug_cast_cells": (None, [_i]),
+    "vl_debug_cast_ctas": (None, [_i]),
     "vl_trace_bruteforce": (_i, [_vp] * 4 + [_i, _i, _vp, _vp, _i, _i] + [_vp] * 6),
     "vl_project_workspace_bytes": (_sz, [_l, _i, _i]),
     "vl_project": (_i, [_vp, _vp, _vp, _l, _d, _d, _i, _i, _i] + [_vp] * 7 + [_sz, _vp]),

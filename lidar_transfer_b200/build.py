@@ -21,6 +21,7 @@ SOURCES = {
     "vl_api.cu": [],
     "vl_bvh_build.cu": [],
     "vl_trace.cu": [],
+    "vl_cast.cu": [],
     "vl_project.cu": ["-fmad=false"],
     "vl_tsdf.cu": ["-fmad=false"],
     "vl_mesh.cu": [],

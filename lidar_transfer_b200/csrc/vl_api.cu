@@ -5,6 +5,7 @@
 // RayTracer.cpp:116-124): it stages the caller's buffers into a grow-only device arena,
 // builds the LBVH, traces and copies the four outputs back -- synchronous, like the reference.
 #include <stdarg.h>
+#include <stddef.h>
 #include <string.h>
 #include <mutex>
 #include "vl_common.cuh"
@@ -37,7 +38,8 @@ std::vector<cudaEvent_t> g_prof_pool;
 thread_local cudaEvent_t g_prof_open[VL_ST_COUNT];
 const char* kStageNames[VL_ST_COUNT] = {"bounds", "morton", "sort_pass", "emit_climb", "top_climb",
                                         "trace", "project_scatter", "project_gather", "tsdf_init", "tsdf_integrate",
-                                        "mesh_count", "mesh_scan", "mesh_compact", "mesh_emit"};
+                                        "mesh_count", "mesh_scan", "mesh_compact", "mesh_emit",
+                                        "beams", "cast_init", "cast_setup", "cast_items", "cast_resolve"};
 cudaEvent_t prof_event() {
   std::lock_guard<std::mutex> lock(g_prof_mu);
   if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
@@ -163,6 +165,55 @@ extern "C" int vl_trace_bruteforce(const float* d_verts, const int* d_faces, con
 }
 
 // ---------------------------------------------------------------------------
+// (ii-b) beam index + scene-streaming cast
+// ---------------------------------------------------------------------------
+extern "C" size_t vl_beams_bytes(int n_rays, int height) {
+  return vl_beams_bytes_impl(n_rays < 0 ? 0 : n_rays, height < 1 ? 1 : height);
+}
+
+extern "C" int vl_beams_build(const float* d_rays, int n_rays, int height, void* d_beams, size_t beams_bytes,
+                              vl_stream stream) {
+  if (n_rays < 0 || height <= 0 || !d_beams || (((uintptr_t)d_beams) & 255) || (n_rays > 0 && !d_rays)) {
+    vl_set_error("vl_beams_build: invalid argument (n_rays %d, height %d, beams %p)", n_rays, height, d_beams);
+    return VL_EINVAL;
+  }
+  if (beams_bytes < vl_beams_bytes(n_rays, height)) {
+    vl_set_error("vl_beams_build: blob too small (%zu < %zu bytes)", beams_bytes, vl_beams_bytes(n_rays, height));
+    return VL_ENOSPACE;
+  }
+  return vl_beams_build_launch(d_rays, n_rays, height, d_beams, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t vl_cast_workspace_bytes(int n_rays, int n_faces) { return vl_cast_workspace_bytes_impl(n_rays, n_faces); }
+
+extern "C" int vl_cast(const void* d_beams, const float* d_verts, const int* d_faces, const int* d_colors,
+                       const float* d_rem, int n_verts, int n_faces, const float* d_origin, int n_rays, int height,
+                       float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id,
+                       int flags, void* d_workspace, size_t workspace_bytes, vl_stream stream) {
+  if (n_rays < 0 || height <= 0 || !d_origin || !d_beams || !d_workspace || (((uintptr_t)d_workspace) & 255) ||
+      (n_rays > 0 && (!d_endpoints || !d_endcolors || !d_range || !d_endrem))) {
+    vl_set_error("vl_cast: invalid argument (n_rays %d, height %d)", n_rays, height);
+    return VL_EINVAL;
+  }
+  if (n_faces < 0 || n_verts < 0 || (n_faces > 0 && (!d_verts || !d_faces || !d_colors || !d_rem))) {
+    vl_set_error("vl_cast: invalid mesh (n_verts %d, n_faces %d)", n_verts, n_faces);
+    return VL_EINVAL;
+  }
+  if (workspace_bytes < vl_cast_workspace_bytes(n_rays, n_faces)) {
+    vl_set_error("vl_cast: workspace too small (%zu < %zu bytes)", workspace_bytes, vl_cast_workspace_bytes(n_rays, n_faces));
+    return VL_ENOSPACE;
+  }
+  return vl_cast_launch(d_beams, d_verts, d_faces, d_colors, d_rem, n_verts, n_faces, d_origin, n_rays, height,
+                        d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, flags, d_workspace,
+                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vl_cast_status(const void* d_workspace, vl_stream stream, int* info) {
+  if (!d_workspace) { vl_set_error("vl_cast_status: null workspace"); return VL_EINVAL; }
+  return vl_cast_status_read(d_workspace, static_cast<cudaStream_t>(stream), info);
+}
+
+// ---------------------------------------------------------------------------
 // host-pointer ctrace: grow-only device arena + one stream, guarded by a mutex
 // ---------------------------------------------------------------------------
 namespace {
@@ -173,6 +224,7 @@ struct HostCtx {
   size_t arena_bytes = 0;
 };
 HostCtx g_ctx;
+std::atomic<int> g_ctrace_method{0};   // 0 = beam index + scene-streaming cast, 1 = LBVH build + traversal
 
 int ctx_reserve(HostCtx& c, size_t bytes) {
   if (!c.stream) VL_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
@@ -186,6 +238,8 @@ int ctx_reserve(HostCtx& c, size_t bytes) {
   return VL_OK;
 }
 }  // namespace
+
+extern "C" void vl_ctrace_method(int method) { g_ctrace_method.store(method == 1 ? 1 : 0); }
 
 extern "C" int vl_ctrace_ids(const float* rays, const float* origin, const float* verts, const int* faces,
                              const int* colors, const float* rem, int n_rays, int n_verts, int n_faces, int height,
@@ -206,7 +260,9 @@ extern "C" int vl_ctrace_ids(const float* rays, const float* origin, const float
   // arena carve-up
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = vl_align256(off + bytes); return o; };
-  const size_t o_blob = take(vl_bvh_blob_bytes(n_faces));
+  const bool lbvh = g_ctrace_method.load() == 1;
+  const size_t o_blob = take(lbvh ? vl_bvh_blob_bytes(n_faces) : vl_beams_bytes(n_rays, height));
+  const size_t o_ws = take(lbvh ? 256 : vl_cast_workspace_bytes(n_rays, n_faces));
   const size_t o_rays = take(12 * nr), o_origin = take(12), o_verts = take(12 * nv), o_faces = take(12 * nf);
   const size_t o_colors = take(12 * nv), o_rem = take(4 * nv);
   const size_t o_ep = take(12 * nr), o_ec = take(12 * nr), o_range = take(4 * nr), o_erem = take(4 * nr), o_id = take(4 * nr);
@@ -214,34 +270,47 @@ extern "C" int vl_ctrace_ids(const float* rays, const float* origin, const float
   if (rc) return rc;
   char* A = c.arena;
   cudaStream_t s = c.stream;
+  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_rays, rays, 12 * nr, cudaMemcpyHostToDevice, s));
+  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_origin, origin, 12, cudaMemcpyHostToDevice, s));
+  if (!lbvh) {   // the beam index only needs the rays: it is built while the mesh is still on its way
+    rc = vl_beams_build_launch((const float*)(A + o_rays), n_rays, height, A + o_blob, s);
+    if (rc) return rc;
+  }
   VL_CUDA_CHECK(cudaMemcpyAsync(A + o_verts, verts, 12 * nv, cudaMemcpyHostToDevice, s));
   VL_CUDA_CHECK(cudaMemcpyAsync(A + o_faces, faces, 12 * nf, cudaMemcpyHostToDevice, s));
   VL_CUDA_CHECK(cudaMemcpyAsync(A + o_colors, colors, 12 * nv, cudaMemcpyHostToDevice, s));
   VL_CUDA_CHECK(cudaMemcpyAsync(A + o_rem, rem, 4 * nv, cudaMemcpyHostToDevice, s));
-  rc = vl_bvh_build_launch((const float*)(A + o_verts), (const int*)(A + o_faces), (const int*)(A + o_colors),
-                           (const float*)(A + o_rem), n_verts, n_faces, A + o_blob, s);
-  if (rc) return rc;
-  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_rays, rays, 12 * nr, cudaMemcpyHostToDevice, s));
-  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_origin, origin, 12, cudaMemcpyHostToDevice, s));
+  if (lbvh) {
+    rc = vl_bvh_build_launch((const float*)(A + o_verts), (const int*)(A + o_faces), (const int*)(A + o_colors),
+                             (const float*)(A + o_rem), n_verts, n_faces, A + o_blob, s);
+    if (rc) return rc;
+  }
   // misses must leave the caller's buffers untouched (RayTracer.cpp:72-90): round-trip their content
   VL_CUDA_CHECK(cudaMemcpyAsync(A + o_ep, endpoints, 12 * nr, cudaMemcpyHostToDevice, s));
   VL_CUDA_CHECK(cudaMemcpyAsync(A + o_ec, endcolors, 12 * nr, cudaMemcpyHostToDevice, s));
   VL_CUDA_CHECK(cudaMemcpyAsync(A + o_range, range, 4 * nr, cudaMemcpyHostToDevice, s));
   VL_CUDA_CHECK(cudaMemcpyAsync(A + o_erem, endrem, 4 * nr, cudaMemcpyHostToDevice, s));
-  rc = vl_trace_launch(A + o_blob, n_faces, (const float*)(A + o_rays), (const float*)(A + o_origin), n_rays, height,
-                       (float*)(A + o_ep), (int*)(A + o_ec), (float*)(A + o_range), (float*)(A + o_erem),
-                       tri_id ? (int*)(A + o_id) : nullptr, 0, s);
+  if (lbvh)
+    rc = vl_trace_launch(A + o_blob, n_faces, (const float*)(A + o_rays), (const float*)(A + o_origin), n_rays, height,
+                         (float*)(A + o_ep), (int*)(A + o_ec), (float*)(A + o_range), (float*)(A + o_erem),
+                         tri_id ? (int*)(A + o_id) : nullptr, 0, s);
+  else
+    rc = vl_cast_launch(A + o_blob, (const float*)(A + o_verts), (const int*)(A + o_faces), (const int*)(A + o_colors),
+                        (const float*)(A + o_rem), n_verts, n_faces, (const float*)(A + o_origin), n_rays, height,
+                        (float*)(A + o_ep), (int*)(A + o_ec), (float*)(A + o_range), (float*)(A + o_erem),
+                        tri_id ? (int*)(A + o_id) : nullptr, 0, A + o_ws, s);
   if (rc) return rc;
   VL_CUDA_CHECK(cudaMemcpyAsync(endpoints, A + o_ep, 12 * nr, cudaMemcpyDeviceToHost, s));
   VL_CUDA_CHECK(cudaMemcpyAsync(endcolors, A + o_ec, 12 * nr, cudaMemcpyDeviceToHost, s));
   VL_CUDA_CHECK(cudaMemcpyAsync(range, A + o_range, 4 * nr, cudaMemcpyDeviceToHost, s));
   VL_CUDA_CHECK(cudaMemcpyAsync(endrem, A + o_erem, 4 * nr, cudaMemcpyDeviceToHost, s));
   if (tri_id) VL_CUDA_CHECK(cudaMemcpyAsync(tri_id, A + o_id, 4 * nr, cudaMemcpyDeviceToHost, s));
-  VlHeader h;
-  VL_CUDA_CHECK(cudaMemcpyAsync(&h, A + o_blob, sizeof(h), cudaMemcpyDeviceToHost, s));
+  int n_bad = 0;   // first int of the LBVH header's n_bad_faces sits at offset 8, of the cast header at offset 0
+  VL_CUDA_CHECK(cudaMemcpyAsync(&n_bad, lbvh ? A + o_blob + offsetof(VlHeader, n_bad_faces) : A + o_ws, sizeof(int),
+                                cudaMemcpyDeviceToHost, s));
   VL_CUDA_CHECK(cudaStreamSynchronize(s));
-  if (h.n_bad_faces > 0) {
-    vl_set_error("ctrace: %d face(s) reference a vertex outside [0, %d); they were skipped", h.n_bad_faces, n_verts);
+  if (n_bad > 0) {
+    vl_set_error("ctrace: %d face(s) reference a vertex outside [0, %d); they were skipped", n_bad, n_verts);
     return VL_EBADMESH;
   }
   return VL_OK;

@@ -1,0 +1,704 @@
+// vl_cast.cu -- (ii-b) scene-streaming closest-hit cast for single-origin ray sets, sm_100a.
+//
+// Replaces the same reference code as vl_bvh_build.cu + vl_trace.cu together (Triangle construction
+// RayTracer.cpp:32-51, BVH::build BVH.cpp:143-243, the ray loop RayTracer.cpp:62-92, BVH::getIntersection
+// BVH.cpp:19-110, Triangle::getIntersection Triangle.h:27-50) with the roles of the two sets swapped.
+//
+// Why: in this pipeline every scan has its own mesh (~1 M triangles) that is cast ONCE with ~131 k rays,
+// and the ctrace ABI gives all rays ONE origin (RayTracer.cpp:116-124: `float* origin` is a single point).
+// Building a hierarchy over the large, single-use set (the triangles) to query it with the small, constant
+// set (the sensor's beams) is backwards on a bandwidth machine.  Here the BEAMS are indexed once per sensor
+// (a direction-space cell grid: yaw x sin(elevation)), and each scan's triangles are streamed through it
+// exactly once: a triangle's central projection is a spherical triangle, its padded (yaw, sine) bounding
+// rectangle selects a few cells, the beams in those cells are tested with the reference's Moller-Trumbore
+// arithmetic (vl_tri_hit, bit-identical to vl_trace.cu) and the closest hit per beam is kept with a 64-bit
+// atomicMin on (t bits << 32 | face index).  No per-scan sort, no per-scan tree, no divergent traversal.
+//
+// Result contract (same as vl_trace.cu): the closest hit over ALL triangles under the
+// reference arithmetic; exact-t ties go to the smaller face index (that is what the packed key orders by).
+// The cell rectangle may only over-select: every bound below is conservative (padded by kPad0 plus the
+// rounding of v - o), so a beam the triangle test would accept is always among the candidates.
+#include "vl_common.cuh"
+
+namespace {
+
+constexpr int kCastThreads = 256;
+constexpr int kCastWarps = kCastThreads / 32;
+constexpr int kFineBins = 4096;     // fine sin(elevation) histogram (prefix sums) for the arithmetic early-out
+constexpr int kChunkItems = 1024;   // (triangle, cell) items per work unit of k_cast_items
+constexpr int kItemBits = 36;       // packed reservation counter: [active triangles : 28][items : 36]
+constexpr float kPi = 3.14159265358979323846f;
+constexpr float kTwoPi = 6.28318530717958647692f;
+constexpr float kInvTwoPi = 0.15915494309189533577f;
+constexpr float kPad0 = 2e-5f;      // angular slack (rad): >> fp32 rounding of yaw / sine / Moller-Trumbore edges
+
+struct VlBeamHeader {
+  unsigned int sine_min_ord, sine_max_ord;  // order-preserving uint encodings, reduced by k_beam_prep
+  int n_binned;                             // rays with a finite direction (the others can never hit)
+  int pad[61];
+};
+static_assert(sizeof(VlBeamHeader) == 256, "beam header is 256 B");
+
+struct VlCastHeader {
+  int n_bad_faces;
+  int overflow;                  // more than 2^36 (triangle, cell) items: results invalid (VL_ENOSPACE)
+  unsigned long long reserved;   // [active triangles : 28][items : 36], bumped once per tile by k_cast_setup
+  unsigned int ticket;           // next chunk of items for k_cast_items
+  int pad[59];
+};
+static_assert(sizeof(VlCastHeader) == 256, "cast header is 256 B");
+
+struct BeamLayout {
+  int n;        // rays cast = width * height (RayTracer.cpp:56)
+  int cw, ch;   // direction cells: yaw x sine
+  size_t off_dir, off_sorted, off_sorted_id, off_cell_start, off_cursor, off_fine, off_blk, total;
+};
+
+int g_cells_per_row = 2;  // cell rows per beam row (vl_debug_cast_cells)
+int g_items_ctas_per_sm = 5;
+
+BeamLayout beam_layout(int n_rays, int height) {
+  BeamLayout L;
+  const int width = height > 0 ? n_rays / height : 0;
+  const long long n = (long long)width * height;
+  L.n = (int)n;
+  int cw = width < 1 ? 1 : (width > 4096 ? 4096 : width);
+  long long ch = (long long)g_cells_per_row * height;
+  if ((long long)cw * ch < n) ch = (n + cw - 1) / cw;
+  if (ch < 1) ch = 1;
+  if (ch > 4096) ch = 4096;
+  L.cw = cw; L.ch = (int)ch;
+  const size_t nn = n > 0 ? (size_t)n : 1, ncell = (size_t)L.cw * L.ch;
+  size_t off = 256;
+  L.off_dir = off;        off = vl_align256(off + 16 * nn);
+  L.off_sorted = off;     off = vl_align256(off + 16 * nn);
+  L.off_sorted_id = off;  off = vl_align256(off + 4 * nn);
+  L.off_cell_start = off; off = vl_align256(off + 4 * (ncell + 1));
+  L.off_cursor = off;     off = vl_align256(off + 4 * ncell);
+  L.off_fine = off;       off = vl_align256(off + 4 * (kFineBins + 1));
+  L.off_blk = off;        off = vl_align256(off + 4 * (ncell / 4096 + 1));
+  L.total = off;
+  return L;
+}
+
+struct BeamParams {
+  int cw, ch;
+  float cw_inv;           // cw / 2 pi
+  float lo, hi;           // sine range of the binned rays
+  float ch_inv, nf_inv;   // cells / fine bins per unit sine (0 when the range is empty)
+};
+
+// the same expressions on the ray side (k_beam_count / k_beam_scatter) and the triangle side (tri_setup)
+__device__ __forceinline__ BeamParams beam_params(const VlBeamHeader* hdr, int cw, int ch) {
+  BeamParams P;
+  P.cw = cw; P.ch = ch;
+  P.cw_inv = (float)cw * kInvTwoPi;
+  P.lo = vl_ordered_to_float(hdr->sine_min_ord);
+  P.hi = vl_ordered_to_float(hdr->sine_max_ord);
+  const float span = P.hi - P.lo;
+  const bool ok = span > 1e-12f;   // false also for the empty set (lo = +inf, hi = -inf / NaN)
+  P.ch_inv = ok ? (float)ch / span : 0.f;
+  P.nf_inv = ok ? (float)kFineBins / span : 0.f;
+  return P;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ int row_of(float s, const BeamParams& P) { return clampi((int)floorf((s - P.lo) * P.ch_inv), 0, P.ch - 1); }
+__device__ __forceinline__ int fine_of(float s, const BeamParams& P) { return clampi((int)floorf((s - P.lo) * P.nf_inv), 0, kFineBins - 1); }
+__device__ __forceinline__ float wrap_pi(float x) { return x - kTwoPi * rintf(x * kInvTwoPi); }
+
+// ---------------------------------------------------------------------------
+// beam index (once per sensor / ray set)
+// ---------------------------------------------------------------------------
+__global__ void k_beam_init(VlBeamHeader* hdr, int* cell_cnt, int ncell_p1, int* fine) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncell_p1; i += stride) cell_cnt[i] = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= kFineBins; i += stride) fine[i] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { hdr->sine_min_ord = 0xffffffffu; hdr->sine_max_ord = 0u; hdr->n_binned = 0; }
+}
+
+// normalised direction (the one vl_tri_hit is given, vl_normalize = Vector3.h:73-89 with IEEE 1/sqrt) + yaw
+__global__ void __launch_bounds__(kCastThreads)
+k_beam_prep(const float* __restrict__ rays, int n, float4* __restrict__ dir, VlBeamHeader* hdr) {
+  __shared__ float s_min[kCastWarps], s_max[kCastWarps];
+  __shared__ int s_cnt[kCastWarps];
+  const int r = blockIdx.x * kCastThreads + threadIdx.x;
+  float smin = INFINITY, smax = -INFINITY;
+  int cnt = 0;
+  if (r < n) {
+    const float3 d = vl_normalize(__ldg(rays + 3 * (size_t)r), __ldg(rays + 3 * (size_t)r + 1), __ldg(rays + 3 * (size_t)r + 2));
+    float yaw = atan2f(d.y, d.x);
+    const bool ok = isfinite(d.x) && isfinite(d.y) && isfinite(d.z) && isfinite(yaw);
+    if (!ok) yaw = __int_as_float(0x7fc00000);
+    dir[r] = make_float4(d.x, d.y, d.z, yaw);
+    if (ok) { smin = smax = d.z; cnt = 1; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+    smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_min[w] = smin; s_max[w] = smax; s_cnt[w] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 1; k < kCastWarps; ++k) { smin = fminf(smin, s_min[k]); smax = fmaxf(smax, s_max[k]); cnt += s_cnt[k]; }
+    if (cnt > 0) {
+      atomicMin(&hdr->sine_min_ord, vl_float_to_ordered(smin));
+      atomicMax(&hdr->sine_max_ord, vl_float_to_ordered(smax));
+      atomicAdd(&hdr->n_binned, cnt);
+    }
+  }
+}
+
+__device__ __forceinline__ int ray_cell(const float4 d, const BeamParams& P) {
+  int col = (int)floorf((d.w + kPi) * P.cw_inv);
+  if (col >= P.cw) col -= P.cw;   // yaw = +pi is the same direction as -pi
+  col = clampi(col, 0, P.cw - 1);
+  return row_of(d.z, P) * P.cw + col;
+}
+
+__global__ void __launch_bounds__(kCastThreads)
+k_beam_count(const float4* __restrict__ dir, int n, const VlBeamHeader* __restrict__ hdr, int cw, int ch,
+             int* __restrict__ cell_cnt, int* __restrict__ fine) {
+  const int r = blockIdx.x * kCastThreads + threadIdx.x;
+  if (r >= n) return;
+  const float4 d = dir[r];
+  if (!(d.w == d.w)) return;
+  const BeamParams P = beam_params(hdr, cw, ch);
+  atomicAdd(&cell_cnt[ray_cell(d, P)], 1);
+  // the rays of one beam row share a fine bin: one atomic per group of equal bins in the warp
+  const int bin = fine_of(d.z, P);
+  const unsigned int peers = __match_any_sync(__activemask(), bin);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&fine[bin], __popc(peers));
+}
+
+// exclusive prefix sums of the cell counts in three coalesced steps (local 4096-element scans, scan of the block
+// totals + of the fine bins, apply) -- in place, plus a copy as the scatter cursor
+constexpr int kScanBlock = 4096;
+
+__device__ __forceinline__ int block_excl_1024(int v, int* s_warp, int* s_total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+  __syncthreads();
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    const int x = s_warp[lane];
+    int xi = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= d) xi += u; }
+    s_warp[lane] = xi - x;
+    if (lane == 31) *s_total = xi;
+  }
+  __syncthreads();
+  return s_warp[w] + incl - v;
+}
+
+__global__ void __launch_bounds__(1024)
+k_beam_scan_local(int* __restrict__ cell, int ncell, int* __restrict__ blk_sum) {
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  const int base = blockIdx.x * kScanBlock + threadIdx.x * 4;
+  int v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = base + k < ncell ? cell[base + k] : 0;
+  int run = block_excl_1024(v[0] + v[1] + v[2] + v[3], s_warp, &s_total);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { if (base + k < ncell) cell[base + k] = run; run += v[k]; }
+  if (threadIdx.x == 0) blk_sum[blockIdx.x] = s_total;
+}
+
+__global__ void __launch_bounds__(1024)
+k_beam_scan_top(int* __restrict__ blk_sum, int nblk, int* __restrict__ cell, int ncell, int* __restrict__ fine) {
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  {
+    const int per = (nblk + 1023) / 1024;
+    const int b = min((int)threadIdx.x * per, nblk), e = min(b + per, nblk);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += blk_sum[i];
+    int run = block_excl_1024(sum, s_warp, &s_total);
+    for (int i = b; i < e; ++i) { const int c = blk_sum[i]; blk_sum[i] = run; run += c; }
+    if (threadIdx.x == 0) cell[ncell] = s_total;
+  }
+  {
+    constexpr int per = kFineBins / 1024;
+    const int b = threadIdx.x * per;
+    int v[per];
+#pragma unroll
+    for (int i = 0; i < per; ++i) v[i] = fine[b + i];
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < per; ++i) sum += v[i];
+    int run = block_excl_1024(sum, s_warp, &s_total);
+#pragma unroll
+    for (int i = 0; i < per; ++i) { fine[b + i] = run; run += v[i]; }
+    if (threadIdx.x == 0) fine[kFineBins] = s_total;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+k_beam_scan_apply(int* __restrict__ cell, int ncell, const int* __restrict__ blk_sum, int* __restrict__ cursor) {
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  if (i >= ncell) return;
+  const int v = cell[i] + blk_sum[i / kScanBlock];
+  cell[i] = v;
+  cursor[i] = v;
+}
+
+__global__ void __launch_bounds__(kCastThreads)
+k_beam_scatter(const float4* __restrict__ dir, int n, const VlBeamHeader* __restrict__ hdr, int cw, int ch,
+               int* __restrict__ cursor, float4* __restrict__ sorted, int* __restrict__ sorted_id) {
+  const int r = blockIdx.x * kCastThreads + threadIdx.x;
+  if (r >= n) return;
+  const float4 d = dir[r];
+  if (!(d.w == d.w)) return;
+  const BeamParams P = beam_params(hdr, cw, ch);
+  const int slot = atomicAdd(&cursor[ray_cell(d, P)], 1);
+  sorted[slot] = d;
+  sorted_id[slot] = r;
+}
+
+// ---------------------------------------------------------------------------
+// per-scan cast
+// ---------------------------------------------------------------------------
+struct TriRec {
+  float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z;
+  int orig;
+  float ymid, yhalf;   // yaw interval centre / half width incl. padding; yhalf < 0 = every yaw
+  float slo, shi;      // padded sine interval
+  int ca, ncx, ra, ncy;
+};
+
+// Conservative (yaw, sine) rectangle of triangle f as seen from o, and the cells it overlaps.
+// Returns the number of cells (0 = no beam can hit it).  The central projection of a planar triangle is a
+// spherical triangle with great-circle edges:
+//   * yaw is monotonic along an edge, so the yaw interval is spanned by the three vertex yaws unless the
+//     z axis pierces the triangle -- exactly when they do not fit in a half circle (extent >= pi);
+//   * sin(elevation) has no interior extremum on the face except at the poles, and along an edge of arc
+//     length L it exceeds its end values by at most L^2 / 8 (|d2/dphi2 sin e| <= 1 on a great circle).
+__device__ __forceinline__ int tri_setup(int f, const float* __restrict__ verts, const int* __restrict__ faces,
+                                         int n_verts, const float3 o, const BeamParams& P,
+                                         const int* fine, TriRec& T, int* bad) {
+  const int i0 = __ldg(faces + 3 * (size_t)f), i1 = __ldg(faces + 3 * (size_t)f + 1), i2 = __ldg(faces + 3 * (size_t)f + 2);
+  if ((unsigned)i0 >= (unsigned)n_verts || (unsigned)i1 >= (unsigned)n_verts || (unsigned)i2 >= (unsigned)n_verts) {
+    *bad = 1;
+    return 0;
+  }
+  const float ax = __ldg(verts + 3 * (size_t)i0), ay = __ldg(verts + 3 * (size_t)i0 + 1), az = __ldg(verts + 3 * (size_t)i0 + 2);
+  const float bx = __ldg(verts + 3 * (size_t)i1), by = __ldg(verts + 3 * (size_t)i1 + 1), bz = __ldg(verts + 3 * (size_t)i1 + 2);
+  const float cx = __ldg(verts + 3 * (size_t)i2), cy = __ldg(verts + 3 * (size_t)i2 + 1), cz = __ldg(verts + 3 * (size_t)i2 + 2);
+  const float p0x = ax - o.x, p0y = ay - o.y, p0z = az - o.z;
+  const float p1x = bx - o.x, p1y = by - o.y, p1z = bz - o.z;
+  const float p2x = cx - o.x, p2y = cy - o.y, p2z = cz - o.z;
+  // a non-finite vertex makes Moller-Trumbore's determinant non-finite: t is then 0, inf or NaN, never accepted
+  // (x * 0 == 0 exactly for finite x only)
+  if (!(((p0x * 0.f + p0y * 0.f + p0z * 0.f) + (p1x * 0.f + p1y * 0.f + p1z * 0.f) + (p2x * 0.f + p2y * 0.f + p2z * 0.f)) == 0.f)) return 0;
+  const float q0 = p0x * p0x + p0y * p0y + p0z * p0z, q1 = p1x * p1x + p1y * p1y + p1z * p1z, q2 = p2x * p2x + p2y * p2y + p2z * p2z;
+  T.v0x = ax; T.v0y = ay; T.v0z = az;
+  T.e1x = __fsub_rn(bx, ax); T.e1y = __fsub_rn(by, ay); T.e1z = __fsub_rn(bz, az);
+  T.e2x = __fsub_rn(cx, ax); T.e2y = __fsub_rn(cy, ay); T.e2z = __fsub_rn(cz, az);
+  T.orig = f;
+  float slo, shi;
+  bool all_yaw;
+  float y0 = 0.f, lo_d = 0.f, hi_d = 0.f, pad_y = 0.f;
+  const float qmin = fminf(q0, fminf(q1, q2)), qmax = fmaxf(q0, fmaxf(q1, q2));
+  if (!(qmin > 1e-30f && qmax < 1e30f)) {
+    slo = -2.f; shi = 2.f; all_yaw = true;   // a vertex at the origin / out of float range: every beam is a candidate
+  } else {
+    const float r0 = rsqrtf(q0), r1 = rsqrtf(q1), r2 = rsqrtf(q2);
+    // absolute rounding of p = v - o (2 ulp of the largest coordinate involved), as an angle at each vertex
+    const float amax = fmaxf(fmaxf(fmaxf(fabsf(ax), fabsf(ay)), fmaxf(fabsf(az), fabsf(bx))),
+                             fmaxf(fmaxf(fmaxf(fabsf(by), fabsf(bz)), fmaxf(fabsf(cx), fabsf(cy))),
+                                   fmaxf(fmaxf(fabsf(cz), fabsf(o.x)), fmaxf(fabsf(o.y), fabsf(o.z)))));
+    const float E = amax * 2.4e-7f;
+    const float u0x = p0x * r0, u0y = p0y * r0, u0z = p0z * r0;
+    const float u1x = p1x * r1, u1y = p1y * r1, u1z = p1z * r1;
+    const float u2x = p2x * r2, u2y = p2y * r2, u2z = p2z * r2;
+    const float c01 = (u0x - u1x) * (u0x - u1x) + (u0y - u1y) * (u0y - u1y) + (u0z - u1z) * (u0z - u1z);
+    const float c12 = (u1x - u2x) * (u1x - u2x) + (u1y - u2y) * (u1y - u2y) + (u1z - u2z) * (u1z - u2z);
+    const float c20 = (u2x - u0x) * (u2x - u0x) + (u2y - u0y) * (u2y - u0y) + (u2z - u0z) * (u2z - u0z);
+    // arc L <= (pi/2) chord  =>  L^2 / 8 <= 0.3085 chord^2
+    const float bulge = 0.31f * fmaxf(c01, fmaxf(c12, c20));
+    const float pad_s = kPad0 + 2.f * E * fmaxf(r0, fmaxf(r1, r2));
+    slo = fminf(u0z, fminf(u1z, u2z)) - bulge - pad_s;
+    shi = fmaxf(u0z, fmaxf(u1z, u2z)) + bulge + pad_s;
+    // quick reject on the vertical field of view before any yaw work
+    if (shi < P.lo || slo > P.hi) return 0;
+    const float h0 = p0x * p0x + p0y * p0y, h1 = p1x * p1x + p1y * p1y, h2 = p2x * p2x + p2y * p2y;
+    const float hmin = fminf(h0, fminf(h1, h2));
+    all_yaw = !(hmin > 1e-30f);
+    if (!all_yaw) {
+      pad_y = kPad0 + 2.f * E * rsqrtf(hmin);
+      y0 = atan2f(p0y, p0x);
+      const float d1 = wrap_pi(atan2f(p1y, p1x) - y0), d2 = wrap_pi(atan2f(p2y, p2x) - y0);
+      lo_d = fminf(0.f, fminf(d1, d2));
+      hi_d = fmaxf(0.f, fmaxf(d1, d2));
+      all_yaw = !((hi_d - lo_d) + 2.f * pad_y < kPi - 1e-3f);
+    }
+    if (all_yaw) {   // the z axis may pierce the triangle: the elevation reaches the pole on that side
+      if (fmaxf(p0z, fmaxf(p1z, p2z)) > 0.f) shi = 2.f;
+      if (fminf(p0z, fminf(p1z, p2z)) < 0.f) slo = -2.f;
+    }
+  }
+  if (shi < P.lo || slo > P.hi) return 0;
+  if (fine[fine_of(shi, P) + 1] - fine[fine_of(slo, P)] == 0) return 0;   // no beam row inside the sine interval
+  T.slo = slo; T.shi = shi;
+  T.ra = row_of(slo, P);
+  T.ncy = row_of(shi, P) - T.ra + 1;
+  if (all_yaw) {
+    T.ca = 0; T.ncx = P.cw; T.ymid = 0.f; T.yhalf = -1.f;
+  } else {
+    const int ca = (int)floorf((y0 + lo_d - pad_y + kPi) * P.cw_inv), cb = (int)floorf((y0 + hi_d + pad_y + kPi) * P.cw_inv);
+    const int ncx = cb - ca + 1;
+    if (ncx >= P.cw) {
+      T.ca = 0; T.ncx = P.cw; T.ymid = 0.f; T.yhalf = -1.f;
+    } else {
+      int c = ca % P.cw;
+      if (c < 0) c += P.cw;
+      T.ca = c; T.ncx = ncx;
+      T.ymid = y0 + 0.5f * (lo_d + hi_d);
+      T.yhalf = 0.5f * (hi_d - lo_d) + pad_y;
+    }
+  }
+  return T.ncx * T.ncy;
+}
+
+// one (triangle, cell) item: test the cell's beams that lie inside the triangle's padded rectangle
+__device__ __forceinline__ void cast_item(const TriRec& T, int l, const BeamParams& P, const int* __restrict__ cell_start,
+                                          const float4* __restrict__ sorted, const int* __restrict__ sorted_id,
+                                          const float3 o, unsigned long long* __restrict__ best) {
+  const int yy = l / T.ncx;
+  int cx = T.ca + (l - yy * T.ncx);
+  if (cx >= P.cw) cx -= P.cw;
+  const int cell = (T.ra + yy) * P.cw + cx;
+  const int s = __ldg(cell_start + cell), e = __ldg(cell_start + cell + 1);
+  for (int k = s; k < e; ++k) {
+    const float4 rd = __ldg(sorted + k);
+    if (rd.z < T.slo || rd.z > T.shi) continue;
+    if (T.yhalf >= 0.f && fabsf(wrap_pi(rd.w - T.ymid)) > T.yhalf) continue;
+    float t;
+    if (vl_tri_hit(make_float4(T.v0x, T.v0y, T.v0z, 0.f), make_float4(T.e1x, T.e1y, T.e1z, 0.f),
+                   make_float4(T.e2x, T.e2y, T.e2z, 0.f), o, make_float3(rd.x, rd.y, rd.z), &t)) {
+      const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned int)T.orig;
+      unsigned long long* slot = best + __ldg(sorted_id + k);
+      if (key < __ldcg(slot)) atomicMin(slot, key);   // a NaN t orders above the initial key and never wins
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long init_key() {
+  return ((unsigned long long)__float_as_uint(999999999.f) << 32) | 0x7fffffffull;   // BVH.cpp:20
+}
+
+__global__ void k_cast_init(unsigned long long* __restrict__ best, int n, VlCastHeader* hdr) {
+  const int stride = gridDim.x * blockDim.x;
+  const unsigned long long k = init_key();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) best[i] = k;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { hdr->n_bad_faces = 0; hdr->overflow = 0; hdr->reserved = 0ull; hdr->ticket = 0u; }
+}
+
+// Step 1: stream the faces once.  Every triangle gets its cell rectangle; the ~30 % that can be hit at all are
+// compacted into a list (face index, first item) in which a triangle covering n cells owns n consecutive
+// "items".  One packed 64-bit atomicAdd per tile reserves list positions and item numbers TOGETHER, so the
+// item numbers increase along the list whatever order the tiles arrive in.
+__global__ void __launch_bounds__(kCastThreads)
+k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const int* __restrict__ fine_g,
+             const float* __restrict__ verts, const int* __restrict__ faces, int n_verts, int n_faces,
+             const float* __restrict__ origin, VlCastHeader* chdr, int* __restrict__ list_f,
+             unsigned long long* __restrict__ list_start) {
+  __shared__ int s_fine[kFineBins + 1];
+  __shared__ unsigned long long s_warp[kCastWarps];
+  __shared__ unsigned long long s_base;
+  for (int i = threadIdx.x; i <= kFineBins; i += kCastThreads) s_fine[i] = __ldg(fine_g + i);
+  __syncthreads();
+  const BeamParams P = beam_params(bhdr, cw, ch);
+  const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n_tiles = (n_faces + kCastThreads - 1) / kCastThreads;
+  int n_bad = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int f = tile * kCastThreads + threadIdx.x;
+    int n_i = 0;
+    if (f < n_faces) {
+      TriRec T;
+      int bad = 0;
+      n_i = tri_setup(f, verts, faces, n_verts, o, P, s_fine, T, &bad);
+      n_bad += bad;
+    }
+    // block-exclusive scan of the packed pair (1 << 36 | n_i): list position and item number in one go
+    const unsigned long long mine = n_i > 0 ? ((1ull << kItemBits) | (unsigned long long)n_i) : 0ull;
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += u;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    unsigned long long before = 0ull, total = 0ull;
+#pragma unroll
+    for (int k = 0; k < kCastWarps; ++k) { const unsigned long long x = s_warp[k]; if (k < w) before += x; total += x; }
+    if (threadIdx.x == 0 && total) {
+      const unsigned long long old = atomicAdd(&chdr->reserved, total);
+      const unsigned long long items_mask = (1ull << kItemBits) - 1ull;
+      if ((old & items_mask) + (total & items_mask) > items_mask) chdr->overflow = 1;
+      s_base = old;
+    }
+    __syncthreads();
+    if (n_i > 0) {
+      const unsigned long long at = s_base + before + incl - mine;
+      const int pos = (int)(at >> kItemBits);
+      if (pos < n_faces) {   // always, unless the item counter overflowed into the position bits
+        list_f[pos] = f;
+        list_start[pos] = at & ((1ull << kItemBits) - 1ull);
+      }
+    }
+    // (s_warp / s_base are rewritten only after the next tile's first barrier)
+  }
+  if (n_bad) atomicAdd(&chdr->n_bad_faces, n_bad);
+}
+
+// largest pos in [0, n) with a[pos] <= key (a is increasing, a[0] <= key): CTA-wide 256-ary search
+__device__ __forceinline__ int coop_search(const unsigned long long* __restrict__ a, int n, unsigned long long key) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int step = (hi - lo + kCastThreads - 1) / kCastThreads;
+    const int p = lo + (int)threadIdx.x * step;
+    const bool ok = p < hi && __ldg(a + p) <= key;
+    const int c = __syncthreads_count(ok);   // the threads that are ok form a prefix
+    lo = lo + (c - 1) * step;
+    hi = min(hi, lo + step);
+  }
+  return lo;
+}
+
+// Step 2: the items, evenly.  CTAs draw chunks of kChunkItems consecutive items from a ticket counter, so a
+// triangle in front of the sensor (thousands of cells) is shared by many CTAs while hundreds of distant
+// ones (a few cells each) fill one chunk.  Per chunk: find the list range, set its triangles up again
+// (cheaper than a 72-byte record round trip through HBM), then one item per thread per step.
+__global__ void __launch_bounds__(kCastThreads)
+k_cast_items(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const int* __restrict__ cell_start,
+             const float4* __restrict__ sorted, const int* __restrict__ sorted_id, const int* __restrict__ fine_g,
+             const float* __restrict__ verts, const int* __restrict__ faces, int n_verts,
+             const float* __restrict__ origin, unsigned long long* __restrict__ best, VlCastHeader* chdr,
+             const int* __restrict__ list_f, const unsigned long long* __restrict__ list_start) {
+  __shared__ TriRec s_rec[kCastThreads];
+  __shared__ unsigned long long s_start[kCastThreads];
+  __shared__ unsigned long long s_last_end;
+  __shared__ unsigned int s_chunk;
+  const unsigned long long reserved = chdr->reserved;
+  const unsigned long long n_items = reserved & ((1ull << kItemBits) - 1ull);
+  const int n_active = (int)(reserved >> kItemBits);
+  if (n_active == 0 || chdr->overflow) return;
+  const BeamParams P = beam_params(bhdr, cw, ch);
+  const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_chunk = atomicAdd(&chdr->ticket, 1u);
+    __syncthreads();
+    const unsigned long long lo_item = (unsigned long long)s_chunk * kChunkItems;
+    if (lo_item >= n_items) break;
+    const unsigned long long hi_item = min(n_items, lo_item + kChunkItems);
+    const int p0 = coop_search(list_start, n_active, lo_item);
+    for (int base = p0;; base += kCastThreads) {
+      const int pos = base + threadIdx.x;
+      unsigned long long st = 0ull;
+      const bool valid = pos < n_active && (st = __ldg(list_start + pos)) < hi_item;
+      if (valid) {
+        int bad = 0;
+        const int n = tri_setup(__ldg(list_f + pos), verts, faces, n_verts, o, P, fine_g, s_rec[threadIdx.x], &bad);
+        s_start[threadIdx.x] = st;
+        const bool last = !(pos + 1 < n_active && __ldg(list_start + pos + 1) < hi_item) || threadIdx.x == kCastThreads - 1;
+        if (last) s_last_end = st + (unsigned long long)n;
+      }
+      const int cnt = __syncthreads_count(valid);   // valid threads form a prefix
+      if (cnt == 0) break;
+      const unsigned long long pass_lo = max(lo_item, s_start[0]), pass_hi = min(hi_item, s_last_end);
+      for (unsigned long long item = pass_lo + threadIdx.x; item < pass_hi; item += kCastThreads) {
+        int j = 0;
+#pragma unroll
+        for (int step = kCastThreads / 2; step > 0; step >>= 1)
+          if (j + step < cnt && s_start[j + step] <= item) j += step;
+        cast_item(s_rec[j], (int)(item - s_start[j]), P, cell_start, sorted, sorted_id, o, best);
+      }
+      if (cnt < kCastThreads) break;
+      __syncthreads();
+    }
+  }
+}
+
+// RayTracer.cpp:73-90 write-back for the winning triangle of each beam; BVH.cpp:106-107 hit = o + d * t
+__global__ void __launch_bounds__(kCastThreads)
+k_cast_resolve(const unsigned long long* __restrict__ best, int n, const float4* __restrict__ dir,
+               const float* __restrict__ origin, const int* __restrict__ faces, const int* __restrict__ colors,
+               const float* __restrict__ rem, float* __restrict__ endpoints, int* __restrict__ endcolors,
+               float* __restrict__ range, float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses) {
+  const int r = blockIdx.x * kCastThreads + threadIdx.x;
+  if (r >= n) return;
+  const unsigned long long key = best[r];
+  if (key < init_key()) {
+    const int f = (int)(unsigned int)(key & 0xffffffffull);
+    const float t = __uint_as_float((unsigned int)(key >> 32));
+    const float4 d = dir[r];
+    const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
+    const int i0 = __ldg(faces + 3 * (size_t)f), i1 = __ldg(faces + 3 * (size_t)f + 1), i2 = __ldg(faces + 3 * (size_t)f + 2);
+    endpoints[3 * (size_t)r + 0] = __fadd_rn(o.x, __fmul_rn(d.x, t));
+    endpoints[3 * (size_t)r + 1] = __fadd_rn(o.y, __fmul_rn(d.y, t));
+    endpoints[3 * (size_t)r + 2] = __fadd_rn(o.z, __fmul_rn(d.z, t));
+    // RayTracer.cpp:36-48 colours pass through float; Triangle.h:53-56 colour of vertex 0
+    endcolors[3 * (size_t)r + 0] = (int)(float)__ldg(colors + 3 * (size_t)i0);
+    endcolors[3 * (size_t)r + 1] = (int)(float)__ldg(colors + 3 * (size_t)i0 + 1);
+    endcolors[3 * (size_t)r + 2] = (int)(float)__ldg(colors + 3 * (size_t)i0 + 2);
+    endrem[r] = __fdiv_rn(__fadd_rn(__fadd_rn(__ldg(rem + i0), __ldg(rem + i1)), __ldg(rem + i2)), 3.0f);   // Triangle.h:63-70
+    range[r] = t;
+    if (tri_id) tri_id[r] = f;
+  } else {
+    if (zero_misses) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { endpoints[3 * (size_t)r + k] = 0.f; endcolors[3 * (size_t)r + k] = 0; }
+      endrem[r] = 0.f;
+      range[r] = 0.f;
+    }
+    if (tri_id) tri_id[r] = -1;
+  }
+}
+
+}  // namespace
+
+extern "C" void vl_debug_cast_cells(int cells_per_beam_row) { g_cells_per_row = cells_per_beam_row < 1 ? 1 : cells_per_beam_row; }
+extern "C" void vl_debug_cast_ctas(int ctas_per_sm) { g_items_ctas_per_sm = ctas_per_sm < 1 ? 1 : ctas_per_sm; }
+
+size_t vl_beams_bytes_impl(int n_rays, int height) { return beam_layout(n_rays, height).total; }
+
+struct CastLayout { size_t off_best, off_list_f, off_list_start, total; };
+
+CastLayout cast_layout(int n_rays, int n_faces) {
+  CastLayout C;
+  const size_t nr = n_rays > 0 ? (size_t)n_rays : 1, nf = n_faces > 0 ? (size_t)n_faces : 1;
+  size_t off = 256;
+  C.off_best = off;       off = vl_align256(off + 8 * nr);
+  C.off_list_start = off; off = vl_align256(off + 8 * nf);
+  C.off_list_f = off;     off = vl_align256(off + 4 * nf);
+  C.total = off;
+  return C;
+}
+
+size_t vl_cast_workspace_bytes_impl(int n_rays, int n_faces) { return cast_layout(n_rays, n_faces).total; }
+
+int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_beams, cudaStream_t stream) {
+  const BeamLayout L = beam_layout(n_rays, height);
+  char* B = static_cast<char*>(d_beams);
+  VlBeamHeader* hdr = reinterpret_cast<VlBeamHeader*>(B);
+  float4* dir = reinterpret_cast<float4*>(B + L.off_dir);
+  float4* sorted = reinterpret_cast<float4*>(B + L.off_sorted);
+  int* sorted_id = reinterpret_cast<int*>(B + L.off_sorted_id);
+  int* cell_start = reinterpret_cast<int*>(B + L.off_cell_start);
+  int* cursor = reinterpret_cast<int*>(B + L.off_cursor);
+  int* fine = reinterpret_cast<int*>(B + L.off_fine);
+  const int ncell = L.cw * L.ch;
+  VlProfScope ps(VL_ST_BEAMS, stream);
+  k_beam_init<<<148, 256, 0, stream>>>(hdr, cell_start, ncell + 1, fine);
+  VL_LAUNCH_CHECK("k_beam_init");
+  if (L.n > 0) {
+    const int nb = (L.n + kCastThreads - 1) / kCastThreads;
+    k_beam_prep<<<nb, kCastThreads, 0, stream>>>(d_rays, L.n, dir, hdr);
+    VL_LAUNCH_CHECK("k_beam_prep");
+    k_beam_count<<<nb, kCastThreads, 0, stream>>>(dir, L.n, hdr, L.cw, L.ch, cell_start, fine);
+    VL_LAUNCH_CHECK("k_beam_count");
+  }
+  int* blk_sum = reinterpret_cast<int*>(B + L.off_blk);
+  const int nblk = (ncell + kScanBlock - 1) / kScanBlock;
+  k_beam_scan_local<<<nblk, 1024, 0, stream>>>(cell_start, ncell, blk_sum);
+  VL_LAUNCH_CHECK("k_beam_scan_local");
+  k_beam_scan_top<<<1, 1024, 0, stream>>>(blk_sum, nblk, cell_start, ncell, fine);
+  VL_LAUNCH_CHECK("k_beam_scan_top");
+  k_beam_scan_apply<<<(ncell + 1023) / 1024, 1024, 0, stream>>>(cell_start, ncell, blk_sum, cursor);
+  VL_LAUNCH_CHECK("k_beam_scan_apply");
+  if (L.n > 0) {
+    const int nb = (L.n + kCastThreads - 1) / kCastThreads;
+    k_beam_scatter<<<nb, kCastThreads, 0, stream>>>(dir, L.n, hdr, L.cw, L.ch, cursor, sorted, sorted_id);
+    VL_LAUNCH_CHECK("k_beam_scatter");
+  }
+  return VL_OK;
+}
+
+int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces, const int* d_colors,
+                   const float* d_rem, int n_verts, int n_faces, const float* d_origin, int n_rays, int height,
+                   float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id, int flags,
+                   void* d_ws, cudaStream_t stream) {
+  const BeamLayout L = beam_layout(n_rays, height);
+  if (d_tri_id && n_rays > L.n)   // rays beyond width * height are never cast (RayTracer.cpp:56)
+    VL_CUDA_CHECK(cudaMemsetAsync(d_tri_id + L.n, 0xff, sizeof(int) * (size_t)(n_rays - L.n), stream));
+  if (L.n <= 0) return VL_OK;
+  const char* B = static_cast<const char*>(d_beams);
+  const VlBeamHeader* bhdr = reinterpret_cast<const VlBeamHeader*>(B);
+  const float4* dir = reinterpret_cast<const float4*>(B + L.off_dir);
+  const float4* sorted = reinterpret_cast<const float4*>(B + L.off_sorted);
+  const int* sorted_id = reinterpret_cast<const int*>(B + L.off_sorted_id);
+  const int* cell_start = reinterpret_cast<const int*>(B + L.off_cell_start);
+  const int* fine = reinterpret_cast<const int*>(B + L.off_fine);
+  char* Wk = static_cast<char*>(d_ws);
+  const CastLayout C = cast_layout(n_rays, n_faces);
+  VlCastHeader* chdr = reinterpret_cast<VlCastHeader*>(Wk);
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(Wk + C.off_best);
+  unsigned long long* list_start = reinterpret_cast<unsigned long long*>(Wk + C.off_list_start);
+  int* list_f = reinterpret_cast<int*>(Wk + C.off_list_f);
+  {
+    VlProfScope ps(VL_ST_CAST_INIT, stream);
+    k_cast_init<<<148, 256, 0, stream>>>(best, L.n, chdr);
+    VL_LAUNCH_CHECK("k_cast_init");
+  }
+  if (n_faces > 0) {
+    {
+      VlProfScope ps(VL_ST_CAST_SETUP, stream);
+      const int n_tiles = (n_faces + kCastThreads - 1) / kCastThreads;
+      const int nb = n_tiles < 148 * 4 ? n_tiles : 148 * 4;
+      k_cast_setup<<<nb, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine, d_verts, d_faces, n_verts, n_faces, d_origin,
+                                                   chdr, list_f, list_start);
+      VL_LAUNCH_CHECK("k_cast_setup");
+    }
+    {
+      VlProfScope ps(VL_ST_CAST_ITEMS, stream);
+      k_cast_items<<<148 * g_items_ctas_per_sm, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, cell_start, sorted, sorted_id,
+                                                                          fine, d_verts, d_faces, n_verts, d_origin, best,
+                                                                          chdr, list_f, list_start);
+      VL_LAUNCH_CHECK("k_cast_items");
+    }
+  }
+  {
+    VlProfScope ps(VL_ST_CAST_RESOLVE, stream);
+    const int nb = (L.n + kCastThreads - 1) / kCastThreads;
+    k_cast_resolve<<<nb, kCastThreads, 0, stream>>>(best, L.n, dir, d_origin, d_faces, d_colors, d_rem, d_endpoints,
+                                                   d_endcolors, d_range, d_endrem, d_tri_id,
+                                                   (flags & VL_TRACE_ZERO_MISSES) != 0);
+    VL_LAUNCH_CHECK("k_cast_resolve");
+  }
+  return VL_OK;
+}
+
+int vl_cast_status_read(const void* d_ws, cudaStream_t stream, int* info) {
+  VlCastHeader h;
+  VL_CUDA_CHECK(cudaMemcpyAsync(&h, d_ws, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  VL_CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (info) {
+    info[0] = h.n_bad_faces;
+    info[1] = (int)(h.reserved >> kItemBits);                                       // triangles that can be hit at all
+    const unsigned long long items = h.reserved & ((1ull << kItemBits) - 1ull);   // (triangle, cell) items
+    info[2] = (int)(items & 0x7fffffffull);
+    info[3] = (int)(items >> 31);
+  }
+  if (h.overflow) {
+    vl_set_error("vl_cast: more than 2^36 (triangle, cell) candidates -- results are invalid, use vl_bvh_build + vl_trace");
+    return VL_ENOSPACE;
+  }
+  if (h.n_bad_faces > 0) {
+    vl_set_error("mesh has %d face(s) with a vertex index outside [0, n_verts)", h.n_bad_faces);
+    return VL_EBADMESH;
+  }
+  return VL_OK;
+}

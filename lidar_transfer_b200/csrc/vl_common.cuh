@@ -18,7 +18,8 @@ void vl_count_launch();
 enum VlStage {
   VL_ST_BOUNDS = 0, VL_ST_MORTON, VL_ST_SORT_PASS, VL_ST_EMIT_CLIMB, VL_ST_TOP_CLIMB,
   VL_ST_TRACE, VL_ST_PROJECT_SCATTER, VL_ST_PROJECT_GATHER, VL_ST_TSDF_INIT, VL_ST_TSDF_INTEGRATE,
-  VL_ST_MESH_COUNT, VL_ST_MESH_SCAN, VL_ST_MESH_COMPACT, VL_ST_MESH_EMIT, VL_ST_COUNT
+  VL_ST_MESH_COUNT, VL_ST_MESH_SCAN, VL_ST_MESH_COMPACT, VL_ST_MESH_EMIT,
+  VL_ST_BEAMS, VL_ST_CAST_INIT, VL_ST_CAST_SETUP, VL_ST_CAST_ITEMS, VL_ST_CAST_RESOLVE, VL_ST_COUNT
 };
 void vl_prof_begin(int stage, cudaStream_t stream);
 void vl_prof_end(int stage, cudaStream_t stream);
@@ -199,3 +200,12 @@ int vl_trace_bruteforce_launch(const float* d_verts, const int* d_faces, const i
                                int n_verts, int n_faces, const float* d_rays, const float* d_origin, int n_rays,
                                int height, float* d_endpoints, int* d_endcolors, float* d_range,
                                float* d_endrem, int* d_tri_id, cudaStream_t stream);
+// vl_cast.cu
+size_t vl_beams_bytes_impl(int n_rays, int height);
+size_t vl_cast_workspace_bytes_impl(int n_rays, int n_faces);
+int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_beams, cudaStream_t stream);
+int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces, const int* d_colors,
+                   const float* d_rem, int n_verts, int n_faces, const float* d_origin, int n_rays, int height,
+                   float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id, int flags,
+                   void* d_ws, cudaStream_t stream);
+int vl_cast_status_read(const void* d_ws, cudaStream_t stream, int* info);

@@ -115,6 +115,60 @@ def trace(bvh, rays, origin, height, out=None, want_ids=True, zero_misses=False)
   return out
 
 
+class Beams:
+  """Direction-space index of one ray set (the target sensor's beams): built once, valid for every scan.
+
+  rays f32[R,3] as MultiSemLaserScan.create_rays returns them (auxiliary/laserscan.py:1092-1119) or any
+  other ray set -- the ctrace ABI gives all rays one origin (RayTracer.cpp:116-124), which is all the
+  index relies on.  `height` as in C_Trace (width = n_rays // height rays per row are cast)."""
+
+  def __init__(self, rays, height, device=None):
+    require_cuda()
+    self.rays = _dev(rays, torch.float32, device).reshape(-1)
+    dev = self.rays.device
+    self.n_rays = self.rays.numel() // 3
+    self.height = int(height)
+    self.blob = torch.empty(lib().vl_beams_bytes(self.n_rays, self.height), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+      check(lib().vl_beams_build(_ptr(self.rays), self.n_rays, self.height, _ptr(self.blob), self.blob.numel(), _stream()))
+
+  def workspace(self, max_faces):
+    """Scratch for cast() on meshes of up to max_faces triangles (8 B per ray + 12 B per face)."""
+    return torch.empty(lib().vl_cast_workspace_bytes(self.n_rays, int(max_faces)), dtype=torch.uint8, device=self.blob.device)
+
+
+def cast(beams, verts, faces, colors, rem, origin, out=None, want_ids=True, zero_misses=False, workspace=None,
+         check_mesh=False):
+  """(ii-b) closest-hit cast of an indexed mesh against indexed beams -- same outputs as
+  Bvh(...) + trace(...), i.e. as C_Trace (RayTracerCython.pyx:15-33 -> RayTracer.cpp:19-92), without a
+  per-scan tree: the triangles are streamed once through the beam index.  Mesh arrays as for Bvh.
+  check_mesh=True synchronises, raises VlidarError(VL_EBADMESH) on out-of-range face indices and adds
+  n_bad_faces / n_active (triangles that can be hit at all) / n_items (triangle-cell candidates) to the result."""
+  dev = beams.blob.device
+  verts = _dev(verts, torch.float32, dev).reshape(-1)
+  faces = _dev(faces, torch.int32, dev).reshape(-1)
+  colors = _dev(colors, torch.int32, dev).reshape(-1)
+  rem = _dev(rem, torch.float32, dev).reshape(-1)
+  origin = _dev(origin, torch.float32, dev).reshape(-1)
+  n_verts, n_faces = verts.numel() // 3, faces.numel() // 3
+  if colors.numel() != 3 * n_verts or rem.numel() != n_verts:
+    raise ValueError("colors must hold 3 ints and rem 1 float per vertex")
+  out = _trace_outputs(beams.n_rays, dev, out, want_ids, torch.empty if zero_misses else torch.zeros)
+  if workspace is None or workspace.numel() < lib().vl_cast_workspace_bytes(beams.n_rays, n_faces):
+    workspace = beams.workspace(n_faces)
+  with torch.cuda.device(dev):
+    check(lib().vl_cast(_ptr(beams.blob), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(rem), n_verts, n_faces,
+                        _ptr(origin), beams.n_rays, beams.height, _ptr(out["endpoints"]), _ptr(out["endcolors"]),
+                        _ptr(out["range"]), _ptr(out["endrem"]), _ptr(out.get("tri_id")),
+                        TRACE_ZERO_MISSES if zero_misses else 0, _ptr(workspace), workspace.numel(), _stream()))
+    if check_mesh:
+      info = (ctypes.c_int * 8)()
+      rc = lib().vl_cast_status(_ptr(workspace), _stream(), info)
+      out["n_bad_faces"], out["n_active"], out["n_items"] = info[0], info[1], info[2] + (info[3] << 31)
+      check(rc)
+  return out
+
+
 def trace_bruteforce(verts, faces, colors, rem, rays, origin, height, out=None):
   """Test aid: same outputs without a BVH (every triangle per ray)."""
   require_cuda()
@@ -250,7 +304,7 @@ class TsdfDevice:
     return out
 
 
-def ctrace_host(rays, origin, verts, faces, colors, rem, height, outputs=None, want_ids=False):
+def ctrace_host(rays, origin, verts, faces, colors, rem, height, outputs=None, want_ids=False, method=None):
   """The reference-compatible HOST-pointer entry point (extern "C" ctrace / vl_ctrace_ids) on numpy
   buffers: H2D, build, trace, D2H inside the call.  outputs: dict of preallocated numpy arrays
   (endpoints, endcolors, range, endrem) updated in place for hits."""
@@ -274,6 +328,8 @@ def ctrace_host(rays, origin, verts, faces, colors, rem, height, outputs=None, w
                    range=np.zeros(n_rays, f32), endrem=np.zeros(n_rays, f32))
   tri_id = np.empty(n_rays, i32) if want_ids else None
   p = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
+  if method is not None:  # "cast" (default of the library) or "lbvh"
+    lib().vl_ctrace_method({"cast": 0, "lbvh": 1}[method])
   check(lib().vl_ctrace_ids(p(rays), p(origin), p(verts), p(faces), p(colors), p(rem), n_rays, verts.size // 3,
                             faces.size // 3, int(height), p(chk(outputs["endpoints"], f32, "endpoints")),
                             p(chk(outputs["endcolors"], i32, "endcolors")), p(chk(outputs["range"], f32, "range")),

@@ -1,8 +1,11 @@
 """One-scan-per-stream executor for batches of independent scans.
 
-Scans are independent units (every scan has its own mesh, so every scan pays its own LBVH build):
-a ScanRenderer owns `n_streams` CUDA streams, each with a pre-allocated BVH blob, staging and output
-buffers, and round-robins scans over them -- no allocation and no host synchronisation in steady state.
+Scans are independent units (every scan has its own mesh): a ScanRenderer owns `n_streams` CUDA streams,
+each with pre-allocated scratch, staging and output buffers, and round-robins scans over them -- no
+allocation and no host synchronisation in steady state.  Two device paths give the same bits:
+method="cast" (default) indexes the sensor's beams ONCE and streams every scan's triangles through that
+index (vl_beams_build + vl_cast); method="lbvh" builds a per-scan LBVH and traverses it per ray
+(vl_bvh_build + vl_trace).
 The reference processes scans one by one in its driver loop (lidar_deform.py:393-458 ->
 TSDFVolume.throw_rays_at_mesh, auxiliary/fusion_lidar.py:426-455 -> C_Trace); this is the batch
 form of the same call, also used to shard scans across GPUs (sharding.py).
@@ -21,10 +24,12 @@ def _ptr(t):
 
 
 class _Slot:
-  def __init__(self, dev, max_verts, max_faces, n_rays, host_io):
+  def __init__(self, dev, max_verts, max_faces, n_rays, host_io, method):
     f32, i32 = torch.float32, torch.int32
     self.stream = torch.cuda.Stream(device=dev)
-    self.blob = torch.empty(lib().vl_bvh_blob_bytes(max_faces), dtype=torch.uint8, device=dev)
+    # per-scan scratch: the LBVH blob, or the cast workspace (8 B per beam)
+    need = lib().vl_bvh_blob_bytes(max_faces) if method == "lbvh" else lib().vl_cast_workspace_bytes(n_rays, max_faces)
+    self.blob = torch.empty(need, dtype=torch.uint8, device=dev)
     self.out = dict(endpoints=torch.empty(3 * n_rays, dtype=f32, device=dev),
                     endcolors=torch.empty(3 * n_rays, dtype=i32, device=dev),
                     range=torch.empty(n_rays, dtype=f32, device=dev),
@@ -44,15 +49,23 @@ class _Slot:
 class ScanRenderer:
   """rays f32[R,3] and origin f32[3] are fixed per renderer (one target sensor)."""
 
-  def __init__(self, rays, origin, height, max_verts, max_faces, n_streams=4, device=None, host_io=False):
+  def __init__(self, rays, origin, height, max_verts, max_faces, n_streams=4, device=None, host_io=False,
+               method="cast"):
     engine.require_cuda()
+    if method not in ("cast", "lbvh"):
+      raise ValueError("method must be 'cast' or 'lbvh'")
+    self.method = method
     self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     self.rays = engine._dev(rays, torch.float32, self.dev).reshape(-1)
     self.origin = engine._dev(origin, torch.float32, self.dev).reshape(-1)
     self.n_rays = self.rays.numel() // 3
     self.height = int(height)
     self.max_verts, self.max_faces = int(max_verts), int(max_faces)
-    self.slots = [_Slot(self.dev, max_verts, max_faces, self.n_rays, host_io) for _ in range(n_streams)]
+    self.slots = [_Slot(self.dev, max_verts, max_faces, self.n_rays, host_io, method) for _ in range(n_streams)]
+    # the beam index depends on the sensor only: built once here, shared (read-only) by every stream
+    self.beams = engine.Beams(self.rays, self.height, self.dev) if method == "cast" else None
+    if self.beams is not None:
+      torch.cuda.current_stream(self.dev).synchronize()
     self.host_io = host_io
     self._next = 0
     self._lib = lib()
@@ -68,6 +81,12 @@ class ScanRenderer:
   def _launch(self, s, verts, faces, colors, rem, n_verts, n_faces):
     L = self._lib
     st = ctypes.c_void_p(s.stream.cuda_stream)
+    if self.method == "cast":
+      check(L.vl_cast(_ptr(self.beams.blob), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(rem), n_verts, n_faces,
+                      _ptr(self.origin), self.n_rays, self.height, _ptr(s.out["endpoints"]), _ptr(s.out["endcolors"]),
+                      _ptr(s.out["range"]), _ptr(s.out["endrem"]), _ptr(s.out["tri_id"]), engine.TRACE_ZERO_MISSES,
+                      _ptr(s.blob), s.blob.numel(), st))
+      return
     check(L.vl_bvh_build(_ptr(verts), _ptr(faces), _ptr(colors), _ptr(rem), n_verts, n_faces, _ptr(s.blob),
                          s.blob.numel(), st))
     check(L.vl_trace(_ptr(s.blob), n_faces, _ptr(self.rays), _ptr(self.origin), self.n_rays, self.height,

@@ -1,0 +1,251 @@
+"""GPU parity of row (ii-b): beam index + scene-streaming cast (vl_beams_build / vl_cast) vs the oracle, through
+the C ABI, bit for bit -- on beam grids, arbitrary ray sets, hostile meshes -- and against the LBVH path
+(vl_bvh_build + vl_trace) at the benchmark's full size."""
+import numpy as np
+import pytest
+
+from lidar_transfer_b200 import synth
+
+pytestmark = pytest.mark.gpu
+KEYS = ("tri_id", "range", "endpoints", "endcolors", "endrem")
+
+
+def _np(out):
+  return {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
+
+
+def _same(got, ref, keys=KEYS, what=""):
+  for k in keys:
+    x, y = np.asarray(got[k]).reshape(-1), np.asarray(ref[k]).reshape(-1)
+    same = x.view(np.int32) == y.view(np.int32)
+    if not same.all():
+      i = int(np.flatnonzero(~same)[0])
+      raise AssertionError("%s %s: %d of %d differ, first at %d: %r vs %r" % (what, k, (~same).sum(), same.size, i, x[i], y[i]))
+
+
+def _attrs(n_verts, seed=0):
+  rng = np.random.default_rng(seed)
+  colors = np.zeros((n_verts, 3), np.int32)
+  colors[:, 2] = rng.choice(synth.STATIC_LABELS, n_verts)
+  rem = rng.random(n_verts, dtype=np.float32)
+  return colors, rem
+
+
+def _run(engine, oracle, verts, faces, rays, origin, H, colors=None, rem=None, lbvh=True):
+  verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+  faces = np.ascontiguousarray(faces, np.int32).reshape(-1, 3)
+  if colors is None:
+    colors, rem = _attrs(verts.shape[0])
+  rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 3)
+  origin = np.asarray(origin, np.float32)
+  ref = oracle.trace(rays, origin, verts, faces, colors, rem, H, oracle.MIN_ID_TIES)
+  beams = engine.Beams(rays, H)
+  got = _np(engine.cast(beams, verts, faces, colors, rem, origin))
+  _same(got, ref, what="cast vs oracle")
+  if lbvh:
+    bvh = engine.Bvh(verts, faces, colors, rem)
+    _same(_np(engine.trace(bvh, rays, origin, H)), got, what="lbvh vs cast")
+  return got, ref
+
+
+@pytest.mark.parametrize("sensor", ["HDL-64E", "HDL-32E", "OS1-128"])
+@pytest.mark.parametrize("origin", [(0.0, 0.0, 0.0), (3.5, -2.25, 0.4)])
+def test_cast_beam_grids_bit_exact_vs_oracle(engine, oracle, sensor, origin):
+  H, W, fu, fd = synth.SENSORS[sensor]
+  W = W // 4
+  sc = synth.make_scene(300 + H, n_side=160, n_boxes=12)
+  rays = oracle.create_rays(fu, fd, H, W)
+  got, _ = _run(engine, oracle, sc["verts"], sc["faces"], rays, origin, H, sc["colors"], sc["rem"])
+  assert (got["tri_id"] >= 0).mean() > 0.8
+
+
+def test_cast_full_resolution_vs_oracle(engine, oracle):
+  sc = synth.make_scene(1300, n_side=300)
+  H, W = 64, 2048
+  rays = oracle.create_rays(3.0, -25.0, H, W)
+  got, _ = _run(engine, oracle, sc["verts"], sc["faces"], rays, np.zeros(3, np.float32), H, sc["colors"], sc["rem"])
+  assert (got["tri_id"] >= 0).mean() > 0.9
+
+
+def _random_dirs(rng, n):
+  d = rng.normal(size=(n, 3)).astype(np.float32)
+  d *= rng.uniform(0.1, 30.0, (n, 1)).astype(np.float32)   # not normalised, like any caller's ray set
+  return d
+
+
+@pytest.mark.parametrize("H", [1, 7, 64])
+def test_cast_arbitrary_ray_sets(engine, oracle, H):
+  """Rays that are no beam grid at all: random directions over the whole sphere (both poles included), ragged
+  counts, zero / NaN / inf / denormal-length directions (normalise to non-finite: must miss)."""
+  rng = np.random.default_rng(50 + H)
+  sc = synth.make_scene(77, n_side=50, n_boxes=10)
+  rays = _random_dirs(rng, 64 * 61 + 3)
+  special = np.array([[0, 0, 1], [0, 0, -1], [0, 0, -5], [1, 0, 0], [-1, 0, 0], [-1, -0.0, 0], [0, 1, 0], [0, -1, 0],
+                      [0, 0, 0], [np.nan, 0, -1], [np.inf, 0, -1], [1e-30, 0, -1e-30], [1e-25, 1e-25, -1e-25],
+                      [3e19, 1e19, -1e19], [1e20, 1.0, -1.0], [-1, 1e-9, -0.03], [-1, -1e-9, -0.03]], np.float32)
+  rays[5:5 + len(special)] = special
+  got, ref = _run(engine, oracle, sc["verts"], sc["faces"], rays, np.array([0.3, 0.2, 0.1], np.float32), H, sc["colors"], sc["rem"])
+  assert (got["tri_id"] >= 0).mean() > 0.3
+  assert got["tri_id"][5 + 8] == -1 and got["tri_id"][5 + 9] == -1
+
+
+def _hostile_mesh(rng, n, origin):
+  """Triangle soup around `origin`: tiny far triangles, huge ones that contain the z axis or the sensor's
+  horizontal plane, needles, zero-area ones, ones with a vertex (almost) at the origin or on the z axis."""
+  o = np.asarray(origin, np.float32)
+  c = o + rng.normal(size=(n, 1, 3)).astype(np.float32) * rng.choice([0.5, 3.0, 20.0, 80.0], (n, 1, 1)).astype(np.float32)
+  tri = c + rng.normal(size=(n, 3, 3)).astype(np.float32) * rng.choice([1e-3, 0.05, 0.5, 5.0, 60.0], (n, 1, 1)).astype(np.float32)
+  k = n // 16
+  tri[0 * k:1 * k, 2] = tri[0 * k:1 * k, 1]                                  # zero area
+  tri[1 * k:2 * k, 2] = tri[1 * k:2 * k, 1] + 1e-4 * (tri[1 * k:2 * k, 0] - tri[1 * k:2 * k, 1])  # needles
+  tri[2 * k:3 * k, 0] = o                                                     # a vertex at the origin
+  tri[3 * k:4 * k, 0, :2] = o[:2]                                             # a vertex on the z axis through the origin
+  big = rng.uniform(-1, 1, (k, 3, 3)).astype(np.float32) * 200.0              # huge: often pierced by the z axis
+  big[:, :, 2] = rng.choice([-30.0, -2.0, 0.0, 2.0, 30.0], (k, 1)).astype(np.float32) + rng.normal(size=(k, 3)).astype(np.float32) * 0.5
+  tri[4 * k:5 * k] = o + big
+  tri[5 * k:6 * k, :, 2] = o[2]                                               # in the sensor's horizontal plane (edge-on)
+  tri[6 * k:7 * k, 1] = o + (tri[6 * k:7 * k, 0] - o) * np.float32(1.5)       # an edge through the origin's ray (radial edge)
+  verts = tri.reshape(-1, 3)
+  faces = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+  return verts, faces
+
+
+@pytest.mark.parametrize("seed,origin", [(1, (0.0, 0.0, 0.0)), (2, (10.0, -4.0, 1.5)), (3, (1.0e4, 2.0e4, 50.0))])
+def test_cast_hostile_meshes(engine, oracle, seed, origin):
+  rng = np.random.default_rng(seed)
+  verts, faces = _hostile_mesh(rng, 4096, origin)
+  grid = oracle.create_rays(25.0, -25.0, 32, 256)
+  got, _ = _run(engine, oracle, verts, faces, grid, origin, 32)
+  assert (got["tri_id"] >= 0).mean() > 0.5
+  rays = _random_dirs(rng, 4000)
+  _run(engine, oracle, verts, faces, rays, origin, 8)
+
+
+def test_cast_non_finite_vertices_and_bad_faces(engine, oracle):
+  from lidar_transfer_b200._lib import VlidarError, VL_EBADMESH
+  sc = synth.make_scene(2, n_side=30, n_boxes=2)
+  verts = sc["verts"].copy()
+  verts[5] = np.nan
+  verts[77, 1] = np.inf
+  verts[200, 2] = -np.inf
+  verts[300] = 3e38
+  rays = oracle.create_rays(3.0, -25.0, 16, 128)
+  got, _ = _run(engine, oracle, verts, sc["faces"], rays, np.zeros(3, np.float32), 16, sc["colors"], sc["rem"], lbvh=False)
+  assert (got["tri_id"] >= 0).mean() > 0.5
+  faces = sc["faces"].copy()
+  faces[7, 1] = sc["verts"].shape[0] + 5
+  faces[11, 0] = -1
+  beams = engine.Beams(rays, 16)
+  with pytest.raises(VlidarError) as e:
+    engine.cast(beams, sc["verts"], faces, sc["colors"], sc["rem"], np.zeros(3, np.float32), check_mesh=True)
+  assert e.value.code == VL_EBADMESH and "2 face" in str(e.value)
+  out = _np(engine.cast(beams, sc["verts"], faces, sc["colors"], sc["rem"], np.zeros(3, np.float32)))
+  assert not np.isin(out["tri_id"], [7, 11]).any() and (out["tri_id"] >= 0).mean() > 0.5
+
+
+@pytest.mark.parametrize("n_faces", [0, 1, 2, 255, 256, 257, 1025])
+def test_cast_tiny_meshes_ragged_rays_and_empty(engine, oracle, n_faces):
+  rng = np.random.default_rng(n_faces)
+  sc = synth.make_scene(9, n_side=24, n_boxes=0)
+  faces = sc["faces"][rng.permutation(sc["faces"].shape[0])[:n_faces]]
+  rays = oracle.create_rays(-5.0, -40.0, 7, 33)[:7 * 33 - 5]   # height 7 -> width 32, 2 rays never cast
+  got, _ = _run(engine, oracle, sc["verts"], faces, rays, np.zeros(3, np.float32), 7, sc["colors"], sc["rem"])
+  assert (got["tri_id"][7 * 32:] == -1).all()
+  if n_faces == 0:
+    assert (got["tri_id"] == -1).all() and (got["range"] == 0).all()
+  if n_faces == 2:   # no rays at all / fewer rays than rows
+    for n in (0, 3):
+      beams = engine.Beams(rays[:n], 7)
+      out = _np(engine.cast(beams, sc["verts"], faces, sc["colors"], sc["rem"], np.zeros(3, np.float32)))
+      assert out["tri_id"].shape == (n,) and (out["tri_id"] == -1).all()
+
+
+def test_cast_close_geometry_is_shared_by_many_ctas(engine, oracle):
+  """Triangles right in front of the sensor cover most of the cell grid: their items span many chunks."""
+  wall = np.array([[1.0, -30.0, -30.0], [1.0, 30.0, -30.0], [1.0, 30.0, 30.0], [1.0, -30.0, 30.0],
+                   [-0.5, -20.0, -20.0], [-0.5, 20.0, -20.0], [-0.5, 0.0, 20.0]], np.float32)
+  faces = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6]], np.int32)
+  sc = synth.make_scene(4, n_side=40, n_boxes=3)
+  verts = np.concatenate([wall, sc["verts"]])
+  faces = np.concatenate([faces, sc["faces"] + len(wall)])
+  colors, rem = _attrs(verts.shape[0], 3)
+  rays = oracle.create_rays(22.5, -22.5, 64, 512)
+  ref = oracle.trace(rays, np.zeros(3, np.float32), verts, faces, colors, rem, 64, oracle.MIN_ID_TIES)
+  beams = engine.Beams(rays, 64)
+  got = _np(engine.cast(beams, verts, faces, colors, rem, np.zeros(3, np.float32), check_mesh=True))
+  _same(got, ref)
+  assert got["n_items"] > 50 * 1024 and 3 <= got["n_active"] < faces.shape[0] and np.isin(got["tri_id"], [0, 1, 2]).mean() > 0.5
+
+
+@pytest.mark.parametrize("cells", [1, 4])
+def test_cast_result_independent_of_cell_grid(engine, oracle, vl, cells):
+  sc = synth.make_scene(88, n_side=100, n_boxes=8)
+  rays = oracle.create_rays(3.0, -25.0, 32, 512)
+  origin = np.array([0.5, 0.5, 0.0], np.float32)
+  base = _np(engine.cast(engine.Beams(rays, 32), sc["verts"], sc["faces"], sc["colors"], sc["rem"], origin))
+  vl.vl_debug_cast_cells(cells)
+  try:
+    alt = _np(engine.cast(engine.Beams(rays, 32), sc["verts"], sc["faces"], sc["colors"], sc["rem"], origin))
+  finally:
+    vl.vl_debug_cast_cells(2)
+  _same(alt, base)
+  _same(base, oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], 32, oracle.MIN_ID_TIES))
+
+
+def test_cast_zero_misses_and_hits_only(engine, oracle):
+  sc = synth.make_scene(21, n_side=20, n_boxes=3)
+  rays = oracle.create_rays(30.0, -25.0, 16, 64)   # the upper rows look at the sky
+  origin = np.zeros(3, np.float32)
+  import torch
+  beams = engine.Beams(rays, 16)
+  n = rays.shape[0]
+  out = dict(endpoints=torch.full((3 * n,), 7.0, device="cuda"), endcolors=torch.full((3 * n,), 7, dtype=torch.int32, device="cuda"),
+             range=torch.full((n,), 7.0, device="cuda"), endrem=torch.full((n,), 7.0, device="cuda"))
+  got = _np(engine.cast(beams, sc["verts"], sc["faces"], sc["colors"], sc["rem"], origin, out=out))
+  miss = got["tri_id"] < 0
+  assert 0.1 < miss.mean() < 0.9
+  assert (got["range"][miss] == 7).all() and (got["endcolors"].reshape(-1, 3)[miss] == 7).all()   # hits only (RayTracer.cpp:72-90)
+  z = _np(engine.cast(beams, sc["verts"], sc["faces"], sc["colors"], sc["rem"], origin, zero_misses=True))
+  assert (z["range"][miss] == 0).all() and not z["endpoints"].reshape(-1, 3)[miss].any()
+  _same(z, oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], 16, oracle.MIN_ID_TIES))
+
+
+def test_host_ctrace_both_methods(engine, oracle):
+  sc = synth.make_scene(11, n_side=60)
+  H, W = 16, 128
+  rays = oracle.create_rays(3.0, -25.0, H, W)
+  rays[:W] = np.array([0, 0, 1], np.float32)
+  origin = np.zeros(3, np.float32)
+  ref = oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES)
+  for method in ("cast", "lbvh", "cast"):
+    out = dict(endpoints=np.full(3 * H * W, 7.0, np.float32), endcolors=np.full(3 * H * W, 7, np.int32),
+               range=np.full(H * W, 7.0, np.float32), endrem=np.full(H * W, 7.0, np.float32))
+    got = engine.ctrace_host(rays, origin, sc["verts"].reshape(-1), sc["faces"].reshape(-1), sc["colors"].reshape(-1),
+                             sc["rem"], H, outputs=out, want_ids=True, method=method)
+    miss = ref["tri_id"] < 0
+    assert miss[:W].all() and np.array_equal(got["tri_id"], ref["tri_id"]), method
+    assert (got["range"][miss] == 7.0).all() and (got["endcolors"].reshape(-1, 3)[miss] == 7).all()
+    hit = ~miss
+    for k in ("range", "endrem"):
+      assert np.array_equal(got[k][hit].view(np.int32), ref[k][hit].view(np.int32)), (method, k)
+    for k in ("endpoints", "endcolors"):
+      assert np.array_equal(got[k].reshape(-1, 3)[hit].view(np.int32), ref[k].reshape(-1, 3)[hit].view(np.int32)), (method, k)
+
+
+def test_cast_full_size_equals_lbvh(engine, oracle):
+  """Benchmark size (1.05 M triangles, 64 x 2048 and 128 x 2048 beams): both device paths, built on different
+  structures, must return the same bits; the cast is idempotent on a reused workspace."""
+  sc = synth.make_scene(1000, n_side=710)
+  bvh = engine.Bvh(sc["verts"], sc["faces"], sc["colors"], sc["rem"])
+  for sensor, origin in (("HDL-64E", (0.0, 0.0, 0.0)), ("OS1-128", (0.7, -0.4, 0.2))):
+    H, W, fu, fd = synth.SENSORS[sensor]
+    rays = oracle.create_rays(fu, fd, H, W)
+    o = np.asarray(origin, np.float32)
+    a = _np(engine.trace(bvh, rays, o, H))
+    beams = engine.Beams(rays, H)
+    ws = beams.workspace(sc["faces"].shape[0])
+    b = _np(engine.cast(beams, sc["verts"], sc["faces"], sc["colors"], sc["rem"], o, workspace=ws))
+    _same(b, a, what=sensor)
+    c = _np(engine.cast(beams, sc["verts"], sc["faces"], sc["colors"], sc["rem"], o, workspace=ws))
+    _same(c, b, what=sensor + " rerun")
+    assert (b["tri_id"] >= 0).mean() > 0.9
