@@ -8,13 +8,15 @@ Workload ("c5-synthetic-1Mtri-64x2048", BASELINE.json configs[4] shape, the conf
 `Mrays/s ... (64x2048 target)` and the north-star target `>= 100 Mrays/s per GPU on a 64x2048 sensor
 over a ~1 M-triangle scene` are quoted on): S seeded synthetic KITTI-shape scans per GPU per step,
 each with ITS OWN ~1.0 M-triangle mesh (ground grid 710 x 710 + boxes, lidar_transfer_b200/synth.py)
-and the HDL-64E beam pattern 64 x 2048 = 131 072 rays.  One step = for every scan of the batch:
-LBVH build over the scan's mesh + closest-hit trace of all rays (rows (i)+(ii) of the hot path).
+and the HDL-64E beam pattern 64 x 2048 = 131 072 rays.  One step = for every scan of the batch: the closest hit
+of all rays against the scan's mesh (rows (i)+(ii) of the hot path), by --method cast (default: beams indexed once
+per sensor, the scan's triangles streamed through the index, vl_cast) or --method lbvh (per-scan LBVH build +
+per-ray traversal, vl_bvh_build + vl_trace); the other method is timed briefly beside it ("other_method").
 Weak scaling: every rank owns S scans; there is no collective on the data path.
 
 value   = rays traced by all ranks / device time, meshes and rays already resident in HBM.
-e2e     = same metric through the host-buffer path (pinned host meshes -> H2D -> build -> trace ->
-          D2H of the five per-ray outputs), copies inside the timed region.
+e2e     = same metric through the host-buffer path (pinned host meshes -> H2D -> cast -> D2H of the five
+          per-ray outputs), copies inside the timed region.
 roofline= dominant kernel of the step (largest share of device time, measured live with CUDA events
           on the launching streams): algorithmic bytes / mean launch duration vs MEASURED_PEAKS.json.
 cpu_baseline / --impl reference = the reference's own C++ ray tracer (oracle/_ref, compiled from the
@@ -38,7 +40,7 @@ H, W = 64, 2048
 FOV_UP, FOV_DOWN = 3.0, -25.0
 N_SIDE = 710  # 2 * 709^2 = 1 005 362 ground triangles (+ boxes)
 WORKLOAD = "c5-synthetic-1Mtri-64x2048"
-METRIC = "Mrays/s (LBVH build + closest-hit trace per scan, 64x2048 target, ~1M-tri mesh per scan)"
+METRIC = "Mrays/s (closest-hit ray cast of a per-scan ~1M-tri mesh, 64x2048 target)"
 
 
 def _ncu_traffic(kernel):
@@ -101,9 +103,9 @@ class ClockSampler:
             "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_scenes(rank, n_scans):
+def make_scenes(rank, n_meshes):
   from lidar_transfer_b200 import synth
-  return [synth.make_scene(1000 + rank * n_scans + k, n_side=N_SIDE) for k in range(n_scans)]
+  return [synth.make_scene(1000 + rank * n_meshes + k, n_side=N_SIDE) for k in range(n_meshes)]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -191,8 +193,9 @@ def run_native(args):
   from lidar_transfer_b200.rays import create_rays
   L = _lib.lib()
   S, K, Wm = args.scans_per_step, args.steps, args.warmup
+  M = min(args.distinct_meshes, S)   # distinct meshes per rank; a step cycles through them S / M times
   rays_np = create_rays(FOV_UP, FOV_DOWN, H, W)
-  scenes = make_scenes(rank, S)
+  scenes = make_scenes(rank, M)
   n_tris = [int(sc["faces"].shape[0]) for sc in scenes]
   n_verts = [int(sc["verts"].shape[0]) for sc in scenes]
   max_f, max_v = max(n_tris), max(n_verts)
@@ -204,7 +207,8 @@ def run_native(args):
               for sc in scenes]
   mesh_bytes = [sum(t.numel() * t.element_size() for t in hs) for hs in h_scenes]
   origin = np.zeros(3, np.float32)
-  rr = pipeline.ScanRenderer(rays_np, origin, H, max_v, max_f, n_streams=args.streams, device=dev, host_io=True)
+  rr = pipeline.ScanRenderer(rays_np, origin, H, max_v, max_f, n_streams=args.streams, device=dev, host_io=True,
+                             method=args.method)
   rr1 = None
   torch.cuda.synchronize()
 
@@ -215,14 +219,14 @@ def run_native(args):
     torch.cuda.synchronize()
 
   def step_device():
-    for ds in d_scenes:
-      rr.submit(*ds)
+    for k in range(S):
+      rr.submit(*d_scenes[k % M])
 
   def step_host():
-    for hs in h_scenes:
-      rr.submit_host(*hs)
+    for k in range(S):
+      rr.submit_host(*h_scenes[k % M])
 
-  def timed(step_fn, n_steps, profile):
+  def timed(step_fn, n_steps, profile, fence=None):
     """K steps bracketed by barrier + synchronize; device time from CUDA events on the current stream,
     which forks to / joins from the renderer's streams."""
     barrier()
@@ -233,7 +237,7 @@ def run_native(args):
     e0.record()
     for _ in range(n_steps):
       step_fn()
-    (rr1 if profile else rr).fence()
+    (fence or (rr1 if profile else rr)).fence()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -269,17 +273,37 @@ def run_native(args):
   # per-kernel durations: same steps again with the library's event profiler on (events are recorded on the
   # launching streams; kept out of the headline timing because each record costs host time per launch)
   # -- on ONE stream, so that a kernel's duration is not inflated by kernels of other scans sharing the SMs
-  rr1 = pipeline.ScanRenderer(rays_np, origin, H, max_v, max_f, n_streams=1, device=dev, host_io=False)
+  rr1 = pipeline.ScanRenderer(rays_np, origin, H, max_v, max_f, n_streams=1, device=dev, host_io=False,
+                              method=args.method)
 
   def step_profile():
     for ds in d_scenes:
       rr1.submit(*ds)
-  ms_prof, _, stage = timed(step_profile, K, profile=True)
+  ms_prof, _, stage = timed(step_profile, max(1, min(K, 4)), profile=True)
+  n_active = n_units = 0.0
+  if args.method == "cast":   # triangles that can be hit at all / work units of the last profiled scan
+    info = (ctypes.c_int * 8)()
+    L.vl_cast_status(ctypes.c_void_p(rr1.slots[0].blob.data_ptr()), ctypes.c_void_p(rr1.slots[0].stream.cuda_stream), info)
+    n_active, n_units = float(info[1]), float(info[2])
+
+  # the other device path on the same scans, briefly (same bits, different structure: tests/test_cast_gpu.py)
+  other = "lbvh" if args.method == "cast" else "cast"
+  rr2 = pipeline.ScanRenderer(rays_np, origin, H, max_v, max_f, n_streams=args.streams, device=dev, host_io=False,
+                              method=other)
+
+  def step_other():
+    for k in range(S):
+      rr2.submit(*d_scenes[k % M])
+  for _ in range(3):
+    step_other()
+  rr2.wait()
+  ms_other, _, _ = timed(step_other, max(1, min(K, 5)), profile=False, fence=rr2)
+  other_value = S * H * W * world * max(1, min(K, 5)) / (ms_other * 1e-3) / 1e6
 
   # parity spot check of the last scan against the library's brute-force kernel on a ray subset is done in
   # tests/; here only a cheap sanity check that rays hit
   rr.wait()
-  hit_frac = float((rr.slots[(len(d_scenes) - 1) % len(rr.slots)].out["tri_id"] >= 0).float().mean().item())
+  hit_frac = float((rr.slots[(S - 1) % len(rr.slots)].out["tri_id"] >= 0).float().mean().item())
 
   if rank != 0:
     if world > 1:
@@ -289,7 +313,7 @@ def run_native(args):
   rays_per_step = S * H * W * world
   value = rays_per_step * K / (ms_dev * 1e-3) / 1e6
   e2e_value = rays_per_step * K / (ms_e2e * 1e-3) / 1e6
-  h2d = sum(mesh_bytes)                       # per rank per step
+  h2d = sum(mesh_bytes[k % M] for k in range(S))   # per rank per step
   d2h = S * (H * W) * (12 + 12 + 4 + 4 + 4)
   peak, peak_src = _peaks()
 
@@ -302,7 +326,15 @@ def run_native(args):
       "emit_climb": 8 * nt + 12 * nt + 28 * nv + 48 * nt + 16 * nt + 64 * 0.3 * nt,   # ~0.3 nodes per triangle are written
       "top_climb": 64 * 0.004 * nt,
       "trace": 112 * nt + 12 * R + 36 * R,
+      # scene-streaming cast: faces + vertices read once; records (64 B) and work units (8 B) of the triangles that
+      # can be hit at all written once, read once; beam index (sorted beams 16 B, cells 4 B, slots 8 B) read once
+      "cast_init": 8 * R,
+      "cast_setup": 12 * nt + 12 * nv + 64 * n_active + 8 * n_units,
+      "cast_items": 64 * n_active + 8 * n_units + 16 * R + 4 * R + 8 * R,
+      "cast_resolve": (8 + 4 + 16) * R + 36 * R + 36 * R,   # keys, slots, directions in; outputs; face/colour/remission gathers
   }
+  path = ("cast_init", "cast_setup", "cast_items", "cast_resolve") if args.method == "cast" else (
+      "bounds", "morton", "sort_pass", "emit_climb", "top_climb", "trace")
   total_stage_ms = sum(v[0] for v in stage.values()) or 1.0
   dom = max(stage.items(), key=lambda kv: kv[1][0])[0]
   dom_ms, dom_n = stage[dom]
@@ -313,23 +345,25 @@ def run_native(args):
   # cpu baseline: the reference C++ ray tracer on a bounded sample of the same scans
   cpu = None
   if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
-    n_calls = min(args.cpu_scans, S)
+    n_calls = min(args.cpu_scans, M)
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     times, kind = time_reference(scenes, rays_np, n_calls=n_calls, warmup=0)
     cpu_val = n_calls * H * W / sum(times) / 1e6
     cpu = {"value": cpu_val, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": kind,
-           "sample": "%d of the step's %d scans (%d tris, %d rays each), one ctrace call per scan incl. triangle "
-                     "construction + BVH build; %.2f s/scan" % (n_calls, S, n_tris[0], R, sum(times) / n_calls)}
+           "sample": "%d of the step's %d distinct scans (%d tris, %d rays each), one ctrace call per scan incl. triangle "
+                     "construction + BVH build; %.2f s/scan" % (n_calls, M, n_tris[0], R, sum(times) / n_calls)}
 
   line = {
       "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
       "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "f32", "data": "synthetic",
-      "config": {"workload": WORKLOAD, "scans_per_step_per_gpu": S, "rays_per_scan": R,
+      "config": {"workload": WORKLOAD, "method": args.method, "scans_per_step_per_gpu": S, "rays_per_scan": R,
                  "tris_per_scan": int(nt), "streams": args.streams,
-                 "l2": "inputs larger than L2: %d distinct meshes x %.0f MB + %.0f MB BVH blob per stream per step"
-                       % (S, mesh_bytes[0] / 1e6, rr.slots[0].blob.numel() / 1e6),
-                 "e2e_api": "ScanRenderer.submit_host (pinned host mesh -> H2D -> vl_bvh_build -> vl_trace -> D2H)"},
+                 "l2": "inputs larger than L2: %d distinct meshes x %.0f MB cycled per step + %.0f MB scratch per stream"
+                       % (M, mesh_bytes[0] / 1e6, rr.slots[0].blob.numel() / 1e6),
+                 "e2e_api": "ScanRenderer.submit_host (pinned host mesh -> H2D -> %s -> D2H of 5 outputs)"
+                            % ("vl_cast" if args.method == "cast" else "vl_bvh_build -> vl_trace"),
+                 "beam_index": "built once per sensor outside the timed region (vl_beams_build, ~40 us)" if args.method == "cast" else None},
       "scans_per_s": S * world * K / (ms_dev * 1e-3),
       "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
               "scans_per_s": S * world * K / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / K},
@@ -337,9 +371,11 @@ def run_native(args):
       "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                    "frac": achieved / peak, "traffic": _ncu_traffic(dom), "peak_source": peak_src,
                    "alg_bytes_per_launch": alg_bytes.get(dom, 0.0), "ms_per_launch": dom_ms / dom_n,
-                   "step_alg_bytes": sum(alg_bytes[k] * (4 if k == "sort_pass" else 1) for k in alg_bytes) * S,
-                   "profiled_ms_per_step": ms_prof / K},
+                   "step_alg_bytes": sum(alg_bytes[k] * (4 if k == "sort_pass" else 1) for k in path) * S,
+                   "scan_alg_bytes_in_out": 12 * nt + 28 * nv + 36 * R,
+                   "tris_that_can_be_hit": n_active, "work_units": n_units},
       "stages": stages_out,
+      "other_method": {"method": other, "value": other_value, "unit": "Mrays/s", "ms_per_step": ms_other / max(1, min(K, 5))},
       "cpu_baseline": cpu,
       "clocks": clocks,
       "hit_fraction": hit_frac,
@@ -355,8 +391,10 @@ def main():
   ap.add_argument("--steps", type=int, default=10)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="native", choices=["native", "reference"])
-  ap.add_argument("--scans-per-step", type=int, default=8)
+  ap.add_argument("--scans-per-step", type=int, default=32)
+  ap.add_argument("--distinct-meshes", type=int, default=8)
   ap.add_argument("--streams", type=int, default=8)
+  ap.add_argument("--method", default="cast", choices=["cast", "lbvh"])
   ap.add_argument("--cpu-scans", type=int, default=8, help="scans timed for cpu_baseline (about 1.2 s each)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   args = ap.parse_args()

@@ -130,6 +130,15 @@ int vl_cast(const void* d_beams, const float* d_verts, const int* d_faces, const
             int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
             int* d_tri_id, int flags, void* d_workspace, size_t workspace_bytes, vl_stream stream);
 int vl_cast_status(const void* d_workspace, vl_stream stream, int* info);
+/* vl_cast for one scan of a batch in a single call (the per-scan host cost is what bounds a batch at this kernel
+ * speed): if ev_ready (cudaEvent_t) is given it is recorded on `producer` (the stream that produced the mesh) and
+ * `stream` waits for it; then vl_cast; then, if h_status (pinned host int[4]) is given, the first 16 bytes of
+ * the workspace header ([0] n_bad_faces, [1] overflow flag) are copied to it; then ev_done (nullable) is recorded. */
+int vl_cast_submit(const void* d_beams, const float* d_verts, const int* d_faces, const int* d_colors,
+                   const float* d_rem, int n_verts, int n_faces, const float* d_origin, int n_rays,
+                   int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
+                   int* d_tri_id, int flags, void* d_workspace, size_t workspace_bytes, vl_stream stream,
+                   vl_stream producer, void* ev_ready, int* h_status, void* ev_done);
 /* Which device path the host-pointer ctrace / vl_ctrace_ids uses: 0 (default) = beam index +
  * vl_cast, 1 = vl_bvh_build + vl_trace.  Process-wide. */
 void vl_ctrace_method(int method);
@@ -216,7 +225,7 @@ void        vl_debug_trace_stats(int* d_stats);
 /* Debug: force the traversal variant: 0 auto, 1 per-ray in storage order, 2 per-ray in 16x8 beam tiles,
  * 4/8/16/32 = warp packets of that tile width. */
 void        vl_debug_trace_mode(int mode);
-/* Debug: cell rows per beam row of the beam index (default 2); changes vl_beams_bytes. */
+/* Debug: cell rows per beam row of the beam index (default 1); changes vl_beams_bytes. */
 void        vl_debug_cast_cells(int cells_per_beam_row);
 /* Debug: persistent CTAs per SM of the item kernel (default 4). */
 void        vl_debug_cast_ctas(int ctas_per_sm);

@@ -208,6 +208,26 @@ extern "C" int vl_cast(const void* d_beams, const float* d_verts, const int* d_f
                         static_cast<cudaStream_t>(stream));
 }
 
+// One scan of a batch, submitted with a single call: make `stream` wait for the producer of the mesh, cast, copy the
+// first 16 bytes of the workspace header (n_bad_faces, overflow, ...) to pinned host memory, record `ev_done`.
+extern "C" int vl_cast_submit(const void* d_beams, const float* d_verts, const int* d_faces, const int* d_colors,
+                              const float* d_rem, int n_verts, int n_faces, const float* d_origin, int n_rays,
+                              int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
+                              int* d_tri_id, int flags, void* d_workspace, size_t workspace_bytes, vl_stream stream,
+                              vl_stream producer, void* ev_ready, int* h_status, void* ev_done) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ev_ready) {
+    VL_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(ev_ready), static_cast<cudaStream_t>(producer)));
+    VL_CUDA_CHECK(cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(ev_ready), 0));
+  }
+  const int rc = vl_cast(d_beams, d_verts, d_faces, d_colors, d_rem, n_verts, n_faces, d_origin, n_rays, height,
+                         d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, flags, d_workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  if (h_status) VL_CUDA_CHECK(cudaMemcpyAsync(h_status, d_workspace, 16, cudaMemcpyDeviceToHost, s));
+  if (ev_done) VL_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(ev_done), s));
+  return VL_OK;
+}
+
 extern "C" int vl_cast_status(const void* d_workspace, vl_stream stream, int* info) {
   if (!d_workspace) { vl_set_error("vl_cast_status: null workspace"); return VL_EINVAL; }
   return vl_cast_status_read(d_workspace, static_cast<cudaStream_t>(stream), info);
@@ -241,26 +261,14 @@ int ctx_reserve(HostCtx& c, size_t bytes) {
 
 extern "C" void vl_ctrace_method(int method) { g_ctrace_method.store(method == 1 ? 1 : 0); }
 
-extern "C" int vl_ctrace_ids(const float* rays, const float* origin, const float* verts, const int* faces,
-                             const int* colors, const float* rem, int n_rays, int n_verts, int n_faces, int height,
-                             float* endpoints, int* endcolors, float* range, float* endrem, int* tri_id) {
-  if (n_rays < 0 || n_verts < 0 || n_faces < 0 || height <= 0 || !origin ||
-      (n_rays > 0 && (!rays || !endpoints || !endcolors || !range || !endrem)) ||
-      (n_faces > 0 && (!verts || !faces || !colors || !rem))) {
-    vl_set_error("ctrace: invalid argument (n_rays %d, n_verts %d, n_faces %d, height %d)", n_rays, n_verts, n_faces, height);
-    return VL_EINVAL;
-  }
-  int n_dev = 0;
-  VL_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
-  if (n_dev <= 0) { vl_set_error("ctrace: no CUDA device (libvlidar has no CPU fallback)"); return VL_ECUDA; }
-  if (n_rays == 0) return VL_OK;
+static int ctrace_run(bool lbvh, bool* overflowed, const float* rays, const float* origin, const float* verts,
+                      const int* faces, const int* colors, const float* rem, int n_rays, int n_verts, int n_faces,
+                      int height, float* endpoints, int* endcolors, float* range, float* endrem, int* tri_id) {
   HostCtx& c = g_ctx;
-  std::lock_guard<std::mutex> lock(c.mu);
   const size_t nr = (size_t)n_rays, nv = (size_t)n_verts, nf = (size_t)n_faces;
   // arena carve-up
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = vl_align256(off + bytes); return o; };
-  const bool lbvh = g_ctrace_method.load() == 1;
   const size_t o_blob = take(lbvh ? vl_bvh_blob_bytes(n_faces) : vl_beams_bytes(n_rays, height));
   const size_t o_ws = take(lbvh ? 256 : vl_cast_workspace_bytes(n_rays, n_faces));
   const size_t o_rays = take(12 * nr), o_origin = take(12), o_verts = take(12 * nv), o_faces = take(12 * nf);
@@ -305,15 +313,44 @@ extern "C" int vl_ctrace_ids(const float* rays, const float* origin, const float
   VL_CUDA_CHECK(cudaMemcpyAsync(range, A + o_range, 4 * nr, cudaMemcpyDeviceToHost, s));
   VL_CUDA_CHECK(cudaMemcpyAsync(endrem, A + o_erem, 4 * nr, cudaMemcpyDeviceToHost, s));
   if (tri_id) VL_CUDA_CHECK(cudaMemcpyAsync(tri_id, A + o_id, 4 * nr, cudaMemcpyDeviceToHost, s));
-  int n_bad = 0;   // first int of the LBVH header's n_bad_faces sits at offset 8, of the cast header at offset 0
-  VL_CUDA_CHECK(cudaMemcpyAsync(&n_bad, lbvh ? A + o_blob + offsetof(VlHeader, n_bad_faces) : A + o_ws, sizeof(int),
-                                cudaMemcpyDeviceToHost, s));
+  int st[2] = {0, 0};   // {n_bad_faces, overflow}: the first two ints of the cast header; n_bad_faces of the LBVH header
+  VL_CUDA_CHECK(cudaMemcpyAsync(st, lbvh ? A + o_blob + offsetof(VlHeader, n_bad_faces) : A + o_ws,
+                                lbvh ? sizeof(int) : 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
   VL_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (!lbvh && st[1]) {   // the cast ran out of work units before touching any output: take the tree instead
+    *overflowed = true;
+    return VL_OK;
+  }
+  const int n_bad = st[0];
   if (n_bad > 0) {
     vl_set_error("ctrace: %d face(s) reference a vertex outside [0, %d); they were skipped", n_bad, n_verts);
     return VL_EBADMESH;
   }
   return VL_OK;
+}
+
+
+extern "C" int vl_ctrace_ids(const float* rays, const float* origin, const float* verts, const int* faces,
+                             const int* colors, const float* rem, int n_rays, int n_verts, int n_faces, int height,
+                             float* endpoints, int* endcolors, float* range, float* endrem, int* tri_id) {
+  if (n_rays < 0 || n_verts < 0 || n_faces < 0 || height <= 0 || !origin ||
+      (n_rays > 0 && (!rays || !endpoints || !endcolors || !range || !endrem)) ||
+      (n_faces > 0 && (!verts || !faces || !colors || !rem))) {
+    vl_set_error("ctrace: invalid argument (n_rays %d, n_verts %d, n_faces %d, height %d)", n_rays, n_verts, n_faces, height);
+    return VL_EINVAL;
+  }
+  int n_dev = 0;
+  VL_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
+  if (n_dev <= 0) { vl_set_error("ctrace: no CUDA device (libvlidar has no CPU fallback)"); return VL_ECUDA; }
+  if (n_rays == 0) return VL_OK;
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  bool overflowed = false;
+  int rc = ctrace_run(g_ctrace_method.load() == 1, &overflowed, rays, origin, verts, faces, colors, rem, n_rays, n_verts,
+                      n_faces, height, endpoints, endcolors, range, endrem, tri_id);
+  if (rc == VL_OK && overflowed)
+    rc = ctrace_run(true, &overflowed, rays, origin, verts, faces, colors, rem, n_rays, n_verts, n_faces, height, endpoints,
+                    endcolors, range, endrem, tri_id);
+  return rc;
 }
 
 extern "C" void ctrace(float* rays, float* origin, float* verts, int* faces, int* colors, float* rem, int n_rays,

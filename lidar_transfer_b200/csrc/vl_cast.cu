@@ -24,13 +24,13 @@ namespace {
 
 constexpr int kCastThreads = 256;
 constexpr int kCastWarps = kCastThreads / 32;
-constexpr int kFineBins = 4096;     // fine sin(elevation) histogram (prefix sums) for the arithmetic early-out
-constexpr int kChunkItems = 1024;   // (triangle, cell) items per work unit of k_cast_items
-constexpr int kItemBits = 36;       // packed reservation counter: [active triangles : 28][items : 36]
-constexpr float kPi = 3.14159265358979323846f;
-constexpr float kTwoPi = 6.28318530717958647692f;
-constexpr float kInvTwoPi = 0.15915494309189533577f;
-constexpr float kPad0 = 2e-5f;      // angular slack (rad): >> fp32 rounding of yaw / sine / Moller-Trumbore edges
+constexpr int kFineBins = 4096;     // fine sin(elevation) occupancy bitmap for the arithmetic early-out
+constexpr int kFineWords = kFineBins / 32;
+constexpr int kSeg = 64;            // cells per item: an item is one run of <= kSeg cells in one cell row
+constexpr int kUnitItems = 1;       // items per work unit (one lane of k_cast_units)
+constexpr int kBatch = 4 * kCastThreads;   // faces per culling batch of k_cast_setup
+constexpr int kUnitBits = 36;       // packed reservation counter: [records : 28][units : 36]
+constexpr float kPad0 = 2e-5f;      // angular slack (rad): >> fp32 rounding of azimuth / sine / Moller-Trumbore edges
 
 struct VlBeamHeader {
   unsigned int sine_min_ord, sine_max_ord;  // order-preserving uint encodings, reduced by k_beam_prep
@@ -41,21 +41,20 @@ static_assert(sizeof(VlBeamHeader) == 256, "beam header is 256 B");
 
 struct VlCastHeader {
   int n_bad_faces;
-  int overflow;                  // more than 2^36 (triangle, cell) items: results invalid (VL_ENOSPACE)
-  unsigned long long reserved;   // [active triangles : 28][items : 36], bumped once per tile by k_cast_setup
-  unsigned int ticket;           // next chunk of items for k_cast_items
-  int pad[59];
+  int overflow;                  // more work units than the workspace holds: results invalid (VL_ENOSPACE)
+  unsigned long long reserved;   // [records : 28][units : 36], bumped once per pass by k_cast_setup
+  int pad[60];
 };
 static_assert(sizeof(VlCastHeader) == 256, "cast header is 256 B");
 
 struct BeamLayout {
   int n;        // rays cast = width * height (RayTracer.cpp:56)
   int cw, ch;   // direction cells: yaw x sine
-  size_t off_dir, off_sorted, off_sorted_id, off_cell_start, off_cursor, off_fine, off_blk, total;
+  size_t off_dir, off_sorted, off_slot_of, off_cell_start, off_cursor, off_fine, off_mask, off_blk, total;
 };
 
-int g_cells_per_row = 2;  // cell rows per beam row (vl_debug_cast_cells)
-int g_items_ctas_per_sm = 5;
+int g_cells_per_row = 1;   // cell rows per beam row (vl_debug_cast_cells)
+int g_items_ctas_per_sm = 8;
 
 BeamLayout beam_layout(int n_rays, int height) {
   BeamLayout L;
@@ -72,10 +71,11 @@ BeamLayout beam_layout(int n_rays, int height) {
   size_t off = 256;
   L.off_dir = off;        off = vl_align256(off + 16 * nn);
   L.off_sorted = off;     off = vl_align256(off + 16 * nn);
-  L.off_sorted_id = off;  off = vl_align256(off + 4 * nn);
+  L.off_slot_of = off;    off = vl_align256(off + 4 * nn);
   L.off_cell_start = off; off = vl_align256(off + 4 * (ncell + 1));
   L.off_cursor = off;     off = vl_align256(off + 4 * ncell);
-  L.off_fine = off;       off = vl_align256(off + 4 * (kFineBins + 1));
+  L.off_fine = off;       off = vl_align256(off + 4 * kFineBins);
+  L.off_mask = off;       off = vl_align256(off + 4 * kFineWords);
   L.off_blk = off;        off = vl_align256(off + 4 * (ncell / 4096 + 1));
   L.total = off;
   return L;
@@ -83,7 +83,7 @@ BeamLayout beam_layout(int n_rays, int height) {
 
 struct BeamParams {
   int cw, ch;
-  float cw_inv;           // cw / 2 pi
+  float cw_inv;           // cw / 4 (cells per unit of pseudo-angle)
   float lo, hi;           // sine range of the binned rays
   float ch_inv, nf_inv;   // cells / fine bins per unit sine (0 when the range is empty)
 };
@@ -92,11 +92,11 @@ struct BeamParams {
 __device__ __forceinline__ BeamParams beam_params(const VlBeamHeader* hdr, int cw, int ch) {
   BeamParams P;
   P.cw = cw; P.ch = ch;
-  P.cw_inv = (float)cw * kInvTwoPi;
+  P.cw_inv = (float)cw * 0.25f;
   P.lo = vl_ordered_to_float(hdr->sine_min_ord);
   P.hi = vl_ordered_to_float(hdr->sine_max_ord);
   const float span = P.hi - P.lo;
-  const bool ok = span > 1e-12f;   // false also for the empty set (lo = +inf, hi = -inf / NaN)
+  const bool ok = span > 1e-12f;   // false also for the empty set (lo, hi = NaN)
   P.ch_inv = ok ? (float)ch / span : 0.f;
   P.nf_inv = ok ? (float)kFineBins / span : 0.f;
   return P;
@@ -104,7 +104,25 @@ __device__ __forceinline__ BeamParams beam_params(const VlBeamHeader* hdr, int c
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 __device__ __forceinline__ int row_of(float s, const BeamParams& P) { return clampi((int)floorf((s - P.lo) * P.ch_inv), 0, P.ch - 1); }
 __device__ __forceinline__ int fine_of(float s, const BeamParams& P) { return clampi((int)floorf((s - P.lo) * P.nf_inv), 0, kFineBins - 1); }
-__device__ __forceinline__ float wrap_pi(float x) { return x - kTwoPi * rintf(x * kInvTwoPi); }
+// Azimuth as a pseudo-angle ("diamond angle") in [-2, 2]: monotonic in atan2(y, x), same wrap point (x < 0, y = 0),
+// quarter turns at -1, 0, 1, one division instead of an arctangent.  d(pseudo)/d(yaw) lies in [0.5, 1] per radian,
+// so an angular pad in radians is a valid pad in pseudo-angle units, and "does not fit in a half circle" is
+// "extent >= 2" exactly (pseudo(yaw + pi) = pseudo(yaw) + 2).
+__device__ __forceinline__ float pseudo_yaw(float y, float x) {
+  const float m = fabsf(x) + fabsf(y);
+  const float t = m > 0.f ? __fdividef(y, m) : 0.f;   // a direction along the z axis has no azimuth: any value will do
+  return x >= 0.f ? t : (y >= 0.f ? 2.f - t : -2.f - t);
+}
+__device__ __forceinline__ float wrap_2(float x) { return x - 4.f * rintf(x * 0.25f); }
+
+// any beam row in fine bins b0..b1 ?
+__device__ __forceinline__ bool fine_any(const unsigned int* __restrict__ m, int b0, int b1) {
+  const int w0 = b0 >> 5, w1 = b1 >> 5;
+  const unsigned int lo_mask = 0xffffffffu << (b0 & 31), hi_mask = 0xffffffffu >> (31 - (b1 & 31));
+  if (w0 == w1) return (m[w0] & lo_mask & hi_mask) != 0u;
+  // an interval that spans a whole 32-bin word is not examined further: "maybe" is always a valid answer
+  return w1 - w0 > 1 || ((m[w0] & lo_mask) | (m[w1] & hi_mask)) != 0u;
+}
 
 // ---------------------------------------------------------------------------
 // beam index (once per sensor / ray set)
@@ -112,11 +130,11 @@ __device__ __forceinline__ float wrap_pi(float x) { return x - kTwoPi * rintf(x 
 __global__ void k_beam_init(VlBeamHeader* hdr, int* cell_cnt, int ncell_p1, int* fine) {
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncell_p1; i += stride) cell_cnt[i] = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= kFineBins; i += stride) fine[i] = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kFineBins; i += stride) fine[i] = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) { hdr->sine_min_ord = 0xffffffffu; hdr->sine_max_ord = 0u; hdr->n_binned = 0; }
 }
 
-// normalised direction (the one vl_tri_hit is given, vl_normalize = Vector3.h:73-89 with IEEE 1/sqrt) + yaw
+// normalised direction (the one vl_tri_hit is given, vl_normalize = Vector3.h:73-89 with IEEE 1/sqrt) + azimuth
 __global__ void __launch_bounds__(kCastThreads)
 k_beam_prep(const float* __restrict__ rays, int n, float4* __restrict__ dir, VlBeamHeader* hdr) {
   __shared__ float s_min[kCastWarps], s_max[kCastWarps];
@@ -126,7 +144,7 @@ k_beam_prep(const float* __restrict__ rays, int n, float4* __restrict__ dir, VlB
   int cnt = 0;
   if (r < n) {
     const float3 d = vl_normalize(__ldg(rays + 3 * (size_t)r), __ldg(rays + 3 * (size_t)r + 1), __ldg(rays + 3 * (size_t)r + 2));
-    float yaw = atan2f(d.y, d.x);
+    float yaw = pseudo_yaw(d.y, d.x);
     const bool ok = isfinite(d.x) && isfinite(d.y) && isfinite(d.z) && isfinite(yaw);
     if (!ok) yaw = __int_as_float(0x7fc00000);
     dir[r] = make_float4(d.x, d.y, d.z, yaw);
@@ -153,8 +171,8 @@ k_beam_prep(const float* __restrict__ rays, int n, float4* __restrict__ dir, VlB
 }
 
 __device__ __forceinline__ int ray_cell(const float4 d, const BeamParams& P) {
-  int col = (int)floorf((d.w + kPi) * P.cw_inv);
-  if (col >= P.cw) col -= P.cw;   // yaw = +pi is the same direction as -pi
+  int col = (int)floorf((d.w + 2.f) * P.cw_inv);
+  if (col >= P.cw) col -= P.cw;   // azimuth +2 is the same direction as -2
   col = clampi(col, 0, P.cw - 1);
   return row_of(d.z, P) * P.cw + col;
 }
@@ -175,7 +193,8 @@ k_beam_count(const float4* __restrict__ dir, int n, const VlBeamHeader* __restri
 }
 
 // exclusive prefix sums of the cell counts in three coalesced steps (local 4096-element scans, scan of the block
-// totals + of the fine bins, apply) -- in place, plus a copy as the scatter cursor
+// totals, apply) -- in place, plus a copy as the scatter cursor; the middle step also folds the fine bins into
+// their occupancy bitmap
 constexpr int kScanBlock = 4096;
 
 __device__ __forceinline__ int block_excl_1024(int v, int* s_warp, int* s_total) {
@@ -213,31 +232,20 @@ k_beam_scan_local(int* __restrict__ cell, int ncell, int* __restrict__ blk_sum) 
 }
 
 __global__ void __launch_bounds__(1024)
-k_beam_scan_top(int* __restrict__ blk_sum, int nblk, int* __restrict__ cell, int ncell, int* __restrict__ fine) {
+k_beam_scan_top(int* __restrict__ blk_sum, int nblk, int* __restrict__ cell, int ncell, const int* __restrict__ fine,
+                unsigned int* __restrict__ fine_mask) {
   __shared__ int s_warp[32];
   __shared__ int s_total;
-  {
-    const int per = (nblk + 1023) / 1024;
-    const int b = min((int)threadIdx.x * per, nblk), e = min(b + per, nblk);
-    int sum = 0;
-    for (int i = b; i < e; ++i) sum += blk_sum[i];
-    int run = block_excl_1024(sum, s_warp, &s_total);
-    for (int i = b; i < e; ++i) { const int c = blk_sum[i]; blk_sum[i] = run; run += c; }
-    if (threadIdx.x == 0) cell[ncell] = s_total;
-  }
-  {
-    constexpr int per = kFineBins / 1024;
-    const int b = threadIdx.x * per;
-    int v[per];
-#pragma unroll
-    for (int i = 0; i < per; ++i) v[i] = fine[b + i];
-    int sum = 0;
-#pragma unroll
-    for (int i = 0; i < per; ++i) sum += v[i];
-    int run = block_excl_1024(sum, s_warp, &s_total);
-#pragma unroll
-    for (int i = 0; i < per; ++i) { fine[b + i] = run; run += v[i]; }
-    if (threadIdx.x == 0) fine[kFineBins] = s_total;
+  const int per = (nblk + 1023) / 1024;
+  const int b = min((int)threadIdx.x * per, nblk), e = min(b + per, nblk);
+  int sum = 0;
+  for (int i = b; i < e; ++i) sum += blk_sum[i];
+  int run = block_excl_1024(sum, s_warp, &s_total);
+  for (int i = b; i < e; ++i) { const int c = blk_sum[i]; blk_sum[i] = run; run += c; }
+  if (threadIdx.x == 0) cell[ncell] = s_total;
+  for (int bin = threadIdx.x; bin < kFineBins; bin += 1024) {   // 32 consecutive bins per warp -> one mask word
+    const unsigned int word = __ballot_sync(0xffffffffu, fine[bin] > 0);
+    if ((threadIdx.x & 31) == 0) fine_mask[bin >> 5] = word;
   }
 }
 
@@ -250,17 +258,19 @@ k_beam_scan_apply(int* __restrict__ cell, int ncell, const int* __restrict__ blk
   cursor[i] = v;
 }
 
+// sorted[slot] = direction + azimuth of the ray that landed in `slot` (cell order); slot_of[r] = its slot, -1 for a
+// ray without a finite direction.  The per-scan hit keys are kept per SLOT, so the cast never needs a ray index.
 __global__ void __launch_bounds__(kCastThreads)
 k_beam_scatter(const float4* __restrict__ dir, int n, const VlBeamHeader* __restrict__ hdr, int cw, int ch,
-               int* __restrict__ cursor, float4* __restrict__ sorted, int* __restrict__ sorted_id) {
+               int* __restrict__ cursor, float4* __restrict__ sorted, int* __restrict__ slot_of) {
   const int r = blockIdx.x * kCastThreads + threadIdx.x;
   if (r >= n) return;
   const float4 d = dir[r];
-  if (!(d.w == d.w)) return;
+  if (!(d.w == d.w)) { slot_of[r] = -1; return; }
   const BeamParams P = beam_params(hdr, cw, ch);
   const int slot = atomicAdd(&cursor[ray_cell(d, P)], 1);
   sorted[slot] = d;
-  sorted_id[slot] = r;
+  slot_of[r] = slot;
 }
 
 // ---------------------------------------------------------------------------
@@ -274,21 +284,18 @@ struct TriRec {
   int ca, ncx, ra, ncy;
 };
 
-// Conservative (yaw, sine) rectangle of triangle f as seen from o, and the cells it overlaps.
-// Returns the number of cells (0 = no beam can hit it).  The central projection of a planar triangle is a
-// spherical triangle with great-circle edges:
-//   * yaw is monotonic along an edge, so the yaw interval is spanned by the three vertex yaws unless the
-//     z axis pierces the triangle -- exactly when they do not fit in a half circle (extent >= pi);
+// Conservative (azimuth, sine) rectangle of a triangle as seen from o, and the cells it overlaps.  The central
+// projection of a planar triangle is a spherical triangle with great-circle edges:
+//   * azimuth is monotonic along an edge, so the azimuth interval is spanned by the three vertex azimuths unless
+//     the z axis pierces the triangle -- exactly when they do not fit in a half circle;
 //   * sin(elevation) has no interior extremum on the face except at the poles, and along an edge of arc
 //     length L it exceeds its end values by at most L^2 / 8 (|d2/dphi2 sin e| <= 1 on a great circle).
-__device__ __forceinline__ int tri_setup(int f, const float* __restrict__ verts, const int* __restrict__ faces,
-                                         int n_verts, const float3 o, const BeamParams& P,
-                                         const int* fine, TriRec& T, int* bad) {
-  const int i0 = __ldg(faces + 3 * (size_t)f), i1 = __ldg(faces + 3 * (size_t)f + 1), i2 = __ldg(faces + 3 * (size_t)f + 2);
-  if ((unsigned)i0 >= (unsigned)n_verts || (unsigned)i1 >= (unsigned)n_verts || (unsigned)i2 >= (unsigned)n_verts) {
-    *bad = 1;
-    return 0;
-  }
+// kFull = false: the cheap part only (sine interval against the vertical field of view and the beam rows), returns
+// 1 when the triangle survives; kFull = true: the whole rectangle, returns the number of items (runs of <= kSeg
+// cells of one cell row; 0 = no beam can hit it).
+template <bool kFull>
+__device__ __forceinline__ int tri_setup(int f, int i0, int i1, int i2, const float* __restrict__ verts, const float3 o,
+                                         const BeamParams& P, const unsigned int* __restrict__ fine_mask, TriRec& T) {
   const float ax = __ldg(verts + 3 * (size_t)i0), ay = __ldg(verts + 3 * (size_t)i0 + 1), az = __ldg(verts + 3 * (size_t)i0 + 2);
   const float bx = __ldg(verts + 3 * (size_t)i1), by = __ldg(verts + 3 * (size_t)i1 + 1), bz = __ldg(verts + 3 * (size_t)i1 + 2);
   const float cx = __ldg(verts + 3 * (size_t)i2), cy = __ldg(verts + 3 * (size_t)i2 + 1), cz = __ldg(verts + 3 * (size_t)i2 + 2);
@@ -299,15 +306,12 @@ __device__ __forceinline__ int tri_setup(int f, const float* __restrict__ verts,
   // (x * 0 == 0 exactly for finite x only)
   if (!(((p0x * 0.f + p0y * 0.f + p0z * 0.f) + (p1x * 0.f + p1y * 0.f + p1z * 0.f) + (p2x * 0.f + p2y * 0.f + p2z * 0.f)) == 0.f)) return 0;
   const float q0 = p0x * p0x + p0y * p0y + p0z * p0z, q1 = p1x * p1x + p1y * p1y + p1z * p1z, q2 = p2x * p2x + p2y * p2y + p2z * p2z;
-  T.v0x = ax; T.v0y = ay; T.v0z = az;
-  T.e1x = __fsub_rn(bx, ax); T.e1y = __fsub_rn(by, ay); T.e1z = __fsub_rn(bz, az);
-  T.e2x = __fsub_rn(cx, ax); T.e2y = __fsub_rn(cy, ay); T.e2z = __fsub_rn(cz, az);
-  T.orig = f;
   float slo, shi;
   bool all_yaw;
   float y0 = 0.f, lo_d = 0.f, hi_d = 0.f, pad_y = 0.f;
   const float qmin = fminf(q0, fminf(q1, q2)), qmax = fmaxf(q0, fmaxf(q1, q2));
   if (!(qmin > 1e-30f && qmax < 1e30f)) {
+    if (!kFull) return 1;
     slo = -2.f; shi = 2.f; all_yaw = true;   // a vertex at the origin / out of float range: every beam is a candidate
   } else {
     const float r0 = rsqrtf(q0), r1 = rsqrtf(q1), r2 = rsqrtf(q2);
@@ -327,68 +331,58 @@ __device__ __forceinline__ int tri_setup(int f, const float* __restrict__ verts,
     const float pad_s = kPad0 + 2.f * E * fmaxf(r0, fmaxf(r1, r2));
     slo = fminf(u0z, fminf(u1z, u2z)) - bulge - pad_s;
     shi = fmaxf(u0z, fmaxf(u1z, u2z)) + bulge + pad_s;
-    // quick reject on the vertical field of view before any yaw work
+    // reject on the vertical field of view and on the beam rows before any azimuth work.  The interval so far is
+    // valid unless the z axis pierces the triangle, which needs the origin inside its xy bounding box.
     if (shi < P.lo || slo > P.hi) return 0;
+    const float e2 = 2.f * E;
+    const bool near_axis = fminf(p0x, fminf(p1x, p2x)) <= e2 && fmaxf(p0x, fmaxf(p1x, p2x)) >= -e2 &&
+                           fminf(p0y, fminf(p1y, p2y)) <= e2 && fmaxf(p0y, fmaxf(p1y, p2y)) >= -e2;
+    if (!near_axis && !fine_any(fine_mask, fine_of(slo, P), fine_of(shi, P))) return 0;
+    if (!kFull) return 1;
     const float h0 = p0x * p0x + p0y * p0y, h1 = p1x * p1x + p1y * p1y, h2 = p2x * p2x + p2y * p2y;
     const float hmin = fminf(h0, fminf(h1, h2));
     all_yaw = !(hmin > 1e-30f);
     if (!all_yaw) {
       pad_y = kPad0 + 2.f * E * rsqrtf(hmin);
-      y0 = atan2f(p0y, p0x);
-      const float d1 = wrap_pi(atan2f(p1y, p1x) - y0), d2 = wrap_pi(atan2f(p2y, p2x) - y0);
+      y0 = pseudo_yaw(p0y, p0x);
+      const float d1 = wrap_2(pseudo_yaw(p1y, p1x) - y0), d2 = wrap_2(pseudo_yaw(p2y, p2x) - y0);
       lo_d = fminf(0.f, fminf(d1, d2));
       hi_d = fmaxf(0.f, fmaxf(d1, d2));
-      all_yaw = !((hi_d - lo_d) + 2.f * pad_y < kPi - 1e-3f);
+      all_yaw = !((hi_d - lo_d) + 2.f * pad_y < 2.f - 1e-3f);
     }
-    if (all_yaw) {   // the z axis may pierce the triangle: the elevation reaches the pole on that side
+    if (all_yaw && near_axis) {   // the z axis may pierce the triangle: the elevation reaches the pole on that side
       if (fmaxf(p0z, fmaxf(p1z, p2z)) > 0.f) shi = 2.f;
       if (fminf(p0z, fminf(p1z, p2z)) < 0.f) slo = -2.f;
     }
   }
   if (shi < P.lo || slo > P.hi) return 0;
-  if (fine[fine_of(shi, P) + 1] - fine[fine_of(slo, P)] == 0) return 0;   // no beam row inside the sine interval
+  if (!fine_any(fine_mask, fine_of(slo, P), fine_of(shi, P))) return 0;   // no beam row inside the sine interval
+  T.v0x = ax; T.v0y = ay; T.v0z = az;
+  T.e1x = __fsub_rn(bx, ax); T.e1y = __fsub_rn(by, ay); T.e1z = __fsub_rn(bz, az);
+  T.e2x = __fsub_rn(cx, ax); T.e2y = __fsub_rn(cy, ay); T.e2z = __fsub_rn(cz, az);
+  T.orig = f;
   T.slo = slo; T.shi = shi;
   T.ra = row_of(slo, P);
   T.ncy = row_of(shi, P) - T.ra + 1;
   if (all_yaw) {
     T.ca = 0; T.ncx = P.cw; T.ymid = 0.f; T.yhalf = -1.f;
   } else {
-    const int ca = (int)floorf((y0 + lo_d - pad_y + kPi) * P.cw_inv), cb = (int)floorf((y0 + hi_d + pad_y + kPi) * P.cw_inv);
+    const int ca = (int)floorf((y0 + lo_d - pad_y + 2.f) * P.cw_inv), cb = (int)floorf((y0 + hi_d + pad_y + 2.f) * P.cw_inv);
     const int ncx = cb - ca + 1;
     if (ncx >= P.cw) {
       T.ca = 0; T.ncx = P.cw; T.ymid = 0.f; T.yhalf = -1.f;
     } else {
-      int c = ca % P.cw;
+      // y0 + lo_d - pad_y > -2 - 2 - pad: ca >= -cw - 1, one or two conditional wraps instead of a modulo
+      int c = ca;
       if (c < 0) c += P.cw;
+      if (c < 0) c += P.cw;
+      if (c >= P.cw) c -= P.cw;
       T.ca = c; T.ncx = ncx;
       T.ymid = y0 + 0.5f * (lo_d + hi_d);
       T.yhalf = 0.5f * (hi_d - lo_d) + pad_y;
     }
   }
-  return T.ncx * T.ncy;
-}
-
-// one (triangle, cell) item: test the cell's beams that lie inside the triangle's padded rectangle
-__device__ __forceinline__ void cast_item(const TriRec& T, int l, const BeamParams& P, const int* __restrict__ cell_start,
-                                          const float4* __restrict__ sorted, const int* __restrict__ sorted_id,
-                                          const float3 o, unsigned long long* __restrict__ best) {
-  const int yy = l / T.ncx;
-  int cx = T.ca + (l - yy * T.ncx);
-  if (cx >= P.cw) cx -= P.cw;
-  const int cell = (T.ra + yy) * P.cw + cx;
-  const int s = __ldg(cell_start + cell), e = __ldg(cell_start + cell + 1);
-  for (int k = s; k < e; ++k) {
-    const float4 rd = __ldg(sorted + k);
-    if (rd.z < T.slo || rd.z > T.shi) continue;
-    if (T.yhalf >= 0.f && fabsf(wrap_pi(rd.w - T.ymid)) > T.yhalf) continue;
-    float t;
-    if (vl_tri_hit(make_float4(T.v0x, T.v0y, T.v0z, 0.f), make_float4(T.e1x, T.e1y, T.e1z, 0.f),
-                   make_float4(T.e2x, T.e2y, T.e2z, 0.f), o, make_float3(rd.x, rd.y, rd.z), &t)) {
-      const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned int)T.orig;
-      unsigned long long* slot = best + __ldg(sorted_id + k);
-      if (key < __ldcg(slot)) atomicMin(slot, key);   // a NaN t orders above the initial key and never wins
-    }
-  }
+  return T.ncy * ((T.ncx + kSeg - 1) / kSeg);
 }
 
 __device__ __forceinline__ unsigned long long init_key() {
@@ -399,148 +393,234 @@ __global__ void k_cast_init(unsigned long long* __restrict__ best, int n, VlCast
   const int stride = gridDim.x * blockDim.x;
   const unsigned long long k = init_key();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) best[i] = k;
-  if (blockIdx.x == 0 && threadIdx.x == 0) { hdr->n_bad_faces = 0; hdr->overflow = 0; hdr->reserved = 0ull; hdr->ticket = 0u; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { hdr->n_bad_faces = 0; hdr->overflow = 0; hdr->reserved = 0ull; }
 }
 
-// Step 1: stream the faces once.  Every triangle gets its cell rectangle; the ~30 % that can be hit at all are
-// compacted into a list (face index, first item) in which a triangle covering n cells owns n consecutive
-// "items".  One packed 64-bit atomicAdd per tile reserves list positions and item numbers TOGETHER, so the
-// item numbers increase along the list whatever order the tiles arrive in.
-__global__ void __launch_bounds__(kCastThreads)
-k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const int* __restrict__ fine_g,
+// Step 1: stream the faces once, in batches of 1024 per CTA.
+//   cull:  every face gets the cheap test (sine interval vs the beam rows); ~70 % of a LiDAR scene's triangles lie
+//          between two beam rows or outside the vertical field of view and stop here.  Survivors are queued in
+//          shared memory, so that
+//   setup: runs on dense warps: the full rectangle, a 64-byte record (edges for the triangle test + rectangle)
+//          and ceil(items / 4) work units (record, first item) appended to global lists -- one packed atomicAdd
+//          per pass reserves both.  List order is irrelevant: a unit is self-contained.
+__global__ void __launch_bounds__(kCastThreads, 4)
+k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsigned int* __restrict__ fine_mask_g,
              const float* __restrict__ verts, const int* __restrict__ faces, int n_verts, int n_faces,
-             const float* __restrict__ origin, VlCastHeader* chdr, int* __restrict__ list_f,
-             unsigned long long* __restrict__ list_start) {
-  __shared__ int s_fine[kFineBins + 1];
+             const float* __restrict__ origin, VlCastHeader* chdr, float4* __restrict__ recs,
+             int2* __restrict__ units, unsigned long long unit_cap) {
+  __shared__ unsigned int s_mask[kFineWords];
+  __shared__ int s_queue[kBatch];
+  __shared__ int s_nq;
   __shared__ unsigned long long s_warp[kCastWarps];
-  __shared__ unsigned long long s_base;
-  for (int i = threadIdx.x; i <= kFineBins; i += kCastThreads) s_fine[i] = __ldg(fine_g + i);
+  __shared__ unsigned long long s_at[kCastThreads + 1];   // per thread of a pass: packed (record position, first unit)
+  if (threadIdx.x < kFineWords) s_mask[threadIdx.x] = __ldg(fine_mask_g + threadIdx.x);
+  if (threadIdx.x == 0) s_nq = 0;
   __syncthreads();
   const BeamParams P = beam_params(bhdr, cw, ch);
   const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int n_tiles = (n_faces + kCastThreads - 1) / kCastThreads;
+  const int n_batches = (n_faces + kBatch - 1) / kBatch;
+  const unsigned long long units_mask = (1ull << kUnitBits) - 1ull;
   int n_bad = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int f = tile * kCastThreads + threadIdx.x;
-    int n_i = 0;
-    if (f < n_faces) {
-      TriRec T;
-      int bad = 0;
-      n_i = tri_setup(f, verts, faces, n_verts, o, P, s_fine, T, &bad);
-      n_bad += bad;
-    }
-    // block-exclusive scan of the packed pair (1 << 36 | n_i): list position and item number in one go
-    const unsigned long long mine = n_i > 0 ? ((1ull << kItemBits) | (unsigned long long)n_i) : 0ull;
-    unsigned long long incl = mine;
+  for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+    // ---- cull
+    int idx[kBatch / kCastThreads][3];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += u;
-    }
-    if (lane == 31) s_warp[w] = incl;
-    __syncthreads();
-    unsigned long long before = 0ull, total = 0ull;
-#pragma unroll
-    for (int k = 0; k < kCastWarps; ++k) { const unsigned long long x = s_warp[k]; if (k < w) before += x; total += x; }
-    if (threadIdx.x == 0 && total) {
-      const unsigned long long old = atomicAdd(&chdr->reserved, total);
-      const unsigned long long items_mask = (1ull << kItemBits) - 1ull;
-      if ((old & items_mask) + (total & items_mask) > items_mask) chdr->overflow = 1;
-      s_base = old;
-    }
-    __syncthreads();
-    if (n_i > 0) {
-      const unsigned long long at = s_base + before + incl - mine;
-      const int pos = (int)(at >> kItemBits);
-      if (pos < n_faces) {   // always, unless the item counter overflowed into the position bits
-        list_f[pos] = f;
-        list_start[pos] = at & ((1ull << kItemBits) - 1ull);
+    for (int k = 0; k < kBatch / kCastThreads; ++k) {   // all index loads first: faces -> verts is a dependent gather
+      const int f = batch * kBatch + k * kCastThreads + threadIdx.x;
+      if (f < n_faces) {
+        idx[k][0] = __ldg(faces + 3 * (size_t)f); idx[k][1] = __ldg(faces + 3 * (size_t)f + 1); idx[k][2] = __ldg(faces + 3 * (size_t)f + 2);
       }
     }
-    // (s_warp / s_base are rewritten only after the next tile's first barrier)
+#pragma unroll
+    for (int k = 0; k < kBatch / kCastThreads; ++k) {
+      const int f = batch * kBatch + k * kCastThreads + threadIdx.x;
+      bool keep = false;
+      if (f < n_faces) {
+        if ((unsigned)idx[k][0] >= (unsigned)n_verts || (unsigned)idx[k][1] >= (unsigned)n_verts || (unsigned)idx[k][2] >= (unsigned)n_verts) {
+          ++n_bad;
+        } else {
+          TriRec dummy;
+          keep = tri_setup<false>(f, idx[k][0], idx[k][1], idx[k][2], verts, o, P, s_mask, dummy) != 0;
+        }
+      }
+      const unsigned int m = __ballot_sync(0xffffffffu, keep);
+      if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_nq, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) s_queue[base + __popc(m & ((1u << lane) - 1u))] = f;
+      }
+    }
+    __syncthreads();
+    const int nq = s_nq;
+    // ---- setup of the survivors
+    for (int qb = 0; qb < nq; qb += kCastThreads) {
+      const int j = qb + threadIdx.x;
+      TriRec T;
+      int n_i = 0;
+      if (j < nq) {
+        const int f = s_queue[j];
+        const int i0 = __ldg(faces + 3 * (size_t)f), i1 = __ldg(faces + 3 * (size_t)f + 1), i2 = __ldg(faces + 3 * (size_t)f + 2);
+        n_i = tri_setup<true>(f, i0, i1, i2, verts, o, P, s_mask, T);
+      }
+      const int n_u = (n_i + kUnitItems - 1) / kUnitItems;
+      // block-exclusive scan of the packed pair (1 << 36 | n_u): record position and first unit in one go
+      const unsigned long long mine = n_i > 0 ? ((1ull << kUnitBits) | (unsigned long long)n_u) : 0ull;
+      unsigned long long incl = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += u;
+      }
+      if (lane == 31) s_warp[w] = incl;
+      __syncthreads();
+      if (w == 0) {
+        const unsigned long long x = lane < kCastWarps ? s_warp[lane] : 0ull;
+        unsigned long long xi = x;
+#pragma unroll
+        for (int d = 1; d < kCastWarps; d <<= 1) {
+          const unsigned long long u = __shfl_up_sync(0xffffffffu, xi, d);
+          if (lane >= d) xi += u;
+        }
+        const unsigned long long total = __shfl_sync(0xffffffffu, xi, kCastWarps - 1);
+        unsigned long long base = 0ull;
+        if (lane == 0 && total) {
+          base = atomicAdd(&chdr->reserved, total);
+          if ((base & units_mask) + (total & units_mask) > unit_cap) chdr->overflow = 1;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < kCastWarps) s_warp[lane] = base + xi - x;
+      }
+      __syncthreads();
+      const unsigned long long at = s_warp[w] + incl - mine;
+      s_at[threadIdx.x] = at;
+      if (threadIdx.x == kCastThreads - 1) s_at[kCastThreads] = at + mine;
+      if (n_i > 0) {
+        const int pos = (int)(at >> kUnitBits);
+        if (pos < n_faces && (at & units_mask) + (unsigned long long)n_u <= unit_cap) {   // always, unless the unit list overflowed
+          float4* r = recs + 4 * (size_t)pos;
+          r[0] = make_float4(T.v0x, T.v0y, T.v0z, T.e1x);
+          r[1] = make_float4(T.e1y, T.e1z, T.e2x, T.e2y);
+          r[2] = make_float4(T.e2z, __int_as_float(T.orig), T.ymid, T.yhalf);
+          r[3] = make_float4(T.slo, T.shi, __int_as_float(T.ca | (T.ncx << 16)), __int_as_float(T.ra | (T.ncy << 16)));
+        }
+      }
+      __syncthreads();
+      // the pass's units, written with consecutive threads on consecutive entries: thread t finds the owner of unit
+      // u_first + t by bisection over the 256 first-unit numbers (a thread without units shares its successor's)
+      {
+        const unsigned long long u_first = s_at[0] & units_mask, u_end = s_at[kCastThreads] & units_mask;
+        for (unsigned long long u = u_first + threadIdx.x; u < u_end && u < unit_cap; u += kCastThreads) {
+          int j = 0;
+#pragma unroll
+          for (int step = kCastThreads / 2; step > 0; step >>= 1)
+            if ((s_at[j + step] & units_mask) <= u) j += step;
+          units[u] = make_int2((int)(s_at[j] >> kUnitBits), (int)(u - (s_at[j] & units_mask)) * kUnitItems);
+        }
+      }
+      __syncthreads();   // s_warp / s_at are reused by the next pass
+    }
+    if (threadIdx.x == 0) s_nq = 0;
+    __syncthreads();
   }
   if (n_bad) atomicAdd(&chdr->n_bad_faces, n_bad);
 }
 
-// largest pos in [0, n) with a[pos] <= key (a is increasing, a[0] <= key): CTA-wide 256-ary search
-__device__ __forceinline__ int coop_search(const unsigned long long* __restrict__ a, int n, unsigned long long key) {
-  int lo = 0, hi = n;
-  while (hi - lo > 1) {
-    const int step = (hi - lo + kCastThreads - 1) / kCastThreads;
-    const int p = lo + (int)threadIdx.x * step;
-    const bool ok = p < hi && __ldg(a + p) <= key;
-    const int c = __syncthreads_count(ok);   // the threads that are ok form a prefix
-    lo = lo + (c - 1) * step;
-    hi = min(hi, lo + step);
-  }
-  return lo;
-}
+// Step 2: a warp per 32 work units.  A unit is one item: a run of <= kSeg cells of one cell row of a triangle's
+// rectangle; the beams of consecutive cells are consecutive in the sorted beam list, so a run is one contiguous
+// range of it (two when it wraps at the azimuth seam).  Each lane decodes its unit and parks the triangle in shared
+// memory; then the warp pools the beams of its 32 units and tests them 32 at a time -- full lanes whatever the
+// mix of units -- keeping the closest hit per beam slot with a fire-and-forget 64-bit atomicMin.  No CTA barrier; a
+// triangle in front of the sensor (thousands of runs) is spread over as many lanes as it has units.
+struct UnitRec {
+  float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z;
+  unsigned int orig;
+  float ymid, yhalf, slo, shi;
+  int ka0, ka1, kb0, kb1;
+};
 
-// Step 2: the items, evenly.  CTAs draw chunks of kChunkItems consecutive items from a ticket counter, so a
-// triangle in front of the sensor (thousands of cells) is shared by many CTAs while hundreds of distant
-// ones (a few cells each) fill one chunk.  Per chunk: find the list range, set its triangles up again
-// (cheaper than a 72-byte record round trip through HBM), then one item per thread per step.
 __global__ void __launch_bounds__(kCastThreads)
-k_cast_items(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const int* __restrict__ cell_start,
-             const float4* __restrict__ sorted, const int* __restrict__ sorted_id, const int* __restrict__ fine_g,
-             const float* __restrict__ verts, const int* __restrict__ faces, int n_verts,
-             const float* __restrict__ origin, unsigned long long* __restrict__ best, VlCastHeader* chdr,
-             const int* __restrict__ list_f, const unsigned long long* __restrict__ list_start) {
-  __shared__ TriRec s_rec[kCastThreads];
-  __shared__ unsigned long long s_start[kCastThreads];
-  __shared__ unsigned long long s_last_end;
-  __shared__ unsigned int s_chunk;
-  const unsigned long long reserved = chdr->reserved;
-  const unsigned long long n_items = reserved & ((1ull << kItemBits) - 1ull);
-  const int n_active = (int)(reserved >> kItemBits);
-  if (n_active == 0 || chdr->overflow) return;
-  const BeamParams P = beam_params(bhdr, cw, ch);
+k_cast_units(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const int* __restrict__ cell_start,
+             const float4* __restrict__ sorted, const float* __restrict__ origin,
+             unsigned long long* __restrict__ best, const VlCastHeader* __restrict__ chdr,
+             const float4* __restrict__ recs, const int2* __restrict__ units) {
+  __shared__ UnitRec s_rec[kCastWarps][32];
+  __shared__ int s_off[kCastWarps][33];
+  if (chdr->overflow) return;
+  const unsigned long long n_units = chdr->reserved & ((1ull << kUnitBits) - 1ull);
   const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
-  while (true) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_chunk = atomicAdd(&chdr->ticket, 1u);
-    __syncthreads();
-    const unsigned long long lo_item = (unsigned long long)s_chunk * kChunkItems;
-    if (lo_item >= n_items) break;
-    const unsigned long long hi_item = min(n_items, lo_item + kChunkItems);
-    const int p0 = coop_search(list_start, n_active, lo_item);
-    for (int base = p0;; base += kCastThreads) {
-      const int pos = base + threadIdx.x;
-      unsigned long long st = 0ull;
-      const bool valid = pos < n_active && (st = __ldg(list_start + pos)) < hi_item;
-      if (valid) {
-        int bad = 0;
-        const int n = tri_setup(__ldg(list_f + pos), verts, faces, n_verts, o, P, fine_g, s_rec[threadIdx.x], &bad);
-        s_start[threadIdx.x] = st;
-        const bool last = !(pos + 1 < n_active && __ldg(list_start + pos + 1) < hi_item) || threadIdx.x == kCastThreads - 1;
-        if (last) s_last_end = st + (unsigned long long)n;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned long long n_groups = (n_units + 31) / 32;
+  const unsigned long long g_stride = (unsigned long long)gridDim.x * kCastWarps;
+  for (unsigned long long g = (unsigned long long)blockIdx.x * kCastWarps + w; g < n_groups; g += g_stride) {
+    const unsigned long long u = g * 32 + lane;
+    int n_r = 0;
+    if (u < n_units) {
+      const int2 unit = __ldg(units + u);
+      const float4* rec = recs + 4 * (size_t)unit.x;
+      const float4 q3 = __ldg(rec + 3);
+      const int pk0 = __float_as_int(q3.z), pk1 = __float_as_int(q3.w);
+      const int ca = pk0 & 0xffff, ncx = pk0 >> 16, ra = pk1 & 0xffff;
+      const int nseg = (ncx + kSeg - 1) / kSeg;
+      int yy = unit.y, sx = 0;
+      if (nseg > 1) { yy = unit.y / nseg; sx = unit.y - yy * nseg; }
+      const int len = min(kSeg, ncx - sx * kSeg);
+      int c_begin = ca + sx * kSeg;
+      if (c_begin >= cw) c_begin -= cw;
+      const int len_a = min(len, cw - c_begin), len_b = len - len_a;
+      const int* row = cell_start + (size_t)(ra + yy) * cw;
+      const int ka0 = __ldg(row + c_begin), ka1 = __ldg(row + c_begin + len_a);
+      int kb0 = 0, kb1 = 0;
+      if (len_b > 0) { kb0 = __ldg(row); kb1 = __ldg(row + len_b); }
+      n_r = ka1 - ka0 + kb1 - kb0;
+      if (n_r > 0) {
+        const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+        UnitRec& R = s_rec[w][lane];
+        R.v0x = q0.x; R.v0y = q0.y; R.v0z = q0.z; R.e1x = q0.w; R.e1y = q1.x; R.e1z = q1.y; R.e2x = q1.z; R.e2y = q1.w; R.e2z = q2.x;
+        R.orig = (unsigned int)__float_as_int(q2.y); R.ymid = q2.z; R.yhalf = q2.w; R.slo = q3.x; R.shi = q3.y;
+        R.ka0 = ka0; R.ka1 = ka1; R.kb0 = kb0; R.kb1 = kb1;
       }
-      const int cnt = __syncthreads_count(valid);   // valid threads form a prefix
-      if (cnt == 0) break;
-      const unsigned long long pass_lo = max(lo_item, s_start[0]), pass_hi = min(hi_item, s_last_end);
-      for (unsigned long long item = pass_lo + threadIdx.x; item < pass_hi; item += kCastThreads) {
-        int j = 0;
-#pragma unroll
-        for (int step = kCastThreads / 2; step > 0; step >>= 1)
-          if (j + step < cnt && s_start[j + step] <= item) j += step;
-        cast_item(s_rec[j], (int)(item - s_start[j]), P, cell_start, sorted, sorted_id, o, best);
-      }
-      if (cnt < kCastThreads) break;
-      __syncthreads();
     }
+    int incl = n_r;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;   // warp-uniform
+    s_off[w][lane] = incl - n_r;
+    if (lane == 31) s_off[w][32] = total;
+    __syncwarp();
+    for (int it = lane; it < total; it += 32) {
+      int j = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) if (s_off[w][j + step] <= it) j += step;
+      const UnitRec& R = s_rec[w][j];
+      int k = R.ka0 + (it - s_off[w][j]);
+      if (k >= R.ka1) k = R.kb0 + (k - R.ka1);
+      const float4 rd = __ldg(sorted + k);
+      if (rd.z < R.slo || rd.z > R.shi) continue;
+      if (R.yhalf >= 0.f && fabsf(wrap_2(rd.w - R.ymid)) > R.yhalf) continue;
+      float t;
+      if (vl_tri_hit(make_float4(R.v0x, R.v0y, R.v0z, 0.f), make_float4(R.e1x, R.e1y, R.e1z, 0.f),
+                     make_float4(R.e2x, R.e2y, R.e2z, 0.f), o, make_float3(rd.x, rd.y, rd.z), &t)) {
+        // a NaN t orders above the initial key and never wins; no value is read back (RED, not ATOM)
+        atomicMin(best + k, ((unsigned long long)__float_as_uint(t) << 32) | R.orig);
+      }
+    }
+    __syncwarp();
   }
 }
 
 // RayTracer.cpp:73-90 write-back for the winning triangle of each beam; BVH.cpp:106-107 hit = o + d * t
 __global__ void __launch_bounds__(kCastThreads)
 k_cast_resolve(const unsigned long long* __restrict__ best, int n, const float4* __restrict__ dir,
-               const float* __restrict__ origin, const int* __restrict__ faces, const int* __restrict__ colors,
+               const int* __restrict__ slot_of, const float* __restrict__ origin, const int* __restrict__ faces, const int* __restrict__ colors,
                const float* __restrict__ rem, float* __restrict__ endpoints, int* __restrict__ endcolors,
                float* __restrict__ range, float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses) {
   const int r = blockIdx.x * kCastThreads + threadIdx.x;
   if (r >= n) return;
-  const unsigned long long key = best[r];
+  const int slot = __ldg(slot_of + r);
+  const unsigned long long key = slot >= 0 ? best[slot] : init_key();
   if (key < init_key()) {
     const int f = (int)(unsigned int)(key & 0xffffffffull);
     const float t = __uint_as_float((unsigned int)(key >> 32));
@@ -575,15 +655,16 @@ extern "C" void vl_debug_cast_ctas(int ctas_per_sm) { g_items_ctas_per_sm = ctas
 
 size_t vl_beams_bytes_impl(int n_rays, int height) { return beam_layout(n_rays, height).total; }
 
-struct CastLayout { size_t off_best, off_list_f, off_list_start, total; };
+struct CastLayout { size_t off_best, off_units, off_recs, total; unsigned long long unit_cap; };
 
 CastLayout cast_layout(int n_rays, int n_faces) {
   CastLayout C;
   const size_t nr = n_rays > 0 ? (size_t)n_rays : 1, nf = n_faces > 0 ? (size_t)n_faces : 1;
   size_t off = 256;
   C.off_best = off;       off = vl_align256(off + 8 * nr);
-  C.off_list_start = off; off = vl_align256(off + 8 * nf);
-  C.off_list_f = off;     off = vl_align256(off + 4 * nf);
+  C.unit_cap = 4 * nf + (1ull << 18);   // a unit is a run of <= 64 cells of one cell row; LiDAR meshes need ~0.6 nf
+  C.off_units = off;      off = vl_align256(off + 8 * (size_t)C.unit_cap);
+  C.off_recs = off;       off = vl_align256(off + 64 * nf);
   C.total = off;
   return C;
 }
@@ -596,32 +677,32 @@ int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_b
   VlBeamHeader* hdr = reinterpret_cast<VlBeamHeader*>(B);
   float4* dir = reinterpret_cast<float4*>(B + L.off_dir);
   float4* sorted = reinterpret_cast<float4*>(B + L.off_sorted);
-  int* sorted_id = reinterpret_cast<int*>(B + L.off_sorted_id);
+  int* slot_of = reinterpret_cast<int*>(B + L.off_slot_of);
   int* cell_start = reinterpret_cast<int*>(B + L.off_cell_start);
   int* cursor = reinterpret_cast<int*>(B + L.off_cursor);
   int* fine = reinterpret_cast<int*>(B + L.off_fine);
+  unsigned int* fine_mask = reinterpret_cast<unsigned int*>(B + L.off_mask);
+  int* blk_sum = reinterpret_cast<int*>(B + L.off_blk);
   const int ncell = L.cw * L.ch;
   VlProfScope ps(VL_ST_BEAMS, stream);
   k_beam_init<<<148, 256, 0, stream>>>(hdr, cell_start, ncell + 1, fine);
   VL_LAUNCH_CHECK("k_beam_init");
+  const int nb = (L.n + kCastThreads - 1) / kCastThreads;
   if (L.n > 0) {
-    const int nb = (L.n + kCastThreads - 1) / kCastThreads;
     k_beam_prep<<<nb, kCastThreads, 0, stream>>>(d_rays, L.n, dir, hdr);
     VL_LAUNCH_CHECK("k_beam_prep");
     k_beam_count<<<nb, kCastThreads, 0, stream>>>(dir, L.n, hdr, L.cw, L.ch, cell_start, fine);
     VL_LAUNCH_CHECK("k_beam_count");
   }
-  int* blk_sum = reinterpret_cast<int*>(B + L.off_blk);
   const int nblk = (ncell + kScanBlock - 1) / kScanBlock;
   k_beam_scan_local<<<nblk, 1024, 0, stream>>>(cell_start, ncell, blk_sum);
   VL_LAUNCH_CHECK("k_beam_scan_local");
-  k_beam_scan_top<<<1, 1024, 0, stream>>>(blk_sum, nblk, cell_start, ncell, fine);
+  k_beam_scan_top<<<1, 1024, 0, stream>>>(blk_sum, nblk, cell_start, ncell, fine, fine_mask);
   VL_LAUNCH_CHECK("k_beam_scan_top");
   k_beam_scan_apply<<<(ncell + 1023) / 1024, 1024, 0, stream>>>(cell_start, ncell, blk_sum, cursor);
   VL_LAUNCH_CHECK("k_beam_scan_apply");
   if (L.n > 0) {
-    const int nb = (L.n + kCastThreads - 1) / kCastThreads;
-    k_beam_scatter<<<nb, kCastThreads, 0, stream>>>(dir, L.n, hdr, L.cw, L.ch, cursor, sorted, sorted_id);
+    k_beam_scatter<<<nb, kCastThreads, 0, stream>>>(dir, L.n, hdr, L.cw, L.ch, cursor, sorted, slot_of);
     VL_LAUNCH_CHECK("k_beam_scatter");
   }
   return VL_OK;
@@ -639,15 +720,15 @@ int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces
   const VlBeamHeader* bhdr = reinterpret_cast<const VlBeamHeader*>(B);
   const float4* dir = reinterpret_cast<const float4*>(B + L.off_dir);
   const float4* sorted = reinterpret_cast<const float4*>(B + L.off_sorted);
-  const int* sorted_id = reinterpret_cast<const int*>(B + L.off_sorted_id);
+  const int* slot_of = reinterpret_cast<const int*>(B + L.off_slot_of);
   const int* cell_start = reinterpret_cast<const int*>(B + L.off_cell_start);
-  const int* fine = reinterpret_cast<const int*>(B + L.off_fine);
+  const unsigned int* fine_mask = reinterpret_cast<const unsigned int*>(B + L.off_mask);
   char* Wk = static_cast<char*>(d_ws);
   const CastLayout C = cast_layout(n_rays, n_faces);
   VlCastHeader* chdr = reinterpret_cast<VlCastHeader*>(Wk);
   unsigned long long* best = reinterpret_cast<unsigned long long*>(Wk + C.off_best);
-  unsigned long long* list_start = reinterpret_cast<unsigned long long*>(Wk + C.off_list_start);
-  int* list_f = reinterpret_cast<int*>(Wk + C.off_list_f);
+  int2* units = reinterpret_cast<int2*>(Wk + C.off_units);
+  float4* recs = reinterpret_cast<float4*>(Wk + C.off_recs);
   {
     VlProfScope ps(VL_ST_CAST_INIT, stream);
     k_cast_init<<<148, 256, 0, stream>>>(best, L.n, chdr);
@@ -656,24 +737,23 @@ int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces
   if (n_faces > 0) {
     {
       VlProfScope ps(VL_ST_CAST_SETUP, stream);
-      const int n_tiles = (n_faces + kCastThreads - 1) / kCastThreads;
-      const int nb = n_tiles < 148 * 4 ? n_tiles : 148 * 4;
-      k_cast_setup<<<nb, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine, d_verts, d_faces, n_verts, n_faces, d_origin,
-                                                   chdr, list_f, list_start);
+      const int n_batches = (n_faces + kBatch - 1) / kBatch;
+      const int nb = n_batches < 148 * 4 ? n_batches : 148 * 4;
+      k_cast_setup<<<nb, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, d_verts, d_faces, n_verts, n_faces,
+                                                   d_origin, chdr, recs, units, C.unit_cap);
       VL_LAUNCH_CHECK("k_cast_setup");
     }
     {
       VlProfScope ps(VL_ST_CAST_ITEMS, stream);
-      k_cast_items<<<148 * g_items_ctas_per_sm, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, cell_start, sorted, sorted_id,
-                                                                          fine, d_verts, d_faces, n_verts, d_origin, best,
-                                                                          chdr, list_f, list_start);
-      VL_LAUNCH_CHECK("k_cast_items");
+      k_cast_units<<<148 * g_items_ctas_per_sm, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, cell_start, sorted, d_origin,
+                                                                          best, chdr, recs, units);
+      VL_LAUNCH_CHECK("k_cast_units");
     }
   }
   {
     VlProfScope ps(VL_ST_CAST_RESOLVE, stream);
     const int nb = (L.n + kCastThreads - 1) / kCastThreads;
-    k_cast_resolve<<<nb, kCastThreads, 0, stream>>>(best, L.n, dir, d_origin, d_faces, d_colors, d_rem, d_endpoints,
+    k_cast_resolve<<<nb, kCastThreads, 0, stream>>>(best, L.n, dir, slot_of, d_origin, d_faces, d_colors, d_rem, d_endpoints,
                                                    d_endcolors, d_range, d_endrem, d_tri_id,
                                                    (flags & VL_TRACE_ZERO_MISSES) != 0);
     VL_LAUNCH_CHECK("k_cast_resolve");
@@ -687,13 +767,14 @@ int vl_cast_status_read(const void* d_ws, cudaStream_t stream, int* info) {
   VL_CUDA_CHECK(cudaStreamSynchronize(stream));
   if (info) {
     info[0] = h.n_bad_faces;
-    info[1] = (int)(h.reserved >> kItemBits);                                       // triangles that can be hit at all
-    const unsigned long long items = h.reserved & ((1ull << kItemBits) - 1ull);   // (triangle, cell) items
+    info[1] = (int)(h.reserved >> kUnitBits);                                       // triangles that can be hit at all
+    const unsigned long long items = h.reserved & ((1ull << kUnitBits) - 1ull);   // work units (<= 4 cell runs each)
     info[2] = (int)(items & 0x7fffffffull);
     info[3] = (int)(items >> 31);
   }
   if (h.overflow) {
-    vl_set_error("vl_cast: more than 2^36 (triangle, cell) candidates -- results are invalid, use vl_bvh_build + vl_trace");
+    vl_set_error("vl_cast: the mesh needs more work units (%llu) than the workspace holds -- results are invalid, use vl_bvh_build + vl_trace",
+                 (unsigned long long)(h.reserved & ((1ull << kUnitBits) - 1ull)));
     return VL_ENOSPACE;
   }
   if (h.n_bad_faces > 0) {

@@ -138,12 +138,14 @@ class Beams:
 
 
 def cast(beams, verts, faces, colors, rem, origin, out=None, want_ids=True, zero_misses=False, workspace=None,
-         check_mesh=False):
+         check_mesh=True):
   """(ii-b) closest-hit cast of an indexed mesh against indexed beams -- same outputs as
   Bvh(...) + trace(...), i.e. as C_Trace (RayTracerCython.pyx:15-33 -> RayTracer.cpp:19-92), without a
   per-scan tree: the triangles are streamed once through the beam index.  Mesh arrays as for Bvh.
-  check_mesh=True synchronises, raises VlidarError(VL_EBADMESH) on out-of-range face indices and adds
-  n_bad_faces / n_active (triangles that can be hit at all) / n_items (triangle-cell candidates) to the result."""
+  check_mesh=True (default) synchronises, raises VlidarError(VL_EBADMESH) on out-of-range face indices or
+  VlidarError(VL_ENOSPACE) when the mesh needs more work units than the workspace holds (nothing was written then:
+  use Bvh + trace), and adds n_bad_faces / n_active (triangles that can be hit at all) / n_units to the result.
+  With check_mesh=False the call is asynchronous and the caller checks lib().vl_cast_status itself."""
   dev = beams.blob.device
   verts = _dev(verts, torch.float32, dev).reshape(-1)
   faces = _dev(faces, torch.int32, dev).reshape(-1)
@@ -164,7 +166,7 @@ def cast(beams, verts, faces, colors, rem, origin, out=None, want_ids=True, zero
     if check_mesh:
       info = (ctypes.c_int * 8)()
       rc = lib().vl_cast_status(_ptr(workspace), _stream(), info)
-      out["n_bad_faces"], out["n_active"], out["n_items"] = info[0], info[1], info[2] + (info[3] << 31)
+      out["n_bad_faces"], out["n_active"], out["n_units"] = info[0], info[1], info[2] + (info[3] << 31)
       check(rc)
   return out
 

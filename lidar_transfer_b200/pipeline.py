@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import engine
+from . import _lib as _lib_mod
 from ._lib import check, lib
 
 
@@ -37,6 +38,18 @@ class _Slot:
                     tri_id=torch.empty(n_rays, dtype=i32, device=dev))
     self.done = torch.cuda.Event()
     self.busy = False
+    # first 16 bytes of the cast workspace header (n_bad_faces, overflow, ...), copied back after every scan
+    self.h_status = torch.zeros(4, dtype=torch.int32, pin_memory=True)
+    self.h_status_np = self.h_status.numpy()
+    self.d_status = self.blob[:16].view(torch.int32)
+    # raw handles for the single-call submission path (vl_cast_submit): events must exist before their handle does
+    self.ready = torch.cuda.Event()
+    self.ready.record(self.stream)
+    self.done.record(self.stream)
+    self.fixed = (self.out["endpoints"].data_ptr(), self.out["endcolors"].data_ptr(), self.out["range"].data_ptr(),
+                  self.out["endrem"].data_ptr(), self.out["tri_id"].data_ptr(), engine.TRACE_ZERO_MISSES,
+                  self.blob.data_ptr(), self.blob.numel(), self.stream.cuda_stream)
+    self.tail = (self.ready.cuda_event, self.h_status.data_ptr(), self.done.cuda_event)
     if host_io:
       # device staging for host-fed meshes + pinned host buffers for the results
       self.d_verts = torch.empty(3 * max_verts, dtype=f32, device=dev)
@@ -69,6 +82,8 @@ class ScanRenderer:
     self.host_io = host_io
     self._next = 0
     self._lib = lib()
+    self._beams_ptr = self.beams.blob.data_ptr() if self.beams is not None else 0
+    self._origin_ptr = self.origin.data_ptr()
 
   def _acquire(self):
     s = self.slots[self._next]
@@ -76,6 +91,7 @@ class ScanRenderer:
     if s.busy:
       s.done.synchronize()  # the slot's previous scan must have drained before its buffers are reused
       s.busy = False
+      self._check(s)
     return s
 
   def _launch(self, s, verts, faces, colors, rem, n_verts, n_faces):
@@ -86,6 +102,8 @@ class ScanRenderer:
                       _ptr(self.origin), self.n_rays, self.height, _ptr(s.out["endpoints"]), _ptr(s.out["endcolors"]),
                       _ptr(s.out["range"]), _ptr(s.out["endrem"]), _ptr(s.out["tri_id"]), engine.TRACE_ZERO_MISSES,
                       _ptr(s.blob), s.blob.numel(), st))
+      with torch.cuda.stream(s.stream):
+        s.h_status.copy_(s.d_status, non_blocking=True)
       return
     check(L.vl_bvh_build(_ptr(verts), _ptr(faces), _ptr(colors), _ptr(rem), n_verts, n_faces, _ptr(s.blob),
                          s.blob.numel(), st))
@@ -101,6 +119,14 @@ class ScanRenderer:
     if n_faces > self.max_faces:
       raise ValueError("mesh has %d faces, renderer was sized for %d" % (n_faces, self.max_faces))
     s = self._acquire()
+    if self.method == "cast":
+      # one C call per scan: wait for the producer stream, four launches, status copy, done event
+      # (the caller is on self.dev; per-scan host time bounds the batch at this kernel speed)
+      check(self._lib.vl_cast_submit(self._beams_ptr, verts.data_ptr(), faces.data_ptr(), colors.data_ptr(), rem.data_ptr(),
+                                     n_verts, n_faces, self._origin_ptr, self.n_rays, self.height, *s.fixed,
+                                     torch.cuda.current_stream(self.dev).cuda_stream, *s.tail))
+      s.busy = True
+      return s
     s.stream.wait_stream(torch.cuda.current_stream(self.dev))
     with torch.cuda.device(self.dev):
       self._launch(s, verts, faces, colors, rem, n_verts, n_faces)
@@ -131,11 +157,19 @@ class ScanRenderer:
     s.busy = True
     return s
 
+  def _check(self, s):
+    """After the slot's scan has drained: the cast must not have run out of work units (its outputs would be all
+    misses); such a mesh has to go through method="lbvh"."""
+    if self.method == "cast" and s.h_status_np[1] != 0:
+      raise _lib_mod.VlidarError(_lib_mod.VL_ENOSPACE, "the mesh needs more cast work units than the workspace holds; "
+                                 "use ScanRenderer(method='lbvh') for it")
+
   def wait(self):
     for s in self.slots:
       if s.busy:
         s.done.synchronize()
         s.busy = False
+        self._check(s)
 
   def fence(self):
     """Make the current torch stream wait for everything submitted so far (device-side join)."""

@@ -41,9 +41,12 @@ for method in methods:
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 10
     a.record()
+    t0 = time.perf_counter()
     for rep in range(reps):
       for s in scenes: R.submit(*s)
+    host_us = 1e6 * (time.perf_counter() - t0) / (reps * len(scenes))
     R.fence(); b.record(); torch.cuda.synchronize()
+    res["%s_%dstream_host_us_per_submit" % (method, n_streams)] = round(host_us, 1)
     us = 1e3 * a.elapsed_time(b) / (reps * len(scenes))
     res["%s_%dstream_us_per_scan" % (method, n_streams)] = round(us, 1)
     res["%s_%dstream_Mrays" % (method, n_streams)] = round(H * W / us, 1)
@@ -56,7 +59,7 @@ for method in methods:
     if method == "cast" and n_streams == 1:
       info = (ctypes.c_int * 8)()
       L.vl_cast_status(ctypes.c_void_p(R.slots[0].blob.data_ptr()), ctypes.c_void_p(R.slots[0].stream.cuda_stream), info)
-      res["n_active"], res["n_items"] = info[1], info[2]
+      res["n_active"], res["n_units"] = info[1], info[2]
       res["hit_fraction"] = float((R.slots[0].out["tri_id"] >= 0).float().mean())
 # beam index build time
 L.vl_profile_enable(1)
