@@ -6,7 +6,8 @@ every stage runs through libvlidar (include/vlidar.h):
   TSDFVolume.integrate           fusion_lidar.py:252-287  -> vl_tsdf_integrate
   TSDFVolume.get_volume          fusion_lidar.py:395-400  -> D2H on request only
   TSDFVolume.get_mesh            fusion_lidar.py:403-424  -> vl_mesh_extract (iso-surface + vertex lookup on device)
-  TSDFVolume.throw_rays_at_mesh  fusion_lidar.py:426-455  -> vl_bvh_build + vl_trace on the device-resident mesh
+  TSDFVolume.throw_rays_at_mesh  fusion_lidar.py:426-455  -> vl_beams_build + vl_cast on the device-resident mesh
+                                                           (vl_bvh_build + vl_trace if the cast reports VL_ENOSPACE)
   meshwrite                      fusion_lidar.py:462-495  -> same ASCII PLY bytes, vectorised
 
 The host-facing values (numpy arrays, dtypes, shapes) are the reference's; `*_device` variants return
@@ -15,7 +16,7 @@ CUDA tensors without the D2H copies for callers that stay on the GPU.
 import numpy as np
 import torch
 
-from .. import engine
+from .. import _lib, engine
 
 FUSION_GPU_MODE = 1  # the reference sets 0 when pycuda is missing and falls back to numpy; there is no fallback here
 
@@ -77,8 +78,15 @@ class TSDFVolume(object):
 
   def throw_rays_at_mesh_device(self, rays, origin, H, W):
     m = self.get_mesh_device()
-    bvh = engine.Bvh(m["verts"], m["faces"], m["colors"].to(torch.int32), m["rem"])  # colors.astype(np.int32), :437
-    out = engine.trace(bvh, rays, origin, H, want_ids=False, zero_misses=True)
+    colors = m["colors"].to(torch.int32)  # colors.astype(np.int32), :437
+    try:
+      beams = engine.Beams(rays, H, m["verts"].device)
+      out = engine.cast(beams, m["verts"], m["faces"], colors, m["rem"], origin, want_ids=False, zero_misses=True)
+    except _lib.VlidarError as e:
+      if e.code != _lib.VL_ENOSPACE:
+        raise
+      bvh = engine.Bvh(m["verts"], m["faces"], colors, m["rem"])
+      out = engine.trace(bvh, rays, origin, H, want_ids=False, zero_misses=True)
     return out, m
 
   def throw_rays_at_mesh(self, rays, origin, H, W, color_lut):

@@ -26,7 +26,9 @@ constexpr int kCastThreads = 256;
 constexpr int kCastWarps = kCastThreads / 32;
 constexpr int kFineBins = 4096;     // fine sin(elevation) occupancy bitmap for the arithmetic early-out
 constexpr int kFineWords = kFineBins / 32;
-constexpr int kSeg = 64;            // cells per item: an item is one run of <= kSeg cells in one cell row
+constexpr int kSegShift = 3;        // an item is one run of <= 8 cells of one cell row ...
+constexpr int kSegShiftWide = 6;    // ... or of <= 64 cells for a triangle wider than kWideCols (bounds the unit count)
+constexpr int kWideCols = 128;
 constexpr int kUnitItems = 1;       // items per work unit (one lane of k_cast_units)
 constexpr int kBatch = 4 * kCastThreads;   // faces per culling batch of k_cast_setup
 constexpr int kUnitBits = 36;       // packed reservation counter: [records : 28][units : 36]
@@ -291,7 +293,7 @@ struct TriRec {
 //   * sin(elevation) has no interior extremum on the face except at the poles, and along an edge of arc
 //     length L it exceeds its end values by at most L^2 / 8 (|d2/dphi2 sin e| <= 1 on a great circle).
 // kFull = false: the cheap part only (sine interval against the vertical field of view and the beam rows), returns
-// 1 when the triangle survives; kFull = true: the whole rectangle, returns the number of items (runs of <= kSeg
+// 1 when the triangle survives; kFull = true: the whole rectangle, returns the number of items (runs of
 // cells of one cell row; 0 = no beam can hit it).
 template <bool kFull>
 __device__ __forceinline__ int tri_setup(int f, int i0, int i1, int i2, const float* __restrict__ verts, const float3 o,
@@ -382,7 +384,8 @@ __device__ __forceinline__ int tri_setup(int f, int i0, int i1, int i2, const fl
       T.yhalf = 0.5f * (hi_d - lo_d) + pad_y;
     }
   }
-  return T.ncy * ((T.ncx + kSeg - 1) / kSeg);
+  const int sh = T.ncx > kWideCols ? kSegShiftWide : kSegShift;
+  return T.ncy * ((T.ncx + (1 << sh) - 1) >> sh);
 }
 
 __device__ __forceinline__ unsigned long long init_key() {
@@ -403,7 +406,10 @@ __global__ void k_cast_init(unsigned long long* __restrict__ best, int n, VlCast
 //   setup: runs on dense warps: the full rectangle, a 64-byte record (edges for the triangle test + rectangle)
 //          and ceil(items / 4) work units (record, first item) appended to global lists -- one packed atomicAdd
 //          per pass reserves both.  List order is irrelevant: a unit is self-contained.
-__global__ void __launch_bounds__(kCastThreads, 4)
+#ifndef VL_SETUP_MINB
+#define VL_SETUP_MINB 4
+#endif
+__global__ void __launch_bounds__(kCastThreads, VL_SETUP_MINB)
 k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsigned int* __restrict__ fine_mask_g,
              const float* __restrict__ verts, const int* __restrict__ faces, int n_verts, int n_faces,
              const float* __restrict__ origin, VlCastHeader* chdr, float4* __restrict__ recs,
@@ -503,7 +509,8 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
           r[0] = make_float4(T.v0x, T.v0y, T.v0z, T.e1x);
           r[1] = make_float4(T.e1y, T.e1z, T.e2x, T.e2y);
           r[2] = make_float4(T.e2z, __int_as_float(T.orig), T.ymid, T.yhalf);
-          r[3] = make_float4(T.slo, T.shi, __int_as_float(T.ca | (T.ncx << 16)), __int_as_float(T.ra | (T.ncy << 16)));
+          r[3] = make_float4(T.slo, T.shi, __int_as_float(T.ca | (T.ncx << 16) | (T.ncx > kWideCols ? (1 << 30) : 0)),
+                             __int_as_float(T.ra | (T.ncy << 16)));
         }
       }
       __syncthreads();
@@ -527,7 +534,7 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
   if (n_bad) atomicAdd(&chdr->n_bad_faces, n_bad);
 }
 
-// Step 2: a warp per 32 work units.  A unit is one item: a run of <= kSeg cells of one cell row of a triangle's
+// Step 2: a warp per 32 work units.  A unit is one item: a run of <= 8 (64 for very wide triangles) cells of one cell row of a triangle's
 // rectangle; the beams of consecutive cells are consecutive in the sorted beam list, so a run is one contiguous
 // range of it (two when it wraps at the azimuth seam).  Each lane decodes its unit and parks the triangle in shared
 // memory; then the warp pools the beams of its 32 units and tests them 32 at a time -- full lanes whatever the
@@ -561,12 +568,13 @@ k_cast_units(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const int* _
       const float4* rec = recs + 4 * (size_t)unit.x;
       const float4 q3 = __ldg(rec + 3);
       const int pk0 = __float_as_int(q3.z), pk1 = __float_as_int(q3.w);
-      const int ca = pk0 & 0xffff, ncx = pk0 >> 16, ra = pk1 & 0xffff;
-      const int nseg = (ncx + kSeg - 1) / kSeg;
+      const int ca = pk0 & 0xffff, ncx = (pk0 >> 16) & 0x1fff, ra = pk1 & 0xffff;
+      const int sh = (pk0 >> 30) & 1 ? kSegShiftWide : kSegShift;
+      const int nseg = (ncx + (1 << sh) - 1) >> sh;
       int yy = unit.y, sx = 0;
       if (nseg > 1) { yy = unit.y / nseg; sx = unit.y - yy * nseg; }
-      const int len = min(kSeg, ncx - sx * kSeg);
-      int c_begin = ca + sx * kSeg;
+      const int len = min(1 << sh, ncx - (sx << sh));
+      int c_begin = ca + (sx << sh);
       if (c_begin >= cw) c_begin -= cw;
       const int len_a = min(len, cw - c_begin), len_b = len - len_a;
       const int* row = cell_start + (size_t)(ra + yy) * cw;
@@ -662,7 +670,7 @@ CastLayout cast_layout(int n_rays, int n_faces) {
   const size_t nr = n_rays > 0 ? (size_t)n_rays : 1, nf = n_faces > 0 ? (size_t)n_faces : 1;
   size_t off = 256;
   C.off_best = off;       off = vl_align256(off + 8 * nr);
-  C.unit_cap = 4 * nf + (1ull << 18);   // a unit is a run of <= 64 cells of one cell row; LiDAR meshes need ~0.6 nf
+  C.unit_cap = 4 * nf + (1ull << 20);   // a unit is a run of <= 8 (64) cells of one cell row; LiDAR meshes need ~0.6 nf
   C.off_units = off;      off = vl_align256(off + 8 * (size_t)C.unit_cap);
   C.off_recs = off;       off = vl_align256(off + 64 * nf);
   C.total = off;
@@ -738,7 +746,7 @@ int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces
     {
       VlProfScope ps(VL_ST_CAST_SETUP, stream);
       const int n_batches = (n_faces + kBatch - 1) / kBatch;
-      const int nb = n_batches < 148 * 4 ? n_batches : 148 * 4;
+      const int nb = n_batches < 148 * VL_SETUP_MINB ? n_batches : 148 * VL_SETUP_MINB;
       k_cast_setup<<<nb, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, d_verts, d_faces, n_verts, n_faces,
                                                    d_origin, chdr, recs, units, C.unit_cap);
       VL_LAUNCH_CHECK("k_cast_setup");

@@ -1,6 +1,7 @@
 """Per-stage device times of the whole synthesis chain at BASELINE.json config-1 size (C1: one 124 668-point
 scan, 64x2048 image, voxel 0.05 m over [-50,50]x[-35.5,35.5]x[-3,2] = 2000 x 1420 x 100 = 284 M voxels), from the
-library's own CUDA events: projection -> TSDF init / integrate -> mesh count / scan / emit -> LBVH build -> trace."""
+library's own CUDA events: projection -> TSDF init / integrate -> mesh count / scan / emit -> cast (and, with a
+second argument, LBVH build -> trace beside it)."""
 import ctypes, json, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -35,8 +36,12 @@ for rep in range(3):
   color_im = pr["proj_label"].to(torch.float32) * 65536.0
   dev.integrate(color_im, pr["range_image"], pr["proj_remissions"])
   m = dev.extract_mesh(want_norms=False)
-  bvh = engine.Bvh(m["verts"], m["faces"], m["colors"].to(torch.int32), m["rem"])
-  out = engine.trace(bvh, rays, origin, H, zero_misses=True)
+  if rep == 0:
+    beams = engine.Beams(rays, H)
+  out = engine.cast(beams, m["verts"], m["faces"], m["colors"].to(torch.int32), m["rem"], origin, zero_misses=True, check_mesh=False)
+  if len(sys.argv) > 2:   # the LBVH path beside it
+    bvh = engine.Bvh(m["verts"], m["faces"], m["colors"].to(torch.int32), m["rem"])
+    out2 = engine.trace(bvh, rays, origin, H, zero_misses=True)
   torch.cuda.synchronize()
   if rep:
     res = collect()
