@@ -184,6 +184,15 @@ int vl_tsdf_integrate(float* d_tsdf, float* d_weight, float* d_color, float* d_r
                       float trunc_margin, float obs_weight, float fov_up_deg, float fov_down_deg,
                       const float* d_color_im, const float* d_depth_im, const float* d_rem_im,
                       int im_h, int im_w, vl_stream stream);
+/* Same result bit for bit, ~1/3 faster: the arctangent, the double-precision image coordinate and the pixel
+ * column (fusion_lidar.py:125, 134-141) depend on a voxel's x and y only and are computed once per z column into
+ * d_workspace (vl_tsdf_workspace_bytes(dx, dy) = 4 B per column, scratch for this call). */
+size_t vl_tsdf_workspace_bytes(int dx, int dy);
+int vl_tsdf_integrate_ws(float* d_tsdf, float* d_weight, float* d_color, float* d_rem,
+                         int dx, int dy, int dz, const float vol_origin[3], float voxel_size,
+                         float trunc_margin, float obs_weight, float fov_up_deg, float fov_down_deg,
+                         const float* d_color_im, const float* d_depth_im, const float* d_rem_im,
+                         int im_h, int im_w, void* d_workspace, size_t workspace_bytes, vl_stream stream);
 
 /* ------------------------------------------------------------------------------------
  * (v) iso-surface extraction + per-vertex label / remission lookup ("next" row N1).

@@ -40,10 +40,33 @@ k_tsdf_init(float4* __restrict__ tsdf, float4* __restrict__ weight, float4* __re
   }
 }
 
+// image column of a voxel position (x, y): :125 yaw, :134-141 proj_x -- depends on x and y only
+__device__ __forceinline__ int tsdf_pixel_x(float cam_pt_x, float cam_pt_y, int im_w) {
+  float yaw = -atan2f(cam_pt_y, cam_pt_x);
+  float proj_x = 0.5 * (yaw / VL_PI + 1.0);        // :134
+  proj_x *= im_w;
+  int proj_x_cl = (int)floorf(proj_x);             // :139-141
+  proj_x_cl = min(im_w - 1, proj_x_cl);
+  proj_x_cl = max(0, proj_x_cl);
+  return proj_x_cl;
+}
+
+// The dz voxels of a z column share x and y, hence the arctangent, the double-precision image coordinate and
+// the pixel column: computed once per column here (same expressions, same bits), looked up per voxel below.
+__global__ void __launch_bounds__(kThreads)
+k_tsdf_columns(int* __restrict__ col_px, const TsdfParams P) {
+  const int c = blockIdx.x * kThreads + threadIdx.x;
+  if (c >= P.dx * P.dy) return;
+  const int vx = c / P.dy, vy = c - vx * P.dy;
+  col_px[c] = tsdf_pixel_x(__fmaf_rn((float)vx, P.voxel_size, P.ox), __fmaf_rn((float)vy, P.voxel_size, P.oy), P.im_w);
+}
+
+template <bool kTable>
 __global__ void __launch_bounds__(kThreads)
 k_tsdf_integrate(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, float* __restrict__ color_vol,
                  float* __restrict__ rem_vol, const TsdfParams P, const float* __restrict__ color_im,
-                 const float* __restrict__ depth_im, const float* __restrict__ rem_im, long long n_vox) {
+                 const float* __restrict__ depth_im, const float* __restrict__ rem_im, long long n_vox,
+                 const int* __restrict__ col_px) {
   const long long vi = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (vi >= n_vox) return;
   const int voxel_idx = (int)vi;
@@ -63,17 +86,16 @@ k_tsdf_integrate(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, f
   const float fov_up = P.fov_up, fov_down = P.fov_down;  // :119-120, hoisted (same IEEE double expression on the host)
   float fov = fabsf(fov_up) + fabsf(fov_down);
   float depth = norm3df(cam_pt_x, cam_pt_y, cam_pt_z);
-  float yaw = -atan2f(cam_pt_y, cam_pt_x);
   float pitch = asinf(cam_pt_z / depth);
   if (pitch > fov_up || pitch < fov_down) return;  // :131-132
-  float proj_x = 0.5 * (yaw / VL_PI + 1.0);        // :134-137
-  float proj_y = 1.0 - (pitch + fabsf(fov_down)) / fov;
-  proj_x *= im_w;
+  // :125, :134-141 -- from the column table when the (float-decoded, :96-98) voxel lies inside it
+  const int vxi = (int)voxel_x, vyi = (int)voxel_y;
+  int proj_x_cl;
+  if (kTable && (unsigned)vxi < (unsigned)P.dx && (unsigned)vyi < (unsigned)P.dy) proj_x_cl = __ldg(col_px + vxi * P.dy + vyi);
+  else proj_x_cl = tsdf_pixel_x(cam_pt_x, cam_pt_y, im_w);
+  float proj_y = 1.0 - (pitch + fabsf(fov_down)) / fov;   // :135
   proj_y *= im_h;
-  int proj_x_cl = (int)floorf(proj_x);             // :139-144
-  proj_x_cl = min(im_w - 1, proj_x_cl);
-  proj_x_cl = max(0, proj_x_cl);
-  int proj_y_cl = (int)floorf(proj_y);
+  int proj_y_cl = (int)floorf(proj_y);             // :142-144
   proj_y_cl = min(im_h - 1, proj_y_cl);
   proj_y_cl = max(0, proj_y_cl);
   int pixel_x = proj_x_cl, pixel_y = proj_y_cl;
@@ -127,16 +149,20 @@ extern "C" int vl_tsdf_init(float* d_tsdf, float* d_weight, float* d_color, floa
   return VL_OK;
 }
 
-extern "C" int vl_tsdf_integrate(float* d_tsdf, float* d_weight, float* d_color, float* d_rem, int dx, int dy, int dz,
-                                 const float vol_origin[3], float voxel_size, float trunc_margin, float obs_weight,
-                                 float fov_up_deg, float fov_down_deg, const float* d_color_im, const float* d_depth_im,
-                                 const float* d_rem_im, int im_h, int im_w, vl_stream stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int tsdf_integrate_impl(float* d_tsdf, float* d_weight, float* d_color, float* d_rem, int dx, int dy, int dz,
+                               const float vol_origin[3], float voxel_size, float trunc_margin, float obs_weight,
+                               float fov_up_deg, float fov_down_deg, const float* d_color_im, const float* d_depth_im,
+                               const float* d_rem_im, int im_h, int im_w, void* d_workspace, size_t workspace_bytes,
+                               cudaStream_t stream) {
   const long long n_vox = (long long)dx * dy * dz;
   if (dx <= 0 || dy <= 0 || dz <= 0 || n_vox > 0x7fffffffLL || im_h <= 0 || im_w <= 0 || !vol_origin || !d_tsdf ||
       !d_weight || !d_color || !d_rem || !d_color_im || !d_depth_im || !d_rem_im) {
     vl_set_error("vl_tsdf_integrate: invalid argument (dims %d x %d x %d, image %d x %d)", dx, dy, dz, im_h, im_w);
     return VL_EINVAL;
+  }
+  if (d_workspace && workspace_bytes < sizeof(int) * (size_t)dx * dy) {
+    vl_set_error("vl_tsdf_integrate_ws: workspace too small (%zu < %zu bytes)", workspace_bytes, sizeof(int) * (size_t)dx * dy);
+    return VL_ENOSPACE;
   }
   TsdfParams P;
   P.dx = dx; P.dy = dy; P.dz = dz;
@@ -147,7 +173,40 @@ extern "C" int vl_tsdf_integrate(float* d_tsdf, float* d_weight, float* d_color,
   P.im_h = im_h; P.im_w = im_w;
   const unsigned int nb = (unsigned int)((n_vox + kThreads - 1) / kThreads);
   VlProfScope ps(VL_ST_TSDF_INTEGRATE, stream);
-  k_tsdf_integrate<<<nb, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, d_color_im, d_depth_im, d_rem_im, n_vox);
+  if (d_workspace) {
+    int* col_px = static_cast<int*>(d_workspace);
+    k_tsdf_columns<<<(dx * dy + kThreads - 1) / kThreads, kThreads, 0, stream>>>(col_px, P);
+    VL_LAUNCH_CHECK("k_tsdf_columns");
+    k_tsdf_integrate<true><<<nb, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, d_color_im, d_depth_im, d_rem_im,
+                                                       n_vox, col_px);
+  } else {
+    k_tsdf_integrate<false><<<nb, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, d_color_im, d_depth_im, d_rem_im,
+                                                        n_vox, nullptr);
+  }
   VL_LAUNCH_CHECK("k_tsdf_integrate");
   return VL_OK;
+}
+
+extern "C" int vl_tsdf_integrate(float* d_tsdf, float* d_weight, float* d_color, float* d_rem, int dx, int dy, int dz,
+                                 const float vol_origin[3], float voxel_size, float trunc_margin, float obs_weight,
+                                 float fov_up_deg, float fov_down_deg, const float* d_color_im, const float* d_depth_im,
+                                 const float* d_rem_im, int im_h, int im_w, vl_stream stream_) {
+  return tsdf_integrate_impl(d_tsdf, d_weight, d_color, d_rem, dx, dy, dz, vol_origin, voxel_size, trunc_margin, obs_weight,
+                             fov_up_deg, fov_down_deg, d_color_im, d_depth_im, d_rem_im, im_h, im_w, nullptr, 0,
+                             static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" size_t vl_tsdf_workspace_bytes(int dx, int dy) {
+  return dx > 0 && dy > 0 ? vl_align256(sizeof(int) * (size_t)dx * dy) : 256;
+}
+
+extern "C" int vl_tsdf_integrate_ws(float* d_tsdf, float* d_weight, float* d_color, float* d_rem, int dx, int dy, int dz,
+                                    const float vol_origin[3], float voxel_size, float trunc_margin, float obs_weight,
+                                    float fov_up_deg, float fov_down_deg, const float* d_color_im, const float* d_depth_im,
+                                    const float* d_rem_im, int im_h, int im_w, void* d_workspace, size_t workspace_bytes,
+                                    vl_stream stream_) {
+  if (!d_workspace) { vl_set_error("vl_tsdf_integrate_ws: null workspace"); return VL_EINVAL; }
+  return tsdf_integrate_impl(d_tsdf, d_weight, d_color, d_rem, dx, dy, dz, vol_origin, voxel_size, trunc_margin, obs_weight,
+                             fov_up_deg, fov_down_deg, d_color_im, d_depth_im, d_rem_im, im_h, im_w, d_workspace,
+                             workspace_bytes, static_cast<cudaStream_t>(stream_));
 }

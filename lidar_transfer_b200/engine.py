@@ -260,19 +260,31 @@ class TsdfDevice:
     with torch.cuda.device(self.tsdf.device):
       check(lib().vl_tsdf_init(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color), _ptr(self.rem), n, _stream()))
 
-  def integrate(self, color_im, depth_im, rem_im, obs_weight=1.0):
-    """color_im: folded single-channel image (label * 65536), depth_im, rem_im: f32[H,W]."""
+  def integrate(self, color_im, depth_im, rem_im, obs_weight=1.0, use_column_table=True):
+    """color_im: folded single-channel image (label * 65536), depth_im, rem_im: f32[H,W].
+    use_column_table: vl_tsdf_integrate_ws (per-column pixel table, same bits) instead of vl_tsdf_integrate."""
     dev = self.tsdf.device
     color_im = _dev(color_im, torch.float32, dev)
     depth_im = _dev(depth_im, torch.float32, dev)
     rem_im = _dev(rem_im, torch.float32, dev)
     im_h, im_w = depth_im.shape
     origin = (ctypes.c_float * 3)(*[float(v) for v in self.origin])
+    if use_column_table:
+      ws = getattr(self, "_col_ws", None)
+      if ws is None:
+        ws = self._col_ws = torch.empty(lib().vl_tsdf_workspace_bytes(self.dim[0], self.dim[1]), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-      check(lib().vl_tsdf_integrate(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color), _ptr(self.rem),
-                                    self.dim[0], self.dim[1], self.dim[2], origin, self.voxel_size,
-                                    self.trunc_margin, float(np.float32(obs_weight)), self.fov_up, self.fov_down,
-                                    _ptr(color_im), _ptr(depth_im), _ptr(rem_im), int(im_h), int(im_w), _stream()))
+      if use_column_table:
+        check(lib().vl_tsdf_integrate_ws(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color), _ptr(self.rem),
+                                         self.dim[0], self.dim[1], self.dim[2], origin, self.voxel_size,
+                                         self.trunc_margin, float(np.float32(obs_weight)), self.fov_up, self.fov_down,
+                                         _ptr(color_im), _ptr(depth_im), _ptr(rem_im), int(im_h), int(im_w),
+                                         _ptr(ws), ws.numel(), _stream()))
+      else:
+        check(lib().vl_tsdf_integrate(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color), _ptr(self.rem),
+                                      self.dim[0], self.dim[1], self.dim[2], origin, self.voxel_size,
+                                      self.trunc_margin, float(np.float32(obs_weight)), self.fov_up, self.fov_down,
+                                      _ptr(color_im), _ptr(depth_im), _ptr(rem_im), int(im_h), int(im_w), _stream()))
 
 
   def extract_mesh(self, level=0.0, want_norms=True):

@@ -108,3 +108,29 @@ def test_tsdf_class_switch_and_empty_image(engine, oracle):
   assert differs.sum() <= 1e-4 * n, differs.sum()
   for k in ("tsdf", "rem"):
     assert (np.abs(g[k][~differs] - vol[k][~differs]) > 1e-5).sum() <= 1e-4 * n, k
+
+
+@pytest.mark.parametrize("vox,bnds", [(0.4, [[-16, 16], [-16, 16], [-3, 2]]), (0.08, [[-30, 30], [-21.3, 20], [-3, 2.05]])])
+def test_tsdf_column_table_gives_the_same_bits(engine, oracle, vox, bnds):
+  """vl_tsdf_integrate_ws (arctangent / double-precision image column once per z column) vs vl_tsdf_integrate
+  (per voxel, the reference kernel's order): all four volumes bit for bit, over three integrations including a class
+  switch; the second volume has 25 M voxels (voxel index beyond 2^24, where the float decode of fusion_lidar.py:96-98
+  leaves the table)."""
+  import torch
+  pts, labels = synth.make_scan_points(12, 60000)
+  H, W, fu, fd = 64, 1024, 3.0, -25.0
+  pr = oracle.project(pts[:, :3].astype(np.float64), pts[:, 3], labels, fu, fd, H, W)
+  bnds = np.array(bnds, np.float64)
+  dim = np.ceil((bnds[:, 1] - bnds[:, 0]) / vox).astype(int)
+  origin = bnds[:, 0].astype(np.float32)
+  a = engine.TsdfDevice(dim, origin, vox, fu, fd)
+  b = engine.TsdfDevice(dim, origin, vox, fu, fd)
+  c1 = oracle.label_to_color_im(pr["proj_label"])
+  c2 = oracle.label_to_color_im(np.where(pr["proj_label"] > 0, 99, 0))
+  closer = (pr["range_image"] * np.float32(0.98)).astype(np.float32)
+  for color_im, depth in ((c1, pr["range_image"]), (c2, closer), (c1, pr["range_image"])):
+    a.integrate(color_im, depth, pr["proj_remissions"], use_column_table=True)
+    b.integrate(color_im, depth, pr["proj_remissions"], use_column_table=False)
+  for k in ("tsdf", "weight", "color", "rem"):
+    assert torch.equal(getattr(a, k).view(torch.int32), getattr(b, k).view(torch.int32)), k
+  assert int((a.tsdf != 1).sum()) > 300
