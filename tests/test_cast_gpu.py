@@ -283,3 +283,36 @@ def test_cast_full_size_equals_lbvh(engine, oracle):
     c = _np(engine.cast(beams, sc["verts"], sc["faces"], sc["colors"], sc["rem"], o, workspace=ws))
     _same(c, b, what=sensor + " rerun")
     assert (b["tri_id"] >= 0).mean() > 0.9
+
+
+def test_cast_config4_size_equals_lbvh(engine, oracle):
+  """BASELINE.json configs[3] shape: a ~2 M-triangle mesh cast with the 128 x 2048 OS1-128 pattern -- both device
+  paths return the same bits; every reported range is the Moller-Trumbore t of the reported triangle (host
+  re-evaluation in float32 with the reference's operation order, Triangle.h:27-50)."""
+  sc = synth.make_scene(4000, n_side=1000)
+  assert sc["faces"].shape[0] > 1.9e6
+  H, W, fu, fd = synth.SENSORS["OS1-128"]
+  rays = oracle.create_rays(fu, fd, H, W)
+  o = np.array([0.3, 0.1, 0.05], np.float32)
+  beams = engine.Beams(rays, H)
+  a = _np(engine.cast(beams, sc["verts"], sc["faces"], sc["colors"], sc["rem"], o))
+  bvh = engine.Bvh(sc["verts"], sc["faces"], sc["colors"], sc["rem"])
+  b = _np(engine.trace(bvh, rays, o, H))
+  _same(a, b, what="config 4")
+  hit = a["tri_id"] >= 0
+  assert hit.mean() > 0.9
+  f32 = np.float32
+  fa = sc["faces"][a["tri_id"][hit]]
+  v0, v1, v2 = (sc["verts"][fa[:, k]] for k in range(3))
+  d = rays[hit]
+  D = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(f32) + (d[:, 2] * d[:, 2] + f32(0)).astype(f32)
+  d = (d * (f32(1) / np.sqrt(D, dtype=f32)).astype(f32)[:, None]).astype(f32)
+  e1, e2 = (v1 - v0).astype(f32), (v2 - v0).astype(f32)
+  cross = lambda p, q: np.stack([(p[:, 1] * q[:, 2]).astype(f32) - (p[:, 2] * q[:, 1]).astype(f32),
+                                 (p[:, 2] * q[:, 0]).astype(f32) - (p[:, 0] * q[:, 2]).astype(f32),
+                                 (p[:, 0] * q[:, 1]).astype(f32) - (p[:, 1] * q[:, 0]).astype(f32)], -1).astype(f32)
+  dot = lambda p, q: (((p[:, 0] * q[:, 0]).astype(f32) + (p[:, 1] * q[:, 1]).astype(f32)).astype(f32) + (p[:, 2] * q[:, 2]).astype(f32)).astype(f32)
+  inv_a = (f32(1) / dot(e1, cross(d, e2))).astype(f32)
+  t = (dot(e2, cross((o[None, :] - v0).astype(f32), e1)) * inv_a).astype(f32)
+  assert np.array_equal(t.view(np.int32), a["range"][hit].view(np.int32))
+  assert np.array_equal(a["endcolors"].reshape(-1, 3)[hit], sc["colors"][fa[:, 0]])
