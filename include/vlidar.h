@@ -218,6 +218,27 @@ int vl_mesh_emit(const float* d_tsdf, const float* d_color, const float* d_rem, 
                  vl_stream stream);
 
 /* ------------------------------------------------------------------------------------
+ * (vi) identity re-render metrics on the device ("next" row N3).
+ *
+ * Replaces: compare() auxiliary/laserscan.py:1181-1301 (masks, difference images, label renumbering) and
+ * iouEval.addBatch auxiliary/np_ioueval.py:32-45 (confusion matrix).  All images are flat device arrays of
+ * n_pixels = H*W entries: colours f32[3*n], labels i32[n] (values in [0, 65536)), ranges / remissions f32[n].
+ * Outputs: d_label_diff f32[3*n], d_range_diff f32[n], d_rem_diff f32[n] (the reference's three images) and
+ * d_conf i64[n_classes^2] -- conf[p][t] counts pixels whose renumbered TARGET label (the prediction, rows) is p
+ * and renumbered SOURCE label is t, labels renumbered to their rank in the sorted union of the masked labels
+ * (:1217-1223).  vl_compare_status synchronises and returns info[0] = number of distinct labels, info[1] = bad-label
+ * flag (VL_EINVAL: a label outside [0, 65536) or more distinct labels than classes -- the reference raises
+ * IndexError there) and the sum of the squared range differences (MSE = sum / n_pixels, :1254).
+ * ---------------------------------------------------------------------------------- */
+size_t vl_compare_workspace_bytes(int n_pixels);
+int vl_compare(const float* d_source_color, const float* d_target_color, const int* d_source_label,
+               const int* d_target_label, const float* d_source_range, const float* d_target_range,
+               const float* d_source_rem, const float* d_target_rem, int n_pixels, int n_classes,
+               float* d_label_diff, float* d_range_diff, float* d_rem_diff, long long* d_conf,
+               void* d_workspace, size_t workspace_bytes, vl_stream stream);
+int vl_compare_status(const void* d_workspace, vl_stream stream, int* info, double* range_sq_sum);
+
+/* ------------------------------------------------------------------------------------
  * measurement aids (no reference counterpart): a process-wide count of kernels launched by
  * this library, and optional per-stage device timing with CUDA events recorded on the
  * launching stream.  vl_profile_collect synchronises the device and ACCUMULATES into

@@ -52,6 +52,9 @@ SIGNATURES = {
     "vl_mesh_workspace_bytes": (_sz, [_i, _i, _i]),
     "vl_mesh_count": (_i, [_vp, _i, _i, _i, _f, _vp, _sz, _vp, _vp]),
     "vl_mesh_emit": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _sz, _ll, _ll, _vp] + [_vp] * 5 + [_vp]),
+    "vl_compare_workspace_bytes": (_sz, [_i]),
+    "vl_compare": (_i, [_vp] * 8 + [_i, _i] + [_vp] * 5 + [_sz, _vp]),
+    "vl_compare_status": (_i, [_vp, _vp, _vp, _vp]),
     "vl_launch_count": (_ll, []),
     "vl_profile_enable": (_i, [_i]),
     "vl_profile_stage_count": (_i, []),

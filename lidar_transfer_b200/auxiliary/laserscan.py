@@ -454,9 +454,29 @@ class MultiSemLaserScan():
     label_image.astype("<u4").tofile(os.path.join(out_dir, "labels", str(idx).zfill(6) + ".label"))
 
 
+def compare_device(scan_source, scan_target):
+  """compare() on the device (engine.compare -> vl_compare): same masks, renumbering and confusion matrix; the three
+  difference images come back as float32 numpy arrays, m_iou / m_acc are identical to compare()'s, MSE is accumulated
+  in double (compare() sums float32 pairwise: equal to ~1e-7 relative)."""
+  from .. import engine
+  if scan_target.adaption == 'cp':
+    target_label, target_color = scan_target.merged.proj_label, scan_target.merged.proj_color
+  else:
+    target_color, target_label = scan_target.proj_color, scan_target.label_image
+  r = engine.compare(np.asarray(scan_source.proj_color), np.asarray(target_color), np.asarray(scan_source.proj_label),
+                     np.asarray(target_label), np.asarray(scan_source.proj_range), np.asarray(scan_target.proj_range),
+                     np.asarray(scan_source.proj_remissions), np.asarray(scan_target.proj_remissions), scan_source.nclasses)
+  print("IoU: ", r["m_iou"])
+  print("Acc: ", r["m_acc"])
+  print("MSE: ", r["mse"])
+  return (r["label_diff"].cpu().numpy(), r["range_diff"].cpu().numpy(), r["rem_diff"].cpu().numpy(),
+          r["m_iou"], r["m_acc"], r["mse"])
+
+
 def compare(scan_source, scan_target):
   """ Compare two scans by examine labels, range and remissions (laserscan.py:1181-1301): the identity
-  re-render self-check.  Returns (label_diff, range_diff, remissions_diff, m_iou, m_acc, MSE). """
+  re-render self-check.  Returns (label_diff, range_diff, remissions_diff, m_iou, m_acc, MSE).
+  (Host numpy, operation for operation like the reference; compare_device() is the same on the GPU.) """
   source_color = np.copy(scan_source.proj_color)
   source_label = np.copy(scan_source.proj_label)
   if scan_target.adaption == 'cp':

@@ -25,6 +25,7 @@ SOURCES = {
     "vl_project.cu": ["-fmad=false"],
     "vl_tsdf.cu": ["-fmad=false"],
     "vl_mesh.cu": [],
+    "vl_metrics.cu": [],
 }
 HEADERS = [os.path.join(CSRC, "vl_common.cuh"), os.path.join(HERE, "..", "include", "vlidar.h")]
 

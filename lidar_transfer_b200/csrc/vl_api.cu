@@ -39,7 +39,7 @@ thread_local cudaEvent_t g_prof_open[VL_ST_COUNT];
 const char* kStageNames[VL_ST_COUNT] = {"bounds", "morton", "sort_pass", "emit_climb", "top_climb",
                                         "trace", "project_scatter", "project_gather", "tsdf_init", "tsdf_integrate",
                                         "mesh_count", "mesh_scan", "mesh_compact", "mesh_emit",
-                                        "beams", "cast_init", "cast_setup", "cast_items", "cast_resolve"};
+                                        "beams", "cast_init", "cast_setup", "cast_items", "cast_resolve", "compare"};
 cudaEvent_t prof_event() {
   std::lock_guard<std::mutex> lock(g_prof_mu);
   if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }

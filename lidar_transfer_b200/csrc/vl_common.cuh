@@ -19,7 +19,7 @@ enum VlStage {
   VL_ST_BOUNDS = 0, VL_ST_MORTON, VL_ST_SORT_PASS, VL_ST_EMIT_CLIMB, VL_ST_TOP_CLIMB,
   VL_ST_TRACE, VL_ST_PROJECT_SCATTER, VL_ST_PROJECT_GATHER, VL_ST_TSDF_INIT, VL_ST_TSDF_INTEGRATE,
   VL_ST_MESH_COUNT, VL_ST_MESH_SCAN, VL_ST_MESH_COMPACT, VL_ST_MESH_EMIT,
-  VL_ST_BEAMS, VL_ST_CAST_INIT, VL_ST_CAST_SETUP, VL_ST_CAST_ITEMS, VL_ST_CAST_RESOLVE, VL_ST_COUNT
+  VL_ST_BEAMS, VL_ST_CAST_INIT, VL_ST_CAST_SETUP, VL_ST_CAST_ITEMS, VL_ST_CAST_RESOLVE, VL_ST_COMPARE, VL_ST_COUNT
 };
 void vl_prof_begin(int stage, cudaStream_t stream);
 void vl_prof_end(int stage, cudaStream_t stream);

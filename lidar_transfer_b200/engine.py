@@ -318,6 +318,60 @@ class TsdfDevice:
     return out
 
 
+def compare(source_color, target_color, source_label, target_label, source_range, target_range, source_rem, target_rem,
+            nclasses, workspace=None):
+  """(vi) identity re-render metrics on the device: the masks, difference images, label renumbering and confusion
+  matrix of compare() (auxiliary/laserscan.py:1181-1301) + iouEval.addBatch (auxiliary/np_ioueval.py:32-45); IoU and
+  accuracy (np_ioueval.py:47-70) are evaluated on the nclasses x nclasses matrix on the host.
+
+  Images as numpy arrays or torch tensors (any device): colours [H,W,3], labels [H,W], ranges / remissions [H,W].
+  Returns dict(label_diff f32[H,W,3], range_diff f32[H,W], rem_diff f32[H,W] (CUDA tensors), conf i64[n,n] (numpy),
+  n_present, m_iou, m_acc, mse).  Synchronises once (the confusion matrix)."""
+  require_cuda()
+  sc = _dev(source_color, torch.float32)
+  dev = sc.device
+  shape = tuple(sc.shape[:-1])
+  n = int(np.prod(shape))
+  tc = _dev(target_color, torch.float32, dev)
+  sl, tl = _dev(source_label, torch.int32, dev), _dev(target_label, torch.int32, dev)
+  sr, tr = _dev(source_range, torch.float32, dev), _dev(target_range, torch.float32, dev)
+  sm, tm = _dev(source_rem, torch.float32, dev), _dev(target_rem, torch.float32, dev)
+  for name, t, k in (("target_color", tc, 3 * n), ("source_label", sl, n), ("target_label", tl, n), ("source_range", sr, n),
+                     ("target_range", tr, n), ("source_rem", sm, n), ("target_rem", tm, n)):
+    if t.numel() != k:
+      raise ValueError("%s has %d elements, expected %d" % (name, t.numel(), k))
+  nclasses = int(nclasses)
+  need = lib().vl_compare_workspace_bytes(n)
+  if workspace is None or workspace.numel() < need:
+    workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+  out = dict(label_diff=torch.empty(shape + (3,), dtype=torch.float32, device=dev),
+             range_diff=torch.empty(shape, dtype=torch.float32, device=dev),
+             rem_diff=torch.empty(shape, dtype=torch.float32, device=dev))
+  conf = torch.empty((nclasses, nclasses), dtype=torch.int64, device=dev)
+  with torch.cuda.device(dev):
+    check(lib().vl_compare(_ptr(sc), _ptr(tc), _ptr(sl), _ptr(tl), _ptr(sr), _ptr(tr), _ptr(sm), _ptr(tm), n, nclasses,
+                           _ptr(out["label_diff"]), _ptr(out["range_diff"]), _ptr(out["rem_diff"]), _ptr(conf),
+                           _ptr(workspace), workspace.numel(), _stream()))
+    info = (ctypes.c_int * 8)()
+    sq = ctypes.c_double(0.0)
+    check(lib().vl_compare_status(_ptr(workspace), _stream(), info, ctypes.byref(sq)))
+  conf = conf.cpu().numpy()
+  k = info[0]
+  # np_ioueval.py:12-17, 47-70 with ignore = the class indices that no renumbered label uses (laserscan.py:1225-1230)
+  ignore = np.arange(k, nclasses)
+  include = np.arange(0, k)
+  c = conf.copy()
+  c[ignore] = 0
+  c[:, ignore] = 0
+  tp = np.diag(c)
+  fp, fn = c.sum(axis=1) - tp, c.sum(axis=0) - tp
+  union = tp + fp + fn + 1e-15
+  out.update(conf=conf, n_present=k, m_iou=(tp[include] / union[include]).mean(),
+             m_acc=tp.sum() / (tp[include].sum() + fp[include].sum() + 1e-15), mse=sq.value / max(n, 1),
+             workspace=workspace)
+  return out
+
+
 def ctrace_host(rays, origin, verts, faces, colors, rem, height, outputs=None, want_ids=False, method=None):
   """The reference-compatible HOST-pointer entry point (extern "C" ctrace / vl_ctrace_ids) on numpy
   buffers: H2D, build, trace, D2H inside the call.  outputs: dict of preallocated numpy arrays

@@ -279,3 +279,56 @@ def mesh_extract(tsdf, color_vol, rem_vol, voxel_size, vol_origin, level=0.0):
   if n:
     args(n, _p(verts, _f32p), _p(faces, _i32p), _p(colors, _u8p), _p(rem, _f32p))
   return dict(verts=verts, faces=faces, colors=colors, rem=rem)
+
+
+def compare_numpy(source_color, target_color, source_label, target_label, source_range, target_range,
+                  source_rem, target_rem, nclasses):
+  """Restatement of compare(), auxiliary/laserscan.py:1181-1301, with iouEval of auxiliary/np_ioueval.py:8-70
+  (pinned to the reference's own compare() by tests/golden/golden_compare_v1.npz).  Returns dict(label_diff,
+  range_diff, rem_diff, conf i64[nclasses, nclasses] (rows = renumbered target label), m_iou, m_acc, mse)."""
+  source_color, target_color = np.copy(source_color), np.copy(target_color)
+  source_label, target_label = np.copy(source_label), np.copy(target_label)
+  black = np.sum(source_color, axis=2) == 0                       # :1200
+  source_label[black] = 0
+  target_label[black] = 0
+  target_color[black] = 0
+  bg = source_label == 0                                          # :1206
+  target_label[bg] = 0
+  target_color[bg] = 0
+  label_diff = abs(source_color - target_color)                   # :1211
+  for i, value in enumerate(np.union1d(np.unique(source_label), np.unique(target_label))):   # :1214-1223
+    ms, mt = source_label == value, target_label == value
+    source_label[ms] = i
+    target_label[mt] = i
+  present = np.union1d(np.unique(source_label), np.unique(target_label))
+  empty = np.isin(np.arange(nclasses), present, invert=True)      # :1225-1227
+  ignore = np.arange(nclasses)[empty]
+  include = np.array([n for n in range(nclasses) if n not in ignore], dtype=np.int64)
+  conf = np.zeros((nclasses, nclasses), np.int64)                 # np_ioueval.py:27-45, x = target (pred), y = source
+  np.add.at(conf, (target_label.reshape(-1), source_label.reshape(-1)), 1)
+  m_iou, m_acc = iou_from_confusion(conf, ignore, include)
+  source_range, target_range = np.copy(source_range), np.copy(target_range)
+  source_range[bg] = 0                                            # :1249-1252
+  target_range[bg] = 0
+  range_diff = (source_range - target_range) ** 2
+  mse = range_diff.sum() / range_diff.size                        # :1254
+  source_rem, target_rem = np.copy(source_rem), np.copy(target_rem)
+  source_rem[bg] = 0                                              # :1270-1276
+  target_rem[bg] = 0
+  rem_diff = (source_rem - target_rem) ** 2
+  return dict(label_diff=label_diff, range_diff=range_diff, rem_diff=rem_diff, conf=conf, m_iou=m_iou, m_acc=m_acc,
+              mse=mse, n_present=len(present))
+
+
+def iou_from_confusion(conf, ignore, include):
+  """iouEval.getStats / getIoU / getacc, auxiliary/np_ioueval.py:47-70."""
+  c = conf.copy()
+  c[ignore] = 0
+  c[:, ignore] = 0
+  tp = np.diag(c)
+  fp = c.sum(axis=1) - tp
+  fn = c.sum(axis=0) - tp
+  union = tp + fp + fn + 1e-15
+  m_iou = (tp[include] / union[include]).mean()
+  m_acc = tp.sum() / (tp[include].sum() + fp[include].sum() + 1e-15)
+  return m_iou, m_acc

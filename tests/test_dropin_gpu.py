@@ -194,6 +194,10 @@ def test_deform_cp_and_mergemesh_and_compare(engine, G, tmp_path):
   assert set(np.unique(ms.label_image[hit])) <= set(int(v) % 256 for v in np.unique(G["scan_label"]))
   label_diff, range_diff, rem_diff, m_iou, m_acc, mse = compare(scan, ms)
   assert label_diff.shape == (H, W, 3) and range_diff.shape == (H, W) and np.isfinite(mse) and 0 <= m_iou <= 1 and 0 <= m_acc <= 1
+  from lidar_transfer_b200.auxiliary.laserscan import compare_device   # the same metrics through vl_compare
+  d_label, d_range, d_rem, d_iou, d_acc, d_mse = compare_device(scan, ms)
+  assert d_iou == m_iou and d_acc == m_acc and abs(d_mse - mse) <= 1e-6 * max(1.0, mse)
+  assert np.array_equal(d_range, range_diff.astype(np.float32)) and np.abs(d_label - label_diff).max() <= 1e-6
   ms.write(str(tmp_path), 4)
   out = np.fromfile(tmp_path / "velodyne" / "000004.bin", np.float32).reshape(-1, 4)
   lab = np.fromfile(tmp_path / "labels" / "000004.label", np.uint32)

@@ -124,3 +124,18 @@ def test_oracle_vs_live_reference_build(oracle):
   got = oracle.trace(rays, o, sc["verts"], sc["faces"], sc["colors"], sc["rem"], 32, oracle.NORMALIZE_SSE)
   for k in ("tri_id", "range", "endpoints", "endcolors", "endrem"):
     assert np.array_equal(_bits(got[k]), _bits(ref[k])), k
+
+
+def test_compare_restatement_matches_reference_golden(oracle):
+  """compare() + iouEval (auxiliary/laserscan.py:1181-1301, np_ioueval.py): the oracle's restatement against vectors
+  produced by the reference's own functions (tests/golden/make_golden_compare.py)."""
+  G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_compare_v1.npz"))
+  for tag in "abc":
+    a = {k: G["cmp_%s_%s" % (tag, k)] for k in ("source_color", "target_color", "source_label", "target_label",
+                                                "source_range", "target_range", "source_rem", "target_rem")}
+    r = oracle.compare_numpy(nclasses=int(G["cmp_%s_nclasses" % tag]), **a)
+    for k in ("label_diff", "range_diff", "rem_diff"):
+      assert np.array_equal(r[k], G["cmp_%s_%s" % (tag, k)]), (tag, k)
+    m_iou, m_acc, mse = G["cmp_%s_scalars" % tag]
+    assert r["m_iou"] == m_iou and r["m_acc"] == m_acc and np.float64(r["mse"]) == mse, (tag, r["m_iou"], r["m_acc"], r["mse"])
+    assert r["conf"].sum() == a["source_label"].size
