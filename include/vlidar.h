@@ -255,6 +255,8 @@ void        vl_debug_trace_stats(int* d_stats);
 /* Debug: force the traversal variant: 0 auto, 1 per-ray in storage order, 2 per-ray in 16x8 beam tiles,
  * 4/8/16/32 = warp packets of that tile width. */
 void        vl_debug_trace_mode(int mode);
+/* Debug: force vl_mesh_count's one-cube-per-lane sweep (default: four cubes per lane when dz % 4 == 0). */
+void        vl_debug_mesh_scalar(int on);
 /* Debug: cell rows per beam row of the beam index (default 1); changes vl_beams_bytes. */
 void        vl_debug_cast_cells(int cells_per_beam_row);
 /* Debug: persistent CTAs per SM of the item kernel (default 4). */

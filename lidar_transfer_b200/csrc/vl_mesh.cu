@@ -103,47 +103,168 @@ k_mesh_count(const float* __restrict__ tsdf, const MeshParams P, int units_per_p
   }
 }
 
-// single CTA: exclusive scans of both unit totals; totals[0] = triangles, totals[1] = active cubes
-__global__ void __launch_bounds__(1024)
-k_mesh_scan(const int* __restrict__ unit_tris, const int* __restrict__ unit_active, long long* __restrict__ tri_offset,
-            long long* __restrict__ act_offset, int n_units, long long* __restrict__ totals) {
-  __shared__ long long warp_sums[2][32];
-  __shared__ long long carry_s[2];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid < 2) carry_s[tid] = 0;
-  __syncthreads();
-  for (int base = 0; base < n_units; base += 1024) {
-    const int idx = base + tid;
-    const long long v0 = idx < n_units ? (long long)unit_tris[idx] : 0ll, v1 = idx < n_units ? (long long)unit_active[idx] : 0ll;
-    long long i0 = v0, i1 = v1;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const long long t0 = __shfl_up_sync(0xffffffffu, i0, off), t1 = __shfl_up_sync(0xffffffffu, i1, off);
-      if (lane >= off) { i0 += t0; i1 += t1; }
+// Same sweep with four z-consecutive cubes per lane (dz % 4 == 0, 16-byte aligned volume): four 128-bit loads per
+// lane and step (the four corner rows), the fifth z value of each row from the neighbour lane, four case bytes
+// stored as one word.  Same case bytes and unit totals as k_mesh_count, a third of the instructions.
+__global__ void __launch_bounds__(kThreads)
+k_mesh_count4(const float* __restrict__ tsdf, const MeshParams P, int units_per_plane, int* __restrict__ unit_tris,
+              int* __restrict__ unit_active, unsigned char* __restrict__ cases) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int u = blockIdx.x * kWarps + wid;
+  if (u >= units_per_plane) return;  // warp-uniform
+  const int x = blockIdx.y, yz = P.dy * P.dz;
+  const float* plane0 = tsdf + (size_t)x * yz;
+  unsigned char* cases0 = cases + (size_t)x * yz;
+  const bool x1 = x + 1 < P.dx;
+  const float L = P.level;
+  int j = u * kUnit + 4 * lane;
+  int y = j / P.dz, z = j - y * P.dz;
+  auto fetch = [&](int jj, int yy, float4* v) {
+    v[0] = v[1] = v[2] = v[3] = make_float4(1.f, 1.f, 1.f, 1.f);   // 1.0 (= empty space) outside the volume
+    if (jj < yz) {
+      const bool y1 = yy + 1 < P.dy;
+      v[0] = __ldg(reinterpret_cast<const float4*>(plane0 + jj));
+      if (x1) v[1] = __ldg(reinterpret_cast<const float4*>(plane0 + yz + jj));
+      if (y1) v[2] = __ldg(reinterpret_cast<const float4*>(plane0 + jj + P.dz));
+      if (x1 && y1) v[3] = __ldg(reinterpret_cast<const float4*>(plane0 + yz + jj + P.dz));
     }
-    if (lane == 31) { warp_sums[0][wid] = i0; warp_sums[1][wid] = i1; }
-    __syncthreads();
-    if (wid < 2) {
-      const long long ws = warp_sums[wid][lane];
-      long long wi = ws;
+  };
+  float4 cur[4], nxt[4];
+  fetch(j, y, cur);
+  int n_tris = 0, n_active = 0;
+  for (int step = 0; step < kUnit / 128; ++step) {
+    int jn = j + 128, yn = y, zn = z + 128;
+    while (zn >= P.dz) { zn -= P.dz; ++yn; }
+    fetch(jn, yn, nxt);
+    unsigned int lo[5] = {0u, 0u, 0u, 0u, 0u};   // lo[k]: bit c set when row c is below the level at z + k
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const long long t = __shfl_up_sync(0xffffffffu, wi, off);
-        if (lane >= off) wi += t;
-      }
-      warp_sums[wid][lane] = wi - ws;
+    for (int c = 0; c < 4; ++c) {
+      const float up = __shfl_down_sync(0xffffffffu, cur[c].x, 1);   // z + 4 = first value of the next lane
+      const float wrap = __shfl_sync(0xffffffffu, nxt[c].x, 0);      // lane 31: lane 0 of the next step
+      const float w = lane == 31 ? wrap : up;
+      lo[0] |= cur[c].x < L ? (1u << c) : 0u;
+      lo[1] |= cur[c].y < L ? (1u << c) : 0u;
+      lo[2] |= cur[c].z < L ? (1u << c) : 0u;
+      lo[3] |= cur[c].w < L ? (1u << c) : 0u;
+      lo[4] |= w < L ? (1u << c) : 0u;
     }
-    __syncthreads();
-    const long long e0 = carry_s[0] + warp_sums[0][wid] + (i0 - v0), e1 = carry_s[1] + warp_sums[1][wid] + (i1 - v1);
-    if (idx < n_units) { tri_offset[idx] = e0; act_offset[idx] = e1; }
-    __syncthreads();
-    if (tid == 1023) { carry_s[0] = e0 + v0; carry_s[1] = e1 + v1; }
-    __syncthreads();
+    const bool row_ok = j < yz && x1 && (y + 1 < P.dy);
+    unsigned int packed = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unsigned int m = lo[k] | (lo[k + 1] << 4);
+      if (!(row_ok && (z + k + 1 < P.dz))) m = 0u;
+      packed |= m << (8 * k);
+      const int cnt = c_tri_count[m];
+      n_tris += cnt;
+      n_active += cnt > 0 ? 1 : 0;
+    }
+    if (j < yz) *reinterpret_cast<unsigned int*>(cases0 + j) = packed;
+    j = jn; y = yn; z = zn;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cur[c] = nxt[c];
+    if (u * kUnit + (step + 1) * 128 >= yz) break;  // warp-uniform: the plane ends inside this unit
   }
-  if (tid == 0) { totals[0] = carry_s[0]; totals[1] = carry_s[1]; }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    n_tris += __shfl_xor_sync(0xffffffffu, n_tris, off);
+    n_active += __shfl_xor_sync(0xffffffffu, n_active, off);
+  }
+  if (lane == 0) {
+    unit_tris[x * units_per_plane + u] = n_tris;
+    unit_active[x * units_per_plane + u] = n_active;
+  }
 }
 
-// active cubes in cube order: list[i] = (voxel index, first triangle slot)
+// exclusive scans of both unit totals in three steps: every CTA scans 8192 units locally (8 consecutive units per
+// thread) and leaves its totals, one CTA scans the block totals, every unit adds its block's offset;
+// totals[0] = triangles, totals[1] = active cubes
+constexpr int kScanPer = 8;
+constexpr int kScanBlockUnits = 1024 * kScanPer;
+
+__device__ __forceinline__ void block_excl2_1024(long long v0, long long v1, long long (*warp_sums)[32], long long* e0,
+                                                 long long* e1, long long* t0, long long* t1) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  long long i0 = v0, i1 = v1;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const long long a = __shfl_up_sync(0xffffffffu, i0, off), b = __shfl_up_sync(0xffffffffu, i1, off);
+    if (lane >= off) { i0 += a; i1 += b; }
+  }
+  if (lane == 31) { warp_sums[0][wid] = i0; warp_sums[1][wid] = i1; }
+  __syncthreads();
+  if (wid < 2) {
+    const long long ws = warp_sums[wid][lane];
+    long long wi = ws;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const long long tt = __shfl_up_sync(0xffffffffu, wi, off);
+      if (lane >= off) wi += tt;
+    }
+    warp_sums[wid][lane] = wi - ws;
+    if (lane == 31) warp_sums[wid + 2][0] = wi;   // grand total of this component
+  }
+  __syncthreads();
+  *e0 = warp_sums[0][wid] + (i0 - v0);
+  *e1 = warp_sums[1][wid] + (i1 - v1);
+  *t0 = warp_sums[2][0];
+  *t1 = warp_sums[3][0];
+}
+
+__global__ void __launch_bounds__(1024)
+k_mesh_scan_local(const int* __restrict__ unit_tris, const int* __restrict__ unit_active, long long* __restrict__ tri_offset,
+                  long long* __restrict__ act_offset, int n_units, long long* __restrict__ blk_tri,
+                  long long* __restrict__ blk_act) {
+  __shared__ long long warp_sums[4][32];
+  const int first = blockIdx.x * kScanBlockUnits + threadIdx.x * kScanPer;
+  int t[kScanPer], a[kScanPer];
+  long long v0 = 0, v1 = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k) {
+    const int idx = first + k;
+    t[k] = idx < n_units ? unit_tris[idx] : 0;
+    a[k] = idx < n_units ? unit_active[idx] : 0;
+    v0 += t[k]; v1 += a[k];
+  }
+  long long e0, e1, t0, t1;
+  block_excl2_1024(v0, v1, warp_sums, &e0, &e1, &t0, &t1);
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k) {
+    const int idx = first + k;
+    if (idx < n_units) { tri_offset[idx] = e0; act_offset[idx] = e1; }
+    e0 += t[k]; e1 += a[k];
+  }
+  if (threadIdx.x == 0) { blk_tri[blockIdx.x] = t0; blk_act[blockIdx.x] = t1; }
+}
+
+__global__ void __launch_bounds__(1024)
+k_mesh_scan_top(long long* __restrict__ blk_tri, long long* __restrict__ blk_act, int n_blocks, long long* __restrict__ totals) {
+  __shared__ long long warp_sums[4][32];
+  long long carry0 = 0, carry1 = 0;
+  for (int base = 0; base < n_blocks; base += 1024) {   // one round up to 8.4 M units
+    const int idx = base + threadIdx.x;
+    const long long v0 = idx < n_blocks ? blk_tri[idx] : 0ll, v1 = idx < n_blocks ? blk_act[idx] : 0ll;
+    long long e0, e1, t0, t1;
+    block_excl2_1024(v0, v1, warp_sums, &e0, &e1, &t0, &t1);
+    if (idx < n_blocks) { blk_tri[idx] = carry0 + e0; blk_act[idx] = carry1 + e1; }
+    carry0 += t0; carry1 += t1;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { totals[0] = carry0; totals[1] = carry1; }
+}
+
+__global__ void __launch_bounds__(1024)
+k_mesh_scan_apply(long long* __restrict__ tri_offset, long long* __restrict__ act_offset, int n_units,
+                  const long long* __restrict__ blk_tri, const long long* __restrict__ blk_act) {
+  const int idx = blockIdx.x * 1024 + threadIdx.x;
+  if (idx >= n_units) return;
+  tri_offset[idx] += blk_tri[idx / kScanBlockUnits];
+  act_offset[idx] += blk_act[idx / kScanBlockUnits];
+}
+
+// active cubes in cube order: list[i] = (voxel index, first triangle slot).  kVec: four case bytes per lane and
+// step (yz % 4 == 0), otherwise one.
+template <int kVec>
 __global__ void __launch_bounds__(kThreads)
 k_mesh_compact(const MeshParams P, int units_per_plane, const unsigned char* __restrict__ cases,
                const int* __restrict__ unit_tris, const long long* __restrict__ tri_offset,
@@ -156,26 +277,33 @@ k_mesh_compact(const MeshParams P, int units_per_plane, const unsigned char* __r
   if (unit_tris[unit] == 0) return;  // nothing active in this unit
   const unsigned char* cases0 = cases + (size_t)x * yz;
   long long tri_run = tri_offset[unit], act_run = act_offset[unit];
-  const unsigned int lt_mask = (1u << lane) - 1u;
-  for (int step = 0; step < kUnit / 32; ++step) {
-    const int j = u * kUnit + step * 32 + lane;
-    if (u * kUnit + step * 32 >= yz) break;
-    const int m = j < yz ? cases0[j] : 0;
-    const int cnt = c_tri_count[m];
-    const unsigned int bal = __ballot_sync(0xffffffffu, cnt > 0);
-    if (bal == 0u) continue;
-    int incl = cnt;
+  for (int step = 0; step < kUnit / (32 * kVec); ++step) {
+    const int j0 = u * kUnit + step * 32 * kVec;
+    if (j0 >= yz) break;
+    const int j = j0 + lane * kVec;
+    unsigned int word = 0u;
+    if (j < yz) word = kVec == 4 ? __ldg(reinterpret_cast<const unsigned int*>(cases0 + j)) : (unsigned int)cases0[j];
+    if (__ballot_sync(0xffffffffu, word != 0u) == 0u) continue;   // case 0 (and 255) have no triangles; 255 is rare
+    int cnt[kVec], tris = 0, act = 0;
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) { cnt[k] = c_tri_count[(word >> (8 * k)) & 255u]; tris += cnt[k]; act += cnt[k] > 0 ? 1 : 0; }
+    int it = tris, ia = act;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += t;
+      const int a = __shfl_up_sync(0xffffffffu, it, off), b = __shfl_up_sync(0xffffffffu, ia, off);
+      if (lane >= off) { it += a; ia += b; }
     }
-    if (cnt > 0) {
-      const long long slot = act_run + __popc(bal & lt_mask);
-      if (slot < n_active) list[slot] = make_uint2((unsigned int)(x * yz + j), (unsigned int)(tri_run + incl - cnt));
+    long long slot = act_run + (ia - act), tri = tri_run + (it - tris);
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) {
+      if (cnt[k] > 0) {
+        if (slot < n_active) list[slot] = make_uint2((unsigned int)(x * yz + j + k), (unsigned int)tri);
+        ++slot;
+        tri += cnt[k];
+      }
     }
-    tri_run += __shfl_sync(0xffffffffu, incl, 31);
-    act_run += __popc(bal);
+    tri_run += __shfl_sync(0xffffffffu, it, 31);
+    act_run += __shfl_sync(0xffffffffu, ia, 31);
   }
 }
 
@@ -255,10 +383,14 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
 
 }  // namespace
 
+static int g_mesh_scalar = 0;   // vl_debug_mesh_scalar(): force the one-cube-per-lane sweep (tests compare the two)
+extern "C" void vl_debug_mesh_scalar(int on) { g_mesh_scalar = on ? 1 : 0; }
+
 static int mesh_units_per_plane(int dy, int dz) { return (int)(((long long)dy * dz + kUnit - 1) / kUnit); }
 
-// workspace: [unit triangle counts i32][unit active counts i32][triangle offsets i64][active offsets i64][case byte per voxel]
-struct MeshWs { size_t tris, active, tri_off, act_off, cases, total; };
+// workspace: [unit triangle counts i32][unit active counts i32][triangle offsets i64][active offsets i64]
+//            [scan-block offsets 2 x i64][case byte per voxel]
+struct MeshWs { size_t tris, active, tri_off, act_off, blk_tri, blk_act, cases, total; int n_scan_blocks; };
 static MeshWs mesh_ws_layout(int dx, int dy, int dz) {
   const size_t n_units = (size_t)dx * mesh_units_per_plane(dy, dz);
   MeshWs w;
@@ -267,6 +399,9 @@ static MeshWs mesh_ws_layout(int dx, int dy, int dz) {
   w.active = off;  off = vl_align256(off + n_units * 4);
   w.tri_off = off; off = vl_align256(off + n_units * 8);
   w.act_off = off; off = vl_align256(off + n_units * 8);
+  w.n_scan_blocks = (int)((n_units + kScanBlockUnits - 1) / kScanBlockUnits);
+  w.blk_tri = off; off = vl_align256(off + (size_t)w.n_scan_blocks * 8);
+  w.blk_act = off; off = vl_align256(off + (size_t)w.n_scan_blocks * 8);
   w.cases = off;   off = vl_align256(off + (size_t)dx * dy * dz);
   w.total = off;
   return w;
@@ -304,15 +439,30 @@ extern "C" int vl_mesh_count(const float* d_tsdf, int dx, int dy, int dz, float 
   const MeshWs w = mesh_ws_layout(dx, dy, dz);
   char* ws = static_cast<char*>(d_workspace);
   { VlProfScope ps(VL_ST_MESH_COUNT, stream);
-  k_mesh_count<<<dim3((upp + kWarps - 1) / kWarps, dx), kThreads, 0, stream>>>(
-      d_tsdf, P, upp, reinterpret_cast<int*>(ws + w.tris), reinterpret_cast<int*>(ws + w.active),
-      reinterpret_cast<unsigned char*>(ws + w.cases)); }
+  const bool vec4 = !g_mesh_scalar && dz % 4 == 0 && ((uintptr_t)d_tsdf & 15) == 0;   // cases start 256-byte aligned
+  if (vec4)
+    k_mesh_count4<<<dim3((upp + kWarps - 1) / kWarps, dx), kThreads, 0, stream>>>(
+        d_tsdf, P, upp, reinterpret_cast<int*>(ws + w.tris), reinterpret_cast<int*>(ws + w.active),
+        reinterpret_cast<unsigned char*>(ws + w.cases));
+  else
+    k_mesh_count<<<dim3((upp + kWarps - 1) / kWarps, dx), kThreads, 0, stream>>>(
+        d_tsdf, P, upp, reinterpret_cast<int*>(ws + w.tris), reinterpret_cast<int*>(ws + w.active),
+        reinterpret_cast<unsigned char*>(ws + w.cases)); }
   VL_LAUNCH_CHECK("k_mesh_count");
   { VlProfScope ps(VL_ST_MESH_SCAN, stream);
-  k_mesh_scan<<<1, 1024, 0, stream>>>(reinterpret_cast<const int*>(ws + w.tris), reinterpret_cast<const int*>(ws + w.active),
-                                      reinterpret_cast<long long*>(ws + w.tri_off), reinterpret_cast<long long*>(ws + w.act_off),
-                                      upp * dx, d_totals); }
-  VL_LAUNCH_CHECK("k_mesh_scan");
+  const int n_units = upp * dx;
+  long long* tri_off = reinterpret_cast<long long*>(ws + w.tri_off);
+  long long* act_off = reinterpret_cast<long long*>(ws + w.act_off);
+  long long* blk_tri = reinterpret_cast<long long*>(ws + w.blk_tri);
+  long long* blk_act = reinterpret_cast<long long*>(ws + w.blk_act);
+  k_mesh_scan_local<<<w.n_scan_blocks, 1024, 0, stream>>>(reinterpret_cast<const int*>(ws + w.tris),
+                                                         reinterpret_cast<const int*>(ws + w.active), tri_off, act_off,
+                                                         n_units, blk_tri, blk_act);
+  VL_LAUNCH_CHECK("k_mesh_scan_local");
+  k_mesh_scan_top<<<1, 1024, 0, stream>>>(blk_tri, blk_act, w.n_scan_blocks, d_totals);
+  VL_LAUNCH_CHECK("k_mesh_scan_top");
+  k_mesh_scan_apply<<<(n_units + 1023) / 1024, 1024, 0, stream>>>(tri_off, act_off, n_units, blk_tri, blk_act); }
+  VL_LAUNCH_CHECK("k_mesh_scan_apply");
   return VL_OK;
 }
 
@@ -337,9 +487,12 @@ extern "C" int vl_mesh_emit(const float* d_tsdf, const float* d_color, const flo
   const unsigned char* cases = reinterpret_cast<const unsigned char*>(ws + w.cases);
   uint2* list = static_cast<uint2*>(d_active_list);
   { VlProfScope ps(VL_ST_MESH_COMPACT, stream);
-  k_mesh_compact<<<dim3((upp + kWarps - 1) / kWarps, dx), kThreads, 0, stream>>>(
-      P, upp, cases, reinterpret_cast<const int*>(ws + w.tris), reinterpret_cast<const long long*>(ws + w.tri_off),
-      reinterpret_cast<const long long*>(ws + w.act_off), n_active, list); }
+  const dim3 grid((upp + kWarps - 1) / kWarps, dx);
+  const int* ut = reinterpret_cast<const int*>(ws + w.tris);
+  const long long* to = reinterpret_cast<const long long*>(ws + w.tri_off);
+  const long long* ao = reinterpret_cast<const long long*>(ws + w.act_off);
+  if (!g_mesh_scalar && ((long long)dy * dz) % 4 == 0) k_mesh_compact<4><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list);
+  else k_mesh_compact<1><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list); }
   VL_LAUNCH_CHECK("k_mesh_compact");
   VlProfScope ps(VL_ST_MESH_EMIT, stream);
   k_mesh_emit<<<(unsigned)((n_active + kThreads - 1) / kThreads), kThreads, 0, stream>>>(

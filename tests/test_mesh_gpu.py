@@ -10,7 +10,9 @@ def _load(dev_vol, name, arr):
   getattr(dev_vol, name).copy_(torch.from_numpy(arr))
 
 
-@pytest.mark.parametrize("shape,seed", [((32, 30, 33), 0), ((70, 9, 130), 1), ((5, 4, 3), 2), ((2, 2, 2), 3)])
+@pytest.mark.parametrize("shape,seed", [((32, 30, 33), 0), ((70, 9, 130), 1), ((5, 4, 3), 2), ((2, 2, 2), 3),
+                                        # dz % 4 == 0: the four-cubes-per-lane sweep (k_mesh_count4)
+                                        ((32, 30, 32), 4), ((70, 9, 128), 5), ((5, 4, 4), 6), ((3, 41, 100), 7), ((2, 2, 8), 8)])
 def test_mesh_extract_bit_exact(engine, oracle, shape, seed):
   rng = np.random.default_rng(seed)
   g = np.stack(np.meshgrid(*[np.arange(n, dtype=np.float64) for n in shape], indexing="ij"), -1)
@@ -40,3 +42,24 @@ def test_empty_volume_gives_empty_mesh(engine):
   dev = engine.TsdfDevice((16, 16, 8), np.zeros(3, np.float32), 0.5, 3.0, -25.0)  # tsdf == 1 everywhere
   m = dev.extract_mesh()
   assert m["faces"].shape == (0, 3) and m["verts"].shape == (0, 3)
+
+
+def test_vectorised_sweep_equals_scalar_sweep(engine, vl):
+  """k_mesh_count4 vs k_mesh_count on a volume with several 2048-cube units per plane and ragged plane ends."""
+  rng = np.random.default_rng(11)
+  shape = (40, 123, 100)
+  g = np.stack(np.meshgrid(*[np.arange(n, dtype=np.float32) for n in shape], indexing="ij"), -1)
+  vol = np.clip((np.linalg.norm(g - np.array(shape, np.float32) / 2, axis=-1) - 17.0) / 4.0 + rng.normal(0, 0.2, shape), -1, 1).astype(np.float32)
+  out = []
+  for scalar in (0, 1):
+    vl.vl_debug_mesh_scalar(scalar)
+    try:
+      dev = engine.TsdfDevice(shape, np.zeros(3, np.float32), 0.1, 3.0, -25.0)
+      _load(dev, "tsdf", vol)
+      out.append(dev.extract_mesh(want_norms=False))
+    finally:
+      vl.vl_debug_mesh_scalar(0)
+  a, b = out
+  assert a["faces"].shape[0] == b["faces"].shape[0] > 10000
+  for k in ("verts", "faces", "colors", "rem"):
+    assert torch.equal(a[k], b[k]), k
