@@ -528,8 +528,10 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
       }
       __syncthreads();   // s_warp / s_at are reused by the next pass
     }
-    if (threadIdx.x == 0) s_nq = 0;
-    __syncthreads();
+    if (nq > 0) {   // (with nq == 0 there was no barrier since the read above, and nothing to reset)
+      if (threadIdx.x == 0) s_nq = 0;
+      __syncthreads();
+    }
   }
   if (n_bad) atomicAdd(&chdr->n_bad_faces, n_bad);
 }
