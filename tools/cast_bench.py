@@ -15,6 +15,7 @@ sensor = sys.argv[3] if len(sys.argv) > 3 else "HDL-64E"
 if len(sys.argv) > 4:
   L.vl_debug_cast_ctas(int(sys.argv[4]))
 methods = sys.argv[5].split(",") if len(sys.argv) > 5 else ("cast", "lbvh")
+STREAMS = [int(v) for v in sys.argv[6].split(",")] if len(sys.argv) > 6 else (1, 8)
 H, W, fu, fd = synth.SENSORS[sensor]
 rays = create_rays(fu, fd, H, W)
 origin = np.zeros(3, np.float32)
@@ -33,7 +34,7 @@ def collect():
 
 res = dict(n_tris=n_t, n_rays=H * W, sensor=sensor)
 for method in methods:
-  for n_streams in (1, 8):
+  for n_streams in STREAMS:
     R = pipeline.ScanRenderer(rays, origin, H, max_v, max_f, n_streams=n_streams, method=method)
     for rep in range(3):
       for s in scenes: R.submit(*s)
