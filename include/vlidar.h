@@ -193,6 +193,14 @@ int vl_tsdf_integrate_ws(float* d_tsdf, float* d_weight, float* d_color, float* 
                          float trunc_margin, float obs_weight, float fov_up_deg, float fov_down_deg,
                          const float* d_color_im, const float* d_depth_im, const float* d_rem_im,
                          int im_h, int im_w, void* d_workspace, size_t workspace_bytes, vl_stream stream);
+/* vl_tsdf_init followed by vl_tsdf_integrate_ws in ONE pass over the volume (the first integration into a new
+ * TSDFVolume, which is every integration of the default `mergemesh` adaption, laserscan.py:968-975): the previous
+ * content of the four volumes is neither read nor assumed, every voxel is written.  Same bits as the two calls. */
+int vl_tsdf_init_integrate(float* d_tsdf, float* d_weight, float* d_color, float* d_rem,
+                           int dx, int dy, int dz, const float vol_origin[3], float voxel_size,
+                           float trunc_margin, float obs_weight, float fov_up_deg, float fov_down_deg,
+                           const float* d_color_im, const float* d_depth_im, const float* d_rem_im,
+                           int im_h, int im_w, void* d_workspace, size_t workspace_bytes, vl_stream stream);
 
 /* ------------------------------------------------------------------------------------
  * (v) iso-surface extraction + per-vertex label / remission lookup ("next" row N1).

@@ -61,7 +61,10 @@ k_tsdf_columns(int* __restrict__ col_px, const TsdfParams P) {
   col_px[c] = tsdf_pixel_x(__fmaf_rn((float)vx, P.voxel_size, P.ox), __fmaf_rn((float)vy, P.voxel_size, P.oy), P.im_w);
 }
 
-template <bool kTable>
+// kTable: pixel column from the per-column table.  kFresh: the volumes are known to hold their initial state
+// (tsdf 1, weight / colour / remission 0, fusion_lidar.py:48-63) -- nothing is read, every voxel is written (its
+// updated value, or the initial one): vl_tsdf_init + vl_tsdf_integrate in one pass over the volume.
+template <bool kTable, bool kFresh>
 __global__ void __launch_bounds__(kThreads)
 k_tsdf_integrate(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, float* __restrict__ color_vol,
                  float* __restrict__ rem_vol, const TsdfParams P, const float* __restrict__ color_im,
@@ -70,60 +73,69 @@ k_tsdf_integrate(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, f
   const long long vi = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (vi >= n_vox) return;
   const int voxel_idx = (int)vi;
-  const int vol_dim_y = P.dy, vol_dim_z = P.dz;
-  // :96-98 (float division: can decode (x+1, -1, z) once voxel_idx exceeds 2^24)
-  float voxel_x = floorf(((float)voxel_idx) / ((float)(vol_dim_y * vol_dim_z)));
-  float voxel_y = floorf(((float)(voxel_idx - ((int)voxel_x) * vol_dim_y * vol_dim_z)) / ((float)vol_dim_z));
-  float voxel_z = (float)(voxel_idx - ((int)voxel_x) * vol_dim_y * vol_dim_z - ((int)voxel_y) * vol_dim_z);
-  // :101-104
-  float voxel_size = P.voxel_size;
-  float pt_x = __fmaf_rn(voxel_x, voxel_size, P.ox);
-  float pt_y = __fmaf_rn(voxel_y, voxel_size, P.oy);
-  float pt_z = __fmaf_rn(voxel_z, voxel_size, P.oz);
-  float cam_pt_x = pt_x, cam_pt_z = pt_z, cam_pt_y = pt_y;
-  // :119-128
-  int im_h = P.im_h, im_w = P.im_w;
-  const float fov_up = P.fov_up, fov_down = P.fov_down;  // :119-120, hoisted (same IEEE double expression on the host)
-  float fov = fabsf(fov_up) + fabsf(fov_down);
-  float depth = norm3df(cam_pt_x, cam_pt_y, cam_pt_z);
-  float pitch = asinf(cam_pt_z / depth);
-  if (pitch > fov_up || pitch < fov_down) return;  // :131-132
-  // :125, :134-141 -- from the column table when the (float-decoded, :96-98) voxel lies inside it
-  const int vxi = (int)voxel_x, vyi = (int)voxel_y;
-  int proj_x_cl;
-  if (kTable && (unsigned)vxi < (unsigned)P.dx && (unsigned)vyi < (unsigned)P.dy) proj_x_cl = __ldg(col_px + vxi * P.dy + vyi);
-  else proj_x_cl = tsdf_pixel_x(cam_pt_x, cam_pt_y, im_w);
-  float proj_y = 1.0 - (pitch + fabsf(fov_down)) / fov;   // :135
-  proj_y *= im_h;
-  int proj_y_cl = (int)floorf(proj_y);             // :142-144
-  proj_y_cl = min(im_h - 1, proj_y_cl);
-  proj_y_cl = max(0, proj_y_cl);
-  int pixel_x = proj_x_cl, pixel_y = proj_y_cl;
-  float depth_value = __ldg(depth_im + pixel_y * im_w + pixel_x);  // :154-156
-  if (depth_value == 0) return;
-  // :190-227 class-aware integration
-  float trunc_margin = P.trunc_margin;
-  float depth_diff = depth_value - depth;
-  if (depth_diff < -trunc_margin) return;
-  float dist = fminf(1.0f, depth_diff / trunc_margin);
-  float dist_old = weight_vol[voxel_idx];  // sic (:197)
-  float old_color = color_vol[voxel_idx];
-  float new_color = __ldg(color_im + pixel_y * im_w + pixel_x);
-  if (old_color == new_color) {
-    float w_old = dist_old;
-    float w_new = w_old + P.obs_weight;
-    weight_vol[voxel_idx] = w_new;
-    tsdf_vol[voxel_idx] = __fmaf_rn(tsdf_vol[voxel_idx], w_old, dist) / w_new;
-    float old_rem = rem_vol[voxel_idx];
-    float new_rem = __ldg(rem_im + pixel_y * im_w + pixel_x);
-    rem_vol[voxel_idx] = __fmaf_rn(old_rem, w_old, new_rem) / w_new;
-  } else if (dist < dist_old) {
-    tsdf_vol[voxel_idx] = dist;
-    float new_b = floorf(new_color / (256 * 256));
-    float new_g = floorf((new_color - new_b * 256 * 256) / 256);
-    float new_r = new_color - new_b * 256 * 256 - new_g * 256;
-    color_vol[voxel_idx] = new_b * 256 * 256 + new_g * 256 + new_r;
-    rem_vol[voxel_idx] = __ldg(rem_im + pixel_y * im_w + pixel_x);
+  float out_tsdf = 1.f, out_weight = 0.f, out_color = 0.f, out_rem = 0.f;   // kFresh: what is stored at the end
+  do {
+    const int vol_dim_y = P.dy, vol_dim_z = P.dz;
+    // :96-98 (float division: can decode (x+1, -1, z) once voxel_idx exceeds 2^24)
+    float voxel_x = floorf(((float)voxel_idx) / ((float)(vol_dim_y * vol_dim_z)));
+    float voxel_y = floorf(((float)(voxel_idx - ((int)voxel_x) * vol_dim_y * vol_dim_z)) / ((float)vol_dim_z));
+    float voxel_z = (float)(voxel_idx - ((int)voxel_x) * vol_dim_y * vol_dim_z - ((int)voxel_y) * vol_dim_z);
+    // :101-104
+    float voxel_size = P.voxel_size;
+    float pt_x = __fmaf_rn(voxel_x, voxel_size, P.ox);
+    float pt_y = __fmaf_rn(voxel_y, voxel_size, P.oy);
+    float pt_z = __fmaf_rn(voxel_z, voxel_size, P.oz);
+    float cam_pt_x = pt_x, cam_pt_z = pt_z, cam_pt_y = pt_y;
+    // :119-128
+    int im_h = P.im_h, im_w = P.im_w;
+    const float fov_up = P.fov_up, fov_down = P.fov_down;  // :119-120, hoisted (same IEEE double expression on the host)
+    float fov = fabsf(fov_up) + fabsf(fov_down);
+    float depth = norm3df(cam_pt_x, cam_pt_y, cam_pt_z);
+    float pitch = asinf(cam_pt_z / depth);
+    if (pitch > fov_up || pitch < fov_down) break;  // :131-132
+    // :125, :134-141 -- from the column table when the (float-decoded, :96-98) voxel lies inside it
+    const int vxi = (int)voxel_x, vyi = (int)voxel_y;
+    int proj_x_cl;
+    if (kTable && (unsigned)vxi < (unsigned)P.dx && (unsigned)vyi < (unsigned)P.dy) proj_x_cl = __ldg(col_px + vxi * P.dy + vyi);
+    else proj_x_cl = tsdf_pixel_x(cam_pt_x, cam_pt_y, im_w);
+    float proj_y = 1.0 - (pitch + fabsf(fov_down)) / fov;   // :135
+    proj_y *= im_h;
+    int proj_y_cl = (int)floorf(proj_y);             // :142-144
+    proj_y_cl = min(im_h - 1, proj_y_cl);
+    proj_y_cl = max(0, proj_y_cl);
+    int pixel_x = proj_x_cl, pixel_y = proj_y_cl;
+    float depth_value = __ldg(depth_im + pixel_y * im_w + pixel_x);  // :154-156
+    if (depth_value == 0) break;
+    // :190-227 class-aware integration
+    float trunc_margin = P.trunc_margin;
+    float depth_diff = depth_value - depth;
+    if (depth_diff < -trunc_margin) break;
+    float dist = fminf(1.0f, depth_diff / trunc_margin);
+    float dist_old = kFresh ? 0.f : weight_vol[voxel_idx];  // sic (:197)
+    float old_color = kFresh ? 0.f : color_vol[voxel_idx];
+    float new_color = __ldg(color_im + pixel_y * im_w + pixel_x);
+    if (old_color == new_color) {
+      float w_old = dist_old;
+      float w_new = w_old + P.obs_weight;
+      out_weight = w_new;
+      out_tsdf = __fmaf_rn(kFresh ? 1.f : tsdf_vol[voxel_idx], w_old, dist) / w_new;
+      float old_rem = kFresh ? 0.f : rem_vol[voxel_idx];
+      float new_rem = __ldg(rem_im + pixel_y * im_w + pixel_x);
+      out_rem = __fmaf_rn(old_rem, w_old, new_rem) / w_new;
+      if (!kFresh) { weight_vol[voxel_idx] = out_weight; tsdf_vol[voxel_idx] = out_tsdf; rem_vol[voxel_idx] = out_rem; }
+      else out_color = old_color;
+    } else if (dist < dist_old) {
+      out_tsdf = dist;
+      float new_b = floorf(new_color / (256 * 256));
+      float new_g = floorf((new_color - new_b * 256 * 256) / 256);
+      float new_r = new_color - new_b * 256 * 256 - new_g * 256;
+      out_color = new_b * 256 * 256 + new_g * 256 + new_r;
+      out_rem = __ldg(rem_im + pixel_y * im_w + pixel_x);
+      if (!kFresh) { tsdf_vol[voxel_idx] = out_tsdf; color_vol[voxel_idx] = out_color; rem_vol[voxel_idx] = out_rem; }
+    }
+  } while (false);
+  if (kFresh) {
+    tsdf_vol[voxel_idx] = out_tsdf; weight_vol[voxel_idx] = out_weight; color_vol[voxel_idx] = out_color; rem_vol[voxel_idx] = out_rem;
   }
 }
 
@@ -153,7 +165,7 @@ static int tsdf_integrate_impl(float* d_tsdf, float* d_weight, float* d_color, f
                                const float vol_origin[3], float voxel_size, float trunc_margin, float obs_weight,
                                float fov_up_deg, float fov_down_deg, const float* d_color_im, const float* d_depth_im,
                                const float* d_rem_im, int im_h, int im_w, void* d_workspace, size_t workspace_bytes,
-                               cudaStream_t stream) {
+                               bool fresh, cudaStream_t stream) {
   const long long n_vox = (long long)dx * dy * dz;
   if (dx <= 0 || dy <= 0 || dz <= 0 || n_vox > 0x7fffffffLL || im_h <= 0 || im_w <= 0 || !vol_origin || !d_tsdf ||
       !d_weight || !d_color || !d_rem || !d_color_im || !d_depth_im || !d_rem_im) {
@@ -177,11 +189,15 @@ static int tsdf_integrate_impl(float* d_tsdf, float* d_weight, float* d_color, f
     int* col_px = static_cast<int*>(d_workspace);
     k_tsdf_columns<<<(dx * dy + kThreads - 1) / kThreads, kThreads, 0, stream>>>(col_px, P);
     VL_LAUNCH_CHECK("k_tsdf_columns");
-    k_tsdf_integrate<true><<<nb, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, d_color_im, d_depth_im, d_rem_im,
-                                                       n_vox, col_px);
+    if (fresh)
+      k_tsdf_integrate<true, true><<<nb, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, d_color_im, d_depth_im,
+                                                               d_rem_im, n_vox, col_px);
+    else
+      k_tsdf_integrate<true, false><<<nb, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, d_color_im, d_depth_im,
+                                                                d_rem_im, n_vox, col_px);
   } else {
-    k_tsdf_integrate<false><<<nb, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, d_color_im, d_depth_im, d_rem_im,
-                                                        n_vox, nullptr);
+    k_tsdf_integrate<false, false><<<nb, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, d_color_im, d_depth_im,
+                                                               d_rem_im, n_vox, nullptr);
   }
   VL_LAUNCH_CHECK("k_tsdf_integrate");
   return VL_OK;
@@ -192,7 +208,7 @@ extern "C" int vl_tsdf_integrate(float* d_tsdf, float* d_weight, float* d_color,
                                  float fov_up_deg, float fov_down_deg, const float* d_color_im, const float* d_depth_im,
                                  const float* d_rem_im, int im_h, int im_w, vl_stream stream_) {
   return tsdf_integrate_impl(d_tsdf, d_weight, d_color, d_rem, dx, dy, dz, vol_origin, voxel_size, trunc_margin, obs_weight,
-                             fov_up_deg, fov_down_deg, d_color_im, d_depth_im, d_rem_im, im_h, im_w, nullptr, 0,
+                             fov_up_deg, fov_down_deg, d_color_im, d_depth_im, d_rem_im, im_h, im_w, nullptr, 0, false,
                              static_cast<cudaStream_t>(stream_));
 }
 
@@ -208,5 +224,16 @@ extern "C" int vl_tsdf_integrate_ws(float* d_tsdf, float* d_weight, float* d_col
   if (!d_workspace) { vl_set_error("vl_tsdf_integrate_ws: null workspace"); return VL_EINVAL; }
   return tsdf_integrate_impl(d_tsdf, d_weight, d_color, d_rem, dx, dy, dz, vol_origin, voxel_size, trunc_margin, obs_weight,
                              fov_up_deg, fov_down_deg, d_color_im, d_depth_im, d_rem_im, im_h, im_w, d_workspace,
-                             workspace_bytes, static_cast<cudaStream_t>(stream_));
+                             workspace_bytes, false, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int vl_tsdf_init_integrate(float* d_tsdf, float* d_weight, float* d_color, float* d_rem, int dx, int dy, int dz,
+                                      const float vol_origin[3], float voxel_size, float trunc_margin, float obs_weight,
+                                      float fov_up_deg, float fov_down_deg, const float* d_color_im, const float* d_depth_im,
+                                      const float* d_rem_im, int im_h, int im_w, void* d_workspace, size_t workspace_bytes,
+                                      vl_stream stream_) {
+  if (!d_workspace) { vl_set_error("vl_tsdf_init_integrate: null workspace"); return VL_EINVAL; }
+  return tsdf_integrate_impl(d_tsdf, d_weight, d_color, d_rem, dx, dy, dz, vol_origin, voxel_size, trunc_margin, obs_weight,
+                             fov_up_deg, fov_down_deg, d_color_im, d_depth_im, d_rem_im, im_h, im_w, d_workspace,
+                             workspace_bytes, true, static_cast<cudaStream_t>(stream_));
 }

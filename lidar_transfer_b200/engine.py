@@ -249,21 +249,36 @@ class TsdfDevice:
     n = self.dim[0] * self.dim[1] * self.dim[2]
     if n >= 2 ** 31:
       raise ValueError("volume of %d voxels exceeds the reference kernel's int voxel index" % n)
-    self.tsdf = torch.empty(self.dim, dtype=torch.float32, device=dev)
-    self.weight = torch.empty(self.dim, dtype=torch.float32, device=dev)
-    self.color = torch.empty(self.dim, dtype=torch.float32, device=dev)
-    self.rem = torch.empty(self.dim, dtype=torch.float32, device=dev)
+    self._vols = tuple(torch.empty(self.dim, dtype=torch.float32, device=dev) for _ in range(4))
     self.reset()
 
   def reset(self):
-    n = self.dim[0] * self.dim[1] * self.dim[2]
-    with torch.cuda.device(self.tsdf.device):
-      check(lib().vl_tsdf_init(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color), _ptr(self.rem), n, _stream()))
+    """Back to the initial state (tsdf 1, weight / colour / remission 0, fusion_lidar.py:48-63).  Lazy: the first
+    integrate() writes the initial values of the voxels it does not update in the same pass
+    (vl_tsdf_init_integrate); anything else that looks at the volumes first materialises them (vl_tsdf_init)."""
+    self._fresh = True
+
+  def _materialise(self):
+    if self._fresh:
+      self._fresh = False
+      t, w, c, r = self._vols
+      with torch.cuda.device(t.device):
+        check(lib().vl_tsdf_init(_ptr(t), _ptr(w), _ptr(c), _ptr(r), t.numel(), _stream()))
+
+  tsdf = property(lambda self: (self._materialise(), self._vols[0])[1])
+  weight = property(lambda self: (self._materialise(), self._vols[1])[1])
+  color = property(lambda self: (self._materialise(), self._vols[2])[1])
+  rem = property(lambda self: (self._materialise(), self._vols[3])[1])
 
   def integrate(self, color_im, depth_im, rem_im, obs_weight=1.0, use_column_table=True):
     """color_im: folded single-channel image (label * 65536), depth_im, rem_im: f32[H,W].
     use_column_table: vl_tsdf_integrate_ws (per-column pixel table, same bits) instead of vl_tsdf_integrate."""
-    dev = self.tsdf.device
+    dev = self._vols[0].device
+    fused = self._fresh and use_column_table   # first integration into a fresh volume: one pass
+    if fused:
+      self._fresh = False
+    else:
+      self._materialise()
     color_im = _dev(color_im, torch.float32, dev)
     depth_im = _dev(depth_im, torch.float32, dev)
     rem_im = _dev(rem_im, torch.float32, dev)
@@ -275,11 +290,11 @@ class TsdfDevice:
         ws = self._col_ws = torch.empty(lib().vl_tsdf_workspace_bytes(self.dim[0], self.dim[1]), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
       if use_column_table:
-        check(lib().vl_tsdf_integrate_ws(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color), _ptr(self.rem),
-                                         self.dim[0], self.dim[1], self.dim[2], origin, self.voxel_size,
-                                         self.trunc_margin, float(np.float32(obs_weight)), self.fov_up, self.fov_down,
-                                         _ptr(color_im), _ptr(depth_im), _ptr(rem_im), int(im_h), int(im_w),
-                                         _ptr(ws), ws.numel(), _stream()))
+        fn = lib().vl_tsdf_init_integrate if fused else lib().vl_tsdf_integrate_ws
+        check(fn(_ptr(self._vols[0]), _ptr(self._vols[1]), _ptr(self._vols[2]), _ptr(self._vols[3]),
+                 self.dim[0], self.dim[1], self.dim[2], origin, self.voxel_size,
+                 self.trunc_margin, float(np.float32(obs_weight)), self.fov_up, self.fov_down,
+                 _ptr(color_im), _ptr(depth_im), _ptr(rem_im), int(im_h), int(im_w), _ptr(ws), ws.numel(), _stream()))
       else:
         check(lib().vl_tsdf_integrate(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color), _ptr(self.rem),
                                       self.dim[0], self.dim[1], self.dim[2], origin, self.voxel_size,
