@@ -53,10 +53,28 @@ def _ncu_traffic(kernel):
 
 
 def _peaks():
+  """HBM roofline denominator: the driver-measured copy bandwidth in MEASURED_PEAKS.json (whatever the key is called,
+  as long as it mentions hbm), else the profiling guide's fallback."""
   p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-  if os.path.exists(p):
-    return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-  return 6650.0, "fallback (B200_PROFILING.md)"
+  try:
+    d = json.load(open(p))
+  except (OSError, ValueError):
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+  def walk(o, path=""):
+    if isinstance(o, dict):
+      for k, v in o.items():
+        yield from walk(v, path + "/" + str(k))
+    elif isinstance(o, (int, float)) and not isinstance(o, bool):
+      yield path.lower(), float(o)
+  cands = [(k, v) for k, v in walk(d) if "hbm" in k and v > 0]
+  pref = [kv for kv in cands if any(t in kv[0] for t in ("gbs", "gb_s", "gbps", "gb/s", "bw", "bandwidth", "copy"))] or cands
+  if not pref:
+    return 6650.0, "fallback (B200_PROFILING.md; no hbm entry in MEASURED_PEAKS.json)"
+  k, v = pref[0]
+  if v < 100.0:   # TB/s
+    v *= 1000.0
+  return v, "measured (MEASURED_PEAKS.json%s)" % k
 
 
 class ClockSampler:
