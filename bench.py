@@ -204,6 +204,10 @@ def run_native(args):
     raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
+  numa = "off"
+  if world > 1 and os.environ.get("VL_NUMA_BIND", "1") != "0":   # before any pinned allocation (first touch)
+    from lidar_transfer_b200 import sharding
+    numa = sharding.bind_to_gpu_numa_node(local_rank)
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 
@@ -395,6 +399,7 @@ def run_native(args):
       "stages": stages_out,
       "other_method": {"method": other, "value": other_value, "unit": "Mrays/s", "ms_per_step": ms_other / max(1, min(K, 5))},
       "cpu_baseline": cpu,
+      "numa": numa,
       "clocks": clocks,
       "hit_fraction": hit_frac,
   }
