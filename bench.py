@@ -189,6 +189,56 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# the whole chain at BASELINE.json config-1 size, reported beside the headline (not part of `value`)
+# ------------------------------------------------------------------------------------------------
+def pipeline_c1(L, dev):
+  """points -> range image -> 284 M-voxel TSDF (voxel 0.05 m) -> iso-surface -> cast, one synthetic 124 668-point
+  scan, per-stage device times from the library's CUDA events (second of two passes)."""
+  import ctypes
+  import torch
+  from lidar_transfer_b200 import engine, synth
+  from lidar_transfer_b200.rays import create_rays
+  pts, labels = synth.make_scan_points(1, 124668)
+  p64 = torch.from_numpy(pts[:, :3].astype(np.float64)).to(dev)
+  rem = torch.from_numpy(pts[:, 3].copy()).to(dev)
+  lab = torch.from_numpy(labels.view(np.int32)).to(dev)
+  vox = 0.05
+  bnds = np.array([[-50, 50], [-35.5, 35.5], [-3, 2]], np.float64)
+  dim = np.ceil((bnds[:, 1] - bnds[:, 0]) / vox).astype(int)
+  rays = torch.from_numpy(create_rays(FOV_UP, FOV_DOWN, H, W)).to(dev)
+  origin = torch.zeros(3, device=dev)
+  beams = engine.Beams(rays, H)
+  vol = engine.TsdfDevice(dim, bnds[:, 0].astype(np.float32), vox, FOV_UP, FOV_DOWN)
+  ws = None
+  wall = None
+  for rep in range(2):
+    torch.cuda.synchronize()
+    L.vl_profile_enable(rep)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pr = engine.project(p64, rem, lab, FOV_UP, FOV_DOWN, H, W, workspace=ws)
+    ws = pr["workspace"]
+    vol.reset()
+    vol.integrate(pr["proj_label"].to(torch.float32) * 65536.0, pr["range_image"], pr["proj_remissions"])
+    m = vol.extract_mesh(want_norms=False)
+    out = engine.cast(beams, m["verts"], m["faces"], m["colors"].to(torch.int32), m["rem"], origin, zero_misses=True,
+                      check_mesh=False)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = e0.elapsed_time(e1)
+  L.vl_profile_enable(0)
+  n_st = L.vl_profile_stage_count()
+  ms_arr, cnt_arr = (ctypes.c_double * n_st)(), (ctypes.c_longlong * n_st)()
+  L.vl_profile_collect(ms_arr, cnt_arr)
+  stages = {L.vl_profile_stage_name(i).decode(): round(1e3 * ms_arr[i] / cnt_arr[i], 1) for i in range(n_st) if cnt_arr[i]}
+  return {"workload": "c1-shape: 124668 points -> 64x2048 image -> %d x %d x %d voxels -> mesh -> 64x2048 cast" % tuple(dim),
+          "n_voxels": int(np.prod(dim)), "n_tris": int(m["faces"].shape[0]),
+          "hit_fraction": float((out["range"] > 0).float().mean()),
+          "stage_us": stages, "kernel_ms_per_scan": round(sum(stages.values()) / 1e3, 3),
+          "ms_per_scan_incl_host": round(wall, 3)}
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_native(args):
@@ -364,6 +414,12 @@ def run_native(args):
   stages_out = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share": v[0] / total_stage_ms,
                     "alg_GBps": alg_bytes.get(k, 0.0) / (v[0] / v[1] * 1e-3) / 1e9} for k, v in stage.items()}
 
+  pipe = None
+  if world == 1 and not args.no_pipeline:
+    del rr2
+    torch.cuda.empty_cache()
+    pipe = pipeline_c1(L, dev)
+
   # cpu baseline: the reference C++ ray tracer on a bounded sample of the same scans
   cpu = None
   if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
@@ -398,6 +454,7 @@ def run_native(args):
                    "tris_that_can_be_hit": n_active, "work_units": n_units},
       "stages": stages_out,
       "other_method": {"method": other, "value": other_value, "unit": "Mrays/s", "ms_per_step": ms_other / max(1, min(K, 5))},
+      "pipeline_c1": pipe,
       "cpu_baseline": cpu,
       "numa": numa,
       "clocks": clocks,
@@ -420,6 +477,7 @@ def main():
   ap.add_argument("--method", default="cast", choices=["cast", "lbvh"])
   ap.add_argument("--cpu-scans", type=int, default=8, help="scans timed for cpu_baseline (about 1.2 s each)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-pipeline", action="store_true", help="skip the config-1 chain measurement (pipeline_c1)")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
   if args.impl == "reference":
