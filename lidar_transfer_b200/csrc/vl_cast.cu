@@ -388,6 +388,42 @@ __device__ __forceinline__ int tri_setup(int f, int i0, int i1, int i2, const fl
   return T.ncy * ((T.ncx + (1 << sh) - 1) >> sh);
 }
 
+// The cull of k_cast_setup: the sine interval of tri_setup with cheaper, looser bounds (every replacement only widens
+// the interval): chord between unit vectors <= |pa - pb| / min(|pa|, |pb|) instead of normalising the vertices,
+// |v| <= |o| + |p| for the rounding term, one MUFU per inverse length.  Returns false only for a triangle that no
+// beam can hit; anything unusual (non-finite, at the origin, out of float range, around the z axis) survives and
+// is decided by tri_setup<true>.
+__device__ __forceinline__ float rsqrt_mufu(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ bool tri_cull(int i0, int i1, int i2, const float* __restrict__ verts, const float3 o,
+                                         float o_max, const BeamParams& P, const unsigned int* __restrict__ fine_mask) {
+  const float p0x = __ldg(verts + 3 * (size_t)i0) - o.x, p0y = __ldg(verts + 3 * (size_t)i0 + 1) - o.y, p0z = __ldg(verts + 3 * (size_t)i0 + 2) - o.z;
+  const float p1x = __ldg(verts + 3 * (size_t)i1) - o.x, p1y = __ldg(verts + 3 * (size_t)i1 + 1) - o.y, p1z = __ldg(verts + 3 * (size_t)i1 + 2) - o.z;
+  const float p2x = __ldg(verts + 3 * (size_t)i2) - o.x, p2y = __ldg(verts + 3 * (size_t)i2 + 1) - o.y, p2z = __ldg(verts + 3 * (size_t)i2 + 2) - o.z;
+  const float q0 = p0x * p0x + p0y * p0y + p0z * p0z, q1 = p1x * p1x + p1y * p1y + p1z * p1z, q2 = p2x * p2x + p2y * p2y + p2z * p2z;
+  const float qmin = fminf(q0, fminf(q1, q2)), qmax = fmaxf(q0, fmaxf(q1, q2));
+  if (!((q0 + q1) + q2 < 1e30f) || !(qmin > 1e-30f)) return true;   // NaN / inf / huge / at the origin: not decided here
+  const float r0 = rsqrt_mufu(q0), r1 = rsqrt_mufu(q1), r2 = rsqrt_mufu(q2);
+  const float rmax = fmaxf(r0, fmaxf(r1, r2)), rmin = fminf(r0, fminf(r1, r2));
+  const float s0 = p0z * r0, s1 = p1z * r1, s2 = p2z * r2;
+  const float d01 = (p0x - p1x) * (p0x - p1x) + (p0y - p1y) * (p0y - p1y) + (p0z - p1z) * (p0z - p1z);
+  const float d12 = (p1x - p2x) * (p1x - p2x) + (p1y - p2y) * (p1y - p2y) + (p1z - p2z) * (p1z - p2z);
+  const float d20 = (p2x - p0x) * (p2x - p0x) + (p2y - p0y) * (p2y - p0y) + (p2z - p0z) * (p2z - p0z);
+  const float bulge = 0.31f * fmaxf(d01, fmaxf(d12, d20)) * rmax * rmax;
+  const float E = 2.4e-7f * (o_max + qmax * rmin);   // every |coordinate| <= |o|_inf + |p|_2
+  const float pad_s = kPad0 + 2.f * E * rmax;
+  const float slo = fminf(s0, fminf(s1, s2)) - bulge - pad_s, shi = fmaxf(s0, fmaxf(s1, s2)) + bulge + pad_s;
+  if (shi < P.lo || slo > P.hi) return false;
+  const float e2 = 2.f * E;
+  const bool near_axis = fminf(p0x, fminf(p1x, p2x)) <= e2 && fmaxf(p0x, fmaxf(p1x, p2x)) >= -e2 &&
+                         fminf(p0y, fminf(p1y, p2y)) <= e2 && fmaxf(p0y, fmaxf(p1y, p2y)) >= -e2;
+  return near_axis || fine_any(fine_mask, fine_of(slo, P), fine_of(shi, P));
+}
+
 __device__ __forceinline__ unsigned long long init_key() {
   return ((unsigned long long)__float_as_uint(999999999.f) << 32) | 0x7fffffffull;   // BVH.cpp:20
 }
@@ -418,12 +454,12 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
   __shared__ int s_queue[kBatch];
   __shared__ int s_nq;
   __shared__ unsigned long long s_warp[kCastWarps];
-  __shared__ unsigned long long s_at[kCastThreads + 1];   // per thread of a pass: packed (record position, first unit)
   if (threadIdx.x < kFineWords) s_mask[threadIdx.x] = __ldg(fine_mask_g + threadIdx.x);
   if (threadIdx.x == 0) s_nq = 0;
   __syncthreads();
   const BeamParams P = beam_params(bhdr, cw, ch);
   const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
+  const float o_max = fmaxf(fabsf(o.x), fmaxf(fabsf(o.y), fabsf(o.z)));
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n_batches = (n_faces + kBatch - 1) / kBatch;
   const unsigned long long units_mask = (1ull << kUnitBits) - 1ull;
@@ -446,8 +482,7 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
         if ((unsigned)idx[k][0] >= (unsigned)n_verts || (unsigned)idx[k][1] >= (unsigned)n_verts || (unsigned)idx[k][2] >= (unsigned)n_verts) {
           ++n_bad;
         } else {
-          TriRec dummy;
-          keep = tri_setup<false>(f, idx[k][0], idx[k][1], idx[k][2], verts, o, P, s_mask, dummy) != 0;
+          keep = tri_cull(idx[k][0], idx[k][1], idx[k][2], verts, o, o_max, P, s_mask);
         }
       }
       const unsigned int m = __ballot_sync(0xffffffffu, keep);
@@ -499,34 +534,23 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
         if (lane < kCastWarps) s_warp[lane] = base + xi - x;
       }
       __syncthreads();
-      const unsigned long long at = s_warp[w] + incl - mine;
-      s_at[threadIdx.x] = at;
-      if (threadIdx.x == kCastThreads - 1) s_at[kCastThreads] = at + mine;
       if (n_i > 0) {
+        const unsigned long long at = s_warp[w] + incl - mine;
         const int pos = (int)(at >> kUnitBits);
-        if (pos < n_faces && (at & units_mask) + (unsigned long long)n_u <= unit_cap) {   // always, unless the unit list overflowed
+        const unsigned long long u0 = at & units_mask;
+        if (pos < n_faces && u0 + (unsigned long long)n_u <= unit_cap) {   // always, unless the unit list overflowed
           float4* r = recs + 4 * (size_t)pos;
           r[0] = make_float4(T.v0x, T.v0y, T.v0z, T.e1x);
           r[1] = make_float4(T.e1y, T.e1z, T.e2x, T.e2y);
           r[2] = make_float4(T.e2z, __int_as_float(T.orig), T.ymid, T.yhalf);
           r[3] = make_float4(T.slo, T.shi, __int_as_float(T.ca | (T.ncx << 16) | (T.ncx > kWideCols ? (1 << 30) : 0)),
                              __int_as_float(T.ra | (T.ncy << 16)));
+          // the owner writes its own units (2 on average; the issue slots of a cooperative, coalesced writer cost more
+          // than these scattered 8-byte stores when several scans share the SMs)
+          for (int k = 0; k < n_u; ++k) units[u0 + k] = make_int2(pos, k * kUnitItems);
         }
       }
-      __syncthreads();
-      // the pass's units, written with consecutive threads on consecutive entries: thread t finds the owner of unit
-      // u_first + t by bisection over the 256 first-unit numbers (a thread without units shares its successor's)
-      {
-        const unsigned long long u_first = s_at[0] & units_mask, u_end = s_at[kCastThreads] & units_mask;
-        for (unsigned long long u = u_first + threadIdx.x; u < u_end && u < unit_cap; u += kCastThreads) {
-          int j = 0;
-#pragma unroll
-          for (int step = kCastThreads / 2; step > 0; step >>= 1)
-            if ((s_at[j + step] & units_mask) <= u) j += step;
-          units[u] = make_int2((int)(s_at[j] >> kUnitBits), (int)(u - (s_at[j] & units_mask)) * kUnitItems);
-        }
-      }
-      __syncthreads();   // s_warp / s_at are reused by the next pass
+      __syncthreads();   // s_warp is reused by the next pass
     }
     if (nq > 0) {   // (with nq == 0 there was no barrier since the read above, and nothing to reset)
       if (threadIdx.x == 0) s_nq = 0;
