@@ -269,6 +269,8 @@ void        vl_debug_mesh_scalar(int on);
 void        vl_debug_cast_cells(int cells_per_beam_row);
 /* Debug: persistent CTAs per SM of the item kernel (default 4). */
 void        vl_debug_cast_ctas(int ctas_per_sm);
+/* Debug: persistent CTAs per SM of the setup kernel (default 4). */
+void        vl_debug_cast_setup_ctas(int ctas_per_sm);
 /* Debug (timing only, leaves the blob unusable): 0 full build, 1 / 2 / 3 = stop after bounds / morton / sort. */
 void        vl_debug_build_stop(int stage);
 

@@ -43,6 +43,7 @@ SIGNATURES = {
     "vl_debug_mesh_scalar": (None, [_i]),
     "vl_debug_cast_cells": (None, [_i]),
     "vl_debug_cast_ctas": (None, [_i]),
+    "vl_debug_cast_setup_ctas": (None, [_i]),
     "vl_trace_bruteforce": (_i, [_vp] * 4 + [_i, _i, _vp, _vp, _i, _i] + [_vp] * 6),
     "vl_project_workspace_bytes": (_sz, [_l, _i, _i]),
     "vl_project": (_i, [_vp, _vp, _vp, _l, _d, _d, _i, _i, _i] + [_vp] * 7 + [_sz, _vp]),

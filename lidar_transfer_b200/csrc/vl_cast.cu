@@ -20,6 +20,11 @@
 // rounding of v - o), so a beam the triangle test would accept is always among the candidates.
 #include "vl_common.cuh"
 
+#ifndef VL_SETUP_MINB
+#define VL_SETUP_MINB 4
+#endif
+#define VL_SETUP_MINB_DEFAULT VL_SETUP_MINB
+
 namespace {
 
 constexpr int kCastThreads = 256;
@@ -56,7 +61,8 @@ struct BeamLayout {
 };
 
 int g_cells_per_row = 1;   // cell rows per beam row (vl_debug_cast_cells)
-int g_items_ctas_per_sm = 8;
+int g_items_ctas_per_sm = 4;
+int g_setup_ctas_per_sm = VL_SETUP_MINB_DEFAULT;
 
 BeamLayout beam_layout(int n_rays, int height) {
   BeamLayout L;
@@ -688,6 +694,7 @@ k_cast_resolve(const unsigned long long* __restrict__ best, int n, const float4*
 
 extern "C" void vl_debug_cast_cells(int cells_per_beam_row) { g_cells_per_row = cells_per_beam_row < 1 ? 1 : cells_per_beam_row; }
 extern "C" void vl_debug_cast_ctas(int ctas_per_sm) { g_items_ctas_per_sm = ctas_per_sm < 1 ? 1 : ctas_per_sm; }
+extern "C" void vl_debug_cast_setup_ctas(int ctas_per_sm) { g_setup_ctas_per_sm = ctas_per_sm < 1 ? 1 : ctas_per_sm; }
 
 size_t vl_beams_bytes_impl(int n_rays, int height) { return beam_layout(n_rays, height).total; }
 
@@ -774,7 +781,7 @@ int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces
     {
       VlProfScope ps(VL_ST_CAST_SETUP, stream);
       const int n_batches = (n_faces + kBatch - 1) / kBatch;
-      const int nb = n_batches < 148 * VL_SETUP_MINB ? n_batches : 148 * VL_SETUP_MINB;
+      const int nb = n_batches < 148 * g_setup_ctas_per_sm ? n_batches : 148 * g_setup_ctas_per_sm;
       k_cast_setup<<<nb, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, d_verts, d_faces, n_verts, n_faces,
                                                    d_origin, chdr, recs, units, C.unit_cap);
       VL_LAUNCH_CHECK("k_cast_setup");

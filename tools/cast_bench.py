@@ -16,6 +16,8 @@ if len(sys.argv) > 4:
   L.vl_debug_cast_ctas(int(sys.argv[4]))
 methods = sys.argv[5].split(",") if len(sys.argv) > 5 else ("cast", "lbvh")
 STREAMS = [int(v) for v in sys.argv[6].split(",")] if len(sys.argv) > 6 else (1, 8)
+if len(sys.argv) > 7:
+  L.vl_debug_cast_setup_ctas(int(sys.argv[7]))
 H, W, fu, fd = synth.SENSORS[sensor]
 rays = create_rays(fu, fd, H, W)
 origin = np.zeros(3, np.float32)
