@@ -169,6 +169,13 @@ int vl_project(const double* d_points, const float* d_remissions, const uint32_t
                uint8_t* d_keep, int* d_n_kept, void* d_workspace, size_t workspace_bytes,
                vl_stream stream);
 
+/* Reverse projection of the `cp` adaption: replaces LaserScan.do_reverse_projection_new
+ * auxiliary/laserscan.py:475-501.  d_depth_im f32[H*W], d_proj_x / d_proj_y f64[H*W] (image coordinates of each
+ * pixel's point in [0, W] / [0, H], float or clamped) -> d_back_points f64[3*H*W], float64 arithmetic like numpy's
+ * (sin / cos of the CUDA library: <= 2 ulp from the host's libm). */
+int vl_reverse_project(const float* d_depth_im, const double* d_proj_x, const double* d_proj_y, int H, int W,
+                       double fov_up_deg, double fov_down_deg, double* d_back_points, vl_stream stream);
+
 /* ------------------------------------------------------------------------------------
  * (iv) class-aware TSDF voxel integration.
  *

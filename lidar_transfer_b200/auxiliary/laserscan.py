@@ -183,16 +183,24 @@ class LaserScan:
       self.proj_y_float = (1.0 - (np.arcsin(w[..., 2] / depth) + abs(fd)) / (abs(fd) + abs(fu))) * self.proj_H
     self.proj_x, self.proj_y = self._clamp(self.proj_x_float, self.proj_y_float)
 
-  def do_reverse_projection_new(self, fov_up, fov_down, preserve_float=False):
-    """Pixel + depth -> xyz (laserscan.py:475-501), the `cp` adaption's back projection."""
+  def do_reverse_projection_new(self, fov_up, fov_down, preserve_float=False, host=False):
+    """Pixel + depth -> xyz (laserscan.py:475-501), the `cp` adaption's back projection, on the device
+    (vl_reverse_project; raises without CUDA -- nothing is selected automatically).  host=True evaluates the
+    reference's float64 numpy expressions instead: the comparison copy the CPU-only tests hold against the
+    reference's goldens, like do_range_projection() above."""
+    if preserve_float:
+      px, py = self.proj_x_float, self.proj_y_float
+    else:
+      px, py = self.proj_x, self.proj_y
+    if not host:
+      self.back_points = engine.reverse_project(self.range_image, np.asarray(px, np.float64), np.asarray(py, np.float64),
+                                                fov_up, fov_down).cpu().numpy()
+      return
     fov_up = fov_up / 180.0 * np.pi
     fov_down = fov_down / 180.0 * np.pi
     fov = abs(fov_down) + abs(fov_up)
     depth = self.range_image
-    if preserve_float:
-      proj_x, proj_y = self.proj_x_float / self.proj_W, self.proj_y_float / self.proj_H
-    else:
-      proj_x, proj_y = self.proj_x / self.proj_W, self.proj_y / self.proj_H
+    proj_x, proj_y = px / self.proj_W, py / self.proj_H
     yaw = (proj_x * 2 - 1.0) * np.pi
     pitch = np.pi / 2 - (1.0 * fov - proj_y * fov - abs(fov_down))
     self.back_points = np.array([depth * np.sin(pitch) * np.cos(-yaw), depth * np.sin(pitch) * np.sin(-yaw),

@@ -127,7 +127,40 @@ k_project_gather(const unsigned long long* __restrict__ keys, const unsigned int
   rem[p] = remissions[i];
 }
 
+// Reverse projection of the `cp` adaption (laserscan.py:475-501): pixel coordinates + depth -> xyz, float64 like the
+// reference's numpy (proj_x / proj_y are the per-pixel image coordinates of the winning point, float or clamped).
+__global__ void __launch_bounds__(kThreads)
+k_reverse_project(const float* __restrict__ depth_im, const double* __restrict__ proj_x, const double* __restrict__ proj_y,
+                  int n, int H, int W, double fov_down_abs, double fov, double pi, double* __restrict__ back_points) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const double depth = (double)depth_im[i];
+  const double px = proj_x[i] / (double)W, py = proj_y[i] / (double)H;          // :484-489
+  const double yaw = (px * 2 - 1.0) * pi;                                          // :492
+  const double pitch = pi / 2 - ((1.0 * fov - py * fov) - fov_down_abs);          // :494
+  back_points[3 * (size_t)i] = depth * sin(pitch) * cos(-yaw);                     // :495-497
+  back_points[3 * (size_t)i + 1] = depth * sin(pitch) * sin(-yaw);
+  back_points[3 * (size_t)i + 2] = depth * cos(pitch);
+}
+
 }  // namespace
+
+extern "C" int vl_reverse_project(const float* d_depth_im, const double* d_proj_x, const double* d_proj_y, int H, int W,
+                                  double fov_up_deg, double fov_down_deg, double* d_back_points, vl_stream stream_) {
+  if (H <= 0 || W <= 0 || !d_depth_im || !d_proj_x || !d_proj_y || !d_back_points) {
+    vl_set_error("vl_reverse_project: invalid argument (H %d, W %d)", H, W);
+    return VL_EINVAL;
+  }
+  const double pi = 3.141592653589793;
+  const double fu = fov_up_deg / 180.0 * pi, fd = fov_down_deg / 180.0 * pi;       // :477-479
+  const double fov = fabs(fd) + fabs(fu);
+  const int n = H * W;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  k_reverse_project<<<(n + kThreads - 1) / kThreads, kThreads, 0, stream>>>(d_depth_im, d_proj_x, d_proj_y, n, H, W, fabs(fd),
+                                                                           fov, pi, d_back_points);
+  VL_LAUNCH_CHECK("k_reverse_project");
+  return VL_OK;
+}
 
 extern "C" size_t vl_project_workspace_bytes(long n_points, int H, int W) {
   size_t nw = (size_t)((n_points + 31) / 32) + 1;

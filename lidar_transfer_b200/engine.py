@@ -231,6 +231,24 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, wor
   return out
 
 
+def reverse_project(depth_im, proj_x, proj_y, fov_up, fov_down):
+  """Pixel coordinates + depth -> xyz on the device, the `cp` adaption's back projection
+  (LaserScan.do_reverse_projection_new, auxiliary/laserscan.py:475-501).  depth_im f32[H,W], proj_x / proj_y [H,W]
+  (float image coordinates or the clamped integer ones).  Returns back_points f64[H*W,3] (CUDA tensor)."""
+  require_cuda()
+  depth_im = _dev(depth_im, torch.float32)
+  dev = depth_im.device
+  H, W = depth_im.shape
+  px, py = _dev(proj_x, torch.float64, dev), _dev(proj_y, torch.float64, dev)
+  if px.numel() != H * W or py.numel() != H * W:
+    raise ValueError("proj_x / proj_y must have one entry per pixel")
+  out = torch.empty((H * W, 3), dtype=torch.float64, device=dev)
+  with torch.cuda.device(dev):
+    check(lib().vl_reverse_project(_ptr(depth_im), _ptr(px), _ptr(py), int(H), int(W), float(fov_up), float(fov_down),
+                                   _ptr(out), _stream()))
+  return out
+
+
 class TsdfDevice:
   """(iv) the four TSDF volumes resident in HBM + the integrate kernel.
 

@@ -111,7 +111,7 @@ def test_reverse_projection_matches_reference(G):
     s.proj_y_float = (1.0 - (np.arcsin(w[..., 2] / depth) + abs(fd / 180 * np.pi)) / (abs(fd / 180 * np.pi) + abs(fu / 180 * np.pi))) * H
     s.proj_x, s.proj_y = s._clamp(s.proj_x_float, s.proj_y_float)
     for pf in (False, True):
-      s.do_reverse_projection_new(fu, fd, preserve_float=pf)
+      s.do_reverse_projection_new(fu, fd, preserve_float=pf, host=True)
       assert np.allclose(s.back_points, G["proj_%s_back_%d" % (tag, int(pf))], rtol=0, atol=1e-9), (tag, pf)
 
 

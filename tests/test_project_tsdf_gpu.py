@@ -134,3 +134,27 @@ def test_tsdf_column_table_gives_the_same_bits(engine, oracle, vox, bnds):
   for k in ("tsdf", "weight", "color", "rem"):
     assert torch.equal(getattr(a, k).view(torch.int32), getattr(b, k).view(torch.int32)), k
   assert int((a.tsdf != 1).sum()) > 300
+
+
+def test_reverse_projection_on_device_matches_reference_golden(engine):
+  """vl_reverse_project (A14, laserscan.py:475-501) against the back-projected points the reference itself produced
+  (tests/golden/golden_v1.npz), both coordinate modes; float64, CUDA sin / cos vs the host's libm: <= 1e-9 m."""
+  import os
+  G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
+  from lidar_transfer_b200.auxiliary.laserscan import LaserScan
+  for tag in ("src", "tgt"):
+    fu, fd, H, W = G["proj_%s_args" % tag]
+    H, W = int(H), int(W)
+    s = LaserScan(H, W)
+    s.range_image = G["proj_%s_range" % tag]
+    w = G["proj_%s_kept_points" % tag][G["proj_%s_index" % tag]]
+    depth = np.linalg.norm(w, 2, axis=2)
+    s.proj_x_float = 0.5 * (-np.arctan2(w[..., 1], w[..., 0]) / np.pi + 1.0) * W
+    s.proj_y_float = (1.0 - (np.arcsin(w[..., 2] / depth) + abs(fd / 180 * np.pi)) / (abs(fd / 180 * np.pi) + abs(fu / 180 * np.pi))) * H
+    s.proj_x, s.proj_y = s._clamp(s.proj_x_float, s.proj_y_float)
+    for pf in (False, True):
+      s.do_reverse_projection_new(fu, fd, preserve_float=pf)
+      ref = G["proj_%s_back_%d" % (tag, int(pf))]
+      assert s.back_points.shape == ref.shape and np.allclose(s.back_points, ref, rtol=0, atol=1e-9), (tag, pf)
+      s.do_reverse_projection_new(fu, fd, preserve_float=pf, host=True)
+      assert np.allclose(s.back_points, ref, rtol=0, atol=1e-9)
