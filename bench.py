@@ -346,7 +346,7 @@ def run_native(args):
   # launching streams; kept out of the headline timing because each record costs host time per launch)
   # -- on ONE stream, so that a kernel's duration is not inflated by kernels of other scans sharing the SMs
   rr1 = pipeline.ScanRenderer(rays_np, origin, H, max_v, max_f, n_streams=1, device=dev, host_io=False,
-                              method=args.method)
+                              method=args.method, use_graph=False)
 
   def step_profile():
     for ds in d_scenes:
@@ -439,6 +439,7 @@ def run_native(args):
                  "tris_per_scan": int(nt), "streams": args.streams,
                  "l2": "inputs larger than L2: %d distinct meshes x %.0f MB cycled per step + %.0f MB scratch per stream"
                        % (M, mesh_bytes[0] / 1e6, rr.slots[0].blob.numel() / 1e6),
+                 "submission": "one CUDA graph launch per scan (vl_cast_graph_launch)" if rr.use_graph else "kernel by kernel",
                  "e2e_api": "ScanRenderer.submit_host (pinned host mesh -> H2D -> %s -> D2H of 5 outputs)"
                             % ("vl_cast" if args.method == "cast" else "vl_bvh_build -> vl_trace"),
                  "beam_index": "built once per sensor outside the timed region (vl_beams_build, ~40 us)" if args.method == "cast" else None},

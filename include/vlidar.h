@@ -139,6 +139,21 @@ int vl_cast_submit(const void* d_beams, const float* d_verts, const int* d_faces
                    int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
                    int* d_tri_id, int flags, void* d_workspace, size_t workspace_bytes, vl_stream stream,
                    vl_stream producer, void* ev_ready, int* h_status, void* ev_done);
+/* The same scan as ONE graph launch.  vl_cast_graph_create captures vl_cast for a stream slot whose beams, origin,
+ * outputs and workspace (sized for max_faces) are fixed; the mesh is whatever the 64-byte descriptor at h_desc
+ * (PINNED host memory: {const float* verts; const int* faces; const int* colors; const float* rem; int n_verts;
+ * int n_faces; 24 bytes unused}, device pointers) holds when the graph's first node copies it to the device -- the caller
+ * rewrites it before every vl_cast_graph_launch and not before the previous launch on that slot has finished.
+ * h_status (nullable, pinned int[4]) receives the workspace header's first 16 bytes as in vl_cast_submit; `stream`
+ * must be idle during creation (it is captured).  vl_cast_graph_launch: optional producer wait as in vl_cast_submit,
+ * the launch, then ev_done (nullable) is recorded. */
+int vl_cast_graph_create(const void* d_beams, const float* d_origin, int n_rays, int height,
+                         float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
+                         int* d_tri_id, int flags, void* d_workspace, size_t workspace_bytes, int max_faces,
+                         const void* h_desc, int* h_status, vl_stream stream, void** out_graph);
+int vl_cast_graph_launch(void* graph, vl_stream stream, vl_stream producer, void* ev_ready, void* ev_done);
+int vl_cast_graph_destroy(void* graph);
+
 /* Which device path the host-pointer ctrace / vl_ctrace_ids uses: 0 (default) = beam index +
  * vl_cast, 1 = vl_bvh_build + vl_trace.  Process-wide. */
 void vl_ctrace_method(int method);

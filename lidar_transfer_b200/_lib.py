@@ -39,6 +39,9 @@ SIGNATURES = {
     "vl_cast": (_i, [_vp] * 5 + [_i, _i, _vp, _i, _i] + [_vp] * 5 + [_i, _vp, _sz, _vp]),
     "vl_cast_status": (_i, [_vp, _vp, _vp]),
     "vl_cast_submit": (_i, [_vp] * 5 + [_i, _i, _vp, _i, _i] + [_vp] * 5 + [_i, _vp, _sz, _vp] + [_vp] * 4),
+    "vl_cast_graph_create": (_i, [_vp, _vp, _i, _i] + [_vp] * 5 + [_i, _vp, _sz, _i, _vp, _vp, _vp, _vp]),
+    "vl_cast_graph_launch": (_i, [_vp] * 5),
+    "vl_cast_graph_destroy": (_i, [_vp]),
     "vl_ctrace_method": (None, [_i]),
     "vl_debug_mesh_scalar": (None, [_i]),
     "vl_debug_cast_cells": (None, [_i]),

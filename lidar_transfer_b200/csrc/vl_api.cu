@@ -228,6 +228,39 @@ extern "C" int vl_cast_submit(const void* d_beams, const float* d_verts, const i
   return VL_OK;
 }
 
+// vl_cast_submit as a replayed CUDA graph (see include/vlidar.h)
+extern "C" int vl_cast_graph_create(const void* d_beams, const float* d_origin, int n_rays, int height,
+                                    float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
+                                    int* d_tri_id, int flags, void* d_workspace, size_t workspace_bytes, int max_faces,
+                                    const void* h_desc, int* h_status, vl_stream stream, void** out_graph) {
+  if (n_rays <= 0 || height <= 0 || max_faces < 0 || !d_beams || !d_origin || !d_workspace || (((uintptr_t)d_workspace) & 255) ||
+      !d_endpoints || !d_endcolors || !d_range || !d_endrem || !h_desc || !out_graph) {
+    vl_set_error("vl_cast_graph_create: invalid argument (n_rays %d, height %d, max_faces %d)", n_rays, height, max_faces);
+    return VL_EINVAL;
+  }
+  if (workspace_bytes < vl_cast_workspace_bytes(n_rays, max_faces)) {
+    vl_set_error("vl_cast_graph_create: workspace too small (%zu < %zu bytes)", workspace_bytes, vl_cast_workspace_bytes(n_rays, max_faces));
+    return VL_ENOSPACE;
+  }
+  return vl_cast_graph_create_impl(d_beams, d_origin, n_rays, height, d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id,
+                                   flags, d_workspace, max_faces, h_desc, h_status, static_cast<cudaStream_t>(stream), out_graph);
+}
+
+extern "C" int vl_cast_graph_launch(void* graph, vl_stream stream, vl_stream producer, void* ev_ready, void* ev_done) {
+  if (!graph) { vl_set_error("vl_cast_graph_launch: null graph"); return VL_EINVAL; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ev_ready) {
+    VL_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(ev_ready), static_cast<cudaStream_t>(producer)));
+    VL_CUDA_CHECK(cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(ev_ready), 0));
+  }
+  const int rc = vl_cast_graph_launch_impl(graph, s);
+  if (rc) return rc;
+  if (ev_done) VL_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(ev_done), s));
+  return VL_OK;
+}
+
+extern "C" int vl_cast_graph_destroy(void* graph) { return vl_cast_graph_destroy_impl(graph); }
+
 extern "C" int vl_cast_status(const void* d_workspace, vl_stream stream, int* info) {
   if (!d_workspace) { vl_set_error("vl_cast_status: null workspace"); return VL_EINVAL; }
   return vl_cast_status_read(d_workspace, static_cast<cudaStream_t>(stream), info);

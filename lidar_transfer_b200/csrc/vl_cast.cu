@@ -54,6 +54,19 @@ struct VlCastHeader {
 };
 static_assert(sizeof(VlCastHeader) == 256, "cast header is 256 B");
 
+// The mesh of one scan.  Passed to the kernels by value (vl_cast), or read from device memory (a replayed CUDA
+// graph, vl_cast_graph_*: the graph's first node copies it from a pinned host copy the caller rewrites per scan).
+struct VlMeshDesc {
+  const float* verts;
+  const int* faces;
+  const int* colors;
+  const float* rem;
+  int n_verts, n_faces;
+  long long pad[3];
+};
+static_assert(sizeof(VlMeshDesc) == 64, "mesh descriptor is 64 B");
+constexpr size_t kDescOffset = 128;   // device copy of the descriptor inside the 256-byte workspace header (the counters use the first 24)
+
 struct BeamLayout {
   int n;        // rays cast = width * height (RayTracer.cpp:56)
   int cw, ch;   // direction cells: yaw x sine
@@ -451,11 +464,16 @@ __global__ void k_cast_init(unsigned long long* __restrict__ best, int n, VlCast
 #ifndef VL_SETUP_MINB
 #define VL_SETUP_MINB 4
 #endif
+template <bool kDescPtr>
 __global__ void __launch_bounds__(kCastThreads, VL_SETUP_MINB)
 k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsigned int* __restrict__ fine_mask_g,
-             const float* __restrict__ verts, const int* __restrict__ faces, int n_verts, int n_faces,
-             const float* __restrict__ origin, VlCastHeader* chdr, float4* __restrict__ recs,
+             const VlMeshDesc mesh_val, const VlMeshDesc* __restrict__ mesh_ptr,
+             const float* __restrict__ origin, VlCastHeader* chdr, float4* __restrict__ recs, int rec_cap,
              int2* __restrict__ units, unsigned long long unit_cap) {
+  const float* __restrict__ verts = kDescPtr ? mesh_ptr->verts : mesh_val.verts;
+  const int* __restrict__ faces = kDescPtr ? mesh_ptr->faces : mesh_val.faces;
+  const int n_verts = kDescPtr ? mesh_ptr->n_verts : mesh_val.n_verts;
+  const int n_faces = kDescPtr ? mesh_ptr->n_faces : mesh_val.n_faces;
   __shared__ unsigned int s_mask[kFineWords];
   __shared__ int s_queue[kBatch];
   __shared__ int s_nq;
@@ -544,7 +562,7 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
         const unsigned long long at = s_warp[w] + incl - mine;
         const int pos = (int)(at >> kUnitBits);
         const unsigned long long u0 = at & units_mask;
-        if (pos < n_faces && u0 + (unsigned long long)n_u <= unit_cap) {   // always, unless the unit list overflowed
+        if (pos < rec_cap && u0 + (unsigned long long)n_u <= unit_cap) {   // always, unless the unit list overflowed
           float4* r = recs + 4 * (size_t)pos;
           r[0] = make_float4(T.v0x, T.v0y, T.v0z, T.e1x);
           r[1] = make_float4(T.e1y, T.e1z, T.e2x, T.e2y);
@@ -654,13 +672,17 @@ k_cast_units(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const int* _
 }
 
 // RayTracer.cpp:73-90 write-back for the winning triangle of each beam; BVH.cpp:106-107 hit = o + d * t
+template <bool kDescPtr>
 __global__ void __launch_bounds__(kCastThreads)
 k_cast_resolve(const unsigned long long* __restrict__ best, int n, const float4* __restrict__ dir,
-               const int* __restrict__ slot_of, const float* __restrict__ origin, const int* __restrict__ faces, const int* __restrict__ colors,
-               const float* __restrict__ rem, float* __restrict__ endpoints, int* __restrict__ endcolors,
+               const int* __restrict__ slot_of, const float* __restrict__ origin, const VlMeshDesc mesh_val,
+               const VlMeshDesc* __restrict__ mesh_ptr, float* __restrict__ endpoints, int* __restrict__ endcolors,
                float* __restrict__ range, float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses) {
   const int r = blockIdx.x * kCastThreads + threadIdx.x;
   if (r >= n) return;
+  const int* __restrict__ faces = kDescPtr ? mesh_ptr->faces : mesh_val.faces;
+  const int* __restrict__ colors = kDescPtr ? mesh_ptr->colors : mesh_val.colors;
+  const float* __restrict__ rem = kDescPtr ? mesh_ptr->rem : mesh_val.rem;
   const int slot = __ldg(slot_of + r);
   const unsigned long long key = slot >= 0 ? best[slot] : init_key();
   if (key < init_key()) {
@@ -751,10 +773,11 @@ int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_b
   return VL_OK;
 }
 
-int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces, const int* d_colors,
-                   const float* d_rem, int n_verts, int n_faces, const float* d_origin, int n_rays, int height,
-                   float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id, int flags,
-                   void* d_ws, cudaStream_t stream) {
+// the four kernels of one cast.  cap_faces sizes the workspace sections (the actual mesh for vl_cast, the largest
+// mesh of a stream slot for a graph); mesh is read from `d_desc` when by_ptr (graph replay) and passed by value otherwise.
+static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr, int cap_faces, const float* d_origin,
+                        int n_rays, int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
+                        int* d_tri_id, int flags, void* d_ws, cudaStream_t stream) {
   const BeamLayout L = beam_layout(n_rays, height);
   if (d_tri_id && n_rays > L.n)   // rays beyond width * height are never cast (RayTracer.cpp:56)
     VL_CUDA_CHECK(cudaMemsetAsync(d_tri_id + L.n, 0xff, sizeof(int) * (size_t)(n_rays - L.n), stream));
@@ -767,23 +790,29 @@ int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces
   const int* cell_start = reinterpret_cast<const int*>(B + L.off_cell_start);
   const unsigned int* fine_mask = reinterpret_cast<const unsigned int*>(B + L.off_mask);
   char* Wk = static_cast<char*>(d_ws);
-  const CastLayout C = cast_layout(n_rays, n_faces);
+  const CastLayout C = cast_layout(n_rays, cap_faces);
   VlCastHeader* chdr = reinterpret_cast<VlCastHeader*>(Wk);
+  const VlMeshDesc* d_desc = reinterpret_cast<const VlMeshDesc*>(Wk + kDescOffset);
   unsigned long long* best = reinterpret_cast<unsigned long long*>(Wk + C.off_best);
   int2* units = reinterpret_cast<int2*>(Wk + C.off_units);
   float4* recs = reinterpret_cast<float4*>(Wk + C.off_recs);
+  const int rec_cap = cap_faces > 0 ? cap_faces : 1;
   {
     VlProfScope ps(VL_ST_CAST_INIT, stream);
     k_cast_init<<<148, 256, 0, stream>>>(best, L.n, chdr);
     VL_LAUNCH_CHECK("k_cast_init");
   }
-  if (n_faces > 0) {
+  if (by_ptr || mesh.n_faces > 0) {
     {
       VlProfScope ps(VL_ST_CAST_SETUP, stream);
-      const int n_batches = (n_faces + kBatch - 1) / kBatch;
-      const int nb = n_batches < 148 * g_setup_ctas_per_sm ? n_batches : 148 * g_setup_ctas_per_sm;
-      k_cast_setup<<<nb, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, d_verts, d_faces, n_verts, n_faces,
-                                                   d_origin, chdr, recs, units, C.unit_cap);
+      const int n_batches = ((by_ptr ? cap_faces : mesh.n_faces) + kBatch - 1) / kBatch;
+      const int nb = n_batches < 148 * g_setup_ctas_per_sm ? (n_batches > 0 ? n_batches : 1) : 148 * g_setup_ctas_per_sm;
+      if (by_ptr)
+        k_cast_setup<true><<<nb, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, mesh, d_desc, d_origin, chdr, recs,
+                                                           rec_cap, units, C.unit_cap);
+      else
+        k_cast_setup<false><<<nb, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, mesh, d_desc, d_origin, chdr, recs,
+                                                            rec_cap, units, C.unit_cap);
       VL_LAUNCH_CHECK("k_cast_setup");
     }
     {
@@ -796,11 +825,66 @@ int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces
   {
     VlProfScope ps(VL_ST_CAST_RESOLVE, stream);
     const int nb = (L.n + kCastThreads - 1) / kCastThreads;
-    k_cast_resolve<<<nb, kCastThreads, 0, stream>>>(best, L.n, dir, slot_of, d_origin, d_faces, d_colors, d_rem, d_endpoints,
-                                                   d_endcolors, d_range, d_endrem, d_tri_id,
-                                                   (flags & VL_TRACE_ZERO_MISSES) != 0);
+    const bool zm = (flags & VL_TRACE_ZERO_MISSES) != 0;
+    if (by_ptr)
+      k_cast_resolve<true><<<nb, kCastThreads, 0, stream>>>(best, L.n, dir, slot_of, d_origin, mesh, d_desc, d_endpoints,
+                                                           d_endcolors, d_range, d_endrem, d_tri_id, zm);
+    else
+      k_cast_resolve<false><<<nb, kCastThreads, 0, stream>>>(best, L.n, dir, slot_of, d_origin, mesh, d_desc, d_endpoints,
+                                                            d_endcolors, d_range, d_endrem, d_tri_id, zm);
     VL_LAUNCH_CHECK("k_cast_resolve");
   }
+  return VL_OK;
+}
+
+int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces, const int* d_colors,
+                   const float* d_rem, int n_verts, int n_faces, const float* d_origin, int n_rays, int height,
+                   float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id, int flags,
+                   void* d_ws, cudaStream_t stream) {
+  VlMeshDesc mesh = {};
+  mesh.verts = d_verts; mesh.faces = d_faces; mesh.colors = d_colors; mesh.rem = d_rem;
+  mesh.n_verts = n_verts; mesh.n_faces = n_faces;
+  return cast_enqueue(d_beams, mesh, false, n_faces, d_origin, n_rays, height, d_endpoints, d_endcolors, d_range, d_endrem,
+                      d_tri_id, flags, d_ws, stream);
+}
+
+// ---------------------------------------------------------------------------
+// one scan = one graph launch: the cast of a stream slot (fixed beams, outputs, workspace) captured once, the mesh
+// changes per scan through a 64-byte descriptor in pinned host memory that the graph's first node copies to the device
+// ---------------------------------------------------------------------------
+int vl_cast_graph_create_impl(const void* d_beams, const float* d_origin, int n_rays, int height, float* d_endpoints,
+                              int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id, int flags, void* d_ws,
+                              int max_faces, const void* h_desc, int* h_status, cudaStream_t stream, void** out_exec) {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  VL_CUDA_CHECK(cudaStreamSynchronize(stream));
+  VL_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+  VlMeshDesc none = {};
+  int rc = VL_OK;
+  cudaError_t e = cudaMemcpyAsync(static_cast<char*>(d_ws) + kDescOffset, h_desc, sizeof(VlMeshDesc), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess)
+    rc = cast_enqueue(d_beams, none, true, max_faces, d_origin, n_rays, height, d_endpoints, d_endcolors, d_range, d_endrem,
+                      d_tri_id, flags, d_ws, stream);
+  if (e == cudaSuccess && rc == VL_OK && h_status)
+    e = cudaMemcpyAsync(h_status, d_ws, 16, cudaMemcpyDeviceToHost, stream);
+  const cudaError_t e2 = cudaStreamEndCapture(stream, &graph);   // always leave capture mode
+  if (rc != VL_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  VL_CUDA_CHECK(e);
+  VL_CUDA_CHECK(e2);
+  VL_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+  VL_CUDA_CHECK(cudaGraphDestroy(graph));
+  *out_exec = exec;
+  return VL_OK;
+}
+
+int vl_cast_graph_launch_impl(void* exec, cudaStream_t stream) {
+  VL_CUDA_CHECK(cudaGraphLaunch(static_cast<cudaGraphExec_t>(exec), stream));
+  for (int k = 0; k < 4; ++k) vl_count_launch();   // init, setup, units, resolve
+  return VL_OK;
+}
+
+int vl_cast_graph_destroy_impl(void* exec) {
+  if (exec) VL_CUDA_CHECK(cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(exec)));
   return VL_OK;
 }
 

@@ -209,3 +209,8 @@ int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces
                    float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id, int flags,
                    void* d_ws, cudaStream_t stream);
 int vl_cast_status_read(const void* d_ws, cudaStream_t stream, int* info);
+int vl_cast_graph_create_impl(const void* d_beams, const float* d_origin, int n_rays, int height, float* d_endpoints,
+                              int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id, int flags, void* d_ws,
+                              int max_faces, const void* h_desc, int* h_status, cudaStream_t stream, void** out_exec);
+int vl_cast_graph_launch_impl(void* exec, cudaStream_t stream);
+int vl_cast_graph_destroy_impl(void* exec);

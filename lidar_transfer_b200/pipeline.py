@@ -50,6 +50,11 @@ class _Slot:
                   self.out["endrem"].data_ptr(), self.out["tri_id"].data_ptr(), engine.TRACE_ZERO_MISSES,
                   self.blob.data_ptr(), self.blob.numel(), self.stream.cuda_stream)
     self.tail = (self.ready.cuda_event, self.h_status.data_ptr(), self.done.cuda_event)
+    # the mesh descriptor of the graph path (vl_cast_graph_*): 4 device pointers, n_verts, n_faces
+    self.h_desc = torch.zeros(8, dtype=torch.int64, pin_memory=True)
+    self.desc64 = self.h_desc.numpy()
+    self.desc32 = self.desc64.view(np.int32)
+    self.graph = None
     if host_io:
       # device staging for host-fed meshes + pinned host buffers for the results
       self.d_verts = torch.empty(3 * max_verts, dtype=f32, device=dev)
@@ -63,7 +68,7 @@ class ScanRenderer:
   """rays f32[R,3] and origin f32[3] are fixed per renderer (one target sensor)."""
 
   def __init__(self, rays, origin, height, max_verts, max_faces, n_streams=4, device=None, host_io=False,
-               method="cast"):
+               method="cast", use_graph=True):
     engine.require_cuda()
     if method not in ("cast", "lbvh"):
       raise ValueError("method must be 'cast' or 'lbvh'")
@@ -84,6 +89,32 @@ class ScanRenderer:
     self._lib = lib()
     self._beams_ptr = self.beams.blob.data_ptr() if self.beams is not None else 0
     self._origin_ptr = self.origin.data_ptr()
+    # method "cast": every slot's four kernels + status copy are captured once and replayed per scan with a new mesh
+    # descriptor (one graph launch instead of six driver calls).  Set use_graph = False to launch kernel by kernel
+    # (the per-stage event profiler of the library needs that).
+    self.use_graph = bool(use_graph) and method == "cast"
+    if self.use_graph:
+      with torch.cuda.device(self.dev):
+        for s in self.slots:
+          g = ctypes.c_void_p()
+          check(self._lib.vl_cast_graph_create(self._beams_ptr, self._origin_ptr, self.n_rays, self.height, *s.fixed[:8],
+                                               self.max_faces, s.h_desc.data_ptr(), s.h_status.data_ptr(),
+                                               s.stream.cuda_stream, ctypes.byref(g)))
+          s.graph = g
+
+  def close(self):
+    """Destroys the slots' graphs (after everything submitted has drained)."""
+    self.wait()
+    for s in self.slots:
+      if s.graph is not None:
+        self._lib.vl_cast_graph_destroy(s.graph)
+        s.graph = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
 
   def _acquire(self):
     s = self.slots[self._next]
@@ -119,6 +150,15 @@ class ScanRenderer:
     if n_faces > self.max_faces:
       raise ValueError("mesh has %d faces, renderer was sized for %d" % (n_faces, self.max_faces))
     s = self._acquire()
+    if self.use_graph and s.graph is not None:
+      # one graph launch per scan: the mesh goes through the slot's pinned descriptor
+      d64, d32 = s.desc64, s.desc32
+      d64[0] = verts.data_ptr(); d64[1] = faces.data_ptr(); d64[2] = colors.data_ptr(); d64[3] = rem.data_ptr()
+      d32[8] = n_verts; d32[9] = n_faces
+      check(self._lib.vl_cast_graph_launch(s.graph, s.fixed[8], torch.cuda.current_stream(self.dev).cuda_stream,
+                                           s.tail[0], s.tail[2]))
+      s.busy = True
+      return s
     if self.method == "cast":
       # one C call per scan: wait for the producer stream, four launches, status copy, done event
       # (the caller is on self.dev; per-scan host time bounds the batch at this kernel speed)

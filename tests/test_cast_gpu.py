@@ -316,3 +316,36 @@ def test_cast_config4_size_equals_lbvh(engine, oracle):
   t = (dot(e2, cross((o[None, :] - v0).astype(f32), e1)) * inv_a).astype(f32)
   assert np.array_equal(t.view(np.int32), a["range"][hit].view(np.int32))
   assert np.array_equal(a["endcolors"].reshape(-1, 3)[hit], sc["colors"][fa[:, 0]])
+
+
+def test_scan_renderer_graph_replay_equals_direct_cast(engine, oracle):
+  """ScanRenderer.submit replays one captured graph per stream slot with the mesh swapped through a pinned descriptor:
+  meshes of different sizes in sequence (larger, smaller, empty, larger again) on 2 slots must give what engine.cast
+  gives, and what the kernel-by-kernel submission gives."""
+  import torch
+  from lidar_transfer_b200 import pipeline
+  H, W, fu, fd = 32, 512, 10.0, -25.0
+  rays = oracle.create_rays(fu, fd, H, W)
+  origin = np.array([0.2, -0.1, 0.0], np.float32)
+  scenes = [synth.make_scene(500 + k, n_side=n, n_boxes=4) for k, n in enumerate((90, 40, 120, 25, 90))]
+  empty = dict(verts=np.zeros((3, 3), np.float32), faces=np.zeros((0, 3), np.int32), colors=np.zeros((3, 3), np.int32), rem=np.zeros(3, np.float32))
+  scenes.insert(2, empty)
+  max_v = max(s["verts"].shape[0] for s in scenes); max_f = max(s["faces"].shape[0] for s in scenes)
+  dev = [tuple(torch.from_numpy(np.ascontiguousarray(s[k]).reshape(-1)).cuda() for k in ("verts", "faces", "colors", "rem")) for s in scenes]
+  beams = engine.Beams(rays, H)
+  want = [_np(engine.cast(beams, s["verts"], s["faces"], s["colors"], s["rem"], origin, zero_misses=True)) for s in scenes]
+  for use_graph in (True, False):
+    R = pipeline.ScanRenderer(rays, origin, H, max_v, max_f, n_streams=2, use_graph=use_graph)
+    assert R.use_graph == use_graph
+    for rep in range(2):
+      for i, d in enumerate(dev):
+        slot = R.submit(*d)
+        slot.done.synchronize()
+        got = {k: v.cpu().numpy() for k, v in slot.out.items()}
+        _same(got, want[i], what="graph %s scene %d rep %d" % (use_graph, i, rep))
+    # several in flight, then drain
+    slots = [R.submit(*dev[i]) for i in (0, 3)]
+    R.wait()
+    for slot, i in zip(slots, (0, 3)):
+      _same({k: v.cpu().numpy() for k, v in slot.out.items()}, want[i], what="in flight")
+    R.close()

@@ -54,6 +54,7 @@ for method in methods:
     res["%s_%dstream_us_per_scan" % (method, n_streams)] = round(us, 1)
     res["%s_%dstream_Mrays" % (method, n_streams)] = round(H * W / us, 1)
     if n_streams == 1:
+      R.use_graph = False   # per-stage events need the kernel-by-kernel path
       L.vl_profile_enable(1)
       for s in scenes: R.submit(*s)
       R.wait()
