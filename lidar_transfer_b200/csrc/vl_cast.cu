@@ -8,11 +8,18 @@
 // and the ctrace ABI gives all rays ONE origin (RayTracer.cpp:116-124: `float* origin` is a single point).
 // Building a hierarchy over the large, single-use set (the triangles) to query it with the small, constant
 // set (the sensor's beams) is backwards on a bandwidth machine.  Here the BEAMS are indexed once per sensor
-// (a direction-space cell grid: yaw x sin(elevation)), and each scan's triangles are streamed through it
-// exactly once: a triangle's central projection is a spherical triangle, its padded (yaw, sine) bounding
+// (a direction-space cell grid: azimuth x sin(elevation)), and each scan's triangles are streamed through it
+// exactly once: a triangle's central projection is a spherical triangle, its padded (azimuth, sine) bounding
 // rectangle selects a few cells, the beams in those cells are tested with the reference's Moller-Trumbore
 // arithmetic (vl_tri_hit, bit-identical to vl_trace.cu) and the closest hit per beam is kept with a 64-bit
 // atomicMin on (t bits << 32 | face index).  No per-scan sort, no per-scan tree, no divergent traversal.
+//
+// Per scan: k_cast_init resets the per-beam keys; k_cast_setup streams the faces in batches of
+// 1024 per CTA -- a cheap cull (sine interval vs the beam rows) that ~70 % of a LiDAR scene's triangles do not
+// survive, then on dense warps the full rectangle, a 64-byte record and one work unit per run of <= 8 cells of a
+// cell row; k_cast_units pools the beams of 32 units per warp and tests them 32 at a time; k_cast_resolve writes the
+// outputs of RayTracer.cpp:73-90 for the winning triangle of each beam.  Records and units live in L2 between the
+// two kernels.  The four launches of a stream slot can be captured once and replayed per scan (vl_cast_graph_*).
 //
 // Result contract (same as vl_trace.cu): the closest hit over ALL triangles under the
 // reference arithmetic; exact-t ties go to the smaller face index (that is what the packed key orders by).
@@ -461,9 +468,6 @@ __global__ void k_cast_init(unsigned long long* __restrict__ best, int n, VlCast
 //   setup: runs on dense warps: the full rectangle, a 64-byte record (edges for the triangle test + rectangle)
 //          and ceil(items / 4) work units (record, first item) appended to global lists -- one packed atomicAdd
 //          per pass reserves both.  List order is irrelevant: a unit is self-contained.
-#ifndef VL_SETUP_MINB
-#define VL_SETUP_MINB 4
-#endif
 template <bool kDescPtr>
 __global__ void __launch_bounds__(kCastThreads, VL_SETUP_MINB)
 k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsigned int* __restrict__ fine_mask_g,
