@@ -181,3 +181,22 @@ dist.destroy_process_group()
   assert sorted(set(d["cover"])) == [1, 2] and d["cover"].count(1) == 12 and d["cover"].count(2) == 11
   assert [s["n"] for s in d["stats"]] == [12, 11]
   assert d["agg"]["scans"] == 23 and d["agg"]["ms"] == 20.0 and np.isclose(d["agg"]["mrays_per_s"], 23 * 100 / 20e-3 / 1e6)
+
+
+def test_cpulist_and_measured_peak_lookup(tmp_path, monkeypatch):
+  """Small host helpers: sysfs cpulist parsing for the per-GPU NUMA binding, and bench.py's tolerant lookup of the
+  driver-written HBM peak (MEASURED_PEAKS.json: key names are not under this repo's control)."""
+  import importlib.util
+  import json
+  from lidar_transfer_b200 import sharding
+  assert sharding._cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and sharding._cpulist("") == set()
+  assert isinstance(sharding.bind_to_gpu_numa_node(0), str)   # never raises, with or without a GPU / sysfs
+  spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+  bench = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(bench)
+  monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+  assert bench._peaks()[0] == 6650.0 and "fallback" in bench._peaks()[1]
+  for content, want in (({"hbm_gbs": 6552.0, "bf16_tflops": 1600.0}, 6552.0), ({"hbm": {"copy_GBps": 6400}}, 6400.0),
+                        ({"hbm_tbs": 6.5}, 6500.0), ({"bf16": 1.0}, 6650.0)):
+    (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps(content))
+    assert bench._peaks()[0] == want, content
