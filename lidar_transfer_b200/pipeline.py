@@ -85,6 +85,7 @@ class ScanRenderer:
     if self.beams is not None:
       torch.cuda.current_stream(self.dev).synchronize()
     self.host_io = host_io
+    self._dev_index = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
     self._next = 0
     self._lib = lib()
     self._beams_ptr = self.beams.blob.data_ptr() if self.beams is not None else 0
@@ -150,6 +151,12 @@ class ScanRenderer:
     if n_faces > self.max_faces:
       raise ValueError("mesh has %d faces, renderer was sized for %d" % (n_faces, self.max_faces))
     s = self._acquire()
+    if torch.cuda.current_device() != self._dev_index:   # launches go to the renderer's device whatever the caller's is
+      with torch.cuda.device(self.dev):
+        return self._submit_on_device(s, verts, faces, colors, rem, n_verts, n_faces)
+    return self._submit_on_device(s, verts, faces, colors, rem, n_verts, n_faces)
+
+  def _submit_on_device(self, s, verts, faces, colors, rem, n_verts, n_faces):
     if self.use_graph and s.graph is not None:
       # one graph launch per scan: the mesh goes through the slot's pinned descriptor
       d64, d32 = s.desc64, s.desc32
@@ -168,8 +175,7 @@ class ScanRenderer:
       s.busy = True
       return s
     s.stream.wait_stream(torch.cuda.current_stream(self.dev))
-    with torch.cuda.device(self.dev):
-      self._launch(s, verts, faces, colors, rem, n_verts, n_faces)
+    self._launch(s, verts, faces, colors, rem, n_verts, n_faces)
     s.done.record(s.stream)
     s.busy = True
     return s
