@@ -195,8 +195,8 @@ extern "C" int vl_cast(const void* d_beams, const float* d_verts, const int* d_f
     vl_set_error("vl_cast: invalid argument (n_rays %d, height %d)", n_rays, height);
     return VL_EINVAL;
   }
-  if (n_faces < 0 || n_verts < 0 || (n_faces > 0 && (!d_verts || !d_faces || !d_colors || !d_rem))) {
-    vl_set_error("vl_cast: invalid mesh (n_verts %d, n_faces %d)", n_verts, n_faces);
+  if (n_faces < 0 || n_verts < 0 || n_faces >= (1 << 28) || (n_faces > 0 && (!d_verts || !d_faces || !d_colors || !d_rem))) {
+    vl_set_error("vl_cast: invalid mesh (n_verts %d, n_faces %d; at most 2^28 - 1 faces)", n_verts, n_faces);
     return VL_EINVAL;
   }
   if (workspace_bytes < vl_cast_workspace_bytes(n_rays, n_faces)) {
@@ -233,7 +233,7 @@ extern "C" int vl_cast_graph_create(const void* d_beams, const float* d_origin, 
                                     float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
                                     int* d_tri_id, int flags, void* d_workspace, size_t workspace_bytes, int max_faces,
                                     const void* h_desc, int* h_status, vl_stream stream, void** out_graph) {
-  if (n_rays <= 0 || height <= 0 || max_faces < 0 || !d_beams || !d_origin || !d_workspace || (((uintptr_t)d_workspace) & 255) ||
+  if (n_rays <= 0 || height <= 0 || max_faces < 0 || max_faces >= (1 << 28) || !d_beams || !d_origin || !d_workspace || (((uintptr_t)d_workspace) & 255) ||
       !d_endpoints || !d_endcolors || !d_range || !d_endrem || !h_desc || !out_graph) {
     vl_set_error("vl_cast_graph_create: invalid argument (n_rays %d, height %d, max_faces %d)", n_rays, height, max_faces);
     return VL_EINVAL;
