@@ -78,7 +78,7 @@ def _peaks():
 
 
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+  """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
   Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
        "clocks_event_reasons.sw_power_cap")
@@ -89,7 +89,7 @@ class ClockSampler:
   def start(self):
     try:
       self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits", "-lms", "200"],
+                                    "--format=csv,noheader,nounits", "-lms", "50"],
                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       threading.Thread(target=self._pump, daemon=True).start()
     except OSError:
