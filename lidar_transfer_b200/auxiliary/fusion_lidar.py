@@ -18,6 +18,47 @@ import torch
 
 from .. import _lib, engine
 
+class LazyHostArray(object):
+  """A device tensor standing in for a numpy array the reference returns but its batch driver never reads (the
+  mesh of deform(): 100-250 MB per scan that only the GUI and the optional PLY dump look at).  Shape / dtype / len are
+  known at once; the device -> host copy happens on first real use (np.asarray, indexing, arithmetic) and is kept."""
+
+  def __init__(self, tensor, fn=None):
+    self._t, self._fn, self._a = tensor, fn, None
+    shape = tuple(tensor.shape) if fn is None else None
+    if fn is not None:            # fn maps the tensor to the final device tensor lazily (e.g. a colour look-up)
+      self._shape, self._dtype = fn("shape"), fn("dtype")
+    else:
+      self._shape, self._dtype = shape, np.dtype(str(tensor.dtype).replace("torch.", ""))
+
+  shape = property(lambda self: self._shape)
+  dtype = property(lambda self: self._dtype)
+  ndim = property(lambda self: len(self._shape))
+  size = property(lambda self: int(np.prod(self._shape)))
+
+  def __len__(self):
+    return self._shape[0]
+
+  def device_tensor(self):
+    return self._t if self._fn is None else self._fn(self._t)
+
+  def __array__(self, dtype=None, copy=None):
+    if self._a is None:
+      self._a = self.device_tensor().cpu().numpy()
+    return self._a if dtype is None else self._a.astype(dtype, copy=False)
+
+  def __getitem__(self, key):
+    return self.__array__()[key]
+
+  def __mul__(self, other):
+    return self.__array__() * other
+
+  __rmul__ = __mul__
+
+  def __repr__(self):
+    return "LazyHostArray(shape=%s, dtype=%s, %s)" % (self._shape, self._dtype, "host copy made" if self._a is not None else "on device")
+
+
 FUSION_GPU_MODE = 1  # the reference sets 0 when pycuda is missing and falls back to numpy; there is no fallback here
 
 

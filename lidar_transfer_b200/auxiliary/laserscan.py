@@ -357,16 +357,31 @@ class MultiSemLaserScan():
     return m
 
   def _cast(self, tsdf_vol, lut):
-    """Ray-cast the target beam pattern against the fused volume and fill the attributes write()/compare() read."""
+    """Ray-cast the target beam pattern against the fused volume and fill the attributes write()/compare() read.
+    The per-ray results (a few MB) come to the host like in the reference; the mesh deform() also returns stays on the
+    device behind LazyHostArray -- the batch driver never looks at it (lidar_deform.py:415), the GUI and the PLY
+    dump get a host copy the moment they do."""
+    import torch
     rays = self.create_rays(self.t_fov_up, self.t_fov_down, self.t_H, self.t_W)
     origin = np.array([0, 0, 0]).astype(np.float32)
-    self.back_points, label_color, verts, colors, faces, self.proj_range, self.proj_remissions = \
-        tsdf_vol.throw_rays_at_mesh(rays, origin, self.t_H, self.t_W, lut)
+    print("Get mesh by marching cubes...")
+    print("Raytracing...")
+    out, m = tsdf_vol.throw_rays_at_mesh_device(rays, origin, self.t_H, self.t_W)
+    self.back_points = out["endpoints"].cpu().numpy().reshape(-1, 3)
+    label_color = out["endcolors"].cpu().numpy().reshape(-1, 3)
+    self.proj_range = out["range"].cpu().numpy().reshape(-1, self.t_W)
+    self.proj_remissions = out["endrem"].cpu().numpy().reshape(-1, self.t_W)
     self.proj_color = label_color.reshape(self.t_H, self.t_W, 3)
     self.label_color = lut[label_color[:, 2]]
     self.label_image = np.copy(self.proj_color[:, :, 2])
     self.proj_color = lut[self.label_image]
-    return verts, lut[colors[:, 2]], faces
+    lut_np = np.asarray(lut)
+
+    def vertex_colors(t):   # lut[colors[:, 2]] (laserscan.py:1004-1005), looked up on the device when it is needed
+      if isinstance(t, str):
+        return (int(m["colors"].shape[0]),) + tuple(lut_np.shape[1:]) if t == "shape" else lut_np.dtype
+      return torch.from_numpy(lut_np).to(t.device)[t[:, 2].long()]
+    return (fl.LazyHostArray(m["verts"]), fl.LazyHostArray(m["colors"], vertex_colors), fl.LazyHostArray(m["faces"]))
 
   def deform(self, adaption, poses, idx):
     """ Deforms laserscan with specified adaption method and transformation (laserscan.py:819-1021) """

@@ -187,6 +187,11 @@ def test_deform_cp_and_mergemesh_and_compare(engine, G, tmp_path):
   ms.open_multiple_scans(names, labels, poses, 0)
   verts, vcolors, faces = ms.deform('mergemesh', poses, 0)
   assert faces.shape[0] > 1000 and verts.shape == (3 * faces.shape[0], 3) and vcolors.shape == verts.shape
+  # the mesh comes back lazily (device-resident until somebody looks): the host view is the reference's arrays
+  v_host, c_host, f_host = np.asarray(verts), np.asarray(vcolors), np.asarray(faces)
+  assert v_host.dtype == np.float32 and v_host.shape == verts.shape and f_host.dtype == np.int32 and len(faces) == f_host.shape[0]
+  assert c_host.shape == v_host.shape and np.array_equal(f_host.reshape(-1), np.arange(3 * f_host.shape[0]))
+  assert np.array_equal(verts[:5], v_host[:5]) and np.array_equal(np.asarray(vcolors[..., ::-1] * 255), c_host[..., ::-1] * 255)
   assert ms.back_points.shape == (H * W, 3) and ms.proj_range.shape == (H, W) and ms.label_image.shape == (H, W)
   assert ms.proj_color.shape == (H, W, 3) and ms.label_color.shape == (H * W, 3)
   hit = ms.proj_range > 0
