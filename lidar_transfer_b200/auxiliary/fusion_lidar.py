@@ -134,8 +134,9 @@ class TSDFVolume(object):
     print("Get mesh by marching cubes...")
     print("Raytracing...")
     out, m = self.throw_rays_at_mesh_device(rays, origin, H, W)
+    # the per-ray results as numpy like the reference; the mesh (elements 2-4) lazily: see LazyHostArray
     return out["endpoints"].cpu().numpy().reshape(-1, 3), out["endcolors"].cpu().numpy().reshape(-1, 3), \
-        m["verts"].cpu().numpy(), m["colors"].cpu().numpy(), m["faces"].cpu().numpy(), \
+        LazyHostArray(m["verts"]), LazyHostArray(m["colors"]), LazyHostArray(m["faces"]), \
         out["range"].cpu().numpy().reshape(-1, W), out["endrem"].cpu().numpy().reshape(-1, W)
 
 
