@@ -349,3 +349,21 @@ def test_scan_renderer_graph_replay_equals_direct_cast(engine, oracle):
     for slot, i in zip(slots, (0, 3)):
       _same({k: v.cpu().numpy() for k, v in slot.out.items()}, want[i], what="in flight")
     R.close()
+
+
+def test_cast_random_configurations_vs_oracle(engine, oracle):
+  """A sweep nobody wrote down by hand: random beam grids (rows, columns, field of view), random origins, hostile
+  soups of random size -- cast == oracle bit for bit (hypothesis drives the parameters, 20 examples)."""
+  from hypothesis import given, settings, strategies as st
+
+  @settings(max_examples=20, deadline=None)
+  @given(seed=st.integers(0, 2 ** 31 - 1), H=st.integers(1, 40), W=st.integers(1, 300), n=st.integers(16, 3000),
+         fu=st.floats(-10.0, 60.0), span=st.floats(1.0, 80.0), far=st.booleans())
+  def run(seed, H, W, n, fu, span, far):
+    rng = np.random.default_rng(seed)
+    origin = (rng.normal(size=3) * (1000.0 if far else 2.0)).astype(np.float32)
+    verts, faces = _hostile_mesh(rng, n, origin)
+    rays = oracle.create_rays(fu, fu - span, H, W)
+    _run(engine, oracle, verts, faces, rays, origin, H, lbvh=False)
+
+  run()
