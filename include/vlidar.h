@@ -183,6 +183,16 @@ int vl_project(const double* d_points, const float* d_remissions, const uint32_t
                float* d_range, int32_t* d_index, int32_t* d_label, float* d_rem,
                uint8_t* d_keep, int* d_n_kept, void* d_workspace, size_t workspace_bytes,
                vl_stream stream);
+/* The same with the optional `beam_angles` step of auxiliary/laserscan.py:321-327: each point's pitch is replaced by
+ * the entry of d_beam_angles f64[n_beam_angles] (device) nearest to it -- first minimum of |pitch - entry|, like
+ * numpy's argmin; the pitch in radians is compared with the list as given, as the reference does -- before the image
+ * row is computed.  n_beam_angles == 0 is vl_project. */
+int vl_project_snap(const double* d_points, const float* d_remissions, const uint32_t* d_labels,
+                    long n_points, double fov_up_deg, double fov_down_deg, int H, int W, int remove,
+                    const double* d_beam_angles, int n_beam_angles,
+                    float* d_range, int32_t* d_index, int32_t* d_label, float* d_rem,
+                    uint8_t* d_keep, int* d_n_kept, void* d_workspace, size_t workspace_bytes,
+                    vl_stream stream);
 
 /* Reverse projection of the `cp` adaption: replaces LaserScan.do_reverse_projection_new
  * auxiliary/laserscan.py:475-501.  d_depth_im f32[H*W], d_proj_x / d_proj_y f64[H*W] (image coordinates of each
@@ -223,6 +233,15 @@ int vl_tsdf_init_integrate(float* d_tsdf, float* d_weight, float* d_color, float
                            float trunc_margin, float obs_weight, float fov_up_deg, float fov_down_deg,
                            const float* d_color_im, const float* d_depth_im, const float* d_rem_im,
                            int im_h, int im_w, void* d_workspace, size_t workspace_bytes, vl_stream stream);
+/* Workspace for vl_tsdf_init_integrate's shell sweep: the column table plus 8 B per image pixel.  With at least this
+ * much workspace (and |fov| <= 35 deg, dy * dz <= 2^24, dx <= 65535, fewer than ~1400 image rows per radian) the fused
+ * first integration brackets every voxel (plain sqrt, arcsine series, image row to a few hundredths) against the range image's
+ * per-pixel [depth, depth + trunc] shell and runs the reference arithmetic only where the bracket cannot rule out an
+ * update; bit-identical to vl_tsdf_init + vl_tsdf_integrate.  With vl_tsdf_workspace_bytes(dx, dy) only, or outside
+ * those limits, every voxel takes the reference arithmetic.  vl_debug_tsdf_shell(0) turns the shell sweep off, (2) runs
+ * it with one voxel per thread instead of four (the variant for dz % 4 != 0); tests compare all of them. */
+size_t vl_tsdf_fresh_workspace_bytes(int dx, int dy, int im_h, int im_w);
+void vl_debug_tsdf_shell(int mode);
 
 /* ------------------------------------------------------------------------------------
  * (v) iso-surface extraction + per-vertex label / remission lookup ("next" row N1).

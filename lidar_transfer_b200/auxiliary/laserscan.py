@@ -152,12 +152,12 @@ class LaserScan:
     """Nearest-point-per-pixel projection (laserscan.py:294-391) as one atomicMin scatter on the device."""
     if method != "depth":
       raise NotImplementedError("only method='depth' (the one deform() uses, laserscan.py:952) runs on the device")
-    if self.beam_angles:
-      raise NotImplementedError("beam_angles snapping (laserscan.py:322-327) is not on the device path yet")
     pts = np.ascontiguousarray(self.points, np.float64)
     out = engine.project(pts, np.ascontiguousarray(self.remissions, np.float32),
                          np.ascontiguousarray(self.label).astype(np.uint32), fov_up, fov_down, self.proj_H, self.proj_W,
-                         remove=remove)
+                         remove=remove, beam_angles=self.beam_angles if self.beam_angles else None)
+    if int(out["n_kept"].item()) == 0:  # the reference fails the same way at :384 (fancy index into an empty array)
+      raise IndexError("do_range_projection_new: no point left after the depth / field-of-view filters")
     keep = out["keep"].cpu().numpy()
     if not remove:  # the reference always drops depth == 0 points (:307-309), FOV filtering is optional
       keep = np.linalg.norm(pts, 2, axis=1) != 0
@@ -180,7 +180,11 @@ class LaserScan:
     fu, fd = fov_up / 180.0 * np.pi, fov_down / 180.0 * np.pi
     with np.errstate(invalid="ignore", divide="ignore"):
       self.proj_x_float = 0.5 * (-np.arctan2(w[..., 1], w[..., 0]) / np.pi + 1.0) * self.proj_W
-      self.proj_y_float = (1.0 - (np.arcsin(w[..., 2] / depth) + abs(fd)) / (abs(fd) + abs(fu))) * self.proj_H
+      pitch = np.arcsin(w[..., 2] / depth)
+      if self.beam_angles:  # :321-327, the H*W winners only
+        ba = np.asarray(self.beam_angles, np.float64)
+        pitch = ba[np.abs(pitch[..., None] - ba).argmin(axis=-1)]
+      self.proj_y_float = (1.0 - (pitch + abs(fd)) / (abs(fd) + abs(fu))) * self.proj_H
     self.proj_x, self.proj_y = self._clamp(self.proj_x_float, self.proj_y_float)
 
   def do_reverse_projection_new(self, fov_up, fov_down, preserve_float=False, host=False):

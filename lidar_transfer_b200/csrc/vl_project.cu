@@ -24,9 +24,9 @@ struct ProjParams {
 };
 
 __global__ void __launch_bounds__(kThreads)
-k_project_scatter(const double* __restrict__ pts, long n, ProjParams P, unsigned long long* __restrict__ keys,
-                  unsigned int* __restrict__ masks, unsigned int* __restrict__ warp_counts,
-                  uint8_t* __restrict__ keep_out) {
+k_project_scatter(const double* __restrict__ pts, long n, ProjParams P, const double* __restrict__ beam_angles,
+                  int n_beam_angles, unsigned long long* __restrict__ keys, unsigned int* __restrict__ masks,
+                  unsigned int* __restrict__ warp_counts, uint8_t* __restrict__ keep_out) {
   const long i = (long)blockIdx.x * kThreads + threadIdx.x;
   bool keep = false;
   if (i < n) {
@@ -34,7 +34,16 @@ k_project_scatter(const double* __restrict__ pts, long n, ProjParams P, unsigned
     const double depth = sqrt((x * x + y * y) + z * z);  // np.linalg.norm(points, 2, axis=1), :304
     if (depth != 0.0) {                                   // :307-309
       const double yaw = -atan2(y, x);
-      const double pitch = asin(z / depth);
+      double pitch = asin(z / depth);
+      if (n_beam_angles > 0) {  // :321-327  pitch <- the list entry nearest to it (argmin: first minimum)
+        int best = 0;
+        double best_d = fabs(pitch - __ldg(beam_angles));
+        for (int k = 1; k < n_beam_angles; ++k) {
+          const double d = fabs(pitch - __ldg(beam_angles + k));
+          if (d < best_d) { best_d = d; best = k; }
+        }
+        pitch = __ldg(beam_angles + best);
+      }
       double proj_x = 0.5 * (yaw / P.pi + 1.0);           // :329-330
       double proj_y = 1.0 - (pitch + P.fov_down_abs) / P.fov;
       if (!P.remove || (proj_y >= 0.0 && proj_y <= 1.0)) {  // :337-345
@@ -167,13 +176,15 @@ extern "C" size_t vl_project_workspace_bytes(long n_points, int H, int W) {
   return vl_align256(8 * (size_t)H * W) + 2 * vl_align256(4 * nw);
 }
 
-extern "C" int vl_project(const double* d_points, const float* d_remissions, const uint32_t* d_labels, long n_points,
-                          double fov_up_deg, double fov_down_deg, int H, int W, int remove, float* d_range,
-                          int32_t* d_index, int32_t* d_label, float* d_rem, uint8_t* d_keep, int* d_n_kept,
-                          void* d_workspace, size_t workspace_bytes, vl_stream stream_) {
+extern "C" int vl_project_snap(const double* d_points, const float* d_remissions, const uint32_t* d_labels,
+                               long n_points, double fov_up_deg, double fov_down_deg, int H, int W, int remove,
+                               const double* d_beam_angles, int n_beam_angles, float* d_range, int32_t* d_index,
+                               int32_t* d_label, float* d_rem, uint8_t* d_keep, int* d_n_kept, void* d_workspace,
+                               size_t workspace_bytes, vl_stream stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (H <= 0 || W <= 0 || n_points < 0 || n_points >= 0x7fffffffL || !d_range || !d_index || !d_label || !d_rem ||
-      !d_workspace || (n_points > 0 && (!d_points || !d_remissions || !d_labels))) {
+      !d_workspace || (n_points > 0 && (!d_points || !d_remissions || !d_labels)) || n_beam_angles < 0 ||
+      (n_beam_angles > 0 && !d_beam_angles)) {
     vl_set_error("vl_project: invalid argument");
     return VL_EINVAL;
   }
@@ -196,7 +207,8 @@ extern "C" int vl_project(const double* d_points, const float* d_remissions, con
   if (n_points > 0) {
     const int nb = (int)((n_points + kThreads - 1) / kThreads);
     VlProfScope ps(VL_ST_PROJECT_SCATTER, stream);
-    k_project_scatter<<<nb, kThreads, 0, stream>>>(d_points, n_points, P, keys, masks, counts, d_keep);
+    k_project_scatter<<<nb, kThreads, 0, stream>>>(d_points, n_points, P, d_beam_angles, n_beam_angles, keys, masks, counts,
+                                                   d_keep);
     VL_LAUNCH_CHECK("k_project_scatter");
   }
   k_scan_counts<<<1, 1024, 0, stream>>>(counts, (long)nw, d_n_kept);
@@ -207,4 +219,12 @@ extern "C" int vl_project(const double* d_points, const float* d_remissions, con
                                                                              n_pix, d_range, d_index, d_label, d_rem);
   VL_LAUNCH_CHECK("k_project_gather");
   return VL_OK;
+}
+
+extern "C" int vl_project(const double* d_points, const float* d_remissions, const uint32_t* d_labels, long n_points,
+                          double fov_up_deg, double fov_down_deg, int H, int W, int remove, float* d_range,
+                          int32_t* d_index, int32_t* d_label, float* d_rem, uint8_t* d_keep, int* d_n_kept,
+                          void* d_workspace, size_t workspace_bytes, vl_stream stream) {
+  return vl_project_snap(d_points, d_remissions, d_labels, n_points, fov_up_deg, fov_down_deg, H, W, remove, nullptr, 0,
+                         d_range, d_index, d_label, d_rem, d_keep, d_n_kept, d_workspace, workspace_bytes, stream);
 }

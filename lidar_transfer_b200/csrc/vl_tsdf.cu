@@ -65,14 +65,10 @@ k_tsdf_columns(int* __restrict__ col_px, const TsdfParams P) {
 // (tsdf 1, weight / colour / remission 0, fusion_lidar.py:48-63) -- nothing is read, every voxel is written (its
 // updated value, or the initial one): vl_tsdf_init + vl_tsdf_integrate in one pass over the volume.
 template <bool kTable, bool kFresh>
-__global__ void __launch_bounds__(kThreads)
-k_tsdf_integrate(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, float* __restrict__ color_vol,
-                 float* __restrict__ rem_vol, const TsdfParams P, const float* __restrict__ color_im,
-                 const float* __restrict__ depth_im, const float* __restrict__ rem_im, long long n_vox,
-                 const int* __restrict__ col_px) {
-  const long long vi = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (vi >= n_vox) return;
-  const int voxel_idx = (int)vi;
+__device__ __forceinline__ void tsdf_voxel(const int voxel_idx, float* __restrict__ tsdf_vol, float* __restrict__ weight_vol,
+                                           float* __restrict__ color_vol, float* __restrict__ rem_vol, const TsdfParams& P,
+                                           const float* __restrict__ color_im, const float* __restrict__ depth_im,
+                                           const float* __restrict__ rem_im, const int* __restrict__ col_px) {
   float out_tsdf = 1.f, out_weight = 0.f, out_color = 0.f, out_rem = 0.f;   // kFresh: what is stored at the end
   do {
     const int vol_dim_y = P.dy, vol_dim_z = P.dz;
@@ -139,7 +135,182 @@ k_tsdf_integrate(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, f
   }
 }
 
+template <bool kTable, bool kFresh>
+__global__ void __launch_bounds__(kThreads)
+k_tsdf_integrate(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, float* __restrict__ color_vol,
+                 float* __restrict__ rem_vol, const TsdfParams P, const float* __restrict__ color_im,
+                 const float* __restrict__ depth_im, const float* __restrict__ rem_im, long long n_vox,
+                 const int* __restrict__ col_px) {
+  const long long vi = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (vi >= n_vox) return;
+  tsdf_voxel<kTable, kFresh>((int)vi, tsdf_vol, weight_vol, color_vol, rem_vol, P, color_im, depth_im, rem_im, col_px);
+}
+
+// ---- first integration into a NEW volume: only a thin shell of voxels can change ---------------------------------
+//
+// With tsdf 1 / weight 0 / colour 0 / remission 0 in the volume (fusion_lidar.py:48-52), the kernel string's update
+// (:190-227) leaves a voxel at its initial value unless its pixel is non-empty (:156), depth_diff >= -trunc (:193) and
+//   * the pixel's colour is 0 (== the volume's: running-average branch, weight becomes obs_weight), or
+//   * dist < dist_old == 0 (class-switch branch), i.e. depth_diff < 0: the voxel lies BEHIND the surface.
+// So per pixel the voxel depths that matter are (lo, hi] with lo = the pixel's depth (-inf for colour 0) and
+// hi = depth + trunc: k_tsdf_shell stores that pair per pixel.  The sweep then needs, per voxel, only a CONSERVATIVE
+// bracket of what the reference computes: the exact pixel column of its z column (k_tsdf_columns), its depth to
+// 1e-5 (plain sqrt instead of norm3df) and its fractional image row to +-eps_row (arcsine by its odd series up to
+// s^11: below |asin|, by < 2e-4 rad for |s| <= 0.62, monotonic beyond) -- one candidate pixel, two when the row
+// estimate is within eps_row of a row boundary.  A voxel whose bracket misses the shell of its candidate pixels, or
+// that is outside the vertical field of view by more than the series' error, is written with the initial values
+// straight away; every other voxel is queued in shared memory and evaluated by tsdf_voxel<true, true> -- the
+// reference arithmetic, dense over the queue.  Voxels within kDecodeWindow of a slab boundary (where the float
+// index decode :96-98 can land in the neighbouring slab) always take that path.
+// kVec 4: a thread owns 4 consecutive voxels of one z column (dz % 4 == 0, 16-byte aligned volumes): one decode,
+// one column lookup, float4 stores.
+constexpr int kFastChunk = 1024;      // voxels per CTA
+constexpr int kDecodeWindow = 256;    // >= 64 (float(idx) for idx < 2^31) + n_vox * 2^-24 (rounding of the quotient)
+constexpr float kAsinErr = 3e-4f;     // series truncation (< 2e-4 for |s| <= 0.62) + float rounding
+constexpr float kDepthRel = 1e-5f;
+
+struct ShellParams {
+  int slab;                // dy * dz  (<= 2^24: the decode of y and z is then exact in float)
+  float inv_dz;
+  float fov_abs_down, h_over_fov, pitch_hi, pitch_lo;   // pitch_hi = fov_up + kAsinErr, pitch_lo = fov_down - kAsinErr
+  float eps_row;           // bound on |estimated - exact| fractional image row (< 0.5)
+};
+
+// shell[c * H + r]: COLUMN-major, so that the rows a z column's voxels fall into lie next to each other
+__global__ void __launch_bounds__(kThreads)
+k_tsdf_shell(const float* __restrict__ depth_im, const float* __restrict__ color_im, int H, int W, float trunc,
+             float2* __restrict__ shell) {
+  const int p = blockIdx.x * kThreads + threadIdx.x;
+  if (p >= H * W) return;
+  const float d = __ldg(depth_im + p);
+  float lo = INFINITY, hi = -INFINITY;                       // :156 empty pixel: nothing is integrated
+  if (d != 0.f) {
+    if (!(fabsf(d) < INFINITY)) { lo = -INFINITY; hi = INFINITY; }   // NaN / inf depth: leave it to the exact path
+    else { lo = __ldg(color_im + p) == 0.f ? -INFINITY : d; hi = d + trunc; }
+  }
+  const int r = p / W, c = p - r * W;
+  shell[c * H + r] = make_float2(lo, hi);
+}
+
+// Bracket of one voxel (x, y fixed per column: xy2 = x^2 + y^2) at height z: its depth to +-kDepthRel and the one or
+// two image rows it can fall into; r0 < 0: outside the vertical field of view for certain (:131).
+struct VoxelBracket { float d_lo, d_hi; int r0, r1; };
+
+__device__ __forceinline__ VoxelBracket shell_bracket(float xy2, float z, const TsdfParams& P, const ShellParams& S) {
+  // bracket only: contracted arithmetic is fine here (the file is compiled with -fmad=false)
+  const float q = __fmaf_rn(z, z, xy2);
+  const float rq = rsqrtf(q);
+  const float d = q * rq;                                    // the origin voxel gives NaN: no comparison rules it out
+  const float sn = z * rq, s2 = sn * sn;
+  // asin(s) = s + s^3/6 + 3 s^5/40 + 15 s^7/336 + 105 s^9/3456 + 945 s^11/42240 + ...
+  float poly = __fmaf_rn(s2, 945.f / 42240, 105.f / 3456);
+  poly = __fmaf_rn(s2, poly, 15.f / 336);
+  poly = __fmaf_rn(s2, poly, 3.f / 40);
+  poly = __fmaf_rn(s2, poly, 1.f / 6);
+  const float pitch = __fmaf_rn(sn * s2, poly, sn);
+  const float rowf = __fmaf_rn(-(pitch + S.fov_abs_down), S.h_over_fov, (float)P.im_h);
+  VoxelBracket b;
+  b.d_lo = d * (1.f - kDepthRel);
+  b.d_hi = d * (1.f + kDepthRel);
+  b.r0 = max(0, min(P.im_h - 1, (int)floorf(rowf - S.eps_row)));
+  b.r1 = max(0, min(P.im_h - 1, (int)floorf(rowf + S.eps_row)));
+  if (pitch > S.pitch_hi || pitch < S.pitch_lo) b.r0 = -1;
+  return b;
+}
+
+template <int kVec>
+__global__ void __launch_bounds__(kThreads)
+k_tsdf_fresh_shell(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, float* __restrict__ color_vol,
+                   float* __restrict__ rem_vol, const TsdfParams P, const ShellParams S,
+                   const float* __restrict__ color_im, const float* __restrict__ depth_im,
+                   const float* __restrict__ rem_im, const int* __restrict__ col_px, const float2* __restrict__ shell) {
+  __shared__ int s_q[kFastChunk];
+  __shared__ int s_nq;
+  const int vx = blockIdx.y;
+  const int base = blockIdx.x * kFastChunk;
+  if (threadIdx.x == 0) s_nq = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned int lt = (1u << lane) - 1;
+  const float x = __fmaf_rn((float)vx, P.voxel_size, P.ox);   // :101-104, the values tsdf_voxel sees
+#pragma unroll
+  for (int k = 0; k < kFastChunk / (kThreads * kVec); ++k) {
+    const int rem_i = base + kVec * (k * kThreads + threadIdx.x);   // kVec 4: slab % 4 == 0, so all four are live or none
+    const bool live = rem_i < S.slab;
+    const int voxel_idx = vx * S.slab + rem_i;
+    unsigned int ex = 0;                                            // bit j: voxel rem_i + j takes the exact path
+    if (live) {
+      if (rem_i < kDecodeWindow || rem_i + kVec > S.slab - kDecodeWindow) {
+        ex = (1u << kVec) - 1;
+      } else {
+        int vy = (int)((float)rem_i * S.inv_dz);
+        int vz = rem_i - vy * P.dz;
+        if (vz < 0) { vy--; vz += P.dz; } else if (vz >= P.dz) { vy++; vz -= P.dz; }
+        const float y = __fmaf_rn((float)vy, P.voxel_size, P.oy);
+        const float xy2 = __fmaf_rn(x, x, y * y);
+        const int px = __ldg(col_px + vx * P.dy + vy);
+        const float2* __restrict__ col = shell + px * P.im_h;
+        VoxelBracket b[kVec];
+        float2 lh[kVec];
+#pragma unroll
+        for (int j = 0; j < kVec; ++j)                               // kVec 4: dz % 4 == 0, same z column
+          b[j] = shell_bracket(xy2, __fmaf_rn((float)(vz + j), P.voxel_size, P.oz), P, S);
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) lh[j] = __ldg(col + max(b[j].r0, 0));   // all loads in flight before the first use
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) {
+          if (b[j].r0 < 0) continue;
+          bool may = !(b[j].d_hi < lh[j].x || b[j].d_lo > lh[j].y);
+          if (b[j].r1 != b[j].r0) {
+            const float2 o = __ldg(col + b[j].r1);
+            may = may || !(b[j].d_hi < o.x || b[j].d_lo > o.y);
+          }
+          if (may) ex |= 1u << j;
+        }
+      }
+      if (kVec == 4) {
+        if (ex == 0) {
+          const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(tsdf_vol + voxel_idx) = one;
+          *reinterpret_cast<float4*>(weight_vol + voxel_idx) = zero;
+          *reinterpret_cast<float4*>(color_vol + voxel_idx) = zero;
+          *reinterpret_cast<float4*>(rem_vol + voxel_idx) = zero;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (!(ex >> j & 1)) { tsdf_vol[voxel_idx + j] = 1.f; weight_vol[voxel_idx + j] = 0.f; color_vol[voxel_idx + j] = 0.f; rem_vol[voxel_idx + j] = 0.f; }
+        }
+      } else if (ex == 0) {
+        tsdf_vol[voxel_idx] = 1.f; weight_vol[voxel_idx] = 0.f; color_vol[voxel_idx] = 0.f; rem_vol[voxel_idx] = 0.f;
+      }
+    }
+    if (__any_sync(0xffffffffu, ex != 0)) {                          // queue the exact-path voxels: one atomic per warp
+      unsigned int m[kVec];
+      int total = 0;
+#pragma unroll
+      for (int j = 0; j < kVec; ++j) { m[j] = __ballot_sync(0xffffffffu, ex >> j & 1); total += __popc(m[j]); }
+      int pos = 0;
+      if (lane == 0) pos = atomicAdd(&s_nq, total);
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+#pragma unroll
+      for (int j = 0; j < kVec; ++j) {
+        if (ex >> j & 1) s_q[pos + __popc(m[j] & lt)] = voxel_idx + j;
+        pos += __popc(m[j]);
+      }
+    }
+  }
+  __syncthreads();
+  const int nq = s_nq;
+  for (int i = threadIdx.x; i < nq; i += kThreads)
+    tsdf_voxel<true, true>(s_q[i], tsdf_vol, weight_vol, color_vol, rem_vol, P, color_im, depth_im, rem_im, col_px);
+}
+
+int g_tsdf_shell = 1;    // vl_debug_tsdf_shell: 0 off, 1 on, 2 on with one voxel per thread
+int g_tsdf_scalar = 0;
+
 }  // namespace
+
+extern "C" void vl_debug_tsdf_shell(int mode) { g_tsdf_shell = mode ? 1 : 0; g_tsdf_scalar = mode == 2; }
 
 extern "C" int vl_tsdf_init(float* d_tsdf, float* d_weight, float* d_color, float* d_rem, long long n_voxels,
                             vl_stream stream_) {
@@ -176,6 +347,7 @@ static int tsdf_integrate_impl(float* d_tsdf, float* d_weight, float* d_color, f
     vl_set_error("vl_tsdf_integrate_ws: workspace too small (%zu < %zu bytes)", workspace_bytes, sizeof(int) * (size_t)dx * dy);
     return VL_ENOSPACE;
   }
+  const size_t shell_off = vl_align256(sizeof(int) * (size_t)dx * dy);
   TsdfParams P;
   P.dx = dx; P.dy = dy; P.dz = dz;
   P.ox = vol_origin[0]; P.oy = vol_origin[1]; P.oz = vol_origin[2];
@@ -189,7 +361,37 @@ static int tsdf_integrate_impl(float* d_tsdf, float* d_weight, float* d_color, f
     int* col_px = static_cast<int*>(d_workspace);
     k_tsdf_columns<<<(dx * dy + kThreads - 1) / kThreads, kThreads, 0, stream>>>(col_px, P);
     VL_LAUNCH_CHECK("k_tsdf_columns");
-    if (fresh)
+    // the shell sweep needs: room for the shell image, y / z decodable in float, a field of view inside the arcsine
+    // series' range, image rows much coarser than its error, a positive truncation margin
+    const double fov_rad = fabs((double)P.fov_up) + fabs((double)P.fov_down);
+    const double eps_row = fov_rad > 0.0 ? 1.02 * kAsinErr * im_h / fov_rad + 1e-3 + 4e-7 * im_h : 1.0;
+    const bool shell_ok = fresh && g_tsdf_shell && workspace_bytes >= shell_off + sizeof(float2) * (size_t)im_h * im_w &&
+                          (long long)dy * dz <= (1LL << 24) && dx <= 65535 && trunc_margin > 0.f && voxel_size > 0.f &&
+                          fabs((double)P.fov_up) <= 0.61 && fabs((double)P.fov_down) <= 0.61 && fov_rad > 0.0 &&
+                          eps_row < 0.45;
+    if (shell_ok) {
+      float2* shell = reinterpret_cast<float2*>(static_cast<char*>(d_workspace) + shell_off);
+      k_tsdf_shell<<<(im_h * im_w + kThreads - 1) / kThreads, kThreads, 0, stream>>>(d_depth_im, d_color_im, im_h, im_w,
+                                                                                   trunc_margin, shell);
+      VL_LAUNCH_CHECK("k_tsdf_shell");
+      ShellParams S;
+      S.slab = dy * dz;
+      S.inv_dz = 1.0f / (float)dz;
+      S.fov_abs_down = fabsf(P.fov_down);
+      S.h_over_fov = (float)im_h / (fabsf(P.fov_up) + fabsf(P.fov_down));
+      S.pitch_hi = P.fov_up + kAsinErr;
+      S.pitch_lo = P.fov_down - kAsinErr;
+      S.eps_row = (float)eps_row;
+      dim3 grid((unsigned int)((S.slab + kFastChunk - 1) / kFastChunk), (unsigned int)dx);
+      const bool vec = dz % 4 == 0 && !g_tsdf_scalar &&
+                       ((((uintptr_t)d_tsdf) | ((uintptr_t)d_weight) | ((uintptr_t)d_color) | ((uintptr_t)d_rem)) & 15) == 0;
+      if (vec)
+        k_tsdf_fresh_shell<4><<<grid, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, S, d_color_im, d_depth_im,
+                                                            d_rem_im, col_px, shell);
+      else
+        k_tsdf_fresh_shell<1><<<grid, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, S, d_color_im, d_depth_im,
+                                                            d_rem_im, col_px, shell);
+    } else if (fresh)
       k_tsdf_integrate<true, true><<<nb, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, d_color_im, d_depth_im,
                                                                d_rem_im, n_vox, col_px);
     else
@@ -214,6 +416,10 @@ extern "C" int vl_tsdf_integrate(float* d_tsdf, float* d_weight, float* d_color,
 
 extern "C" size_t vl_tsdf_workspace_bytes(int dx, int dy) {
   return dx > 0 && dy > 0 ? vl_align256(sizeof(int) * (size_t)dx * dy) : 256;
+}
+
+extern "C" size_t vl_tsdf_fresh_workspace_bytes(int dx, int dy, int im_h, int im_w) {
+  return vl_tsdf_workspace_bytes(dx, dy) + (im_h > 0 && im_w > 0 ? vl_align256(sizeof(float2) * (size_t)im_h * im_w) : 0);
 }
 
 extern "C" int vl_tsdf_integrate_ws(float* d_tsdf, float* d_weight, float* d_color, float* d_rem, int dx, int dy, int dz,

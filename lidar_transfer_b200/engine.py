@@ -191,17 +191,21 @@ def trace_bruteforce(verts, faces, colors, rem, rays, origin, height, out=None):
   return out
 
 
-def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, workspace=None):
+def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, workspace=None, beam_angles=None):
   """(iii) spherical range-image projection, the device equivalent of
   LaserScan.do_range_projection_new('depth') + do_label_projection_new
   (auxiliary/laserscan.py:294-391, 672-676).
 
   points f64[N,3], remissions f32[N], labels u32/i32[N].  Returns dict of CUDA tensors:
   range_image f32[H,W] (0 empty), index i32[H,W] (-1 empty, into the kept points),
-  proj_label i32[H,W], proj_remissions f32[H,W] (-1 empty), keep bool[N], n_kept i32[1]."""
+  proj_label i32[H,W], proj_remissions f32[H,W] (-1 empty), keep bool[N], n_kept i32[1].
+  beam_angles (non-empty sequence): the pitch snapping of laserscan.py:321-327 (vl_project_snap)."""
   require_cuda()
   points = _dev(points, torch.float64).reshape(-1)
   dev = points.device
+  ba = None
+  if beam_angles is not None and len(beam_angles):
+    ba = _dev(np.asarray(beam_angles, np.float64).reshape(-1), torch.float64, dev)
   n = points.numel() // 3
   remissions = _dev(remissions, torch.float32, dev).reshape(-1)
   if torch.is_tensor(labels) and labels.dtype in (torch.int32, torch.uint32):
@@ -222,10 +226,11 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, wor
              keep=torch.empty(max(n, 1), dtype=torch.uint8, device=dev),
              n_kept=torch.zeros(1, dtype=torch.int32, device=dev))
   with torch.cuda.device(dev):
-    check(lib().vl_project(_ptr(points), _ptr(remissions), _ptr(labels), n, float(fov_up), float(fov_down), H, W,
-                           1 if remove else 0, _ptr(out["range_image"]), _ptr(out["index"]), _ptr(out["proj_label"]),
-                           _ptr(out["proj_remissions"]), _ptr(out["keep"]), _ptr(out["n_kept"]), _ptr(workspace),
-                           workspace.numel(), _stream()))
+    check(lib().vl_project_snap(_ptr(points), _ptr(remissions), _ptr(labels), n, float(fov_up), float(fov_down), H, W,
+                                1 if remove else 0, _ptr(ba) if ba is not None else None,
+                                ba.numel() if ba is not None else 0, _ptr(out["range_image"]), _ptr(out["index"]),
+                                _ptr(out["proj_label"]), _ptr(out["proj_remissions"]), _ptr(out["keep"]),
+                                _ptr(out["n_kept"]), _ptr(workspace), workspace.numel(), _stream()))
   out["keep"] = out["keep"][:n].bool()
   out["workspace"] = workspace
   return out
@@ -304,8 +309,9 @@ class TsdfDevice:
     origin = (ctypes.c_float * 3)(*[float(v) for v in self.origin])
     if use_column_table:
       ws = getattr(self, "_col_ws", None)
-      if ws is None:
-        ws = self._col_ws = torch.empty(lib().vl_tsdf_workspace_bytes(self.dim[0], self.dim[1]), dtype=torch.uint8, device=dev)
+      need = lib().vl_tsdf_fresh_workspace_bytes(self.dim[0], self.dim[1], int(im_h), int(im_w))  # column table + shell image
+      if ws is None or ws.numel() < need:
+        ws = self._col_ws = torch.empty(need, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
       if use_column_table:
         fn = lib().vl_tsdf_init_integrate if fused else lib().vl_tsdf_integrate_ws

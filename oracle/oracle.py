@@ -129,11 +129,13 @@ def create_rays(fov_up, fov_down, H, W):
   return np.ascontiguousarray(beams.reshape(W * H, -1).astype(np.float32))
 
 
-def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True):
-  """vlo_project: do_range_projection_new('depth') + do_label_projection_new,
-  auxiliary/laserscan.py:294-391, 672-676."""
+def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, beam_angles=None):
+  """vlo_project[_snap]: do_range_projection_new('depth') + do_label_projection_new,
+  auxiliary/laserscan.py:294-391, 672-676; beam_angles (a non-empty list) turns on the pitch snapping of
+  :321-327."""
   lib = _lib(os.path.join(_HERE, "liboracle.so"))
-  lib.vlo_project.restype = ctypes.c_long
+  lib.vlo_project_snap.restype = ctypes.c_long
+  ba = np.ascontiguousarray(beam_angles if beam_angles is not None else [], np.float64).reshape(-1)
   points = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
   n = points.shape[0]
   remissions = np.ascontiguousarray(remissions, np.float32)
@@ -141,10 +143,11 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True):
   out = dict(range_image=np.empty(H * W, np.float32), index=np.empty(H * W, np.int32),
              proj_label=np.empty(H * W, np.int32), proj_remissions=np.empty(H * W, np.float32),
              keep=np.empty(n, np.uint8))
-  kept = lib.vlo_project(_p(points, _f64p), _p(remissions, _f32p), _p(labels, _u32p), ctypes.c_long(n),
-                         ctypes.c_double(fov_up), ctypes.c_double(fov_down), ctypes.c_int(H), ctypes.c_int(W),
-                         ctypes.c_int(1 if remove else 0), _p(out["range_image"], _f32p), _p(out["index"], _i32p),
-                         _p(out["proj_label"], _i32p), _p(out["proj_remissions"], _f32p), _p(out["keep"], _u8p))
+  kept = lib.vlo_project_snap(_p(points, _f64p), _p(remissions, _f32p), _p(labels, _u32p), ctypes.c_long(n),
+                              ctypes.c_double(fov_up), ctypes.c_double(fov_down), ctypes.c_int(H), ctypes.c_int(W),
+                              ctypes.c_int(1 if remove else 0), _p(ba, _f64p), ctypes.c_int(ba.size),
+                              _p(out["range_image"], _f32p), _p(out["index"], _i32p),
+                              _p(out["proj_label"], _i32p), _p(out["proj_remissions"], _f32p), _p(out["keep"], _u8p))
   for k in ("range_image", "index", "proj_label", "proj_remissions"):
     out[k] = out[k].reshape(H, W)
   out["n_kept"] = int(kept)
@@ -152,7 +155,7 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True):
   return out
 
 
-def project_numpy(points, remissions, labels, fov_up, fov_down, H, W, remove=True):
+def project_numpy(points, remissions, labels, fov_up, fov_down, H, W, remove=True, beam_angles=None):
   """Pure-numpy/Python-loop restatement of the same projection (small inputs only);
   line-for-line semantics of auxiliary/laserscan.py:294-391 used to cross-check vlo_project."""
   points = np.asarray(points, np.float64).reshape(-1, 3)
@@ -166,6 +169,10 @@ def project_numpy(points, remissions, labels, fov_up, fov_down, H, W, remove=Tru
   depth, points, remissions, labels = depth[k0], points[k0], remissions[k0], labels[k0]
   yaw = -np.arctan2(points[:, 1], points[:, 0])
   pitch = np.arcsin(points[:, 2] / depth)
+  if beam_angles is not None and len(beam_angles):  # :321-327
+    ba = np.asarray(beam_angles, np.float64)
+    for i in range(len(pitch)):
+      pitch[i] = ba[np.abs(pitch[i] - ba).argmin()]
   proj_x = 0.5 * (yaw / np.pi + 1.0)
   proj_y = 1.0 - (pitch + abs(fd)) / fov
   keep = k0.copy()

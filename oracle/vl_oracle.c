@@ -345,10 +345,15 @@ int vlo_trace(const float* rays, const float* origin_in, const float* verts, con
  * marks which input points survive the depth!=0 and FOV filters.
  * Returns the number of kept points.
  */
-long vlo_project(const double* points, const float* remissions, const uint32_t* labels, long n,
-                 double fov_up_deg, double fov_down_deg, int H, int W, int remove,
-                 float* range_image, int32_t* index, int32_t* proj_label, float* proj_rem,
-                 uint8_t* keep) {
+/* vlo_project_snap: the same with the `beam_angles` step of :321-327 -- each point's pitch is replaced by the
+ * entry of beam_angles[0..n_beam_angles) nearest to it (np.abs(pitch - beam_angles).argmin(): first minimum;
+ * the reference compares the pitch in radians with the list as given).  n_beam_angles == 0: no snapping
+ * (`if self.beam_angles:` is false for None and for an empty list). */
+long vlo_project_snap(const double* points, const float* remissions, const uint32_t* labels, long n,
+                      double fov_up_deg, double fov_down_deg, int H, int W, int remove,
+                      const double* beam_angles, int n_beam_angles,
+                      float* range_image, int32_t* index, int32_t* proj_label, float* proj_rem,
+                      uint8_t* keep) {
   const double pi = 3.141592653589793; /* np.pi */
   double fov_up = fov_up_deg / 180.0 * pi;
   double fov_down = fov_down_deg / 180.0 * pi;
@@ -364,6 +369,15 @@ long vlo_project(const double* points, const float* remissions, const uint32_t* 
     if (depth == 0) continue; /* :307-309 */
     double yaw = -atan2(y, x);
     double pitch = asin(z / depth);
+    if (n_beam_angles > 0) { /* :321-327 */
+      int best = 0;
+      double best_d = fabs(pitch - beam_angles[0]);
+      for (int k = 1; k < n_beam_angles; ++k) {
+        double d = fabs(pitch - beam_angles[k]);
+        if (d < best_d) { best_d = d; best = k; }
+      }
+      pitch = beam_angles[best];
+    }
     double proj_x = 0.5 * (yaw / pi + 1.0);
     double proj_y = 1.0 - (pitch + fabs(fov_down)) / fov;
     if (remove && !(proj_y >= 0 && proj_y <= 1)) continue; /* :337-345 */
@@ -384,6 +398,14 @@ long vlo_project(const double* points, const float* remissions, const uint32_t* 
     kept++;
   }
   return kept;
+}
+
+long vlo_project(const double* points, const float* remissions, const uint32_t* labels, long n,
+                 double fov_up_deg, double fov_down_deg, int H, int W, int remove,
+                 float* range_image, int32_t* index, int32_t* proj_label, float* proj_rem,
+                 uint8_t* keep) {
+  return vlo_project_snap(points, remissions, labels, n, fov_up_deg, fov_down_deg, H, W, remove, 0, 0, range_image,
+                          index, proj_label, proj_rem, keep);
 }
 
 /* ------------------------------------------------------------------ */

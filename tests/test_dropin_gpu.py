@@ -145,6 +145,39 @@ def test_semlaserscan_projection_matches_reference_golden(engine, G, tag):
     assert np.allclose(s.back_points, G["proj_%s_back_%d" % (tag, int(pf))], rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize("tag,remove", [("rad", True), ("rad", False), ("deg", False)])
+def test_semlaserscan_beam_angle_snapping_matches_reference_golden(engine, G, tag, remove):
+  """SemLaserScan(beam_angles=...).do_range_projection_new through vl_project_snap vs the reference's own Python
+  (tests/golden/make_golden_beams.py), including the per-pixel float row of the snapped pitch."""
+  from lidar_transfer_b200.auxiliary.laserscan import SemLaserScan
+  B = np.load(os.path.join(os.path.dirname(GOLDEN), "golden_beams_v1.npz"))
+  fu, fd, H, W = B["args"]
+  s = SemLaserScan(int(H), int(W), 20, color_dict=_lut(G), beam_angles=B["beams_" + tag].tolist())
+  s.points, s.remissions, s.label = B["points_f32"].astype(np.float64), B["rem"].copy(), B["label"].copy()
+  s.colorize()
+  s.do_range_projection_new(fu, fd, remove=remove)
+  s.do_label_projection_new()
+  k = "%s_%d_" % (tag, int(remove))
+  assert s.points.shape[0] == int(B[k + "n_kept"][0])
+  assert np.array_equal(s.index, B[k + "index"]) and np.array_equal(s.proj_label, B[k + "label"])
+  assert np.array_equal(s.range_image.view(np.int32), B[k + "range"].view(np.int32))
+  assert np.array_equal(s.proj_remissions.view(np.int32), B[k + "rem"].view(np.int32))
+  assert np.array_equal(s.proj_y_float, B[k + "proj_y_float"])
+
+
+def test_semlaserscan_projection_with_no_surviving_point_raises_like_the_reference(engine, G):
+  """Degree-valued beam_angles + remove=True: every row falls outside [0, 1]; the reference stops with an IndexError
+  at laserscan.py:384 and so does the shim."""
+  from lidar_transfer_b200.auxiliary.laserscan import SemLaserScan
+  B = np.load(os.path.join(os.path.dirname(GOLDEN), "golden_beams_v1.npz"))
+  fu, fd, H, W = B["args"]
+  s = SemLaserScan(int(H), int(W), 20, color_dict=_lut(G), beam_angles=B["beams_deg"].tolist())
+  s.points, s.remissions, s.label = B["points_f32"].astype(np.float64), B["rem"].copy(), B["label"].copy()
+  s.colorize()
+  with pytest.raises(IndexError):
+    s.do_range_projection_new(fu, fd, remove=True)
+
+
 def _dataset(G, tmp_path):
   scan = np.concatenate([G["scan_points_f32"], G["scan_rem"][:, None]], axis=1).astype(np.float32)
   names, labels = [], []

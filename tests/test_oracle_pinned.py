@@ -44,6 +44,28 @@ def test_projection(oracle, G, tag, impl):
   assert (got["index"] >= 0).sum() > 0.2 * H * W
 
 
+@pytest.mark.parametrize("tag,remove", [("rad", True), ("rad", False), ("deg", False)])
+@pytest.mark.parametrize("impl", ["c", "numpy"])
+def test_projection_with_beam_angle_snapping(oracle, tag, remove, impl):
+  """laserscan.py:321-327 (pitch <- nearest entry of beam_angles), recorded from the reference's own Python by
+  tests/golden/make_golden_beams.py; `deg` is the list in degrees (every pitch lands on one of two entries)."""
+  B = np.load(os.path.join(os.path.dirname(GOLDEN), "golden_beams_v1.npz"))
+  fu, fd, H, W = B["args"]
+  fn = oracle.project if impl == "c" else oracle.project_numpy
+  got = fn(B["points_f32"].astype(np.float64), B["rem"], B["label"], fu, fd, int(H), int(W), remove=remove,
+           beam_angles=B["beams_" + tag].tolist())
+  k = "%s_%d_" % (tag, int(remove))
+  assert got["n_kept"] == int(B[k + "n_kept"][0])
+  assert np.array_equal(got["index"], B[k + "index"]) and np.array_equal(got["proj_label"], B[k + "label"])
+  assert np.array_equal(_bits(got["range_image"]), _bits(B[k + "range"]))
+  assert np.array_equal(_bits(got["proj_remissions"]), _bits(B[k + "rem"]))
+  rows = np.unique(np.nonzero(got["index"] >= 0)[0]).size
+  assert rows == (16 if tag == "rad" else 2)
+  # without the list the same points fill a different image: the step is not a no-op on this input
+  plain = fn(B["points_f32"].astype(np.float64), B["rem"], B["label"], fu, fd, int(H), int(W), remove=remove)
+  assert not np.array_equal(plain["index"], got["index"])
+
+
 def test_tsdf_restatement_matches_reference_kernel(oracle, G):
   vox, fu, fd = G["tsdf_args"]
   vol = oracle.tsdf_new_volume(G["tsdf_dim"])

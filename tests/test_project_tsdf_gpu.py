@@ -7,6 +7,31 @@ from lidar_transfer_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("seed,n,H,n_ba,remove", [(5, 4000, 16, 16, True), (6, 124668, 64, 64, True),
+                                                  (7, 30000, 32, 7, False), (8, 3000, 8, 1, False)])
+def test_projection_with_beam_angles_matches_oracle(engine, oracle, seed, n, H, n_ba, remove):
+  """vl_project_snap vs the oracle's restatement of laserscan.py:321-327 (itself pinned to the reference's Python by
+  tests/golden/golden_beams_v1.npz); a list with duplicate and equidistant entries exercises argmin's first-minimum
+  rule."""
+  fu, fd, W = 3.0, -25.0, 512
+  pts, labels = synth.make_scan_points(seed, n)
+  points = pts[:, :3].astype(np.float64)
+  points[::89] = 0.0
+  rng = np.random.default_rng(seed)
+  ba = np.sort(np.concatenate([np.linspace(fd, fu, n_ba) / 180.0 * np.pi, rng.uniform(-0.5, 0.1, 3)])).tolist()
+  ba = ba + ba[:2]  # duplicates after the first occurrence must never win
+  ref = oracle.project(points, pts[:, 3], labels, fu, fd, H, W, remove=remove, beam_angles=ba)
+  got = engine.project(points, pts[:, 3], labels, fu, fd, H, W, remove=remove, beam_angles=ba)
+  assert int(got["n_kept"].item()) == ref["n_kept"] > 0
+  assert np.array_equal(got["keep"].cpu().numpy(), ref["keep"])
+  for k in ("index", "proj_label"):
+    assert np.array_equal(got[k].cpu().numpy(), ref[k]), k
+  for k in ("range_image", "proj_remissions"):
+    assert np.array_equal(got[k].cpu().numpy().view(np.int32), ref[k].view(np.int32)), k
+  plain = engine.project(points, pts[:, 3], labels, fu, fd, H, W, remove=remove)
+  assert not np.array_equal(plain["index"].cpu().numpy(), ref["index"])
+
+
 @pytest.mark.parametrize("seed,n,H,W,fu,fd", [(1, 5000, 16, 128, 3.0, -25.0), (2, 124668, 64, 2048, 3.0, -25.0),
                                              (3, 124668, 64, 2048, 10.67, -30.67)])
 def test_projection_matches_oracle(engine, oracle, seed, n, H, W, fu, fd):
@@ -134,6 +159,80 @@ def test_tsdf_column_table_gives_the_same_bits(engine, oracle, vox, bnds):
   for k in ("tsdf", "weight", "color", "rem"):
     assert torch.equal(getattr(a, k).view(torch.int32), getattr(b, k).view(torch.int32)), k
   assert int((a.tsdf != 1).sum()) > 300
+
+
+@pytest.mark.parametrize("case", ["c1", "zero_labels", "bad_depths", "origin_inside", "fine_rows", "too_fine_rows", "steep_fov",
+                                  "os1", "odd_dz"])
+def test_tsdf_fresh_shell_sweep_gives_the_same_bits(engine, oracle, case):
+  """The first integration into a new volume (vl_tsdf_init_integrate) brackets every voxel against the range image's
+  [depth, depth + trunc] shell and evaluates the reference arithmetic only where an update cannot be ruled out:
+  all four volumes must equal, bit for bit, (a) the same call with the shell sweep switched off, (b) the sweep with
+  one voxel per thread instead of four and (c) the per-voxel kernel on a volume reset by vl_tsdf_init.  Cases: the
+  config-1 volume (284 M voxels, float index decode beyond 2^24), pixels of label 0 (their voxels IN FRONT of the
+  surface are written too), NaN / inf / negative depths, a volume around the sensor (the origin voxel's NaN pitch),
+  512 image rows (a third of the voxels have two candidate rows) and 1024 (finer than the bracket: the sweep must
+  decline), fields of view at and beyond the arcsine series' range, dz % 4 != 0."""
+  import torch
+  from lidar_transfer_b200._lib import lib
+  H, W, fu, fd, vox = 64, 1024, 3.0, -25.0, 0.25
+  bnds = [[-20, 20], [-16.1, 16], [-3, 2]]
+  n_pts, seed = 60000, 21
+  if case == "c1":
+    H, W, vox, bnds, n_pts = 64, 2048, 0.05, [[-50, 50], [-35.5, 35.5], [-3.5, 1.5]], 124668
+  elif case == "fine_rows":
+    H, W = 512, 256
+  elif case == "too_fine_rows":
+    H, W = 1024, 128
+  elif case == "odd_dz":
+    bnds, vox = [[-20, 20], [-16.1, 16], [-3, 2.1]], 0.3   # 134 x 108 x 17 voxels
+  elif case == "steep_fov":
+    fu, fd = 10.67, -30.67
+  elif case == "os1":
+    H, fu, fd = 128, 22.5, -22.5
+  elif case == "origin_inside":
+    bnds, vox = [[-4, 4], [-4, 4], [-2, 2]], 0.125   # origin is a voxel corner: pt == (0, 0, 0) for one voxel
+  pts, labels = synth.make_scan_points(seed, n_pts)
+  if case == "origin_inside":
+    pts[:, :3] *= 0.08
+  pr = oracle.project(pts[:, :3].astype(np.float64), pts[:, 3], labels, fu, fd, H, W)
+  lab, depth = pr["proj_label"].copy(), pr["range_image"].copy()
+  rng = np.random.default_rng(seed)
+  if case == "zero_labels":
+    lab[rng.random(lab.shape) < 0.3] = 0
+  if case == "bad_depths":
+    r = rng.random(depth.shape)
+    depth[r < 0.02] = np.nan
+    depth[(r >= 0.02) & (r < 0.04)] = np.inf
+    depth[(r >= 0.04) & (r < 0.06)] = -3.0
+    depth[(r >= 0.06) & (r < 0.08)] = 1e-3
+  color_im = oracle.label_to_color_im(lab)
+  bnds = np.array(bnds, np.float64)
+  dim = np.ceil((bnds[:, 1] - bnds[:, 0]) / vox).astype(int)
+  origin = bnds[:, 0].astype(np.float32)
+  vols = {}
+  for tag, mode in (("shell", 1), ("shell1", 2), ("plain", 0)):
+    lib().vl_debug_tsdf_shell(mode)
+    try:
+      d = engine.TsdfDevice(dim, origin, vox, fu, fd)
+      d.integrate(color_im, depth, pr["proj_remissions"])
+      vols[tag] = [getattr(d, k).view(torch.int32).clone() for k in ("tsdf", "weight", "color", "rem")]
+      del d
+    finally:
+      lib().vl_debug_tsdf_shell(1)
+  for other in ("plain", "shell1"):
+    for k, a, b in zip(("tsdf", "weight", "color", "rem"), vols["shell"], vols[other]):
+      assert torch.equal(a, b), (case, other, k, int((a != b).sum()))
+    del vols[other]
+  if case == "odd_dz":
+    assert dim[2] % 4 != 0
+  d = engine.TsdfDevice(dim, origin, vox, fu, fd)
+  d.integrate(color_im, depth, pr["proj_remissions"], use_column_table=False)   # vl_tsdf_init + the per-voxel kernel
+  n_changed = int((d.tsdf != 1).sum())
+  for k, a in zip(("tsdf", "weight", "color", "rem"), vols["shell"]):
+    assert torch.equal(a, getattr(d, k).view(torch.int32)), (case, k)
+  assert n_changed > (50 if case == "origin_inside" else 300), n_changed
+  if case == "zero_labels":
+    assert int(((d.weight > 0) & (d.tsdf == 1)).sum()) > 1000   # free space in front of label-0 pixels: weight 1, tsdf 1
 
 
 def test_reverse_projection_on_device_matches_reference_golden(engine):

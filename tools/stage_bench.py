@@ -9,6 +9,8 @@ from lidar_transfer_b200 import synth, engine, _lib
 from lidar_transfer_b200.rays import create_rays
 
 L = _lib.lib()
+if os.environ.get("VL_TSDF_SHELL") == "0":   # first integration without the shell sweep, for comparison
+  L.vl_debug_tsdf_shell(0)
 H, W, fu, fd = 64, 2048, 3.0, -25.0
 vox = float(sys.argv[1]) if len(sys.argv) > 1 else 0.05
 pts, labels = synth.make_scan_points(1, 124668)
