@@ -176,6 +176,174 @@ k_mesh_count4(const float* __restrict__ tsdf, const MeshParams P, int units_per_
   }
 }
 
+// ---- the same counts from a BIT volume ----------------------------------------------------------------------------
+//
+// A cube's case index only needs one bit per corner (value < level), and 98 % of the cubes have all eight equal.
+//   k_mesh_bits        reads the TSDF volume ONCE (128-bit loads, one comparison per voxel) and leaves 1 bit per voxel:
+//                      plane x = words [x * pw, (x + 1) * pw), bit j = y * dz + z of the plane
+//   k_mesh_count_bits  32 cubes per word operation: the corner rows (x, y), (x + 1, y), (x, y + 1), (x + 1, y + 1) at
+//                      z and z + 1 are eight funnel-shifted views of the two planes; active = OR of the eight AND NOT
+//                      AND of the eight AND valid; only the active bits are expanded into a case index.  Same unit
+//                      totals as k_mesh_count (a warp unit = 64 words, two per lane).
+//   k_mesh_compact_bits the same sweep once more, writing (voxel index, first triangle slot) in cube order.
+// No case byte per voxel is stored: k_mesh_emit forms the index from the eight corner values it loads anyway.
+struct CubeWords { unsigned int c[8]; unsigned int active; };
+
+__device__ __forceinline__ unsigned int bits_at(const unsigned int* __restrict__ plane, int pw, int bit) {
+  const int k = bit >> 5;
+  return __funnelshift_r(__ldg(plane + min(k, pw - 1)), __ldg(plane + min(k + 1, pw - 1)), bit & 31);
+}
+
+// word w of plane p0 (p1 = plane x + 1): corner-row bit words and the mask of cubes that carry triangles' candidates.
+// Reads clamped to the plane: bits fetched for cubes outside the valid range are masked out.
+__device__ __forceinline__ CubeWords cube_words(const unsigned int* __restrict__ p0, const unsigned int* __restrict__ p1,
+                                                int pw, int w, int dy, int dz) {
+  CubeWords cw;
+  const int j0 = 32 * w;
+  cw.c[0] = __ldg(p0 + w);            cw.c[1] = __ldg(p1 + w);
+  cw.c[2] = bits_at(p0, pw, j0 + dz); cw.c[3] = bits_at(p1, pw, j0 + dz);
+  cw.c[4] = bits_at(p0, pw, j0 + 1);  cw.c[5] = bits_at(p1, pw, j0 + 1);
+  cw.c[6] = bits_at(p0, pw, j0 + dz + 1); cw.c[7] = bits_at(p1, pw, j0 + dz + 1);
+  unsigned int any = 0u, all = 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { any |= cw.c[k]; all &= cw.c[k]; }
+  unsigned int act = any & ~all;
+  if (act) {
+    const int rows_left = (dy - 1) * dz - j0;                 // cubes with y + 1 < dy: j < (dy - 1) * dz
+    unsigned int valid = rows_left >= 32 ? 0xffffffffu : (rows_left <= 0 ? 0u : ((1u << rows_left) - 1u));
+    for (int b = dz - 1 - j0 % dz; b < 32; b += dz) valid &= ~(1u << b);   // z + 1 < dz
+    act &= valid;
+  }
+  cw.active = act;
+  return cw;
+}
+
+__device__ __forceinline__ int cube_case(const CubeWords& cw, int b) {
+  int m = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m |= (int)((cw.c[k] >> b) & 1u) << k;
+  return m;
+}
+
+template <int kVec>
+__global__ void __launch_bounds__(kThreads)
+k_mesh_bits(const float* __restrict__ tsdf, const MeshParams P, int pw, unsigned int* __restrict__ bits) {
+  const int lane = threadIdx.x & 31;
+  const int x = blockIdx.y, yz = P.dy * P.dz;
+  const float* plane = tsdf + (size_t)x * yz;
+  unsigned int* out = bits + (size_t)x * pw;
+  const float L = P.level;
+  const int warp = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  constexpr int kWordsPerWarp = 128;                          // 4096 voxels
+  const int w0 = warp * kWordsPerWarp;
+  if (w0 >= pw) return;
+  if (kVec == 4) {
+    // a step = 128 voxels = 4 words: lane l holds voxels 4 l .. 4 l + 3, eight lanes make a word
+#pragma unroll 4
+    for (int s = 0; s < kWordsPerWarp / 4; ++s) {
+      const int j = 32 * w0 + 128 * s + 4 * lane;
+      unsigned int n = 0u;
+      if (j < yz) {                                           // yz % 4 == 0: all four or none
+        const float4 v = __ldg(reinterpret_cast<const float4*>(plane + j));
+        n = (v.x < L ? 1u : 0u) | (v.y < L ? 2u : 0u) | (v.z < L ? 4u : 0u) | (v.w < L ? 8u : 0u);
+      }
+      const unsigned int word = __reduce_or_sync(0xffu << (lane & 24), n << (4 * (lane & 7)));
+      const int w = w0 + 4 * s + (lane >> 3);
+      if ((lane & 7) == 0 && w < pw) out[w] = word;
+    }
+  } else {
+#pragma unroll 4
+    for (int s = 0; s < kWordsPerWarp; ++s) {
+      const int w = w0 + s;
+      if (w >= pw) break;
+      const int j = 32 * w + lane;
+      const unsigned int word = __ballot_sync(0xffffffffu, j < yz && __ldg(plane + j) < L);
+      if (lane == 0) out[w] = word;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_mesh_count_bits(const unsigned int* __restrict__ bits, const MeshParams P, int pw, int units_per_plane,
+                  int* __restrict__ unit_tris, int* __restrict__ unit_active) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int u = blockIdx.x * kWarps + wid;
+  if (u >= units_per_plane) return;  // warp-uniform
+  const int x = blockIdx.y;
+  int n_tris = 0, n_active = 0;
+  if (x + 1 < P.dx) {
+    const unsigned int* p0 = bits + (size_t)x * pw;
+    const unsigned int* p1 = p0 + pw;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int w = u * (kUnit / 32) + 2 * lane + h;
+      if (w >= pw) break;
+      const CubeWords cw = cube_words(p0, p1, pw, w, P.dy, P.dz);
+      for (unsigned int a = cw.active; a; a &= a - 1) {
+        const int cnt = c_tri_count[cube_case(cw, __ffs(a) - 1)];
+        n_tris += cnt;
+        n_active += cnt > 0 ? 1 : 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    n_tris += __shfl_xor_sync(0xffffffffu, n_tris, off);
+    n_active += __shfl_xor_sync(0xffffffffu, n_active, off);
+  }
+  if (lane == 0) {
+    unit_tris[x * units_per_plane + u] = n_tris;
+    unit_active[x * units_per_plane + u] = n_active;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_mesh_compact_bits(const unsigned int* __restrict__ bits, const MeshParams P, int pw, int units_per_plane,
+                    const int* __restrict__ unit_tris, const long long* __restrict__ tri_offset,
+                    const long long* __restrict__ act_offset, long long n_active, uint2* __restrict__ list) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int u = blockIdx.x * kWarps + wid;
+  if (u >= units_per_plane) return;
+  const int x = blockIdx.y, yz = P.dy * P.dz;
+  const int unit = x * units_per_plane + u;
+  if (unit_tris[unit] == 0) return;  // nothing active in this unit (covers x + 1 == dx)
+  const unsigned int* p0 = bits + (size_t)x * pw;
+  const unsigned int* p1 = p0 + pw;
+  CubeWords cw[2];
+  int tris = 0, act = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int w = u * (kUnit / 32) + 2 * lane + h;
+    cw[h].active = 0u;
+    if (w < pw) cw[h] = cube_words(p0, p1, pw, w, P.dy, P.dz);
+    for (unsigned int a = cw[h].active; a; a &= a - 1) {
+      const int cnt = c_tri_count[cube_case(cw[h], __ffs(a) - 1)];
+      tris += cnt;
+      act += cnt > 0 ? 1 : 0;
+    }
+  }
+  int it = tris, ia = act;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, it, off), b = __shfl_up_sync(0xffffffffu, ia, off);
+    if (lane >= off) { it += a; ia += b; }
+  }
+  long long slot = act_offset[unit] + (ia - act), tri = tri_offset[unit] + (it - tris);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j0 = 32 * (u * (kUnit / 32) + 2 * lane + h);
+    for (unsigned int a = cw[h].active; a; a &= a - 1) {
+      const int b = __ffs(a) - 1;
+      const int cnt = c_tri_count[cube_case(cw[h], b)];
+      if (cnt > 0) {
+        if (slot < n_active) list[slot] = make_uint2((unsigned int)(x * yz + j0 + b), (unsigned int)tri);
+        ++slot;
+        tri += cnt;
+      }
+    }
+  }
+}
+
 // exclusive scans of both unit totals in three steps: every CTA scans 8192 units locally (8 consecutive units per
 // thread) and leaves its totals, one CTA scans the block totals, every unit adds its block's offset;
 // totals[0] = triangles, totals[1] = active cubes
@@ -309,19 +477,22 @@ k_mesh_compact(const MeshParams P, int units_per_plane, const unsigned char* __r
 
 __global__ void __launch_bounds__(kThreads)
 k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol, const float* __restrict__ rem_vol,
-            const MeshParams P, const unsigned char* __restrict__ cases, const uint2* __restrict__ list, long long n_active,
+            const MeshParams P, const uint2* __restrict__ list, long long n_active,
             long long capacity, float* __restrict__ verts, int* __restrict__ faces, float* __restrict__ norms,
             unsigned char* __restrict__ colors, float* __restrict__ rem_out) {
   const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n_active) return;
   const uint2 ent = list[i];
   const int vi = (int)ent.x, yz = P.dy * P.dz;
-  const int mc = cases[vi];
   const int x = vi / yz, jj = vi - x * yz, y = jj / P.dz, z = jj - y * P.dz;
   const float* cube0 = tsdf + vi;
   float v[8];
+  int mc = 0;   // case index: bit c set when corner c (bit 0 x, bit 1 y, bit 2 z) is below the level
 #pragma unroll
-  for (int c = 0; c < 8; ++c) v[c] = __ldg(cube0 + (size_t)(c & 1) * yz + ((c >> 1) & 1) * P.dz + ((c >> 2) & 1));
+  for (int c = 0; c < 8; ++c) {
+    v[c] = __ldg(cube0 + (size_t)(c & 1) * yz + ((c >> 1) & 1) * P.dz + ((c >> 2) & 1));
+    mc |= v[c] < P.level ? (1 << c) : 0;
+  }
   const int cnt = c_tri_count[mc];
   for (int t = 0; t < cnt; ++t) {
     const long long tri = (long long)ent.y + t;
@@ -383,14 +554,19 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
 
 }  // namespace
 
-static int g_mesh_scalar = 0;   // vl_debug_mesh_scalar(): force the one-cube-per-lane sweep (tests compare the two)
-extern "C" void vl_debug_mesh_scalar(int on) { g_mesh_scalar = on ? 1 : 0; }
+// vl_debug_mesh_scalar(mode), tests compare all four: 0 bit-volume sweep (128-bit loads when dz % 4 == 0), 1 the same
+// with scalar loads, 2 / 3 the case-byte sweep (k_mesh_count4 / k_mesh_count + k_mesh_compact), the previous
+// formulation, kept for comparison.  Set it before vl_mesh_workspace_bytes: modes 2 / 3 need a byte per voxel.
+static int g_mesh_mode = 0;
+extern "C" void vl_debug_mesh_scalar(int mode) { g_mesh_mode = mode >= 0 && mode <= 3 ? mode : 0; }
+#define g_mesh_scalar (g_mesh_mode == 3)
+static int mesh_plane_words(int dy, int dz) { return (int)(((long long)dy * dz + 31) / 32); }
 
 static int mesh_units_per_plane(int dy, int dz) { return (int)(((long long)dy * dz + kUnit - 1) / kUnit); }
 
 // workspace: [unit triangle counts i32][unit active counts i32][triangle offsets i64][active offsets i64]
-//            [scan-block offsets 2 x i64][case byte per voxel]
-struct MeshWs { size_t tris, active, tri_off, act_off, blk_tri, blk_act, cases, total; int n_scan_blocks; };
+//            [scan-block offsets 2 x i64][bit per voxel, plane-wise | case byte per voxel (modes 2 / 3)]
+struct MeshWs { size_t tris, active, tri_off, act_off, blk_tri, blk_act, cases, bits, total; int n_scan_blocks; };
 static MeshWs mesh_ws_layout(int dx, int dy, int dz) {
   const size_t n_units = (size_t)dx * mesh_units_per_plane(dy, dz);
   MeshWs w;
@@ -402,7 +578,8 @@ static MeshWs mesh_ws_layout(int dx, int dy, int dz) {
   w.n_scan_blocks = (int)((n_units + kScanBlockUnits - 1) / kScanBlockUnits);
   w.blk_tri = off; off = vl_align256(off + (size_t)w.n_scan_blocks * 8);
   w.blk_act = off; off = vl_align256(off + (size_t)w.n_scan_blocks * 8);
-  w.cases = off;   off = vl_align256(off + (size_t)dx * dy * dz);
+  w.cases = w.bits = off;
+  off = vl_align256(off + (g_mesh_mode >= 2 ? (size_t)dx * dy * dz : 4 * (size_t)dx * mesh_plane_words(dy, dz)));
   w.total = off;
   return w;
 }
@@ -439,15 +616,29 @@ extern "C" int vl_mesh_count(const float* d_tsdf, int dx, int dy, int dz, float 
   const MeshWs w = mesh_ws_layout(dx, dy, dz);
   char* ws = static_cast<char*>(d_workspace);
   { VlProfScope ps(VL_ST_MESH_COUNT, stream);
+  const dim3 grid((upp + kWarps - 1) / kWarps, dx);
+  if (g_mesh_mode < 2) {
+    const int pw = mesh_plane_words(dy, dz);
+    unsigned int* bits = reinterpret_cast<unsigned int*>(ws + w.bits);
+    const dim3 bgrid((pw + 128 * kWarps - 1) / (128 * kWarps), dx);
+    if (g_mesh_mode == 0 && ((long long)dy * dz) % 4 == 0 && ((uintptr_t)d_tsdf & 15) == 0)
+      k_mesh_bits<4><<<bgrid, kThreads, 0, stream>>>(d_tsdf, P, pw, bits);
+    else
+      k_mesh_bits<1><<<bgrid, kThreads, 0, stream>>>(d_tsdf, P, pw, bits);
+    VL_LAUNCH_CHECK("k_mesh_bits");
+    k_mesh_count_bits<<<grid, kThreads, 0, stream>>>(bits, P, pw, upp, reinterpret_cast<int*>(ws + w.tris),
+                                                    reinterpret_cast<int*>(ws + w.active));
+  } else {
   const bool vec4 = !g_mesh_scalar && dz % 4 == 0 && ((uintptr_t)d_tsdf & 15) == 0;   // cases start 256-byte aligned
   if (vec4)
-    k_mesh_count4<<<dim3((upp + kWarps - 1) / kWarps, dx), kThreads, 0, stream>>>(
+    k_mesh_count4<<<grid, kThreads, 0, stream>>>(
         d_tsdf, P, upp, reinterpret_cast<int*>(ws + w.tris), reinterpret_cast<int*>(ws + w.active),
         reinterpret_cast<unsigned char*>(ws + w.cases));
   else
-    k_mesh_count<<<dim3((upp + kWarps - 1) / kWarps, dx), kThreads, 0, stream>>>(
+    k_mesh_count<<<grid, kThreads, 0, stream>>>(
         d_tsdf, P, upp, reinterpret_cast<int*>(ws + w.tris), reinterpret_cast<int*>(ws + w.active),
-        reinterpret_cast<unsigned char*>(ws + w.cases)); }
+        reinterpret_cast<unsigned char*>(ws + w.cases));
+  } }
   VL_LAUNCH_CHECK("k_mesh_count");
   { VlProfScope ps(VL_ST_MESH_SCAN, stream);
   const int n_units = upp * dx;
@@ -491,12 +682,15 @@ extern "C" int vl_mesh_emit(const float* d_tsdf, const float* d_color, const flo
   const int* ut = reinterpret_cast<const int*>(ws + w.tris);
   const long long* to = reinterpret_cast<const long long*>(ws + w.tri_off);
   const long long* ao = reinterpret_cast<const long long*>(ws + w.act_off);
-  if (!g_mesh_scalar && ((long long)dy * dz) % 4 == 0) k_mesh_compact<4><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list);
+  if (g_mesh_mode < 2)
+    k_mesh_compact_bits<<<grid, kThreads, 0, stream>>>(reinterpret_cast<const unsigned int*>(ws + w.bits), P,
+                                                      mesh_plane_words(dy, dz), upp, ut, to, ao, n_active, list);
+  else if (!g_mesh_scalar && ((long long)dy * dz) % 4 == 0) k_mesh_compact<4><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list);
   else k_mesh_compact<1><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list); }
   VL_LAUNCH_CHECK("k_mesh_compact");
   VlProfScope ps(VL_ST_MESH_EMIT, stream);
   k_mesh_emit<<<(unsigned)((n_active + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
-      d_tsdf, d_color, d_rem, P, cases, list, n_active, n_tris, d_verts, d_faces, d_norms, d_colors, d_rem_out);
+      d_tsdf, d_color, d_rem, P, list, n_active, n_tris, d_verts, d_faces, d_norms, d_colors, d_rem_out);
   VL_LAUNCH_CHECK("k_mesh_emit");
   return VL_OK;
 }

@@ -64,3 +64,15 @@ def test_identity_rerender_at_config1_size(engine):
   assert m2["faces"].shape[0] == n_t and torch.equal(m2["verts"], m["verts"]) and torch.equal(m2["colors"], m["colors"])
   for k in ("range", "endcolors", "endpoints", "endrem", "tri_id"):
     assert torch.equal(out2[k], out[k]), k
+  # ... and so do the previous formulations of the two volume sweeps (every voxel through the reference arithmetic in
+  # the first integration; case-byte mesh sweep), at the full 284 M voxels
+  from lidar_transfer_b200._lib import lib
+  lib().vl_debug_tsdf_shell(0); lib().vl_debug_mesh_scalar(2)
+  try:
+    pr3, m3, out3 = _chain(engine, beams, pts64, rem, labels, H, W, fu, fd, dim, origin0, vox)
+  finally:
+    lib().vl_debug_tsdf_shell(1); lib().vl_debug_mesh_scalar(0)
+  assert m3["faces"].shape[0] == n_t
+  for k in ("verts", "colors", "rem"):
+    assert torch.equal(m3[k], m[k]), k
+  assert torch.equal(out3["range"], out["range"]) and torch.equal(out3["tri_id"], out["tri_id"])
