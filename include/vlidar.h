@@ -257,7 +257,8 @@ void vl_debug_tsdf_shell(int mode);
  * flat normals), d_colors u8[9T] = (r, g, b) of the nearest voxel's folded colour with the
  * reference's uint8 wrap (:417-423), d_rem_out f32[3T].
  * ---------------------------------------------------------------------------------- */
-size_t vl_mesh_workspace_bytes(int dx, int dy, int dz);   /* ~1 byte per voxel (the cube case indices) */
+size_t vl_mesh_workspace_bytes(int dx, int dy, int dz);   /* ~1 bit per voxel + 24 B per 2048 voxels */
+size_t vl_mesh_list_bytes(long long n_tris, long long n_active);
 int vl_mesh_count(const float* d_tsdf, int dx, int dy, int dz, float level, void* d_workspace,
                   size_t workspace_bytes, long long* d_totals, vl_stream stream);
 int vl_mesh_emit(const float* d_tsdf, const float* d_color, const float* d_rem, int dx, int dy, int dz,

@@ -4,15 +4,19 @@
 // volumes to the host (3.4 GB at the default 284 M voxels), runs scikit-image's marching_cubes_lewiner on the
 // CPU (:407) and looks vertex colours / remissions up with numpy (:409-423).  Here the volumes stay in HBM:
 //
-//   k_mesh_count    a warp sweeps a unit of 2048 consecutive cubes of one yz-plane (cube index == voxel index of
-//                   its low corner): 4 corner reads per cube, the 4 corners one step up in z come from the
-//                   neighbour lane (lane 31: from the already prefetched next step); the 256-case index is kept
-//                   as one byte per cube; per-unit totals of triangles and of active cubes
-//   k_mesh_scan     exclusive scan of both unit totals (single CTA) -> unit offsets + grand totals
-//   k_mesh_compact  sweep over the case bytes: the active cubes (1-2 % of the volume) are written, in cube order,
-//                   as (voxel index, first triangle slot) -- warp ballots / shuffles only, no barriers, no atomics
-//   k_mesh_emit     one thread per ACTIVE cube writes its 1-5 triangles (dense warps, neighbouring threads write
-//                   neighbouring slots); output order = cube order, deterministic
+//   k_mesh_bits         reads the TSDF volume once and leaves one bit per voxel (value < level)
+//   k_mesh_count_bits   cube cases 32 at a time from funnel-shifted bit words; per-unit totals of triangles and of
+//                       active cubes (a unit = 2048 consecutive cubes of one yz-plane, cube index == voxel index of
+//                       its low corner)
+//   k_mesh_scan_*       exclusive scan of both unit totals -> unit offsets + grand totals
+//   k_mesh_compact_bits the same sweep again: the active cubes (1-2 % of the volume) are written, in cube order, as
+//                       (voxel index, first triangle slot) -- warp shuffles only, no barriers, no atomics -- plus,
+//                       per 256 triangle slots, the list index of the cube that holds the first of them
+//   k_mesh_emit         one thread per TRIANGLE (its cube by bisection over 256 list entries in shared memory),
+//                       outputs staged in shared memory and written as whole lines; output order = cube order,
+//                       deterministic
+//   (k_mesh_count / k_mesh_count4 / k_mesh_compact: the previous case-byte formulation, kept for comparison,
+//   vl_debug_mesh_scalar(2 / 3))
 //
 // Output is an indexed triangle SOUP: 3 vertices per triangle, faces = (3t, 3t+1, 3t+2).  Vertex positions,
 // world transform (verts * voxel_size + origin, float32, :412), nearest-voxel lookup (np.round = half-to-even,
@@ -29,9 +33,12 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kUnit = 2048;                      // cubes per warp unit (64 steps of 32)
 
-__constant__ signed char c_tri_table[256][15] = VL_MC_TRI_TABLE;
 __constant__ unsigned char c_tri_count[256] = VL_MC_TRI_COUNT;
 __constant__ unsigned char c_edge_corners[12][2] = VL_MC_EDGE_CORNERS;
+// k_mesh_emit indexes the triangle table with a different case per lane: a constant-bank access would be replayed per
+// distinct address, a cached global load is not
+__device__ const signed char g_tri_table[256][15] = VL_MC_TRI_TABLE;
+constexpr int kEmitTris = 256;                   // triangles per k_mesh_emit CTA
 
 struct MeshParams {
   int dx, dy, dz;
@@ -300,7 +307,8 @@ k_mesh_count_bits(const unsigned int* __restrict__ bits, const MeshParams P, int
 __global__ void __launch_bounds__(kThreads)
 k_mesh_compact_bits(const unsigned int* __restrict__ bits, const MeshParams P, int pw, int units_per_plane,
                     const int* __restrict__ unit_tris, const long long* __restrict__ tri_offset,
-                    const long long* __restrict__ act_offset, long long n_active, uint2* __restrict__ list) {
+                    const long long* __restrict__ act_offset, long long n_active, uint2* __restrict__ list,
+                    unsigned int* __restrict__ cta_first) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int u = blockIdx.x * kWarps + wid;
   if (u >= units_per_plane) return;
@@ -337,6 +345,8 @@ k_mesh_compact_bits(const unsigned int* __restrict__ bits, const MeshParams P, i
       const int cnt = c_tri_count[cube_case(cw[h], b)];
       if (cnt > 0) {
         if (slot < n_active) list[slot] = make_uint2((unsigned int)(x * yz + j0 + b), (unsigned int)tri);
+        const long long kb = (tri + kEmitTris - 1) / kEmitTris;   // the cube that holds triangle kb * kEmitTris
+        if (kb * kEmitTris < tri + cnt) cta_first[kb] = (unsigned int)slot;
         ++slot;
         tri += cnt;
       }
@@ -436,7 +446,8 @@ template <int kVec>
 __global__ void __launch_bounds__(kThreads)
 k_mesh_compact(const MeshParams P, int units_per_plane, const unsigned char* __restrict__ cases,
                const int* __restrict__ unit_tris, const long long* __restrict__ tri_offset,
-               const long long* __restrict__ act_offset, long long n_active, uint2* __restrict__ list) {
+               const long long* __restrict__ act_offset, long long n_active, uint2* __restrict__ list,
+               unsigned int* __restrict__ cta_first) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int u = blockIdx.x * kWarps + wid;
   if (u >= units_per_plane) return;
@@ -466,6 +477,8 @@ k_mesh_compact(const MeshParams P, int units_per_plane, const unsigned char* __r
     for (int k = 0; k < kVec; ++k) {
       if (cnt[k] > 0) {
         if (slot < n_active) list[slot] = make_uint2((unsigned int)(x * yz + j + k), (unsigned int)tri);
+        const long long kb = (tri + kEmitTris - 1) / kEmitTris;   // the cube that holds triangle kb * kEmitTris
+        if (kb * kEmitTris < tri + cnt[k]) cta_first[kb] = (unsigned int)slot;
         ++slot;
         tri += cnt[k];
       }
@@ -475,32 +488,53 @@ k_mesh_compact(const MeshParams P, int units_per_plane, const unsigned char* __r
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
+// One thread per TRIANGLE, kEmitTris consecutive triangle slots per CTA: cta_first[blockIdx.x] (left by the compaction)
+// is the list index of the cube that holds the CTA's first triangle; the next kEmitTris list entries cover all its
+// triangles (every listed cube has at least one), each thread finds its cube by bisection in shared memory.  The
+// outputs are staged in shared memory and leave as whole lines (the per-cube version wrote 36-byte pieces with a
+// different triangle count per lane).
+__global__ void __launch_bounds__(kEmitTris)
 k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol, const float* __restrict__ rem_vol,
             const MeshParams P, const uint2* __restrict__ list, long long n_active,
-            long long capacity, float* __restrict__ verts, int* __restrict__ faces, float* __restrict__ norms,
-            unsigned char* __restrict__ colors, float* __restrict__ rem_out) {
-  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n_active) return;
-  const uint2 ent = list[i];
-  const int vi = (int)ent.x, yz = P.dy * P.dz;
-  const int x = vi / yz, jj = vi - x * yz, y = jj / P.dz, z = jj - y * P.dz;
-  const float* cube0 = tsdf + vi;
-  float v[8];
-  int mc = 0;   // case index: bit c set when corner c (bit 0 x, bit 1 y, bit 2 z) is below the level
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    v[c] = __ldg(cube0 + (size_t)(c & 1) * yz + ((c >> 1) & 1) * P.dz + ((c >> 2) & 1));
-    mc |= v[c] < P.level ? (1 << c) : 0;
+            const unsigned int* __restrict__ cta_first, long long n_tris, float* __restrict__ verts,
+            int* __restrict__ faces, float* __restrict__ norms, unsigned char* __restrict__ colors,
+            float* __restrict__ rem_out, int vec_ok) {
+  __shared__ unsigned int s_first[kEmitTris], s_vi[kEmitTris];
+  __shared__ __align__(16) float s_v[kEmitTris * 9];
+  __shared__ float s_r[kEmitTris * 3];
+  __shared__ __align__(16) unsigned char s_c[kEmitTris * 9];
+  const int tid = threadIdx.x;
+  const long long T0 = (long long)blockIdx.x * kEmitTris;
+  const int nT = (int)min((long long)kEmitTris, n_tris - T0);
+  {
+    const long long sidx = (long long)cta_first[blockIdx.x] + tid;
+    uint2 ent = make_uint2(0u, 0xffffffffu);
+    if (sidx < n_active) ent = list[sidx];
+    s_vi[tid] = ent.x;
+    s_first[tid] = ent.y;
   }
-  const int cnt = c_tri_count[mc];
-  for (int t = 0; t < cnt; ++t) {
-    const long long tri = (long long)ent.y + t;
-    if (tri >= capacity) break;
+  __syncthreads();
+  float nx = 0.f, ny = 0.f, nz = 0.f;
+  if (tid < nT) {
+    const unsigned int T = (unsigned int)(T0 + tid);
+    int lo = 0;                                                // last entry whose first slot is <= T
+#pragma unroll
+    for (int step = kEmitTris / 2; step > 0; step >>= 1)
+      if (s_first[lo + step] <= T) lo += step;
+    const int vi = (int)s_vi[lo], t = (int)(T - s_first[lo]), yz = P.dy * P.dz;
+    const int x = vi / yz, jj = vi - x * yz, y = jj / P.dz, z = jj - y * P.dz;
+    const float* cube0 = tsdf + vi;
+    float v[8];
+    int mc = 0;   // case index: bit c set when corner c (bit 0 x, bit 1 y, bit 2 z) is below the level
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      v[c] = __ldg(cube0 + (size_t)(c & 1) * yz + ((c >> 1) & 1) * P.dz + ((c >> 2) & 1));
+      mc |= v[c] < P.level ? (1 << c) : 0;
+    }
     float pw[3][3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const int e = c_tri_table[mc][3 * t + k];
+      const int e = __ldg(&g_tri_table[mc][3 * t + k]);
       const int ca = c_edge_corners[e][0], cb = c_edge_corners[e][1];
       // vertex on the edge ca -> cb (cb = ca + one axis step), float32 like skimage's output
       float va = v[0], vb = v[0];
@@ -522,33 +556,58 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
       const float cb_ = floorf(__fdiv_rn(rgb, 65536.0f));
       const float cg_ = floorf(__fdiv_rn(__fsub_rn(rgb, __fmul_rn(cb_, 65536.0f)), 256.0f));
       const float cr_ = __fsub_rn(__fsub_rn(rgb, __fmul_rn(cb_, 65536.0f)), __fmul_rn(cg_, 256.0f));
-      const long long vtx = 3 * tri + k;
-      colors[3 * vtx + 0] = (unsigned char)((long long)floorf(cr_) & 255);
-      colors[3 * vtx + 1] = (unsigned char)((long long)floorf(cg_) & 255);
-      colors[3 * vtx + 2] = (unsigned char)((long long)floorf(cb_) & 255);
-      rem_out[vtx] = __ldg(rem_vol + ni);
+      const int vtx = 3 * tid + k;                             // vertex slot within the CTA
+      s_c[3 * vtx + 0] = (unsigned char)((long long)floorf(cr_) & 255);
+      s_c[3 * vtx + 1] = (unsigned char)((long long)floorf(cg_) & 255);
+      s_c[3 * vtx + 2] = (unsigned char)((long long)floorf(cb_) & 255);
+      s_r[vtx] = __ldg(rem_vol + ni);
       // :412 verts * voxel_size + origin
       pw[k][0] = __fadd_rn(__fmul_rn(pv[0], P.voxel_size), P.ox);
       pw[k][1] = __fadd_rn(__fmul_rn(pv[1], P.voxel_size), P.oy);
       pw[k][2] = __fadd_rn(__fmul_rn(pv[2], P.voxel_size), P.oz);
-      verts[3 * vtx + 0] = pw[k][0];
-      verts[3 * vtx + 1] = pw[k][1];
-      verts[3 * vtx + 2] = pw[k][2];
-      faces[vtx] = (int)vtx;
+      s_v[3 * vtx + 0] = pw[k][0];
+      s_v[3 * vtx + 1] = pw[k][1];
+      s_v[3 * vtx + 2] = pw[k][2];
     }
     if (norms) {  // flat normal of the triangle for all three vertices (only consumed by meshwrite)
       const float ax = pw[1][0] - pw[0][0], ay = pw[1][1] - pw[0][1], az = pw[1][2] - pw[0][2];
       const float bx = pw[2][0] - pw[0][0], by = pw[2][1] - pw[0][1], bz = pw[2][2] - pw[0][2];
-      float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+      nx = ay * bz - az * by; ny = az * bx - ax * bz; nz = ax * by - ay * bx;
       const float nn = sqrtf(nx * nx + ny * ny + nz * nz);
       if (nn > 0.f) { nx /= nn; ny /= nn; nz /= nn; }
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        norms[3 * (3 * tri + k) + 0] = nx;
-        norms[3 * (3 * tri + k) + 1] = ny;
-        norms[3 * (3 * tri + k) + 2] = nz;
-      }
     }
+  }
+  __syncthreads();
+  const bool full = vec_ok && nT == kEmitTris;
+  auto put9 = [&](float* __restrict__ dst) {                   // s_v -> 9 floats per triangle of this CTA
+    if (full) {
+      float4* d4 = reinterpret_cast<float4*>(dst + 9 * T0);
+      const float4* s4 = reinterpret_cast<const float4*>(s_v);
+      for (int i = tid; i < kEmitTris * 9 / 4; i += kEmitTris) d4[i] = s4[i];
+    } else {
+      for (int i = tid; i < 9 * nT; i += kEmitTris) dst[9 * T0 + i] = s_v[i];
+    }
+  };
+  put9(verts);
+  for (int i = tid; i < 3 * nT; i += kEmitTris) {
+    faces[3 * T0 + i] = (int)(3 * T0 + i);
+    rem_out[3 * T0 + i] = s_r[i];
+  }
+  if (full) {
+    unsigned int* d = reinterpret_cast<unsigned int*>(colors + 9 * T0);
+    const unsigned int* sc = reinterpret_cast<const unsigned int*>(s_c);
+    for (int i = tid; i < kEmitTris * 9 / 4; i += kEmitTris) d[i] = sc[i];
+  } else {
+    for (int i = tid; i < 9 * nT; i += kEmitTris) colors[9 * T0 + i] = s_c[i];
+  }
+  if (norms) {
+    __syncthreads();
+    if (tid < nT) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { s_v[9 * tid + 3 * k] = nx; s_v[9 * tid + 3 * k + 1] = ny; s_v[9 * tid + 3 * k + 2] = nz; }
+    }
+    __syncthreads();
+    put9(norms);
   }
 }
 
@@ -657,6 +716,11 @@ extern "C" int vl_mesh_count(const float* d_tsdf, int dx, int dy, int dz, float 
   return VL_OK;
 }
 
+extern "C" size_t vl_mesh_list_bytes(long long n_tris, long long n_active) {
+  if (n_tris < 0 || n_active < 0) return 256;
+  return vl_align256(8 * (size_t)n_active) + vl_align256(4 * (size_t)((n_tris + kEmitTris - 1) / kEmitTris + 1));
+}
+
 extern "C" int vl_mesh_emit(const float* d_tsdf, const float* d_color, const float* d_rem, int dx, int dy, int dz,
                             float level, float voxel_size, const float vol_origin[3], const void* d_workspace,
                             size_t workspace_bytes, long long n_tris, long long n_active, void* d_active_list,
@@ -677,6 +741,7 @@ extern "C" int vl_mesh_emit(const float* d_tsdf, const float* d_color, const flo
   const char* ws = static_cast<const char*>(d_workspace);
   const unsigned char* cases = reinterpret_cast<const unsigned char*>(ws + w.cases);
   uint2* list = static_cast<uint2*>(d_active_list);
+  unsigned int* cta_first = reinterpret_cast<unsigned int*>(static_cast<char*>(d_active_list) + vl_align256(8 * (size_t)n_active));
   { VlProfScope ps(VL_ST_MESH_COMPACT, stream);
   const dim3 grid((upp + kWarps - 1) / kWarps, dx);
   const int* ut = reinterpret_cast<const int*>(ws + w.tris);
@@ -684,13 +749,14 @@ extern "C" int vl_mesh_emit(const float* d_tsdf, const float* d_color, const flo
   const long long* ao = reinterpret_cast<const long long*>(ws + w.act_off);
   if (g_mesh_mode < 2)
     k_mesh_compact_bits<<<grid, kThreads, 0, stream>>>(reinterpret_cast<const unsigned int*>(ws + w.bits), P,
-                                                      mesh_plane_words(dy, dz), upp, ut, to, ao, n_active, list);
-  else if (!g_mesh_scalar && ((long long)dy * dz) % 4 == 0) k_mesh_compact<4><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list);
-  else k_mesh_compact<1><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list); }
+                                                      mesh_plane_words(dy, dz), upp, ut, to, ao, n_active, list, cta_first);
+  else if (!g_mesh_scalar && ((long long)dy * dz) % 4 == 0) k_mesh_compact<4><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list, cta_first);
+  else k_mesh_compact<1><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list, cta_first); }
   VL_LAUNCH_CHECK("k_mesh_compact");
   VlProfScope ps(VL_ST_MESH_EMIT, stream);
-  k_mesh_emit<<<(unsigned)((n_active + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
-      d_tsdf, d_color, d_rem, P, list, n_active, n_tris, d_verts, d_faces, d_norms, d_colors, d_rem_out);
+  const int vec_ok = ((((uintptr_t)d_verts) | ((uintptr_t)d_norms)) & 15) == 0 && (((uintptr_t)d_colors) & 3) == 0;
+  k_mesh_emit<<<(unsigned)((n_tris + kEmitTris - 1) / kEmitTris), kEmitTris, 0, stream>>>(
+      d_tsdf, d_color, d_rem, P, list, n_active, cta_first, n_tris, d_verts, d_faces, d_norms, d_colors, d_rem_out, vec_ok);
   VL_LAUNCH_CHECK("k_mesh_emit");
   return VL_OK;
 }

@@ -348,7 +348,7 @@ class TsdfDevice:
                  norms=torch.empty((3 * n_t, 3), dtype=torch.float32, device=dev) if want_norms else None,
                  colors=torch.empty((3 * n_t, 3), dtype=torch.uint8, device=dev),
                  rem=torch.empty(3 * n_t, dtype=torch.float32, device=dev))
-      active = torch.empty(max(n_a, 1), dtype=torch.int64, device=dev)
+      active = torch.empty(lib().vl_mesh_list_bytes(n_t, n_a), dtype=torch.uint8, device=dev)   # scratch of vl_mesh_emit
       check(lib().vl_mesh_emit(_ptr(self.tsdf), _ptr(self.color), _ptr(self.rem), self.dim[0], self.dim[1], self.dim[2],
                                float(level), self.voxel_size, origin, _ptr(ws), ws.numel(), n_t, n_a, _ptr(active),
                                _ptr(out["verts"]), _ptr(out["faces"]), _ptr(out["norms"]), _ptr(out["colors"]),
