@@ -38,6 +38,7 @@ __constant__ unsigned char c_edge_corners[12][2] = VL_MC_EDGE_CORNERS;
 // k_mesh_emit indexes the triangle table with a different case per lane: a constant-bank access would be replayed per
 // distinct address, a cached global load is not
 __device__ const signed char g_tri_table[256][15] = VL_MC_TRI_TABLE;
+__device__ const unsigned char g_tri_count[256] = VL_MC_TRI_COUNT;
 constexpr int kEmitTris = 256;                   // triangles per k_mesh_emit CTA
 
 struct MeshParams {
@@ -225,11 +226,70 @@ __device__ __forceinline__ CubeWords cube_words(const unsigned int* __restrict__
   return cw;
 }
 
-__device__ __forceinline__ int cube_case(const CubeWords& cw, int b) {
+// The active cubes of a warp unit, 32 at a time.  Lane l holds the two words 2 l, 2 l + 1 of the unit (cw[0], cw[1]);
+// a lane looping over its own bits would keep 2-3 lanes of the warp busy (the surface crosses each 32-cube word at most
+// once or twice, but somewhere in the warp a lane has several).  Instead the warp ranks all active cubes of the unit in
+// cube order (excl = exclusive prefix of the per-lane counts) and lane i of a batch takes the cube of rank `want`: the
+// owner lane by bisection over excl, the word and the bit by rank, the eight corner bits by shuffles from the owner.
+struct ActiveCube { int pos, m; bool ok; };   // pos: cube index within the unit, m: case index
+
+__device__ __forceinline__ ActiveCube nth_active(const CubeWords (&cw)[2], int excl, int total, int want) {
+  ActiveCube r;
+  r.ok = want < total;
+  int o = 0;                                               // the last lane whose prefix is <= want
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1) {
+    const int p = __shfl_sync(0xffffffffu, excl, o + step);
+    if (p <= want) o += step;
+  }
+  int rnk = want - __shfl_sync(0xffffffffu, excl, o);
+  const unsigned int a0 = __shfl_sync(0xffffffffu, cw[0].active, o), a1 = __shfl_sync(0xffffffffu, cw[1].active, o);
+  const int n0 = __popc(a0);
+  const int h = rnk >= n0 ? 1 : 0;
+  const unsigned int act = h ? a1 : a0;
+  rnk -= h ? n0 : 0;
+  int b = 0;                                               // position of the set bit of rank rnk in act
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    const int c = __popc((act >> b) & ((1u << sft) - 1u));
+    if (rnk >= c) { b += sft; rnk -= c; }
+  }
+  b &= 31;                                                 // lanes beyond the total carry no cube (masked by ok)
   int m = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) m |= (int)((cw.c[k] >> b) & 1u) << k;
-  return m;
+  for (int k = 0; k < 8; ++k) {
+    const unsigned int c0 = __shfl_sync(0xffffffffu, cw[0].c[k], o), c1 = __shfl_sync(0xffffffffu, cw[1].c[k], o);
+    m |= (int)(((h ? c1 : c0) >> b) & 1u) << k;
+  }
+  r.pos = 64 * o + 32 * h + b;
+  r.m = m;
+  return r;
+}
+
+// both words of this lane + the exclusive prefix / total of the active-cube counts over the warp
+__device__ __forceinline__ void unit_words(const unsigned int* __restrict__ p0, const unsigned int* __restrict__ p1, int pw,
+                                           int u, int lane, int dy, int dz, CubeWords (&cw)[2], int* excl, int* total) {
+  int n = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int w = u * (kUnit / 32) + 2 * lane + h;
+    if (w < pw) {
+      cw[h] = cube_words(p0, p1, pw, w, dy, dz);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cw[h].c[k] = 0u;
+      cw[h].active = 0u;
+    }
+    n += __popc(cw[h].active);
+  }
+  int incl = n;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += t;
+  }
+  *excl = incl - n;
+  *total = __shfl_sync(0xffffffffu, incl, 31);
 }
 
 template <int kVec>
@@ -273,6 +333,7 @@ k_mesh_bits(const float* __restrict__ tsdf, const MeshParams P, int pw, unsigned
 __global__ void __launch_bounds__(kThreads)
 k_mesh_count_bits(const unsigned int* __restrict__ bits, const MeshParams P, int pw, int units_per_plane,
                   int* __restrict__ unit_tris, int* __restrict__ unit_active) {
+  static_assert(kUnit == 2048, "a lane holds two 32-cube words of its warp's unit");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int u = blockIdx.x * kWarps + wid;
   if (u >= units_per_plane) return;  // warp-uniform
@@ -280,17 +341,14 @@ k_mesh_count_bits(const unsigned int* __restrict__ bits, const MeshParams P, int
   int n_tris = 0, n_active = 0;
   if (x + 1 < P.dx) {
     const unsigned int* p0 = bits + (size_t)x * pw;
-    const unsigned int* p1 = p0 + pw;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int w = u * (kUnit / 32) + 2 * lane + h;
-      if (w >= pw) break;
-      const CubeWords cw = cube_words(p0, p1, pw, w, P.dy, P.dz);
-      for (unsigned int a = cw.active; a; a &= a - 1) {
-        const int cnt = c_tri_count[cube_case(cw, __ffs(a) - 1)];
-        n_tris += cnt;
-        n_active += cnt > 0 ? 1 : 0;
-      }
+    CubeWords cw[2];
+    int excl, total;
+    unit_words(p0, p0 + pw, pw, u, lane, P.dy, P.dz, cw, &excl, &total);
+    for (int base = 0; base < total; base += 32) {   // warp-uniform
+      const ActiveCube ac = nth_active(cw, excl, total, base + lane);
+      const int cnt = ac.ok ? (int)__ldg(&g_tri_count[ac.m]) : 0;
+      n_tris += cnt;
+      n_active += cnt > 0 ? 1 : 0;
     }
   }
 #pragma unroll
@@ -316,41 +374,29 @@ k_mesh_compact_bits(const unsigned int* __restrict__ bits, const MeshParams P, i
   const int unit = x * units_per_plane + u;
   if (unit_tris[unit] == 0) return;  // nothing active in this unit (covers x + 1 == dx)
   const unsigned int* p0 = bits + (size_t)x * pw;
-  const unsigned int* p1 = p0 + pw;
   CubeWords cw[2];
-  int tris = 0, act = 0;
+  int excl, total;
+  unit_words(p0, p0 + pw, pw, u, lane, P.dy, P.dz, cw, &excl, &total);
+  long long tri_run = tri_offset[unit], act_run = act_offset[unit];
+  const unsigned int vi0 = (unsigned int)(x * yz + u * kUnit);
+  for (int base = 0; base < total; base += 32) {     // warp-uniform; ranks follow the cube order
+    const ActiveCube ac = nth_active(cw, excl, total, base + lane);
+    const int cnt = ac.ok ? (int)__ldg(&g_tri_count[ac.m]) : 0;
+    const int one = cnt > 0 ? 1 : 0;
+    int it = cnt, ia = one;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int w = u * (kUnit / 32) + 2 * lane + h;
-    cw[h].active = 0u;
-    if (w < pw) cw[h] = cube_words(p0, p1, pw, w, P.dy, P.dz);
-    for (unsigned int a = cw[h].active; a; a &= a - 1) {
-      const int cnt = c_tri_count[cube_case(cw[h], __ffs(a) - 1)];
-      tris += cnt;
-      act += cnt > 0 ? 1 : 0;
+    for (int off = 1; off < 32; off <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, it, off), b = __shfl_up_sync(0xffffffffu, ia, off);
+      if (lane >= off) { it += a; ia += b; }
     }
-  }
-  int it = tris, ia = act;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const int a = __shfl_up_sync(0xffffffffu, it, off), b = __shfl_up_sync(0xffffffffu, ia, off);
-    if (lane >= off) { it += a; ia += b; }
-  }
-  long long slot = act_offset[unit] + (ia - act), tri = tri_offset[unit] + (it - tris);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int j0 = 32 * (u * (kUnit / 32) + 2 * lane + h);
-    for (unsigned int a = cw[h].active; a; a &= a - 1) {
-      const int b = __ffs(a) - 1;
-      const int cnt = c_tri_count[cube_case(cw[h], b)];
-      if (cnt > 0) {
-        if (slot < n_active) list[slot] = make_uint2((unsigned int)(x * yz + j0 + b), (unsigned int)tri);
-        const long long kb = (tri + kEmitTris - 1) / kEmitTris;   // the cube that holds triangle kb * kEmitTris
-        if (kb * kEmitTris < tri + cnt) cta_first[kb] = (unsigned int)slot;
-        ++slot;
-        tri += cnt;
-      }
+    if (cnt > 0) {
+      const long long slot = act_run + (ia - 1), tri = tri_run + (it - cnt);
+      if (slot < n_active) list[slot] = make_uint2(vi0 + (unsigned int)ac.pos, (unsigned int)tri);
+      const long long kb = (tri + kEmitTris - 1) / kEmitTris;   // the cube that holds triangle kb * kEmitTris
+      if (kb * kEmitTris < tri + cnt) cta_first[kb] = (unsigned int)slot;
     }
+    tri_run += __shfl_sync(0xffffffffu, it, 31);
+    act_run += __shfl_sync(0xffffffffu, ia, 31);
   }
 }
 
