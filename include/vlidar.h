@@ -238,7 +238,8 @@ int vl_tsdf_init_integrate(float* d_tsdf, float* d_weight, float* d_color, float
  * first integration brackets every voxel (plain sqrt, arcsine series, image row to a few hundredths) against the range image's
  * per-pixel [depth, depth + trunc] shell and runs the reference arithmetic only where the bracket cannot rule out an
  * update; bit-identical to vl_tsdf_init + vl_tsdf_integrate.  With vl_tsdf_workspace_bytes(dx, dy) only, or outside
- * those limits, every voxel takes the reference arithmetic.  vl_debug_tsdf_shell(0) turns the shell sweep off, (2) runs
+ * those limits, every voxel takes the reference arithmetic.  vl_tsdf_integrate_ws with this much workspace takes the same
+ * sweep for LATER integrations (free space is skipped only for voxels never written).  vl_debug_tsdf_shell(0) turns the shell sweep off, (2) runs
  * it with one voxel per thread instead of four (the variant for dz % 4 != 0); tests compare all of them. */
 size_t vl_tsdf_fresh_workspace_bytes(int dx, int dy, int im_h, int im_w);
 void vl_debug_tsdf_shell(int mode);

@@ -218,7 +218,13 @@ __device__ __forceinline__ VoxelBracket shell_bracket(float xy2, float z, const 
   return b;
 }
 
-template <int kVec>
+// kFresh false: a LATER integration (the volume holds earlier scans).  A voxel behind every candidate pixel's shell,
+// outside the field of view or on an empty pixel is skipped as before -- those exits of the kernel string do not look
+// at the volume.  A voxel IN FRONT of its candidates (free space, all of them labelled) is left alone only if it has
+// never been written (colour 0 and weight 0: then `old_color == new_color` fails and `dist < weight` fails for every
+// dist >= 0); its colour and weight are read for that, everything else about it is not.  Nothing is written outside
+// the queue.
+template <int kVec, bool kFresh>
 __global__ void __launch_bounds__(kThreads)
 k_tsdf_fresh_shell(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, float* __restrict__ color_vol,
                    float* __restrict__ rem_vol, const TsdfParams P, const ShellParams S,
@@ -257,18 +263,38 @@ k_tsdf_fresh_shell(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol,
           b[j] = shell_bracket(xy2, __fmaf_rn((float)(vz + j), P.voxel_size, P.oz), P, S);
 #pragma unroll
         for (int j = 0; j < kVec; ++j) lh[j] = __ldg(col + max(b[j].r0, 0));   // all loads in flight before the first use
+        unsigned int front = 0;                                      // kFresh false: free space, decided by the voxel's state
 #pragma unroll
         for (int j = 0; j < kVec; ++j) {
           if (b[j].r0 < 0) continue;
-          bool may = !(b[j].d_hi < lh[j].x || b[j].d_lo > lh[j].y);
+          // per candidate pixel: behind its shell (or empty pixel) / in front of it / neither
+          bool behind = b[j].d_lo > lh[j].y;
+          bool infront = !behind && b[j].d_hi < lh[j].x;
+          bool may = !behind && !infront;
           if (b[j].r1 != b[j].r0) {
             const float2 o = __ldg(col + b[j].r1);
-            may = may || !(b[j].d_hi < o.x || b[j].d_lo > o.y);
+            const bool behind2 = b[j].d_lo > o.y, infront2 = !behind2 && b[j].d_hi < o.x;
+            may = may || (!behind2 && !infront2);
+            infront = infront || infront2;
           }
           if (may) ex |= 1u << j;
+          else if (infront) front |= 1u << j;
+        }
+        if (!kFresh && front) {
+          if (kVec == 4) {
+            const float4 c = *reinterpret_cast<const float4*>(color_vol + voxel_idx);
+            const float4 w = *reinterpret_cast<const float4*>(weight_vol + voxel_idx);
+            const unsigned int touched = ((c.x != 0.f || w.x != 0.f) ? 1u : 0u) | ((c.y != 0.f || w.y != 0.f) ? 2u : 0u) |
+                                         ((c.z != 0.f || w.z != 0.f) ? 4u : 0u) | ((c.w != 0.f || w.w != 0.f) ? 8u : 0u);
+            ex |= front & touched;
+          } else if (color_vol[voxel_idx] != 0.f || weight_vol[voxel_idx] != 0.f) {
+            ex |= 1u;
+          }
         }
       }
-      if (kVec == 4) {
+      if (!kFresh) {
+        // nothing to reset
+      } else if (kVec == 4) {
         if (ex == 0) {
           const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(tsdf_vol + voxel_idx) = one;
@@ -302,7 +328,7 @@ k_tsdf_fresh_shell(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol,
   __syncthreads();
   const int nq = s_nq;
   for (int i = threadIdx.x; i < nq; i += kThreads)
-    tsdf_voxel<true, true>(s_q[i], tsdf_vol, weight_vol, color_vol, rem_vol, P, color_im, depth_im, rem_im, col_px);
+    tsdf_voxel<true, kFresh>(s_q[i], tsdf_vol, weight_vol, color_vol, rem_vol, P, color_im, depth_im, rem_im, col_px);
 }
 
 int g_tsdf_shell = 1;    // vl_debug_tsdf_shell: 0 off, 1 on, 2 on with one voxel per thread
@@ -365,7 +391,7 @@ static int tsdf_integrate_impl(float* d_tsdf, float* d_weight, float* d_color, f
     // series' range, image rows much coarser than its error, a positive truncation margin
     const double fov_rad = fabs((double)P.fov_up) + fabs((double)P.fov_down);
     const double eps_row = fov_rad > 0.0 ? 1.02 * kAsinErr * im_h / fov_rad + 1e-3 + 4e-7 * im_h : 1.0;
-    const bool shell_ok = fresh && g_tsdf_shell && workspace_bytes >= shell_off + sizeof(float2) * (size_t)im_h * im_w &&
+    const bool shell_ok = g_tsdf_shell && workspace_bytes >= shell_off + sizeof(float2) * (size_t)im_h * im_w &&
                           (long long)dy * dz <= (1LL << 24) && dx <= 65535 && trunc_margin > 0.f && voxel_size > 0.f &&
                           fabs((double)P.fov_up) <= 0.61 && fabs((double)P.fov_down) <= 0.61 && fov_rad > 0.0 &&
                           eps_row < 0.45;
@@ -385,12 +411,11 @@ static int tsdf_integrate_impl(float* d_tsdf, float* d_weight, float* d_color, f
       dim3 grid((unsigned int)((S.slab + kFastChunk - 1) / kFastChunk), (unsigned int)dx);
       const bool vec = dz % 4 == 0 && !g_tsdf_scalar &&
                        ((((uintptr_t)d_tsdf) | ((uintptr_t)d_weight) | ((uintptr_t)d_color) | ((uintptr_t)d_rem)) & 15) == 0;
-      if (vec)
-        k_tsdf_fresh_shell<4><<<grid, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, S, d_color_im, d_depth_im,
-                                                            d_rem_im, col_px, shell);
-      else
-        k_tsdf_fresh_shell<1><<<grid, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, S, d_color_im, d_depth_im,
-                                                            d_rem_im, col_px, shell);
+#define VL_SHELL_LAUNCH(V, F) k_tsdf_fresh_shell<V, F><<<grid, kThreads, 0, stream>>>( \
+          d_tsdf, d_weight, d_color, d_rem, P, S, d_color_im, d_depth_im, d_rem_im, col_px, shell)
+      if (vec) { if (fresh) VL_SHELL_LAUNCH(4, true); else VL_SHELL_LAUNCH(4, false); }
+      else { if (fresh) VL_SHELL_LAUNCH(1, true); else VL_SHELL_LAUNCH(1, false); }
+#undef VL_SHELL_LAUNCH
     } else if (fresh)
       k_tsdf_integrate<true, true><<<nb, kThreads, 0, stream>>>(d_tsdf, d_weight, d_color, d_rem, P, d_color_im, d_depth_im,
                                                                d_rem_im, n_vox, col_px);

@@ -206,6 +206,11 @@ def test_tsdf_fresh_shell_sweep_gives_the_same_bits(engine, oracle, case):
     depth[(r >= 0.04) & (r < 0.06)] = -3.0
     depth[(r >= 0.06) & (r < 0.08)] = 1e-3
   color_im = oracle.label_to_color_im(lab)
+  # later integrations take the same sweep (free space is skipped only for voxels never written): another class seen
+  # 2 % closer (class switch in front of the first surface), the same again (running average), the first image again
+  color_2 = oracle.label_to_color_im(np.where(lab > 0, 99, 0))
+  closer = (depth * np.float32(0.98)).astype(np.float32)
+  seq = [(color_im, depth)] if case == "c1" else [(color_im, depth), (color_2, closer), (color_2, closer), (color_im, depth)]
   bnds = np.array(bnds, np.float64)
   dim = np.ceil((bnds[:, 1] - bnds[:, 0]) / vox).astype(int)
   origin = bnds[:, 0].astype(np.float32)
@@ -214,7 +219,8 @@ def test_tsdf_fresh_shell_sweep_gives_the_same_bits(engine, oracle, case):
     lib().vl_debug_tsdf_shell(mode)
     try:
       d = engine.TsdfDevice(dim, origin, vox, fu, fd)
-      d.integrate(color_im, depth, pr["proj_remissions"])
+      for c_im, d_im in seq:
+        d.integrate(c_im, d_im, pr["proj_remissions"])
       vols[tag] = [getattr(d, k).view(torch.int32).clone() for k in ("tsdf", "weight", "color", "rem")]
       del d
     finally:
@@ -226,13 +232,16 @@ def test_tsdf_fresh_shell_sweep_gives_the_same_bits(engine, oracle, case):
   if case == "odd_dz":
     assert dim[2] % 4 != 0
   d = engine.TsdfDevice(dim, origin, vox, fu, fd)
-  d.integrate(color_im, depth, pr["proj_remissions"], use_column_table=False)   # vl_tsdf_init + the per-voxel kernel
+  for c_im, d_im in seq:
+    d.integrate(c_im, d_im, pr["proj_remissions"], use_column_table=False)   # vl_tsdf_init + the per-voxel kernel
   n_changed = int((d.tsdf != 1).sum())
   for k, a in zip(("tsdf", "weight", "color", "rem"), vols["shell"]):
     assert torch.equal(a, getattr(d, k).view(torch.int32)), (case, k)
   assert n_changed > (50 if case == "origin_inside" else 300), n_changed
   if case == "zero_labels":
-    assert int(((d.weight > 0) & (d.tsdf == 1)).sum()) > 1000   # free space in front of label-0 pixels: weight 1, tsdf 1
+    assert int(((d.weight > 0) & (d.tsdf == 1)).sum()) > 1000   # free space in front of label-0 pixels: weight > 0, tsdf 1
+  if case != "c1":
+    assert int((d.weight > 1).sum()) > 50 and len(torch.unique(d.color)) >= 3   # running average and class switch happened
 
 
 def test_reverse_projection_on_device_matches_reference_golden(engine):
