@@ -17,6 +17,7 @@ import os
 import numpy as np
 
 from .. import engine
+from .. import scanio
 from ..rays import create_rays as _create_rays
 from . import fusion_lidar as fl
 from .np_ioueval import iouEval
@@ -453,9 +454,10 @@ class MultiSemLaserScan():
   def create_rays(self, fov_up, fov_down, H, W):
     return _create_rays(fov_up, fov_down, H, W)
 
-  def write(self, out_dir, idx, write_png=False):
+  def write(self, out_dir, idx, write_png=False, writer=None):
     """KITTI .bin (float32 x,y,z,remission) + .label (uint32) of the re-rendered scan; the reference's filter
-    rules (laserscan.py:1133-1158) with array writes instead of per-point struct.pack."""
+    rules (laserscan.py:1133-1158) with array writes instead of per-point struct.pack.  writer: a
+    scanio.AsyncScanWriter -- filtering and the two file writes then happen on its thread (same bytes)."""
     if write_png:
       raise NotImplementedError("write_png references an undefined name in the reference (laserscan.py:1124-1126)")
     if self.adaption == 'cp':
@@ -469,16 +471,11 @@ class MultiSemLaserScan():
       back_points = self.back_points.reshape(-1, 3)
       label_image = self.label_image.reshape(-1)
       remissions = self.proj_remissions.reshape(-1)
-    valid = label_image >= 0
-    back_points, remissions, label_image = back_points[valid], remissions[valid], label_image[valid].astype(np.int32)
-    keep = np.sum(back_points, axis=1) != 0  # remove points with (0, 0, 0)
-    back_points, remissions, label_image = back_points[keep], remissions[keep], label_image[keep]
-    assert back_points.shape[0] == label_image.shape[0]
-    rec = np.empty((back_points.shape[0], 4), dtype="<f4")
-    rec[:, 0:3] = back_points
-    rec[:, 3] = remissions
-    rec.tofile(os.path.join(out_dir, "velodyne", str(idx).zfill(6) + ".bin"))
-    label_image.astype("<u4").tofile(os.path.join(out_dir, "labels", str(idx).zfill(6) + ".label"))
+    if writer is not None:
+      writer.submit(idx, np.asarray(back_points), np.asarray(remissions), np.asarray(label_image))
+      return
+    rec, labels = scanio.filter_scan_for_write(back_points, remissions, label_image)
+    scanio.write_scan(out_dir, idx, rec, labels)
 
 
 def compare_device(scan_source, scan_target):

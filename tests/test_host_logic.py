@@ -126,6 +126,12 @@ def test_write_produces_the_reference_bytes(G, tmp_path):
   ms.write(str(tmp_path), 7)
   assert np.array_equal(np.fromfile(tmp_path / "velodyne" / "000007.bin", np.uint8), G["write_bin"])
   assert np.array_equal(np.fromfile(tmp_path / "labels" / "000007.label", np.uint8), G["write_label"])
+  # the same bytes (pinned to the reference's own write() by the golden) through the writer thread
+  from lidar_transfer_b200.scanio import AsyncScanWriter
+  with AsyncScanWriter(str(tmp_path / "async")) as w:
+    ms.write(str(tmp_path / "async"), 7, writer=w)
+  assert np.array_equal(np.fromfile(tmp_path / "async" / "velodyne" / "000007.bin", np.uint8), G["write_bin"])
+  assert np.array_equal(np.fromfile(tmp_path / "async" / "labels" / "000007.label", np.uint8), G["write_label"])
 
 
 def test_meshwrite_format(tmp_path):
