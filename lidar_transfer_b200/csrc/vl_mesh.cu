@@ -664,7 +664,6 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
 // formulation, kept for comparison.  Set it before vl_mesh_workspace_bytes: modes 2 / 3 need a byte per voxel.
 static int g_mesh_mode = 0;
 extern "C" void vl_debug_mesh_scalar(int mode) { g_mesh_mode = mode >= 0 && mode <= 3 ? mode : 0; }
-#define g_mesh_scalar (g_mesh_mode == 3)
 static int mesh_plane_words(int dy, int dz) { return (int)(((long long)dy * dz + 31) / 32); }
 
 static int mesh_units_per_plane(int dy, int dz) { return (int)(((long long)dy * dz + kUnit - 1) / kUnit); }
@@ -734,7 +733,7 @@ extern "C" int vl_mesh_count(const float* d_tsdf, int dx, int dy, int dz, float 
     k_mesh_count_bits<<<grid, kThreads, 0, stream>>>(bits, P, pw, upp, reinterpret_cast<int*>(ws + w.tris),
                                                     reinterpret_cast<int*>(ws + w.active));
   } else {
-  const bool vec4 = !g_mesh_scalar && dz % 4 == 0 && ((uintptr_t)d_tsdf & 15) == 0;   // cases start 256-byte aligned
+  const bool vec4 = g_mesh_mode != 3 && dz % 4 == 0 && ((uintptr_t)d_tsdf & 15) == 0;   // cases start 256-byte aligned
   if (vec4)
     k_mesh_count4<<<grid, kThreads, 0, stream>>>(
         d_tsdf, P, upp, reinterpret_cast<int*>(ws + w.tris), reinterpret_cast<int*>(ws + w.active),
@@ -796,7 +795,7 @@ extern "C" int vl_mesh_emit(const float* d_tsdf, const float* d_color, const flo
   if (g_mesh_mode < 2)
     k_mesh_compact_bits<<<grid, kThreads, 0, stream>>>(reinterpret_cast<const unsigned int*>(ws + w.bits), P,
                                                       mesh_plane_words(dy, dz), upp, ut, to, ao, n_active, list, cta_first);
-  else if (!g_mesh_scalar && ((long long)dy * dz) % 4 == 0) k_mesh_compact<4><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list, cta_first);
+  else if (g_mesh_mode != 3 && ((long long)dy * dz) % 4 == 0) k_mesh_compact<4><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list, cta_first);
   else k_mesh_compact<1><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list, cta_first); }
   VL_LAUNCH_CHECK("k_mesh_compact");
   VlProfScope ps(VL_ST_MESH_EMIT, stream);
