@@ -205,7 +205,10 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, wor
   dev = points.device
   ba = None
   if beam_angles is not None and len(beam_angles):
-    ba = _dev(np.asarray(beam_angles, np.float64).reshape(-1), torch.float64, dev)
+    ba_host = np.asarray(beam_angles, np.float64).reshape(-1)
+    if not np.isfinite(ba_host).all():   # numpy's argmin would pick the first NaN; refuse instead of guessing
+      raise ValueError("beam_angles must be finite")
+    ba = _dev(ba_host, torch.float64, dev)
   n = points.numel() // 3
   remissions = _dev(remissions, torch.float32, dev).reshape(-1)
   if torch.is_tensor(labels) and labels.dtype in (torch.int32, torch.uint32):

@@ -15,8 +15,9 @@
  *     against the reference C++ ray tracer compiled from its own sources
  *     with -ffp-contract=off (oracle/_ref/libref_raytracer_nofma.so), and
  *     against the known-answer ray/triangle of auxiliary/raytracing.py:229-263.
- *   - vlo_project is checked against the reference's own Python
- *     (auxiliary/laserscan.py imported with stub modules, tests/golden/make_golden.py).
+ *   - vlo_project / vlo_project_snap are checked against the reference's own Python
+ *     (auxiliary/laserscan.py imported with stub modules, tests/golden/make_golden.py and
+ *     make_golden_beams.py for the beam_angles step).
  *   - vlo_tsdf_integrate is checked BIT-EXACT against the reference's CUDA
  *     kernel string (auxiliary/fusion_lidar.py:66-229) extracted at build
  *     time and compiled for the CPU (oracle/_ref/libref_tsdf.so).

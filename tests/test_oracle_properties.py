@@ -77,3 +77,28 @@ def test_projection_keeps_the_nearest_point_whatever_the_order(oracle, seed, n):
     d = np.linalg.norm(pts[kept], 2, axis=1).astype(np.float32)
     filled = a["index"] >= 0
     assert np.array_equal(d[a["index"][filled]].view(np.int32), a["range_image"][filled].view(np.int32))
+
+
+@settings(max_examples=25, deadline=None)
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 400), n_ba=st.integers(1, 40), remove=st.booleans())
+def test_beam_angle_snapping_c_restatement_equals_the_python_loop(oracle, seed, n, n_ba, remove):
+  """vlo_project_snap vs the line-for-line numpy restatement of laserscan.py:321-327 (both pinned to the reference's own
+  Python by golden_beams_v1.npz) on random points and random lists with duplicates and exact mid-points (argmin ties:
+  the first entry wins)."""
+  rng = np.random.default_rng(seed)
+  pts = rng.normal(0, 10, (n, 3))
+  pts[rng.random(n) < 0.05] = 0.0
+  ba = np.sort(rng.uniform(-0.6, 0.2, n_ba))
+  ba = np.concatenate([ba, ba[:1], ba[-1:]]).tolist()      # duplicates
+  if n_ba >= 2:                                           # a point whose pitch is exactly half-way between two entries
+    mid = 0.5 * (ba[0] + ba[1])
+    pts[0] = [np.cos(mid) * 7.0, 0.0, np.sin(mid) * 7.0]
+  rem = rng.random(n).astype(np.float32)
+  lab = rng.integers(0, 260, n).astype(np.uint32)
+  a = oracle.project(pts, rem, lab, 3.0, -25.0, 16, 64, remove=remove, beam_angles=ba)
+  b = oracle.project_numpy(pts, rem, lab, 3.0, -25.0, 16, 64, remove=remove, beam_angles=ba)
+  assert a["n_kept"] == b["n_kept"] and np.array_equal(a["keep"], b["keep"])
+  for k in ("index", "proj_label"):
+    assert np.array_equal(a[k], b[k]), k
+  for k in ("range_image", "proj_remissions"):
+    assert np.array_equal(a[k].view(np.int32), b[k].view(np.int32)), k
