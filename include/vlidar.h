@@ -234,7 +234,7 @@ int vl_tsdf_init_integrate(float* d_tsdf, float* d_weight, float* d_color, float
                            const float* d_color_im, const float* d_depth_im, const float* d_rem_im,
                            int im_h, int im_w, void* d_workspace, size_t workspace_bytes, vl_stream stream);
 /* Workspace for vl_tsdf_init_integrate's shell sweep: the column table plus 8 B per image pixel.  With at least this
- * much workspace (and |fov| <= 35 deg, dy * dz <= 2^24, dx <= 65535, fewer than ~1400 image rows per radian) the fused
+ * much workspace (and |fov| <= 35 deg, dy * dz <= 2^24, dx <= 65535, fewer than ~40000 image rows per radian) the fused
  * first integration brackets every voxel (plain sqrt, arcsine series, image row to a few hundredths) against the range image's
  * per-pixel [depth, depth + trunc] shell and runs the reference arithmetic only where the bracket cannot rule out an
  * update; bit-identical to vl_tsdf_init + vl_tsdf_integrate.  With vl_tsdf_workspace_bytes(dx, dy) only, or outside

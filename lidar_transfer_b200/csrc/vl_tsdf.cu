@@ -155,8 +155,8 @@ k_tsdf_integrate(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, f
 // So per pixel the voxel depths that matter are (lo, hi] with lo = the pixel's depth (-inf for colour 0) and
 // hi = depth + trunc: k_tsdf_shell stores that pair per pixel.  The sweep then needs, per voxel, only a CONSERVATIVE
 // bracket of what the reference computes: the exact pixel column of its z column (k_tsdf_columns), its depth to
-// 1e-5 (plain sqrt instead of norm3df) and its fractional image row to +-eps_row (arcsine by its odd series up to
-// s^11: below |asin|, by < 2e-4 rad for |s| <= 0.62, monotonic beyond) -- one candidate pixel, two when the row
+// 1e-5 (rsqrt.approx instead of norm3df) and its fractional image row to +-eps_row (arcsine by its odd series up to
+// s^15: below |asin|, by < 6e-6 rad for |s| <= 0.62, monotonic beyond) -- one candidate pixel, two when the row
 // estimate is within eps_row of a row boundary.  A voxel whose bracket misses the shell of its candidate pixels, or
 // that is outside the vertical field of view by more than the series' error, is written with the initial values
 // straight away; every other voxel is queued in shared memory and evaluated by tsdf_voxel<true, true> -- the
@@ -166,7 +166,7 @@ k_tsdf_integrate(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, f
 // one column lookup, float4 stores.
 constexpr int kFastChunk = 1024;      // voxels per CTA
 constexpr int kDecodeWindow = 256;    // >= 64 (float(idx) for idx < 2^31) + n_vox * 2^-24 (rounding of the quotient)
-constexpr float kAsinErr = 3e-4f;     // series truncation (< 2e-4 for |s| <= 0.62) + float rounding
+constexpr float kAsinErr = 1e-5f;     // series truncation (< 6e-6 for |s| <= 0.62) + float rounding
 constexpr float kDepthRel = 1e-5f;
 
 struct ShellParams {
@@ -197,13 +197,17 @@ k_tsdf_shell(const float* __restrict__ depth_im, const float* __restrict__ color
 struct VoxelBracket { float d_lo, d_hi; int r0, r1; };
 
 __device__ __forceinline__ VoxelBracket shell_bracket(float xy2, float z, const TsdfParams& P, const ShellParams& S) {
-  // bracket only: contracted arithmetic is fine here (the file is compiled with -fmad=false)
+  // bracket only: contracted and approximate arithmetic is fine here (the file is compiled with -fmad=false)
   const float q = __fmaf_rn(z, z, xy2);
-  const float rq = rsqrtf(q);
-  const float d = q * rq;                                    // the origin voxel gives NaN: no comparison rules it out
+  float rq;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(q));   // 2 ulp; q == 0 (the origin voxel) gives inf
+  const float d = q * rq;                                    // ... and d = NaN: no comparison rules that voxel out
   const float sn = z * rq, s2 = sn * sn;
-  // asin(s) = s + s^3/6 + 3 s^5/40 + 15 s^7/336 + 105 s^9/3456 + 945 s^11/42240 + ...
-  float poly = __fmaf_rn(s2, 945.f / 42240, 105.f / 3456);
+  // asin(s) = s + s^3/6 + 3 s^5/40 + 15 s^7/336 + 105 s^9/3456 + 945 s^11/42240 + 10395 s^13/599040
+  //           + 135135 s^15/9676800 + ...   (remainder < 6e-6 for |s| <= 0.62)
+  float poly = __fmaf_rn(s2, 135135.f / 9676800, 10395.f / 599040);
+  poly = __fmaf_rn(s2, poly, 945.f / 42240);
+  poly = __fmaf_rn(s2, poly, 105.f / 3456);
   poly = __fmaf_rn(s2, poly, 15.f / 336);
   poly = __fmaf_rn(s2, poly, 3.f / 40);
   poly = __fmaf_rn(s2, poly, 1.f / 6);
@@ -212,8 +216,11 @@ __device__ __forceinline__ VoxelBracket shell_bracket(float xy2, float z, const 
   VoxelBracket b;
   b.d_lo = d * (1.f - kDepthRel);
   b.d_hi = d * (1.f + kDepthRel);
-  b.r0 = max(0, min(P.im_h - 1, (int)floorf(rowf - S.eps_row)));
-  b.r1 = max(0, min(P.im_h - 1, (int)floorf(rowf + S.eps_row)));
+  const float f0 = floorf(rowf - S.eps_row);                 // eps_row < 0.5: floor(rowf + eps_row) is f0 or f0 + 1
+  const int r0 = (int)f0;
+  const int r1 = rowf + S.eps_row >= f0 + 1.f ? r0 + 1 : r0;
+  b.r0 = max(0, min(P.im_h - 1, r0));
+  b.r1 = max(0, min(P.im_h - 1, r1));
   if (pitch > S.pitch_hi || pitch < S.pitch_lo) b.r0 = -1;
   return b;
 }
@@ -390,7 +397,7 @@ static int tsdf_integrate_impl(float* d_tsdf, float* d_weight, float* d_color, f
     // the shell sweep needs: room for the shell image, y / z decodable in float, a field of view inside the arcsine
     // series' range, image rows much coarser than its error, a positive truncation margin
     const double fov_rad = fabs((double)P.fov_up) + fabs((double)P.fov_down);
-    const double eps_row = fov_rad > 0.0 ? 1.02 * kAsinErr * im_h / fov_rad + 1e-3 + 4e-7 * im_h : 1.0;
+    const double eps_row = fov_rad > 0.0 ? 1.02 * kAsinErr * im_h / fov_rad + 2e-4 + 4e-7 * im_h : 1.0;
     const bool shell_ok = g_tsdf_shell && workspace_bytes >= shell_off + sizeof(float2) * (size_t)im_h * im_w &&
                           (long long)dy * dz <= (1LL << 24) && dx <= 65535 && trunc_margin > 0.f && voxel_size > 0.f &&
                           fabs((double)P.fov_up) <= 0.61 && fabs((double)P.fov_down) <= 0.61 && fov_rad > 0.0 &&

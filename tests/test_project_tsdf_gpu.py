@@ -170,8 +170,8 @@ def test_tsdf_fresh_shell_sweep_gives_the_same_bits(engine, oracle, case):
   one voxel per thread instead of four and (c) the per-voxel kernel on a volume reset by vl_tsdf_init.  Cases: the
   config-1 volume (284 M voxels, float index decode beyond 2^24), pixels of label 0 (their voxels IN FRONT of the
   surface are written too), NaN / inf / negative depths, a volume around the sensor (the origin voxel's NaN pitch),
-  512 image rows (a third of the voxels have two candidate rows) and 1024 (finer than the bracket: the sweep must
-  decline), fields of view at and beyond the arcsine series' range, dz % 4 != 0."""
+  512 and 1024 image rows (rows much finer than the voxels: many voxels sit near a row boundary and take two
+  candidate rows), fields of view at and beyond the arcsine series' range, dz % 4 != 0."""
   import torch
   from lidar_transfer_b200._lib import lib
   H, W, fu, fd, vox = 64, 1024, 3.0, -25.0, 0.25
