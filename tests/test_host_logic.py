@@ -38,6 +38,31 @@ def test_library_exports_every_declared_symbol(vl):
   assert vl.vl_profile_stage_count() >= 5
 
 
+def test_header_is_plain_c_and_cxx(tmp_path):
+  """include/vlidar.h is what a cgo / Cython / ctypes-generator binding would include: it has to compile as C99 (no C++
+  types, no default arguments) and as C++."""
+  import shutil, subprocess
+  src = tmp_path / "hdr_check.c"
+  src.write_text('#include "vlidar.h"\nint main(void) { return vl_abi_version() < 0; }\n')
+  inc = os.path.join(ROOT, "include")
+  if shutil.which("gcc"):
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+  if shutil.which("g++"):
+    subprocess.run(["g++", "-std=c++14", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)], check=True)
+
+
+def test_workspace_queries_need_no_gpu(vl):
+  """The size queries are pure host arithmetic (callers allocate before the first launch)."""
+  n_vox = 2000 * 1420 * 100
+  mesh = vl.vl_mesh_workspace_bytes(2000, 1420, 100)
+  assert n_vox // 8 <= mesh < n_vox // 8 + (1 << 23)                      # one bit per voxel + unit counters
+  assert vl.vl_mesh_list_bytes(4330960, 2240000) >= 8 * 2240000 + 4 * (4330960 // 256)
+  col = vl.vl_tsdf_workspace_bytes(2000, 1420)
+  fresh = vl.vl_tsdf_fresh_workspace_bytes(2000, 1420, 64, 2048)
+  assert col >= 4 * 2000 * 1420 and fresh >= col + 8 * 64 * 2048
+  assert vl.vl_project_workspace_bytes(124668, 64, 2048) >= 8 * 64 * 2048
+
+
 def test_no_cuda_means_loud_failure_not_fallback(vl):
   import torch
   if torch.cuda.is_available():
