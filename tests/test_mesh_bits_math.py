@@ -75,3 +75,42 @@ def test_word_sweep_equals_the_per_cube_definition(seed, dx, dy, dz, density):
           want[(x, y * dz + z)] = m
   assert got == want
   assert all(j < yz for (_, j) in got)
+
+
+def _nth_active(act0, act1, excl, want):
+  """nth_active: owner lane by bisection over the exclusive prefix, word by rank, bit by popcount selection."""
+  o = 0
+  step = 16
+  while step:
+    if excl[o + step] <= want:
+      o += step
+    step >>= 1
+  rnk = want - excl[o]
+  n0 = bin(act0[o]).count("1")
+  h = 1 if rnk >= n0 else 0
+  act = act1[o] if h else act0[o]
+  rnk -= n0 if h else 0
+  b, sft = 0, 16
+  while sft:
+    c = bin((act >> b) & ((1 << sft) - 1)).count("1")
+    if rnk >= c:
+      b += sft
+      rnk -= c
+    sft >>= 1
+  return 64 * o + 32 * h + (b & 31)
+
+
+@settings(max_examples=60, deadline=None)
+@given(seed=st.integers(0, 2 ** 31 - 1), density=st.sampled_from([0.0, 0.01, 0.05, 0.5, 1.0]))
+def test_rank_selection_enumerates_the_active_cubes_of_a_unit_in_cube_order(seed, density):
+  rng = np.random.default_rng(seed)
+  bits = rng.random(2048) < density
+  if density == 0.01:
+    bits[rng.integers(0, 2048)] = True
+  act0 = [int(sum(1 << b for b in range(32) if bits[64 * l + b])) for l in range(32)]
+  act1 = [int(sum(1 << b for b in range(32) if bits[64 * l + 32 + b])) for l in range(32)]
+  counts = [bin(a).count("1") + bin(c).count("1") for a, c in zip(act0, act1)]
+  excl = [int(v) for v in np.concatenate([[0], np.cumsum(counts)[:-1]])]
+  total = sum(counts)
+  got = [_nth_active(act0, act1, excl, r) for r in range(total)]
+  assert got == [int(j) for j in np.flatnonzero(bits)]
