@@ -365,8 +365,8 @@ k_mesh_count_bits(const unsigned int* __restrict__ bits, const MeshParams P, int
 __global__ void __launch_bounds__(kThreads)
 k_mesh_compact_bits(const unsigned int* __restrict__ bits, const MeshParams P, int pw, int units_per_plane,
                     const int* __restrict__ unit_tris, const long long* __restrict__ tri_offset,
-                    const long long* __restrict__ act_offset, long long n_active, uint2* __restrict__ list,
-                    unsigned int* __restrict__ cta_first) {
+                    const long long* __restrict__ act_offset, long long n_active, long long n_tris,
+                    uint2* __restrict__ list, unsigned int* __restrict__ cta_first) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int u = blockIdx.x * kWarps + wid;
   if (u >= units_per_plane) return;
@@ -393,7 +393,7 @@ k_mesh_compact_bits(const unsigned int* __restrict__ bits, const MeshParams P, i
       const long long slot = act_run + (ia - 1), tri = tri_run + (it - cnt);
       if (slot < n_active) list[slot] = make_uint2(vi0 + (unsigned int)ac.pos, (unsigned int)tri);
       const long long kb = (tri + kEmitTris - 1) / kEmitTris;   // the cube that holds triangle kb * kEmitTris
-      if (kb * kEmitTris < tri + cnt) cta_first[kb] = (unsigned int)slot;
+      if (kb * kEmitTris < tri + cnt && kb * kEmitTris < n_tris) cta_first[kb] = (unsigned int)slot;
     }
     tri_run += __shfl_sync(0xffffffffu, it, 31);
     act_run += __shfl_sync(0xffffffffu, ia, 31);
@@ -492,7 +492,7 @@ template <int kVec>
 __global__ void __launch_bounds__(kThreads)
 k_mesh_compact(const MeshParams P, int units_per_plane, const unsigned char* __restrict__ cases,
                const int* __restrict__ unit_tris, const long long* __restrict__ tri_offset,
-               const long long* __restrict__ act_offset, long long n_active, uint2* __restrict__ list,
+               const long long* __restrict__ act_offset, long long n_active, long long n_tris, uint2* __restrict__ list,
                unsigned int* __restrict__ cta_first) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int u = blockIdx.x * kWarps + wid;
@@ -524,7 +524,7 @@ k_mesh_compact(const MeshParams P, int units_per_plane, const unsigned char* __r
       if (cnt[k] > 0) {
         if (slot < n_active) list[slot] = make_uint2((unsigned int)(x * yz + j + k), (unsigned int)tri);
         const long long kb = (tri + kEmitTris - 1) / kEmitTris;   // the cube that holds triangle kb * kEmitTris
-        if (kb * kEmitTris < tri + cnt[k]) cta_first[kb] = (unsigned int)slot;
+        if (kb * kEmitTris < tri + cnt[k] && kb * kEmitTris < n_tris) cta_first[kb] = (unsigned int)slot;
         ++slot;
         tri += cnt[k];
       }
@@ -794,9 +794,9 @@ extern "C" int vl_mesh_emit(const float* d_tsdf, const float* d_color, const flo
   const long long* ao = reinterpret_cast<const long long*>(ws + w.act_off);
   if (g_mesh_mode < 2)
     k_mesh_compact_bits<<<grid, kThreads, 0, stream>>>(reinterpret_cast<const unsigned int*>(ws + w.bits), P,
-                                                      mesh_plane_words(dy, dz), upp, ut, to, ao, n_active, list, cta_first);
-  else if (g_mesh_mode != 3 && ((long long)dy * dz) % 4 == 0) k_mesh_compact<4><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list, cta_first);
-  else k_mesh_compact<1><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, list, cta_first); }
+                                                      mesh_plane_words(dy, dz), upp, ut, to, ao, n_active, n_tris, list, cta_first);
+  else if (g_mesh_mode != 3 && ((long long)dy * dz) % 4 == 0) k_mesh_compact<4><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, n_tris, list, cta_first);
+  else k_mesh_compact<1><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, n_tris, list, cta_first); }
   VL_LAUNCH_CHECK("k_mesh_compact");
   VlProfScope ps(VL_ST_MESH_EMIT, stream);
   const int vec_ok = ((((uintptr_t)d_verts) | ((uintptr_t)d_norms)) & 15) == 0 && (((uintptr_t)d_colors) & 3) == 0;
