@@ -250,10 +250,12 @@ void vl_debug_tsdf_shell(int mode);
  * Replaces: TSDFVolume.get_volume + get_mesh, auxiliary/fusion_lidar.py:395-424 (D2H of three
  * volumes, scikit-image marching_cubes_lewiner at level 0 on the CPU, numpy vertex lookup).
  * Two calls because the output size is data dependent: vl_mesh_count sweeps the volume,
- * leaves per-cube case indices and per-unit offsets in the workspace and the grand totals in
- * d_totals (device long long[2]: [0] triangles T, [1] active cubes A); the caller reads them,
- * allocates the outputs plus an 8*A-byte scratch list, and calls vl_mesh_emit with the SAME
- * workspace.  Output is a triangle soup in cube order: d_verts f32[9T] (world frame,
+ * leaves one bit per voxel (value < level) and per-unit offsets in the workspace and the grand
+ * totals in d_totals (device long long[2]: [0] triangles T, [1] active cubes A); the caller reads
+ * them, allocates the outputs plus a scratch list of vl_mesh_list_bytes(T, A) bytes (8 B per active
+ * cube + 4 B per 256 triangles), and calls vl_mesh_emit with the SAME workspace (n_tris / n_active
+ * below the counted totals truncate the output to the first n_tris triangles in cube order; nothing
+ * is written beyond the sizes they imply).  Output is a triangle soup in cube order: d_verts f32[9T] (world frame,
  * verts * voxel_size + origin, :412), d_faces i32[3T] = 0..3T-1, d_norms f32[9T] (nullable,
  * flat normals), d_colors u8[9T] = (r, g, b) of the nearest voxel's folded colour with the
  * reference's uint8 wrap (:417-423), d_rem_out f32[3T].
