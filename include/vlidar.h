@@ -235,7 +235,7 @@ int vl_tsdf_init_integrate(float* d_tsdf, float* d_weight, float* d_color, float
                            int im_h, int im_w, void* d_workspace, size_t workspace_bytes, vl_stream stream);
 /* Workspace for vl_tsdf_init_integrate's shell sweep: the column table plus 8 B per image pixel.  With at least this
  * much workspace (and |fov| <= 35 deg, dy * dz <= 2^24, dx <= 65535, fewer than ~40000 image rows per radian) the fused
- * first integration brackets every voxel (plain sqrt, arcsine series, image row to a few hundredths) against the range image's
+ * first integration brackets every voxel (reciprocal square root, arcsine series to s^15, image row to a few thousandths) against the range image's
  * per-pixel [depth, depth + trunc] shell and runs the reference arithmetic only where the bracket cannot rule out an
  * update; bit-identical to vl_tsdf_init + vl_tsdf_integrate.  With vl_tsdf_workspace_bytes(dx, dy) only, or outside
  * those limits, every voxel takes the reference arithmetic.  vl_tsdf_integrate_ws with this much workspace takes the same
