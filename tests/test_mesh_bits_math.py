@@ -114,3 +114,36 @@ def test_rank_selection_enumerates_the_active_cubes_of_a_unit_in_cube_order(seed
   total = sum(counts)
   got = [_nth_active(act0, act1, excl, r) for r in range(total)]
   assert got == [int(j) for j in np.flatnonzero(bits)]
+
+
+@settings(max_examples=40, deadline=None)
+@given(seed=st.integers(0, 2 ** 31 - 1), n_active=st.integers(1, 3000), max_cnt=st.sampled_from([1, 2, 5]))
+def test_per_triangle_emit_finds_every_triangles_cube(seed, n_active, max_cnt):
+  """k_mesh_compact_bits leaves, per 256 triangle slots, the list index of the cube holding the first of them
+  (cta_first[kb] for the cube whose slot range contains kb * 256); k_mesh_emit loads 256 list entries from there and
+  each thread bisects for the last entry whose first slot is <= its triangle.  Every triangle must land on its cube."""
+  rng = np.random.default_rng(seed)
+  E = 256
+  cnt = rng.integers(1, max_cnt + 1, n_active)
+  first = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+  n_tris = int(cnt.sum())
+  n_ctas = (n_tris + E - 1) // E
+  cta_first = [None] * n_ctas
+  for slot in range(n_active):                      # the compaction's marker rule
+    tri, c = int(first[slot]), int(cnt[slot])
+    kb = (tri + E - 1) // E
+    if kb * E < tri + c and kb * E < n_tris:
+      assert cta_first[kb] is None
+      cta_first[kb] = slot
+  assert all(v is not None for v in cta_first)
+  owner = np.repeat(np.arange(n_active), cnt)       # the cube of every triangle
+  for k in range(n_ctas):
+    s_first = [int(first[cta_first[k] + i]) if cta_first[k] + i < n_active else 0xffffffff for i in range(E)]
+    for t in range(min(E, n_tris - k * E)):
+      T = k * E + t
+      lo, step = 0, E // 2
+      while step:
+        if s_first[lo + step] <= T:
+          lo += step
+        step >>= 1
+      assert cta_first[k] + lo == owner[T] and 0 <= T - s_first[lo] < cnt[owner[T]]
