@@ -102,3 +102,30 @@ def test_beam_angle_snapping_c_restatement_equals_the_python_loop(oracle, seed, 
     assert np.array_equal(a[k], b[k]), k
   for k in ("range_image", "proj_remissions"):
     assert np.array_equal(a[k].view(np.int32), b[k].view(np.int32)), k
+
+
+@settings(max_examples=200, deadline=None)
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 40), spread=st.sampled_from([0.0, 1e-9, 1e-7, 1e-3]))
+def test_one_atomic_min_key_reproduces_the_sequential_pixel_loop(seed, n, spread):
+  """vl_project.cu replaces the reference's sequential per-point loop (laserscan.py:373-382: a point wins a pixel when
+  its float64 depth is below the float32 value stored there, or the pixel is empty) by ONE 64-bit atomicMin per point on
+  key = float32(depth) bits << 32 | (depth < float32(depth) ? 0x7fffffff - i : 0x80000000 | i).  The winner of the
+  minimum key must be the loop's winner for every arrival order -- including float64 depths that collapse onto one
+  float32 value, where the loop's outcome depends on which side of that value each depth lies."""
+  rng = np.random.default_rng(seed)
+  base = rng.uniform(0.5, 80.0)
+  depth = base * (1.0 + spread * rng.integers(-3, 4, n))          # float64, many exact ties
+  # the reference's loop for one pixel
+  stored, winner = np.float32(0.0), -1
+  for i in range(n):
+    if depth[i] < stored or winner == -1:
+      stored, winner = np.float32(depth[i]), i
+  # the key
+  keys = []
+  for i in range(n):
+    R = np.float32(depth[i])
+    lo = (0x7fffffff - i) if depth[i] < np.float64(R) else (0x80000000 | i)
+    keys.append((int(R.view(np.uint32)) << 32) | lo)
+  k = min(keys)
+  got = (0x7fffffff - (k & 0xffffffff)) if (k & 0xffffffff) < 0x80000000 else (k & 0x7fffffff)
+  assert got == winner and np.uint32(k >> 32) == stored.view(np.uint32)
