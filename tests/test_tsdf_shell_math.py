@@ -101,3 +101,35 @@ def test_bracket_never_rules_out_a_voxel_the_kernel_string_would_change(seed, H,
     assert changes.sum() <= exact.sum()
     if zero_frac == 0.0:
       assert skipped.mean() > 0.6, skipped.mean()      # the bracket is worth having: most voxels never reach the arithmetic
+
+
+@settings(max_examples=60, deadline=None)
+@given(seed=st.integers(0, 2 ** 31 - 1), dy=st.integers(1, 4096), dz=st.integers(1, 4096))
+def test_float_index_decode_equals_the_integer_decode_away_from_slab_boundaries(seed, dy, dz):
+  """The kernel string decodes voxel_idx with float32 divisions (fusion_lidar.py:96-98), which lands in the neighbouring
+  slab for some indices beyond 2^24.  The shell sweep uses the integer decode for voxels at least kDecodeWindow = 256
+  away from a slab boundary (and dy * dz <= 2^24) and the float decode for the rest; the two must agree there, for any
+  volume below 2^31 voxels."""
+  rng = np.random.default_rng(seed)
+  slab = dy * dz
+  if slab > (1 << 24) or slab <= 512:
+    return
+  dx = int(min(65535, ((1 << 31) - 1) // slab))
+  n = 20000
+  x = rng.integers(0, dx, n)
+  rem = np.concatenate([rng.integers(256, slab - 256, n - 4), [256, 257, slab - 257, slab - 258]])
+  x[-4:] = dx - 1                                                  # the largest indices: the coarsest float spacing
+  idx = (x * slab + rem).astype(np.int64)
+  assert idx.max() < (1 << 31)
+  fx = np.floor(idx.astype(np.float32) / np.float32(slab))
+  r1 = (idx - fx.astype(np.int64) * slab)
+  fy = np.floor(r1.astype(np.float32) / np.float32(dz))
+  fz = r1 - fy.astype(np.int64) * dz
+  assert np.array_equal(fx.astype(np.int64), x)
+  assert np.array_equal(fy.astype(np.int64), rem // dz) and np.array_equal(fz, rem % dz)
+  # the sweep's own y / z decode: one multiplication by 1 / dz and a correction by one
+  vy = (rem.astype(np.float32) * (np.float32(1.0) / np.float32(dz))).astype(np.int64)
+  vz = rem - vy * dz
+  vy = np.where(vz < 0, vy - 1, np.where(vz >= dz, vy + 1, vy))
+  vz = rem - vy * dz
+  assert np.array_equal(vy, rem // dz) and (vz >= 0).all() and (vz < dz).all()
