@@ -90,8 +90,10 @@ def test_beam_angle_snapping_c_restatement_equals_the_python_loop(oracle, seed, 
   pts[rng.random(n) < 0.05] = 0.0
   ba = np.sort(rng.uniform(-0.6, 0.2, n_ba))
   ba = np.concatenate([ba, ba[:1], ba[-1:]]).tolist()      # duplicates
-  if n_ba >= 2:                                           # a point whose pitch is exactly half-way between two entries
-    mid = 0.5 * (ba[0] + ba[1])
+  if n_ba >= 2:                                           # a point whose pitch is next to the half-way mark of two entries
+    # (1e-7 rad off it: numpy's SIMD arcsin and libm's asin differ by an ulp on AVX-512 hosts, which would decide an
+    # exact mid-point differently in the two restatements; exact argmin ties are exercised by the duplicates above)
+    mid = 0.5 * (ba[0] + ba[1]) + 1e-7
     pts[0] = [np.cos(mid) * 7.0, 0.0, np.sin(mid) * 7.0]
   rem = rng.random(n).astype(np.float32)
   lab = rng.integers(0, 260, n).astype(np.uint32)
