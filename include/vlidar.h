@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VL_ABI_VERSION 1
+#define VL_ABI_VERSION 2
 
 #define VL_OK            0
 #define VL_EINVAL       -1   /* bad argument (null pointer, negative size, misaligned blob) */
@@ -66,6 +66,21 @@ int vl_ctrace_ids(const float* rays, const float* origin, const float* verts, co
                   int* tri_id);
 
 /* ------------------------------------------------------------------------------------
+ * Ray normalisation on the HOST, the reference's own arithmetic.
+ *
+ * Replaces: normalize() auxiliary/raytracer/Vector3.h:73-89 as the Ray constructor applies it (Ray.h:11-12):
+ * D = (x*x + y*y) + (z*z + 0) (the two hadd steps), r = rsqrtps(D), one Newton step
+ * r = 1.5*r + ((D * -0.5) * r) * (r * r), d = (x, y, z) * r -- every operation rounded separately (no FMA), the
+ * reciprocal square root estimate being the x86 instruction itself, so the result is bit for bit what the reference
+ * computes on the same host.  rays / out: HOST float32[3*n_rays] (may alias).  The rays are a per-sensor constant
+ * (create_rays, auxiliary/laserscan.py:1092-1119): normalise once, upload, and pass VL_RAYS_NORMALIZED to
+ * vl_beams_build / vl_trace so that the device's triangle test sees the reference's own unit vectors; without the flag
+ * the device normalises with IEEE 1/sqrt (<= 2 ulp away, which decides beams through shared edges differently).
+ * Returns VL_OK, or VL_EINVAL on a host without SSE (callers then stay with the device's IEEE normalisation).
+ * ---------------------------------------------------------------------------------- */
+int vl_normalize_rays(const float* rays, int n_rays, float* out);
+
+/* ------------------------------------------------------------------------------------
  * (i) LBVH build over the per-scan triangle mesh.
  *
  * Replaces: Triangle construction RayTracer.cpp:32-51 + BVH::BVH/build BVH.cpp:112-243.
@@ -87,7 +102,7 @@ int vl_bvh_status(const void* d_blob, int n_faces, vl_stream stream, int* info);
  * Replaces: the ray loop RayTracer.cpp:62-92, BVH::getIntersection BVH.cpp:19-110,
  * BBox::intersect BBox.cpp:52-100, Triangle::getIntersection Triangle.h:27-50,
  * normalize Vector3.h:73-89 (IEEE 1/sqrt instead of rsqrtps+NR).
- * d_rays float32[3*n_rays] (not normalised), d_origin float32[3] on the device.
+ * d_rays float32[3*n_rays] (not normalised; unit vectors with VL_RAYS_NORMALIZED), d_origin float32[3] on the device.
  * Outputs as in ctrace (hits only) except d_tri_id (nullable): written for every ray,
  * original face index or -1.  Exact-t ties go to the smaller face index.
  * flags: VL_TRACE_ZERO_MISSES writes 0 to all four outputs of a missing ray (what the
@@ -95,6 +110,7 @@ int vl_bvh_status(const void* d_blob, int n_faces, vl_stream stream, int* info);
  * ---------------------------------------------------------------------------------- */
 #define VL_TRACE_ZERO_MISSES 1
 #define VL_TRACE_PACKET      2   /* warp-packet traversal (8x4 beam tiles share one stack) instead of per-ray stacks */
+#define VL_RAYS_NORMALIZED   4   /* d_rays hold unit directions already (vl_normalize_rays): used as given, not re-normalised */
 int vl_trace(const void* d_blob, int n_faces, const float* d_rays, const float* d_origin,
              int n_rays, int height, float* d_endpoints, int* d_endcolors, float* d_range,
              float* d_endrem, int* d_tri_id, int flags, vl_stream stream);
@@ -110,7 +126,7 @@ int vl_trace(const void* d_blob, int n_faces, const float* d_rays, const float* 
  * vl_bvh_build + vl_trace (closest hit over all triangles, exact-t ties to the smaller face
  * index), no per-scan tree.
  *
- * vl_beams_build: d_rays f32[3*n_rays] (not normalised) -> d_beams, a caller-provided device
+ * vl_beams_build: d_rays f32[3*n_rays] (not normalised; unit vectors with VL_RAYS_NORMALIZED) -> d_beams, a caller-provided device
  * blob of vl_beams_bytes(n_rays, height) bytes, 256-byte aligned; valid for every later
  * vl_cast with the same (n_rays, height), any origin, any mesh.
  * vl_cast: mesh arrays as in vl_bvh_build, outputs / flags as in vl_trace; d_workspace of
@@ -123,7 +139,7 @@ int vl_trace(const void* d_blob, int n_faces, const float* d_rays, const float* 
  * ---------------------------------------------------------------------------------- */
 size_t vl_beams_bytes(int n_rays, int height);
 int vl_beams_build(const float* d_rays, int n_rays, int height, void* d_beams, size_t beams_bytes,
-                   vl_stream stream);
+                   int flags /* 0 or VL_RAYS_NORMALIZED */, vl_stream stream);
 size_t vl_cast_workspace_bytes(int n_rays, int n_faces);
 int vl_cast(const void* d_beams, const float* d_verts, const int* d_faces, const int* d_colors,
             const float* d_rem, int n_verts, int n_faces, const float* d_origin, int n_rays,
@@ -157,13 +173,21 @@ int vl_cast_graph_destroy(void* graph);
 /* Which device path the host-pointer ctrace / vl_ctrace_ids uses: 0 (default) = beam index +
  * vl_cast, 1 = vl_bvh_build + vl_trace.  Process-wide. */
 void vl_ctrace_method(int method);
+/* How ctrace / vl_ctrace_ids normalise the rays: 0 (default) = vl_normalize_rays on the host (the reference's bits),
+ * 1 = IEEE 1/sqrt on the device.  Process-wide. */
+void vl_ctrace_normalize(int mode);
+/* How often ctrace found the previous call's rays again (beam index reused) / had to rebuild it. */
+void vl_ctrace_cache_stats(long long* hits, long long* misses);
+/* Host wall time (ms) of the phases of the most recent ctrace: [0] ray comparison / beam index, [1] staging of the
+ * mesh + host->device issue, [2] cast + device->host (wait), [3] merge of the hits into the caller's buffers. */
+void vl_ctrace_timing(double* ms4);
 
 /* Test aid: same outputs by testing every triangle per ray (no BVH). */
 int vl_trace_bruteforce(const float* d_verts, const int* d_faces, const int* d_colors,
                         const float* d_rem, int n_verts, int n_faces, const float* d_rays,
                         const float* d_origin, int n_rays, int height, float* d_endpoints,
                         int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id,
-                        vl_stream stream);
+                        int flags /* 0 or VL_RAYS_NORMALIZED */, vl_stream stream);
 
 /* ------------------------------------------------------------------------------------
  * (iii) spherical range-image projection (atomicMin-on-depth scatter).

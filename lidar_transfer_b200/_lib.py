@@ -34,7 +34,11 @@ SIGNATURES = {
     "vl_bvh_status": (_i, [_vp, _i, _vp, _vp]),
     "vl_trace": (_i, [_vp, _i, _vp, _vp, _i, _i] + [_vp] * 5 + [_i, _vp]),
     "vl_beams_bytes": (_sz, [_i, _i]),
-    "vl_beams_build": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
+    "vl_beams_build": (_i, [_vp, _i, _i, _vp, _sz, _i, _vp]),
+    "vl_normalize_rays": (_i, [_vp, _i, _vp]),
+    "vl_ctrace_normalize": (None, [_i]),
+    "vl_ctrace_cache_stats": (None, [_vp, _vp]),
+    "vl_ctrace_timing": (None, [_vp]),
     "vl_cast_workspace_bytes": (_sz, [_i, _i]),
     "vl_cast": (_i, [_vp] * 5 + [_i, _i, _vp, _i, _i] + [_vp] * 5 + [_i, _vp, _sz, _vp]),
     "vl_cast_status": (_i, [_vp, _vp, _vp]),
@@ -47,7 +51,7 @@ SIGNATURES = {
     "vl_debug_cast_cells": (None, [_i]),
     "vl_debug_cast_ctas": (None, [_i]),
     "vl_debug_cast_setup_ctas": (None, [_i]),
-    "vl_trace_bruteforce": (_i, [_vp] * 4 + [_i, _i, _vp, _vp, _i, _i] + [_vp] * 6),
+    "vl_trace_bruteforce": (_i, [_vp] * 4 + [_i, _i, _vp, _vp, _i, _i] + [_vp] * 5 + [_i, _vp]),
     "vl_project_workspace_bytes": (_sz, [_l, _i, _i]),
     "vl_project": (_i, [_vp, _vp, _vp, _l, _d, _d, _i, _i, _i] + [_vp] * 7 + [_sz, _vp]),
     "vl_project_snap": (_i, [_vp, _vp, _vp, _l, _d, _d, _i, _i, _i, _vp, _i] + [_vp] * 7 + [_sz, _vp]),
@@ -92,8 +96,8 @@ def lib():
       fn = getattr(L, name)  # AttributeError here = header/library mismatch
       fn.restype = res
       fn.argtypes = args
-    if L.vl_abi_version() != 1:
-      raise ImportError("libvlidar ABI version %d, expected 1" % L.vl_abi_version())
+    if L.vl_abi_version() != 2:
+      raise ImportError("libvlidar ABI version %d, expected 2" % L.vl_abi_version())
     _lib = L
   return _lib
 

@@ -19,6 +19,7 @@ COMMON = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-l
           "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
 SOURCES = {
     "vl_api.cu": [],
+    "vl_host.cu": ["-Xcompiler", "-ffp-contract=off"],   # vl_normalize_rays: the reference's roundings, never an FMA
     "vl_bvh_build.cu": [],
     "vl_trace.cu": [],
     "vl_cast.cu": [],

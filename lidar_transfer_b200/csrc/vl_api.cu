@@ -1,9 +1,6 @@
-// vl_api.cu -- the C ABI of libvlidar.so (declared in include/vlidar.h).
-//
-// Device-pointer entry points are thin validated wrappers around the launchers.  The
-// host-pointer `ctrace` keeps the reference's own signature (auxiliary/raytracer/
-// RayTracer.cpp:116-124): it stages the caller's buffers into a grow-only device arena,
-// builds the LBVH, traces and copies the four outputs back -- synchronous, like the reference.
+// vl_api.cu -- the device-pointer C ABI of libvlidar.so (declared in include/vlidar.h): thin validated wrappers
+// around the launchers, error text, launch counter and the per-stage event profiler.  The host-pointer `ctrace`
+// (the reference's own signature) lives in vl_host.cu.
 #include <stdarg.h>
 #include <stddef.h>
 #include <string.h>
@@ -14,7 +11,6 @@
 // error text
 // ---------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static thread_local int g_ctrace_status = VL_OK;
 
 void vl_set_error(const char* fmt, ...) {
   va_list ap;
@@ -90,7 +86,6 @@ extern "C" int vl_profile_collect(double* stage_ms, long long* stage_launches) {
 
 extern "C" int vl_abi_version(void) { return VL_ABI_VERSION; }
 extern "C" const char* vl_last_error(void) { return g_err; }
-extern "C" int vl_ctrace_status(void) { return g_ctrace_status; }
 
 extern "C" int vl_device_count(void) {
   int n = 0;
@@ -153,7 +148,7 @@ extern "C" int vl_trace(const void* d_blob, int n_faces, const float* d_rays, co
 extern "C" int vl_trace_bruteforce(const float* d_verts, const int* d_faces, const int* d_colors, const float* d_rem,
                                    int n_verts, int n_faces, const float* d_rays, const float* d_origin, int n_rays,
                                    int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
-                                   int* d_tri_id, vl_stream stream) {
+                                   int* d_tri_id, int flags, vl_stream stream) {
   int rc = check_trace_args("vl_trace_bruteforce", d_rays, d_origin, n_rays, height, d_endpoints, d_endcolors, d_range, d_endrem);
   if (rc) return rc;
   if (n_faces < 0 || n_verts < 0 || (n_faces > 0 && (!d_verts || !d_faces || !d_colors || !d_rem))) {
@@ -161,7 +156,7 @@ extern "C" int vl_trace_bruteforce(const float* d_verts, const int* d_faces, con
     return VL_EINVAL;
   }
   return vl_trace_bruteforce_launch(d_verts, d_faces, d_colors, d_rem, n_verts, n_faces, d_rays, d_origin, n_rays, height,
-                                    d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, static_cast<cudaStream_t>(stream));
+                                    d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, flags, static_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------------------
@@ -172,7 +167,7 @@ extern "C" size_t vl_beams_bytes(int n_rays, int height) {
 }
 
 extern "C" int vl_beams_build(const float* d_rays, int n_rays, int height, void* d_beams, size_t beams_bytes,
-                              vl_stream stream) {
+                              int flags, vl_stream stream) {
   if (n_rays < 0 || height <= 0 || !d_beams || (((uintptr_t)d_beams) & 255) || (n_rays > 0 && !d_rays)) {
     vl_set_error("vl_beams_build: invalid argument (n_rays %d, height %d, beams %p)", n_rays, height, d_beams);
     return VL_EINVAL;
@@ -181,7 +176,7 @@ extern "C" int vl_beams_build(const float* d_rays, int n_rays, int height, void*
     vl_set_error("vl_beams_build: blob too small (%zu < %zu bytes)", beams_bytes, vl_beams_bytes(n_rays, height));
     return VL_ENOSPACE;
   }
-  return vl_beams_build_launch(d_rays, n_rays, height, d_beams, static_cast<cudaStream_t>(stream));
+  return vl_beams_build_launch(d_rays, n_rays, height, d_beams, flags, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t vl_cast_workspace_bytes(int n_rays, int n_faces) { return vl_cast_workspace_bytes_impl(n_rays, n_faces); }
@@ -266,130 +261,3 @@ extern "C" int vl_cast_status(const void* d_workspace, vl_stream stream, int* in
   return vl_cast_status_read(d_workspace, static_cast<cudaStream_t>(stream), info);
 }
 
-// ---------------------------------------------------------------------------
-// host-pointer ctrace: grow-only device arena + one stream, guarded by a mutex
-// ---------------------------------------------------------------------------
-namespace {
-struct HostCtx {
-  std::mutex mu;
-  cudaStream_t stream = nullptr;
-  char* arena = nullptr;
-  size_t arena_bytes = 0;
-};
-HostCtx g_ctx;
-std::atomic<int> g_ctrace_method{0};   // 0 = beam index + scene-streaming cast, 1 = LBVH build + traversal
-
-int ctx_reserve(HostCtx& c, size_t bytes) {
-  if (!c.stream) VL_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-  if (bytes > c.arena_bytes) {
-    if (c.arena) VL_CUDA_CHECK(cudaFree(c.arena));
-    c.arena = nullptr; c.arena_bytes = 0;
-    size_t want = bytes + bytes / 4;
-    VL_CUDA_CHECK(cudaMalloc(&c.arena, want));
-    c.arena_bytes = want;
-  }
-  return VL_OK;
-}
-}  // namespace
-
-extern "C" void vl_ctrace_method(int method) { g_ctrace_method.store(method == 1 ? 1 : 0); }
-
-static int ctrace_run(bool lbvh, bool* overflowed, const float* rays, const float* origin, const float* verts,
-                      const int* faces, const int* colors, const float* rem, int n_rays, int n_verts, int n_faces,
-                      int height, float* endpoints, int* endcolors, float* range, float* endrem, int* tri_id) {
-  HostCtx& c = g_ctx;
-  const size_t nr = (size_t)n_rays, nv = (size_t)n_verts, nf = (size_t)n_faces;
-  // arena carve-up
-  size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off = vl_align256(off + bytes); return o; };
-  const size_t o_blob = take(lbvh ? vl_bvh_blob_bytes(n_faces) : vl_beams_bytes(n_rays, height));
-  const size_t o_ws = take(lbvh ? 256 : vl_cast_workspace_bytes(n_rays, n_faces));
-  const size_t o_rays = take(12 * nr), o_origin = take(12), o_verts = take(12 * nv), o_faces = take(12 * nf);
-  const size_t o_colors = take(12 * nv), o_rem = take(4 * nv);
-  const size_t o_ep = take(12 * nr), o_ec = take(12 * nr), o_range = take(4 * nr), o_erem = take(4 * nr), o_id = take(4 * nr);
-  int rc = ctx_reserve(c, off);
-  if (rc) return rc;
-  char* A = c.arena;
-  cudaStream_t s = c.stream;
-  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_rays, rays, 12 * nr, cudaMemcpyHostToDevice, s));
-  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_origin, origin, 12, cudaMemcpyHostToDevice, s));
-  if (!lbvh) {   // the beam index only needs the rays: it is built while the mesh is still on its way
-    rc = vl_beams_build_launch((const float*)(A + o_rays), n_rays, height, A + o_blob, s);
-    if (rc) return rc;
-  }
-  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_verts, verts, 12 * nv, cudaMemcpyHostToDevice, s));
-  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_faces, faces, 12 * nf, cudaMemcpyHostToDevice, s));
-  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_colors, colors, 12 * nv, cudaMemcpyHostToDevice, s));
-  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_rem, rem, 4 * nv, cudaMemcpyHostToDevice, s));
-  if (lbvh) {
-    rc = vl_bvh_build_launch((const float*)(A + o_verts), (const int*)(A + o_faces), (const int*)(A + o_colors),
-                             (const float*)(A + o_rem), n_verts, n_faces, A + o_blob, s);
-    if (rc) return rc;
-  }
-  // misses must leave the caller's buffers untouched (RayTracer.cpp:72-90): round-trip their content
-  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_ep, endpoints, 12 * nr, cudaMemcpyHostToDevice, s));
-  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_ec, endcolors, 12 * nr, cudaMemcpyHostToDevice, s));
-  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_range, range, 4 * nr, cudaMemcpyHostToDevice, s));
-  VL_CUDA_CHECK(cudaMemcpyAsync(A + o_erem, endrem, 4 * nr, cudaMemcpyHostToDevice, s));
-  if (lbvh)
-    rc = vl_trace_launch(A + o_blob, n_faces, (const float*)(A + o_rays), (const float*)(A + o_origin), n_rays, height,
-                         (float*)(A + o_ep), (int*)(A + o_ec), (float*)(A + o_range), (float*)(A + o_erem),
-                         tri_id ? (int*)(A + o_id) : nullptr, 0, s);
-  else
-    rc = vl_cast_launch(A + o_blob, (const float*)(A + o_verts), (const int*)(A + o_faces), (const int*)(A + o_colors),
-                        (const float*)(A + o_rem), n_verts, n_faces, (const float*)(A + o_origin), n_rays, height,
-                        (float*)(A + o_ep), (int*)(A + o_ec), (float*)(A + o_range), (float*)(A + o_erem),
-                        tri_id ? (int*)(A + o_id) : nullptr, 0, A + o_ws, s);
-  if (rc) return rc;
-  VL_CUDA_CHECK(cudaMemcpyAsync(endpoints, A + o_ep, 12 * nr, cudaMemcpyDeviceToHost, s));
-  VL_CUDA_CHECK(cudaMemcpyAsync(endcolors, A + o_ec, 12 * nr, cudaMemcpyDeviceToHost, s));
-  VL_CUDA_CHECK(cudaMemcpyAsync(range, A + o_range, 4 * nr, cudaMemcpyDeviceToHost, s));
-  VL_CUDA_CHECK(cudaMemcpyAsync(endrem, A + o_erem, 4 * nr, cudaMemcpyDeviceToHost, s));
-  if (tri_id) VL_CUDA_CHECK(cudaMemcpyAsync(tri_id, A + o_id, 4 * nr, cudaMemcpyDeviceToHost, s));
-  int st[2] = {0, 0};   // {n_bad_faces, overflow}: the first two ints of the cast header; n_bad_faces of the LBVH header
-  VL_CUDA_CHECK(cudaMemcpyAsync(st, lbvh ? A + o_blob + offsetof(VlHeader, n_bad_faces) : A + o_ws,
-                                lbvh ? sizeof(int) : 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-  VL_CUDA_CHECK(cudaStreamSynchronize(s));
-  if (!lbvh && st[1]) {   // the cast ran out of work units before touching any output: take the tree instead
-    *overflowed = true;
-    return VL_OK;
-  }
-  const int n_bad = st[0];
-  if (n_bad > 0) {
-    vl_set_error("ctrace: %d face(s) reference a vertex outside [0, %d); they were skipped", n_bad, n_verts);
-    return VL_EBADMESH;
-  }
-  return VL_OK;
-}
-
-
-extern "C" int vl_ctrace_ids(const float* rays, const float* origin, const float* verts, const int* faces,
-                             const int* colors, const float* rem, int n_rays, int n_verts, int n_faces, int height,
-                             float* endpoints, int* endcolors, float* range, float* endrem, int* tri_id) {
-  if (n_rays < 0 || n_verts < 0 || n_faces < 0 || height <= 0 || !origin ||
-      (n_rays > 0 && (!rays || !endpoints || !endcolors || !range || !endrem)) ||
-      (n_faces > 0 && (!verts || !faces || !colors || !rem))) {
-    vl_set_error("ctrace: invalid argument (n_rays %d, n_verts %d, n_faces %d, height %d)", n_rays, n_verts, n_faces, height);
-    return VL_EINVAL;
-  }
-  int n_dev = 0;
-  VL_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
-  if (n_dev <= 0) { vl_set_error("ctrace: no CUDA device (libvlidar has no CPU fallback)"); return VL_ECUDA; }
-  if (n_rays == 0) return VL_OK;
-  std::lock_guard<std::mutex> lock(g_ctx.mu);
-  bool overflowed = false;
-  int rc = ctrace_run(g_ctrace_method.load() == 1, &overflowed, rays, origin, verts, faces, colors, rem, n_rays, n_verts,
-                      n_faces, height, endpoints, endcolors, range, endrem, tri_id);
-  if (rc == VL_OK && overflowed)
-    rc = ctrace_run(true, &overflowed, rays, origin, verts, faces, colors, rem, n_rays, n_verts, n_faces, height, endpoints,
-                    endcolors, range, endrem, tri_id);
-  return rc;
-}
-
-extern "C" void ctrace(float* rays, float* origin, float* verts, int* faces, int* colors, float* rem, int n_rays,
-                       int n_verts, int n_faces, int height, float* endpoints, int* endcolors, float* range,
-                       float* endrem) {
-  g_ctrace_status = vl_ctrace_ids(rays, origin, verts, faces, colors, rem, n_rays, n_verts, n_faces, height, endpoints,
-                                  endcolors, range, endrem, nullptr);
-  if (g_ctrace_status != VL_OK) fprintf(stderr, "libvlidar ctrace error %d: %s\n", g_ctrace_status, g_err);
-}

@@ -162,16 +162,17 @@ __global__ void k_beam_init(VlBeamHeader* hdr, int* cell_cnt, int ncell_p1, int*
   if (blockIdx.x == 0 && threadIdx.x == 0) { hdr->sine_min_ord = 0xffffffffu; hdr->sine_max_ord = 0u; hdr->n_binned = 0; }
 }
 
-// normalised direction (the one vl_tri_hit is given, vl_normalize = Vector3.h:73-89 with IEEE 1/sqrt) + azimuth
+// normalised direction (the one vl_tri_hit is given: vl_normalize = Vector3.h:73-89 with IEEE 1/sqrt, or the caller's
+// own unit vectors -- vl_normalize_rays, the reference's rsqrtps + Newton step evaluated on the host) + azimuth
 __global__ void __launch_bounds__(kCastThreads)
-k_beam_prep(const float* __restrict__ rays, int n, float4* __restrict__ dir, VlBeamHeader* hdr) {
+k_beam_prep(const float* __restrict__ rays, int n, bool prenorm, float4* __restrict__ dir, VlBeamHeader* hdr) {
   __shared__ float s_min[kCastWarps], s_max[kCastWarps];
   __shared__ int s_cnt[kCastWarps];
   const int r = blockIdx.x * kCastThreads + threadIdx.x;
   float smin = INFINITY, smax = -INFINITY;
   int cnt = 0;
   if (r < n) {
-    const float3 d = vl_normalize(__ldg(rays + 3 * (size_t)r), __ldg(rays + 3 * (size_t)r + 1), __ldg(rays + 3 * (size_t)r + 2));
+    const float3 d = vl_ray_dir(rays, (size_t)r, prenorm);
     float yaw = pseudo_yaw(d.y, d.x);
     const bool ok = isfinite(d.x) && isfinite(d.y) && isfinite(d.z) && isfinite(yaw);
     if (!ok) yaw = __int_as_float(0x7fc00000);
@@ -740,7 +741,7 @@ CastLayout cast_layout(int n_rays, int n_faces) {
 
 size_t vl_cast_workspace_bytes_impl(int n_rays, int n_faces) { return cast_layout(n_rays, n_faces).total; }
 
-int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_beams, cudaStream_t stream) {
+int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_beams, int flags, cudaStream_t stream) {
   const BeamLayout L = beam_layout(n_rays, height);
   char* B = static_cast<char*>(d_beams);
   VlBeamHeader* hdr = reinterpret_cast<VlBeamHeader*>(B);
@@ -758,7 +759,7 @@ int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_b
   VL_LAUNCH_CHECK("k_beam_init");
   const int nb = (L.n + kCastThreads - 1) / kCastThreads;
   if (L.n > 0) {
-    k_beam_prep<<<nb, kCastThreads, 0, stream>>>(d_rays, L.n, dir, hdr);
+    k_beam_prep<<<nb, kCastThreads, 0, stream>>>(d_rays, L.n, (flags & VL_RAYS_NORMALIZED) != 0, dir, hdr);
     VL_LAUNCH_CHECK("k_beam_prep");
     k_beam_count<<<nb, kCastThreads, 0, stream>>>(dir, L.n, hdr, L.cw, L.ch, cell_start, fine);
     VL_LAUNCH_CHECK("k_beam_count");

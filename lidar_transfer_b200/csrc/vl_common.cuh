@@ -190,6 +190,13 @@ __device__ __forceinline__ float3 vl_normalize(float x, float y, float z) {
   return make_float3(__fmul_rn(x, r), __fmul_rn(y, r), __fmul_rn(z, r));
 }
 
+// direction of ray r: normalised here, or -- VL_RAYS_NORMALIZED -- taken as given (the host normalised it with the
+// reference's own rsqrtps + Newton step, vl_normalize_rays, so vl_tri_hit sees the reference's bits)
+__device__ __forceinline__ float3 vl_ray_dir(const float* __restrict__ rays, size_t r, bool prenorm) {
+  const float x = __ldg(rays + 3 * r), y = __ldg(rays + 3 * r + 1), z = __ldg(rays + 3 * r + 2);
+  return prenorm ? make_float3(x, y, z) : vl_normalize(x, y, z);
+}
+
 // internal launchers (implemented in the .cu files, called by vl_api.cu)
 int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_colors, const float* d_rem,
                         int n_verts, int n_faces, void* d_blob, cudaStream_t stream);
@@ -199,11 +206,11 @@ int vl_trace_launch(const void* d_blob, int n_faces, const float* d_rays, const 
 int vl_trace_bruteforce_launch(const float* d_verts, const int* d_faces, const int* d_colors, const float* d_rem,
                                int n_verts, int n_faces, const float* d_rays, const float* d_origin, int n_rays,
                                int height, float* d_endpoints, int* d_endcolors, float* d_range,
-                               float* d_endrem, int* d_tri_id, cudaStream_t stream);
+                               float* d_endrem, int* d_tri_id, int flags, cudaStream_t stream);
 // vl_cast.cu
 size_t vl_beams_bytes_impl(int n_rays, int height);
 size_t vl_cast_workspace_bytes_impl(int n_rays, int n_faces);
-int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_beams, cudaStream_t stream);
+int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_beams, int flags, cudaStream_t stream);
 int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces, const int* d_colors,
                    const float* d_rem, int n_verts, int n_faces, const float* d_origin, int n_rays, int height,
                    float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id, int flags,

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kTraceThreads)
 k_trace(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ nodes, const VlTri* __restrict__ tris,
         const int4* __restrict__ c0, const float* __restrict__ rays, const float* __restrict__ origin, int n_traced,
         int width, int height, float* __restrict__ endpoints, int* __restrict__ endcolors, float* __restrict__ range,
-        float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses, int* __restrict__ stats) {
+        float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses, bool prenorm, int* __restrict__ stats) {
   __shared__ uint2 sstack[kSmemStack][kTraceThreads];
   int r;
   if (kTiled) {
@@ -140,7 +140,7 @@ k_trace(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ nodes, cons
     if (r >= n_traced) return;
   }
   const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
-  const float3 d = vl_normalize(__ldg(rays + 3 * (size_t)r), __ldg(rays + 3 * (size_t)r + 1), __ldg(rays + 3 * (size_t)r + 2));
+  const float3 d = vl_ray_dir(rays, (size_t)r, prenorm);
   const float3 inv_d = make_float3(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));  // Ray.h:11-12
   Hit best;
   best.t = 999999999.f;  // BVH.cpp:20
@@ -184,13 +184,13 @@ k_trace_bruteforce(const float* __restrict__ verts, const int* __restrict__ face
                    const float* __restrict__ rem, int n_verts, int n_faces, const float* __restrict__ rays,
                    const float* __restrict__ origin, int n_traced, float* __restrict__ endpoints,
                    int* __restrict__ endcolors, float* __restrict__ range, float* __restrict__ endrem,
-                   int* __restrict__ tri_id) {
+                   int* __restrict__ tri_id, bool prenorm) {
   __shared__ float4 sv0[kBfTile], se1[kBfTile], se2[kBfTile];
   const int r = blockIdx.x * kTraceThreads + threadIdx.x;
   const bool active = r < n_traced;
   const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
   float3 d = make_float3(0.f, 0.f, 0.f);
-  if (active) d = vl_normalize(__ldg(rays + 3 * (size_t)r), __ldg(rays + 3 * (size_t)r + 1), __ldg(rays + 3 * (size_t)r + 2));
+  if (active) d = vl_ray_dir(rays, (size_t)r, prenorm);
   float best_t = 999999999.f;
   int best = -1;
   for (int base = 0; base < n_faces; base += kBfTile) {
@@ -256,7 +256,7 @@ k_trace_packet(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ node
                const int4* __restrict__ c0, const float* __restrict__ rays, const float* __restrict__ origin,
                int width, int height, float* __restrict__ endpoints, int* __restrict__ endcolors,
                float* __restrict__ range, float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses,
-               int* __restrict__ stats) {
+               bool prenorm, int* __restrict__ stats) {
   constexpr int TH = 32 / TW;
   __shared__ float s_tn[kPktWarps][kPktStack][32];
   __shared__ int s_ref[kPktWarps][kPktStack];
@@ -269,7 +269,7 @@ k_trace_packet(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ node
   const size_t r = (size_t)row * width + col;
   const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
   float3 d = make_float3(0.f, 0.f, 0.f);
-  if (valid) d = vl_normalize(__ldg(rays + 3 * r), __ldg(rays + 3 * r + 1), __ldg(rays + 3 * r + 2));
+  if (valid) d = vl_ray_dir(rays, r, prenorm);
   const float3 inv_d = make_float3(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));
   // a lane with a zero / NaN direction component needs the NaN-filtering slab (BBox.cpp:70-80)
   const bool odd_lane = valid && (d.x == 0.f || d.y == 0.f || d.z == 0.f || !(d.x == d.x));
@@ -378,7 +378,7 @@ int vl_trace_launch(const void* d_blob, int n_faces, const float* d_rays, const 
   const VlNode* nodes = reinterpret_cast<const VlNode*>(blob + L.off_nodes);
   const VlTri* tris = reinterpret_cast<const VlTri*>(blob + L.off_tris);
   const int4* c0 = reinterpret_cast<const int4*>(blob + L.off_c0);
-  const bool zm = (flags & VL_TRACE_ZERO_MISSES) != 0;
+  const bool zm = (flags & VL_TRACE_ZERO_MISSES) != 0, pn = (flags & VL_RAYS_NORMALIZED) != 0;
   int mode = g_debug_mode;
   // measured on B200 (gpurun_out/trace_stats_710.txt): per-thread stacks 0.180 ms, 8x4 packets 0.185 ms per
   // 131 072 rays over 1.05 M triangles -- packets test 1.65x the triangles, so per-thread is the default
@@ -388,11 +388,11 @@ int vl_trace_launch(const void* d_blob, int n_faces, const float* d_rays, const 
   if (mode == 1) {
     const int nb = (int)((n_traced + kTraceThreads - 1) / kTraceThreads);
     k_trace<false><<<nb, kTraceThreads, 0, stream>>>(hdr, nodes, tris, c0, d_rays, d_origin, (int)n_traced, width, height,
-                                                    d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, zm, g_debug_stats);
+                                                    d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, zm, pn, g_debug_stats);
   } else if (mode == 2) {
     const int nb = ((width + 15) / 16) * ((height + 7) / 8);
     k_trace<true><<<nb, kTraceThreads, 0, stream>>>(hdr, nodes, tris, c0, d_rays, d_origin, (int)n_traced, width, height,
-                                                   d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, zm, g_debug_stats);
+                                                   d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, zm, pn, g_debug_stats);
   } else {
     const int tw = mode, th = 32 / mode;
     const long long n_tiles = (long long)((width + tw - 1) / tw) * ((height + th - 1) / th);
@@ -400,7 +400,7 @@ int vl_trace_launch(const void* d_blob, int n_faces, const float* d_rays, const 
 #define VL_PKT(TW_)                                                                                              \
   k_trace_packet<TW_><<<nb, kPktWarps * 32, 0, stream>>>(hdr, nodes, tris, c0, d_rays, d_origin, width, height,   \
                                                          d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id,  \
-                                                         zm, g_debug_stats)
+                                                         zm, pn, g_debug_stats)
     if (tw == 8) VL_PKT(8); else if (tw == 16) VL_PKT(16); else if (tw == 4) VL_PKT(4); else VL_PKT(32);
 #undef VL_PKT
   }
@@ -411,7 +411,7 @@ int vl_trace_launch(const void* d_blob, int n_faces, const float* d_rays, const 
 int vl_trace_bruteforce_launch(const float* d_verts, const int* d_faces, const int* d_colors, const float* d_rem,
                                int n_verts, int n_faces, const float* d_rays, const float* d_origin, int n_rays,
                                int height, float* d_endpoints, int* d_endcolors, float* d_range,
-                               float* d_endrem, int* d_tri_id, cudaStream_t stream) {
+                               float* d_endrem, int* d_tri_id, int flags, cudaStream_t stream) {
   const int width = n_rays / height;
   const long long n_traced = (long long)width * height;
   if (d_tri_id && n_rays > n_traced)
@@ -420,7 +420,7 @@ int vl_trace_bruteforce_launch(const float* d_verts, const int* d_faces, const i
   const int nb = (int)((n_traced + kTraceThreads - 1) / kTraceThreads);
   k_trace_bruteforce<<<nb, kTraceThreads, 0, stream>>>(d_verts, d_faces, d_colors, d_rem, n_verts, n_faces, d_rays,
                                                       d_origin, (int)n_traced, d_endpoints, d_endcolors, d_range,
-                                                      d_endrem, d_tri_id);
+                                                      d_endrem, d_tri_id, (flags & VL_RAYS_NORMALIZED) != 0);
   VL_LAUNCH_CHECK("k_trace_bruteforce");
   return VL_OK;
 }

@@ -77,6 +77,35 @@ class Bvh:
 
 
 TRACE_ZERO_MISSES = 1
+RAYS_NORMALIZED = 4
+
+# How ray directions are normalised before the triangle test (normalize(), auxiliary/raytracer/Vector3.h:73-89):
+#   "sse"  -- on the host by lib().vl_normalize_rays, the reference's own rsqrtps + Newton step: the device sees the
+#             reference's unit vectors bit for bit (x86 hosts; the default there);
+#   "ieee" -- on the device with IEEE 1 / sqrt (<= 2 ulp from the reference's; portable).
+DEFAULT_NORMALIZE = "sse"
+
+
+def normalize_rays(rays):
+  """Host-side normalize() of the reference (Vector3.h:73-89) on a ray set: numpy / torch f32[R,3] -> numpy f32[3R]."""
+  if torch.is_tensor(rays):
+    rays = rays.detach().cpu().numpy()
+  rays = np.ascontiguousarray(rays, np.float32).reshape(-1)
+  out = np.empty_like(rays)
+  check(lib().vl_normalize_rays(ctypes.c_void_p(rays.ctypes.data), rays.size // 3, ctypes.c_void_p(out.ctypes.data)))
+  return out
+
+
+def _prepare_rays(rays, normalize, device):
+  """-> (flat CUDA tensor, flags for the library)."""
+  mode = DEFAULT_NORMALIZE if normalize is None else normalize
+  if mode == "sse":
+    return _dev(normalize_rays(rays), torch.float32, device).reshape(-1), RAYS_NORMALIZED
+  if mode == "ieee":
+    return _dev(rays, torch.float32, device).reshape(-1), 0
+  if mode == "given":   # the caller's own unit vectors, used as they are
+    return _dev(rays, torch.float32, device).reshape(-1), RAYS_NORMALIZED
+  raise ValueError("normalize must be 'sse', 'ieee' or 'given'")
 
 
 def _trace_outputs(n_rays, dev, out, want_ids, alloc=torch.zeros):
@@ -95,23 +124,23 @@ def _trace_outputs(n_rays, dev, out, want_ids, alloc=torch.zeros):
   return out
 
 
-def trace(bvh, rays, origin, height, out=None, want_ids=True, zero_misses=False):
+def trace(bvh, rays, origin, height, out=None, want_ids=True, zero_misses=False, normalize=None):
   """(ii) closest-hit ray cast; the device-resident equivalent of C_Trace
   (auxiliary/raytracer/RayTracerCython.pyx:15-33 -> RayTracer.cpp:56-92).
 
-  rays f32[R,3] (any length, normalised on device), origin f32[3].  Returns dict of flat CUDA
+  rays f32[R,3] (any length; normalised as `normalize` says, see DEFAULT_NORMALIZE), origin f32[3].  Returns dict of flat CUDA
   tensors: endpoints[3R], endcolors[3R], range[R], endrem[R] (written for hits only -- pass
   `out` to keep previous content, or zero_misses=True to have the kernel write 0 for misses)
   and tri_id[R] (original face index, -1 = miss)."""
   dev = bvh.blob.device
-  rays = _dev(rays, torch.float32, dev).reshape(-1)
+  rays, ray_flags = _prepare_rays(rays, normalize, dev)
   origin = _dev(origin, torch.float32, dev).reshape(-1)
   n_rays = rays.numel() // 3
   out = _trace_outputs(n_rays, dev, out, want_ids, torch.empty if zero_misses else torch.zeros)
   with torch.cuda.device(dev):
     check(lib().vl_trace(_ptr(bvh.blob), bvh.n_faces, _ptr(rays), _ptr(origin), n_rays, int(height),
                          _ptr(out["endpoints"]), _ptr(out["endcolors"]), _ptr(out["range"]), _ptr(out["endrem"]),
-                         _ptr(out.get("tri_id")), TRACE_ZERO_MISSES if zero_misses else 0, _stream()))
+                         _ptr(out.get("tri_id")), (TRACE_ZERO_MISSES if zero_misses else 0) | ray_flags, _stream()))
   return out
 
 
@@ -120,17 +149,19 @@ class Beams:
 
   rays f32[R,3] as MultiSemLaserScan.create_rays returns them (auxiliary/laserscan.py:1092-1119) or any
   other ray set -- the ctrace ABI gives all rays one origin (RayTracer.cpp:116-124), which is all the
-  index relies on.  `height` as in C_Trace (width = n_rays // height rays per row are cast)."""
+  index relies on.  `height` as in C_Trace (width = n_rays // height rays per row are cast).  `normalize`: see
+  DEFAULT_NORMALIZE (the directions are normalised once, here)."""
 
-  def __init__(self, rays, height, device=None):
+  def __init__(self, rays, height, device=None, normalize=None):
     require_cuda()
-    self.rays = _dev(rays, torch.float32, device).reshape(-1)
+    self.rays, ray_flags = _prepare_rays(rays, normalize, device)
     dev = self.rays.device
     self.n_rays = self.rays.numel() // 3
     self.height = int(height)
     self.blob = torch.empty(lib().vl_beams_bytes(self.n_rays, self.height), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-      check(lib().vl_beams_build(_ptr(self.rays), self.n_rays, self.height, _ptr(self.blob), self.blob.numel(), _stream()))
+      check(lib().vl_beams_build(_ptr(self.rays), self.n_rays, self.height, _ptr(self.blob), self.blob.numel(), ray_flags,
+                                 _stream()))
 
   def workspace(self, max_faces):
     """Scratch for cast() on meshes of up to max_faces triangles (8 B per ray + 12 B per face)."""
@@ -171,7 +202,7 @@ def cast(beams, verts, faces, colors, rem, origin, out=None, want_ids=True, zero
   return out
 
 
-def trace_bruteforce(verts, faces, colors, rem, rays, origin, height, out=None):
+def trace_bruteforce(verts, faces, colors, rem, rays, origin, height, out=None, normalize=None):
   """Test aid: same outputs without a BVH (every triangle per ray)."""
   require_cuda()
   verts = _dev(verts, torch.float32).reshape(-1)
@@ -179,7 +210,7 @@ def trace_bruteforce(verts, faces, colors, rem, rays, origin, height, out=None):
   faces = _dev(faces, torch.int32, dev).reshape(-1)
   colors = _dev(colors, torch.int32, dev).reshape(-1)
   rem = _dev(rem, torch.float32, dev).reshape(-1)
-  rays = _dev(rays, torch.float32, dev).reshape(-1)
+  rays, ray_flags = _prepare_rays(rays, normalize, dev)
   origin = _dev(origin, torch.float32, dev).reshape(-1)
   n_rays = rays.numel() // 3
   out = _trace_outputs(n_rays, dev, out, True)
@@ -187,7 +218,7 @@ def trace_bruteforce(verts, faces, colors, rem, rays, origin, height, out=None):
     check(lib().vl_trace_bruteforce(_ptr(verts), _ptr(faces), _ptr(colors), _ptr(rem), verts.numel() // 3,
                                     faces.numel() // 3, _ptr(rays), _ptr(origin), n_rays, int(height),
                                     _ptr(out["endpoints"]), _ptr(out["endcolors"]), _ptr(out["range"]),
-                                    _ptr(out["endrem"]), _ptr(out["tri_id"]), _stream()))
+                                    _ptr(out["endrem"]), _ptr(out["tri_id"]), ray_flags, _stream()))
   return out
 
 
@@ -414,7 +445,8 @@ def compare(source_color, target_color, source_label, target_label, source_range
   return out
 
 
-def ctrace_host(rays, origin, verts, faces, colors, rem, height, outputs=None, want_ids=False, method=None):
+def ctrace_host(rays, origin, verts, faces, colors, rem, height, outputs=None, want_ids=False, method=None,
+                normalize=None):
   """The reference-compatible HOST-pointer entry point (extern "C" ctrace / vl_ctrace_ids) on numpy
   buffers: H2D, build, trace, D2H inside the call.  outputs: dict of preallocated numpy arrays
   (endpoints, endcolors, range, endrem) updated in place for hits."""
@@ -440,6 +472,7 @@ def ctrace_host(rays, origin, verts, faces, colors, rem, height, outputs=None, w
   p = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
   if method is not None:  # "cast" (default of the library) or "lbvh"
     lib().vl_ctrace_method({"cast": 0, "lbvh": 1}[method])
+  lib().vl_ctrace_normalize({"sse": 0, "ieee": 1}[DEFAULT_NORMALIZE if normalize is None else normalize])
   check(lib().vl_ctrace_ids(p(rays), p(origin), p(verts), p(faces), p(colors), p(rem), n_rays, verts.size // 3,
                             faces.size // 3, int(height), p(chk(outputs["endpoints"], f32, "endpoints")),
                             p(chk(outputs["endcolors"], i32, "endcolors")), p(chk(outputs["range"], f32, "range")),

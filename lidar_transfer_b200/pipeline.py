@@ -38,6 +38,8 @@ class _Slot:
                     tri_id=torch.empty(n_rays, dtype=i32, device=dev))
     self.done = torch.cuda.Event()
     self.busy = False
+    self.inputs = None   # the mesh tensors of the scan in flight: held until it has drained (see ScanRenderer.submit)
+    self.owner = None
     # first 16 bytes of the cast workspace header (n_bad_faces, overflow, ...), copied back after every scan
     self.h_status = torch.zeros(4, dtype=torch.int32, pin_memory=True)
     self.h_status_np = self.h_status.numpy()
@@ -63,25 +65,40 @@ class _Slot:
       self.d_rem = torch.empty(max_verts, dtype=f32, device=dev)
       self.h_out = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in self.out.items()}
 
+  def result(self):
+    """Waits for THIS slot's scan, raises VlidarError(VL_ENOSPACE) if its cast ran out of work units (outputs invalid;
+    the mesh needs ScanRenderer(method='lbvh')), releases the input tensors and returns the output dict (`h_out` for a
+    host-fed scan).  Idempotent until the slot is reused."""
+    if self.busy:
+      self.done.synchronize()
+      self.busy = False
+      self.inputs = None
+      self.owner._check(self)
+    return getattr(self, "h_out", None) if self.owner.host_io and self.host_fed else self.out
+
 
 class ScanRenderer:
   """rays f32[R,3] and origin f32[3] are fixed per renderer (one target sensor)."""
 
   def __init__(self, rays, origin, height, max_verts, max_faces, n_streams=4, device=None, host_io=False,
-               method="cast", use_graph=True):
+               method="cast", use_graph=True, normalize=None):
     engine.require_cuda()
     if method not in ("cast", "lbvh"):
       raise ValueError("method must be 'cast' or 'lbvh'")
     self.method = method
     self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    self.rays = engine._dev(rays, torch.float32, self.dev).reshape(-1)
+    # directions normalised once per sensor (engine.DEFAULT_NORMALIZE: on the host, the reference's own arithmetic)
+    self.rays, self.ray_flags = engine._prepare_rays(rays, normalize, self.dev)
     self.origin = engine._dev(origin, torch.float32, self.dev).reshape(-1)
     self.n_rays = self.rays.numel() // 3
     self.height = int(height)
     self.max_verts, self.max_faces = int(max_verts), int(max_faces)
     self.slots = [_Slot(self.dev, max_verts, max_faces, self.n_rays, host_io, method) for _ in range(n_streams)]
+    for s in self.slots:
+      s.owner, s.host_fed = self, False
     # the beam index depends on the sensor only: built once here, shared (read-only) by every stream
-    self.beams = engine.Beams(self.rays, self.height, self.dev) if method == "cast" else None
+    self.beams = (engine.Beams(self.rays, self.height, self.dev, normalize="given" if self.ray_flags else "ieee")
+                  if method == "cast" else None)
     if self.beams is not None:
       torch.cuda.current_stream(self.dev).synchronize()
     self.host_io = host_io
@@ -121,9 +138,7 @@ class ScanRenderer:
     s = self.slots[self._next]
     self._next = (self._next + 1) % len(self.slots)
     if s.busy:
-      s.done.synchronize()  # the slot's previous scan must have drained before its buffers are reused
-      s.busy = False
-      self._check(s)
+      s.result()  # the slot's previous scan must have drained before its buffers are reused (raises if it overflowed)
     return s
 
   def _launch(self, s, verts, faces, colors, rem, n_verts, n_faces):
@@ -141,16 +156,20 @@ class ScanRenderer:
                          s.blob.numel(), st))
     check(L.vl_trace(_ptr(s.blob), n_faces, _ptr(self.rays), _ptr(self.origin), self.n_rays, self.height,
                      _ptr(s.out["endpoints"]), _ptr(s.out["endcolors"]), _ptr(s.out["range"]), _ptr(s.out["endrem"]),
-                     _ptr(s.out["tri_id"]), engine.TRACE_ZERO_MISSES, st))
+                     _ptr(s.out["tri_id"]), engine.TRACE_ZERO_MISSES | self.ray_flags, st))
 
   def submit(self, verts, faces, colors, rem):
     """Device-resident mesh (flat CUDA tensors: verts f32[3N_v], faces i32[3N_t], colors i32[3N_v],
-    rem f32[N_v]).  Asynchronous; returns the slot whose `.out` tensors hold the result once
-    `slot.done` has completed."""
+    rem f32[N_v]).  Asynchronous; returns the slot: `slot.result()` waits for this scan, checks it and returns the
+    output tensors (`slot.out`; valid until the slot is reused, n_streams submissions later).
+    Lifetime: the kernels read the four tensors on the slot's own stream, which the caching allocator does not know
+    about -- the slot therefore keeps references to them until the scan has drained (result() / wait() / reuse of the
+    slot), so the caller may drop or overwrite its own references right after submit()."""
     n_verts, n_faces = verts.numel() // 3, faces.numel() // 3
     if n_faces > self.max_faces:
       raise ValueError("mesh has %d faces, renderer was sized for %d" % (n_faces, self.max_faces))
     s = self._acquire()
+    s.inputs, s.host_fed = (verts, faces, colors, rem), False
     if torch.cuda.current_device() != self._dev_index:   # launches go to the renderer's device whatever the caller's is
       with torch.cuda.device(self.dev):
         return self._submit_on_device(s, verts, faces, colors, rem, n_verts, n_faces)
@@ -182,7 +201,8 @@ class ScanRenderer:
 
   def submit_host(self, verts, faces, colors, rem):
     """Host mesh (pinned or pageable torch CPU tensors / numpy arrays, flat, reference dtypes):
-    H2D on the slot's stream, build, trace, D2H of the five outputs into the slot's pinned buffers."""
+    H2D on the slot's stream, build, trace, D2H of the five outputs into the slot's pinned buffers.  The slot keeps
+    references to the host tensors until the scan has drained (the copies are asynchronous for pinned memory)."""
     if not self.host_io:
       raise RuntimeError("renderer was created without host_io=True")
     as_t = lambda a: torch.from_numpy(a) if isinstance(a, np.ndarray) else a
@@ -191,6 +211,7 @@ class ScanRenderer:
     if n_faces > self.max_faces or n_verts > self.max_verts:
       raise ValueError("mesh (%d verts, %d faces) exceeds the renderer's capacity" % (n_verts, n_faces))
     s = self._acquire()
+    s.inputs, s.host_fed = (verts, faces, colors, rem), True
     with torch.cuda.device(self.dev), torch.cuda.stream(s.stream):
       s.d_verts[:3 * n_verts].copy_(verts, non_blocking=True)
       s.d_faces[:3 * n_faces].copy_(faces, non_blocking=True)
@@ -211,11 +232,14 @@ class ScanRenderer:
                                  "use ScanRenderer(method='lbvh') for it")
 
   def wait(self):
+    err = None
     for s in self.slots:
-      if s.busy:
-        s.done.synchronize()
-        s.busy = False
-        self._check(s)
+      try:
+        s.result()
+      except _lib_mod.VlidarError as e:   # drain every slot before reporting the first failure
+        err = err or e
+    if err is not None:
+      raise err
 
   def fence(self):
     """Make the current torch stream wait for everything submitted so far (device-side join)."""

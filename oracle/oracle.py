@@ -90,6 +90,24 @@ def trace(rays, origin, verts, faces, colors, rem, height, flags=0):
   return out
 
 
+def normalize_rays(rays, flags=NORMALIZE_SSE):
+  """vlo_normalize_rays: normalize() of Vector3.h:73-89 alone (SSE mode = the reference's bits)."""
+  lib = _lib(os.path.join(_HERE, "liboracle.so"))
+  rays = np.ascontiguousarray(rays, np.float32).reshape(-1)
+  out = np.empty_like(rays)
+  lib.vlo_normalize_rays(_p(rays, _f32p), ctypes.c_long(rays.size // 3), ctypes.c_uint(flags), _p(out, _f32p))
+  return out
+
+
+def ray_triangle(ray, origin, v0, v1, v2, flags=NORMALIZE_SSE):
+  """vlo_ray_triangle: t of one ray against one triangle under the reference arithmetic, or None on a miss."""
+  lib = _lib(os.path.join(_HERE, "liboracle.so"))
+  a = [np.ascontiguousarray(x, np.float32).reshape(3) for x in (ray, origin, v0, v1, v2)]
+  t = ctypes.c_float(0.0)
+  hit = lib.vlo_ray_triangle(*[_p(x, _f32p) for x in a], ctypes.c_uint(flags), ctypes.byref(t))
+  return np.float32(t.value) if hit else None
+
+
 def ref_ctrace(rays, origin, verts, faces, colors, rem, height, variant="nofma", ids=False):
   """The reference's own extern "C" ctrace (RayTracer.cpp:116-124) compiled from its sources.
 

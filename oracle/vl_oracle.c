@@ -595,4 +595,25 @@ long long vlo_mesh_extract(const float* tsdf, const float* color_vol, const floa
   return n_tris;
 }
 
+/* The normalisation alone (Vector3.h:73-89) for n rays: what the product's vl_normalize_rays must reproduce bit for
+ * bit in SSE mode. */
+void vlo_normalize_rays(const float* rays, long n, unsigned flags, float* out) {
+  for (long i = 0; i < n; ++i) {
+    v3 d = vlo_normalize(v3_make(rays[3 * i], rays[3 * i + 1], rays[3 * i + 2]), flags);
+    out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
+  }
+}
+
+/* One ray against one triangle (Ray.h:11-12 normalise + Triangle.h:27-50): returns 1 and *t on a hit.  Used by the
+ * parity tests to PROVE that two triangles the device and the reference disagree on are an exact-t tie
+ * (BVH.cpp:59 keeps the first strictly smaller t in traversal order). */
+int vlo_ray_triangle(const float* ray, const float* origin, const float* v0, const float* v1, const float* v2,
+                     unsigned flags, float* t_out) {
+  vlo_tri T;
+  memset(&T, 0, sizeof(T));
+  T.v0 = v3_make(v0[0], v0[1], v0[2]); T.v1 = v3_make(v1[0], v1[1], v1[2]); T.v2 = v3_make(v2[0], v2[1], v2[2]);
+  v3 d = vlo_normalize(v3_make(ray[0], ray[1], ray[2]), flags);
+  return vlo_tri_hit(&T, v3_make(origin[0], origin[1], origin[2]), d, t_out);
+}
+
 int vlo_abi_version(void) { return 1; }

@@ -38,7 +38,7 @@ def _run(engine, oracle, verts, faces, rays, origin, H, colors=None, rem=None, l
     colors, rem = _attrs(verts.shape[0])
   rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 3)
   origin = np.asarray(origin, np.float32)
-  ref = oracle.trace(rays, origin, verts, faces, colors, rem, H, oracle.MIN_ID_TIES)
+  ref = oracle.trace(rays, origin, verts, faces, colors, rem, H, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE)
   beams = engine.Beams(rays, H)
   got = _np(engine.cast(beams, verts, faces, colors, rem, origin))
   _same(got, ref, what="cast vs oracle")
@@ -170,7 +170,7 @@ def test_cast_close_geometry_is_shared_by_many_ctas(engine, oracle):
   faces = np.concatenate([faces, sc["faces"] + len(wall)])
   colors, rem = _attrs(verts.shape[0], 3)
   rays = oracle.create_rays(22.5, -22.5, 64, 512)
-  ref = oracle.trace(rays, np.zeros(3, np.float32), verts, faces, colors, rem, 64, oracle.MIN_ID_TIES)
+  ref = oracle.trace(rays, np.zeros(3, np.float32), verts, faces, colors, rem, 64, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE)
   beams = engine.Beams(rays, 64)
   got = _np(engine.cast(beams, verts, faces, colors, rem, np.zeros(3, np.float32), check_mesh=True))
   _same(got, ref)
@@ -189,7 +189,7 @@ def test_cast_result_independent_of_cell_grid(engine, oracle, vl, cells):
   finally:
     vl.vl_debug_cast_cells(1)
   _same(alt, base)
-  _same(base, oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], 32, oracle.MIN_ID_TIES))
+  _same(base, oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], 32, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE))
 
 
 def test_cast_work_unit_overflow_is_reported_and_ctrace_falls_back(engine, oracle):
@@ -207,7 +207,7 @@ def test_cast_work_unit_overflow_is_reported_and_ctrace_falls_back(engine, oracl
   colors, rem = _attrs(verts.shape[0], 9)
   H, W = 64, 2048
   rays = oracle.create_rays(3.0, -25.0, H, W)
-  ref = oracle.trace(rays, origin, verts, faces, colors, rem, H, oracle.MIN_ID_TIES)
+  ref = oracle.trace(rays, origin, verts, faces, colors, rem, H, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE)
   beams = engine.Beams(rays, H)
   import torch
   out = dict(endpoints=torch.full((3 * H * W,), 7.0, device="cuda"), endcolors=torch.full((3 * H * W,), 7, dtype=torch.int32, device="cuda"),
@@ -222,7 +222,7 @@ def test_cast_work_unit_overflow_is_reported_and_ctrace_falls_back(engine, oracl
   # the same kind of mesh, small enough for the unit list: the cast itself answers
   k = 12
   got2 = _np(engine.cast(beams, verts[:3 * k], faces[:k], colors[:3 * k], rem[:3 * k], origin, check_mesh=True))
-  _same(got2, oracle.trace(rays, origin, verts[:3 * k], faces[:k], colors[:3 * k], rem[:3 * k], H, oracle.MIN_ID_TIES))
+  _same(got2, oracle.trace(rays, origin, verts[:3 * k], faces[:k], colors[:3 * k], rem[:3 * k], H, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE))
   assert got2["n_units"] > 10000
 
 
@@ -241,7 +241,7 @@ def test_cast_zero_misses_and_hits_only(engine, oracle):
   assert (got["range"][miss] == 7).all() and (got["endcolors"].reshape(-1, 3)[miss] == 7).all()   # hits only (RayTracer.cpp:72-90)
   z = _np(engine.cast(beams, sc["verts"], sc["faces"], sc["colors"], sc["rem"], origin, zero_misses=True))
   assert (z["range"][miss] == 0).all() and not z["endpoints"].reshape(-1, 3)[miss].any()
-  _same(z, oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], 16, oracle.MIN_ID_TIES))
+  _same(z, oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], 16, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE))
 
 
 def test_host_ctrace_both_methods(engine, oracle):
@@ -250,7 +250,7 @@ def test_host_ctrace_both_methods(engine, oracle):
   rays = oracle.create_rays(3.0, -25.0, H, W)
   rays[:W] = np.array([0, 0, 1], np.float32)
   origin = np.zeros(3, np.float32)
-  ref = oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES)
+  ref = oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE)
   for method in ("cast", "lbvh", "cast"):
     out = dict(endpoints=np.full(3 * H * W, 7.0, np.float32), endcolors=np.full(3 * H * W, 7, np.int32),
                range=np.full(H * W, 7.0, np.float32), endrem=np.full(H * W, 7.0, np.float32))
@@ -304,9 +304,7 @@ def test_cast_config4_size_equals_lbvh(engine, oracle):
   f32 = np.float32
   fa = sc["faces"][a["tri_id"][hit]]
   v0, v1, v2 = (sc["verts"][fa[:, k]] for k in range(3))
-  d = rays[hit]
-  D = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(f32) + (d[:, 2] * d[:, 2] + f32(0)).astype(f32)
-  d = (d * (f32(1) / np.sqrt(D, dtype=f32)).astype(f32)[:, None]).astype(f32)
+  d = oracle.normalize_rays(rays, oracle.NORMALIZE_SSE).reshape(-1, 3)[hit]   # engine.DEFAULT_NORMALIZE == "sse"
   e1, e2 = (v1 - v0).astype(f32), (v2 - v0).astype(f32)
   cross = lambda p, q: np.stack([(p[:, 1] * q[:, 2]).astype(f32) - (p[:, 2] * q[:, 1]).astype(f32),
                                  (p[:, 2] * q[:, 0]).astype(f32) - (p[:, 0] * q[:, 2]).astype(f32),

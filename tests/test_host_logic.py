@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(vl):
   for n in names:
     assert hasattr(raw, n), "libvlidar.so does not export %s" % n
   assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-  assert vl.vl_abi_version() == 1
+  assert vl.vl_abi_version() == 2
   assert vl.vl_bvh_blob_bytes(0) >= 256 and vl.vl_bvh_blob_bytes(1000) > 112 * 1000
   assert vl.vl_profile_stage_count() >= 5
 
@@ -231,3 +231,30 @@ def test_cpulist_and_measured_peak_lookup(tmp_path, monkeypatch):
                         ({"hbm_tbs": 6.5}, 6500.0), ({"bf16": 1.0}, 6650.0)):
     (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps(content))
     assert bench._peaks()[0] == want, content
+
+
+def test_host_normaliser_is_the_reference_normalize_bit_for_bit(vl, oracle):
+  """vl_normalize_rays (product, host) == vlo_normalize in SSE mode (oracle; pinned bit-exact to the reference's
+  compiled Vector3.h:73-89 through the trace goldens) on beam grids, random directions of every magnitude, zero,
+  denormal, inf and NaN components -- so the device's triangle test sees the reference's own unit vectors."""
+  import ctypes
+  from lidar_transfer_b200.rays import create_rays
+  rng = np.random.default_rng(5)
+  sets = [create_rays(3.0, -25.0, 64, 2048), create_rays(22.5, -22.5, 128, 2048), create_rays(10.67, -30.67, 32, 1024),
+          (rng.normal(size=(100000, 3)) * 10.0 ** rng.uniform(-20, 18, (100000, 1))).astype(np.float32),
+          np.array([[0, 0, 0], [0, 0, 1], [1e-30, 0, 0], [1e-42, 1e-43, 0], [np.inf, 1, 0], [np.nan, 0, 1], [3e38, 3e38, 3e38],
+                    [-0.0, 0.0, -2.0]], np.float32)]
+  for rays in sets:
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1)
+    out = np.empty_like(rays)
+    assert vl.vl_normalize_rays(ctypes.c_void_p(rays.ctypes.data), rays.size // 3, ctypes.c_void_p(out.ctypes.data)) == 0
+    ref = oracle.normalize_rays(rays, oracle.NORMALIZE_SSE)
+    assert np.array_equal(out.view(np.int32), ref.view(np.int32))
+  # in place, and the IEEE mode is a different function (<= 2 ulp away, not equal everywhere)
+  rays = np.ascontiguousarray(sets[0]).reshape(-1).copy()
+  ref = oracle.normalize_rays(rays, oracle.NORMALIZE_SSE)
+  assert vl.vl_normalize_rays(ctypes.c_void_p(rays.ctypes.data), rays.size // 3, ctypes.c_void_p(rays.ctypes.data)) == 0
+  assert np.array_equal(rays.view(np.int32), ref.view(np.int32))
+  ieee = oracle.normalize_rays(sets[0], 0)
+  ulp = np.abs(ieee.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))
+  assert 0 < ulp.max() <= 4

@@ -1,9 +1,19 @@
-"""The device cast against THE REFERENCE ITSELF (oracle/_ref: the reference's C++ ray tracer compiled from its own
-sources, shipped to the GPU box) at the BASELINE.json config shapes, with the tolerances the north star states:
-hit mask / labels / triangle ids equal (up to exact edge ties: the reference normalises directions with x86 rsqrtps +
-one Newton step, the device with IEEE 1/sqrt, <= 2 ulp apart) and ranges within 1e-4 relative.  The bit-exact chain
-oracle <-> reference (SSE mode) and CUDA <-> oracle (IEEE mode) is tests/test_oracle_pinned.py + test_cast_gpu.py;
-this file closes the triangle directly, at full size, and leaves its counters in gpurun_out/ for profiles/."""
+"""The device cast and the device LBVH traversal against THE REFERENCE ITSELF (oracle/_ref: the reference's C++ ray
+tracer compiled from its own sources with -ffp-contract=off, shipped to the GPU box) at the BASELINE.json config shapes.
+
+The ray directions are normalised on the host by the product's vl_normalize_rays -- the reference's own rsqrtps +
+Newton step (Vector3.h:73-89) -- so the device's Moller-Trumbore test sees the reference's unit vectors.  The bar is
+therefore bit equality, not a tolerance: hit mask equal for every beam; range and end point bits equal for every beam;
+triangle id, label and remission equal for every beam EXCEPT beams of two kinds, and each such beam is PROVEN to be of
+its kind here with the oracle's restatement of the reference's ray / triangle test (vlo_ray_triangle, Triangle.h:27-50):
+  (a) exact-t ties -- the same t, bit for bit, for the device's triangle and the reference's (BVH.cpp:59 keeps the
+      first strictly smaller t in ITS traversal order, the device the smaller face index); ranges / end points equal;
+  (b) box culls of the reference -- its own triangle test accepts BOTH triangles and the device's t is the smaller
+      one: the reference's exact slab test (BBox.cpp:52-100) skipped the sub-tree of a closer triangle that its
+      triangle test hits (beams lying exactly in an axis plane through grid-aligned mesh edges; seen on columns 0 and
+      W-1, yaw = 180 degrees, of marching-cubes meshes).  The device returns the closest hit over ALL triangles, which is
+      what the reference computes whenever its tree does not get in the way.
+Counters go to gpurun_out/ for profiles/."""
 import json
 import os
 import time
@@ -43,6 +53,24 @@ CONFIGS = {
 }
 
 
+def _pair_t(oracle, sc, rays, o, r, id_a, id_b):
+  """t of ray r against triangles id_a (the device's) and id_b (the reference's) under the reference's ray / triangle
+  arithmetic (None = miss)."""
+  ts = []
+  for f in (id_a, id_b):
+    v = sc["verts"].reshape(-1, 3)[sc["faces"].reshape(-1, 3)[f]]
+    ts.append(oracle.ray_triangle(rays.reshape(-1, 3)[r], o, v[0], v[1], v[2], oracle.NORMALIZE_SSE))
+  return ts
+
+
+def _tie_proof(oracle, sc, rays, o, r, id_a, id_b, t_bits):
+  """True when triangles id_a and id_b are hit by ray r at exactly the same t (whose bits are t_bits)."""
+  ta, tb = _pair_t(oracle, sc, rays, o, r, id_a, id_b)
+  if ta is None or tb is None:
+    return False
+  return bool(np.float32(ta).view(np.int32) == np.float32(tb).view(np.int32) == t_bits)
+
+
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_cast_vs_compiled_reference(engine, oracle, name):
   if not oracle.have_ref("libref_ids_nofma.so"):
@@ -57,36 +85,80 @@ def test_cast_vs_compiled_reference(engine, oracle, name):
   t0 = time.perf_counter()
   ref = oracle.ref_ctrace(rays, o, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, ids=True)
   t_ref = time.perf_counter() - t0
-  beams = engine.Beams(rays, H)
-  got = engine.cast(beams, sc["verts"], sc["faces"], sc["colors"], sc["rem"], o)
-  got = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in got.items()}
+  beams = engine.Beams(rays, H)     # engine.DEFAULT_NORMALIZE == "sse": the reference's own normalisation
+  assert engine.DEFAULT_NORMALIZE == "sse"
+  paths = {"cast": engine.cast(beams, sc["verts"], sc["faces"], sc["colors"], sc["rem"], o)}
+  if name in ("c3-synthetic-500k-64x2048", "c2-hdl32-32x1024-tsdf-mesh"):   # the LBVH path as well
+    paths["lbvh"] = engine.trace(engine.Bvh(sc["verts"], sc["faces"], sc["colors"], sc["rem"]), rays, o, H)
   n = H * W
-  hit_g, hit_r = got["tri_id"] >= 0, ref["tri_id"] >= 0
-  mask_diff = int((hit_g != hit_r).sum())
-  both = hit_g & hit_r
-  id_diff = int((got["tri_id"][both] != ref["tri_id"][both]).sum())
-  lab_g, lab_r = got["endcolors"].reshape(-1, 3)[both], ref["endcolors"].reshape(-1, 3)[both]
-  label_diff = int((lab_g != lab_r).any(axis=1).sum())
-  same = both.copy()
-  same[both] = got["tri_id"][both] == ref["tri_id"][both]
+  for path, got in paths.items():
+    got = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in got.items()}
+    hit_g, hit_r = got["tri_id"] >= 0, ref["tri_id"] >= 0
+    mask_diff = int((hit_g != hit_r).sum())
+    both = hit_g & hit_r
+    diff = np.flatnonzero(both & (got["tri_id"] != ref["tri_id"]))
+    proven = [r for r in diff if _tie_proof(oracle, sc, rays, o, r, got["tri_id"][r], ref["tri_id"][r], got["range"][r].view(np.int32))]
+    unproven, box_culls = [], []
+    for r in diff:
+      if r not in proven:
+        ta, tb = _pair_t(oracle, sc, rays, o, r, got["tri_id"][r], ref["tri_id"][r])
+        if ta is not None and tb is not None and ta < tb and np.float32(ta).view(np.int32) == got["range"][r].view(np.int32) and \
+            np.float32(tb).view(np.int32) == ref["range"][r].view(np.int32):
+          box_culls.append(int(r))   # kind (b): the reference's own triangle test hits the device's triangle, closer
+          continue
+        unproven.append(dict(ray=int(r), dir=rays.reshape(-1, 3)[r].tolist(), device_tri=int(got["tri_id"][r]), device_t=float(got["range"][r]),
+                             reference_tri=int(ref["tri_id"][r]), reference_t=float(ref["range"][r]),
+                             oracle_t_device_tri=None if ta is None else float(ta), oracle_t_reference_tri=None if tb is None else float(tb),
+                             device_tri_verts=sc["verts"].reshape(-1, 3)[sc["faces"].reshape(-1, 3)[got["tri_id"][r]]].tolist(),
+                             reference_tri_verts=sc["verts"].reshape(-1, 3)[sc["faces"].reshape(-1, 3)[ref["tri_id"][r]]].tolist()))
+    same = both.copy()
+    same[diff] = False
+    tie_or_same = both.copy()
+    tie_or_same[box_culls] = False
+    lab_g, lab_r = got["endcolors"].reshape(-1, 3), ref["endcolors"].reshape(-1, 3)
+    label_diff_off_ties = int((lab_g[same] != lab_r[same]).any(axis=1).sum())
+    label_diff_on_ties = int((lab_g[diff] != lab_r[diff]).any(axis=1).sum())
+    range_bits_diff = int((got["range"][tie_or_same].view(np.int32) != ref["range"][tie_or_same].view(np.int32)).sum())
+    ep_bits_diff = int((got["endpoints"].reshape(-1, 3)[tie_or_same].view(np.int32) != ref["endpoints"].reshape(-1, 3)[tie_or_same].view(np.int32)).any(axis=1).sum())
+    rem_bits_diff = int((got["endrem"][same].view(np.int32) != ref["endrem"][same].view(np.int32)).sum())
+    report = dict(config=name, path=path, normalize="sse", n_tris=int(n_t), n_rays=int(n), hit_fraction=float(hit_g.mean()),
+                  hit_mask_mismatches=mask_diff, triangle_id_mismatches=int(diff.size), proven_exact_t_ties=len(proven), proven_reference_box_culls=len(box_culls),
+                  label_mismatches_on_ties=label_diff_on_ties, label_mismatches_elsewhere=label_diff_off_ties,
+                  range_bit_mismatches=range_bits_diff, endpoint_bit_mismatches=ep_bits_diff,
+                  remission_bit_mismatches_off_ties=rem_bits_diff, reference_ctrace_seconds=round(t_ref, 3), unproven=unproven)
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    try:
+      os.makedirs(out_dir, exist_ok=True)
+      with open(os.path.join(out_dir, "reference_parity_%s_%s.json" % (name, path)), "w") as f:
+        json.dump(report, f)
+    except OSError:
+      pass
+    assert hit_g.mean() > 0.3, report
+    assert mask_diff == 0, report
+    assert len(proven) + len(box_culls) == diff.size and not unproven, report   # every id mismatch is of a proven kind
+    assert diff.size <= 64, report                                              # and there is only a handful of them
+    assert label_diff_off_ties == 0 and rem_bits_diff == 0, report
+    assert range_bits_diff == 0 and ep_bits_diff == 0, report
+
+
+def test_ieee_mode_differs_from_the_reference_only_at_edge_beams(engine, oracle):
+  """The portable mode (IEEE 1/sqrt on the device, <= 2 ulp from the reference's directions): the round-1 behaviour,
+  kept behind normalize="ieee" -- ranges of beams that agree on the triangle within 1e-4 relative (north star), a few
+  dozen beams through shared edges pick the neighbouring triangle."""
+  if not oracle.have_ref("libref_ids_nofma.so"):
+    pytest.skip("oracle/_ref is not present")
+  sc = synth.make_scene(1003, n_side=500)
+  H, W, fu, fd = synth.SENSORS["HDL-64E"]
+  rays = create_rays(fu, fd, H, W)
+  o = np.zeros(3, np.float32)
+  ref = oracle.ref_ctrace(rays, o, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, ids=True)
+  got = engine.cast(engine.Beams(rays, H, normalize="ieee"), sc["verts"], sc["faces"], sc["colors"], sc["rem"], o)
+  got = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in got.items()}
+  same = (got["tri_id"] == ref["tri_id"]) & (ref["tri_id"] >= 0)
+  assert ((got["tri_id"] >= 0) != (ref["tri_id"] >= 0)).sum() <= 16
+  assert (~same & (ref["tri_id"] >= 0)).sum() <= 1e-3 * H * W
   rel = np.abs(got["range"][same] - ref["range"][same]) / np.maximum(ref["range"][same], 1e-6)
-  rel_all = np.abs(got["range"][both] - ref["range"][both]) / np.maximum(ref["range"][both], 1e-6)
-  ep = np.abs(got["endpoints"].reshape(-1, 3)[same] - ref["endpoints"].reshape(-1, 3)[same]).max() if same.any() else 0.0
-  rem_d = np.abs(got["endrem"][same] - ref["endrem"][same]).max() if same.any() else 0.0
-  report = dict(config=name, n_tris=int(n_t), n_rays=int(n), hit_fraction=float(hit_g.mean()), hit_mask_mismatches=mask_diff,
-                triangle_id_mismatches=id_diff, label_mismatches=label_diff, range_rel_err_max_same_triangle=float(rel.max()) if rel.size else 0.0,
-                range_rel_err_max_all_hits=float(rel_all.max()) if rel_all.size else 0.0, endpoint_abs_err_max=float(ep),
-                remission_abs_err_max=float(rem_d), reference_ctrace_seconds=round(t_ref, 3))
-  out_dir = os.path.join(ROOT, "gpurun_out")
-  try:
-    os.makedirs(out_dir, exist_ok=True)
-    with open(os.path.join(out_dir, "reference_parity_%s.json" % name), "w") as f:
-      json.dump(report, f)
-  except OSError:
-    pass
-  # north star: integer ids / labels exact, ranges within 1e-4 relative -- up to exact-tie beams (a handful per 100 k)
-  assert hit_g.mean() > 0.3, report
-  assert mask_diff <= 1e-4 * n, report
-  assert id_diff <= 1e-3 * n and label_diff <= 1e-3 * n, report
-  assert report["range_rel_err_max_same_triangle"] <= 1e-4, report
-  assert rem_d <= 1e-6, report
+  assert rel.max() <= 1e-4
+  # and it is exactly the oracle's IEEE mode
+  ora = oracle.trace(rays, o, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES)
+  assert np.array_equal(got["tri_id"], ora["tri_id"]) and np.array_equal(got["range"].view(np.int32), ora["range"].view(np.int32))

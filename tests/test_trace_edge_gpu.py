@@ -27,7 +27,7 @@ def _run(engine, oracle, verts, faces, rays, origin, H, colors=None, rem=None):
     rem = (np.arange(verts.shape[0]) % 13 / 13.0).astype(np.float32)
   rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 3)
   origin = np.asarray(origin, np.float32)
-  ref = oracle.trace(rays, origin, verts, faces, colors, rem, H, oracle.MIN_ID_TIES)
+  ref = oracle.trace(rays, origin, verts, faces, colors, rem, H, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE)
   bvh = engine.Bvh(verts, faces, colors, rem)
   got = _np(engine.trace(bvh, rays, origin, H))
   _same(got, ref)
@@ -161,10 +161,7 @@ def test_full_size_properties(engine, oracle):
   hit = tid >= 0
   fa = sc["faces"][tid[hit]]
   v0, v1, v2 = (sc["verts"][fa[:, k]] for k in range(3))
-  d = rays[hit]
-  D = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(f32) + (d[:, 2] * d[:, 2] + f32(0)).astype(f32)
-  inv = (f32(1) / np.sqrt(D, dtype=f32)).astype(f32)
-  d = (d * inv[:, None]).astype(f32)
+  d = oracle.normalize_rays(rays, oracle.NORMALIZE_SSE).reshape(-1, 3)[hit]   # engine.DEFAULT_NORMALIZE == "sse"
   e1, e2 = (v1 - v0).astype(f32), (v2 - v0).astype(f32)
   cross = lambda p, q: np.stack([(p[:, 1] * q[:, 2]).astype(f32) - (p[:, 2] * q[:, 1]).astype(f32),
                                  (p[:, 2] * q[:, 0]).astype(f32) - (p[:, 0] * q[:, 2]).astype(f32),

@@ -28,7 +28,7 @@ def test_bvh_trace_bit_exact_vs_oracle(engine, oracle, n_side, H, W):
   sc = synth.make_scene(1000 + n_side, n_side=n_side)
   rays = oracle.create_rays(3.0, -25.0, H, W)
   origin = np.zeros(3, np.float32)
-  ref = oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES)
+  ref = oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE)
   bvh = engine.Bvh(sc["verts"], sc["faces"], sc["colors"], sc["rem"])
   st = bvh.status()
   assert st["n_tris"] == sc["faces"].shape[0] and st["n_bad_faces"] == 0
@@ -41,7 +41,7 @@ def test_bruteforce_kernel_matches_oracle_bruteforce(engine, oracle):
   sc = synth.make_scene(7, n_side=40)
   rays = oracle.create_rays(10.0, -30.0, 16, 64)
   origin = np.array([0.5, -0.25, 0.3], np.float32)
-  ref = oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], 16, oracle.BRUTE_FORCE)
+  ref = oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], 16, oracle.BRUTE_FORCE | oracle.NORMALIZE_SSE)
   got = _np(engine.trace_bruteforce(sc["verts"], sc["faces"], sc["colors"], sc["rem"], rays, origin, 16))
   _assert_bit_equal(got, ref)
   bvh = engine.Bvh(sc["verts"], sc["faces"], sc["colors"], sc["rem"])
@@ -54,13 +54,13 @@ def test_host_ctrace_drop_in(engine, oracle):
   H, W = 16, 128
   rays = oracle.create_rays(3.0, -25.0, H, W)
   origin = np.zeros(3, np.float32)
-  ref = oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES)
+  ref = oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE)
   out = dict(endpoints=np.full(3 * H * W, 7.0, np.float32), endcolors=np.full(3 * H * W, 7, np.int32),
              range=np.full(H * W, 7.0, np.float32), endrem=np.full(H * W, 7.0, np.float32))
   # add rays that miss (pointing up) to check that misses leave the buffers untouched
   rays2 = rays.copy()
   rays2[:W] = np.array([0, 0, 1], np.float32)
-  ref2 = oracle.trace(rays2, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES)
+  ref2 = oracle.trace(rays2, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE)
   got = engine.ctrace_host(rays2, origin, sc["verts"].reshape(-1), sc["faces"].reshape(-1), sc["colors"].reshape(-1),
                            sc["rem"], H, outputs=out, want_ids=True)
   miss = ref2["tri_id"] < 0
