@@ -16,11 +16,13 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
 #include "vl_common.cuh"
 #if defined(__SSE__) || defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
 #include <xmmintrin.h>
 #define VL_HAVE_SSE 1
 #endif
@@ -53,58 +55,82 @@ extern "C" int vl_normalize_rays(const float* rays, int n_rays, float* out) {
 }
 
 // ---------------------------------------------------------------------------
-// pageable -> pinned staging by a pool of copy threads
+// a small pool of host threads: pageable -> pinned staging, and the merge of the results
 // ---------------------------------------------------------------------------
 namespace {
 
 struct Chunk { size_t off; const char* src; size_t bytes; };
 
-class CopyPool {
+// memcpy into the staging buffer with non-temporal stores: the destination is only read by the DMA engine, so it
+// should neither be fetched for ownership nor displace the source from the caches
+inline void copy_stream(char* dst, const char* src, size_t bytes) {
+#ifdef VL_HAVE_SSE
+  static const bool nt = getenv("VLIDAR_NO_NT") == nullptr;
+  if (nt && (((uintptr_t)dst) & 15) == 0 && bytes >= 4096) {
+    const size_t n16 = bytes / 64;
+    const __m128i* s = reinterpret_cast<const __m128i*>(src);
+    __m128i* d = reinterpret_cast<__m128i*>(dst);
+    for (size_t i = 0; i < n16; ++i) {
+      const __m128i a = _mm_loadu_si128(s + 4 * i), b = _mm_loadu_si128(s + 4 * i + 1);
+      const __m128i c = _mm_loadu_si128(s + 4 * i + 2), e = _mm_loadu_si128(s + 4 * i + 3);
+      _mm_stream_si128(d + 4 * i, a); _mm_stream_si128(d + 4 * i + 1, b);
+      _mm_stream_si128(d + 4 * i + 2, c); _mm_stream_si128(d + 4 * i + 3, e);
+    }
+    _mm_sfence();
+    const size_t done = n16 * 64;
+    if (done < bytes) memcpy(dst + done, src + done, bytes - done);
+    return;
+  }
+#endif
+  memcpy(dst, src, bytes);
+}
+
+// A handful of detached worker threads that run fn(0) .. fn(n-1) together with the calling thread.  `progress(k)` is
+// called on the calling thread, in order, whenever items 0 .. k-1 are all done (at least `batch` new ones, or the tail).
+class WorkPool {
  public:
-  static CopyPool& get() {
-    static CopyPool* p = new CopyPool();   // never destroyed: the workers are detached and outlive static destructors
+  static WorkPool& get() {
+    static WorkPool* p = new WorkPool();   // never destroyed: the workers are detached and outlive static destructors
     return *p;
   }
-  // copies every chunk into dst + chunk.off; `flush(off_end)` is called on the calling thread, in order, whenever the
-  // chunks up to byte offset off_end (exclusive) are all in place
-  template <class Flush>
-  void run(char* dst, const std::vector<Chunk>& chunks, Flush flush) {
-    const int n = (int)chunks.size();
-    if (n == 0) return;
-    if (n_workers_ == 0) {
-      for (const Chunk& c : chunks) memcpy(dst + c.off, c.src, c.bytes);
-      flush(chunks.back().off + chunks.back().bytes);
+  int workers() const { return n_workers_; }
+  template <class Fn, class Progress>
+  void run(int n, int batch, Fn fn, Progress progress) {
+    if (n <= 0) return;
+    if (n_workers_ == 0 || n == 1) {
+      for (int i = 0; i < n; ++i) fn(i);
+      progress(n);
       return;
     }
     if ((int)done_.size() < n) done_ = std::vector<std::atomic<int>>(n);
     for (int i = 0; i < n; ++i) done_[i].store(0, std::memory_order_relaxed);
+    std::function<void(int)> f = fn;
     {
       std::lock_guard<std::mutex> lock(mu_);
-      dst_ = dst; chunks_ = &chunks; next_.store(0); active_ = n_workers_; ++generation_;
+      fn_ = &f; n_ = n; next_.store(0); active_ = n_workers_; ++generation_;
     }
     cv_.notify_all();
     int issued = 0;
     while (issued < n) {
       int k = issued;
       while (k < n && done_[k].load(std::memory_order_acquire)) ++k;
-      if (k > issued && (k == n || k - issued >= 4)) {   // >= 4 MB per DMA, or the tail
-        flush(chunks[k - 1].off + chunks[k - 1].bytes);
+      if (k > issued && (k == n || k - issued >= batch)) {
+        progress(k);
         issued = k;
-      } else if (k < n) {
-        // lend a hand instead of spinning
+      } else if (k < n) {   // lend a hand instead of spinning
         const int i = next_.fetch_add(1);
-        if (i < n) { memcpy(dst + chunks[i].off, chunks[i].src, chunks[i].bytes); done_[i].store(1, std::memory_order_release); }
+        if (i < n) { f(i); done_[i].store(1, std::memory_order_release); }
         else std::this_thread::yield();
       }
     }
     std::unique_lock<std::mutex> lock(mu_);
     idle_cv_.wait(lock, [&] { return active_ == 0; });
-    chunks_ = nullptr;
+    fn_ = nullptr;
   }
 
  private:
-  CopyPool() {
-    int want = 4;
+  WorkPool() {
+    int want = 3;   // measured on the B200 box's host (profiles/r02_ctrace_staging.md): 0 / 1 / 2 / 3 / 4 workers -> 3.3 / 2.0 / 1.8 / 1.75 / 1.9 ms
     if (const char* e = getenv("VLIDAR_COPY_THREADS")) want = atoi(e);
     const int hw = (int)std::thread::hardware_concurrency();
     if (hw > 0 && want > hw - 1) want = hw - 1;
@@ -118,14 +144,13 @@ class CopyPool {
       std::unique_lock<std::mutex> lock(mu_);
       cv_.wait(lock, [&] { return generation_ != seen; });
       seen = generation_;
-      char* dst = dst_;
-      const std::vector<Chunk>* chunks = chunks_;
+      const std::function<void(int)>* f = fn_;
+      const int n = n_;
       lock.unlock();
-      const int n = (int)chunks->size();
       for (;;) {
         const int i = next_.fetch_add(1);
         if (i >= n) break;
-        memcpy(dst + (*chunks)[i].off, (*chunks)[i].src, (*chunks)[i].bytes);
+        (*f)(i);
         done_[i].store(1, std::memory_order_release);
       }
       lock.lock();
@@ -136,9 +161,8 @@ class CopyPool {
   std::mutex mu_;
   std::condition_variable cv_, idle_cv_;
   unsigned long long generation_ = 0;
-  int active_ = 0;
-  char* dst_ = nullptr;
-  const std::vector<Chunk>* chunks_ = nullptr;
+  int active_ = 0, n_ = 0;
+  const std::function<void(int)>* fn_ = nullptr;
   std::atomic<int> next_{0};
   std::vector<std::atomic<int>> done_;
 };
@@ -259,10 +283,19 @@ int ctrace_locked(HostCtx& c, const float* rays, const float* origin, const floa
   add_chunks(chunks, o_rem, rem, 4 * nv);
   size_t sent = 0;
   cudaError_t copy_err = cudaSuccess;
-  CopyPool::get().run(P, chunks, [&](size_t end) {
-    if (copy_err == cudaSuccess) copy_err = cudaMemcpyAsync(A + sent, P + sent, end - sent, cudaMemcpyHostToDevice, s);
-    sent = end;
-  });
+  static const bool direct = getenv("VLIDAR_CTRACE_DIRECT") != nullptr;   // measurement aid: the driver's own pageable path
+  if (direct) {
+    for (const Chunk& ch : chunks)
+      if (copy_err == cudaSuccess) copy_err = cudaMemcpyAsync(A + ch.off, ch.src, ch.bytes, cudaMemcpyHostToDevice, s);
+  } else {
+    WorkPool::get().run((int)chunks.size(), 4,   // >= 4 MB per DMA, or the tail
+        [&](int i) { copy_stream(P + chunks[i].off, chunks[i].src, chunks[i].bytes); },
+        [&](int k) {
+          const size_t end = chunks[k - 1].off + chunks[k - 1].bytes;
+          if (copy_err == cudaSuccess) copy_err = cudaMemcpyAsync(A + sent, P + sent, end - sent, cudaMemcpyHostToDevice, s);
+          sent = end;
+        });
+  }
   VL_CUDA_CHECK(copy_err);
   const double t2 = now_ms();
 
@@ -311,14 +344,24 @@ int ctrace_locked(HostCtx& c, const float* rays, const float* origin, const floa
   const float* h_range = reinterpret_cast<const float*>(P + o_range);
   const float* h_erem = reinterpret_cast<const float*>(P + o_erem);
   const int* h_id = reinterpret_cast<const int*>(P + o_id);
-  for (size_t r = 0; r < nr; ++r) {
-    if (h_id[r] < 0) continue;
-    endpoints[3 * r] = h_ep[3 * r]; endpoints[3 * r + 1] = h_ep[3 * r + 1]; endpoints[3 * r + 2] = h_ep[3 * r + 2];
-    endcolors[3 * r] = h_ec[3 * r]; endcolors[3 * r + 1] = h_ec[3 * r + 1]; endcolors[3 * r + 2] = h_ec[3 * r + 2];
-    range[r] = h_range[r];
-    endrem[r] = h_erem[r];
-  }
-  if (tri_id) memcpy(tri_id, h_id, 4 * nr);
+  constexpr size_t kMergeBlock = 16384;
+  WorkPool::get().run((int)((nr + kMergeBlock - 1) / kMergeBlock), 1 << 30, [&](int b) {
+    const size_t r0 = (size_t)b * kMergeBlock, r1 = r0 + kMergeBlock < nr ? r0 + kMergeBlock : nr;
+    size_t r = r0;
+    while (r < r1) {   // runs of hits leave as block copies
+      while (r < r1 && h_id[r] < 0) ++r;
+      size_t e = r;
+      while (e < r1 && h_id[e] >= 0) ++e;
+      if (e > r) {
+        memcpy(endpoints + 3 * r, h_ep + 3 * r, 12 * (e - r));
+        memcpy(endcolors + 3 * r, h_ec + 3 * r, 12 * (e - r));
+        memcpy(range + r, h_range + r, 4 * (e - r));
+        memcpy(endrem + r, h_erem + r, 4 * (e - r));
+      }
+      r = e;
+    }
+    if (tri_id) memcpy(tri_id + r0, h_id + r0, 4 * (r1 - r0));
+  }, [](int) {});
   c.t_ms[0] = t1 - t0; c.t_ms[1] = t2 - t1; c.t_ms[2] = t3 - t2; c.t_ms[3] = now_ms() - t3;
   if (st[0] > 0) {
     vl_set_error("ctrace: %d face(s) reference a vertex outside [0, %d); they were skipped", st[0], n_verts);

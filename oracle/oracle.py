@@ -268,6 +268,45 @@ def tsdf_integrate(vol, vol_origin, voxel_size, color_im, depth_im, rem_im, fov_
   return dict(n_vis=int(counters[0]), n_written=int(counters[1]))
 
 
+class RefCudaTsdf:
+  """The reference's CUDA `integrate` kernel itself (oracle/_ref/libref_tsdf_cuda.so: the kernel string of
+  auxiliary/fusion_lidar.py:66-229 compiled by nvcc for sm_100a with pycuda's defaults, launched with the reference's
+  geometry) on torch CUDA tensors -- the checker the -m gpu tests hold the product's TSDF integration to, bit for bit.
+  Mirrors TSDFVolume.__init__ / integrate (fusion_lidar.py:23-63, 252-287).  Needs a GPU; test infrastructure only."""
+
+  def __init__(self, vol_dim, vol_origin, voxel_size, fov_up, fov_down):
+    import torch
+    self.dim = tuple(int(v) for v in vol_dim)
+    self.origin = np.asarray(vol_origin, np.float32).copy()
+    self.voxel_size, self.fov_up, self.fov_down = float(voxel_size), float(fov_up), float(fov_down)
+    n = self.dim[0] * self.dim[1] * self.dim[2]
+    # one element past the end belongs to the kernel's `voxel_idx > n` guard (fusion_lidar.py:92)
+    self._pad = [torch.empty(n + 1, dtype=torch.float32, device="cuda") for _ in range(4)]
+    self._pad[0].fill_(1.0)
+    for t in self._pad[1:]:
+      t.zero_()
+    self.tsdf, self.weight, self.color, self.rem = (t[:n].view(self.dim) for t in self._pad)
+    self.lib = _lib(os.path.join(_REF_DIR, "libref_tsdf_cuda.so"))
+
+  def integrate(self, color_im, depth_im, rem_im, obs_weight=1.0):
+    import torch
+    im_h, im_w = depth_im.shape
+    vd, vo, other = _tsdf_args(self.dim, self.origin, self.voxel_size, im_h, im_w, self.voxel_size * 5, obs_weight,
+                               self.fov_up, self.fov_down)
+    cam_pose = np.eye(4, dtype=np.float32).reshape(-1)
+    color_im = np.ascontiguousarray(color_im, np.float32).reshape(-1)
+    depth_im = np.ascontiguousarray(depth_im, np.float32).reshape(-1)
+    rem_im = np.ascontiguousarray(rem_im, np.float32).reshape(-1)
+    torch.cuda.synchronize()
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = self.lib.ref_tsdf_integrate_cuda(vp(self._pad[0]), vp(self._pad[1]), vp(self._pad[2]), vp(self._pad[3]), _p(vd, _f32p),
+                                          _p(vo, _f32p), _p(cam_pose, _f32p), _p(other, _f32p), _p(color_im, _f32p),
+                                          _p(depth_im, _f32p), _p(rem_im, _f32p), ctypes.c_int(im_h), ctypes.c_int(im_w))
+    if rc < 0:
+      raise RuntimeError("ref_tsdf_integrate_cuda failed")
+    return rc
+
+
 def mesh_attributes(verts_vox, color_vol, rem_vol, voxel_size, vol_origin):
   """Vertex world coords / colours / remission lookup of TSDFVolume.get_mesh,
   auxiliary/fusion_lidar.py:408-423 (numpy, verbatim order)."""

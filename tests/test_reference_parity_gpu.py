@@ -30,9 +30,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _tsdf_mesh(engine, sensor, vox, bnds):
-  """Config 1 / 2 shape: the mesh the engine's own projection -> TSDF -> iso-surface chain produces."""
+  """Config 1 / 2: the mesh the engine's own projection -> TSDF -> iso-surface chain produces from the REAL scan 0
+  of the reference's fixture (tests/golden/minimal_fixture.zip) at BASELINE's voxel size 0.05 and the bounds the
+  reference's mergemesh clips to (2000 x 1420 x 100 voxels)."""
+  import zipfile
   H, W, fu, fd = synth.SENSORS[sensor]
-  pts, labels = synth.make_scan_points(1, 124668)
+  z = zipfile.ZipFile(os.path.join(ROOT, "tests", "golden", "minimal_fixture.zip"))
+  scan = np.frombuffer(z.read("minimal/sequences/00/velodyne/000000.bin"), np.float32).reshape(-1, 4)
+  labels = np.frombuffer(z.read("minimal/sequences/00/labels/000000.label"), np.uint32) & 0xFFFF
+  keep = ~np.isin(labels, [0, 1])                                       # config/lidar_transfer.yaml `ignore`
+  pts, labels = scan[keep], labels[keep]
   pr = engine.project(pts[:, :3].astype(np.float64), pts[:, 3], labels, fu, fd, 64, 2048)   # source image 64 x 2048 (mergemesh)
   bnds = np.array(bnds, np.float64)
   dim = np.ceil((bnds[:, 1] - bnds[:, 0]) / vox).astype(int)
@@ -45,8 +52,8 @@ def _tsdf_mesh(engine, sensor, vox, bnds):
 
 CONFIGS = {
     # name: (mesh maker, target sensor, origin)
-    "c1-identity-64x2048-tsdf-mesh": (lambda e: _tsdf_mesh(e, "HDL-64E", 0.1, [[-50, 50], [-35.5, 35.5], [-3, 2]]), "HDL-64E", (0, 0, 0)),
-    "c2-hdl32-32x1024-tsdf-mesh": (lambda e: _tsdf_mesh(e, "HDL-32E", 0.1, [[-50, 50], [-35.5, 35.5], [-3, 2]]), "HDL-32E", (0, 0, 0)),
+    "c1-identity-64x2048-tsdf-mesh": (lambda e: _tsdf_mesh(e, "HDL-64E", 0.05, [[-50, 50], [-31, 40], [-3, 2]]), "HDL-64E", (0, 0, 0)),
+    "c2-hdl32-32x1024-tsdf-mesh": (lambda e: _tsdf_mesh(e, "HDL-32E", 0.05, [[-50, 50], [-31, 40], [-3, 2]]), "HDL-32E", (0, 0, 0)),
     "c3-synthetic-500k-64x2048": (lambda e: synth.make_scene(1003, n_side=500), "HDL-64E", (0, 0, 0)),
     "c4-2Mtri-128x2048": (lambda e: synth.make_scene(4000, n_side=1000), "OS1-128", (0.3, 0.1, 0.05)),
     "c5-synthetic-1Mtri-64x2048": (lambda e: synth.make_scene(1000, n_side=710), "HDL-64E", (0, 0, 0)),

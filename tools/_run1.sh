@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -q 2>&1 | tail -25
-for k in 0 1 2 4; do VLIDAR_COPY_THREADS=$k python tools/ctrace_bench.py 710 20 2>&1 | tail -1; done
-nproc; lscpu | grep -E "Model name|Socket|NUMA"
+python -m pytest tests/test_reference_driver_gpu.py -m gpu -q -rs -s > gpurun_out/drv.log 2>&1
+grep -n "passed\|failed\|^FAILED\|scan [0-9]: voxels\|SKIP\|Error\|integrations\|^E  " gpurun_out/drv.log | cut -c1-400 | head -60
