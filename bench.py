@@ -6,23 +6,31 @@
 
 Workload ("c5-synthetic-1Mtri-64x2048", BASELINE.json configs[4] shape, the config the metric
 `Mrays/s ... (64x2048 target)` and the north-star target `>= 100 Mrays/s per GPU on a 64x2048 sensor
-over a ~1 M-triangle scene` are quoted on): S seeded synthetic KITTI-shape scans per GPU per step,
-each with ITS OWN ~1.0 M-triangle mesh (ground grid 710 x 710 + boxes, lidar_transfer_b200/synth.py)
-and the HDL-64E beam pattern 64 x 2048 = 131 072 rays.  One step = for every scan of the batch: the closest hit
-of all rays against the scan's mesh (rows (i)+(ii) of the hot path), by --method cast (default: beams indexed once
+over a ~1 M-triangle scene` are quoted on): seeded synthetic KITTI-shape scans, each with ITS OWN
+~1.05 M-triangle mesh (ground grid 710 x 710 + boxes, lidar_transfer_b200/synth.py) and the HDL-64E beam
+pattern 64 x 2048 = 131 072 rays.  One step = a batch of scans per GPU; per scan the closest hit of all
+rays against the scan's mesh (rows (i)+(ii) of the hot path), by --method cast (default: beams indexed once
 per sensor, the scan's triangles streamed through the index, vl_cast) or --method lbvh (per-scan LBVH build +
-per-ray traversal, vl_bvh_build + vl_trace); the other method is timed briefly beside it ("other_method").
-Weak scaling: every rank owns S scans; there is no collective on the data path.
+per-ray traversal); the other method is timed briefly beside it ("other_method").
+Weak scaling: every rank owns its scans; there is no collective on the data path.
 
-value   = rays traced by all ranks / device time, meshes and rays already resident in HBM.
-e2e     = same metric through the host-buffer path (pinned host meshes -> H2D -> cast -> D2H of the five
-          per-ray outputs), copies inside the timed region.
-roofline= dominant kernel of the step (largest share of device time, measured live with CUDA events
-          on the launching streams): algorithmic bytes / mean launch duration vs MEASURED_PEAKS.json.
+value         = rays cast by all ranks / device time (CUDA events), meshes and rays already resident in HBM;
+                2048 scans per step and GPU, so that the timed region of the driver's 20 steps lasts > 1 s.
+e2e           = the same metric through the reference-facing plugin call: auxiliary.raytracer.RayTracerCython.C_Trace
+                -> extern "C" ctrace (include/vlidar.h) on PAGEABLE numpy buffers, one synchronous call per scan like
+                the reference's caller (fusion_lidar.py:440-450), host<->device copies inside the timed region.
+e2e_pipelined = the repo's own batch API on pinned host meshes (ScanRenderer.submit_host, 8 streams).
+e2e_deform    = N=1: MultiSemLaserScan.open_multiple_scans + deform('mergemesh') on the reference's real fixture at
+                config-1 size (voxel 0.05, 284 M voxels), wall time per scan.
+roofline      = dominant kernel of the step (largest share of device time, CUDA events on the launching stream):
+                COMPULSORY bytes (inputs once + outputs once) / mean launch duration vs MEASURED_PEAKS.json, with the
+                issue-slot fraction (the binding limit of this path) beside it.
+pipeline_c1 / pipeline_c4 = the whole chain (project -> TSDF -> mesh -> cast) at BASELINE.json configs[0] / [3] size.
 cpu_baseline / --impl reference = the reference's own C++ ray tracer (oracle/_ref, compiled from the
-          reference sources with its shipped flags) on the same meshes, all host threads.
+                reference sources with its shipped flags) on the same meshes, all host threads.
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -41,15 +49,25 @@ FOV_UP, FOV_DOWN = 3.0, -25.0
 N_SIDE = 710  # 2 * 709^2 = 1 005 362 ground triangles (+ boxes)
 WORKLOAD = "c5-synthetic-1Mtri-64x2048"
 METRIC = "Mrays/s (closest-hit ray cast of a per-scan ~1M-tri mesh, 64x2048 target)"
+FIXTURE = os.path.join(ROOT, "tests", "golden", "minimal_fixture.zip")
 
 
-def _ncu_traffic(kernel):
-  """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
-  p = os.path.join(ROOT, "profiles", "r01_%s_ncu_full.json" % kernel)
-  try:
-    return float(json.load(open(p))["dram_bytes_per_launch"])
-  except (OSError, KeyError, ValueError):
-    return None
+def shared_config():
+  """The keys both arms print: the workload, nothing arm-specific (the driver compares the two dicts)."""
+  return {"workload": WORKLOAD, "rays_per_scan": H * W, "beams": "%dx%d HDL-64E fov +%g/%g" % (H, W, FOV_UP, FOV_DOWN),
+          "tris_per_scan": "~1.05 M (ground grid %d x %d + 40 boxes, seeds 1000+k)" % (N_SIDE, N_SIDE),
+          "scene_generator": "lidar_transfer_b200.synth.make_scene", "one_mesh_per_scan": True}
+
+
+def _ncu(kernel):
+  """Per-launch counters of `kernel` from the committed ncu --set full capture (profiles/), or {}."""
+  for rnd in ("r02", "r01"):
+    p = os.path.join(ROOT, "profiles", "%s_%s_ncu_full.json" % (rnd, kernel))
+    try:
+      return json.load(open(p))
+    except (OSError, ValueError):
+      continue
+  return {}
 
 
 def _peaks():
@@ -104,7 +122,7 @@ class ClockSampler:
       return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
     time.sleep(0.25)
     self.proc.terminate()
-    sm, smax, reasons = [], [], set()
+    sm, smax, power, reasons = [], [], [], set()
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     for ln in self.lines:
       f = [x.strip() for x in ln.split(",")]
@@ -112,13 +130,14 @@ class ClockSampler:
         continue
       try:
         sm.append(float(f[1])); smax.append(float(f[2]))
+        power.append(float(f[3]))
       except ValueError:
         continue
       for name, val in zip(names, f[5:9]):
         if val.lower().startswith("active"):
           reasons.add(name)
     return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-            "samples": len(sm), "reasons": sorted(reasons)}
+            "samples": len(sm), "power_w_max": max(power) if power else None, "reasons": sorted(reasons)}
 
 
 def make_scenes(rank, n_meshes):
@@ -178,8 +197,9 @@ def run_reference(args):
       "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": {"workload": WORKLOAD, "scans_per_step": 1, "rays_per_scan": H * W,
-                 "tris_per_scan": int(scenes[0]["faces"].shape[0])},
+      "config": shared_config(),
+      "arm": {"scans_per_step": 1, "api": "extern \"C\" ctrace of oracle/_ref/libref_raytracer.so (reference flags), one call per scan",
+              "threads": cores},
       "scans_per_s": args.steps / total,
       "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
       "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -189,55 +209,128 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-# the whole chain at BASELINE.json config-1 size, reported beside the headline (not part of `value`)
+# the whole chain at BASELINE.json config sizes, reported beside the headline (not part of `value`)
 # ------------------------------------------------------------------------------------------------
-def pipeline_c1(L, dev):
-  """points -> range image -> 284 M-voxel TSDF (voxel 0.05 m) -> iso-surface -> cast, one synthetic 124 668-point
-  scan: per-stage device times from the library's CUDA events (second pass) and the whole chain between two events
-  including the host's part -- allocation of the data-dependent outputs, the one synchronisation that reads the
-  triangle count -- with the per-stage events off (third pass)."""
-  import ctypes
+def _fixture_scan(k):
+  """Scan k of the reference's fixture (tests/golden/minimal_fixture.zip) with the `ignore` classes removed, or None."""
+  import zipfile
+  try:
+    z = zipfile.ZipFile(FIXTURE)
+    scan = np.frombuffer(z.read("minimal/sequences/00/velodyne/%06d.bin" % k), np.float32).reshape(-1, 4)
+    label = np.frombuffer(z.read("minimal/sequences/00/labels/%06d.label" % k), np.uint32) & 0xFFFF
+  except (OSError, KeyError):
+    return None
+  keep = ~np.isin(label, [0, 1])
+  return scan[keep].copy(), label[keep].copy()
+
+
+def _collect_stages(L):
+  n_st = L.vl_profile_stage_count()
+  ms_arr, cnt_arr = (ctypes.c_double * n_st)(), (ctypes.c_longlong * n_st)()
+  L.vl_profile_collect(ms_arr, cnt_arr)
+  return {L.vl_profile_stage_name(i).decode(): (ms_arr[i], cnt_arr[i]) for i in range(n_st) if cnt_arr[i]}
+
+
+def pipeline_chain(L, dev, scans, src_fov, bnds, vox, target, reps=3):
+  """points -> range image(s) -> TSDF -> iso-surface -> cast.  scans: list of (float32[N,4], uint32[N]) fused into ONE
+  volume (one = mergemesh / config 1, several = the mesh adaption / config 4).  Per-stage device times from the
+  library's CUDA events (second pass) and the whole chain between two events including the host's part -- allocation
+  of the data-dependent outputs, the one synchronisation that reads the triangle count -- with the events off (third)."""
   import torch
-  from lidar_transfer_b200 import engine, synth
+  from lidar_transfer_b200 import engine
   from lidar_transfer_b200.rays import create_rays
-  pts, labels = synth.make_scan_points(1, 124668)
-  p64 = torch.from_numpy(pts[:, :3].astype(np.float64)).to(dev)
-  rem = torch.from_numpy(pts[:, 3].copy()).to(dev)
-  lab = torch.from_numpy(labels.view(np.int32)).to(dev)
-  vox = 0.05
-  bnds = np.array([[-50, 50], [-35.5, 35.5], [-3, 2]], np.float64)
+  tH, tW, tfu, tfd = target
+  dpts = [(torch.from_numpy(p[:, :3].astype(np.float64)).to(dev), torch.from_numpy(p[:, 3].copy()).to(dev),
+           torch.from_numpy(l.view(np.int32).copy()).to(dev)) for p, l in scans]
+  bnds = np.array(bnds, np.float64)
   dim = np.ceil((bnds[:, 1] - bnds[:, 0]) / vox).astype(int)
-  rays = torch.from_numpy(create_rays(FOV_UP, FOV_DOWN, H, W)).to(dev)
+  beams = engine.Beams(create_rays(tfu, tfd, tH, tW), tH)
   origin = torch.zeros(3, device=dev)
-  beams = engine.Beams(rays, H)
-  vol = engine.TsdfDevice(dim, bnds[:, 0].astype(np.float32), vox, FOV_UP, FOV_DOWN)
-  ws = None
-  wall = None
-  for rep in range(3):   # warm-up, per-stage events on (their bookkeeping costs host time), whole-chain time with them off
+  vol = engine.TsdfDevice(dim, bnds[:, 0].astype(np.float32), vox, src_fov[0], src_fov[1])
+  ws, wall, stages = None, None, {}
+  for rep in range(reps):   # warm-up, per-stage events on (their bookkeeping costs host time), whole-chain time with them off
     torch.cuda.synchronize()
     L.vl_profile_enable(1 if rep == 1 else 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    pr = engine.project(p64, rem, lab, FOV_UP, FOV_DOWN, H, W, workspace=ws)
-    ws = pr["workspace"]
     vol.reset()
-    vol.integrate(pr["proj_label"].to(torch.float32) * 65536.0, pr["range_image"], pr["proj_remissions"])
+    for p64, rem, lab in dpts:
+      pr = engine.project(p64, rem, lab, src_fov[0], src_fov[1], H, W, workspace=ws)
+      ws = pr["workspace"]
+      vol.integrate(pr["proj_label"].to(torch.float32) * 65536.0, pr["range_image"], pr["proj_remissions"])
     m = vol.extract_mesh(want_norms=False)
     out = engine.cast(beams, m["verts"], m["faces"], m["colors"].to(torch.int32), m["rem"], origin, zero_misses=True,
                       check_mesh=False)
     e1.record()
     torch.cuda.synchronize()
     wall = e0.elapsed_time(e1)
-  L.vl_profile_enable(0)
-  n_st = L.vl_profile_stage_count()
-  ms_arr, cnt_arr = (ctypes.c_double * n_st)(), (ctypes.c_longlong * n_st)()
-  L.vl_profile_collect(ms_arr, cnt_arr)
-  stages = {L.vl_profile_stage_name(i).decode(): round(1e3 * ms_arr[i] / cnt_arr[i], 1) for i in range(n_st) if cnt_arr[i]}
-  return {"workload": "c1-shape: 124668 points -> 64x2048 image -> %d x %d x %d voxels -> mesh -> 64x2048 cast" % tuple(dim),
-          "n_voxels": int(np.prod(dim)), "n_tris": int(m["faces"].shape[0]),
-          "hit_fraction": float((out["range"] > 0).float().mean()),
-          "stage_us": stages, "kernel_ms_per_scan": round(sum(stages.values()) / 1e3, 3),
-          "ms_per_scan_incl_host": round(wall, 3)}
+    if rep == 1:
+      L.vl_profile_enable(0)
+      stages = {k: round(1e3 * v[0], 1) for k, v in _collect_stages(L).items()}   # us per chain (all launches of a stage summed)
+  return {"n_scans_fused": len(scans), "n_points": [int(p.shape[0]) for p, _ in scans], "voxel_size": vox,
+          "volume": "%d x %d x %d" % tuple(dim), "n_voxels": int(np.prod(dim)), "n_tris": int(m["faces"].shape[0]),
+          "target": "%dx%d fov +%g/%g" % (tH, tW, tfu, tfd), "hit_fraction": float((out["range"] > 0).float().mean()),
+          "stage_us": stages, "kernel_ms_per_chain": round(sum(stages.values()) / 1e3, 3), "ms_per_chain_incl_host": round(wall, 3)}
+
+
+def pipelines(L, dev):
+  from lidar_transfer_b200 import synth
+  real = _fixture_scan(0)
+  c1_scan = real if real is not None else synth.make_scan_points(1, 124668)
+  c1 = pipeline_chain(L, dev, [c1_scan], (FOV_UP, FOV_DOWN), [[-50, 50], [-31, 40], [-3, 2]], 0.05, (H, W, FOV_UP, FOV_DOWN))
+  c1["workload"] = "BASELINE configs[0]: %s scan 0 -> 64x2048 image -> 284 M voxels at 0.05 m (the bounds mergemesh clips to) -> mesh -> identity cast" % (
+      "minimal.zip" if real is not None else "synthetic")
+  # configs[3]: n_frames = 5 fused by the `mesh` adaption (one range image per scan at the source field of view, all into
+  # one volume with the configuration's bounds), cast with the OS1-128 pattern.  The fixture has 3 scans, so the five are
+  # synthetic KITTI-shape scans of one static world (seeds 1..5).
+  c4 = pipeline_chain(L, dev, [synth.make_scan_points(s, 124668) for s in range(1, 6)], (FOV_UP, FOV_DOWN),
+                      [[-50, 50], [-50, 50], [-5, 5]], 0.1, synth.SENSORS["OS1-128"])
+  c4["workload"] = "BASELINE configs[3]: 5 synthetic scans fused (deform('mesh') semantics) -> 100 M voxels at 0.1 m -> mesh -> 128x2048 OS1-128 cast"
+  return c1, c4
+
+
+def deform_leg(n_scans=3, reps=2):
+  """The reference-shaped per-scan call the driver makes (lidar_deform.py:396-415): open_multiple_scans +
+  deform('mergemesh') on the real fixture at config-1 size, files on disk -> numpy attributes.  Wall ms per scan."""
+  import tempfile
+  import zipfile
+  import yaml
+  if not os.path.exists(FIXTURE):
+    return None
+  from lidar_transfer_b200.auxiliary import laserscan as ls
+  d = tempfile.mkdtemp(prefix="vl_bench_")
+  zipfile.ZipFile(FIXTURE).extractall(d)
+  cfg = yaml.safe_load(open(os.path.join(d, "config", "lidar_transfer.yaml")))
+  src = yaml.safe_load(open(os.path.join(d, "minimal", "config.yaml")))
+  seq = os.path.join(d, "minimal", "sequences", "00")
+  scan_names = [os.path.join(seq, "velodyne", "%06d.bin" % k) for k in range(3)]
+  label_names = [os.path.join(seq, "labels", "%06d.label" % k) for k in range(3)]
+  poses = [np.eye(4) for _ in range(3)]
+  t_open, t_deform = [], []
+  devnull = os.open(os.devnull, os.O_WRONLY)
+  saved = os.dup(1)
+  os.dup2(devnull, 1)   # the classes print like the reference's
+  try:
+    for rep in range(reps):
+      for idx in range(n_scans):
+        t0 = time.perf_counter()
+        scans = ls.MultiSemLaserScan(src, src, cfg["number_of_scans"], len(cfg["color_map"]), cfg["ignore"], cfg["moving"],
+                                     cfg["color_map"], transformation=cfg["transformation"], preserve_float=cfg["preserve_float"],
+                                     voxel_size=cfg["voxel_size"], vol_bnds=np.array(cfg["voxel_bounds"]).reshape(3, 2))
+        scans.open_multiple_scans(scan_names, label_names, poses, idx)
+        t1 = time.perf_counter()
+        scans.deform("mergemesh", poses, idx)
+        _ = scans.proj_range[0, 0] + scans.label_image[0, 0] + scans.back_points[0, 0]   # the attributes write() / compare() read
+        t2 = time.perf_counter()
+        if rep > 0:
+          t_open.append(t1 - t0)
+          t_deform.append(t2 - t1)
+  finally:
+    os.dup2(saved, 1)
+    os.close(devnull)
+  return {"api": "MultiSemLaserScan.open_multiple_scans + deform('mergemesh'), minimal.zip scans 0-2, voxel %.2f (config 1)" % cfg["voxel_size"],
+          "open_ms_per_scan": round(1e3 * float(np.mean(t_open)), 2), "deform_ms_per_scan": round(1e3 * float(np.mean(t_deform)), 2),
+          "rays_per_scan": H * W, "value": H * W / float(np.mean(t_open) + np.mean(t_deform)) / 1e6, "unit": "Mrays/s"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -263,24 +356,29 @@ def run_native(args):
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 
-  from lidar_transfer_b200 import _lib, engine, pipeline
+  from lidar_transfer_b200 import _lib, pipeline
+  from lidar_transfer_b200.auxiliary.raytracer import RayTracerCython as rtc
   from lidar_transfer_b200.rays import create_rays
   L = _lib.lib()
   S, K, Wm = args.scans_per_step, args.steps, args.warmup
-  M = min(args.distinct_meshes, S)   # distinct meshes per rank; a step cycles through them S / M times
+  Se, Sp = args.e2e_scans_per_step, args.pipelined_scans_per_step
+  M = min(args.distinct_meshes, S)   # distinct meshes per rank; a step cycles through them
   rays_np = create_rays(FOV_UP, FOV_DOWN, H, W)
   scenes = make_scenes(rank, M)
   n_tris = [int(sc["faces"].shape[0]) for sc in scenes]
   n_verts = [int(sc["verts"].shape[0]) for sc in scenes]
   max_f, max_v = max(n_tris), max(n_verts)
+  R = H * W
 
-  # device-resident inputs (value leg) and pinned host inputs (e2e leg)
+  # device-resident inputs (value leg), pageable numpy inputs (e2e = plugin call), pinned host inputs (pipelined leg)
   d_scenes = [tuple(torch.from_numpy(sc[k].reshape(-1)).to(dev) for k in ("verts", "faces", "colors", "rem"))
               for sc in scenes]
+  np_scenes = [tuple(np.ascontiguousarray(sc[k].reshape(-1)) for k in ("verts", "faces", "colors", "rem")) for sc in scenes]
   h_scenes = [tuple(torch.from_numpy(sc[k].reshape(-1)).pin_memory() for k in ("verts", "faces", "colors", "rem"))
               for sc in scenes]
-  mesh_bytes = [sum(t.numel() * t.element_size() for t in hs) for hs in h_scenes]
+  mesh_bytes = [sum(a.nbytes for a in ns) for ns in np_scenes]
   origin = np.zeros(3, np.float32)
+  rays_flat = rays_np.reshape(-1)
   rr = pipeline.ScanRenderer(rays_np, origin, H, max_v, max_f, n_streams=args.streams, device=dev, host_io=True,
                              method=args.method)
   rr1 = None
@@ -296,9 +394,27 @@ def run_native(args):
     for k in range(S):
       rr.submit(*d_scenes[k % M])
 
-  def step_host():
-    for k in range(S):
+  def step_pipelined():
+    for k in range(Sp):
       rr.submit_host(*h_scenes[k % M])
+
+  L.vl_ctrace_method(0 if args.method == "cast" else 1)
+
+  def step_plugin():
+    """The reference caller's sequence per scan (fusion_lidar.py:440-450): zero-filled outputs, one C_Trace call."""
+    for k in range(Se):
+      v, f, c, r = np_scenes[k % M]
+      ep, ec = np.zeros(3 * R, np.float32), np.zeros(3 * R, np.int32)
+      rg, rm = np.zeros(R, np.float32), np.zeros(R, np.float32)
+      rtc.C_Trace(rays_flat, origin, v, f, c, r, ep, ec, rg, rm, H, W)
+    return rg
+
+  def reduce_max(ms):
+    if world > 1:
+      t = torch.tensor([ms], dtype=torch.float64, device=dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t.item())
+    return ms
 
   def timed(step_fn, n_steps, profile, fence=None):
     """K steps bracketed by barrier + synchronize; device time from CUDA events on the current stream,
@@ -319,33 +435,43 @@ def run_native(args):
     stage = None
     if profile:
       L.vl_profile_enable(0)
-      n_st = L.vl_profile_stage_count()
-      ms_arr = (ctypes.c_double * n_st)()
-      cnt_arr = (ctypes.c_longlong * n_st)()
-      L.vl_profile_collect(ms_arr, cnt_arr)
-      stage = {L.vl_profile_stage_name(i).decode(): (ms_arr[i], cnt_arr[i]) for i in range(n_st) if cnt_arr[i]}
-    if world > 1:
-      t = torch.tensor([ms], dtype=torch.float64, device=dev)
-      dist.all_reduce(t, op=dist.ReduceOp.MAX)
-      ms = float(t.item())
-    return ms, launches, stage
+      stage = _collect_stages(L)
+    return reduce_max(ms), launches, stage
 
-  import ctypes
-  for _ in range(Wm):  # warm-up: both legs
+  def timed_host(step_fn, n_steps):
+    """K steps of SYNCHRONOUS host calls (the plugin call returns with the results on the host): wall clock between two
+    barriers; the library's kernels run on its own stream, which torch's events do not see."""
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+      step_fn()
+    ms = 1e3 * (time.perf_counter() - t0)
+    barrier()
+    return reduce_max(ms)
+
+  for _ in range(Wm):  # warm-up: all legs
     step_device()
   rr.wait()
   for _ in range(min(Wm, 3)):
-    step_host()
+    step_pipelined()
   rr.wait()
+  for _ in range(min(Wm, 3)):
+    last_rg = step_plugin()
 
   sampler = ClockSampler(local_rank)
   if rank == 0:
     sampler.start()
   ms_dev, launches, _ = timed(step_device, K, profile=False)
-  ms_e2e, _, _ = timed(step_host, K, profile=False)
+  ms_e2e = timed_host(step_plugin, K)
+  ms_pipe, _, _ = timed(step_pipelined, K, profile=False)
   clocks = sampler.stop() if rank == 0 else None
-  # per-kernel durations: same steps again with the library's event profiler on (events are recorded on the
-  # launching streams; kept out of the headline timing because each record costs host time per launch)
+  phase = (ctypes.c_double * 4)()
+  L.vl_ctrace_timing(phase)
+  hits_c, miss_c = ctypes.c_longlong(0), ctypes.c_longlong(0)
+  L.vl_ctrace_cache_stats(ctypes.byref(hits_c), ctypes.byref(miss_c))
+
+  # per-kernel durations: the distinct scans again with the library's event profiler on (events are recorded on the
+  # launching stream; kept out of the headline timing because each record costs host time per launch)
   # -- on ONE stream, so that a kernel's duration is not inflated by kernels of other scans sharing the SMs
   rr1 = pipeline.ScanRenderer(rays_np, origin, H, max_v, max_f, n_streams=1, device=dev, host_io=False,
                               method=args.method, use_graph=False)
@@ -353,7 +479,7 @@ def run_native(args):
   def step_profile():
     for ds in d_scenes:
       rr1.submit(*ds)
-  ms_prof, _, stage = timed(step_profile, max(1, min(K, 4)), profile=True)
+  ms_prof, _, stage = timed(step_profile, 4, profile=True)
   n_active = n_units = 0.0
   if args.method == "cast":   # triangles that can be hit at all / work units of the last profiled scan
     info = (ctypes.c_int * 8)()
@@ -364,18 +490,16 @@ def run_native(args):
   other = "lbvh" if args.method == "cast" else "cast"
   rr2 = pipeline.ScanRenderer(rays_np, origin, H, max_v, max_f, n_streams=args.streams, device=dev, host_io=False,
                               method=other)
+  So = min(S, 256)
 
   def step_other():
-    for k in range(S):
+    for k in range(So):
       rr2.submit(*d_scenes[k % M])
-  for _ in range(3):
-    step_other()
+  step_other()
   rr2.wait()
-  ms_other, _, _ = timed(step_other, max(1, min(K, 5)), profile=False, fence=rr2)
-  other_value = S * H * W * world * max(1, min(K, 5)) / (ms_other * 1e-3) / 1e6
+  ms_other, _, _ = timed(step_other, 3, profile=False, fence=rr2)
+  other_value = So * R * world * 3 / (ms_other * 1e-3) / 1e6
 
-  # parity spot check of the last scan against the library's brute-force kernel on a ray subset is done in
-  # tests/; here only a cheap sanity check that rays hit
   rr.wait()
   hit_frac = float((rr.slots[(S - 1) % len(rr.slots)].out["tri_id"] >= 0).float().mean().item())
 
@@ -384,43 +508,52 @@ def run_native(args):
       dist.destroy_process_group()
     return
 
-  rays_per_step = S * H * W * world
-  value = rays_per_step * K / (ms_dev * 1e-3) / 1e6
-  e2e_value = rays_per_step * K / (ms_e2e * 1e-3) / 1e6
-  h2d = sum(mesh_bytes[k % M] for k in range(S))   # per rank per step
-  d2h = S * (H * W) * (12 + 12 + 4 + 4 + 4)
+  value = S * R * world * K / (ms_dev * 1e-3) / 1e6
+  e2e_value = Se * R * world * K / (ms_e2e * 1e-3) / 1e6
+  pipe_value = Sp * R * world * K / (ms_pipe * 1e-3) / 1e6
+  h2d = sum(mesh_bytes[k % M] for k in range(Se))   # per rank per step, through the plugin call
+  d2h = Se * R * (12 + 12 + 4 + 4 + 4)              # the packed results incl. the hit ids the merge reads
   peak, peak_src = _peaks()
 
-  # roofline of the dominant kernel (algorithmic bytes per launch, DESIGN.md "kernels")
-  nt = float(np.mean(n_tris)); nv = float(np.mean(n_verts)); R = H * W
+  # roofline of the dominant kernel.  COMPULSORY bytes per launch: every input once + every output once; records and
+  # work units that live between two kernels of a scan are intermediates (they stay in L2) and do not count.
+  nt = float(np.mean(n_tris)); nv = float(np.mean(n_verts))
   alg_bytes = {
       "bounds": 12 * nv,
-      "morton": 12 * nt + 12 * nv + 4 * nt + 4 * nt,          # faces + verts(gather, once) + key + flag
-      "sort_pass": (4 + 4) * nt * 2,                          # key+val in, key+val out (one 8-bit digit)
-      "emit_climb": 8 * nt + 12 * nt + 28 * nv + 48 * nt + 16 * nt + 64 * 0.3 * nt,   # ~0.3 nodes per triangle are written
+      "morton": 12 * nt + 12 * nv + 8 * nt,
+      "sort_pass": 16 * nt,
+      "emit_climb": 8 * nt + 12 * nt + 28 * nv + 64 * nt + 64 * 0.3 * nt,
       "top_climb": 64 * 0.004 * nt,
       "trace": 112 * nt + 12 * R + 36 * R,
-      # scene-streaming cast: faces + vertices read once; records (64 B) and work units (8 B) of the triangles that
-      # can be hit at all written once, read once; beam index (sorted beams 16 B, cells 4 B, slots 8 B) read once
       "cast_init": 8 * R,
-      "cast_setup": 12 * nt + 12 * nv + 64 * n_active + 8 * n_units,
-      "cast_items": 64 * n_active + 8 * n_units + 16 * R + 4 * R + 8 * R,
-      "cast_resolve": (8 + 4 + 16) * R + 36 * R + 36 * R,   # keys, slots, directions in; outputs; face/colour/remission gathers
+      "cast_setup": 12 * nt + 12 * nv,                      # faces + vertices in; records / units are intermediates
+      "cast_items": 16 * R + 8 * R,                         # sorted beams in, closest-hit keys out
+      "cast_resolve": (8 + 4 + 16) * R + 36 * R,            # keys, slots, directions in; five outputs out
   }
-  path = ("cast_init", "cast_setup", "cast_items", "cast_resolve") if args.method == "cast" else (
-      "bounds", "morton", "sort_pass", "emit_climb", "top_climb", "trace")
+  ncu_names = {"cast_setup": "cast_setup", "cast_items": "cast_items", "cast_resolve": "cast_resolve", "cast_init": "cast_init",
+               "trace": "trace"}
   total_stage_ms = sum(v[0] for v in stage.values()) or 1.0
   dom = max(stage.items(), key=lambda kv: kv[1][0])[0]
   dom_ms, dom_n = stage[dom]
   achieved = alg_bytes.get(dom, 0.0) / (dom_ms / dom_n * 1e-3) / 1e9
+  cap = _ncu(ncu_names.get(dom, dom))
+  sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+  sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+  issue = None
+  if cap.get("warp_instructions"):   # instructions issued / issue slots available during the launch (4 schedulers per SM)
+    issue = float(cap["warp_instructions"]) / (dom_ms / dom_n * 1e-3 * sm_hz * sm_count * 4)
   stages_out = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share": v[0] / total_stage_ms,
-                    "alg_GBps": alg_bytes.get(k, 0.0) / (v[0] / v[1] * 1e-3) / 1e9} for k, v in stage.items()}
+                    "compulsory_GBps": alg_bytes.get(k, 0.0) / (v[0] / v[1] * 1e-3) / 1e9} for k, v in stage.items()}
+  scan_bytes = 12 * nt + 28 * nv + 12 * R + 36 * R      # one scan: mesh + rays in, five outputs out
+  step_gbps = scan_bytes * S * K / (ms_dev * 1e-3) / 1e9
 
-  pipe = None
+  pipe_c1 = pipe_c4 = deform = None
   if world == 1 and not args.no_pipeline:
     del rr2
     torch.cuda.empty_cache()
-    pipe = pipeline_c1(L, dev)
+    pipe_c1, pipe_c4 = pipelines(L, dev)
+    torch.cuda.empty_cache()
+    deform = deform_leg()
 
   # cpu baseline: the reference C++ ray tracer on a bounded sample of the same scans
   cpu = None
@@ -428,7 +561,7 @@ def run_native(args):
     n_calls = min(args.cpu_scans, M)
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     times, kind = time_reference(scenes, rays_np, n_calls=n_calls, warmup=0)
-    cpu_val = n_calls * H * W / sum(times) / 1e6
+    cpu_val = n_calls * R / sum(times) / 1e6
     cpu = {"value": cpu_val, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": kind,
            "sample": "%d of the step's %d distinct scans (%d tris, %d rays each), one ctrace call per scan incl. triangle "
                      "construction + BVH build; %.2f s/scan" % (n_calls, M, n_tris[0], R, sum(times) / n_calls)}
@@ -437,27 +570,43 @@ def run_native(args):
       "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
       "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "f32", "data": "synthetic",
-      "config": {"workload": WORKLOAD, "method": args.method, "scans_per_step_per_gpu": S, "rays_per_scan": R,
-                 "tris_per_scan": int(nt), "streams": args.streams,
-                 "l2": "inputs larger than L2: %d distinct meshes x %.0f MB cycled per step + %.0f MB scratch per stream"
-                       % (M, mesh_bytes[0] / 1e6, rr.slots[0].blob.numel() / 1e6),
-                 "submission": "one CUDA graph launch per scan (vl_cast_graph_launch)" if rr.use_graph else "kernel by kernel",
-                 "e2e_api": "ScanRenderer.submit_host (pinned host mesh -> H2D -> %s -> D2H of 5 outputs)"
-                            % ("vl_cast" if args.method == "cast" else "vl_bvh_build -> vl_trace"),
-                 "beam_index": "built once per sensor outside the timed region (vl_beams_build, ~40 us)" if args.method == "cast" else None},
+      "config": shared_config(),
+      "arm": {"method": args.method, "scans_per_step_per_gpu": S, "e2e_scans_per_step_per_gpu": Se,
+              "pipelined_scans_per_step_per_gpu": Sp, "streams": args.streams, "tris_per_scan_mean": int(nt),
+              "timed_region_s": {"value": ms_dev / 1e3, "e2e": ms_e2e / 1e3, "e2e_pipelined": ms_pipe / 1e3},
+              "l2": "inputs larger than L2: %d distinct meshes x %.0f MB cycled per step + %.0f MB scratch per stream"
+                    % (M, mesh_bytes[0] / 1e6, rr.slots[0].blob.numel() / 1e6),
+              "submission": "one CUDA graph launch per scan (vl_cast_graph_launch)" if rr.use_graph else "kernel by kernel",
+              "normalize": "ray directions normalised once per sensor on the host with the reference's rsqrtps + Newton step (vl_normalize_rays)",
+              "beam_index": "built once per sensor outside the timed region (vl_beams_build, ~40 us)" if args.method == "cast" else None},
       "scans_per_s": S * world * K / (ms_dev * 1e-3),
       "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-              "scans_per_s": S * world * K / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / K},
+              "scans_per_s": Se * world * K / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / K, "ms_per_scan": ms_e2e / K / Se,
+              "api": "auxiliary.raytracer.RayTracerCython.C_Trace -> extern \"C\" ctrace (include/vlidar.h) on pageable numpy "
+                     "buffers, one synchronous call per scan, outputs zero-filled by the caller (fusion_lidar.py:440-450)",
+              "timer": "host wall clock around synchronous calls, max over ranks",
+              "last_call_phase_ms": {"ray_compare_beam_cache": phase[0], "stage_and_h2d_issue": phase[1], "cast_and_d2h_wait": phase[2],
+                                     "merge_hits": phase[3]},
+              "beam_cache": {"hits": hits_c.value, "rebuilds": miss_c.value},
+              "hit_fraction": float((last_rg > 0).mean())},
+      "e2e_pipelined": {"value": pipe_value, "unit": "Mrays/s", "scans_per_s": Sp * world * K / (ms_pipe * 1e-3), "ms_per_step": ms_pipe / K,
+                        "h2d_bytes_per_step": sum(mesh_bytes[k % M] for k in range(Sp)) * world, "d2h_bytes_per_step": Sp * R * 36 * world,
+                        "api": "ScanRenderer.submit_host (pinned host mesh -> H2D -> %s -> D2H of 5 outputs), %d streams"
+                               % ("vl_cast" if args.method == "cast" else "vl_bvh_build -> vl_trace", args.streams)},
+      "e2e_deform": deform,
       "gpu_launches": int(launches),
       "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                   "frac": achieved / peak, "traffic": _ncu_traffic(dom), "peak_source": peak_src,
+                   "frac": achieved / peak, "traffic": cap.get("dram_bytes_per_launch"), "peak_source": peak_src,
+                   "bytes": "compulsory: inputs once + outputs once (faces + vertices for cast_setup); intermediates between kernels excluded",
                    "alg_bytes_per_launch": alg_bytes.get(dom, 0.0), "ms_per_launch": dom_ms / dom_n,
-                   "step_alg_bytes": sum(alg_bytes[k] * (4 if k == "sort_pass" else 1) for k in path) * S,
-                   "scan_alg_bytes_in_out": 12 * nt + 28 * nv + 36 * R,
+                   "issue_slot_frac": issue, "warp_instructions_per_launch": cap.get("warp_instructions"),
+                   "limit": "issue-bound: the reference's Moller-Trumbore arithmetic with every rounding explicit (no FMA contraction)",
+                   "whole_step": {"compulsory_bytes_per_scan": scan_bytes, "GBps": step_gbps, "frac": step_gbps / peak},
                    "tris_that_can_be_hit": n_active, "work_units": n_units},
       "stages": stages_out,
-      "other_method": {"method": other, "value": other_value, "unit": "Mrays/s", "ms_per_step": ms_other / max(1, min(K, 5))},
-      "pipeline_c1": pipe,
+      "other_method": {"method": other, "value": other_value, "unit": "Mrays/s", "ms_per_step": ms_other / 3, "scans_per_step": So},
+      "pipeline_c1": pipe_c1,
+      "pipeline_c4": pipe_c4,
       "cpu_baseline": cpu,
       "numa": numa,
       "clocks": clocks,
@@ -474,13 +623,15 @@ def main():
   ap.add_argument("--steps", type=int, default=10)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="native", choices=["native", "reference"])
-  ap.add_argument("--scans-per-step", type=int, default=32)
+  ap.add_argument("--scans-per-step", type=int, default=2048, help="device-resident scans per step and GPU (value leg)")
+  ap.add_argument("--e2e-scans-per-step", type=int, default=48, help="plugin calls per step and GPU (e2e leg)")
+  ap.add_argument("--pipelined-scans-per-step", type=int, default=96, help="ScanRenderer.submit_host scans per step and GPU")
   ap.add_argument("--distinct-meshes", type=int, default=8)
   ap.add_argument("--streams", type=int, default=8)
   ap.add_argument("--method", default="cast", choices=["cast", "lbvh"])
   ap.add_argument("--cpu-scans", type=int, default=8, help="scans timed for cpu_baseline (about 1.2 s each)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
-  ap.add_argument("--no-pipeline", action="store_true", help="skip the config-1 chain measurement (pipeline_c1)")
+  ap.add_argument("--no-pipeline", action="store_true", help="skip the config-1 / config-4 chains and the deform leg")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
   if args.impl == "reference":

@@ -218,6 +218,11 @@ int vl_project_snap(const double* d_points, const float* d_remissions, const uin
                     uint8_t* d_keep, int* d_n_kept, void* d_workspace, size_t workspace_bytes,
                     vl_stream stream);
 
+/* Axis-aligned bounds of the points the projection kept: replaces SemLaserScan.get_bnds (auxiliary/laserscan.py:
+ * np.amin / np.amax over the points after remove_points), which `mergemesh` clips the volume to (laserscan.py:957-962).
+ * d_keep (nullable: every point) is vl_project's keep mask; d_bounds6 f64[6] = min x y z, max x y z (exact). */
+int vl_points_bounds(const double* d_points, const uint8_t* d_keep, long n_points, double* d_bounds6, vl_stream stream);
+
 /* Reverse projection of the `cp` adaption: replaces LaserScan.do_reverse_projection_new
  * auxiliary/laserscan.py:475-501.  d_depth_im f32[H*W], d_proj_x / d_proj_y f64[H*W] (image coordinates of each
  * pixel's point in [0, W] / [0, H], float or clamped) -> d_back_points f64[3*H*W], float64 arithmetic like numpy's

@@ -55,6 +55,7 @@ SIGNATURES = {
     "vl_project_workspace_bytes": (_sz, [_l, _i, _i]),
     "vl_project": (_i, [_vp, _vp, _vp, _l, _d, _d, _i, _i, _i] + [_vp] * 7 + [_sz, _vp]),
     "vl_project_snap": (_i, [_vp, _vp, _vp, _l, _d, _d, _i, _i, _i, _vp, _i] + [_vp] * 7 + [_sz, _vp]),
+    "vl_points_bounds": (_i, [_vp, _vp, _l, _vp, _vp]),
     "vl_reverse_project": (_i, [_vp, _vp, _vp, _i, _i, _d, _d, _vp, _vp]),
     "vl_tsdf_init": (_i, [_vp] * 4 + [_ll, _vp]),
     "vl_tsdf_integrate": (_i, [_vp] * 4 + [_i, _i, _i, _vp] + [_f] * 5 + [_vp] * 3 + [_i, _i, _vp]),

@@ -101,43 +101,68 @@ class TSDFVolume(object):
     self._dev.integrate(color_im, depth_im, rem_im, obs_weight)
     self._mesh = None
 
+  def integrate_device(self, label_im, depth_im, rem_im, obs_weight=1.):
+    """integrate() for images that are already on the device: label_im i32[H,W] is channel 0 of the reference's
+    colour image (proj_label3[:, :, 0] = label, the other two zero: laserscan.py:970-973), whose fold :259-264 is
+    label * 65536 -- exact in float32 for every 16-bit label."""
+    self._dev.integrate(label_im.to(torch.float32) * 65536.0, depth_im, rem_im, obs_weight)
+    self._mesh = None
+
   # Copy voxel volume to CPU
   def get_volume(self):
     return self._dev.tsdf.cpu().numpy(), self._dev.color.cpu().numpy(), self._dev.rem.cpu().numpy()
 
-  def get_mesh_device(self):
-    """Device-resident mesh: dict(verts f32[N_v,3], faces i32[N_t,3], norms f32[N_v,3], colors u8[N_v,3], rem f32[N_v])."""
-    if self._mesh is None:
-      self._mesh = self._dev.extract_mesh()
+  def get_mesh_device(self, want_norms=False):
+    """Device-resident mesh: dict(verts f32[N_v,3], faces i32[N_t,3], norms f32[N_v,3] or None, colors u8[N_v,3],
+    rem f32[N_v]).  The normals are only written when asked for (the ray cast does not read them)."""
+    if self._mesh is None or (want_norms and self._mesh["norms"] is None):
+      self._mesh = self._dev.extract_mesh(want_norms=want_norms)
     return self._mesh
 
   # Get mesh of voxel volume via marching cubes
   def get_mesh(self, color_lut):
-    m = self.get_mesh_device()
+    m = self.get_mesh_device(want_norms=True)
     return (m["verts"].cpu().numpy(), m["faces"].cpu().numpy(), m["norms"].cpu().numpy(),
             m["colors"].cpu().numpy(), m["rem"].cpu().numpy())
+
+  _beams_cache = {}   # (ray buffer id, H, device) -> (rays, Beams): the beam index is the target sensor's constant
 
   def throw_rays_at_mesh_device(self, rays, origin, H, W):
     m = self.get_mesh_device()
     colors = m["colors"].to(torch.int32)  # colors.astype(np.int32), :437
+    dev = m["verts"].device
+    R = int(np.asarray(rays).size // 3) if not torch.is_tensor(rays) else rays.numel() // 3
+    # the four per-ray outputs as views of ONE buffer (a single device -> host copy for the caller)
+    packed = torch.empty(32 * R, dtype=torch.uint8, device=dev)
+    outs = dict(packed=packed, endpoints=packed[:12 * R].view(torch.float32), endcolors=packed[12 * R:24 * R].view(torch.int32),
+                range=packed[24 * R:28 * R].view(torch.float32), endrem=packed[28 * R:32 * R].view(torch.float32))
     try:
-      beams = engine.Beams(rays, H, m["verts"].device)
-      out = engine.cast(beams, m["verts"], m["faces"], colors, m["rem"], origin, want_ids=False, zero_misses=True)
+      key = (id(rays), int(H), str(dev))
+      hit = TSDFVolume._beams_cache.get(key)
+      if hit is None or hit[0] is not rays:
+        if len(TSDFVolume._beams_cache) > 8:
+          TSDFVolume._beams_cache.clear()
+        hit = TSDFVolume._beams_cache[key] = (rays, engine.Beams(rays, H, dev))
+      beams = hit[1]
+      out = engine.cast(beams, m["verts"], m["faces"], colors, m["rem"], origin, out=outs, want_ids=False, zero_misses=True)
     except _lib.VlidarError as e:
       if e.code != _lib.VL_ENOSPACE:
         raise
       bvh = engine.Bvh(m["verts"], m["faces"], colors, m["rem"])
-      out = engine.trace(bvh, rays, origin, H, want_ids=False, zero_misses=True)
+      out = engine.trace(bvh, rays, origin, H, out=outs, want_ids=False, zero_misses=True)
     return out, m
 
   def throw_rays_at_mesh(self, rays, origin, H, W, color_lut):
     print("Get mesh by marching cubes...")
     print("Raytracing...")
     out, m = self.throw_rays_at_mesh_device(rays, origin, H, W)
-    # the per-ray results as numpy like the reference; the mesh (elements 2-4) lazily: see LazyHostArray
-    return out["endpoints"].cpu().numpy().reshape(-1, 3), out["endcolors"].cpu().numpy().reshape(-1, 3), \
+    # the per-ray results as numpy like the reference (one device -> host copy of the packed buffer); the mesh
+    # (elements 2-4) lazily: see LazyHostArray
+    a = out["packed"].cpu().numpy()
+    R = a.size // 32
+    return a[:12 * R].view(np.float32).reshape(-1, 3), a[12 * R:24 * R].view(np.int32).reshape(-1, 3), \
         LazyHostArray(m["verts"]), LazyHostArray(m["colors"]), LazyHostArray(m["faces"]), \
-        out["range"].cpu().numpy().reshape(-1, W), out["endrem"].cpu().numpy().reshape(-1, W)
+        a[24 * R:28 * R].view(np.float32).reshape(-1, W), a[28 * R:32 * R].view(np.float32).reshape(-1, W)
 
 
 # ------------------------------------------------------------------------------

@@ -23,7 +23,53 @@ from . import fusion_lidar as fl
 from .np_ioueval import iouEval
 
 
-class LaserScan:
+class _LazyAttrs(object):
+  """Attributes whose value is produced on first read.  The reference computes every derived array eagerly in numpy;
+  at hundreds of scans per second most of them are never looked at (the GUI's images, the per-point colours, the
+  per-pixel coordinates only the `cp` adaption needs), so they are kept as thunks -- often over tensors that are still on
+  the device -- and materialise, with the reference's values, dtypes and shapes, the moment somebody reads them."""
+
+  def _lazy_set(self, name, thunk):
+    d = self.__dict__
+    d.pop(name, None)
+    d.setdefault("_lazy", {})[name] = thunk
+
+  def _lazy_take(self, name):
+    """The current producer of `name` (a thunk returning its value), detached from the attribute."""
+    d = self.__dict__
+    lazy = d.get("_lazy")
+    if lazy and name in lazy:
+      return lazy.pop(name)
+    value = d.pop(name)
+    return lambda: value
+
+  def __getattr__(self, name):   # reached only when the normal lookup fails
+    lazy = self.__dict__.get("_lazy")
+    if lazy and name in lazy:
+      value = lazy.pop(name)()
+      self.__dict__[name] = value
+      return value
+    raise AttributeError("%s object has no attribute %r" % (type(self).__name__, name))
+
+  def __setattr__(self, name, value):
+    lazy = self.__dict__.get("_lazy")
+    if lazy:
+      lazy.pop(name, None)
+    object.__setattr__(self, name, value)
+
+
+def _once(fn):
+  """fn() evaluated at most once."""
+  box = []
+
+  def get():
+    if not box:
+      box.append(fn())
+    return box[0]
+  return get
+
+
+class LaserScan(_LazyAttrs):
   """Class that contains LaserScan with x,y,z,r"""
   EXTENSIONS_SCAN = ['.bin']
 
@@ -42,14 +88,17 @@ class LaserScan:
     self.points = np.zeros((0, 3), dtype=np.float32)
     self.remissions = np.zeros((0, ), dtype=np.float32)
     self.back_points = np.zeros((0, 3), dtype=np.float32)
-    self.proj_range = np.full((H, W), -1, dtype=np.float32)
-    self.proj_xyz = np.full((H, W, 3), -1, dtype=np.float32)
-    self.proj_remissions = np.full((H, W), -1, dtype=np.float32)
-    self.proj_idx = np.full((H, W), -1, dtype=np.int32)
+    # the image-sized defaults (laserscan.py:66-98) are allocated when first touched
+    self._lazy_set("proj_range", lambda: np.full((H, W), -1, dtype=np.float32))
+    self._lazy_set("proj_xyz", lambda: np.full((H, W, 3), -1, dtype=np.float32))
+    self._lazy_set("proj_remissions", lambda: np.full((H, W), -1, dtype=np.float32))
+    self._lazy_set("proj_idx", lambda: np.full((H, W), -1, dtype=np.int32))
     self.proj_x = np.zeros((0, 1), dtype=np.float32)
     self.proj_y = np.zeros((0, 1), dtype=np.float32)
     self.unproj_range = np.zeros((0, 1), dtype=np.float32)
-    self.proj_mask = np.zeros((H, W), dtype=np.int32)
+    self._lazy_set("proj_mask", lambda: np.zeros((H, W), dtype=np.int32))
+    self._proj_dev = None
+    self._bnds = None
 
   def size(self):
     return self.points.shape[0]
@@ -100,7 +149,17 @@ class LaserScan:
     self.points = self.points[keep_index]
     self.remissions = self.remissions[keep_index]
     self.label = self.label[keep_index]
-    self.label_color = self.label_color[keep_index]
+    if "label_color" in self.__dict__:   # still a thunk over `label` otherwise (colorize): filtering label filters it
+      self.label_color = self.label_color[keep_index]
+
+  def _remove_points_deferred(self, keep_fn):
+    """remove_points with a keep mask that is still on the device: the four per-point arrays become thunks."""
+    for name in ("points", "remissions", "label"):
+      old = self._lazy_take(name)
+      self._lazy_set(name, (lambda old: lambda: old()[keep_fn()])(old))
+    if "label_color" in self.__dict__:
+      old = self._lazy_take("label_color")
+      self._lazy_set("label_color", (lambda old: lambda: old()[keep_fn()])(old))
 
   # ---- projections ---------------------------------------------------------------------------
   def _angles(self, fov_up, fov_down, remove):
@@ -150,43 +209,64 @@ class LaserScan:
     self.proj_mask = (self.proj_idx > 0).astype(np.float32)
 
   def do_range_projection_new(self, fov_up, fov_down, remove=False, method="depth"):
-    """Nearest-point-per-pixel projection (laserscan.py:294-391) as one atomicMin scatter on the device."""
+    """Nearest-point-per-pixel projection (laserscan.py:294-391) as one atomicMin scatter on the device.  The images
+    stay on the device (`_proj_dev`, what deform() feeds to the TSDF integration); every host attribute the reference
+    sets here is a thunk with the reference's value."""
     if method != "depth":
       raise NotImplementedError("only method='depth' (the one deform() uses, laserscan.py:952) runs on the device")
     pts = np.ascontiguousarray(self.points, np.float64)
     out = engine.project(pts, np.ascontiguousarray(self.remissions, np.float32),
                          np.ascontiguousarray(self.label).astype(np.uint32), fov_up, fov_down, self.proj_H, self.proj_W,
-                         remove=remove, beam_angles=self.beam_angles if self.beam_angles else None)
-    if int(out["n_kept"].item()) == 0:  # the reference fails the same way at :384 (fancy index into an empty array)
+                         remove=remove, beam_angles=self.beam_angles if self.beam_angles else None, want_bounds=True)
+    meta = out["meta"].cpu().numpy()            # one 64-byte copy: bounds of the kept points + their number
+    if int(meta[48:52].view(np.int32)[0]) == 0:  # the reference fails the same way at :384 (fancy index into an empty array)
       raise IndexError("do_range_projection_new: no point left after the depth / field-of-view filters")
-    keep = out["keep"].cpu().numpy()
-    if not remove:  # the reference always drops depth == 0 points (:307-309), FOV filtering is optional
-      keep = np.linalg.norm(pts, 2, axis=1) != 0
-    self.remove_points(keep)
+    self._proj_dev = out
     self._fov = (fov_up, fov_down)
-    self.index = out["index"].cpu().numpy()
-    self.range_image = out["range_image"].cpu().numpy()
-    self.proj_remissions = out["proj_remissions"].cpu().numpy()
-    self._proj_label_dev = out["proj_label"].cpu().numpy()
-    mask = self.index >= 0
-    self.label_image = np.zeros((self.proj_H, self.proj_W, 1))
-    self.label_image[mask, 0] = self.label[self.index[mask]]
-    self.label_color_image = np.zeros((self.proj_H, self.proj_W, 3))
-    self.label_color_image[mask] = self.label_color[self.index[mask]]
-    self.proj_range = self.range_image
-    self.unproj_range = np.linalg.norm(self.points, 2, axis=1)
+    H, W = self.proj_H, self.proj_W
+    if remove:
+      keep_fn = _once(lambda: out["keep"].cpu().numpy())
+      self._bnds = meta[:48].view(np.float64).reshape(2, 3).T.copy()   # get_bnds() of the kept points, from the device
+    else:  # the reference always drops depth == 0 points (:307-309), FOV filtering is optional
+      keep_fn = _once(lambda: np.linalg.norm(pts, 2, axis=1) != 0)
+      self._bnds = None
+    self._remove_points_deferred(keep_fn)
+    self._lazy_set("index", lambda: out["index"].cpu().numpy())
+    self._lazy_set("range_image", lambda: out["range_image"].cpu().numpy())
+    self._lazy_set("proj_remissions", lambda: out["proj_remissions"].cpu().numpy())
+    self._lazy_set("proj_range", lambda: self.range_image)
+
+    def label_image():
+      mask = self.index >= 0
+      im = np.zeros((H, W, 1))
+      im[mask, 0] = self.label[self.index[mask]]
+      return im
+
+    def label_color_image():
+      mask = self.index >= 0
+      im = np.zeros((H, W, 3))
+      im[mask] = self.label_color[self.index[mask]]
+      return im
+    self._lazy_set("label_image", label_image)
+    self._lazy_set("label_color_image", label_color_image)
+    self._lazy_set("unproj_range", lambda: np.linalg.norm(self.points, 2, axis=1))
+
     # per-pixel image coordinates of the winning point (float and clamped), laserscan.py:384-388
-    w = self.points[self.index]  # index -1 wraps to the last point, exactly like the reference's fancy index
-    depth = np.linalg.norm(w, 2, axis=2)
-    fu, fd = fov_up / 180.0 * np.pi, fov_down / 180.0 * np.pi
-    with np.errstate(invalid="ignore", divide="ignore"):
-      self.proj_x_float = 0.5 * (-np.arctan2(w[..., 1], w[..., 0]) / np.pi + 1.0) * self.proj_W
-      pitch = np.arcsin(w[..., 2] / depth)
-      if self.beam_angles:  # :321-327, the H*W winners only
-        ba = np.asarray(self.beam_angles, np.float64)
-        pitch = ba[np.abs(pitch[..., None] - ba).argmin(axis=-1)]
-      self.proj_y_float = (1.0 - (pitch + abs(fd)) / (abs(fd) + abs(fu))) * self.proj_H
-    self.proj_x, self.proj_y = self._clamp(self.proj_x_float, self.proj_y_float)
+    def coords():
+      w = self.points[self.index]  # index -1 wraps to the last point, exactly like the reference's fancy index
+      depth = np.linalg.norm(w, 2, axis=2)
+      fu, fd = fov_up / 180.0 * np.pi, fov_down / 180.0 * np.pi
+      with np.errstate(invalid="ignore", divide="ignore"):
+        xf = 0.5 * (-np.arctan2(w[..., 1], w[..., 0]) / np.pi + 1.0) * W
+        pitch = np.arcsin(w[..., 2] / depth)
+        if self.beam_angles:  # :321-327, the H*W winners only
+          ba = np.asarray(self.beam_angles, np.float64)
+          pitch = ba[np.abs(pitch[..., None] - ba).argmin(axis=-1)]
+        yf = (1.0 - (pitch + abs(fd)) / (abs(fd) + abs(fu))) * H
+      return (xf, yf) + self._clamp(xf, yf)
+    coords = _once(coords)
+    for k, name in enumerate(("proj_x_float", "proj_y_float", "proj_x", "proj_y")):
+      self._lazy_set(name, (lambda k: lambda: coords()[k])(k))
 
   def do_reverse_projection_new(self, fov_up, fov_down, preserve_float=False, host=False):
     """Pixel + depth -> xyz (laserscan.py:475-501), the `cp` adaption's back projection, on the device
@@ -232,8 +312,11 @@ class SemLaserScan(LaserScan):
     self.label_image = np.zeros((0, ), dtype=np.uint32)
     self.label_color_image = np.zeros((0, 3), dtype=np.uint32)
     self.label_color = np.zeros((0, 3), dtype=np.float32)
-    self.proj_label = np.zeros((self.proj_H, self.proj_W), dtype=np.int32)
-    self.proj_color = np.zeros((self.proj_H, self.proj_W, 3), dtype=float)
+    H, W = self.proj_H, self.proj_W
+    zeros_label = lambda: np.zeros((H, W), dtype=np.int32)
+    zeros_label.is_default = True
+    self._lazy_set("proj_label", zeros_label)
+    self._lazy_set("proj_color", lambda: np.zeros((H, W, 3), dtype=float))
 
   @staticmethod
   def _read_label(filename, extensions):
@@ -262,7 +345,8 @@ class SemLaserScan(LaserScan):
     self.do_label_projection()
 
   def colorize(self):
-    self.label_color = self.color_lut[self.label].reshape((-1, 3))
+    # laserscan.py:640-643; a thunk over `label`: remove_points / remove_classes filter label, which filters this
+    self._lazy_set("label_color", lambda: self.color_lut[self.label].reshape((-1, 3)))
 
   def do_label_projection(self):
     mask = self.proj_idx >= 0
@@ -270,21 +354,35 @@ class SemLaserScan(LaserScan):
     self.proj_color[mask] = self.color_lut[self.label[self.proj_idx[mask]]]
 
   def do_label_projection_new(self):
-    mask = self.index >= 0
-    self.proj_label[mask] = self.label[self.index[mask]]
-    self.proj_color[mask] = self.color_lut[self.label[self.index[mask]]]
+    # laserscan.py:672-676: proj_label[mask] = label[index[mask]], proj_color[mask] = color_lut[...]; on top of whatever
+    # the two images hold (zeros after reset()), evaluated when read -- the label image itself is already on the device
+    base_label, base_color = self._lazy_take("proj_label"), self._lazy_take("proj_color")
+    dev = self._proj_dev
+
+    def proj_label():
+      if getattr(base_label, "is_default", False) and dev is not None:
+        return dev["proj_label"].cpu().numpy()   # zeros + labels of the winners: what the device image holds
+      im, mask = base_label(), self.index >= 0
+      im[mask] = self.label[self.index[mask]]
+      return im
+
+    def proj_color():
+      im, mask = base_color(), self.index >= 0
+      im[mask] = self.color_lut[self.label[self.index[mask]]]
+      return im
+    self._lazy_set("proj_label", proj_label)
+    self._lazy_set("proj_color", proj_color)
 
   def remove_class(self, class_index):
     self.remove_classes([class_index])
 
   def remove_classes(self, classes):
     keep_index = ~np.isin(self.label, np.asarray(list(classes), dtype=np.int64))
-    self.points = self.points[keep_index]
-    self.remissions = self.remissions[keep_index]
-    self.label = self.label[keep_index]
-    self.label_color = self.label_color[keep_index]
+    self.remove_points(keep_index)
 
   def get_bnds(self):
+    if getattr(self, "_bnds", None) is not None and "points" not in self.__dict__:
+      return self._bnds   # the kept points are still to be filtered on the host: their bounds came back from the device
     return np.concatenate((np.amin(self.points, axis=0).reshape(3, 1), np.amax(self.points, axis=0).reshape(3, 1)), axis=1)
 
   def _label_map(self, sequential):
@@ -300,7 +398,7 @@ class SemLaserScan(LaserScan):
     return self._label_map(False)
 
 
-class MultiSemLaserScan():
+class MultiSemLaserScan(_LazyAttrs):
   """Class that contains multiple LaserScans with x,y,z,r,label,color_label"""
   write_ply = False  # the reference writes ./test.ply after every mergemesh deform (laserscan.py:1010)
 
@@ -358,35 +456,58 @@ class MultiSemLaserScan():
     m.points = np.concatenate([m.points] + [s.points for s in self.scans])
     m.remissions = np.concatenate([m.remissions] + [s.remissions for s in self.scans])
     m.label = np.concatenate([m.label] + [s.label for s in self.scans])
-    m.label_color = np.concatenate([m.label_color] + [s.label_color for s in self.scans])
+    m.colorize()   # = the concatenation of the scans' label_color (laserscan.py:944): one look-up table for all, lazily
     return m
 
+  _rays_cache = {}
+
   def _cast(self, tsdf_vol, lut):
-    """Ray-cast the target beam pattern against the fused volume and fill the attributes write()/compare() read.
-    The per-ray results (a few MB) come to the host like in the reference; the mesh deform() also returns stays on the
-    device behind LazyHostArray -- the batch driver never looks at it (lidar_deform.py:415), the GUI and the PLY
-    dump get a host copy the moment they do."""
+    """Ray-cast the target beam pattern against the fused volume and fill the attributes write() / compare() read.
+    The per-ray results stay on the device in ONE packed buffer that comes to the host, once, when the first of
+    back_points / proj_range / proj_remissions / label_image / proj_color / label_color is read; the mesh deform() also
+    returns stays on the device behind LazyHostArray -- the batch driver never looks at it (lidar_deform.py:415), the
+    GUI and the PLY dump get a host copy the moment they do."""
     import torch
-    rays = self.create_rays(self.t_fov_up, self.t_fov_down, self.t_H, self.t_W)
+    key = (self.t_fov_up, self.t_fov_down, self.t_H, self.t_W)
+    rays = MultiSemLaserScan._rays_cache.get(key)   # the target sensor's constant (create_rays, laserscan.py:981)
+    if rays is None:
+      rays = MultiSemLaserScan._rays_cache[key] = self.create_rays(*key)
     origin = np.array([0, 0, 0]).astype(np.float32)
     print("Get mesh by marching cubes...")
     print("Raytracing...")
     out, m = tsdf_vol.throw_rays_at_mesh_device(rays, origin, self.t_H, self.t_W)
-    self.back_points = out["endpoints"].cpu().numpy().reshape(-1, 3)
-    label_color = out["endcolors"].cpu().numpy().reshape(-1, 3)
-    self.proj_range = out["range"].cpu().numpy().reshape(-1, self.t_W)
-    self.proj_remissions = out["endrem"].cpu().numpy().reshape(-1, self.t_W)
-    self.proj_color = label_color.reshape(self.t_H, self.t_W, 3)
-    self.label_color = lut[label_color[:, 2]]
-    self.label_image = np.copy(self.proj_color[:, :, 2])
-    self.proj_color = lut[self.label_image]
+    tH, tW, R = self.t_H, self.t_W, self.t_H * self.t_W
     lut_np = np.asarray(lut)
+
+    def host():   # [endpoints 3R f32 | endcolors 3R i32 | range R f32 | endrem R f32], one device -> host copy
+      a = out["packed"].cpu().numpy()
+      return (a[:12 * R].view(np.float32).reshape(-1, 3), a[12 * R:24 * R].view(np.int32).reshape(-1, 3),
+              a[24 * R:28 * R].view(np.float32).reshape(-1, tW), a[28 * R:32 * R].view(np.float32).reshape(-1, tW))
+    host = _once(host)
+    self._lazy_set("back_points", lambda: host()[0])
+    self._lazy_set("proj_range", lambda: host()[2])
+    self._lazy_set("proj_remissions", lambda: host()[3])
+    self._lazy_set("label_image", lambda: np.copy(host()[1].reshape(tH, tW, 3)[:, :, 2]))   # laserscan.py:1001-1003
+    self._lazy_set("label_color", lambda: lut_np[host()[1][:, 2]])
+    self._lazy_set("proj_color", lambda: lut_np[self.label_image])
 
     def vertex_colors(t):   # lut[colors[:, 2]] (laserscan.py:1004-1005), looked up on the device when it is needed
       if isinstance(t, str):
         return (int(m["colors"].shape[0]),) + tuple(lut_np.shape[1:]) if t == "shape" else lut_np.dtype
       return torch.from_numpy(lut_np).to(t.device)[t[:, 2].long()]
     return (fl.LazyHostArray(m["verts"]), fl.LazyHostArray(m["colors"], vertex_colors), fl.LazyHostArray(m["faces"]))
+
+  @staticmethod
+  def _integrate(tsdf_vol, scan):
+    """tsdf_vol.integrate(proj_label3, proj_range, proj_remissions, eye(3)) (laserscan.py:890-897, 970-975) on the
+    images the projection left on the device -- unless somebody replaced the host attributes in between."""
+    dev = scan._proj_dev
+    if dev is not None and not any(k in scan.__dict__ for k in ("proj_label", "proj_range", "range_image", "proj_remissions")):
+      tsdf_vol.integrate_device(dev["proj_label"], dev["range_image"], dev["proj_remissions"], obs_weight=1.)
+      return
+    proj_label3 = np.zeros(scan.proj_color.shape)
+    proj_label3[:, :, 0] = scan.proj_label
+    tsdf_vol.integrate(proj_label3, scan.proj_range, scan.proj_remissions, np.eye(3), obs_weight=1.)
 
   def deform(self, adaption, poses, idx):
     """ Deforms laserscan with specified adaption method and transformation (laserscan.py:819-1021) """
@@ -414,9 +535,7 @@ class MultiSemLaserScan():
       tsdf_vol = fl.TSDFVolume(vol_bnds, voxel_size=self.voxel_size, fov_up=self.fov_up, fov_down=self.fov_down)
       for i, scan in enumerate(self.scans):
         print("Fusing scan %d/%d" % (i + 1, self.nscans))
-        proj_label3 = np.zeros(scan.proj_color.shape)
-        proj_label3[:, :, 0] = scan.proj_label
-        tsdf_vol.integrate(proj_label3, scan.proj_range, scan.proj_remissions, np.eye(3), obs_weight=1.)
+        self._integrate(tsdf_vol, scan)
       return self._cast(tsdf_vol, self.scans[0].color_lut)
 
     elif adaption == 'mergemesh':  # all scans merged into ONE range image (source size, TARGET fov), then fused
@@ -430,9 +549,7 @@ class MultiSemLaserScan():
       vol_bnds[:, 1] = np.minimum(vol_bnds[:, 1], merged_bnds[:, 1])
       print("Initializing voxel volume...")
       tsdf_vol = fl.TSDFVolume(vol_bnds, voxel_size=self.voxel_size, fov_up=self.t_fov_up, fov_down=self.t_fov_down)
-      proj_label3 = np.zeros(m.proj_color.shape)
-      proj_label3[:, :, 0] = m.proj_label
-      tsdf_vol.integrate(proj_label3, m.proj_range, m.proj_remissions, np.eye(3), obs_weight=1.)
+      self._integrate(tsdf_vol, m)
       print("target dim:", self.t_H, self.t_W)
       verts, colors, faces = self._cast(tsdf_vol, m.color_lut)
       if self.write_ply:

@@ -152,7 +152,59 @@ k_reverse_project(const float* __restrict__ depth_im, const double* __restrict__
   back_points[3 * (size_t)i + 2] = depth * cos(pitch);
 }
 
+// SemLaserScan.get_bnds (laserscan.py: np.amin / np.amax of the points over axis 0) restricted to the points the
+// projection kept: one CTA, no atomics -- minima and maxima are exact whatever the order.  out[0..2] = min xyz,
+// out[3..5] = max xyz (+inf / -inf when no point is kept).
+__global__ void __launch_bounds__(1024)
+k_points_bounds(const double* __restrict__ pts, const uint8_t* __restrict__ keep, long n, double* __restrict__ out) {
+  __shared__ double s_lo[3][32], s_hi[3][32];
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (long i = threadIdx.x; i < n; i += 1024) {
+    if (keep && !keep[i]) continue;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double v = pts[3 * i + k];
+      lo[k] = v < lo[k] ? v : lo[k];     // np.amin / np.amax propagate NaN; points with NaN never survive the filters
+      hi[k] = v > hi[k] ? v : hi[k];
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+    if (lane == 0) { s_lo[k][w] = lo[k]; s_hi[k][w] = hi[k]; }
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double a = s_lo[k][lane], b = s_hi[k][lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a = fmin(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+      }
+      if (lane == 0) { out[k] = a; out[3 + k] = b; }
+    }
+  }
+}
+
 }  // namespace
+
+extern "C" int vl_points_bounds(const double* d_points, const uint8_t* d_keep, long n_points, double* d_bounds6,
+                                vl_stream stream_) {
+  if (n_points < 0 || !d_bounds6 || (n_points > 0 && !d_points)) {
+    vl_set_error("vl_points_bounds: invalid argument");
+    return VL_EINVAL;
+  }
+  k_points_bounds<<<1, 1024, 0, static_cast<cudaStream_t>(stream_)>>>(d_points, d_keep, n_points, d_bounds6);
+  VL_LAUNCH_CHECK("k_points_bounds");
+  return VL_OK;
+}
 
 extern "C" int vl_reverse_project(const float* d_depth_im, const double* d_proj_x, const double* d_proj_y, int H, int W,
                                   double fov_up_deg, double fov_down_deg, double* d_back_points, vl_stream stream_) {

@@ -222,7 +222,8 @@ def trace_bruteforce(verts, faces, colors, rem, rays, origin, height, out=None, 
   return out
 
 
-def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, workspace=None, beam_angles=None):
+def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, workspace=None, beam_angles=None,
+            want_bounds=False):
   """(iii) spherical range-image projection, the device equivalent of
   LaserScan.do_range_projection_new('depth') + do_label_projection_new
   (auxiliary/laserscan.py:294-391, 672-676).
@@ -230,7 +231,9 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, wor
   points f64[N,3], remissions f32[N], labels u32/i32[N].  Returns dict of CUDA tensors:
   range_image f32[H,W] (0 empty), index i32[H,W] (-1 empty, into the kept points),
   proj_label i32[H,W], proj_remissions f32[H,W] (-1 empty), keep bool[N], n_kept i32[1].
-  beam_angles (non-empty sequence): the pitch snapping of laserscan.py:321-327 (vl_project_snap)."""
+  beam_angles (non-empty sequence): the pitch snapping of laserscan.py:321-327 (vl_project_snap).
+  want_bounds: also `bounds` f64[6] = min xyz, max xyz of the kept points (SemLaserScan.get_bnds on the device,
+  vl_points_bounds); `bounds` and `n_kept` then share one 64-byte buffer `meta` (a single small D2H for both)."""
   require_cuda()
   points = _dev(points, torch.float64).reshape(-1)
   dev = points.device
@@ -242,7 +245,7 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, wor
     ba = _dev(ba_host, torch.float64, dev)
   n = points.numel() // 3
   remissions = _dev(remissions, torch.float32, dev).reshape(-1)
-  if torch.is_tensor(labels) and labels.dtype in (torch.int32, torch.uint32):
+  if torch.is_tensor(labels) and labels.dtype in (torch.int32, getattr(torch, "uint32", torch.int32)):
     labels = labels.to(dev).contiguous().view(torch.int32)
   else:
     labels = _dev(np.asarray(labels.cpu() if torch.is_tensor(labels) else labels).astype(np.uint32).view(np.int32),
@@ -257,14 +260,17 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, wor
              index=torch.empty((H, W), dtype=torch.int32, device=dev),
              proj_label=torch.empty((H, W), dtype=torch.int32, device=dev),
              proj_remissions=torch.empty((H, W), dtype=torch.float32, device=dev),
-             keep=torch.empty(max(n, 1), dtype=torch.uint8, device=dev),
-             n_kept=torch.zeros(1, dtype=torch.int32, device=dev))
+             keep=torch.empty(max(n, 1), dtype=torch.uint8, device=dev))
+  meta = torch.zeros(64, dtype=torch.uint8, device=dev)
+  out["meta"], out["bounds"], out["n_kept"] = meta, meta[:48].view(torch.float64), meta[48:52].view(torch.int32)
   with torch.cuda.device(dev):
     check(lib().vl_project_snap(_ptr(points), _ptr(remissions), _ptr(labels), n, float(fov_up), float(fov_down), H, W,
                                 1 if remove else 0, _ptr(ba) if ba is not None else None,
                                 ba.numel() if ba is not None else 0, _ptr(out["range_image"]), _ptr(out["index"]),
                                 _ptr(out["proj_label"]), _ptr(out["proj_remissions"]), _ptr(out["keep"]),
                                 _ptr(out["n_kept"]), _ptr(workspace), workspace.numel(), _stream()))
+    if want_bounds:
+      check(lib().vl_points_bounds(_ptr(points), _ptr(out["keep"]), n, _ptr(out["bounds"]), _stream()))
   out["keep"] = out["keep"][:n].bool()
   out["workspace"] = workspace
   return out
@@ -306,8 +312,49 @@ class TsdfDevice:
     n = self.dim[0] * self.dim[1] * self.dim[2]
     if n >= 2 ** 31:
       raise ValueError("volume of %d voxels exceeds the reference kernel's int voxel index" % n)
-    self._vols = tuple(torch.empty(self.dim, dtype=torch.float32, device=dev) for _ in range(4))
+    self._store = self._acquire(n, dev)
+    self._vols = tuple(f[:n].view(self.dim) for f in self._store["flat"])
     self.reset()
+
+  # The reference allocates (and uploads) four new volumes per TSDFVolume, i.e. per scan (laserscan.py:968,
+  # fusion_lidar.py:48-63).  Here the storage of a volume that has been dropped is kept for the next one of a similar
+  # size (bounds are clipped to each scan's points, so sizes differ slightly from scan to scan): no cudaMalloc / cudaFree
+  # -- and none of their device synchronisations -- in a batch.  At most _POOL_KEEP idle stores are kept.
+  _pool = []
+  _POOL_KEEP = 2
+
+  @classmethod
+  def _acquire(cls, n, dev):
+    best = None
+    for st in cls._pool:
+      if st["dev"] == dev and n <= st["cap"] <= max(2 * n, n + (1 << 24)) and (best is None or st["cap"] < best["cap"]):
+        best = st
+    if best is not None:
+      cls._pool.remove(best)
+      return best
+    cap = n + n // 16 + 1024    # a little head room for the next scan's slightly larger box
+    return dict(dev=dev, cap=cap, flat=tuple(torch.empty(cap, dtype=torch.float32, device=dev) for _ in range(4)), ws={})
+
+  def release(self):
+    """Hands the storage back for reuse; the volumes must not be used afterwards."""
+    st, self._store = getattr(self, "_store", None), None
+    if st is not None:
+      self._vols = None
+      TsdfDevice._pool.append(st)
+      while len(TsdfDevice._pool) > TsdfDevice._POOL_KEEP:
+        TsdfDevice._pool.pop(0)
+
+  def __del__(self):
+    try:
+      self.release()
+    except Exception:
+      pass
+
+  def _workspace(self, name, need, dev):
+    ws = self._store["ws"].get(name)
+    if ws is None or ws.numel() < need:
+      ws = self._store["ws"][name] = torch.empty(need, dtype=torch.uint8, device=dev)
+    return ws
 
   def reset(self):
     """Back to the initial state (tsdf 1, weight / colour / remission 0, fusion_lidar.py:48-63).  Lazy: the first
@@ -332,9 +379,7 @@ class TsdfDevice:
     use_column_table: vl_tsdf_integrate_ws (per-column pixel table, same bits) instead of vl_tsdf_integrate."""
     dev = self._vols[0].device
     fused = self._fresh and use_column_table   # first integration into a fresh volume: one pass
-    if fused:
-      self._fresh = False
-    else:
+    if not fused:
       self._materialise()
     color_im = _dev(color_im, torch.float32, dev)
     depth_im = _dev(depth_im, torch.float32, dev)
@@ -342,10 +387,8 @@ class TsdfDevice:
     im_h, im_w = depth_im.shape
     origin = (ctypes.c_float * 3)(*[float(v) for v in self.origin])
     if use_column_table:
-      ws = getattr(self, "_col_ws", None)
       need = lib().vl_tsdf_fresh_workspace_bytes(self.dim[0], self.dim[1], int(im_h), int(im_w))  # column table + shell image
-      if ws is None or ws.numel() < need:
-        ws = self._col_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+      ws = self._workspace("columns", need, dev)
     with torch.cuda.device(dev):
       if use_column_table:
         fn = lib().vl_tsdf_init_integrate if fused else lib().vl_tsdf_integrate_ws
@@ -353,6 +396,8 @@ class TsdfDevice:
                  self.dim[0], self.dim[1], self.dim[2], origin, self.voxel_size,
                  self.trunc_margin, float(np.float32(obs_weight)), self.fov_up, self.fov_down,
                  _ptr(color_im), _ptr(depth_im), _ptr(rem_im), int(im_h), int(im_w), _ptr(ws), ws.numel(), _stream()))
+        if fused:
+          self._fresh = False   # only once the fused reset + integration has been accepted: a failed call leaves the volume "fresh"
       else:
         check(lib().vl_tsdf_integrate(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color), _ptr(self.rem),
                                       self.dim[0], self.dim[1], self.dim[2], origin, self.voxel_size,
@@ -368,9 +413,7 @@ class TsdfDevice:
     dev = self.tsdf.device
     n = self.dim[0] * self.dim[1] * self.dim[2]
     need = lib().vl_mesh_workspace_bytes(self.dim[0], self.dim[1], self.dim[2])
-    ws = getattr(self, "_mesh_ws", None)
-    if ws is None or ws.numel() < need:
-      ws = self._mesh_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    ws = self._workspace("mesh", need, dev)
     totals = torch.zeros(2, dtype=torch.int64, device=dev)
     origin = (ctypes.c_float * 3)(*[float(v) for v in self.origin])
     with torch.cuda.device(dev):

@@ -1,2 +1,2 @@
-python -m pytest tests/test_reference_driver_gpu.py -m gpu -q -rs -s > gpurun_out/drv.log 2>&1
-grep -n "passed\|failed\|^FAILED\|scan [0-9]: voxels\|SKIP\|Error\|integrations\|^E  " gpurun_out/drv.log | cut -c1-400 | head -60
+python tools/deform_timing.py 4 2>&1 | tail -45
+python -m pytest tests/test_dropin_gpu.py tests/test_reference_driver_gpu.py tests/test_project_tsdf_gpu.py tests/test_chain_gpu.py -m gpu -q -x 2>&1 | tail -5
