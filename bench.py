@@ -25,6 +25,8 @@ e2e_deform    = N=1: MultiSemLaserScan.open_multiple_scans + deform('mergemesh')
 roofline      = dominant kernel of the step (largest share of device time, CUDA events on the launching stream):
                 COMPULSORY bytes (inputs once + outputs once) / mean launch duration vs MEASURED_PEAKS.json, with the
                 issue-slot fraction (the binding limit of this path) beside it.
+pipeline_sharded = BASELINE configs[4] as the real pipeline: a 1000-scan manifest sharded over the ranks, points in,
+                results out, the mesh born on the device (scans/s at N GPUs; strong scaling of a fixed manifest).
 pipeline_c1 / pipeline_c4 = the whole chain (project -> TSDF -> mesh -> cast) at BASELINE.json configs[0] / [3] size.
 cpu_baseline / --impl reference = the reference's own C++ ray tracer (oracle/_ref, compiled from the
                 reference sources with its shipped flags) on the same meshes, all host threads.
@@ -289,6 +291,61 @@ def pipelines(L, dev):
   return c1, c4
 
 
+def sharded_pipeline_leg(rank, world, dev, n_manifest, barrier, reduce_max):
+  """BASELINE.json configs[4] as the REAL pipeline: a manifest of n_manifest scans sharded round-robin over the ranks
+  (sharding.scans_for_rank), every scan through points (pinned host, 2.9 MB + 1 MB up) -> range image -> 284 M-voxel TSDF
+  -> mesh -> 64x2048 cast -> results (4.2 MB packed, down to pinned host memory), no collective.  The mesh is born on
+  the device, so a scan moves 4 MB up instead of the 27 MB of the host-mesh interface.  Returns (scans, max-over-ranks ms)."""
+  import torch
+  from lidar_transfer_b200 import engine, sharding, synth
+  from lidar_transfer_b200.rays import create_rays
+  mine = sharding.scans_for_rank(n_manifest, rank, world)
+  P = 4   # distinct point clouds per rank, cycled (scan k uses cloud k mod P)
+  clouds = []
+  for k in range(P):
+    real = _fixture_scan(k % 3) if k < 3 else None
+    pts, lab = real if real is not None else synth.make_scan_points(100 + rank * P + k, 124668)
+    clouds.append((torch.from_numpy(pts[:, :3].astype(np.float64)).pin_memory(), torch.from_numpy(pts[:, 3].copy()).pin_memory(),
+                   torch.from_numpy(lab.view(np.int32).copy()).pin_memory()))
+  bnds = np.array([[-50, 50], [-31, 40], [-3, 2]], np.float64)
+  dim = np.ceil((bnds[:, 1] - bnds[:, 0]) / 0.05).astype(int)
+  beams = engine.Beams(create_rays(FOV_UP, FOV_DOWN, H, W), H)
+  origin = torch.zeros(3, device=dev)
+  vol = engine.TsdfDevice(dim, bnds[:, 0].astype(np.float32), 0.05, FOV_UP, FOV_DOWN)
+  R = H * W
+  packed = torch.empty(32 * R, dtype=torch.uint8, device=dev)
+  outs = dict(endpoints=packed[:12 * R].view(torch.float32), endcolors=packed[12 * R:24 * R].view(torch.int32),
+              range=packed[24 * R:28 * R].view(torch.float32), endrem=packed[28 * R:32 * R].view(torch.float32))
+  h_out = [torch.empty(32 * R, dtype=torch.uint8).pin_memory() for _ in range(2)]
+  ws = None
+  hits = 0.0
+
+  def one(k):
+    nonlocal ws
+    p64, rem, lab = (t.to(dev, non_blocking=True) for t in clouds[k % P])
+    pr = engine.project(p64, rem, lab, FOV_UP, FOV_DOWN, H, W, workspace=ws)
+    ws = pr["workspace"]
+    vol.reset()
+    vol.integrate(pr["proj_label"].to(torch.float32) * 65536.0, pr["range_image"], pr["proj_remissions"])
+    m = vol.extract_mesh(want_norms=False)
+    engine.cast(beams, m["verts"], m["faces"], m["colors"].to(torch.int32), m["rem"], origin, out=outs, want_ids=False,
+                zero_misses=True, check_mesh=False)
+    h_out[k & 1].copy_(packed, non_blocking=True)
+  for k in range(3):
+    one(k)
+  barrier()
+  t0 = time.perf_counter()
+  for k in mine:
+    one(k)
+  torch.cuda.synchronize()
+  ms = 1e3 * (time.perf_counter() - t0)
+  hits = float((h_out[(mine[-1]) & 1][24 * R:28 * R].view(torch.float32) > 0).float().mean()) if mine else 0.0
+  barrier()
+  up = sum(t.numel() * t.element_size() for t in clouds[0])
+  return {"scans": n_manifest, "ms": reduce_max(ms), "h2d_bytes_per_scan": up, "d2h_bytes_per_scan": 32 * R, "hit_fraction": hits,
+          "scans_this_rank": len(mine)}
+
+
 def deform_leg(n_scans=3, reps=2):
   """The reference-shaped per-scan call the driver makes (lidar_deform.py:396-415): open_multiple_scans +
   deform('mergemesh') on the real fixture at config-1 size, files on disk -> numpy attributes.  Wall ms per scan."""
@@ -503,6 +560,13 @@ def run_native(args):
   rr.wait()
   hit_frac = float((rr.slots[(S - 1) % len(rr.slots)].out["tri_id"] >= 0).float().mean().item())
 
+  sharded = None
+  if not args.no_pipeline:   # every rank takes part: the 1000-scan manifest of BASELINE.json configs[4], real pipeline
+    del rr2
+    rr.close()
+    torch.cuda.empty_cache()
+    sharded = sharded_pipeline_leg(rank, world, dev, args.manifest_scans, barrier, reduce_max)
+
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
@@ -549,7 +613,6 @@ def run_native(args):
 
   pipe_c1 = pipe_c4 = deform = None
   if world == 1 and not args.no_pipeline:
-    del rr2
     torch.cuda.empty_cache()
     pipe_c1, pipe_c4 = pipelines(L, dev)
     torch.cuda.empty_cache()
@@ -594,6 +657,14 @@ def run_native(args):
                         "api": "ScanRenderer.submit_host (pinned host mesh -> H2D -> %s -> D2H of 5 outputs), %d streams"
                                % ("vl_cast" if args.method == "cast" else "vl_bvh_build -> vl_trace", args.streams)},
       "e2e_deform": deform,
+      "pipeline_sharded": None if sharded is None else {
+          "workload": "BASELINE configs[4] as the real pipeline: %d scans sharded round-robin over %d GPU(s), each: points "
+                      "(pinned host) -> 64x2048 image -> 284 M-voxel TSDF -> mesh -> 64x2048 cast -> results to pinned host; "
+                      "no collective" % (sharded["scans"], world),
+          "scans_per_s": sharded["scans"] / (sharded["ms"] * 1e-3), "value": sharded["scans"] * R / (sharded["ms"] * 1e-3) / 1e6,
+          "unit": "Mrays/s", "ms_total": sharded["ms"], "ms_per_scan_per_gpu": sharded["ms"] / max(1, sharded["scans_this_rank"]),
+          "h2d_bytes_per_scan": sharded["h2d_bytes_per_scan"], "d2h_bytes_per_scan": sharded["d2h_bytes_per_scan"],
+          "scaling": "strong (fixed manifest)", "hit_fraction": sharded["hit_fraction"]},
       "gpu_launches": int(launches),
       "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                    "frac": achieved / peak, "traffic": cap.get("dram_bytes_per_launch"), "peak_source": peak_src,
@@ -631,7 +702,8 @@ def main():
   ap.add_argument("--method", default="cast", choices=["cast", "lbvh"])
   ap.add_argument("--cpu-scans", type=int, default=8, help="scans timed for cpu_baseline (about 1.2 s each)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
-  ap.add_argument("--no-pipeline", action="store_true", help="skip the config-1 / config-4 chains and the deform leg")
+  ap.add_argument("--no-pipeline", action="store_true", help="skip the config-1 / config-4 chains, the deform leg and the sharded pipeline")
+  ap.add_argument("--manifest-scans", type=int, default=1000, help="scans of the sharded real-pipeline leg (all ranks together)")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
   if args.impl == "reference":

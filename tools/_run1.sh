@@ -1,2 +1,3 @@
-python tools/deform_timing.py 4 2>&1 | tail -45
-python -m pytest tests/test_dropin_gpu.py tests/test_reference_driver_gpu.py tests/test_project_tsdf_gpu.py tests/test_chain_gpu.py -m gpu -q -x 2>&1 | tail -5
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline --scans-per-step 256 --manifest-scans 200 > gpurun_out/bench_r02_c.json 2> gpurun_out/bench_r02_c.err; echo rc=$?; tail -5 gpurun_out/bench_r02_c.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_r02_c.json')); print(d['pipeline_sharded']); print(d['e2e_deform']); print(d['value'], d['e2e']['value'])"
