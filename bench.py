@@ -261,8 +261,7 @@ def pipeline_chain(L, dev, scans, src_fov, bnds, vox, target, reps=3):
       ws = pr["workspace"]
       vol.integrate(pr["proj_label"].to(torch.float32) * 65536.0, pr["range_image"], pr["proj_remissions"])
     m = vol.extract_mesh(want_norms=False)
-    out = engine.cast(beams, m["verts"], m["faces"], m["colors"].to(torch.int32), m["rem"], origin, zero_misses=True,
-                      check_mesh=False)
+    out = engine.cast(beams, m["verts"], m["faces"], m["colors"], m["rem"], origin, zero_misses=True, check_mesh=False)
     e1.record()
     torch.cuda.synchronize()
     wall = e0.elapsed_time(e1)
@@ -328,8 +327,8 @@ def sharded_pipeline_leg(rank, world, dev, n_manifest, barrier, reduce_max):
     vol.reset()
     vol.integrate(pr["proj_label"].to(torch.float32) * 65536.0, pr["range_image"], pr["proj_remissions"])
     m = vol.extract_mesh(want_norms=False)
-    engine.cast(beams, m["verts"], m["faces"], m["colors"].to(torch.int32), m["rem"], origin, out=outs, want_ids=False,
-                zero_misses=True, check_mesh=False)
+    engine.cast(beams, m["verts"], m["faces"], m["colors"], m["rem"], origin, out=outs, want_ids=False, zero_misses=True,
+                check_mesh=False)
     h_out[k & 1].copy_(packed, non_blocking=True)
   for k in range(3):
     one(k)

@@ -111,6 +111,7 @@ int vl_bvh_status(const void* d_blob, int n_faces, vl_stream stream, int* info);
 #define VL_TRACE_ZERO_MISSES 1
 #define VL_TRACE_PACKET      2   /* warp-packet traversal (8x4 beam tiles share one stack) instead of per-ray stacks */
 #define VL_RAYS_NORMALIZED   4   /* d_rays hold unit directions already (vl_normalize_rays): used as given, not re-normalised */
+#define VL_COLORS_U8         8   /* vl_cast only: d_colors is uint8[3*n_verts] (what vl_mesh_emit writes) instead of int32[3*n_verts] */
 int vl_trace(const void* d_blob, int n_faces, const float* d_rays, const float* d_origin,
              int n_rays, int height, float* d_endpoints, int* d_endcolors, float* d_range,
              float* d_endrem, int* d_tri_id, int flags, vl_stream stream);
@@ -273,6 +274,28 @@ int vl_tsdf_init_integrate(float* d_tsdf, float* d_weight, float* d_color, float
 size_t vl_tsdf_fresh_workspace_bytes(int dx, int dy, int im_h, int im_w);
 void vl_debug_tsdf_shell(int mode);
 
+/* SPARSE (blocked) volumes -- the reference's own TODO, auxiliary/fusion_lidar.py:45 ("larger voxel volume ... by
+ * splitting"), instead of its four dense arrays initialised per scan (:48-63).  d_hull i32[dx*dy] holds, per z column,
+ * the interval [z_lo, z_hi] of voxels that are materialised in the four arrays (z_lo | z_hi << 16; 1 | 0 << 16 = none);
+ * a voxel outside its column's hull is in the initial state by definition (tsdf 1, weight / colour / remission 0) and
+ * its memory is never read or written.  vl_tsdf_sparse_integrate: the integration of vl_tsdf_integrate into such a
+ * volume -- fresh != 0: a NEW volume (the arrays' and d_hull's previous content is ignored: no reset pass at all);
+ * the hull of a column grows to cover every voxel the reference kernel could change (a conservative interval derived
+ * from the range image), voxels entering a hull are written (initial or integrated value), voxels already in it are
+ * integrated like a later scan, nothing else is touched.  Same values as the dense calls for every voxel, bit for bit
+ * (vl_tsdf_densify materialises the rest: afterwards the arrays are the dense volumes and every hull is the whole
+ * column).  Outside the sweep's limits (see vl_tsdf_fresh_workspace_bytes; also dz <= 32767, fov_up >= 0 >= fov_down)
+ * the call densifies and takes the dense path.  vl_mesh_count_sparse / vl_mesh_emit_sparse read sparse volumes. */
+size_t vl_tsdf_sparse_workspace_bytes(int dx, int dy, int im_h, int im_w);
+int vl_tsdf_sparse_integrate(float* d_tsdf, float* d_weight, float* d_color, float* d_rem,
+                             int dx, int dy, int dz, const float vol_origin[3], float voxel_size,
+                             float trunc_margin, float obs_weight, float fov_up_deg, float fov_down_deg,
+                             const float* d_color_im, const float* d_depth_im, const float* d_rem_im,
+                             int im_h, int im_w, int* d_hull, int fresh, void* d_workspace, size_t workspace_bytes,
+                             vl_stream stream);
+int vl_tsdf_densify(float* d_tsdf, float* d_weight, float* d_color, float* d_rem, int dx, int dy, int dz,
+                    int* d_hull, vl_stream stream);
+
 /* ------------------------------------------------------------------------------------
  * (v) iso-surface extraction + per-vertex label / remission lookup ("next" row N1).
  *
@@ -298,6 +321,18 @@ int vl_mesh_emit(const float* d_tsdf, const float* d_color, const float* d_rem, 
                  size_t workspace_bytes, long long n_tris, long long n_active, void* d_active_list,
                  float* d_verts, int* d_faces, float* d_norms, unsigned char* d_colors, float* d_rem_out,
                  vl_stream stream);
+
+/* The same on a SPARSE volume (vl_tsdf_sparse_integrate): d_hull i32[dx*dy] as there; voxels outside their column's hull
+ * count as the initial values (tsdf 1, colour / remission 0) and are not read.  Same mesh, bit for bit and in the same
+ * order, as vl_tsdf_densify + vl_mesh_count / vl_mesh_emit; the cube sweeps skip the empty part of the volume.
+ * Needs level <= 1 and dz < 1984. */
+int vl_mesh_count_sparse(const float* d_tsdf, int dx, int dy, int dz, float level, const int* d_hull,
+                         void* d_workspace, size_t workspace_bytes, long long* d_totals, vl_stream stream);
+int vl_mesh_emit_sparse(const float* d_tsdf, const float* d_color, const float* d_rem, int dx, int dy, int dz,
+                        float level, float voxel_size, const float vol_origin[3], const int* d_hull,
+                        const void* d_workspace, size_t workspace_bytes, long long n_tris, long long n_active,
+                        void* d_active_list, float* d_verts, int* d_faces, float* d_norms, unsigned char* d_colors,
+                        float* d_rem_out, vl_stream stream);
 
 /* ------------------------------------------------------------------------------------
  * (vi) identity re-render metrics on the device ("next" row N3).

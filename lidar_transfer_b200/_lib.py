@@ -64,6 +64,11 @@ SIGNATURES = {
     "vl_debug_tsdf_shell": (None, [_i]),
     "vl_tsdf_integrate_ws": (_i, [_vp] * 4 + [_i, _i, _i, _vp] + [_f] * 5 + [_vp] * 3 + [_i, _i, _vp, _sz, _vp]),
     "vl_tsdf_init_integrate": (_i, [_vp] * 4 + [_i, _i, _i, _vp] + [_f] * 5 + [_vp] * 3 + [_i, _i, _vp, _sz, _vp]),
+    "vl_tsdf_sparse_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "vl_tsdf_sparse_integrate": (_i, [_vp] * 4 + [_i, _i, _i, _vp] + [_f] * 5 + [_vp] * 3 + [_i, _i, _vp, _i, _vp, _sz, _vp]),
+    "vl_tsdf_densify": (_i, [_vp] * 4 + [_i, _i, _i, _vp, _vp]),
+    "vl_mesh_count_sparse": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _sz, _vp, _vp]),
+    "vl_mesh_emit_sparse": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _sz, _ll, _ll, _vp] + [_vp] * 5 + [_vp]),
     "vl_mesh_workspace_bytes": (_sz, [_i, _i, _i]),
     "vl_mesh_list_bytes": (_sz, [_ll, _ll]),
     "vl_mesh_count": (_i, [_vp, _i, _i, _i, _f, _vp, _sz, _vp, _vp]),

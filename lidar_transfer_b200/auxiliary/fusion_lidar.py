@@ -129,7 +129,7 @@ class TSDFVolume(object):
 
   def throw_rays_at_mesh_device(self, rays, origin, H, W):
     m = self.get_mesh_device()
-    colors = m["colors"].to(torch.int32)  # colors.astype(np.int32), :437
+    colors = m["colors"]   # uint8, read as it is by the cast (the reference converts: colors.astype(np.int32), :437)
     dev = m["verts"].device
     R = int(np.asarray(rays).size // 3) if not torch.is_tensor(rays) else rays.numel() // 3
     # the four per-ray outputs as views of ONE buffer (a single device -> host copy for the caller)
@@ -148,7 +148,7 @@ class TSDFVolume(object):
     except _lib.VlidarError as e:
       if e.code != _lib.VL_ENOSPACE:
         raise
-      bvh = engine.Bvh(m["verts"], m["faces"], colors, m["rem"])
+      bvh = engine.Bvh(m["verts"], m["faces"], colors.to(torch.int32), m["rem"])
       out = engine.trace(bvh, rays, origin, H, out=outs, want_ids=False, zero_misses=True)
     return out, m
 

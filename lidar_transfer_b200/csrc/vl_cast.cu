@@ -682,7 +682,8 @@ __global__ void __launch_bounds__(kCastThreads)
 k_cast_resolve(const unsigned long long* __restrict__ best, int n, const float4* __restrict__ dir,
                const int* __restrict__ slot_of, const float* __restrict__ origin, const VlMeshDesc mesh_val,
                const VlMeshDesc* __restrict__ mesh_ptr, float* __restrict__ endpoints, int* __restrict__ endcolors,
-               float* __restrict__ range, float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses) {
+               float* __restrict__ range, float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses,
+               bool colors_u8) {
   const int r = blockIdx.x * kCastThreads + threadIdx.x;
   if (r >= n) return;
   const int* __restrict__ faces = kDescPtr ? mesh_ptr->faces : mesh_val.faces;
@@ -700,9 +701,16 @@ k_cast_resolve(const unsigned long long* __restrict__ best, int n, const float4*
     endpoints[3 * (size_t)r + 1] = __fadd_rn(o.y, __fmul_rn(d.y, t));
     endpoints[3 * (size_t)r + 2] = __fadd_rn(o.z, __fmul_rn(d.z, t));
     // RayTracer.cpp:36-48 colours pass through float; Triangle.h:53-56 colour of vertex 0
-    endcolors[3 * (size_t)r + 0] = (int)(float)__ldg(colors + 3 * (size_t)i0);
-    endcolors[3 * (size_t)r + 1] = (int)(float)__ldg(colors + 3 * (size_t)i0 + 1);
-    endcolors[3 * (size_t)r + 2] = (int)(float)__ldg(colors + 3 * (size_t)i0 + 2);
+    if (colors_u8) {   // VL_COLORS_U8: the mesh extraction's uint8 colours as they are (colors.astype(np.int32), fusion_lidar.py:437)
+      const unsigned char* c8 = reinterpret_cast<const unsigned char*>(colors) + 3 * (size_t)i0;
+      endcolors[3 * (size_t)r + 0] = (int)__ldg(c8);
+      endcolors[3 * (size_t)r + 1] = (int)__ldg(c8 + 1);
+      endcolors[3 * (size_t)r + 2] = (int)__ldg(c8 + 2);
+    } else {
+      endcolors[3 * (size_t)r + 0] = (int)(float)__ldg(colors + 3 * (size_t)i0);
+      endcolors[3 * (size_t)r + 1] = (int)(float)__ldg(colors + 3 * (size_t)i0 + 1);
+      endcolors[3 * (size_t)r + 2] = (int)(float)__ldg(colors + 3 * (size_t)i0 + 2);
+    }
     endrem[r] = __fdiv_rn(__fadd_rn(__fadd_rn(__ldg(rem + i0), __ldg(rem + i1)), __ldg(rem + i2)), 3.0f);   // Triangle.h:63-70
     range[r] = t;
     if (tri_id) tri_id[r] = f;
@@ -830,13 +838,13 @@ static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr
   {
     VlProfScope ps(VL_ST_CAST_RESOLVE, stream);
     const int nb = (L.n + kCastThreads - 1) / kCastThreads;
-    const bool zm = (flags & VL_TRACE_ZERO_MISSES) != 0;
+    const bool zm = (flags & VL_TRACE_ZERO_MISSES) != 0, c8 = (flags & VL_COLORS_U8) != 0;
     if (by_ptr)
       k_cast_resolve<true><<<nb, kCastThreads, 0, stream>>>(best, L.n, dir, slot_of, d_origin, mesh, d_desc, d_endpoints,
-                                                           d_endcolors, d_range, d_endrem, d_tri_id, zm);
+                                                           d_endcolors, d_range, d_endrem, d_tri_id, zm, c8);
     else
       k_cast_resolve<false><<<nb, kCastThreads, 0, stream>>>(best, L.n, dir, slot_of, d_origin, mesh, d_desc, d_endpoints,
-                                                            d_endcolors, d_range, d_endrem, d_tri_id, zm);
+                                                            d_endcolors, d_range, d_endrem, d_tri_id, zm, c8);
     VL_LAUNCH_CHECK("k_cast_resolve");
   }
   return VL_OK;

@@ -330,16 +330,87 @@ k_mesh_bits(const float* __restrict__ tsdf, const MeshParams P, int pw, unsigned
   }
 }
 
+// k_mesh_bits over a SPARSE volume (vl_tsdf_sparse_integrate): hull[column] = [z_lo, z_hi] is the interval of the
+// column's voxels that exist; every other voxel holds the initial value 1 by definition -- its bit is (1 < level) = 0
+// (level <= 1, checked by the caller), and its memory is not read.  The bit volume and the per-unit flags are zeroed
+// first; a CTA owns 256 consecutive z columns and ENUMERATES the groups of kVec z-consecutive voxels inside their hulls
+// (block scan of the per-column counts, bisection in shared memory), so that every lane loads a group that exists; a
+// group's bits are OR-ed into its word, and the unit of 64 words it belongs to is flagged (unit_any) so that the cube
+// sweeps skip the empty part of the volume.
+template <int kVec>
+__global__ void __launch_bounds__(kThreads)
+k_mesh_bits_sparse(const float* __restrict__ tsdf, const MeshParams P, int pw, const int* __restrict__ hull,
+                   unsigned int* __restrict__ bits, int units_per_plane, int* __restrict__ unit_any) {
+  __shared__ int s_off[kThreads + 1];
+  __shared__ int s_hull[kThreads];
+  __shared__ int s_warp[kWarps];
+  const int n_cols = P.dx * P.dy;
+  const int c0 = blockIdx.x * kThreads;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int ng = 0;
+  {
+    const int c = c0 + threadIdx.x;
+    const int h = c < n_cols ? __ldg(hull + c) : 1;
+    s_hull[threadIdx.x] = h;
+    const int lo = h & 0xffff, hi = (h >> 16) & 0xffff;
+    if (lo <= hi) ng = hi / kVec - lo / kVec + 1;
+  }
+  int incl = ng;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  int wbase = 0;
+#pragma unroll
+  for (int k = 0; k < kWarps; ++k) wbase += k < w ? s_warp[k] : 0;
+  s_off[threadIdx.x] = wbase + incl - ng;
+  if (threadIdx.x == kThreads - 1) s_off[kThreads] = wbase + incl;
+  __syncthreads();
+  const int total = s_off[kThreads];
+  const float L = P.level;
+  for (int i = threadIdx.x; i < total; i += kThreads) {
+    int j = 0;
+#pragma unroll
+    for (int step = kThreads / 2; step > 0; step >>= 1) if (s_off[j + step] <= i) j += step;
+    const int h = s_hull[j];
+    const int lo = h & 0xffff, hi = (h >> 16) & 0xffff;
+    const int c = c0 + j;
+    const int x = c / P.dy, y = c - x * P.dy;
+    const int z = (lo / kVec + (i - s_off[j])) * kVec;
+    const float* p = tsdf + (size_t)c * P.dz + z;
+    unsigned int n;
+    if (kVec == 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+      n = ((v.x < L && z >= lo && z <= hi) ? 1u : 0u) | ((v.y < L && z + 1 >= lo && z + 1 <= hi) ? 2u : 0u) |
+          ((v.z < L && z + 2 >= lo && z + 2 <= hi) ? 4u : 0u) | ((v.w < L && z + 3 >= lo && z + 3 <= hi) ? 8u : 0u);
+    } else {
+      n = __ldg(p) < L ? 1u : 0u;
+    }
+    if (n) {
+      const int bit = y * P.dz + z;                           // kVec 4: dz % 4 == 0, the nibble lies inside one word
+      const int wd = bit >> 5;
+      atomicOr(bits + (size_t)x * pw + wd, n << (bit & 31));
+      unit_any[x * units_per_plane + (wd >> 6)] = 1;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_mesh_count_bits(const unsigned int* __restrict__ bits, const MeshParams P, int pw, int units_per_plane,
-                  int* __restrict__ unit_tris, int* __restrict__ unit_active) {
+                  int* __restrict__ unit_tris, int* __restrict__ unit_active, const int* __restrict__ unit_any) {
   static_assert(kUnit == 2048, "a lane holds two 32-cube words of its warp's unit");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int u = blockIdx.x * kWarps + wid;
   if (u >= units_per_plane) return;  // warp-uniform
   const int x = blockIdx.y;
   int n_tris = 0, n_active = 0;
-  if (x + 1 < P.dx) {
+  bool skip = false;
+  if (unit_any && x + 1 < P.dx) {   // sparse volume: a cube of unit u reads bits of units u, u + 1 of planes x, x + 1 (dz + 1 < 2048)
+    const int* a0 = unit_any + x * units_per_plane, *a1 = a0 + units_per_plane;
+    const int un = min(u + 1, units_per_plane - 1);
+    skip = !(a0[u] | a0[un] | a1[u] | a1[un]);
+  }
+  if (x + 1 < P.dx && !skip) {
     const unsigned int* p0 = bits + (size_t)x * pw;
     CubeWords cw[2];
     int excl, total;
@@ -544,7 +615,7 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
             const MeshParams P, const uint2* __restrict__ list, long long n_active,
             const unsigned int* __restrict__ cta_first, long long n_tris, float* __restrict__ verts,
             int* __restrict__ faces, float* __restrict__ norms, unsigned char* __restrict__ colors,
-            float* __restrict__ rem_out, int vec_ok) {
+            float* __restrict__ rem_out, int vec_ok, const int* __restrict__ hull) {
   __shared__ unsigned int s_first[kEmitTris], s_vi[kEmitTris];
   __shared__ __align__(16) float s_v[kEmitTris * 9];
   __shared__ float s_r[kEmitTris * 3];
@@ -572,9 +643,16 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
     const float* cube0 = tsdf + vi;
     float v[8];
     int mc = 0;   // case index: bit c set when corner c (bit 0 x, bit 1 y, bit 2 z) is below the level
+    int hc[4] = {0x7fff0000, 0x7fff0000, 0x7fff0000, 0x7fff0000};   // sparse volume: hulls of the cube's four z columns
+    if (hull) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) hc[c] = __ldg(hull + (size_t)(x + (c & 1)) * P.dy + y + ((c >> 1) & 1));
+    }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      v[c] = __ldg(cube0 + (size_t)(c & 1) * yz + ((c >> 1) & 1) * P.dz + ((c >> 2) & 1));
+      const int zc = z + ((c >> 2) & 1);
+      const bool exists = zc >= (hc[c & 3] & 0xffff) && zc <= ((hc[c & 3] >> 16) & 0xffff);
+      v[c] = exists ? __ldg(cube0 + (size_t)(c & 1) * yz + ((c >> 1) & 1) * P.dz + ((c >> 2) & 1)) : 1.f;   // outside a hull: the initial value
       mc |= v[c] < P.level ? (1 << c) : 0;
     }
     float pw[3][3];
@@ -597,7 +675,12 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
       const int iy = min(max(__float2int_rn(pv[1]), 0), P.dy - 1);
       const int iz = min(max(__float2int_rn(pv[2]), 0), P.dz - 1);
       const long long ni = ((long long)ix * P.dy + iy) * P.dz + iz;
-      const float rgb = __ldg(color_vol + ni);
+      bool exists = true;
+      if (hull) {
+        const int hn = __ldg(hull + (size_t)ix * P.dy + iy);
+        exists = iz >= (hn & 0xffff) && iz <= ((hn >> 16) & 0xffff);
+      }
+      const float rgb = exists ? __ldg(color_vol + ni) : 0.f;
       // fusion_lidar.py:417-423 (float32 arithmetic, then astype(uint8) wraps modulo 256)
       const float cb_ = floorf(__fdiv_rn(rgb, 65536.0f));
       const float cg_ = floorf(__fdiv_rn(__fsub_rn(rgb, __fmul_rn(cb_, 65536.0f)), 256.0f));
@@ -606,7 +689,7 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
       s_c[3 * vtx + 0] = (unsigned char)((long long)floorf(cr_) & 255);
       s_c[3 * vtx + 1] = (unsigned char)((long long)floorf(cg_) & 255);
       s_c[3 * vtx + 2] = (unsigned char)((long long)floorf(cb_) & 255);
-      s_r[vtx] = __ldg(rem_vol + ni);
+      s_r[vtx] = exists ? __ldg(rem_vol + ni) : 0.f;
       // :412 verts * voxel_size + origin
       pw[k][0] = __fadd_rn(__fmul_rn(pv[0], P.voxel_size), P.ox);
       pw[k][1] = __fadd_rn(__fmul_rn(pv[1], P.voxel_size), P.oy);
@@ -709,12 +792,16 @@ static int mesh_args(const char* who, const float* d_tsdf, int dx, int dy, int d
   return VL_OK;
 }
 
-extern "C" int vl_mesh_count(const float* d_tsdf, int dx, int dy, int dz, float level, void* d_workspace,
-                             size_t workspace_bytes, long long* d_totals, vl_stream stream_) {
+static int mesh_count_impl(const float* d_tsdf, int dx, int dy, int dz, float level, const int* d_hull, void* d_workspace,
+                           size_t workspace_bytes, long long* d_totals, vl_stream stream_) {
   MeshParams P;
   int rc = mesh_args("vl_mesh_count", d_tsdf, dx, dy, dz, d_workspace, workspace_bytes, &P, level, 1.f, nullptr);
   if (rc) return rc;
   if (!d_totals) { vl_set_error("vl_mesh_count: null d_totals"); return VL_EINVAL; }
+  if (d_hull && (!(level <= 1.f) || g_mesh_mode >= 2 || dz + 64 > kUnit)) {
+    vl_set_error("vl_mesh_count_sparse: needs level <= 1 (the value of a voxel outside its hull), dz < %d and the bit-volume sweep", kUnit - 64);
+    return VL_EINVAL;
+  }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int upp = mesh_units_per_plane(dy, dz);
   const MeshWs w = mesh_ws_layout(dx, dy, dz);
@@ -725,13 +812,22 @@ extern "C" int vl_mesh_count(const float* d_tsdf, int dx, int dy, int dz, float 
     const int pw = mesh_plane_words(dy, dz);
     unsigned int* bits = reinterpret_cast<unsigned int*>(ws + w.bits);
     const dim3 bgrid((pw + 128 * kWarps - 1) / (128 * kWarps), dx);
-    if (g_mesh_mode == 0 && ((long long)dy * dz) % 4 == 0 && ((uintptr_t)d_tsdf & 15) == 0)
+    int* unit_any = d_hull ? reinterpret_cast<int*>(ws + w.tri_off) : nullptr;   // free until the scan writes the offsets
+    if (d_hull) {
+      VL_CUDA_CHECK(cudaMemsetAsync(bits, 0, 4 * (size_t)dx * pw, stream));
+      VL_CUDA_CHECK(cudaMemsetAsync(unit_any, 0, 4 * (size_t)dx * upp, stream));
+      const int hgrid = (dx * dy + kThreads - 1) / kThreads;
+      if (g_mesh_mode == 0 && dz % 4 == 0 && ((uintptr_t)d_tsdf & 15) == 0)
+        k_mesh_bits_sparse<4><<<hgrid, kThreads, 0, stream>>>(d_tsdf, P, pw, d_hull, bits, upp, unit_any);
+      else
+        k_mesh_bits_sparse<1><<<hgrid, kThreads, 0, stream>>>(d_tsdf, P, pw, d_hull, bits, upp, unit_any);
+    } else if (g_mesh_mode == 0 && ((long long)dy * dz) % 4 == 0 && ((uintptr_t)d_tsdf & 15) == 0)
       k_mesh_bits<4><<<bgrid, kThreads, 0, stream>>>(d_tsdf, P, pw, bits);
     else
       k_mesh_bits<1><<<bgrid, kThreads, 0, stream>>>(d_tsdf, P, pw, bits);
     VL_LAUNCH_CHECK("k_mesh_bits");
     k_mesh_count_bits<<<grid, kThreads, 0, stream>>>(bits, P, pw, upp, reinterpret_cast<int*>(ws + w.tris),
-                                                    reinterpret_cast<int*>(ws + w.active));
+                                                    reinterpret_cast<int*>(ws + w.active), unit_any);
   } else {
   const bool vec4 = g_mesh_mode != 3 && dz % 4 == 0 && ((uintptr_t)d_tsdf & 15) == 0;   // cases start 256-byte aligned
   if (vec4)
@@ -761,16 +857,27 @@ extern "C" int vl_mesh_count(const float* d_tsdf, int dx, int dy, int dz, float 
   return VL_OK;
 }
 
+extern "C" int vl_mesh_count(const float* d_tsdf, int dx, int dy, int dz, float level, void* d_workspace,
+                             size_t workspace_bytes, long long* d_totals, vl_stream stream) {
+  return mesh_count_impl(d_tsdf, dx, dy, dz, level, nullptr, d_workspace, workspace_bytes, d_totals, stream);
+}
+
+extern "C" int vl_mesh_count_sparse(const float* d_tsdf, int dx, int dy, int dz, float level, const int* d_hull,
+                                    void* d_workspace, size_t workspace_bytes, long long* d_totals, vl_stream stream) {
+  if (!d_hull) { vl_set_error("vl_mesh_count_sparse: null d_hull"); return VL_EINVAL; }
+  return mesh_count_impl(d_tsdf, dx, dy, dz, level, d_hull, d_workspace, workspace_bytes, d_totals, stream);
+}
+
 extern "C" size_t vl_mesh_list_bytes(long long n_tris, long long n_active) {
   if (n_tris < 0 || n_active < 0) return 256;
   return vl_align256(8 * (size_t)n_active) + vl_align256(4 * (size_t)((n_tris + kEmitTris - 1) / kEmitTris + 1));
 }
 
-extern "C" int vl_mesh_emit(const float* d_tsdf, const float* d_color, const float* d_rem, int dx, int dy, int dz,
-                            float level, float voxel_size, const float vol_origin[3], const void* d_workspace,
-                            size_t workspace_bytes, long long n_tris, long long n_active, void* d_active_list,
-                            float* d_verts, int* d_faces, float* d_norms, unsigned char* d_colors, float* d_rem_out,
-                            vl_stream stream_) {
+static int mesh_emit_impl(const float* d_tsdf, const float* d_color, const float* d_rem, int dx, int dy, int dz,
+                          float level, float voxel_size, const float vol_origin[3], const int* d_hull, const void* d_workspace,
+                          size_t workspace_bytes, long long n_tris, long long n_active, void* d_active_list,
+                          float* d_verts, int* d_faces, float* d_norms, unsigned char* d_colors, float* d_rem_out,
+                          vl_stream stream_) {
   MeshParams P;
   int rc = mesh_args("vl_mesh_emit", d_tsdf, dx, dy, dz, d_workspace, workspace_bytes, &P, level, voxel_size, vol_origin);
   if (rc) return rc;
@@ -801,7 +908,26 @@ extern "C" int vl_mesh_emit(const float* d_tsdf, const float* d_color, const flo
   VlProfScope ps(VL_ST_MESH_EMIT, stream);
   const int vec_ok = ((((uintptr_t)d_verts) | ((uintptr_t)d_norms)) & 15) == 0 && (((uintptr_t)d_colors) & 3) == 0;
   k_mesh_emit<<<(unsigned)((n_tris + kEmitTris - 1) / kEmitTris), kEmitTris, 0, stream>>>(
-      d_tsdf, d_color, d_rem, P, list, n_active, cta_first, n_tris, d_verts, d_faces, d_norms, d_colors, d_rem_out, vec_ok);
+      d_tsdf, d_color, d_rem, P, list, n_active, cta_first, n_tris, d_verts, d_faces, d_norms, d_colors, d_rem_out, vec_ok, d_hull);
   VL_LAUNCH_CHECK("k_mesh_emit");
   return VL_OK;
+}
+
+extern "C" int vl_mesh_emit(const float* d_tsdf, const float* d_color, const float* d_rem, int dx, int dy, int dz,
+                            float level, float voxel_size, const float vol_origin[3], const void* d_workspace,
+                            size_t workspace_bytes, long long n_tris, long long n_active, void* d_active_list,
+                            float* d_verts, int* d_faces, float* d_norms, unsigned char* d_colors, float* d_rem_out,
+                            vl_stream stream) {
+  return mesh_emit_impl(d_tsdf, d_color, d_rem, dx, dy, dz, level, voxel_size, vol_origin, nullptr, d_workspace, workspace_bytes,
+                        n_tris, n_active, d_active_list, d_verts, d_faces, d_norms, d_colors, d_rem_out, stream);
+}
+
+extern "C" int vl_mesh_emit_sparse(const float* d_tsdf, const float* d_color, const float* d_rem, int dx, int dy, int dz,
+                                   float level, float voxel_size, const float vol_origin[3], const int* d_hull,
+                                   const void* d_workspace, size_t workspace_bytes, long long n_tris, long long n_active,
+                                   void* d_active_list, float* d_verts, int* d_faces, float* d_norms,
+                                   unsigned char* d_colors, float* d_rem_out, vl_stream stream) {
+  if (!d_hull) { vl_set_error("vl_mesh_emit_sparse: null d_hull"); return VL_EINVAL; }
+  return mesh_emit_impl(d_tsdf, d_color, d_rem, dx, dy, dz, level, voxel_size, vol_origin, d_hull, d_workspace, workspace_bytes,
+                        n_tris, n_active, d_active_list, d_verts, d_faces, d_norms, d_colors, d_rem_out, stream);
 }

@@ -78,6 +78,11 @@ class Bvh:
 
 TRACE_ZERO_MISSES = 1
 RAYS_NORMALIZED = 4
+COLORS_U8 = 8
+
+# TSDF volumes are SPARSE by default (per z column only an interval of voxels exists, vl_tsdf_sparse_integrate); the
+# properties tsdf / weight / color / rem and get_volume() hand out dense views (materialised on first use).
+DEFAULT_SPARSE = True
 
 # How ray directions are normalised before the triangle test (normalize(), auxiliary/raytracer/Vector3.h:73-89):
 #   "sse"  -- on the host by lib().vl_normalize_rays, the reference's own rsqrtps + Newton step: the device sees the
@@ -172,7 +177,8 @@ def cast(beams, verts, faces, colors, rem, origin, out=None, want_ids=True, zero
          check_mesh=True):
   """(ii-b) closest-hit cast of an indexed mesh against indexed beams -- same outputs as
   Bvh(...) + trace(...), i.e. as C_Trace (RayTracerCython.pyx:15-33 -> RayTracer.cpp:19-92), without a
-  per-scan tree: the triangles are streamed once through the beam index.  Mesh arrays as for Bvh.
+  per-scan tree: the triangles are streamed once through the beam index.  Mesh arrays as for Bvh; colors may also be
+  a uint8 CUDA tensor (TsdfDevice.extract_mesh's), read as it is (VL_COLORS_U8).
   check_mesh=True (default) synchronises, raises VlidarError(VL_EBADMESH) on out-of-range face indices or
   VlidarError(VL_ENOSPACE) when the mesh needs more work units than the workspace holds (nothing was written then:
   use Bvh + trace), and adds n_bad_faces / n_active (triangles that can be hit at all) / n_units to the result.
@@ -180,7 +186,8 @@ def cast(beams, verts, faces, colors, rem, origin, out=None, want_ids=True, zero
   dev = beams.blob.device
   verts = _dev(verts, torch.float32, dev).reshape(-1)
   faces = _dev(faces, torch.int32, dev).reshape(-1)
-  colors = _dev(colors, torch.int32, dev).reshape(-1)
+  colors_u8 = torch.is_tensor(colors) and colors.dtype == torch.uint8   # the mesh extraction's colours, used as they are
+  colors = _dev(colors, torch.uint8 if colors_u8 else torch.int32, dev).reshape(-1)
   rem = _dev(rem, torch.float32, dev).reshape(-1)
   origin = _dev(origin, torch.float32, dev).reshape(-1)
   n_verts, n_faces = verts.numel() // 3, faces.numel() // 3
@@ -193,7 +200,8 @@ def cast(beams, verts, faces, colors, rem, origin, out=None, want_ids=True, zero
     check(lib().vl_cast(_ptr(beams.blob), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(rem), n_verts, n_faces,
                         _ptr(origin), beams.n_rays, beams.height, _ptr(out["endpoints"]), _ptr(out["endcolors"]),
                         _ptr(out["range"]), _ptr(out["endrem"]), _ptr(out.get("tri_id")),
-                        TRACE_ZERO_MISSES if zero_misses else 0, _ptr(workspace), workspace.numel(), _stream()))
+                        (TRACE_ZERO_MISSES if zero_misses else 0) | (COLORS_U8 if colors_u8 else 0), _ptr(workspace),
+                        workspace.numel(), _stream()))
     if check_mesh:
       info = (ctypes.c_int * 8)()
       rc = lib().vl_cast_status(_ptr(workspace), _stream(), info)
@@ -300,8 +308,9 @@ class TsdfDevice:
   Device-side core of auxiliary.fusion_lidar.TSDFVolume (auxiliary/fusion_lidar.py:23-63,
   252-287); the reference-shaped class lives in lidar_transfer_b200/auxiliary/fusion_lidar.py."""
 
-  def __init__(self, vol_dim, vol_origin, voxel_size, fov_up, fov_down, device=None):
+  def __init__(self, vol_dim, vol_origin, voxel_size, fov_up, fov_down, device=None, sparse=None):
     require_cuda()
+    self.sparse = DEFAULT_SPARSE if sparse is None else bool(sparse)
     self.dim = tuple(int(v) for v in vol_dim)
     self.origin = np.asarray(vol_origin, np.float32).copy()
     self.voxel_size = float(np.float32(voxel_size))
@@ -314,6 +323,8 @@ class TsdfDevice:
       raise ValueError("volume of %d voxels exceeds the reference kernel's int voxel index" % n)
     self._store = self._acquire(n, dev)
     self._vols = tuple(f[:n].view(self.dim) for f in self._store["flat"])
+    if self.dim[2] > 32767:
+      self.sparse = False
     self.reset()
 
   # The reference allocates (and uploads) four new volumes per TSDFVolume, i.e. per scan (laserscan.py:968,
@@ -361,13 +372,28 @@ class TsdfDevice:
     integrate() writes the initial values of the voxels it does not update in the same pass
     (vl_tsdf_init_integrate); anything else that looks at the volumes first materialises them (vl_tsdf_init)."""
     self._fresh = True
+    self._dense = False   # sparse volume: every voxel materialised (hull = whole columns)?
+
+  def _hull(self):
+    """Per z column the interval of voxels that exist (vl_tsdf_sparse_integrate), i32[dx * dy] on the device."""
+    n_cols = self.dim[0] * self.dim[1]
+    return self._workspace("hull", 4 * n_cols, self._vols[0].device)[:4 * n_cols].view(torch.int32)
 
   def _materialise(self):
+    """Dense volumes: what the properties below, get_volume() and the dense API see."""
+    t, w, c, r = self._vols
     if self._fresh:
       self._fresh = False
-      t, w, c, r = self._vols
       with torch.cuda.device(t.device):
         check(lib().vl_tsdf_init(_ptr(t), _ptr(w), _ptr(c), _ptr(r), t.numel(), _stream()))
+      if self.sparse:
+        self._hull().fill_((self.dim[2] - 1) << 16)
+        self._dense = True
+    elif self.sparse and not self._dense:
+      with torch.cuda.device(t.device):
+        check(lib().vl_tsdf_densify(_ptr(t), _ptr(w), _ptr(c), _ptr(r), self.dim[0], self.dim[1], self.dim[2],
+                                    _ptr(self._hull()), _stream()))
+      self._dense = True
 
   tsdf = property(lambda self: (self._materialise(), self._vols[0])[1])
   weight = property(lambda self: (self._materialise(), self._vols[1])[1])
@@ -378,14 +404,27 @@ class TsdfDevice:
     """color_im: folded single-channel image (label * 65536), depth_im, rem_im: f32[H,W].
     use_column_table: vl_tsdf_integrate_ws (per-column pixel table, same bits) instead of vl_tsdf_integrate."""
     dev = self._vols[0].device
-    fused = self._fresh and use_column_table   # first integration into a fresh volume: one pass
-    if not fused:
-      self._materialise()
     color_im = _dev(color_im, torch.float32, dev)
     depth_im = _dev(depth_im, torch.float32, dev)
     rem_im = _dev(rem_im, torch.float32, dev)
     im_h, im_w = depth_im.shape
     origin = (ctypes.c_float * 3)(*[float(v) for v in self.origin])
+    if self.sparse and use_column_table:
+      # sparse volume: no reset pass, only the voxels inside the columns' hulls exist (vl_tsdf_sparse_integrate)
+      need = lib().vl_tsdf_sparse_workspace_bytes(self.dim[0], self.dim[1], int(im_h), int(im_w))
+      ws = self._workspace("columns", need, dev)
+      with torch.cuda.device(dev):
+        check(lib().vl_tsdf_sparse_integrate(_ptr(self._vols[0]), _ptr(self._vols[1]), _ptr(self._vols[2]), _ptr(self._vols[3]),
+                                             self.dim[0], self.dim[1], self.dim[2], origin, self.voxel_size, self.trunc_margin,
+                                             float(np.float32(obs_weight)), self.fov_up, self.fov_down, _ptr(color_im),
+                                             _ptr(depth_im), _ptr(rem_im), int(im_h), int(im_w), _ptr(self._hull()),
+                                             1 if self._fresh else 0, _ptr(ws), ws.numel(), _stream()))
+      if self._fresh:
+        self._fresh, self._dense = False, False
+      return
+    fused = self._fresh and use_column_table   # first integration into a fresh volume: one pass
+    if not fused:
+      self._materialise()
     if use_column_table:
       need = lib().vl_tsdf_fresh_workspace_bytes(self.dim[0], self.dim[1], int(im_h), int(im_w))  # column table + shell image
       ws = self._workspace("columns", need, dev)
@@ -410,15 +449,29 @@ class TsdfDevice:
     the device-resident equivalent of TSDFVolume.get_mesh (auxiliary/fusion_lidar.py:403-424).
     Returns dict(verts f32[N_v,3] world frame, faces i32[N_t,3], norms f32[N_v,3], colors u8[N_v,3],
     rem f32[N_v]) -- a triangle soup, N_v = 3 N_t.  Synchronises once (the triangle count)."""
-    dev = self.tsdf.device
+    hull = None
+    if self.sparse and not self._fresh and not self._dense and level <= 1.0 and self.dim[2] + 64 <= 2048:
+      hull = self._hull()    # sparse volume: the mesh kernels read inside the hulls only
+      vols = self._vols
+    else:
+      vols = (self.tsdf, self.weight, self.color, self.rem)
+    dev = vols[0].device
     n = self.dim[0] * self.dim[1] * self.dim[2]
     need = lib().vl_mesh_workspace_bytes(self.dim[0], self.dim[1], self.dim[2])
     ws = self._workspace("mesh", need, dev)
     totals = torch.zeros(2, dtype=torch.int64, device=dev)
     origin = (ctypes.c_float * 3)(*[float(v) for v in self.origin])
     with torch.cuda.device(dev):
-      check(lib().vl_mesh_count(_ptr(self.tsdf), self.dim[0], self.dim[1], self.dim[2], float(level), _ptr(ws),
-                                ws.numel(), _ptr(totals), _stream()))
+      if hull is not None:
+        rc = lib().vl_mesh_count_sparse(_ptr(vols[0]), self.dim[0], self.dim[1], self.dim[2], float(level), _ptr(hull), _ptr(ws),
+                                        ws.numel(), _ptr(totals), _stream())
+        if rc == _lib.VL_EINVAL:   # e.g. a debug sweep that needs the dense volume (vl_debug_mesh_scalar(2 / 3))
+          hull, vols = None, (self.tsdf, self.weight, self.color, self.rem)
+        else:
+          check(rc)
+      if hull is None:
+        check(lib().vl_mesh_count(_ptr(vols[0]), self.dim[0], self.dim[1], self.dim[2], float(level), _ptr(ws),
+                                  ws.numel(), _ptr(totals), _stream()))
       n_t, n_a = (int(v) for v in totals.tolist())  # the one host synchronisation of the extraction
       out = dict(verts=torch.empty((3 * n_t, 3), dtype=torch.float32, device=dev),
                  faces=torch.empty((n_t, 3), dtype=torch.int32, device=dev),
@@ -426,10 +479,16 @@ class TsdfDevice:
                  colors=torch.empty((3 * n_t, 3), dtype=torch.uint8, device=dev),
                  rem=torch.empty(3 * n_t, dtype=torch.float32, device=dev))
       active = torch.empty(lib().vl_mesh_list_bytes(n_t, n_a), dtype=torch.uint8, device=dev)   # scratch of vl_mesh_emit
-      check(lib().vl_mesh_emit(_ptr(self.tsdf), _ptr(self.color), _ptr(self.rem), self.dim[0], self.dim[1], self.dim[2],
-                               float(level), self.voxel_size, origin, _ptr(ws), ws.numel(), n_t, n_a, _ptr(active),
-                               _ptr(out["verts"]), _ptr(out["faces"]), _ptr(out["norms"]), _ptr(out["colors"]),
-                               _ptr(out["rem"]), _stream()))
+      if hull is not None:
+        check(lib().vl_mesh_emit_sparse(_ptr(vols[0]), _ptr(vols[2]), _ptr(vols[3]), self.dim[0], self.dim[1], self.dim[2],
+                                        float(level), self.voxel_size, origin, _ptr(hull), _ptr(ws), ws.numel(), n_t, n_a,
+                                        _ptr(active), _ptr(out["verts"]), _ptr(out["faces"]), _ptr(out["norms"]),
+                                        _ptr(out["colors"]), _ptr(out["rem"]), _stream()))
+      else:
+        check(lib().vl_mesh_emit(_ptr(vols[0]), _ptr(vols[2]), _ptr(vols[3]), self.dim[0], self.dim[1], self.dim[2],
+                                 float(level), self.voxel_size, origin, _ptr(ws), ws.numel(), n_t, n_a, _ptr(active),
+                                 _ptr(out["verts"]), _ptr(out["faces"]), _ptr(out["norms"]), _ptr(out["colors"]),
+                                 _ptr(out["rem"]), _stream()))
       out["n_active_cubes"] = n_a
     return out
 

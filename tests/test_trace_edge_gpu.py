@@ -147,7 +147,8 @@ def test_full_size_properties(engine, oracle):
   _same(a, b)
   # header: n_tris, root reference, bad faces, climb depth, scene bounds (the header's padding and the node slots that
   # no sub-tree of > 4 triangles owns are never written, so they hold whatever the allocation held)
-  assert torch.equal(bvh.blob[:40], bvh2.blob[:40])
+  # (bytes 12..16 = the deepest climb, a statistic that depends on which child reaches a node second: not compared)
+  assert torch.equal(bvh.blob[:12], bvh2.blob[:12]) and torch.equal(bvh.blob[16:40], bvh2.blob[16:40])
   assert (a["tri_id"] >= 0).mean() > 0.99
   sub = np.arange(0, H * W, 997)[: 8 * 16]
   bf = _np(engine.trace_bruteforce(sc["verts"], sc["faces"], sc["colors"], sc["rem"], rays[sub], origin, 8))
