@@ -416,6 +416,8 @@ def run_native(args):
   from lidar_transfer_b200.auxiliary.raytracer import RayTracerCython as rtc
   from lidar_transfer_b200.rays import create_rays
   L = _lib.lib()
+  if os.environ.get("VL_CAST_REARM") is not None:   # A/B aid
+    L.vl_debug_cast_rearm(int(os.environ["VL_CAST_REARM"]))
   S, K, Wm = args.scans_per_step, args.steps, args.warmup
   Se, Sp = args.e2e_scans_per_step, args.pipelined_scans_per_step
   M = min(args.distinct_meshes, S)   # distinct meshes per rank; a step cycles through them

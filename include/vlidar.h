@@ -111,6 +111,7 @@ int vl_bvh_status(const void* d_blob, int n_faces, vl_stream stream, int* info);
 #define VL_TRACE_ZERO_MISSES 1
 #define VL_TRACE_PACKET      2   /* warp-packet traversal (8x4 beam tiles share one stack) instead of per-ray stacks */
 #define VL_RAYS_NORMALIZED   4   /* d_rays hold unit directions already (vl_normalize_rays): used as given, not re-normalised */
+#define VL_TRACE_PERSISTENT 16   /* vl_trace: persistent warps pulling rays from a counter, warp-wide ray compaction, top of the tree staged in shared memory by TMA (cp.async.bulk + mbarrier) */
 #define VL_COLORS_U8         8   /* vl_cast only: d_colors is uint8[3*n_verts] (what vl_mesh_emit writes) instead of int32[3*n_verts] */
 int vl_trace(const void* d_blob, int n_faces, const float* d_rays, const float* d_origin,
              int n_rays, int height, float* d_endpoints, int* d_endcolors, float* d_range,
@@ -149,8 +150,8 @@ int vl_cast(const void* d_beams, const float* d_verts, const int* d_faces, const
 int vl_cast_status(const void* d_workspace, vl_stream stream, int* info);
 /* vl_cast for one scan of a batch in a single call (the per-scan host cost is what bounds a batch at this kernel
  * speed): if ev_ready (cudaEvent_t) is given it is recorded on `producer` (the stream that produced the mesh) and
- * `stream` waits for it; then vl_cast; then, if h_status (pinned host int[4]) is given, the first 16 bytes of
- * the workspace header ([0] n_bad_faces, [1] overflow flag) are copied to it; then ev_done (nullable) is recorded. */
+ * `stream` waits for it; then vl_cast; then, if h_status (pinned host int[4]) is given, bytes 16..31 of
+ * the workspace header ([0] n_bad_faces, [1] overflow flag of this scan) are copied to it; then ev_done (nullable) is recorded. */
 int vl_cast_submit(const void* d_beams, const float* d_verts, const int* d_faces, const int* d_colors,
                    const float* d_rem, int n_verts, int n_faces, const float* d_origin, int n_rays,
                    int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
@@ -161,7 +162,7 @@ int vl_cast_submit(const void* d_beams, const float* d_verts, const int* d_faces
  * (PINNED host memory: {const float* verts; const int* faces; const int* colors; const float* rem; int n_verts;
  * int n_faces; 24 bytes unused}, device pointers) holds when the graph's first node copies it to the device -- the caller
  * rewrites it before every vl_cast_graph_launch and not before the previous launch on that slot has finished.
- * h_status (nullable, pinned int[4]) receives the workspace header's first 16 bytes as in vl_cast_submit; `stream`
+ * h_status (nullable, pinned int[4]) receives the scan's counters as in vl_cast_submit; `stream`
  * must be idle during creation (it is captured).  vl_cast_graph_launch: optional producer wait as in vl_cast_submit,
  * the launch, then ev_done (nullable) is recorded. */
 int vl_cast_graph_create(const void* d_beams, const float* d_origin, int n_rays, int height,
@@ -370,12 +371,14 @@ int         vl_profile_collect(double* stage_ms, long long* stage_launches);
  * {inner nodes visited, triangles tested} to d_stats[2*r .. 2*r+1] (device int[2*n_rays]). */
 void        vl_debug_trace_stats(int* d_stats);
 /* Debug: force the traversal variant: 0 auto, 1 per-ray in storage order, 2 per-ray in 16x8 beam tiles,
- * 4/8/16/32 = warp packets of that tile width. */
+ * 3 persistent warps + ray compaction + TMA-staged top of the tree, 4/8/16/32 = warp packets of that tile width. */
 void        vl_debug_trace_mode(int mode);
 /* Debug: force vl_mesh_count's one-cube-per-lane sweep (default: four cubes per lane when dz % 4 == 0). */
 void        vl_debug_mesh_scalar(int on);
 /* Debug: cell rows per beam row of the beam index (default 1); changes vl_beams_bytes. */
 void        vl_debug_cast_cells(int cells_per_beam_row);
+/* Debug: 1 = graphs created from now on have no reset kernel (k_cast_resolve re-arms the slot), 0 (default) = k_cast_init per scan. */
+void        vl_debug_cast_rearm(int on);
 /* Debug: persistent CTAs per SM of the item kernel (default 4). */
 void        vl_debug_cast_ctas(int ctas_per_sm);
 /* Debug: persistent CTAs per SM of the setup kernel (default 4). */

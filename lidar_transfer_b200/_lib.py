@@ -49,6 +49,7 @@ SIGNATURES = {
     "vl_ctrace_method": (None, [_i]),
     "vl_debug_mesh_scalar": (None, [_i]),
     "vl_debug_cast_cells": (None, [_i]),
+    "vl_debug_cast_rearm": (None, [_i]),
     "vl_debug_cast_ctas": (None, [_i]),
     "vl_debug_cast_setup_ctas": (None, [_i]),
     "vl_trace_bruteforce": (_i, [_vp] * 4 + [_i, _i, _vp, _vp, _i, _i] + [_vp] * 5 + [_i, _vp]),

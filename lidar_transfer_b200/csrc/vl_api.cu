@@ -47,6 +47,18 @@ cudaEvent_t prof_event() {
 
 void vl_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+int vl_sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 void vl_prof_begin(int stage, cudaStream_t stream) {
   if (!g_prof_on.load(std::memory_order_relaxed)) return;
   cudaEvent_t e = prof_event();
@@ -218,7 +230,8 @@ extern "C" int vl_cast_submit(const void* d_beams, const float* d_verts, const i
   const int rc = vl_cast(d_beams, d_verts, d_faces, d_colors, d_rem, n_verts, n_faces, d_origin, n_rays, height,
                          d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, flags, d_workspace, workspace_bytes, stream);
   if (rc) return rc;
-  if (h_status) VL_CUDA_CHECK(cudaMemcpyAsync(h_status, d_workspace, 16, cudaMemcpyDeviceToHost, s));
+  // bytes 16..31 of the workspace header: the scan's counters as k_cast_resolve left them for the host
+  if (h_status) VL_CUDA_CHECK(cudaMemcpyAsync(h_status, static_cast<char*>(d_workspace) + 16, 16, cudaMemcpyDeviceToHost, s));
   if (ev_done) VL_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(ev_done), s));
   return VL_OK;
 }

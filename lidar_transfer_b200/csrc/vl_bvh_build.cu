@@ -634,6 +634,30 @@ k_top_climb(const unsigned int* __restrict__ keys, int n, VlHeader* hdr, VlNode*
   }
 }
 
+// The top VL_TOP_LEVELS levels of the finished tree, copied into heap order (node i -> children 2 i + 1, 2 i + 2) so that
+// k_trace_persistent can stage them in shared memory with ONE bulk copy (cp.async.bulk) and address them without
+// following references.  A slot whose node does not exist (its parent's child is a leaf, or absent) is never read.
+__global__ void __launch_bounds__(1024)
+k_top_pack(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ nodes, VlNode* __restrict__ top) {
+  __shared__ int s_ref[VL_TOP_NODES + 1];
+  if (threadIdx.x == 0) s_ref[0] = hdr->n_tris > 0 ? hdr->root_ref : -1;
+  __syncthreads();
+  for (int L = 0; L < VL_TOP_LEVELS; ++L) {
+    const int n = 1 << L, base = n - 1;
+    for (int t = threadIdx.x; t < n; t += 1024) {
+      const int i = base + t, g = s_ref[i];
+      int c0 = -1, c1 = -1;
+      if (g >= 0) {
+        const float4 a = nodes[g].q[0], b = nodes[g].q[1], c = nodes[g].q[2], e = nodes[g].q[3];
+        top[i].q[0] = a; top[i].q[1] = b; top[i].q[2] = c; top[i].q[3] = e;
+        c0 = __float_as_int(b.z); c1 = __float_as_int(e.z);
+      }
+      if (L + 1 < VL_TOP_LEVELS) { s_ref[2 * i + 1] = c0; s_ref[2 * i + 2] = c1; }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 int g_debug_build_stop = 0;  // vl_debug_build_stop(): 0 full build; 1 / 2 / 3 = return after bounds / morton / sort (timing only)
@@ -656,9 +680,9 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
   unsigned int* vals1 = reinterpret_cast<unsigned int*>(blob + L.off_vals1);
   int* flags = reinterpret_cast<int*>(blob + L.off_flags);
 
-  // persistent grids: 148 SMs x 4 resident CTAs
+  // persistent grids: SM count (148 on B200) x 4 resident CTAs
   int nb_verts = (n_verts + kThreads - 1) / kThreads;
-  if (nb_verts > 148 * 4) nb_verts = 148 * 4;
+  if (nb_verts > vl_sm_count() * 4) nb_verts = vl_sm_count() * 4;
   if (nb_verts < 1) nb_verts = 1;
   { VlProfScope ps(VL_ST_BOUNDS, stream);
   k_bounds<<<nb_verts, kThreads, 0, stream>>>(d_verts, n_verts, hdr); }
@@ -667,7 +691,7 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
   const int nt = L.n_sort_tiles;
   const int n_state_words = 256 * VL_SORT_PASSES * L.n_state_tiles;
   int nb_faces = (n_faces + kThreads - 1) / kThreads;
-  if (nb_faces > 148 * 4) nb_faces = 148 * 4;
+  if (nb_faces > vl_sm_count() * 4) nb_faces = vl_sm_count() * 4;
   { VlProfScope ps(VL_ST_MORTON, stream);
   k_morton<<<nb_faces, kThreads, 0, stream>>>(d_verts, d_faces, n_verts, n_faces, hdr, keys0, flags, ghist, tile_state,
                                              n_state_words); }
@@ -701,9 +725,11 @@ int vl_bvh_build_launch(const float* d_verts, const int* d_faces, const int* d_c
   if (nb_climb > 1) {
     VlProfScope ps(VL_ST_TOP_CLIMB, stream);
     int nb_top = (nb_climb * 16 + kTopThreads - 1) / kTopThreads;  // ~ a dozen queued nodes per CTA is typical
-    if (nb_top > 148 * 8) nb_top = 148 * 8;
+    if (nb_top > vl_sm_count() * 8) nb_top = vl_sm_count() * 8;
     k_top_climb<<<nb_top, kTopThreads, 0, stream>>>(keys0, n_faces, hdr, nodes, flags, vals1);
     VL_LAUNCH_CHECK("k_top_climb");
   }
+  k_top_pack<<<1, 1024, 0, stream>>>(hdr, nodes, reinterpret_cast<VlNode*>(blob + L.off_top));
+  VL_LAUNCH_CHECK("k_top_pack");
   return VL_OK;
 }

@@ -57,8 +57,13 @@ struct VlCastHeader {
   int n_bad_faces;
   int overflow;                  // more work units than the workspace holds: results invalid (VL_ENOSPACE)
   unsigned long long reserved;   // [records : 28][units : 36], bumped once per pass by k_cast_setup
-  int pad[60];
+  // the three counters above as k_cast_resolve found them: what the host reads (vl_cast_status, the 16-byte status copy)
+  int snap_bad_faces;
+  int snap_overflow;
+  unsigned long long snap_reserved;
+  int pad[56];
 };
+constexpr size_t kSnapOffset = 16;
 static_assert(sizeof(VlCastHeader) == 256, "cast header is 256 B");
 
 // The mesh of one scan.  Passed to the kernels by value (vl_cast), or read from device memory (a replayed CUDA
@@ -81,6 +86,10 @@ struct BeamLayout {
 };
 
 int g_cells_per_row = 1;   // cell rows per beam row (vl_debug_cast_cells)
+// vl_debug_cast_rearm: 1 = a slot's graph has no reset kernel (k_cast_resolve re-arms the keys and counters it has just
+// read), 0 (default) = k_cast_init per scan.  Measured (profiles/r02_experiments.md): WITHOUT the 3.6 us reset kernel the
+// step is 15 % slower (2720 vs 3136 Mrays/s at 8 streams, A/B on one box) -- kept as a switch, off.
+int g_graph_rearm = 0;
 int g_items_ctas_per_sm = 4;
 int g_setup_ctas_per_sm = VL_SETUP_MINB_DEFAULT;
 
@@ -679,18 +688,23 @@ k_cast_units(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const int* _
 // RayTracer.cpp:73-90 write-back for the winning triangle of each beam; BVH.cpp:106-107 hit = o + d * t
 template <bool kDescPtr>
 __global__ void __launch_bounds__(kCastThreads)
-k_cast_resolve(const unsigned long long* __restrict__ best, int n, const float4* __restrict__ dir,
+k_cast_resolve(unsigned long long* best, int n, const float4* __restrict__ dir,
                const int* __restrict__ slot_of, const float* __restrict__ origin, const VlMeshDesc mesh_val,
                const VlMeshDesc* __restrict__ mesh_ptr, float* __restrict__ endpoints, int* __restrict__ endcolors,
                float* __restrict__ range, float* __restrict__ endrem, int* __restrict__ tri_id, bool zero_misses,
-               bool colors_u8) {
+               bool colors_u8, VlCastHeader* __restrict__ chdr, bool rearm) {
   const int r = blockIdx.x * kCastThreads + threadIdx.x;
+  if (r == 0) {   // the counters of this scan for the host; rearm: ... and cleared for the next scan (no k_cast_init then)
+    chdr->snap_bad_faces = chdr->n_bad_faces; chdr->snap_overflow = chdr->overflow; chdr->snap_reserved = chdr->reserved;
+    if (rearm) { chdr->n_bad_faces = 0; chdr->overflow = 0; chdr->reserved = 0ull; }
+  }
   if (r >= n) return;
   const int* __restrict__ faces = kDescPtr ? mesh_ptr->faces : mesh_val.faces;
   const int* __restrict__ colors = kDescPtr ? mesh_ptr->colors : mesh_val.colors;
   const float* __restrict__ rem = kDescPtr ? mesh_ptr->rem : mesh_val.rem;
   const int slot = __ldg(slot_of + r);
   const unsigned long long key = slot >= 0 ? best[slot] : init_key();
+  if (rearm && slot >= 0) best[slot] = init_key();   // every slot belongs to exactly one beam: re-armed for the next scan
   if (key < init_key()) {
     const int f = (int)(unsigned int)(key & 0xffffffffull);
     const float t = __uint_as_float((unsigned int)(key >> 32));
@@ -727,6 +741,7 @@ k_cast_resolve(const unsigned long long* __restrict__ best, int n, const float4*
 
 }  // namespace
 
+extern "C" void vl_debug_cast_rearm(int on) { g_graph_rearm = on ? 1 : 0; }
 extern "C" void vl_debug_cast_cells(int cells_per_beam_row) { g_cells_per_row = cells_per_beam_row < 1 ? 1 : cells_per_beam_row; }
 extern "C" void vl_debug_cast_ctas(int ctas_per_sm) { g_items_ctas_per_sm = ctas_per_sm < 1 ? 1 : ctas_per_sm; }
 extern "C" void vl_debug_cast_setup_ctas(int ctas_per_sm) { g_setup_ctas_per_sm = ctas_per_sm < 1 ? 1 : ctas_per_sm; }
@@ -763,7 +778,7 @@ int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_b
   int* blk_sum = reinterpret_cast<int*>(B + L.off_blk);
   const int ncell = L.cw * L.ch;
   VlProfScope ps(VL_ST_BEAMS, stream);
-  k_beam_init<<<148, 256, 0, stream>>>(hdr, cell_start, ncell + 1, fine);
+  k_beam_init<<<vl_sm_count(), 256, 0, stream>>>(hdr, cell_start, ncell + 1, fine);
   VL_LAUNCH_CHECK("k_beam_init");
   const int nb = (L.n + kCastThreads - 1) / kCastThreads;
   if (L.n > 0) {
@@ -790,7 +805,7 @@ int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_b
 // mesh of a stream slot for a graph); mesh is read from `d_desc` when by_ptr (graph replay) and passed by value otherwise.
 static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr, int cap_faces, const float* d_origin,
                         int n_rays, int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
-                        int* d_tri_id, int flags, void* d_ws, cudaStream_t stream) {
+                        int* d_tri_id, int flags, void* d_ws, cudaStream_t stream, bool init, bool rearm) {
   const BeamLayout L = beam_layout(n_rays, height);
   if (d_tri_id && n_rays > L.n)   // rays beyond width * height are never cast (RayTracer.cpp:56)
     VL_CUDA_CHECK(cudaMemsetAsync(d_tri_id + L.n, 0xff, sizeof(int) * (size_t)(n_rays - L.n), stream));
@@ -810,16 +825,17 @@ static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr
   int2* units = reinterpret_cast<int2*>(Wk + C.off_units);
   float4* recs = reinterpret_cast<float4*>(Wk + C.off_recs);
   const int rec_cap = cap_faces > 0 ? cap_faces : 1;
-  {
+  if (init) {
     VlProfScope ps(VL_ST_CAST_INIT, stream);
-    k_cast_init<<<148, 256, 0, stream>>>(best, L.n, chdr);
+    k_cast_init<<<vl_sm_count(), 256, 0, stream>>>(best, L.n, chdr);
     VL_LAUNCH_CHECK("k_cast_init");
   }
   if (by_ptr || mesh.n_faces > 0) {
     {
       VlProfScope ps(VL_ST_CAST_SETUP, stream);
       const int n_batches = ((by_ptr ? cap_faces : mesh.n_faces) + kBatch - 1) / kBatch;
-      const int nb = n_batches < 148 * g_setup_ctas_per_sm ? (n_batches > 0 ? n_batches : 1) : 148 * g_setup_ctas_per_sm;
+      const int cap = vl_sm_count() * g_setup_ctas_per_sm;
+      const int nb = n_batches < cap ? (n_batches > 0 ? n_batches : 1) : cap;
       if (by_ptr)
         k_cast_setup<true><<<nb, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, mesh, d_desc, d_origin, chdr, recs,
                                                            rec_cap, units, C.unit_cap);
@@ -830,7 +846,7 @@ static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr
     }
     {
       VlProfScope ps(VL_ST_CAST_ITEMS, stream);
-      k_cast_units<<<148 * g_items_ctas_per_sm, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, cell_start, sorted, d_origin,
+      k_cast_units<<<vl_sm_count() * g_items_ctas_per_sm, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, cell_start, sorted, d_origin,
                                                                           best, chdr, recs, units);
       VL_LAUNCH_CHECK("k_cast_units");
     }
@@ -841,10 +857,10 @@ static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr
     const bool zm = (flags & VL_TRACE_ZERO_MISSES) != 0, c8 = (flags & VL_COLORS_U8) != 0;
     if (by_ptr)
       k_cast_resolve<true><<<nb, kCastThreads, 0, stream>>>(best, L.n, dir, slot_of, d_origin, mesh, d_desc, d_endpoints,
-                                                           d_endcolors, d_range, d_endrem, d_tri_id, zm, c8);
+                                                           d_endcolors, d_range, d_endrem, d_tri_id, zm, c8, chdr, rearm);
     else
       k_cast_resolve<false><<<nb, kCastThreads, 0, stream>>>(best, L.n, dir, slot_of, d_origin, mesh, d_desc, d_endpoints,
-                                                            d_endcolors, d_range, d_endrem, d_tri_id, zm, c8);
+                                                            d_endcolors, d_range, d_endrem, d_tri_id, zm, c8, chdr, rearm);
     VL_LAUNCH_CHECK("k_cast_resolve");
   }
   return VL_OK;
@@ -858,7 +874,7 @@ int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces
   mesh.verts = d_verts; mesh.faces = d_faces; mesh.colors = d_colors; mesh.rem = d_rem;
   mesh.n_verts = n_verts; mesh.n_faces = n_faces;
   return cast_enqueue(d_beams, mesh, false, n_faces, d_origin, n_rays, height, d_endpoints, d_endcolors, d_range, d_endrem,
-                      d_tri_id, flags, d_ws, stream);
+                      d_tri_id, flags, d_ws, stream, true, false);
 }
 
 // ---------------------------------------------------------------------------
@@ -870,6 +886,14 @@ int vl_cast_graph_create_impl(const void* d_beams, const float* d_origin, int n_
                               int max_faces, const void* h_desc, int* h_status, cudaStream_t stream, void** out_exec) {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
+  {   // the workspace of a slot is armed ONCE, here; every replay's k_cast_resolve re-arms it for the next scan
+    const BeamLayout L = beam_layout(n_rays, height);
+    const CastLayout C = cast_layout(n_rays, max_faces);
+    char* Wk = static_cast<char*>(d_ws);
+    k_cast_init<<<vl_sm_count(), 256, 0, stream>>>(reinterpret_cast<unsigned long long*>(Wk + C.off_best), L.n > 0 ? L.n : 0,
+                                                  reinterpret_cast<VlCastHeader*>(Wk));
+    VL_LAUNCH_CHECK("k_cast_init");
+  }
   VL_CUDA_CHECK(cudaStreamSynchronize(stream));
   VL_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
   VlMeshDesc none = {};
@@ -877,9 +901,9 @@ int vl_cast_graph_create_impl(const void* d_beams, const float* d_origin, int n_
   cudaError_t e = cudaMemcpyAsync(static_cast<char*>(d_ws) + kDescOffset, h_desc, sizeof(VlMeshDesc), cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess)
     rc = cast_enqueue(d_beams, none, true, max_faces, d_origin, n_rays, height, d_endpoints, d_endcolors, d_range, d_endrem,
-                      d_tri_id, flags, d_ws, stream);
+                      d_tri_id, flags, d_ws, stream, !g_graph_rearm, g_graph_rearm != 0);
   if (e == cudaSuccess && rc == VL_OK && h_status)
-    e = cudaMemcpyAsync(h_status, d_ws, 16, cudaMemcpyDeviceToHost, stream);
+    e = cudaMemcpyAsync(h_status, static_cast<char*>(d_ws) + kSnapOffset, 16, cudaMemcpyDeviceToHost, stream);
   const cudaError_t e2 = cudaStreamEndCapture(stream, &graph);   // always leave capture mode
   if (rc != VL_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
   VL_CUDA_CHECK(e);
@@ -892,7 +916,7 @@ int vl_cast_graph_create_impl(const void* d_beams, const float* d_origin, int n_
 
 int vl_cast_graph_launch_impl(void* exec, cudaStream_t stream) {
   VL_CUDA_CHECK(cudaGraphLaunch(static_cast<cudaGraphExec_t>(exec), stream));
-  for (int k = 0; k < 4; ++k) vl_count_launch();   // init, setup, units, resolve
+  for (int k = 0; k < (g_graph_rearm ? 3 : 4); ++k) vl_count_launch();   // setup, units, resolve (the slot was armed once, at creation)
   return VL_OK;
 }
 
@@ -906,19 +930,19 @@ int vl_cast_status_read(const void* d_ws, cudaStream_t stream, int* info) {
   VL_CUDA_CHECK(cudaMemcpyAsync(&h, d_ws, sizeof(h), cudaMemcpyDeviceToHost, stream));
   VL_CUDA_CHECK(cudaStreamSynchronize(stream));
   if (info) {
-    info[0] = h.n_bad_faces;
-    info[1] = (int)(h.reserved >> kUnitBits);                                       // triangles that can be hit at all
-    const unsigned long long items = h.reserved & ((1ull << kUnitBits) - 1ull);   // work units (<= 4 cell runs each)
+    info[0] = h.snap_bad_faces;
+    info[1] = (int)(h.snap_reserved >> kUnitBits);                                       // triangles that can be hit at all
+    const unsigned long long items = h.snap_reserved & ((1ull << kUnitBits) - 1ull);   // work units (<= 4 cell runs each)
     info[2] = (int)(items & 0x7fffffffull);
     info[3] = (int)(items >> 31);
   }
-  if (h.overflow) {
+  if (h.snap_overflow) {
     vl_set_error("vl_cast: the mesh needs more work units (%llu) than the workspace holds -- results are invalid, use vl_bvh_build + vl_trace",
-                 (unsigned long long)(h.reserved & ((1ull << kUnitBits) - 1ull)));
+                 (unsigned long long)(h.snap_reserved & ((1ull << kUnitBits) - 1ull)));
     return VL_ENOSPACE;
   }
-  if (h.n_bad_faces > 0) {
-    vl_set_error("mesh has %d face(s) with a vertex index outside [0, n_verts)", h.n_bad_faces);
+  if (h.snap_bad_faces > 0) {
+    vl_set_error("mesh has %d face(s) with a vertex index outside [0, n_verts)", h.snap_bad_faces);
     return VL_EBADMESH;
   }
   return VL_OK;

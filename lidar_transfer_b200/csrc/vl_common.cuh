@@ -10,6 +10,7 @@
 // ---------------------------------------------------------------------------
 void vl_set_error(const char* fmt, ...);
 void vl_count_launch();
+int vl_sm_count();   // multiProcessorCount of the current device (cached per device; 148 on B200): persistent grids are sized from it
 
 // ---------------------------------------------------------------------------
 // optional per-stage device timing (CUDA events on the launching stream), off by default.
@@ -99,11 +100,14 @@ __host__ __device__ inline int vl_leaf_count(int ref) { return (~ref) & 7; }
 #endif
 #define VL_SORT_TILE (VL_SORT_THREADS * VL_SORT_ITEMS)  // keys per radix-sort tile
 #define VL_SORT_PASSES 4                                // 8-bit digits over the 32-bit Morton key
+#define VL_TOP_LEVELS 11                                // levels of the tree kept in heap order for shared-memory staging
+#define VL_TOP_NODES ((1 << VL_TOP_LEVELS) - 1)         // 2047 nodes x 64 B = 128 KB
 
 // sort scratch: [digit histograms 4 x 256 u32][4 tile tickets, padded to 256 B][tile + group states 4 x n_state_tiles x 256 u32]
 struct VlBlobLayout {
   size_t off_nodes, off_tris, off_c0, off_keys0, off_keys1, off_vals0, off_vals1, off_flags;
   size_t off_ghist, off_tickets, off_tile_state;
+  size_t off_top;     // the top VL_TOP_LEVELS levels of the tree in heap order (k_top_pack), staged by TMA in k_trace_persistent
   size_t total;
   int n_sort_tiles;
   int n_state_tiles;  // state rows per pass: one per tile + one per group of 32 tiles
@@ -128,6 +132,7 @@ __host__ inline VlBlobLayout vl_blob_layout(int n) {
   L.off_tickets = off;    off = vl_align256(off + 4 * VL_SORT_PASSES);
   L.n_state_tiles = L.n_sort_tiles + (L.n_sort_tiles + 31) / 32;
   L.off_tile_state = off; off = vl_align256(off + 4 * 256 * (size_t)VL_SORT_PASSES * (size_t)L.n_state_tiles);
+  L.off_top = off;        off = vl_align256(off + 64 * (size_t)VL_TOP_NODES);
   L.total = off;
   return L;
 }

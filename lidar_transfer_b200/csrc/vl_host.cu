@@ -318,7 +318,7 @@ int ctrace_locked(HostCtx& c, const float* rays, const float* origin, const floa
                           (float*)(A + o_ep), (int*)(A + o_ec), (float*)(A + o_range), (float*)(A + o_erem), (int*)(A + o_id),
                           0, A + o_ws, s);
       if (rc) return rc;
-      VL_CUDA_CHECK(cudaMemcpyAsync(A + o_st, A + o_ws, 16, cudaMemcpyDeviceToDevice, s));   // {n_bad_faces, overflow, ..}
+      VL_CUDA_CHECK(cudaMemcpyAsync(A + o_st, A + o_ws + 16, 16, cudaMemcpyDeviceToDevice, s));   // {n_bad_faces, overflow, ..} as k_cast_resolve left them
     }
     // (4) one copy back
     VL_CUDA_CHECK(cudaMemcpyAsync(P + o_ep, A + o_ep, io_bytes - o_ep, cudaMemcpyDeviceToHost, s));

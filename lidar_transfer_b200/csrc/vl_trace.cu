@@ -354,6 +354,192 @@ k_trace_packet(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ node
   if (stats) { stats[2 * r] = n_nodes; stats[2 * r + 1] = n_tris; }
 }
 
+// ---------------------------------------------------------------------------
+// North-star (ii) as BASELINE.json spells it: persistent warps that pull rays from a global counter, warp-wide
+// compaction (lanes whose ray has finished take the next rays as soon as fewer than 8 lanes of the warp are live), the
+// per-lane stack in shared memory, and the top VL_TOP_LEVELS levels of the tree (2047 nodes x 64 B = 128 KB, heap
+// order, k_top_pack) staged ONCE per CTA by the TMA engine: cp.async.bulk global -> shared, completion on an mbarrier
+// (UBLKCP in the SASS).  One 512-thread CTA per SM: 128 KB of nodes + 48 KB of stacks.  Same result contract and the
+// same arithmetic as k_trace (slab<>, vl_tri_hit): bit-identical outputs, tests/test_trace_gpu.py.
+// ---------------------------------------------------------------------------
+constexpr int kPtThreads = 512;
+constexpr int kPtStack = 12;        // stack entries per lane in shared memory (deeper: local memory)
+constexpr int kPtLocal = 52;
+constexpr int kTopFlag = 0x40000000;   // reference = heap index into the staged top of the tree
+constexpr int kRefillIdle = 24;     // refill as soon as 24 lanes are idle (fewer than 8 live)
+constexpr size_t kPtTopBytes = 64 * (size_t)VL_TOP_NODES;                     // 131 008, a multiple of 16
+constexpr size_t kPtSmemBytes = 64 * (size_t)(VL_TOP_NODES + 1) + sizeof(uint2) * kPtStack * kPtThreads;
+
+__device__ unsigned int g_pt_counters[64];
+
+__device__ __forceinline__ unsigned int smem_addr(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+
+template <bool kNanFilter>
+__device__ __forceinline__ int pt_node_step(int ref, const VlNode* __restrict__ nodes, const VlNode* s_top, const float3 o,
+                                            const float3 inv_d, float best_t, uint2* s_stack, uint2* lstack, int& sp, int tid,
+                                            bool* popped) {
+  float4 a, b, c, e;
+  const bool cached = (ref & kTopFlag) != 0;
+  const int hi = ref & ~kTopFlag;
+  if (cached) { const float4* q = s_top[hi].q; a = q[0]; b = q[1]; c = q[2]; e = q[3]; }
+  else { const float4* q = nodes[ref].q; a = __ldg(q); b = __ldg(q + 1); c = __ldg(q + 2); e = __ldg(q + 3); }
+  float tn0, tf0, tn1, tf1;
+  slab<kNanFilter>(a.x, a.y, a.z, a.w, b.x, b.y, o, inv_d, &tn0, &tf0);
+  slab<kNanFilter>(c.x, c.y, c.z, c.w, e.x, e.y, o, inv_d, &tn1, &tf1);
+  tf0 = tf0 * 1.0000004f; tf1 = tf1 * 1.0000004f;
+  const bool h0 = (tf0 >= 0.f) & (tf0 >= tn0) & (tn0 <= best_t);
+  const bool h1 = (tf1 >= 0.f) & (tf1 >= tn1) & (tn1 <= best_t);
+  int r0 = __float_as_int(b.z), r1 = __float_as_int(e.z);
+  if (cached && hi < (1 << (VL_TOP_LEVELS - 1)) - 1) {   // the children of a staged node above the last level are staged too
+    if (r0 >= 0) r0 = (2 * hi + 1) | kTopFlag;
+    if (r1 >= 0) r1 = (2 * hi + 2) | kTopFlag;
+  }
+  *popped = false;
+  if (h0 & h1) {
+    const bool swap = tn1 < tn0;
+    const uint2 ent = make_uint2((unsigned)(swap ? r0 : r1), __float_as_uint(swap ? tn0 : tn1));
+    if (sp < kPtStack) s_stack[sp * kPtThreads + tid] = ent; else lstack[sp - kPtStack] = ent;
+    ++sp;
+    return swap ? r1 : r0;
+  }
+  if (h0) return r0;
+  if (h1) return r1;
+  *popped = true;
+  return kDoneRef;   // the caller pops
+}
+
+extern __shared__ __align__(128) unsigned char pt_smem[];
+
+__global__ void __launch_bounds__(kPtThreads, 1)
+k_trace_persistent(const VlHeader* __restrict__ hdr, const VlNode* __restrict__ nodes, const VlNode* __restrict__ top_g,
+                   const VlTri* __restrict__ tris, const int4* __restrict__ c0, const float* __restrict__ rays,
+                   const float* __restrict__ origin, int n_traced, int width, int height, float* __restrict__ endpoints,
+                   int* __restrict__ endcolors, float* __restrict__ range, float* __restrict__ endrem,
+                   int* __restrict__ tri_id, bool zero_misses, bool prenorm, unsigned int* __restrict__ counter) {
+  VlNode* s_top = reinterpret_cast<VlNode*>(pt_smem);
+  uint2* s_stack = reinterpret_cast<uint2*>(pt_smem + 64 * (size_t)(VL_TOP_NODES + 1));
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned int lt = (1u << lane) - 1u;
+  // ---- stage the top of the tree: one thread arms the mbarrier with the byte count and issues the bulk copies
+  const unsigned int bar = smem_addr(&s_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned int)kPtTopBytes) : "memory");
+    const char* src = reinterpret_cast<const char*>(top_g);
+    for (unsigned int off = 0; off < (unsigned int)kPtTopBytes; off += 32768u) {
+      const unsigned int n = min(32768u, (unsigned int)kPtTopBytes - off);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_addr(pt_smem + off)), "l"(src + off), "r"(n), "r"(bar) : "memory");
+    }
+  }
+  {
+    unsigned int done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+    }
+  }
+  // ---- persistent warps
+  const bool grid_rays = height >= 4 && width >= 8;
+  const int tiles_x = (width + 7) >> 3, tiles_y = (height + 3) >> 2;
+  const int n_work = grid_rays ? tiles_x * tiles_y * 32 : n_traced;
+  const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
+  const int root = hdr->n_tris > 0 ? (hdr->root_ref >= 0 ? (0 | kTopFlag) : hdr->root_ref) : kDoneRef;
+  uint2 lstack[kPtLocal];
+  int r = -1, ref = kDoneRef, sp = 0;
+  float3 d = make_float3(0.f, 0.f, 0.f), inv_d = d;
+  bool odd = false;
+  Hit best;
+  best.t = 0.f; best.pos = -1; best.orig = 0; best.rem = 0.f;
+  bool more = true;
+  for (;;) {
+    const unsigned int idle = __ballot_sync(0xffffffffu, r < 0);
+    if (idle == 0xffffffffu && !more) break;
+    if (more && __popc(idle) >= kRefillIdle) {               // warp-uniform
+      const int cnt = __popc(idle);
+      int base = 0;
+      if (lane == 0) base = (int)atomicAdd(counter, (unsigned int)cnt);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (r < 0) {
+        const int idx = base + __popc(idle & lt);
+        if (idx < n_work) {
+          int rr = idx;
+          if (grid_rays) {                                     // 8 x 4 beam tiles, tile-major: neighbours stay together
+            const int tile = idx >> 5, in = idx & 31;
+            const int col = (tile % tiles_x) * 8 + (in & 7), row = (tile / tiles_x) * 4 + (in >> 3);
+            rr = (col < width && row < height) ? row * width + col : -1;
+          }
+          if (rr >= 0) {
+            r = rr;
+            d = vl_ray_dir(rays, (size_t)r, prenorm);
+            inv_d = make_float3(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));  // Ray.h:11-12
+            odd = d.x == 0.f || d.y == 0.f || d.z == 0.f || !(d.x == d.x);
+            best.t = 999999999.f;  // BVH.cpp:20
+            best.pos = -1; best.orig = 0x7fffffff; best.rem = 0.f;
+            sp = 0;
+            ref = root;
+          }
+        }
+      }
+      if (base + cnt >= n_work) more = false;
+    }
+    if (r >= 0) {
+      auto pop = [&]() -> int {
+        while (sp > 0) {
+          --sp;
+          const uint2 ent = sp < kPtStack ? s_stack[sp * kPtThreads + tid] : lstack[sp - kPtStack];
+          if (__uint_as_float(ent.y) <= best.t) return (int)ent.x;
+        }
+        return kDoneRef;
+      };
+      while (ref >= 0) {                                       // inner nodes until this lane holds a leaf (or is done)
+        bool popped;
+        int nxt = odd ? pt_node_step<true>(ref, nodes, s_top, o, inv_d, best.t, s_stack, lstack, sp, tid, &popped)
+                      : pt_node_step<false>(ref, nodes, s_top, o, inv_d, best.t, s_stack, lstack, sp, tid, &popped);
+        ref = popped ? pop() : nxt;
+      }
+      if (ref != kDoneRef) {
+        const int first = vl_leaf_first(ref), count = vl_leaf_count(ref);
+        for (int k = 0; k < count; ++k) {
+          const float4* tq = reinterpret_cast<const float4*>(tris + first + k);
+          const float4 v0 = __ldg(tq), e1 = __ldg(tq + 1), e2 = __ldg(tq + 2);
+          float t;
+          if (vl_tri_hit(v0, e1, e2, o, d, &t)) {
+            const int orig = __float_as_int(v0.w);
+            if (t < best.t || (t == best.t && orig < best.orig)) { best.t = t; best.pos = first + k; best.orig = orig; best.rem = e1.w; }
+          }
+        }
+        ref = pop();
+      }
+      if (ref == kDoneRef) {                                   // this ray is finished: write it, free the lane
+        if (best.pos >= 0) {
+          const int4 col = __ldg(c0 + best.pos);
+          endpoints[3 * (size_t)r + 0] = __fadd_rn(o.x, __fmul_rn(d.x, best.t));
+          endpoints[3 * (size_t)r + 1] = __fadd_rn(o.y, __fmul_rn(d.y, best.t));
+          endpoints[3 * (size_t)r + 2] = __fadd_rn(o.z, __fmul_rn(d.z, best.t));
+          endcolors[3 * (size_t)r + 0] = col.x;
+          endcolors[3 * (size_t)r + 1] = col.y;
+          endcolors[3 * (size_t)r + 2] = col.z;
+          endrem[r] = best.rem;
+          range[r] = best.t;
+        } else if (zero_misses) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { endpoints[3 * (size_t)r + k] = 0.f; endcolors[3 * (size_t)r + k] = 0; }
+          endrem[r] = 0.f;
+          range[r] = 0.f;
+        }
+        if (tri_id) tri_id[r] = best.pos >= 0 ? best.orig : -1;
+        r = -1;
+      }
+    }
+  }
+}
+
 int* g_debug_stats = nullptr;  // vl_debug_trace_stats(): per-ray {inner nodes visited, triangles tested}
 int g_debug_mode = 0;          // vl_debug_trace_mode(): 0 auto, 1 per-ray storage order, 2 per-ray 16x8 tiles, 4/8/16/32 packet tile width
 
@@ -382,10 +568,22 @@ int vl_trace_launch(const void* d_blob, int n_faces, const float* d_rays, const 
   int mode = g_debug_mode;
   // measured on B200 (gpurun_out/trace_stats_710.txt): per-thread stacks 0.180 ms, 8x4 packets 0.185 ms per
   // 131 072 rays over 1.05 M triangles -- packets test 1.65x the triangles, so per-thread is the default
-  if (mode == 0) mode = (flags & VL_TRACE_PACKET) ? ((height >= 4 && width >= 8) ? 8 : 32) : 2;
+  if (mode == 0) mode = (flags & VL_TRACE_PERSISTENT) ? 3 : ((flags & VL_TRACE_PACKET) ? ((height >= 4 && width >= 8) ? 8 : 32) : 2);
   VlProfScope ps(VL_ST_TRACE, stream);
   if (mode == 2 && !(height >= 4 && width >= 8)) mode = 1;
-  if (mode == 1) {
+  if (mode == 3) {   // persistent warps + ray compaction + TMA-staged top of the tree (VL_TRACE_PERSISTENT)
+    static unsigned int next_slot = 0;
+    const int sm_count = vl_sm_count();
+    VL_CUDA_CHECK(cudaFuncSetAttribute(k_trace_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPtSmemBytes));
+    unsigned int* counters = nullptr;
+    VL_CUDA_CHECK(cudaGetSymbolAddress(reinterpret_cast<void**>(&counters), g_pt_counters));
+    unsigned int* counter = counters + (next_slot++ & 63u);
+    VL_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+    const VlNode* top = reinterpret_cast<const VlNode*>(blob + L.off_top);
+    k_trace_persistent<<<sm_count, kPtThreads, kPtSmemBytes, stream>>>(hdr, nodes, top, tris, c0, d_rays, d_origin, (int)n_traced,
+                                                                      width, height, d_endpoints, d_endcolors, d_range, d_endrem,
+                                                                      d_tri_id, zm, pn, counter);
+  } else if (mode == 1) {
     const int nb = (int)((n_traced + kTraceThreads - 1) / kTraceThreads);
     k_trace<false><<<nb, kTraceThreads, 0, stream>>>(hdr, nodes, tris, c0, d_rays, d_origin, (int)n_traced, width, height,
                                                     d_endpoints, d_endcolors, d_range, d_endrem, d_tri_id, zm, pn, g_debug_stats);

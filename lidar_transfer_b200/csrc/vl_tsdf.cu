@@ -672,7 +672,7 @@ extern "C" int vl_tsdf_init(float* d_tsdf, float* d_weight, float* d_color, floa
   const bool aligned = ((((uintptr_t)d_tsdf) | ((uintptr_t)d_weight) | ((uintptr_t)d_color) | ((uintptr_t)d_rem)) & 15) == 0;
   const long long n4 = aligned ? n_voxels / 4 : 0;
   long long want = (n_voxels / 4 + kThreads - 1) / kThreads;
-  int nb = (int)(want < 1 ? 1 : (want > 148LL * 16 ? 148LL * 16 : want));
+  int nb = (int)(want < 1 ? 1 : (want > vl_sm_count() * 16LL ? vl_sm_count() * 16LL : want));
   VlProfScope ps(VL_ST_TSDF_INIT, stream);
   k_tsdf_init<<<nb, kThreads, 0, stream>>>(reinterpret_cast<float4*>(d_tsdf), reinterpret_cast<float4*>(d_weight),
                                           reinterpret_cast<float4*>(d_color), reinterpret_cast<float4*>(d_rem), n4,

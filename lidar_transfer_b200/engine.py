@@ -129,14 +129,18 @@ def _trace_outputs(n_rays, dev, out, want_ids, alloc=torch.zeros):
   return out
 
 
-def trace(bvh, rays, origin, height, out=None, want_ids=True, zero_misses=False, normalize=None):
+TRACE_PERSISTENT = 16
+
+
+def trace(bvh, rays, origin, height, out=None, want_ids=True, zero_misses=False, normalize=None, persistent=False):
   """(ii) closest-hit ray cast; the device-resident equivalent of C_Trace
   (auxiliary/raytracer/RayTracerCython.pyx:15-33 -> RayTracer.cpp:56-92).
 
   rays f32[R,3] (any length; normalised as `normalize` says, see DEFAULT_NORMALIZE), origin f32[3].  Returns dict of flat CUDA
   tensors: endpoints[3R], endcolors[3R], range[R], endrem[R] (written for hits only -- pass
   `out` to keep previous content, or zero_misses=True to have the kernel write 0 for misses)
-  and tri_id[R] (original face index, -1 = miss)."""
+  and tri_id[R] (original face index, -1 = miss).  persistent=True: the persistent-warp kernel (rays pulled from a
+  counter, warp-wide compaction, top of the tree staged in shared memory by TMA; VL_TRACE_PERSISTENT) -- same bits."""
   dev = bvh.blob.device
   rays, ray_flags = _prepare_rays(rays, normalize, dev)
   origin = _dev(origin, torch.float32, dev).reshape(-1)
@@ -145,7 +149,8 @@ def trace(bvh, rays, origin, height, out=None, want_ids=True, zero_misses=False,
   with torch.cuda.device(dev):
     check(lib().vl_trace(_ptr(bvh.blob), bvh.n_faces, _ptr(rays), _ptr(origin), n_rays, int(height),
                          _ptr(out["endpoints"]), _ptr(out["endcolors"]), _ptr(out["range"]), _ptr(out["endrem"]),
-                         _ptr(out.get("tri_id")), (TRACE_ZERO_MISSES if zero_misses else 0) | ray_flags, _stream()))
+                         _ptr(out.get("tri_id")),
+                         (TRACE_ZERO_MISSES if zero_misses else 0) | ray_flags | (TRACE_PERSISTENT if persistent else 0), _stream()))
   return out
 
 

@@ -40,10 +40,10 @@ class _Slot:
     self.busy = False
     self.inputs = None   # the mesh tensors of the scan in flight: held until it has drained (see ScanRenderer.submit)
     self.owner = None
-    # first 16 bytes of the cast workspace header (n_bad_faces, overflow, ...), copied back after every scan
+    # bytes 16..31 of the cast workspace header (n_bad_faces, overflow, ... as k_cast_resolve left them), copied back after every scan
     self.h_status = torch.zeros(4, dtype=torch.int32, pin_memory=True)
     self.h_status_np = self.h_status.numpy()
-    self.d_status = self.blob[:16].view(torch.int32)
+    self.d_status = self.blob[16:32].view(torch.int32)
     # raw handles for the single-call submission path (vl_cast_submit): events must exist before their handle does
     self.ready = torch.cuda.Event()
     self.ready.record(self.stream)

@@ -71,3 +71,25 @@ def test_host_ctrace_drop_in(engine, oracle):
   assert np.array_equal(got["range"][hit].view(np.int32), ref2["range"][hit].view(np.int32))
   assert np.array_equal(got["endpoints"].reshape(-1, 3)[hit].view(np.int32), ref2["endpoints"].reshape(-1, 3)[hit].view(np.int32))
   assert np.array_equal(got["endcolors"].reshape(-1, 3)[hit], ref2["endcolors"].reshape(-1, 3)[hit])
+
+
+@pytest.mark.parametrize("n_side,H,W,origin", [(40, 8, 64, (0, 0, 0)), (120, 64, 512, (0.5, -0.25, 0.3)), (300, 64, 2048, (0, 0, 0)),
+                                                  (60, 3, 50, (0, 0, 0)), (2, 4, 8, (0, 0, 0))])
+def test_persistent_tma_trace_is_bit_identical(engine, oracle, n_side, H, W, origin):
+  """North-star (ii) as specified -- persistent warps pulling rays from a counter, warp-wide ray compaction, the top 11
+  levels of the tree staged in shared memory by cp.async.bulk + mbarrier (k_trace_persistent, VL_TRACE_PERSISTENT) --
+  against the oracle and against the default per-ray kernel: beam grids, a ray set that is not a grid (3 x 50), a
+  two-triangle mesh whose root is a leaf, ragged tiles, rays that miss."""
+  sc = synth.make_scene(2000 + n_side, n_side=max(n_side, 2), n_boxes=4 if n_side > 10 else 0)
+  rays = oracle.create_rays(10.0, -30.0, H, W)
+  rays[::7] = np.array([0.0, 0.0, 1.0], np.float32)      # straight up: misses, and zero direction components
+  o = np.asarray(origin, np.float32)
+  ref = oracle.trace(rays, o, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE)
+  bvh = engine.Bvh(sc["verts"], sc["faces"], sc["colors"], sc["rem"])
+  a = _np(engine.trace(bvh, rays, o, H, persistent=True))
+  b = _np(engine.trace(bvh, rays, o, H))
+  _assert_bit_equal(a, b)
+  _assert_bit_equal(a, ref)
+  z = _np(engine.trace(bvh, rays, o, H, persistent=True, zero_misses=True, out={k: v for k, v in engine.trace(bvh, rays, o, H).items()}))
+  miss = ref["tri_id"] < 0
+  assert (z["range"][miss] == 0).all() and np.array_equal(z["tri_id"], ref["tri_id"])
