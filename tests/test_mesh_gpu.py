@@ -72,3 +72,21 @@ def test_all_four_sweeps_give_the_same_mesh(engine, vl, shape):
     assert a["faces"].shape[0] == b["faces"].shape[0]
     for k in ("verts", "faces", "colors", "rem"):
       assert torch.equal(a[k], b[k]), k
+
+
+def test_topology_ambiguity_is_bounded_on_the_real_scan(engine):
+  """Parity of the iso-surface against scikit-image's marching_cubes_lewiner is UNPINNED (scikit-image is absent from the
+  reference tree and from this image, its version unpinned by the reference).  What can be said: both algorithms put the
+  same vertex on every cut cube edge; they can differ in topology only in cubes with an ambiguous sign configuration.
+  tools/mesh_ambiguity.py counts those on the real scan (and checks, on the way, that the device's triangle count equals
+  the case-table count over a sign volume formed independently with torch): a few per cent of the active cubes."""
+  import importlib.util
+  import os
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  spec = importlib.util.spec_from_file_location("mesh_ambiguity", os.path.join(root, "tools", "mesh_ambiguity.py"))
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  r = mod.run(0.1)
+  assert r["triangles"] > 500000 and r["active_cubes"] > 200000
+  assert r["ambiguous_cube_fraction"] < 0.10 and r["beam_fraction"] < 0.15, r
+  assert mod.ambiguous_cases().sum() == 128
