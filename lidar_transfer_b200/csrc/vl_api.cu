@@ -6,6 +6,7 @@
 #include <string.h>
 #include <mutex>
 #include "vl_common.cuh"
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges around every stage, visible to nsys / ncu, free when no tool is attached
 
 // ---------------------------------------------------------------------------
 // error text
@@ -60,12 +61,14 @@ int vl_sm_count() {
 }
 
 void vl_prof_begin(int stage, cudaStream_t stream) {
+  nvtxRangePushA(stage >= 0 && stage < VL_ST_COUNT ? kStageNames[stage] : "vlidar");
   if (!g_prof_on.load(std::memory_order_relaxed)) return;
   cudaEvent_t e = prof_event();
   cudaEventRecord(e, stream);
   g_prof_open[stage] = e;
 }
 void vl_prof_end(int stage, cudaStream_t stream) {
+  nvtxRangePop();
   if (!g_prof_on.load(std::memory_order_relaxed) || !g_prof_open[stage]) return;
   cudaEvent_t e = prof_event();
   cudaEventRecord(e, stream);

@@ -558,6 +558,12 @@ k_emit_climb(const float* __restrict__ verts, const int* __restrict__ faces, con
       const int k = parent - B0, me = is_left ? 0 : 1;
       s_slot[k][me].a = make_float4(bmin[0], bmin[1], bmin[2], bmax[0]);
       s_slot[k][me].b = make_float4(bmax[1], bmax[2], __int_as_float(ref), __int_as_float(is_left ? l : r));
+      // Release / acquire hand-over between the two children of node k (the classic bottom-up LBVH refit): each child
+      // publishes its slot, fences, then exchanges the flag -- exactly one of them reads 1, and it is the one that ran
+      // its exchange SECOND, i.e. after the sibling's fence made the sibling's slot visible; the fence below orders its
+      // own reads after the exchange.  compute-sanitizer --tool racecheck reports the slot accesses as hazards because it
+      // orders shared-memory accesses by barriers only and does not model ordering through an atomic flag
+      // (profiles/r01_sanitizer.md); the build is bit-reproducible (tests/test_trace_edge_gpu.py::test_full_size_properties).
       __threadfence_block();
       if (atomicExch(&s_flag[k], 1) == 0) break;  // first child to arrive stops here
       __threadfence_block();

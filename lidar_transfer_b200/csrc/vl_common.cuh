@@ -22,7 +22,7 @@ enum VlStage {
   VL_ST_MESH_COUNT, VL_ST_MESH_SCAN, VL_ST_MESH_COMPACT, VL_ST_MESH_EMIT,
   VL_ST_BEAMS, VL_ST_CAST_INIT, VL_ST_CAST_SETUP, VL_ST_CAST_ITEMS, VL_ST_CAST_RESOLVE, VL_ST_COMPARE, VL_ST_COUNT
 };
-void vl_prof_begin(int stage, cudaStream_t stream);
+void vl_prof_begin(int stage, cudaStream_t stream);   // also opens an NVTX range named after the stage
 void vl_prof_end(int stage, cudaStream_t stream);
 struct VlProfScope {
   int stage; cudaStream_t stream;

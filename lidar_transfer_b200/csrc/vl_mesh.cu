@@ -618,7 +618,7 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
             float* __restrict__ rem_out, int vec_ok, const int* __restrict__ hull) {
   __shared__ unsigned int s_first[kEmitTris], s_vi[kEmitTris];
   __shared__ __align__(16) float s_v[kEmitTris * 9];
-  __shared__ float s_r[kEmitTris * 3];
+  __shared__ __align__(16) float s_r[kEmitTris * 3];
   __shared__ __align__(16) unsigned char s_c[kEmitTris * 9];
   const int tid = threadIdx.x;
   const long long T0 = (long long)blockIdx.x * kEmitTris;
@@ -708,6 +708,28 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
   }
   __syncthreads();
   const bool full = vec_ok && nT == kEmitTris;
+  if (full && !norms) {
+    // A full CTA's outputs are four contiguous, 16-byte aligned runs (9216 B of vertices, 2304 B of colours, 3072 B of
+    // remissions, 3072 B of face indices): handed to the TMA engine as bulk stores shared -> global (cp.async.bulk,
+    // UBLKCP in the SASS) by one thread instead of being copied out by all 256 in a loop.
+    __shared__ __align__(16) int s_f[kEmitTris * 3];
+    for (int i = tid; i < 3 * kEmitTris; i += kEmitTris) s_f[i] = (int)(3 * T0 + i);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the generic-proxy writes above, visible to the async proxy
+    __syncthreads();
+    if (tid == 0) {
+      auto bulk = [](void* dst, const void* src, unsigned int bytes) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(dst), "r"((unsigned int)__cvta_generic_to_shared(src)), "r"(bytes) : "memory");
+      };
+      bulk(verts + 9 * T0, s_v, kEmitTris * 9 * 4);
+      bulk(colors + 9 * T0, s_c, kEmitTris * 9);
+      bulk(rem_out + 3 * T0, s_r, kEmitTris * 3 * 4);
+      bulk(faces + 3 * T0, s_f, kEmitTris * 3 * 4);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must stay intact until it has been read
+    }
+    return;
+  }
   auto put9 = [&](float* __restrict__ dst) {                   // s_v -> 9 floats per triangle of this CTA
     if (full) {
       float4* d4 = reinterpret_cast<float4*>(dst + 9 * T0);
@@ -906,7 +928,7 @@ static int mesh_emit_impl(const float* d_tsdf, const float* d_color, const float
   else k_mesh_compact<1><<<grid, kThreads, 0, stream>>>(P, upp, cases, ut, to, ao, n_active, n_tris, list, cta_first); }
   VL_LAUNCH_CHECK("k_mesh_compact");
   VlProfScope ps(VL_ST_MESH_EMIT, stream);
-  const int vec_ok = ((((uintptr_t)d_verts) | ((uintptr_t)d_norms)) & 15) == 0 && (((uintptr_t)d_colors) & 3) == 0;
+  const int vec_ok = ((((uintptr_t)d_verts) | ((uintptr_t)d_norms) | ((uintptr_t)d_colors) | ((uintptr_t)d_rem_out) | ((uintptr_t)d_faces)) & 15) == 0;
   k_mesh_emit<<<(unsigned)((n_tris + kEmitTris - 1) / kEmitTris), kEmitTris, 0, stream>>>(
       d_tsdf, d_color, d_rem, P, list, n_active, cta_first, n_tris, d_verts, d_faces, d_norms, d_colors, d_rem_out, vec_ok, d_hull);
   VL_LAUNCH_CHECK("k_mesh_emit");
