@@ -498,7 +498,6 @@ k_tsdf_hull_sweep(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, 
   __shared__ int s_off[kHullCols + 1];
   __shared__ int s_hull[kHullCols], s_old[kHullCols];
   __shared__ int s_warp[kThreads / 32];
-  __shared__ int s_nq;
   const int n_cols = P.dx * P.dy;
   const int c0 = blockIdx.x * kHullCols;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -518,7 +517,6 @@ k_tsdf_hull_sweep(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, 
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
   if (lane == 31) s_warp[w] = incl;
-  if (threadIdx.x == 0) s_nq = 0;
   __syncthreads();
   int wbase = 0;
 #pragma unroll
@@ -527,8 +525,8 @@ k_tsdf_hull_sweep(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, 
   if (threadIdx.x == kThreads - 1) s_off[kHullCols] = wbase + incl;
   __syncthreads();
   const int total = s_off[kHullCols];
-  for (int base = 0; base < total; base += kThreads) {    // CTA-uniform
-    const int i = base + threadIdx.x;
+  for (int base = w * 32; base < total; base += kThreads) {    // warp-uniform: warp w takes groups [base, base + 32)
+    const int i = base + lane;
     unsigned int ex = 0, fresh_m = 0;
     int voxel_idx = 0;
     if (i < total) {
@@ -601,32 +599,28 @@ k_tsdf_hull_sweep(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, 
           if (init_m >> jj & 1) { tsdf_vol[voxel_idx + jj] = 1.f; weight_vol[voxel_idx + jj] = 0.f; color_vol[voxel_idx + jj] = 0.f; rem_vol[voxel_idx + jj] = 0.f; }
       }
     }
+    // the exact-path voxels of this warp's 32 groups, compacted into the warp's own queue and evaluated right away on
+    // dense lanes: no CTA barrier inside the loop (a CTA-wide queue cost 8.9 barrier-stall cycles per issue)
     if (__any_sync(0xffffffffu, ex != 0)) {
+      unsigned int* q = s_q + w * (32 * kVec);
       unsigned int m[kVec];
-      int tot = 0;
-#pragma unroll
-      for (int jj = 0; jj < kVec; ++jj) { m[jj] = __ballot_sync(0xffffffffu, ex >> jj & 1); tot += __popc(m[jj]); }
       int pos = 0;
-      if (lane == 0) pos = atomicAdd(&s_nq, tot);
-      pos = __shfl_sync(0xffffffffu, pos, 0);
 #pragma unroll
       for (int jj = 0; jj < kVec; ++jj) {
-        if (ex >> jj & 1) s_q[pos + __popc(m[jj] & lt)] = (unsigned int)(voxel_idx + jj) | ((fresh_m >> jj & 1) ? 0x80000000u : 0u);
+        m[jj] = __ballot_sync(0xffffffffu, ex >> jj & 1);
+        if (ex >> jj & 1) q[pos + __popc(m[jj] & lt)] = (unsigned int)(voxel_idx + jj) | ((fresh_m >> jj & 1) ? 0x80000000u : 0u);
         pos += __popc(m[jj]);
       }
+      __syncwarp();
+      for (int k = lane; k < pos; k += 32) {
+        const unsigned int e = q[k];
+        if (e & 0x80000000u)
+          tsdf_voxel<true, true>((int)(e & 0x7fffffffu), tsdf_vol, weight_vol, color_vol, rem_vol, P, color_im, depth_im, rem_im, col_px);
+        else
+          tsdf_voxel<true, false>((int)e, tsdf_vol, weight_vol, color_vol, rem_vol, P, color_im, depth_im, rem_im, col_px);
+      }
+      __syncwarp();
     }
-    __syncthreads();
-    const int nq = s_nq;
-    for (int k = threadIdx.x; k < nq; k += kThreads) {
-      const unsigned int q = s_q[k];
-      if (q & 0x80000000u)
-        tsdf_voxel<true, true>((int)(q & 0x7fffffffu), tsdf_vol, weight_vol, color_vol, rem_vol, P, color_im, depth_im, rem_im, col_px);
-      else
-        tsdf_voxel<true, false>((int)q, tsdf_vol, weight_vol, color_vol, rem_vol, P, color_im, depth_im, rem_im, col_px);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_nq = 0;
-    __syncthreads();
   }
 }
 
