@@ -130,9 +130,16 @@ class WorkPool {
 
  private:
   WorkPool() {
-    int want = 3;   // measured on the B200 box's host (profiles/r02_ctrace_staging.md): 0 / 1 / 2 / 3 / 4 workers -> 3.3 / 2.0 / 1.8 / 1.75 / 1.9 ms
-    if (const char* e = getenv("VLIDAR_COPY_THREADS")) want = atoi(e);
+    // workers beside the calling thread.  Measured on the B200 box's host (profiles/r02_experiments.md, 1 M-triangle scan):
+    // 0 / 1 / 2 / 3 / 5 workers -> 3.3 / 2.0 / 1.8 / 1.21 / 1.15 ms per call (the last two with non-temporal stores).
+    // Default: the process's share of the host's threads (torchrun exports LOCAL_WORLD_SIZE: one process per GPU), at most 5.
     const int hw = (int)std::thread::hardware_concurrency();
+    int local_world = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = atoi(e) > 0 ? atoi(e) : 1;
+    int want = hw > 0 ? hw / local_world - 1 : 3;
+    if (want > 5) want = 5;
+    if (want < 1) want = 1;
+    if (const char* e = getenv("VLIDAR_COPY_THREADS")) want = atoi(e);
     if (hw > 0 && want > hw - 1) want = hw - 1;
     if (want < 0) want = 0;
     n_workers_ = want;
