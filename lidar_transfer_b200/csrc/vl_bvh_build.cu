@@ -556,18 +556,30 @@ k_emit_climb(const float* __restrict__ verts, const int* __restrict__ faces, con
     if (parent >= B0 && parent < B1 && s_local[parent - B0]) {
       // ---- the whole sub-tree of `parent` lives in this CTA: the children meet in shared memory ----
       const int k = parent - B0, me = is_left ? 0 : 1;
-      s_slot[k][me].a = make_float4(bmin[0], bmin[1], bmin[2], bmax[0]);
-      s_slot[k][me].b = make_float4(bmax[1], bmax[2], __int_as_float(ref), __int_as_float(is_left ? l : r));
+      // (the slot words are written and read with shared-memory atomics: the hand-over is ordered by the flag, which
+      // racecheck cannot see -- atomic accesses are the form of this release / acquire pair that it accepts)
+      {
+        int* sw = reinterpret_cast<int*>(&s_slot[k][me]);
+        const float wv[8] = {bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], __int_as_float(ref), __int_as_float(is_left ? l : r)};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) atomicExch(sw + q, __float_as_int(wv[q]));
+      }
       // Release / acquire hand-over between the two children of node k (the classic bottom-up LBVH refit): each child
       // publishes its slot, fences, then exchanges the flag -- exactly one of them reads 1, and it is the one that ran
       // its exchange SECOND, i.e. after the sibling's fence made the sibling's slot visible; the fence below orders its
-      // own reads after the exchange.  compute-sanitizer --tool racecheck reports the slot accesses as hazards because it
-      // orders shared-memory accesses by barriers only and does not model ordering through an atomic flag
-      // (profiles/r01_sanitizer.md); the build is bit-reproducible (tests/test_trace_edge_gpu.py::test_full_size_properties).
+      // own reads after the exchange.  compute-sanitizer --tool racecheck orders shared-memory accesses by barriers only
+      // and does not model ordering through an atomic flag: with plain loads / stores on the slots it reported them as
+      // hazards (profiles/r01_sanitizer.md, r02_sanitizer.md); the build is bit-reproducible
+      // (tests/test_trace_edge_gpu.py::test_full_size_properties).
       __threadfence_block();
       if (atomicExch(&s_flag[k], 1) == 0) break;  // first child to arrive stops here
       __threadfence_block();
-      const float4 sa = s_slot[k][me ^ 1].a, sb = s_slot[k][me ^ 1].b;
+      float4 sa, sb;
+      {
+        int* sr = reinterpret_cast<int*>(&s_slot[k][me ^ 1]);
+        sa = make_float4(__int_as_float(atomicOr(sr + 0, 0)), __int_as_float(atomicOr(sr + 1, 0)), __int_as_float(atomicOr(sr + 2, 0)), __int_as_float(atomicOr(sr + 3, 0)));
+        sb = make_float4(__int_as_float(atomicOr(sr + 4, 0)), __int_as_float(atomicOr(sr + 5, 0)), __int_as_float(atomicOr(sr + 6, 0)), __int_as_float(atomicOr(sr + 7, 0)));
+      }
       const int sref = __float_as_int(sb.z);
       if (is_left) r = __float_as_int(sb.w); else l = __float_as_int(sb.w);
       const int size = r - l + 1;

@@ -365,3 +365,79 @@ def test_cast_random_configurations_vs_oracle(engine, oracle):
     _run(engine, oracle, verts, faces, rays, origin, H, lbvh=False)
 
   run()
+
+
+def test_ctrace_beam_cache_follows_the_rays_and_threads_are_serialised(engine, oracle, vl):
+  """The host entry point keeps the normalised rays + beam index of the previous call on the device: the same rays again
+  must hit the cache, different rays (same count, same pointer, content edited in place) must rebuild it, and the results
+  must be the oracle's either way; two Python threads calling at once are serialised by the library's mutex."""
+  import ctypes
+  import threading
+  sc = synth.make_scene(77, n_side=70, n_boxes=6)
+  H, W = 16, 128
+  rays = oracle.create_rays(3.0, -25.0, H, W)
+  origin = np.zeros(3, np.float32)
+  args = (origin, sc["verts"].reshape(-1), sc["faces"].reshape(-1), sc["colors"].reshape(-1), sc["rem"], H)
+
+  def stats():
+    h, m = ctypes.c_longlong(0), ctypes.c_longlong(0)
+    vl.vl_ctrace_cache_stats(ctypes.byref(h), ctypes.byref(m))
+    return h.value, m.value
+  flags = oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE
+  ref = oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, flags)
+  a = engine.ctrace_host(rays, *args, want_ids=True)
+  h0, m0 = stats()
+  b = engine.ctrace_host(rays, *args, want_ids=True)
+  h1, m1 = stats()
+  assert (h1, m1) == (h0 + 1, m0)                                       # same rays: index reused
+  assert np.array_equal(a["tri_id"], ref["tri_id"]) and np.array_equal(b["range"].view(np.int32), ref["range"].view(np.int32))
+  rays[5::3] *= np.float32(-1.0)                                         # edited in place: same buffer, new content
+  ref2 = oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, flags)
+  c = engine.ctrace_host(rays, *args, want_ids=True)
+  h2, m2 = stats()
+  assert (h2, m2) == (h1, m1 + 1)                                       # rebuilt
+  assert np.array_equal(c["tri_id"], ref2["tri_id"]) and np.array_equal(c["range"].view(np.int32), ref2["range"].view(np.int32))
+  assert not np.array_equal(ref["tri_id"], ref2["tri_id"])
+  out = [None, None]
+
+  def work(k):
+    for _ in range(5):
+      out[k] = engine.ctrace_host(rays, *args, want_ids=True)
+  ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+  [t.start() for t in ts]
+  [t.join() for t in ts]
+  for k in range(2):
+    assert np.array_equal(out[k]["tri_id"], ref2["tri_id"]) and np.array_equal(out[k]["endpoints"].view(np.int32), ref2["endpoints"].view(np.int32))
+  ieee = engine.ctrace_host(rays, *args, want_ids=True, normalize="ieee")   # the portable mode: the oracle's IEEE mode
+  ref3 = oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES)
+  assert np.array_equal(ieee["tri_id"], ref3["tri_id"]) and np.array_equal(ieee["range"].view(np.int32), ref3["range"].view(np.int32))
+  engine.ctrace_host(rays, *args, normalize="sse")                         # back to the default for the tests that follow
+
+
+def test_scan_renderer_keeps_its_inputs_alive_until_the_scan_has_drained(engine, oracle):
+  """ScanRenderer.submit() reads the caller's tensors on the slot's own stream, which the caching allocator does not know
+  about: the slot holds references until the scan has drained, so a caller that drops its mesh right after
+  submit() and immediately allocates and overwrites same-sized tensors must still get the right answer."""
+  import torch
+  from lidar_transfer_b200 import pipeline
+  H, W = 32, 512
+  rays = oracle.create_rays(10.0, -25.0, H, W)
+  origin = np.zeros(3, np.float32)
+  scenes = [synth.make_scene(900 + k, n_side=150, n_boxes=6) for k in range(3)]
+  want = [oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE) for sc in scenes]
+  mv, mf = max(s["verts"].shape[0] for s in scenes), max(s["faces"].shape[0] for s in scenes)
+  rr = pipeline.ScanRenderer(rays, origin, H, mv, mf, n_streams=3)
+  slots = []
+  for sc in scenes:
+    mesh = [torch.from_numpy(sc[k].reshape(-1)).cuda() for k in ("verts", "faces", "colors", "rem")]
+    slots.append(rr.submit(*mesh))
+    shapes = [(t.shape, t.dtype) for t in mesh]
+    del mesh                                                             # the caller lets go at once ...
+    junk = [torch.full(s, 7, dtype=d, device="cuda") for s, d in shapes]   # ... and the allocator may hand the blocks out again
+    del junk
+  for slot, ref in zip(slots, want):
+    out = slot.result()
+    assert slot.inputs is None
+    assert np.array_equal(out["tri_id"].cpu().numpy(), ref["tri_id"])
+    assert np.array_equal(out["range"].cpu().numpy().view(np.int32), ref["range"].view(np.int32))
+  rr.close()
