@@ -4,7 +4,7 @@ must contain EVERY voxel of that column that the reference's kernel string (fusi
 never-written volume -- whatever the last bits of its norm3df / asinf are -- because voxels outside the hull are never
 looked at again.  It must also be worth having (a small part of the volume).  The GPU tests hold the kernels to the
 reference's own CUDA kernel on ten configurations; this test covers the space between them, and fails when a margin is
-mutated (rows narrower than they are, no bin of slack in the range table)."""
+mutated (rows narrower than they are, a shell half as deep)."""
 import numpy as np
 from hypothesis import given, settings, strategies as st
 
@@ -39,7 +39,7 @@ def _hulls(x2d, y2d, px2d, depth_im, color_im, H, W, fov_up, fov_down, trunc, oz
   if mutate == "no_pitch_slack":
     e_p = -0.45 * fov_rad / H      # rows narrower than they are
   lo = np.where(depth_im == 0, np.inf, np.where(color_im == 0, -np.inf, depth_im)).astype(F)
-  hi = np.where(depth_im == 0, -np.inf, depth_im + trunc).astype(F)
+  hi = np.where(depth_im == 0, -np.inf, depth_im + (trunc * F(0.5) if mutate == "half_shell" else trunc)).astype(F)
   junk = (depth_im != 0) & ~np.isfinite(depth_im)
   lo[junk], hi[junk] = -np.inf, np.inf
   r = np.arange(H)
@@ -151,9 +151,9 @@ def test_hull_contains_every_voxel_the_kernel_string_would_change(seed, H, fov, 
 
 def test_the_margins_matter():
   """Each mutation of a margin lets at least one changed voxel fall outside its hull on some seed: the test has teeth.
-  (The extra voxel at each end of a hull, `no_voxel_slack`, is belt and braces on top of floor / ceil and is not needed
-  by any of these cases.)"""
-  for mutate in ("no_pitch_slack", "no_bin_slack"):
+  (The extra voxel at each end of a hull and the extra bin at each end of a range-table entry, `no_voxel_slack` /
+  `no_bin_slack`, are belt and braces on top of floor / ceil and the 1 mm offsets: none of these cases needs them.)"""
+  for mutate in ("no_pitch_slack", "half_shell"):
     caught = False
     for seed in range(40):
       for H, fov, vox in ((64, (3.0, -25.0), 0.1), (128, (22.5, -22.5), 0.05), (16, (10.67, -30.67), 0.25)):
