@@ -490,10 +490,9 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
   const int n_faces = kDescPtr ? mesh_ptr->n_faces : mesh_val.n_faces;
   __shared__ unsigned int s_mask[kFineWords];
   __shared__ int s_queue[kBatch];
-  __shared__ int s_nq;
-  __shared__ unsigned long long s_warp[kCastWarps];
+  __shared__ int s_nq, s_next;
   if (threadIdx.x < kFineWords) s_mask[threadIdx.x] = __ldg(fine_mask_g + threadIdx.x);
-  if (threadIdx.x == 0) s_nq = 0;
+  if (threadIdx.x == 0) { s_nq = 0; s_next = 0; }
   __syncthreads();
   const BeamParams P = beam_params(bhdr, cw, ch);
   const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
@@ -533,9 +532,14 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
     }
     __syncthreads();
     const int nq = s_nq;
-    // ---- setup of the survivors
-    for (int qb = 0; qb < nq; qb += kCastThreads) {
-      const int j = qb + threadIdx.x;
+    // ---- setup of the survivors: every WARP takes 32 of them at a time from the queue and reserves its records and
+    // units with its own packed atomicAdd (warp scan by shuffles) -- no block scan and no barrier inside this phase
+    for (;;) {
+      int start = 0;
+      if (lane == 0) start = atomicAdd(&s_next, 32);
+      start = __shfl_sync(0xffffffffu, start, 0);
+      if (start >= nq) break;                                   // warp-uniform
+      const int j = start + lane;
       TriRec T;
       int n_i = 0;
       if (j < nq) {
@@ -544,7 +548,6 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
         n_i = tri_setup<true>(f, i0, i1, i2, verts, o, P, s_mask, T);
       }
       const int n_u = (n_i + kUnitItems - 1) / kUnitItems;
-      // block-exclusive scan of the packed pair (1 << 36 | n_u): record position and first unit in one go
       const unsigned long long mine = n_i > 0 ? ((1ull << kUnitBits) | (unsigned long long)n_u) : 0ull;
       unsigned long long incl = mine;
 #pragma unroll
@@ -552,28 +555,15 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
         const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += u;
       }
-      if (lane == 31) s_warp[w] = incl;
-      __syncthreads();
-      if (w == 0) {
-        const unsigned long long x = lane < kCastWarps ? s_warp[lane] : 0ull;
-        unsigned long long xi = x;
-#pragma unroll
-        for (int d = 1; d < kCastWarps; d <<= 1) {
-          const unsigned long long u = __shfl_up_sync(0xffffffffu, xi, d);
-          if (lane >= d) xi += u;
-        }
-        const unsigned long long total = __shfl_sync(0xffffffffu, xi, kCastWarps - 1);
-        unsigned long long base = 0ull;
-        if (lane == 0 && total) {
-          base = atomicAdd(&chdr->reserved, total);
-          if ((base & units_mask) + (total & units_mask) > unit_cap) chdr->overflow = 1;
-        }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (lane < kCastWarps) s_warp[lane] = base + xi - x;
+      const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+      unsigned long long base = 0ull;
+      if (lane == 0 && total) {
+        base = atomicAdd(&chdr->reserved, total);
+        if ((base & units_mask) + (total & units_mask) > unit_cap) chdr->overflow = 1;
       }
-      __syncthreads();
+      base = __shfl_sync(0xffffffffu, base, 0);
       if (n_i > 0) {
-        const unsigned long long at = s_warp[w] + incl - mine;
+        const unsigned long long at = base + incl - mine;
         const int pos = (int)(at >> kUnitBits);
         const unsigned long long u0 = at & units_mask;
         if (pos < rec_cap && u0 + (unsigned long long)n_u <= unit_cap) {   // always, unless the unit list overflowed
@@ -583,17 +573,13 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
           r[2] = make_float4(T.e2z, __int_as_float(T.orig), T.ymid, T.yhalf);
           r[3] = make_float4(T.slo, T.shi, __int_as_float(T.ca | (T.ncx << 16) | (T.ncx > kWideCols ? (1 << 30) : 0)),
                              __int_as_float(T.ra | (T.ncy << 16)));
-          // the owner writes its own units (2 on average; the issue slots of a cooperative, coalesced writer cost more
-          // than these scattered 8-byte stores when several scans share the SMs)
           for (int k = 0; k < n_u; ++k) units[u0 + k] = make_int2(pos, k * kUnitItems);
         }
       }
-      __syncthreads();   // s_warp is reused by the next pass
     }
-    if (nq > 0) {   // (with nq == 0 there was no barrier since the read above, and nothing to reset)
-      if (threadIdx.x == 0) s_nq = 0;
-      __syncthreads();
-    }
+    __syncthreads();   // the queue is reused by the next batch
+    if (threadIdx.x == 0) { s_nq = 0; s_next = 0; }
+    __syncthreads();
   }
   if (n_bad) atomicAdd(&chdr->n_bad_faces, n_bad);
 }
