@@ -527,6 +527,14 @@ def run_native(args):
   L.vl_ctrace_timing(phase)
   hits_c, miss_c = ctypes.c_longlong(0), ctypes.c_longlong(0)
   L.vl_ctrace_cache_stats(ctypes.byref(hits_c), ctypes.byref(miss_c))
+  wire_bytes = []
+  for k in range(M):   # outside the timed region: what one call per distinct mesh moves over PCIe
+    v, f, c, r = np_scenes[k]
+    rtc.C_Trace(rays_flat, origin, v, f, c, r, np.zeros(3 * R, np.float32), np.zeros(3 * R, np.int32), np.zeros(R, np.float32),
+                np.zeros(R, np.float32), H, W)
+    up, down = ctypes.c_longlong(0), ctypes.c_longlong(0)
+    L.vl_ctrace_traffic(ctypes.byref(up), ctypes.byref(down))
+    wire_bytes.append((up.value, down.value))
 
   # per-kernel durations: the distinct scans again with the library's event profiler on (events are recorded on the
   # launching stream; kept out of the headline timing because each record costs host time per launch)
@@ -576,8 +584,10 @@ def run_native(args):
   value = S * R * world * K / (ms_dev * 1e-3) / 1e6
   e2e_value = Se * R * world * K / (ms_e2e * 1e-3) / 1e6
   pipe_value = Sp * R * world * K / (ms_pipe * 1e-3) / 1e6
-  h2d = sum(mesh_bytes[k % M] for k in range(Se))   # per rank per step, through the plugin call
-  d2h = Se * R * (12 + 12 + 4 + 4 + 4)              # the packed results incl. the hit ids the merge reads
+  # bytes the plugin call moves per rank per step, as the library counted them (vl_ctrace_traffic): the staging copy packs
+  # faces / colours, of the results the end points are recomputed on the host (include/vlidar.h: vl_ctrace_wire)
+  h2d = sum(wire_bytes[k % M][0] for k in range(Se))
+  d2h = sum(wire_bytes[k % M][1] for k in range(Se))
   peak, peak_src = _peaks()
 
   # roofline of the dominant kernel.  COMPULSORY bytes per launch: every input once + every output once; records and
@@ -649,7 +659,9 @@ def run_native(args):
               "api": "auxiliary.raytracer.RayTracerCython.C_Trace -> extern \"C\" ctrace (include/vlidar.h) on pageable numpy "
                      "buffers, one synchronous call per scan, outputs zero-filled by the caller (fusion_lidar.py:440-450)",
               "timer": "host wall clock around synchronous calls, max over ranks",
-              "last_call_phase_ms": {"ray_compare_beam_cache": phase[0], "stage_and_h2d_issue": phase[1], "cast_and_d2h_wait": phase[2],
+              "caller_bytes_per_scan": {"mesh_in": mesh_bytes[0], "results_out": 32 * R},
+              "wire": "staging copy packs faces (3 x 21 bit) and colours (3 x u8); end points recomputed on the host from the range",
+              "last_call_phase_ms": {"beam_index_rebuild": phase[0], "stage_raycompare_h2d_issue": phase[1], "cast_and_d2h_wait": phase[2],
                                      "merge_hits": phase[3]},
               "beam_cache": {"hits": hits_c.value, "rebuilds": miss_c.value},
               "hit_fraction": float((last_rg > 0).mean())},

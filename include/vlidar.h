@@ -180,9 +180,17 @@ void vl_ctrace_method(int method);
 void vl_ctrace_normalize(int mode);
 /* How often ctrace found the previous call's rays again (beam index reused) / had to rebuild it. */
 void vl_ctrace_cache_stats(long long* hits, long long* misses);
-/* Host wall time (ms) of the phases of the most recent ctrace: [0] ray comparison / beam index, [1] staging of the
- * mesh + host->device issue, [2] cast + device->host (wait), [3] merge of the hits into the caller's buffers. */
+/* Host wall time (ms) of the phases of the most recent ctrace: [0] beam index (re)build, [1] staging of the mesh
+ * (+ comparison of the rays with the cached sensor) + host->device issue, [2] cast + device->host (wait), [3] merge of the
+ * hits into the caller's buffers. */
 void vl_ctrace_timing(double* ms4);
+/* How the mesh of a ctrace call crosses PCIe: 1 (default) = packed by the staging copy (faces 3 x 21 bits in 8 B when
+ * n_verts <= 2^21, colours 3 B per vertex when every component is in 0 .. 255, anything that does not fit travels raw;
+ * of the results the end points stay on the device and are recomputed on the host as o + d * t from the unit directions
+ * the host made itself, BVH.cpp:106-107), 0 = every array as the caller holds it.  Same results either way.  Process-wide. */
+void vl_ctrace_wire(int packed);
+/* Bytes the most recent ctrace moved host->device / device->host. */
+void vl_ctrace_traffic(long long* h2d_bytes, long long* d2h_bytes);
 
 /* Test aid: same outputs by testing every triangle per ray (no BVH). */
 int vl_trace_bruteforce(const float* d_verts, const int* d_faces, const int* d_colors,

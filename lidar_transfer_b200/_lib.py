@@ -39,6 +39,8 @@ SIGNATURES = {
     "vl_ctrace_normalize": (None, [_i]),
     "vl_ctrace_cache_stats": (None, [_vp, _vp]),
     "vl_ctrace_timing": (None, [_vp]),
+    "vl_ctrace_wire": (None, [_i]),
+    "vl_ctrace_traffic": (None, [_vp, _vp]),
     "vl_cast_workspace_bytes": (_sz, [_i, _i]),
     "vl_cast": (_i, [_vp] * 5 + [_i, _i, _vp, _i, _i] + [_vp] * 5 + [_i, _vp, _sz, _vp]),
     "vl_cast_status": (_i, [_vp, _vp, _vp]),

@@ -791,9 +791,11 @@ int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_b
 // mesh of a stream slot for a graph); mesh is read from `d_desc` when by_ptr (graph replay) and passed by value otherwise.
 static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr, int cap_faces, const float* d_origin,
                         int n_rays, int height, float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem,
-                        int* d_tri_id, int flags, void* d_ws, cudaStream_t stream, bool init, bool rearm) {
+                        int* d_tri_id, int flags, void* d_ws, cudaStream_t stream, bool init, bool rearm,
+                        int phases = VL_CAST_PHASE_FRONT | VL_CAST_PHASE_RESOLVE) {
   const BeamLayout L = beam_layout(n_rays, height);
-  if (d_tri_id && n_rays > L.n)   // rays beyond width * height are never cast (RayTracer.cpp:56)
+  const bool front = (phases & VL_CAST_PHASE_FRONT) != 0, back = (phases & VL_CAST_PHASE_RESOLVE) != 0;
+  if (back && d_tri_id && n_rays > L.n)   // rays beyond width * height are never cast (RayTracer.cpp:56)
     VL_CUDA_CHECK(cudaMemsetAsync(d_tri_id + L.n, 0xff, sizeof(int) * (size_t)(n_rays - L.n), stream));
   if (L.n <= 0) return VL_OK;
   const char* B = static_cast<const char*>(d_beams);
@@ -811,12 +813,12 @@ static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr
   int2* units = reinterpret_cast<int2*>(Wk + C.off_units);
   float4* recs = reinterpret_cast<float4*>(Wk + C.off_recs);
   const int rec_cap = cap_faces > 0 ? cap_faces : 1;
-  if (init) {
+  if (init && front) {
     VlProfScope ps(VL_ST_CAST_INIT, stream);
     k_cast_init<<<vl_sm_count(), 256, 0, stream>>>(best, L.n, chdr);
     VL_LAUNCH_CHECK("k_cast_init");
   }
-  if (by_ptr || mesh.n_faces > 0) {
+  if (front && (by_ptr || mesh.n_faces > 0)) {
     {
       VlProfScope ps(VL_ST_CAST_SETUP, stream);
       const int n_batches = ((by_ptr ? cap_faces : mesh.n_faces) + kBatch - 1) / kBatch;
@@ -837,7 +839,7 @@ static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr
       VL_LAUNCH_CHECK("k_cast_units");
     }
   }
-  {
+  if (back) {
     VlProfScope ps(VL_ST_CAST_RESOLVE, stream);
     const int nb = (L.n + kCastThreads - 1) / kCastThreads;
     const bool zm = (flags & VL_TRACE_ZERO_MISSES) != 0, c8 = (flags & VL_COLORS_U8) != 0;
@@ -855,12 +857,12 @@ static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr
 int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces, const int* d_colors,
                    const float* d_rem, int n_verts, int n_faces, const float* d_origin, int n_rays, int height,
                    float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id, int flags,
-                   void* d_ws, cudaStream_t stream) {
+                   void* d_ws, cudaStream_t stream, int phases) {
   VlMeshDesc mesh = {};
   mesh.verts = d_verts; mesh.faces = d_faces; mesh.colors = d_colors; mesh.rem = d_rem;
   mesh.n_verts = n_verts; mesh.n_faces = n_faces;
   return cast_enqueue(d_beams, mesh, false, n_faces, d_origin, n_rays, height, d_endpoints, d_endcolors, d_range, d_endrem,
-                      d_tri_id, flags, d_ws, stream, true, false);
+                      d_tri_id, flags, d_ws, stream, true, false, phases);
 }
 
 // ---------------------------------------------------------------------------

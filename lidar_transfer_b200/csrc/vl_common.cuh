@@ -219,7 +219,11 @@ int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_b
 int vl_cast_launch(const void* d_beams, const float* d_verts, const int* d_faces, const int* d_colors,
                    const float* d_rem, int n_verts, int n_faces, const float* d_origin, int n_rays, int height,
                    float* d_endpoints, int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id, int flags,
-                   void* d_ws, cudaStream_t stream);
+                   void* d_ws, cudaStream_t stream, int phases = 3);
+// phases of one cast: FRONT = reset + setup + units (needs verts and faces only), RESOLVE = the write-back (needs the
+// colours and remissions too) -- the host-pointer ctrace launches the front while the colours are still on their way
+#define VL_CAST_PHASE_FRONT 1
+#define VL_CAST_PHASE_RESOLVE 2
 int vl_cast_status_read(const void* d_ws, cudaStream_t stream, int* info);
 int vl_cast_graph_create_impl(const void* d_beams, const float* d_origin, int n_rays, int height, float* d_endpoints,
                               int* d_endcolors, float* d_range, float* d_endrem, int* d_tri_id, int flags, void* d_ws,

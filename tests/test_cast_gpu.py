@@ -441,3 +441,92 @@ def test_scan_renderer_keeps_its_inputs_alive_until_the_scan_has_drained(engine,
     assert np.array_equal(out["tri_id"].cpu().numpy(), ref["tri_id"])
     assert np.array_equal(out["range"].cpu().numpy().view(np.int32), ref["range"].view(np.int32))
   rr.close()
+
+
+def _ctrace_out(n, fill=7):
+  return dict(endpoints=np.full(3 * n, fill, np.float32), endcolors=np.full(3 * n, fill, np.int32),
+              range=np.full(n, fill, np.float32), endrem=np.full(n, fill, np.float32))
+
+
+@pytest.mark.parametrize("method", ["cast", "lbvh"])
+def test_ctrace_wire_formats_do_not_change_a_bit(engine, oracle, vl, method):
+  """The staging copy of ctrace packs what crosses PCIe (faces 3 x 21 bits, colours 3 bytes, end points recomputed on the
+  host from the range): packed and raw calls must produce the same bytes in the caller's buffers -- hits and untouched
+  misses -- and both must be the oracle's, on a ray count that is not a multiple of the height."""
+  import ctypes
+  sc = synth.make_scene(31, n_side=90, n_boxes=8)
+  H, W = 16, 200
+  rays = np.ascontiguousarray(np.concatenate([oracle.create_rays(25.0, -25.0, H, W), np.array([[0, 0, -1]] * 5, np.float32)]))
+  origin = np.array([0.5, -1.25, 0.25], np.float32)
+  n = rays.shape[0]
+  ref = oracle.trace(rays, origin, sc["verts"], sc["faces"], sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE)
+  args = (origin, sc["verts"].reshape(-1), sc["faces"].reshape(-1), sc["colors"].reshape(-1), sc["rem"], H)
+  got, traffic = {}, {}
+  try:
+    for wire in (1, 0):
+      vl.vl_ctrace_wire(wire)
+      got[wire] = engine.ctrace_host(rays, *args, outputs=_ctrace_out(n), want_ids=True, method=method)
+      a, b = ctypes.c_longlong(0), ctypes.c_longlong(0)
+      vl.vl_ctrace_traffic(ctypes.byref(a), ctypes.byref(b))
+      traffic[wire] = (a.value, b.value)
+  finally:
+    vl.vl_ctrace_wire(1)
+    engine.ctrace_host(rays[:H], *args, method="cast")
+  miss = ref["tri_id"] < 0
+  assert 0.05 < miss.mean() < 0.95 and miss[H * W:].all()        # the five rays beyond width * height are never cast
+  for wire in (1, 0):
+    assert np.array_equal(got[wire]["tri_id"], ref["tri_id"])
+    hit = ~miss
+    for k, c in (("range", 1), ("endrem", 1), ("endpoints", 3), ("endcolors", 3)):
+      x, y = got[wire][k].reshape(-1, c).view(np.int32), np.asarray(ref[k]).reshape(-1, c).view(np.int32)
+      assert np.array_equal(x[hit], y[hit]), (wire, k)
+      assert (got[wire][k].reshape(-1, c)[miss] == 7).all(), (wire, k)   # hits only (RayTracer.cpp:72-90)
+  assert traffic[1][0] < 0.72 * traffic[0][0] and traffic[1][1] < 0.7 * traffic[0][1], traffic
+
+
+def test_ctrace_arrays_that_do_not_fit_the_wire_formats_travel_raw(engine, oracle, vl):
+  """Colour components outside 0 .. 255 (the reference passes them through float, RayTracer.cpp:36-48), meshes with more
+  than 2^21 vertices and face indices that no 21-bit field holds must give the raw path's results."""
+  from lidar_transfer_b200._lib import VlidarError, VL_EBADMESH
+  sc = synth.make_scene(32, n_side=50, n_boxes=4)
+  H, W = 8, 128
+  rays = oracle.create_rays(3.0, -25.0, H, W)
+  origin = np.zeros(3, np.float32)
+  flags = oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE
+  verts, faces, rem = sc["verts"], sc["faces"], sc["rem"]
+  # (a) colours: negative, > 255 and beyond float's integer range
+  colors = sc["colors"].copy()
+  colors[::3, 0] = -5
+  colors[1::3, 1] = 70000
+  colors[2::3, 2] = 16777217
+  ref = oracle.trace(rays, origin, verts, faces, colors, rem, H, flags)
+  for method in ("cast", "lbvh"):
+    got = engine.ctrace_host(rays, origin, verts.reshape(-1), faces.reshape(-1), colors.reshape(-1), rem, H, want_ids=True, method=method)
+    assert np.array_equal(got["tri_id"], ref["tri_id"]) and np.array_equal(got["endcolors"], ref["endcolors"].reshape(-1)), method
+    assert (got["endcolors"].reshape(-1, 3)[ref["tri_id"] >= 0].max(axis=0) > 255).any()
+  # (b) more than 2^21 vertices: the faces travel as int32 triples; the mesh's own vertices sit at the END of the array
+  pad = (1 << 21) + 17
+  big_v = np.concatenate([np.zeros((pad, 3), np.float32), verts])
+  big_c = np.concatenate([np.zeros((pad, 3), np.int32), sc["colors"]])
+  big_r = np.concatenate([np.zeros(pad, np.float32), rem])
+  big_f = (faces + pad).astype(np.int32)
+  ref_b = oracle.trace(rays, origin, verts, faces, sc["colors"], rem, H, flags)
+  got = engine.ctrace_host(rays, origin, big_v.reshape(-1), big_f.reshape(-1), big_c.reshape(-1), big_r, H, want_ids=True, method="cast")
+  _same(got, ref_b, what="ctrace, 2^21 + vertices")
+  # (c) a face index no 21-bit field holds (and a negative one): bad faces, skipped and reported; the others are cast
+  bad_f = faces.copy()
+  bad_f[3, 1] = 1 << 22
+  bad_f[10, 0] = -2
+  keep = np.ones(faces.shape[0], bool)
+  keep[[3, 10]] = False
+  ref_c = oracle.trace(rays, origin, verts, faces[keep], sc["colors"], rem, H, flags)
+  ids = np.flatnonzero(keep).astype(np.int32)
+  out = _ctrace_out(H * W, 0)
+  tri = np.empty(H * W, np.int32)
+  p = lambda a: a.ctypes.data
+  rc = vl.vl_ctrace_ids(p(rays), p(origin), p(verts), p(bad_f), p(sc["colors"]), p(rem), H * W, verts.shape[0], bad_f.shape[0], H,
+                        p(out["endpoints"]), p(out["endcolors"]), p(out["range"]), p(out["endrem"]), p(tri))
+  assert rc == VL_EBADMESH
+  want = np.where(ref_c["tri_id"] >= 0, ids[np.maximum(ref_c["tri_id"], 0)], -1)
+  assert np.array_equal(tri, want) and np.array_equal(out["range"].view(np.int32), ref_c["range"].view(np.int32))
+  engine.ctrace_host(rays, origin, verts.reshape(-1), faces.reshape(-1), sc["colors"].reshape(-1), rem, H)   # and the library carries on
