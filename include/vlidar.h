@@ -387,6 +387,9 @@ void        vl_debug_mesh_scalar(int on);
 void        vl_debug_cast_cells(int cells_per_beam_row);
 /* Debug: 1 = graphs created from now on have no reset kernel (k_cast_resolve re-arms the slot), 0 (default) = k_cast_init per scan. */
 void        vl_debug_cast_rearm(int on);
+/* Debug: 1 (default) = a triangle's rectangle drops the cell rows at both ends none of whose beams lies inside its sine
+ * interval (exact: the comparison k_cast_units makes per beam), 0 = every cell row the interval touches (A/B aid). */
+void        vl_debug_cast_row_trim(int on);
 /* Debug: persistent CTAs per SM of the item kernel (default 4). */
 void        vl_debug_cast_ctas(int ctas_per_sm);
 /* Debug: persistent CTAs per SM of the setup kernel (default 4). */

@@ -82,7 +82,7 @@ constexpr size_t kDescOffset = 128;   // device copy of the descriptor inside th
 struct BeamLayout {
   int n;        // rays cast = width * height (RayTracer.cpp:56)
   int cw, ch;   // direction cells: yaw x sine
-  size_t off_dir, off_sorted, off_slot_of, off_cell_start, off_cursor, off_fine, off_mask, off_blk, total;
+  size_t off_dir, off_sorted, off_slot_of, off_cell_start, off_cursor, off_fine, off_mask, off_blk, off_rowlim, total;
 };
 
 int g_cells_per_row = 1;   // cell rows per beam row (vl_debug_cast_cells)
@@ -91,6 +91,7 @@ int g_cells_per_row = 1;   // cell rows per beam row (vl_debug_cast_cells)
 // step is 15 % slower (2720 vs 3136 Mrays/s at 8 streams, A/B on one box) -- kept as a switch, off.
 int g_graph_rearm = 0;
 int g_items_ctas_per_sm = 4;
+int g_row_trim = 1;          // vl_debug_cast_row_trim: 0 = rectangles keep every cell row their sine interval touches (A/B aid)
 int g_setup_ctas_per_sm = VL_SETUP_MINB_DEFAULT;
 
 BeamLayout beam_layout(int n_rays, int height) {
@@ -114,6 +115,7 @@ BeamLayout beam_layout(int n_rays, int height) {
   L.off_fine = off;       off = vl_align256(off + 4 * kFineBins);
   L.off_mask = off;       off = vl_align256(off + 4 * kFineWords);
   L.off_blk = off;        off = vl_align256(off + 4 * (ncell / 4096 + 1));
+  L.off_rowlim = off;     off = vl_align256(off + 8 * (size_t)L.ch);   // per cell row: smallest / largest sine of its beams (ordered uints)
   L.total = off;
   return L;
 }
@@ -164,9 +166,10 @@ __device__ __forceinline__ bool fine_any(const unsigned int* __restrict__ m, int
 // ---------------------------------------------------------------------------
 // beam index (once per sensor / ray set)
 // ---------------------------------------------------------------------------
-__global__ void k_beam_init(VlBeamHeader* hdr, int* cell_cnt, int ncell_p1, int* fine) {
+__global__ void k_beam_init(VlBeamHeader* hdr, int* cell_cnt, int ncell_p1, int* fine, uint2* row_lim, int ch) {
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncell_p1; i += stride) cell_cnt[i] = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ch; i += stride) row_lim[i] = make_uint2(0xffffffffu, 0u);   // empty row
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kFineBins; i += stride) fine[i] = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) { hdr->sine_min_ord = 0xffffffffu; hdr->sine_max_ord = 0u; hdr->n_binned = 0; }
 }
@@ -217,13 +220,19 @@ __device__ __forceinline__ int ray_cell(const float4 d, const BeamParams& P) {
 
 __global__ void __launch_bounds__(kCastThreads)
 k_beam_count(const float4* __restrict__ dir, int n, const VlBeamHeader* __restrict__ hdr, int cw, int ch,
-             int* __restrict__ cell_cnt, int* __restrict__ fine) {
+             int* __restrict__ cell_cnt, int* __restrict__ fine, uint2* __restrict__ row_lim) {
   const int r = blockIdx.x * kCastThreads + threadIdx.x;
   if (r >= n) return;
   const float4 d = dir[r];
   if (!(d.w == d.w)) return;
   const BeamParams P = beam_params(hdr, cw, ch);
   atomicAdd(&cell_cnt[ray_cell(d, P)], 1);
+  {   // sine range of the beams of this cell row (tri_setup trims the rows at both ends of a rectangle with it)
+    const int row = row_of(d.z, P);
+    const unsigned int ord = vl_float_to_ordered(d.z);
+    atomicMin(&row_lim[row].x, ord);
+    atomicMax(&row_lim[row].y, ord);
+  }
   // the rays of one beam row share a fine bin: one atomic per group of equal bins in the warp
   const int bin = fine_of(d.z, P);
   const unsigned int peers = __match_any_sync(__activemask(), bin);
@@ -333,7 +342,8 @@ struct TriRec {
 // cells of one cell row; 0 = no beam can hit it).
 template <bool kFull>
 __device__ __forceinline__ int tri_setup(int f, int i0, int i1, int i2, const float* __restrict__ verts, const float3 o,
-                                         const BeamParams& P, const unsigned int* __restrict__ fine_mask, TriRec& T) {
+                                         const BeamParams& P, const unsigned int* __restrict__ fine_mask,
+                                         const uint2* __restrict__ row_lim, TriRec& T) {
   const float ax = __ldg(verts + 3 * (size_t)i0), ay = __ldg(verts + 3 * (size_t)i0 + 1), az = __ldg(verts + 3 * (size_t)i0 + 2);
   const float bx = __ldg(verts + 3 * (size_t)i1), by = __ldg(verts + 3 * (size_t)i1 + 1), bz = __ldg(verts + 3 * (size_t)i1 + 2);
   const float cx = __ldg(verts + 3 * (size_t)i2), cy = __ldg(verts + 3 * (size_t)i2 + 1), cz = __ldg(verts + 3 * (size_t)i2 + 2);
@@ -400,8 +410,18 @@ __device__ __forceinline__ int tri_setup(int f, int i0, int i1, int i2, const fl
   T.e2x = __fsub_rn(cx, ax); T.e2y = __fsub_rn(cy, ay); T.e2z = __fsub_rn(cz, az);
   T.orig = f;
   T.slo = slo; T.shi = shi;
-  T.ra = row_of(slo, P);
-  T.ncy = row_of(shi, P) - T.ra + 1;
+  // cell rows of the sine interval, trimmed at both ends by rows none of whose beams lies inside it (the same
+  // comparison on the same values as the per-beam filter of k_cast_units: an exact saving, half the candidates of a
+  // typical LiDAR triangle, whose interval is narrower than a cell row and straddles a row boundary)
+  int ra = row_of(slo, P), rb = row_of(shi, P);
+  if (row_lim) {
+    // float comparisons, as the filter's (an empty row decodes to NaN limits and fails both)
+    for (; ra <= rb; ++ra) { const uint2 l = __ldg(row_lim + ra); if (vl_ordered_to_float(l.y) >= slo && vl_ordered_to_float(l.x) <= shi) break; }
+    for (; rb > ra; --rb) { const uint2 l = __ldg(row_lim + rb); if (vl_ordered_to_float(l.y) >= slo && vl_ordered_to_float(l.x) <= shi) break; }
+    if (ra > rb) return 0;
+  }
+  T.ra = ra;
+  T.ncy = rb - ra + 1;
   if (all_yaw) {
     T.ca = 0; T.ncx = P.cw; T.ymid = 0.f; T.yhalf = -1.f;
   } else {
@@ -483,7 +503,7 @@ __global__ void __launch_bounds__(kCastThreads, VL_SETUP_MINB)
 k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsigned int* __restrict__ fine_mask_g,
              const VlMeshDesc mesh_val, const VlMeshDesc* __restrict__ mesh_ptr,
              const float* __restrict__ origin, VlCastHeader* chdr, float4* __restrict__ recs, int rec_cap,
-             int2* __restrict__ units, unsigned long long unit_cap) {
+             int2* __restrict__ units, unsigned long long unit_cap, const uint2* __restrict__ row_lim) {
   const float* __restrict__ verts = kDescPtr ? mesh_ptr->verts : mesh_val.verts;
   const int* __restrict__ faces = kDescPtr ? mesh_ptr->faces : mesh_val.faces;
   const int n_verts = kDescPtr ? mesh_ptr->n_verts : mesh_val.n_verts;
@@ -545,7 +565,7 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
       if (j < nq) {
         const int f = s_queue[j];
         const int i0 = __ldg(faces + 3 * (size_t)f), i1 = __ldg(faces + 3 * (size_t)f + 1), i2 = __ldg(faces + 3 * (size_t)f + 2);
-        n_i = tri_setup<true>(f, i0, i1, i2, verts, o, P, s_mask, T);
+        n_i = tri_setup<true>(f, i0, i1, i2, verts, o, P, s_mask, row_lim, T);
       }
       const int n_u = (n_i + kUnitItems - 1) / kUnitItems;
       const unsigned long long mine = n_i > 0 ? ((1ull << kUnitBits) | (unsigned long long)n_u) : 0ull;
@@ -729,6 +749,7 @@ k_cast_resolve(unsigned long long* best, int n, const float4* __restrict__ dir,
 
 extern "C" void vl_debug_cast_rearm(int on) { g_graph_rearm = on ? 1 : 0; }
 extern "C" void vl_debug_cast_cells(int cells_per_beam_row) { g_cells_per_row = cells_per_beam_row < 1 ? 1 : cells_per_beam_row; }
+extern "C" void vl_debug_cast_row_trim(int on) { g_row_trim = on ? 1 : 0; }
 extern "C" void vl_debug_cast_ctas(int ctas_per_sm) { g_items_ctas_per_sm = ctas_per_sm < 1 ? 1 : ctas_per_sm; }
 extern "C" void vl_debug_cast_setup_ctas(int ctas_per_sm) { g_setup_ctas_per_sm = ctas_per_sm < 1 ? 1 : ctas_per_sm; }
 
@@ -764,13 +785,14 @@ int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_b
   int* blk_sum = reinterpret_cast<int*>(B + L.off_blk);
   const int ncell = L.cw * L.ch;
   VlProfScope ps(VL_ST_BEAMS, stream);
-  k_beam_init<<<vl_sm_count(), 256, 0, stream>>>(hdr, cell_start, ncell + 1, fine);
+  uint2* row_lim = reinterpret_cast<uint2*>(B + L.off_rowlim);
+  k_beam_init<<<vl_sm_count(), 256, 0, stream>>>(hdr, cell_start, ncell + 1, fine, row_lim, L.ch);
   VL_LAUNCH_CHECK("k_beam_init");
   const int nb = (L.n + kCastThreads - 1) / kCastThreads;
   if (L.n > 0) {
     k_beam_prep<<<nb, kCastThreads, 0, stream>>>(d_rays, L.n, (flags & VL_RAYS_NORMALIZED) != 0, dir, hdr);
     VL_LAUNCH_CHECK("k_beam_prep");
-    k_beam_count<<<nb, kCastThreads, 0, stream>>>(dir, L.n, hdr, L.cw, L.ch, cell_start, fine);
+    k_beam_count<<<nb, kCastThreads, 0, stream>>>(dir, L.n, hdr, L.cw, L.ch, cell_start, fine, row_lim);
     VL_LAUNCH_CHECK("k_beam_count");
   }
   const int nblk = (ncell + kScanBlock - 1) / kScanBlock;
@@ -805,6 +827,7 @@ static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr
   const int* slot_of = reinterpret_cast<const int*>(B + L.off_slot_of);
   const int* cell_start = reinterpret_cast<const int*>(B + L.off_cell_start);
   const unsigned int* fine_mask = reinterpret_cast<const unsigned int*>(B + L.off_mask);
+  const uint2* row_lim = g_row_trim ? reinterpret_cast<const uint2*>(B + L.off_rowlim) : nullptr;
   char* Wk = static_cast<char*>(d_ws);
   const CastLayout C = cast_layout(n_rays, cap_faces);
   VlCastHeader* chdr = reinterpret_cast<VlCastHeader*>(Wk);
@@ -826,10 +849,10 @@ static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr
       const int nb = n_batches < cap ? (n_batches > 0 ? n_batches : 1) : cap;
       if (by_ptr)
         k_cast_setup<true><<<nb, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, mesh, d_desc, d_origin, chdr, recs,
-                                                           rec_cap, units, C.unit_cap);
+                                                           rec_cap, units, C.unit_cap, row_lim);
       else
         k_cast_setup<false><<<nb, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, mesh, d_desc, d_origin, chdr, recs,
-                                                            rec_cap, units, C.unit_cap);
+                                                            rec_cap, units, C.unit_cap, row_lim);
       VL_LAUNCH_CHECK("k_cast_setup");
     }
     {
