@@ -36,8 +36,7 @@ namespace {
 
 constexpr int kCastThreads = 256;
 constexpr int kCastWarps = kCastThreads / 32;
-constexpr int kFineBins = 4096;     // fine sin(elevation) occupancy bitmap for the arithmetic early-out
-constexpr int kFineWords = kFineBins / 32;
+constexpr int kFineBins = 4096;     // fine sin(elevation) bins of the next-beam-sine table (the arithmetic early-out)
 constexpr int kSegShift = 3;        // an item is one run of <= 8 cells of one cell row ...
 constexpr int kSegShiftWide = 6;    // ... or of <= 64 cells for a triangle wider than kWideCols (bounds the unit count)
 constexpr int kWideCols = 128;
@@ -113,7 +112,7 @@ BeamLayout beam_layout(int n_rays, int height) {
   L.off_cell_start = off; off = vl_align256(off + 4 * (ncell + 1));
   L.off_cursor = off;     off = vl_align256(off + 4 * ncell);
   L.off_fine = off;       off = vl_align256(off + 4 * kFineBins);
-  L.off_mask = off;       off = vl_align256(off + 4 * kFineWords);
+  L.off_mask = off;       off = vl_align256(off + 4 * kFineBins);   // next-beam-sine table (floats), see beam_in
   L.off_blk = off;        off = vl_align256(off + 4 * (ncell / 4096 + 1));
   L.off_rowlim = off;     off = vl_align256(off + 8 * (size_t)L.ch);   // per cell row: smallest / largest sine of its beams (ordered uints)
   L.total = off;
@@ -154,13 +153,12 @@ __device__ __forceinline__ float pseudo_yaw(float y, float x) {
 }
 __device__ __forceinline__ float wrap_2(float x) { return x - 4.f * rintf(x * 0.25f); }
 
-// any beam row in fine bins b0..b1 ?
-__device__ __forceinline__ bool fine_any(const unsigned int* __restrict__ m, int b0, int b1) {
-  const int w0 = b0 >> 5, w1 = b1 >> 5;
-  const unsigned int lo_mask = 0xffffffffu << (b0 & 31), hi_mask = 0xffffffffu >> (31 - (b1 & 31));
-  if (w0 == w1) return (m[w0] & lo_mask & hi_mask) != 0u;
-  // an interval that spans a whole 32-bin word is not examined further: "maybe" is always a valid answer
-  return w1 - w0 > 1 || ((m[w0] & lo_mask) | (m[w1] & hi_mask)) != 0u;
+// Is there a beam whose sine lies in [slo, shi]?  nxt[b] = the smallest beam sine among the fine bins >= b (+inf when
+// there is none).  A beam with z >= slo sits in a bin >= fine_of(slo) (fine_of is monotonic), so z >= nxt[fine_of(slo)]:
+// if any beam lies in [slo, shi] then nxt[fine_of(slo)] <= shi.  The converse fails only when the smallest sine of bin
+// fine_of(slo) itself lies below slo -- "maybe" is always a valid answer.  One bin index, one load, one comparison.
+__device__ __forceinline__ bool beam_in(const float* __restrict__ nxt, float slo, float shi, const BeamParams& P) {
+  return __ldg(nxt + fine_of(slo, P)) <= shi;
 }
 
 // ---------------------------------------------------------------------------
@@ -170,7 +168,7 @@ __global__ void k_beam_init(VlBeamHeader* hdr, int* cell_cnt, int ncell_p1, int*
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncell_p1; i += stride) cell_cnt[i] = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ch; i += stride) row_lim[i] = make_uint2(0xffffffffu, 0u);   // empty row
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kFineBins; i += stride) fine[i] = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kFineBins; i += stride) fine[i] = (int)0xffffffffu;   // smallest sine of the bin (ordered), none yet
   if (blockIdx.x == 0 && threadIdx.x == 0) { hdr->sine_min_ord = 0xffffffffu; hdr->sine_max_ord = 0u; hdr->n_binned = 0; }
 }
 
@@ -233,10 +231,7 @@ k_beam_count(const float4* __restrict__ dir, int n, const VlBeamHeader* __restri
     atomicMin(&row_lim[row].x, ord);
     atomicMax(&row_lim[row].y, ord);
   }
-  // the rays of one beam row share a fine bin: one atomic per group of equal bins in the warp
-  const int bin = fine_of(d.z, P);
-  const unsigned int peers = __match_any_sync(__activemask(), bin);
-  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&fine[bin], __popc(peers));
+  atomicMin(reinterpret_cast<unsigned int*>(fine) + fine_of(d.z, P), vl_float_to_ordered(d.z));
 }
 
 // exclusive prefix sums of the cell counts in three coalesced steps (local 4096-element scans, scan of the block
@@ -280,9 +275,10 @@ k_beam_scan_local(int* __restrict__ cell, int ncell, int* __restrict__ blk_sum) 
 
 __global__ void __launch_bounds__(1024)
 k_beam_scan_top(int* __restrict__ blk_sum, int nblk, int* __restrict__ cell, int ncell, const int* __restrict__ fine,
-                unsigned int* __restrict__ fine_mask) {
+                float* __restrict__ nxt, uint2* __restrict__ row_lim, int ch) {
   __shared__ int s_warp[32];
   __shared__ int s_total;
+  __shared__ unsigned int s_min[kFineBins];
   const int per = (nblk + 1023) / 1024;
   const int b = min((int)threadIdx.x * per, nblk), e = min(b + per, nblk);
   int sum = 0;
@@ -290,9 +286,29 @@ k_beam_scan_top(int* __restrict__ blk_sum, int nblk, int* __restrict__ cell, int
   int run = block_excl_1024(sum, s_warp, &s_total);
   for (int i = b; i < e; ++i) { const int c = blk_sum[i]; blk_sum[i] = run; run += c; }
   if (threadIdx.x == 0) cell[ncell] = s_total;
-  for (int bin = threadIdx.x; bin < kFineBins; bin += 1024) {   // 32 consecutive bins per warp -> one mask word
-    const unsigned int word = __ballot_sync(0xffffffffu, fine[bin] > 0);
-    if ((threadIdx.x & 31) == 0) fine_mask[bin >> 5] = word;
+  // next-beam-sine table: suffix minimum of the per-bin smallest sines (ordered uints order like the floats)
+  for (int bin = threadIdx.x; bin < kFineBins; bin += 1024) s_min[bin] = (unsigned int)fine[bin];
+  __syncthreads();
+  for (int d = 1; d < kFineBins; d <<= 1) {
+    unsigned int v[kFineBins / 1024];
+#pragma unroll
+    for (int k = 0; k < kFineBins / 1024; ++k) {
+      const int bin = threadIdx.x + 1024 * k;
+      v[k] = bin + d < kFineBins ? min(s_min[bin], s_min[bin + d]) : s_min[bin];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kFineBins / 1024; ++k) s_min[threadIdx.x + 1024 * k] = v[k];
+    __syncthreads();
+  }
+  for (int bin = threadIdx.x; bin < kFineBins; bin += 1024)
+    nxt[bin] = s_min[bin] == 0xffffffffu ? INFINITY : vl_ordered_to_float(s_min[bin]);
+  // per cell row: the sine limits as floats, NaN for a row without beams (every comparison with them fails)
+  for (int r = threadIdx.x; r < ch; r += 1024) {
+    const uint2 l = row_lim[r];
+    const bool any = l.x <= l.y;
+    const float lo = any ? vl_ordered_to_float(l.x) : __int_as_float(0x7fc00000), hi = any ? vl_ordered_to_float(l.y) : __int_as_float(0x7fc00000);
+    row_lim[r] = make_uint2(__float_as_uint(lo), __float_as_uint(hi));
   }
 }
 
@@ -342,8 +358,8 @@ struct TriRec {
 // cells of one cell row; 0 = no beam can hit it).
 template <bool kFull>
 __device__ __forceinline__ int tri_setup(int f, int i0, int i1, int i2, const float* __restrict__ verts, const float3 o,
-                                         const BeamParams& P, const unsigned int* __restrict__ fine_mask,
-                                         const uint2* __restrict__ row_lim, TriRec& T) {
+                                         const BeamParams& P, const float* __restrict__ fine_mask,
+                                         const float2* __restrict__ row_lim, TriRec& T) {
   const float ax = __ldg(verts + 3 * (size_t)i0), ay = __ldg(verts + 3 * (size_t)i0 + 1), az = __ldg(verts + 3 * (size_t)i0 + 2);
   const float bx = __ldg(verts + 3 * (size_t)i1), by = __ldg(verts + 3 * (size_t)i1 + 1), bz = __ldg(verts + 3 * (size_t)i1 + 2);
   const float cx = __ldg(verts + 3 * (size_t)i2), cy = __ldg(verts + 3 * (size_t)i2 + 1), cz = __ldg(verts + 3 * (size_t)i2 + 2);
@@ -385,7 +401,7 @@ __device__ __forceinline__ int tri_setup(int f, int i0, int i1, int i2, const fl
     const float e2 = 2.f * E;
     const bool near_axis = fminf(p0x, fminf(p1x, p2x)) <= e2 && fmaxf(p0x, fmaxf(p1x, p2x)) >= -e2 &&
                            fminf(p0y, fminf(p1y, p2y)) <= e2 && fmaxf(p0y, fmaxf(p1y, p2y)) >= -e2;
-    if (!near_axis && !fine_any(fine_mask, fine_of(slo, P), fine_of(shi, P))) return 0;
+    if (!near_axis && !beam_in(fine_mask, slo, shi, P)) return 0;
     if (!kFull) return 1;
     const float h0 = p0x * p0x + p0y * p0y, h1 = p1x * p1x + p1y * p1y, h2 = p2x * p2x + p2y * p2y;
     const float hmin = fminf(h0, fminf(h1, h2));
@@ -404,7 +420,7 @@ __device__ __forceinline__ int tri_setup(int f, int i0, int i1, int i2, const fl
     }
   }
   if (shi < P.lo || slo > P.hi) return 0;
-  if (!fine_any(fine_mask, fine_of(slo, P), fine_of(shi, P))) return 0;   // no beam row inside the sine interval
+  if (!beam_in(fine_mask, slo, shi, P)) return 0;   // no beam row inside the sine interval
   T.v0x = ax; T.v0y = ay; T.v0z = az;
   T.e1x = __fsub_rn(bx, ax); T.e1y = __fsub_rn(by, ay); T.e1z = __fsub_rn(bz, az);
   T.e2x = __fsub_rn(cx, ax); T.e2y = __fsub_rn(cy, ay); T.e2z = __fsub_rn(cz, az);
@@ -415,9 +431,9 @@ __device__ __forceinline__ int tri_setup(int f, int i0, int i1, int i2, const fl
   // typical LiDAR triangle, whose interval is narrower than a cell row and straddles a row boundary)
   int ra = row_of(slo, P), rb = row_of(shi, P);
   if (row_lim) {
-    // float comparisons, as the filter's (an empty row decodes to NaN limits and fails both)
-    for (; ra <= rb; ++ra) { const uint2 l = __ldg(row_lim + ra); if (vl_ordered_to_float(l.y) >= slo && vl_ordered_to_float(l.x) <= shi) break; }
-    for (; rb > ra; --rb) { const uint2 l = __ldg(row_lim + rb); if (vl_ordered_to_float(l.y) >= slo && vl_ordered_to_float(l.x) <= shi) break; }
+    // float comparisons, as the filter's (an empty row holds NaN limits and fails both)
+    for (; ra <= rb; ++ra) { const float2 l = __ldg(row_lim + ra); if (l.y >= slo && l.x <= shi) break; }
+    for (; rb > ra; --rb) { const float2 l = __ldg(row_lim + rb); if (l.y >= slo && l.x <= shi) break; }
     if (ra > rb) return 0;
   }
   T.ra = ra;
@@ -456,7 +472,7 @@ __device__ __forceinline__ float rsqrt_mufu(float x) {
 }
 
 __device__ __forceinline__ bool tri_cull(int i0, int i1, int i2, const float* __restrict__ verts, const float3 o,
-                                         float o_max, const BeamParams& P, const unsigned int* __restrict__ fine_mask) {
+                                         float o_max, const BeamParams& P, const float* __restrict__ fine_mask) {
   const float p0x = __ldg(verts + 3 * (size_t)i0) - o.x, p0y = __ldg(verts + 3 * (size_t)i0 + 1) - o.y, p0z = __ldg(verts + 3 * (size_t)i0 + 2) - o.z;
   const float p1x = __ldg(verts + 3 * (size_t)i1) - o.x, p1y = __ldg(verts + 3 * (size_t)i1 + 1) - o.y, p1z = __ldg(verts + 3 * (size_t)i1 + 2) - o.z;
   const float p2x = __ldg(verts + 3 * (size_t)i2) - o.x, p2y = __ldg(verts + 3 * (size_t)i2 + 1) - o.y, p2z = __ldg(verts + 3 * (size_t)i2 + 2) - o.z;
@@ -477,7 +493,7 @@ __device__ __forceinline__ bool tri_cull(int i0, int i1, int i2, const float* __
   const float e2 = 2.f * E;
   const bool near_axis = fminf(p0x, fminf(p1x, p2x)) <= e2 && fmaxf(p0x, fmaxf(p1x, p2x)) >= -e2 &&
                          fminf(p0y, fminf(p1y, p2y)) <= e2 && fmaxf(p0y, fmaxf(p1y, p2y)) >= -e2;
-  return near_axis || fine_any(fine_mask, fine_of(slo, P), fine_of(shi, P));
+  return near_axis || beam_in(fine_mask, slo, shi, P);
 }
 
 __device__ __forceinline__ unsigned long long init_key() {
@@ -500,19 +516,21 @@ __global__ void k_cast_init(unsigned long long* __restrict__ best, int n, VlCast
 //          per pass reserves both.  List order is irrelevant: a unit is self-contained.
 template <bool kDescPtr>
 __global__ void __launch_bounds__(kCastThreads, VL_SETUP_MINB)
-k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsigned int* __restrict__ fine_mask_g,
+k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const float* __restrict__ s_mask,
              const VlMeshDesc mesh_val, const VlMeshDesc* __restrict__ mesh_ptr,
              const float* __restrict__ origin, VlCastHeader* chdr, float4* __restrict__ recs, int rec_cap,
-             int2* __restrict__ units, unsigned long long unit_cap, const uint2* __restrict__ row_lim) {
+             int2* __restrict__ units, unsigned long long unit_cap, const float2* __restrict__ row_lim) {
   const float* __restrict__ verts = kDescPtr ? mesh_ptr->verts : mesh_val.verts;
   const int* __restrict__ faces = kDescPtr ? mesh_ptr->faces : mesh_val.faces;
   const int n_verts = kDescPtr ? mesh_ptr->n_verts : mesh_val.n_verts;
   const int n_faces = kDescPtr ? mesh_ptr->n_faces : mesh_val.n_faces;
-  __shared__ unsigned int s_mask[kFineWords];
-  __shared__ int s_queue[kBatch];
-  __shared__ int s_nq, s_next;
-  if (threadIdx.x < kFineWords) s_mask[threadIdx.x] = __ldg(fine_mask_g + threadIdx.x);
-  if (threadIdx.x == 0) { s_nq = 0; s_next = 0; }
+  // ONE barrier per batch: the survivor queue is double-buffered (batch b + 2 overwrites the queue of batch b only after
+  // the barrier of batch b + 1, which every thread reaches after its share of batch b's setup), the two counters are
+  // triple-buffered (the set of batch b + 2 is cleared by thread 0 right after the barrier of batch b, i.e. before it
+  // arrives at the barrier of batch b + 1 that precedes every use)
+  __shared__ int s_queue[2][kBatch];
+  __shared__ int s_nq[3], s_next[3];
+  if (threadIdx.x < 3) { s_nq[threadIdx.x] = 0; s_next[threadIdx.x] = 0; }
   __syncthreads();
   const BeamParams P = beam_params(bhdr, cw, ch);
   const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
@@ -521,7 +539,9 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
   const int n_batches = (n_faces + kBatch - 1) / kBatch;
   const unsigned long long units_mask = (1ull << kUnitBits) - 1ull;
   int n_bad = 0;
-  for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+  int it = 0;
+  for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
+    const int cb = it % 3, qb = it & 1;
     // ---- cull
     int idx[kBatch / kCastThreads][3];
 #pragma unroll
@@ -545,25 +565,26 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
       const unsigned int m = __ballot_sync(0xffffffffu, keep);
       if (m) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(&s_nq, __popc(m));
+        if (lane == 0) base = atomicAdd(&s_nq[cb], __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (keep) s_queue[base + __popc(m & ((1u << lane) - 1u))] = f;
+        if (keep) s_queue[qb][base + __popc(m & ((1u << lane) - 1u))] = f;
       }
     }
     __syncthreads();
-    const int nq = s_nq;
+    if (threadIdx.x == 0) { const int rb = (it + 2) % 3; s_nq[rb] = 0; s_next[rb] = 0; }
+    const int nq = s_nq[cb];
     // ---- setup of the survivors: every WARP takes 32 of them at a time from the queue and reserves its records and
     // units with its own packed atomicAdd (warp scan by shuffles) -- no block scan and no barrier inside this phase
     for (;;) {
       int start = 0;
-      if (lane == 0) start = atomicAdd(&s_next, 32);
+      if (lane == 0) start = atomicAdd(&s_next[cb], 32);
       start = __shfl_sync(0xffffffffu, start, 0);
       if (start >= nq) break;                                   // warp-uniform
       const int j = start + lane;
       TriRec T;
       int n_i = 0;
       if (j < nq) {
-        const int f = s_queue[j];
+        const int f = s_queue[qb][j];
         const int i0 = __ldg(faces + 3 * (size_t)f), i1 = __ldg(faces + 3 * (size_t)f + 1), i2 = __ldg(faces + 3 * (size_t)f + 2);
         n_i = tri_setup<true>(f, i0, i1, i2, verts, o, P, s_mask, row_lim, T);
       }
@@ -597,9 +618,6 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const unsign
         }
       }
     }
-    __syncthreads();   // the queue is reused by the next batch
-    if (threadIdx.x == 0) { s_nq = 0; s_next = 0; }
-    __syncthreads();
   }
   if (n_bad) atomicAdd(&chdr->n_bad_faces, n_bad);
 }
@@ -781,7 +799,7 @@ int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_b
   int* cell_start = reinterpret_cast<int*>(B + L.off_cell_start);
   int* cursor = reinterpret_cast<int*>(B + L.off_cursor);
   int* fine = reinterpret_cast<int*>(B + L.off_fine);
-  unsigned int* fine_mask = reinterpret_cast<unsigned int*>(B + L.off_mask);
+  float* fine_mask = reinterpret_cast<float*>(B + L.off_mask);
   int* blk_sum = reinterpret_cast<int*>(B + L.off_blk);
   const int ncell = L.cw * L.ch;
   VlProfScope ps(VL_ST_BEAMS, stream);
@@ -798,7 +816,7 @@ int vl_beams_build_launch(const float* d_rays, int n_rays, int height, void* d_b
   const int nblk = (ncell + kScanBlock - 1) / kScanBlock;
   k_beam_scan_local<<<nblk, 1024, 0, stream>>>(cell_start, ncell, blk_sum);
   VL_LAUNCH_CHECK("k_beam_scan_local");
-  k_beam_scan_top<<<1, 1024, 0, stream>>>(blk_sum, nblk, cell_start, ncell, fine, fine_mask);
+  k_beam_scan_top<<<1, 1024, 0, stream>>>(blk_sum, nblk, cell_start, ncell, fine, fine_mask, row_lim, L.ch);
   VL_LAUNCH_CHECK("k_beam_scan_top");
   k_beam_scan_apply<<<(ncell + 1023) / 1024, 1024, 0, stream>>>(cell_start, ncell, blk_sum, cursor);
   VL_LAUNCH_CHECK("k_beam_scan_apply");
@@ -826,8 +844,8 @@ static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr
   const float4* sorted = reinterpret_cast<const float4*>(B + L.off_sorted);
   const int* slot_of = reinterpret_cast<const int*>(B + L.off_slot_of);
   const int* cell_start = reinterpret_cast<const int*>(B + L.off_cell_start);
-  const unsigned int* fine_mask = reinterpret_cast<const unsigned int*>(B + L.off_mask);
-  const uint2* row_lim = g_row_trim ? reinterpret_cast<const uint2*>(B + L.off_rowlim) : nullptr;
+  const float* fine_mask = reinterpret_cast<const float*>(B + L.off_mask);
+  const float2* row_lim = g_row_trim ? reinterpret_cast<const float2*>(B + L.off_rowlim) : nullptr;
   char* Wk = static_cast<char*>(d_ws);
   const CastLayout C = cast_layout(n_rays, cap_faces);
   VlCastHeader* chdr = reinterpret_cast<VlCastHeader*>(Wk);
