@@ -296,7 +296,7 @@ def sharded_pipeline_leg(rank, world, dev, n_manifest, barrier, reduce_max):
   -> mesh -> 64x2048 cast -> results (4.2 MB packed, down to pinned host memory), no collective.  The mesh is born on
   the device, so a scan moves 4 MB up instead of the 27 MB of the host-mesh interface.  Returns (scans, max-over-ranks ms)."""
   import torch
-  from lidar_transfer_b200 import engine, sharding, synth
+  from lidar_transfer_b200 import pipeline, sharding, synth
   from lidar_transfer_b200.rays import create_rays
   mine = sharding.scans_for_rank(n_manifest, rank, world)
   P = 4   # distinct point clouds per rank, cycled (scan k uses cloud k mod P)
@@ -308,41 +308,23 @@ def sharded_pipeline_leg(rank, world, dev, n_manifest, barrier, reduce_max):
                    torch.from_numpy(lab.view(np.int32).copy()).pin_memory()))
   bnds = np.array([[-50, 50], [-31, 40], [-3, 2]], np.float64)
   dim = np.ceil((bnds[:, 1] - bnds[:, 0]) / 0.05).astype(int)
-  beams = engine.Beams(create_rays(FOV_UP, FOV_DOWN, H, W), H)
-  origin = torch.zeros(3, device=dev)
-  vol = engine.TsdfDevice(dim, bnds[:, 0].astype(np.float32), 0.05, FOV_UP, FOV_DOWN)
   R = H * W
-  packed = torch.empty(32 * R, dtype=torch.uint8, device=dev)
-  outs = dict(endpoints=packed[:12 * R].view(torch.float32), endcolors=packed[12 * R:24 * R].view(torch.int32),
-              range=packed[24 * R:28 * R].view(torch.float32), endrem=packed[28 * R:32 * R].view(torch.float32))
-  h_out = [torch.empty(32 * R, dtype=torch.uint8).pin_memory() for _ in range(2)]
-  ws = None
-  hits = 0.0
-
-  def one(k):
-    nonlocal ws
-    p64, rem, lab = (t.to(dev, non_blocking=True) for t in clouds[k % P])
-    pr = engine.project(p64, rem, lab, FOV_UP, FOV_DOWN, H, W, workspace=ws)
-    ws = pr["workspace"]
-    vol.reset()
-    vol.integrate(pr["proj_label"].to(torch.float32) * 65536.0, pr["range_image"], pr["proj_remissions"])
-    m = vol.extract_mesh(want_norms=False)
-    engine.cast(beams, m["verts"], m["faces"], m["colors"], m["rem"], origin, out=outs, want_ids=False, zero_misses=True,
-                check_mesh=False)
-    h_out[k & 1].copy_(packed, non_blocking=True)
-  for k in range(3):
-    one(k)
+  n_lanes = int(os.environ.get("VL_PIPE_LANES", "3"))   # measured: 1 / 2 / 3 / 4 / 6 scans in flight -> 1064 / 1211 / 1717 / 1676 / 447 scans per second
+  pipe = pipeline.ScanPipeline(create_rays(FOV_UP, FOV_DOWN, H, W), H, FOV_UP, FOV_DOWN, bnds, 0.05, H, W, n_lanes=n_lanes, device=dev)
+  for _ in pipe.run(clouds[k % P] for k in range(3)):
+    pass
   barrier()
   t0 = time.perf_counter()
-  for k in mine:
-    one(k)
+  last = None
+  for _, h in pipe.run(clouds[k % P] for k in mine):
+    last = h
   torch.cuda.synchronize()
   ms = 1e3 * (time.perf_counter() - t0)
-  hits = float((h_out[(mine[-1]) & 1][24 * R:28 * R].view(torch.float32) > 0).float().mean()) if mine else 0.0
+  hits = float((last[24 * R:28 * R].view(torch.float32) > 0).float().mean()) if last is not None else 0.0
   barrier()
   up = sum(t.numel() * t.element_size() for t in clouds[0])
   return {"scans": n_manifest, "ms": reduce_max(ms), "h2d_bytes_per_scan": up, "d2h_bytes_per_scan": 32 * R, "hit_fraction": hits,
-          "scans_this_rank": len(mine)}
+          "scans_this_rank": len(mine), "scans_in_flight": n_lanes}
 
 
 def deform_leg(n_scans=3, reps=2):

@@ -454,6 +454,11 @@ class TsdfDevice:
     the device-resident equivalent of TSDFVolume.get_mesh (auxiliary/fusion_lidar.py:403-424).
     Returns dict(verts f32[N_v,3] world frame, faces i32[N_t,3], norms f32[N_v,3], colors u8[N_v,3],
     rem f32[N_v]) -- a triangle soup, N_v = 3 N_t.  Synchronises once (the triangle count)."""
+    return self.extract_mesh_finish(self.extract_mesh_begin(level), want_norms)
+
+  def extract_mesh_begin(self, level=0.0):
+    """First half of extract_mesh: the counting sweep is enqueued on the current stream and the two totals start their
+    way to pinned host memory; nothing waits.  pipeline.ScanPipeline puts another scan's kernels between the halves."""
     hull = None
     if self.sparse and not self._fresh and not self._dense and level <= 1.0 and self.dim[2] + 64 <= 2048:
       hull = self._hull()    # sparse volume: the mesh kernels read inside the hulls only
@@ -461,11 +466,10 @@ class TsdfDevice:
     else:
       vols = (self.tsdf, self.weight, self.color, self.rem)
     dev = vols[0].device
-    n = self.dim[0] * self.dim[1] * self.dim[2]
     need = lib().vl_mesh_workspace_bytes(self.dim[0], self.dim[1], self.dim[2])
     ws = self._workspace("mesh", need, dev)
-    totals = torch.zeros(2, dtype=torch.int64, device=dev)
-    origin = (ctypes.c_float * 3)(*[float(v) for v in self.origin])
+    totals = self._workspace("mesh_totals", 16, dev)[:16].view(torch.int64)
+    totals.zero_()
     with torch.cuda.device(dev):
       if hull is not None:
         rc = lib().vl_mesh_count_sparse(_ptr(vols[0]), self.dim[0], self.dim[1], self.dim[2], float(level), _ptr(hull), _ptr(ws),
@@ -477,7 +481,21 @@ class TsdfDevice:
       if hull is None:
         check(lib().vl_mesh_count(_ptr(vols[0]), self.dim[0], self.dim[1], self.dim[2], float(level), _ptr(ws),
                                   ws.numel(), _ptr(totals), _stream()))
-      n_t, n_a = (int(v) for v in totals.tolist())  # the one host synchronisation of the extraction
+    if getattr(self, "_h_totals", None) is None:
+      self._h_totals = torch.zeros(2, dtype=torch.int64).pin_memory()
+      self._ev_totals = torch.cuda.Event()
+    self._h_totals.copy_(totals, non_blocking=True)
+    self._ev_totals.record(torch.cuda.current_stream(dev))
+    return dict(level=float(level), hull=hull, vols=vols, ws=ws, dev=dev)
+
+  def extract_mesh_finish(self, ctx, want_norms=True):
+    """Second half: waits for the totals (the one host synchronisation of the extraction), allocates the mesh and
+    enqueues the emit on the current stream (the stream extract_mesh_begin ran on)."""
+    hull, vols, ws, dev, level = ctx["hull"], ctx["vols"], ctx["ws"], ctx["dev"], ctx["level"]
+    self._ev_totals.synchronize()
+    n_t, n_a = (int(v) for v in self._h_totals.tolist())
+    origin = (ctypes.c_float * 3)(*[float(v) for v in self.origin])
+    with torch.cuda.device(dev):
       out = dict(verts=torch.empty((3 * n_t, 3), dtype=torch.float32, device=dev),
                  faces=torch.empty((n_t, 3), dtype=torch.int32, device=dev),
                  norms=torch.empty((3 * n_t, 3), dtype=torch.float32, device=dev) if want_norms else None,
@@ -495,6 +513,7 @@ class TsdfDevice:
                                  _ptr(out["verts"]), _ptr(out["faces"]), _ptr(out["norms"]), _ptr(out["colors"]),
                                  _ptr(out["rem"]), _stream()))
       out["n_active_cubes"] = n_a
+      out["_scratch"] = active   # read by the emit kernel in flight: lives as long as the mesh does
     return out
 
 

@@ -246,3 +246,106 @@ class ScanRenderer:
     cur = torch.cuda.current_stream(self.dev)
     for s in self.slots:
       cur.wait_stream(s.stream)
+
+
+class _Lane:
+  """One scan in flight of a ScanPipeline: its own stream, TSDF volume, projection workspace and result buffers."""
+
+  def __init__(self, owner):
+    dev = owner.dev
+    self.stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.device(dev):
+      self.vol = engine.TsdfDevice(owner.dim, owner.vol_origin, owner.voxel_size, owner.fov_up, owner.fov_down)
+    R = owner.n_rays
+    self.packed = torch.empty(32 * R, dtype=torch.uint8, device=dev)   # endpoints | endcolors | range | endrem
+    self.outs = dict(endpoints=self.packed[:12 * R].view(torch.float32), endcolors=self.packed[12 * R:24 * R].view(torch.int32),
+                     range=self.packed[24 * R:28 * R].view(torch.float32), endrem=self.packed[28 * R:32 * R].view(torch.float32))
+    self.h_out = torch.empty(32 * R, dtype=torch.uint8).pin_memory()
+    self.done = torch.cuda.Event()
+    self.ws = None
+    self.ctx = None      # between the halves: the mesh count is on its way
+    self.tag = None
+    self.mesh = None     # the mesh of the scan whose cast is in flight (kept until the next scan of this lane)
+    self.inputs = None
+
+
+class ScanPipeline:
+  """The whole per-scan chain for batches of independent scans, points in -> per-ray results out:
+  projection (vl_project) -> sparse TSDF (vl_tsdf_sparse_integrate) -> iso-surface (vl_mesh_*) -> cast (vl_cast),
+  i.e. what MultiSemLaserScan.deform('mergemesh') does for one scan (auxiliary/laserscan.py:921-1012), software-pipelined
+  over `n_lanes` scans in flight: the chain has ONE host synchronisation per scan (the triangle count that sizes the
+  mesh), and while the host waits for the count of scan k the kernels of scan k + 1 are already queued on another
+  stream.  Same kernels, same bits as the sequential engine calls (tests/test_chain_gpu.py).
+
+      pipe = ScanPipeline(rays, height, src_fov, vol_bnds, voxel_size, im_h, im_w)
+      for tag, h_out in pipe.run(clouds):      # clouds: iterable of (points f64[N,3], remission f32[N], label i32[N])
+        ...                                    # h_out: pinned uint8[32 R] = endpoints | endcolors | range | endrem
+
+  Scans are independent, so a multi-GPU job gives each rank its own ScanPipeline over its shard (sharding.py)."""
+
+  def __init__(self, rays, height, fov_up, fov_down, vol_bnds, voxel_size, im_h, im_w, n_lanes=3, device=None, origin=None):
+    engine.require_cuda()
+    self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    self.fov_up, self.fov_down = float(fov_up), float(fov_down)
+    self.im_h, self.im_w = int(im_h), int(im_w)
+    bnds = np.asarray(vol_bnds, np.float64).reshape(3, 2)
+    self.dim = np.ceil((bnds[:, 1] - bnds[:, 0]) / voxel_size).astype(int)   # fusion_lidar.py:39-41
+    self.vol_origin = bnds[:, 0].astype(np.float32)
+    self.voxel_size = float(voxel_size)
+    self.height = int(height)
+    self.beams = engine.Beams(rays, self.height, self.dev)
+    self.n_rays = self.beams.n_rays
+    self.origin = torch.zeros(3, device=self.dev) if origin is None else engine._dev(origin, torch.float32, self.dev).reshape(-1)
+    self.lanes = [_Lane(self) for _ in range(max(1, int(n_lanes)))]
+    torch.cuda.current_stream(self.dev).synchronize()
+
+  def _front(self, lane, tag, cloud):
+    """points -> range / label / remission image -> TSDF -> triangle count on its way to the host"""
+    with torch.cuda.stream(lane.stream):
+      p64, rem, lab = (t.to(self.dev, non_blocking=True) if torch.is_tensor(t) else t for t in cloud)
+      lane.inputs = (p64, rem, lab)
+      pr = engine.project(p64, rem, lab, self.fov_up, self.fov_down, self.im_h, self.im_w, workspace=lane.ws)
+      lane.ws = pr["workspace"]
+      lane.vol.reset()
+      lane.vol.integrate(pr["proj_label"].to(torch.float32) * 65536.0, pr["range_image"], pr["proj_remissions"])
+      lane.ctx = lane.vol.extract_mesh_begin()
+      lane.tag = tag
+
+  def _back(self, lane):
+    """triangle count -> mesh -> cast -> results on their way to pinned host memory"""
+    with torch.cuda.stream(lane.stream):
+      m = lane.vol.extract_mesh_finish(lane.ctx, want_norms=False)
+      engine.cast(self.beams, m["verts"], m["faces"], m["colors"], m["rem"], self.origin, out=lane.outs, want_ids=False,
+                  zero_misses=True, check_mesh=False)
+      lane.h_out.copy_(lane.packed, non_blocking=True)
+      lane.done.record(lane.stream)
+      lane.mesh, lane.ctx = m, None
+
+  def run(self, clouds):
+    """Generator over (tag, pinned result buffer) in submission order; `clouds` yields (points, remission, label) or
+    (tag, points, remission, label).  A yielded buffer is valid until its lane is reused, n_lanes scans later."""
+    n = len(self.lanes)
+    waiting = []   # lanes in flight, oldest first (round robin: a lane that is needed again is always the oldest)
+    k = 0
+
+    def hand_out(w):
+      if w.ctx is not None:
+        self._back(w)
+      w.done.synchronize()
+      return w.tag, w.h_out
+
+    for item in clouds:
+      tag, cloud = (item[0], item[1:]) if len(item) == 4 else (k, item)
+      lane = self.lanes[k % n]
+      if waiting and waiting[0] is lane:
+        yield hand_out(waiting.pop(0))
+      self._front(lane, tag, cloud)
+      # every earlier scan still waiting for its count gets its second half now: the count has had a whole front of
+      # another scan to arrive, and the kernels just queued keep the device busy while the host allocates and launches
+      for w in waiting:
+        if w.ctx is not None:
+          self._back(w)
+      waiting.append(lane)
+      k += 1
+    for w in waiting:
+      yield hand_out(w)

@@ -76,3 +76,37 @@ def test_identity_rerender_at_config1_size(engine):
   for k in ("verts", "colors", "rem"):
     assert torch.equal(m3[k], m[k]), k
   assert torch.equal(out3["range"], out["range"]) and torch.equal(out3["tri_id"], out["tri_id"])
+
+
+@pytest.mark.parametrize("n_lanes", [1, 2, 3])
+def test_scan_pipeline_equals_the_sequential_chain(engine, n_lanes):
+  """pipeline.ScanPipeline keeps several scans in flight (the host waits for one scan's triangle count while the next
+  scan's kernels run on another stream): every scan's packed result must be the bytes the sequential engine calls give,
+  in submission order, whatever the number of lanes, with clouds of different sizes."""
+  from lidar_transfer_b200 import pipeline
+  H, W, fu, fd = 32, 512, 10.0, -25.0
+  rays = create_rays(fu, fd, H, W)
+  vox = 0.25
+  bnds = np.array([[-40, 40], [-40, 40], [-4, 3]], np.float64)
+  dim = np.ceil((bnds[:, 1] - bnds[:, 0]) / vox).astype(int)
+  clouds = []
+  for k in range(7):
+    pts, lab = synth.make_scan_points(40 + k, 20000 + 7000 * (k % 3))
+    clouds.append((torch.from_numpy(pts[:, :3].astype(np.float64)).pin_memory(), torch.from_numpy(pts[:, 3].copy()).pin_memory(),
+                   torch.from_numpy(lab.view(np.int32).copy()).pin_memory()))
+  beams = engine.Beams(rays, H)
+  o = np.zeros(3, np.float32)
+  want = []
+  for p64, rem, lab in clouds:
+    _, m, out = _chain(engine, beams, p64.cuda(), rem.cuda(), lab.cuda(), H, W, fu, fd, dim, bnds[:, 0].astype(np.float32), vox)
+    want.append(torch.cat([out[k].reshape(-1).view(torch.uint8) for k in ("endpoints", "endcolors", "range", "endrem")]).cpu())
+    assert m["faces"].shape[0] > 1000 and float((out["tri_id"] >= 0).float().mean()) > 0.3
+  assert not torch.equal(want[0], want[1])
+  pipe = pipeline.ScanPipeline(rays, H, fu, fd, bnds, vox, H, W, n_lanes=n_lanes)
+  got = [(tag, h.clone()) for tag, h in pipe.run(clouds)]
+  assert [t for t, _ in got] == list(range(len(clouds)))
+  for (tag, h), w in zip(got, want):
+    assert torch.equal(h, w), tag
+  # tagged items, a second run on the same pipeline
+  got2 = [(tag, h.clone()) for tag, h in pipe.run([("s%d" % k,) + c for k, c in enumerate(clouds[:3])])]
+  assert [t for t, _ in got2] == ["s0", "s1", "s2"] and all(torch.equal(h, w) for (_, h), w in zip(got2, want))
