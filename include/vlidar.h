@@ -131,7 +131,8 @@ int vl_trace(const void* d_blob, int n_faces, const float* d_rays, const float* 
  * vl_beams_build: d_rays f32[3*n_rays] (not normalised; unit vectors with VL_RAYS_NORMALIZED) -> d_beams, a caller-provided device
  * blob of vl_beams_bytes(n_rays, height) bytes, 256-byte aligned; valid for every later
  * vl_cast with the same (n_rays, height), any origin, any mesh.
- * vl_cast: mesh arrays as in vl_bvh_build, outputs / flags as in vl_trace; d_workspace of
+ * vl_cast: mesh arrays as in vl_bvh_build -- or d_faces = NULL for a triangle SOUP, face f = vertices (3f, 3f+1, 3f+2), the
+ * layout vl_mesh_emit produces: no index array is read (or has to be written) at all; outputs / flags as in vl_trace; d_workspace of
  * vl_cast_workspace_bytes(n_rays, n_faces) bytes (8 B per ray + 12 B per face, 256-byte
  * aligned) is scratch for this call.  vl_cast_status synchronises the stream and returns
  * VL_OK, VL_EBADMESH or VL_ENOSPACE (more than 2^36 triangle-cell candidates: results
@@ -317,7 +318,7 @@ int vl_tsdf_densify(float* d_tsdf, float* d_weight, float* d_color, float* d_rem
  * cube + 4 B per 256 triangles), and calls vl_mesh_emit with the SAME workspace (n_tris / n_active
  * below the counted totals truncate the output to the first n_tris triangles in cube order; nothing
  * is written beyond the sizes they imply).  Output is a triangle soup in cube order: d_verts f32[9T] (world frame,
- * verts * voxel_size + origin, :412), d_faces i32[3T] = 0..3T-1, d_norms f32[9T] (nullable,
+ * verts * voxel_size + origin, :412), d_faces i32[3T] = 0..3T-1 (nullable: vl_cast takes a soup without it), d_norms f32[9T] (nullable,
  * flat normals), d_colors u8[9T] = (r, g, b) of the nearest voxel's folded colour with the
  * reference's uint8 wrap (:417-423), d_rem_out f32[3T].
  * ---------------------------------------------------------------------------------- */

@@ -205,7 +205,8 @@ extern "C" int vl_cast(const void* d_beams, const float* d_verts, const int* d_f
     vl_set_error("vl_cast: invalid argument (n_rays %d, height %d)", n_rays, height);
     return VL_EINVAL;
   }
-  if (n_faces < 0 || n_verts < 0 || n_faces >= (1 << 28) || (n_faces > 0 && (!d_verts || !d_faces || !d_colors || !d_rem))) {
+  // d_faces == NULL: a triangle soup, face f = vertices (3f, 3f+1, 3f+2) -- what vl_mesh_emit produces
+  if (n_faces < 0 || n_verts < 0 || n_faces >= (1 << 28) || (n_faces > 0 && (!d_verts || !d_colors || !d_rem))) {
     vl_set_error("vl_cast: invalid mesh (n_verts %d, n_faces %d; at most 2^28 - 1 faces)", n_verts, n_faces);
     return VL_EINVAL;
   }

@@ -548,7 +548,8 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const float*
     for (int k = 0; k < kBatch / kCastThreads; ++k) {   // all index loads first: faces -> verts is a dependent gather
       const int f = batch * kBatch + k * kCastThreads + threadIdx.x;
       if (f < n_faces) {
-        idx[k][0] = __ldg(faces + 3 * (size_t)f); idx[k][1] = __ldg(faces + 3 * (size_t)f + 1); idx[k][2] = __ldg(faces + 3 * (size_t)f + 2);
+        if (faces) { idx[k][0] = __ldg(faces + 3 * (size_t)f); idx[k][1] = __ldg(faces + 3 * (size_t)f + 1); idx[k][2] = __ldg(faces + 3 * (size_t)f + 2); }
+        else { idx[k][0] = 3 * f; idx[k][1] = 3 * f + 1; idx[k][2] = 3 * f + 2; }   // triangle soup: faces = (3f, 3f+1, 3f+2), no index array
       }
     }
 #pragma unroll
@@ -585,7 +586,8 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const float*
       int n_i = 0;
       if (j < nq) {
         const int f = s_queue[qb][j];
-        const int i0 = __ldg(faces + 3 * (size_t)f), i1 = __ldg(faces + 3 * (size_t)f + 1), i2 = __ldg(faces + 3 * (size_t)f + 2);
+        const int i0 = faces ? __ldg(faces + 3 * (size_t)f) : 3 * f, i1 = faces ? __ldg(faces + 3 * (size_t)f + 1) : 3 * f + 1,
+                  i2 = faces ? __ldg(faces + 3 * (size_t)f + 2) : 3 * f + 2;
         n_i = tri_setup<true>(f, i0, i1, i2, verts, o, P, s_mask, row_lim, T);
       }
       const int n_u = (n_i + kUnitItems - 1) / kUnitItems;
@@ -734,7 +736,8 @@ k_cast_resolve(unsigned long long* best, int n, const float4* __restrict__ dir,
     const float t = __uint_as_float((unsigned int)(key >> 32));
     const float4 d = dir[r];
     const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
-    const int i0 = __ldg(faces + 3 * (size_t)f), i1 = __ldg(faces + 3 * (size_t)f + 1), i2 = __ldg(faces + 3 * (size_t)f + 2);
+    const int i0 = faces ? __ldg(faces + 3 * (size_t)f) : 3 * f, i1 = faces ? __ldg(faces + 3 * (size_t)f + 1) : 3 * f + 1,
+              i2 = faces ? __ldg(faces + 3 * (size_t)f + 2) : 3 * f + 2;
     endpoints[3 * (size_t)r + 0] = __fadd_rn(o.x, __fmul_rn(d.x, t));
     endpoints[3 * (size_t)r + 1] = __fadd_rn(o.y, __fmul_rn(d.y, t));
     endpoints[3 * (size_t)r + 2] = __fadd_rn(o.z, __fmul_rn(d.z, t));

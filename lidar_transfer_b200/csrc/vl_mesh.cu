@@ -713,7 +713,7 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
     // remissions, 3072 B of face indices): handed to the TMA engine as bulk stores shared -> global (cp.async.bulk,
     // UBLKCP in the SASS) by one thread instead of being copied out by all 256 in a loop.
     __shared__ __align__(16) int s_f[kEmitTris * 3];
-    for (int i = tid; i < 3 * kEmitTris; i += kEmitTris) s_f[i] = (int)(3 * T0 + i);
+    if (faces) for (int i = tid; i < 3 * kEmitTris; i += kEmitTris) s_f[i] = (int)(3 * T0 + i);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the generic-proxy writes above, visible to the async proxy
     __syncthreads();
     if (tid == 0) {
@@ -724,7 +724,7 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
       bulk(verts + 9 * T0, s_v, kEmitTris * 9 * 4);
       bulk(colors + 9 * T0, s_c, kEmitTris * 9);
       bulk(rem_out + 3 * T0, s_r, kEmitTris * 3 * 4);
-      bulk(faces + 3 * T0, s_f, kEmitTris * 3 * 4);
+      if (faces) bulk(faces + 3 * T0, s_f, kEmitTris * 3 * 4);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must stay intact until it has been read
     }
@@ -741,7 +741,7 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
   };
   put9(verts);
   for (int i = tid; i < 3 * nT; i += kEmitTris) {
-    faces[3 * T0 + i] = (int)(3 * T0 + i);
+    if (faces) faces[3 * T0 + i] = (int)(3 * T0 + i);
     rem_out[3 * T0 + i] = s_r[i];
   }
   if (full) {
@@ -904,7 +904,7 @@ static int mesh_emit_impl(const float* d_tsdf, const float* d_color, const float
   int rc = mesh_args("vl_mesh_emit", d_tsdf, dx, dy, dz, d_workspace, workspace_bytes, &P, level, voxel_size, vol_origin);
   if (rc) return rc;
   if (!d_color || !d_rem || !vol_origin || n_tris < 0 || n_active < 0 || n_tris >= (1ll << 31) / 3 ||
-      (n_tris > 0 && (!d_verts || !d_faces || !d_colors || !d_rem_out || !d_active_list || n_active == 0))) {
+      (n_tris > 0 && (!d_verts || !d_colors || !d_rem_out || !d_active_list || n_active == 0))) {   // d_faces may be NULL: the soup's index array is implicit
     vl_set_error("vl_mesh_emit: invalid argument (n_tris %lld, n_active %lld)", n_tris, n_active);
     return VL_EINVAL;
   }

@@ -190,12 +190,13 @@ def cast(beams, verts, faces, colors, rem, origin, out=None, want_ids=True, zero
   With check_mesh=False the call is asynchronous and the caller checks lib().vl_cast_status itself."""
   dev = beams.blob.device
   verts = _dev(verts, torch.float32, dev).reshape(-1)
-  faces = _dev(faces, torch.int32, dev).reshape(-1)
+  faces = _dev(faces, torch.int32, dev).reshape(-1) if faces is not None else None   # None: a triangle soup, face f = vertices 3f .. 3f+2
   colors_u8 = torch.is_tensor(colors) and colors.dtype == torch.uint8   # the mesh extraction's colours, used as they are
   colors = _dev(colors, torch.uint8 if colors_u8 else torch.int32, dev).reshape(-1)
   rem = _dev(rem, torch.float32, dev).reshape(-1)
   origin = _dev(origin, torch.float32, dev).reshape(-1)
-  n_verts, n_faces = verts.numel() // 3, faces.numel() // 3
+  n_verts = verts.numel() // 3
+  n_faces = faces.numel() // 3 if faces is not None else n_verts // 3
   if colors.numel() != 3 * n_verts or rem.numel() != n_verts:
     raise ValueError("colors must hold 3 ints and rem 1 float per vertex")
   out = _trace_outputs(beams.n_rays, dev, out, want_ids, torch.empty if zero_misses else torch.zeros)
@@ -236,7 +237,7 @@ def trace_bruteforce(verts, faces, colors, rem, rays, origin, height, out=None, 
 
 
 def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, workspace=None, beam_angles=None,
-            want_bounds=False):
+            want_bounds=False, out=None, want_keep=True):
   """(iii) spherical range-image projection, the device equivalent of
   LaserScan.do_range_projection_new('depth') + do_label_projection_new
   (auxiliary/laserscan.py:294-391, 672-676).
@@ -246,7 +247,9 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, wor
   proj_label i32[H,W], proj_remissions f32[H,W] (-1 empty), keep bool[N], n_kept i32[1].
   beam_angles (non-empty sequence): the pitch snapping of laserscan.py:321-327 (vl_project_snap).
   want_bounds: also `bounds` f64[6] = min xyz, max xyz of the kept points (SemLaserScan.get_bnds on the device,
-  vl_points_bounds); `bounds` and `n_kept` then share one 64-byte buffer `meta` (a single small D2H for both)."""
+  vl_points_bounds); `bounds` and `n_kept` then share one 64-byte buffer `meta` (a single small D2H for both).
+  out: the dict of an earlier call with the same H, W -- its tensors are written again instead of allocating new ones
+  (pipeline.ScanPipeline: no allocation per scan); want_keep=False leaves `keep` as the raw uint8 buffer."""
   require_cuda()
   points = _dev(points, torch.float64).reshape(-1)
   dev = points.device
@@ -269,13 +272,20 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, wor
   need = lib().vl_project_workspace_bytes(n, H, W)
   if workspace is None or workspace.numel() < need:
     workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-  out = dict(range_image=torch.empty((H, W), dtype=torch.float32, device=dev),
-             index=torch.empty((H, W), dtype=torch.int32, device=dev),
-             proj_label=torch.empty((H, W), dtype=torch.int32, device=dev),
-             proj_remissions=torch.empty((H, W), dtype=torch.float32, device=dev),
-             keep=torch.empty(max(n, 1), dtype=torch.uint8, device=dev))
-  meta = torch.zeros(64, dtype=torch.uint8, device=dev)
-  out["meta"], out["bounds"], out["n_kept"] = meta, meta[:48].view(torch.float64), meta[48:52].view(torch.int32)
+  if out is not None and tuple(out["range_image"].shape) == (H, W) and out["range_image"].device == dev and \
+      out["_keep_buf"].numel() >= max(n, 1):
+    out = dict(out)
+    out["keep"] = out["_keep_buf"]
+    out["meta"].zero_()
+  else:
+    out = dict(range_image=torch.empty((H, W), dtype=torch.float32, device=dev),
+               index=torch.empty((H, W), dtype=torch.int32, device=dev),
+               proj_label=torch.empty((H, W), dtype=torch.int32, device=dev),
+               proj_remissions=torch.empty((H, W), dtype=torch.float32, device=dev),
+               keep=torch.empty(max(n, 1) + max(n, 1) // 4, dtype=torch.uint8, device=dev))
+    out["_keep_buf"] = out["keep"]
+    meta = torch.zeros(64, dtype=torch.uint8, device=dev)
+    out["meta"], out["bounds"], out["n_kept"] = meta, meta[:48].view(torch.float64), meta[48:52].view(torch.int32)
   with torch.cuda.device(dev):
     check(lib().vl_project_snap(_ptr(points), _ptr(remissions), _ptr(labels), n, float(fov_up), float(fov_down), H, W,
                                 1 if remove else 0, _ptr(ba) if ba is not None else None,
@@ -284,7 +294,7 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, wor
                                 _ptr(out["n_kept"]), _ptr(workspace), workspace.numel(), _stream()))
     if want_bounds:
       check(lib().vl_points_bounds(_ptr(points), _ptr(out["keep"]), n, _ptr(out["bounds"]), _stream()))
-  out["keep"] = out["keep"][:n].bool()
+  out["keep"] = out["keep"][:n].bool() if want_keep else out["keep"][:n]
   out["workspace"] = workspace
   return out
 
@@ -449,12 +459,13 @@ class TsdfDevice:
                                       _ptr(color_im), _ptr(depth_im), _ptr(rem_im), int(im_h), int(im_w), _stream()))
 
 
-  def extract_mesh(self, level=0.0, want_norms=True):
+  def extract_mesh(self, level=0.0, want_norms=True, want_faces=True):
     """(v) iso-surface of the TSDF volume at `level` + per-vertex colour / remission lookup on the device;
     the device-resident equivalent of TSDFVolume.get_mesh (auxiliary/fusion_lidar.py:403-424).
     Returns dict(verts f32[N_v,3] world frame, faces i32[N_t,3], norms f32[N_v,3], colors u8[N_v,3],
-    rem f32[N_v]) -- a triangle soup, N_v = 3 N_t.  Synchronises once (the triangle count)."""
-    return self.extract_mesh_finish(self.extract_mesh_begin(level), want_norms)
+    rem f32[N_v]) -- a triangle soup, N_v = 3 N_t.  Synchronises once (the triangle count).
+    want_faces=False: faces is None (the index array of a soup is 0 .. 3 N_t - 1; cast() takes the soup without it)."""
+    return self.extract_mesh_finish(self.extract_mesh_begin(level), want_norms, want_faces=want_faces)
 
   def extract_mesh_begin(self, level=0.0):
     """First half of extract_mesh: the counting sweep is enqueued on the current stream and the two totals start their
@@ -488,20 +499,38 @@ class TsdfDevice:
     self._ev_totals.record(torch.cuda.current_stream(dev))
     return dict(level=float(level), hull=hull, vols=vols, ws=ws, dev=dev)
 
-  def extract_mesh_finish(self, ctx, want_norms=True):
+  def extract_mesh_finish(self, ctx, want_norms=True, buffers=None, want_faces=True):
     """Second half: waits for the totals (the one host synchronisation of the extraction), allocates the mesh and
-    enqueues the emit on the current stream (the stream extract_mesh_begin ran on)."""
+    enqueues the emit on the current stream (the stream extract_mesh_begin ran on).  buffers: a dict the caller keeps
+    between calls -- the mesh arrays are then views into grow-only storage held there (valid until the next call with the
+    same dict) instead of fresh allocations."""
     hull, vols, ws, dev, level = ctx["hull"], ctx["vols"], ctx["ws"], ctx["dev"], ctx["level"]
     self._ev_totals.synchronize()
     n_t, n_a = (int(v) for v in self._h_totals.tolist())
     origin = (ctypes.c_float * 3)(*[float(v) for v in self.origin])
     with torch.cuda.device(dev):
-      out = dict(verts=torch.empty((3 * n_t, 3), dtype=torch.float32, device=dev),
-                 faces=torch.empty((n_t, 3), dtype=torch.int32, device=dev),
-                 norms=torch.empty((3 * n_t, 3), dtype=torch.float32, device=dev) if want_norms else None,
-                 colors=torch.empty((3 * n_t, 3), dtype=torch.uint8, device=dev),
-                 rem=torch.empty(3 * n_t, dtype=torch.float32, device=dev))
-      active = torch.empty(lib().vl_mesh_list_bytes(n_t, n_a), dtype=torch.uint8, device=dev)   # scratch of vl_mesh_emit
+      list_bytes = lib().vl_mesh_list_bytes(n_t, n_a)
+      if buffers is not None:
+        if buffers.get("cap_t", -1) < n_t or (want_norms and buffers.get("norms") is None) or (want_faces and buffers.get("faces") is None):
+          cap = n_t + n_t // 4 + 1024
+          buffers.update(cap_t=cap, verts=torch.empty((3 * cap, 3), dtype=torch.float32, device=dev),
+                         faces=torch.empty((cap, 3), dtype=torch.int32, device=dev) if want_faces else None,
+                         norms=torch.empty((3 * cap, 3), dtype=torch.float32, device=dev) if want_norms else None,
+                         colors=torch.empty((3 * cap, 3), dtype=torch.uint8, device=dev),
+                         rem=torch.empty(3 * cap, dtype=torch.float32, device=dev))
+        if buffers.get("active") is None or buffers["active"].numel() < list_bytes:
+          buffers["active"] = torch.empty(list_bytes + list_bytes // 4, dtype=torch.uint8, device=dev)
+        out = dict(verts=buffers["verts"][:3 * n_t], faces=buffers["faces"][:n_t] if want_faces else None,
+                   norms=buffers["norms"][:3 * n_t] if want_norms else None, colors=buffers["colors"][:3 * n_t],
+                   rem=buffers["rem"][:3 * n_t])
+        active = buffers["active"]
+      else:
+        out = dict(verts=torch.empty((3 * n_t, 3), dtype=torch.float32, device=dev),
+                   faces=torch.empty((n_t, 3), dtype=torch.int32, device=dev) if want_faces else None,
+                   norms=torch.empty((3 * n_t, 3), dtype=torch.float32, device=dev) if want_norms else None,
+                   colors=torch.empty((3 * n_t, 3), dtype=torch.uint8, device=dev),
+                   rem=torch.empty(3 * n_t, dtype=torch.float32, device=dev))
+        active = torch.empty(list_bytes, dtype=torch.uint8, device=dev)   # scratch of vl_mesh_emit
       if hull is not None:
         check(lib().vl_mesh_emit_sparse(_ptr(vols[0]), _ptr(vols[2]), _ptr(vols[3]), self.dim[0], self.dim[1], self.dim[2],
                                         float(level), self.voxel_size, origin, _ptr(hull), _ptr(ws), ws.numel(), n_t, n_a,
@@ -512,7 +541,7 @@ class TsdfDevice:
                                  float(level), self.voxel_size, origin, _ptr(ws), ws.numel(), n_t, n_a, _ptr(active),
                                  _ptr(out["verts"]), _ptr(out["faces"]), _ptr(out["norms"]), _ptr(out["colors"]),
                                  _ptr(out["rem"]), _stream()))
-      out["n_active_cubes"] = n_a
+      out["n_active_cubes"], out["n_tris"] = n_a, n_t
       out["_scratch"] = active   # read by the emit kernel in flight: lives as long as the mesh does
     return out
 

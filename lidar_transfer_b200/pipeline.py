@@ -263,6 +263,10 @@ class _Lane:
     self.h_out = torch.empty(32 * R, dtype=torch.uint8).pin_memory()
     self.done = torch.cuda.Event()
     self.ws = None
+    self.proj = None     # the projection's output tensors, written again by every scan of this lane
+    self.color_im = torch.empty((owner.im_h, owner.im_w), dtype=torch.float32, device=dev)
+    self.mesh_buf = {}   # grow-only storage of the mesh arrays (engine.TsdfDevice.extract_mesh_finish)
+    self.cast_ws = None  # grow-only cast workspace
     self.ctx = None      # between the halves: the mesh count is on its way
     self.tag = None
     self.mesh = None     # the mesh of the scan whose cast is in flight (kept until the next scan of this lane)
@@ -304,19 +308,25 @@ class ScanPipeline:
     with torch.cuda.stream(lane.stream):
       p64, rem, lab = (t.to(self.dev, non_blocking=True) if torch.is_tensor(t) else t for t in cloud)
       lane.inputs = (p64, rem, lab)
-      pr = engine.project(p64, rem, lab, self.fov_up, self.fov_down, self.im_h, self.im_w, workspace=lane.ws)
+      pr = lane.proj = engine.project(p64, rem, lab, self.fov_up, self.fov_down, self.im_h, self.im_w, workspace=lane.ws,
+                                      out=lane.proj, want_keep=False)
       lane.ws = pr["workspace"]
+      lane.color_im.copy_(pr["proj_label"])   # the folded single-channel colour image (label * 65536, fusion_lidar.py:263-264)
+      lane.color_im.mul_(65536.0)
       lane.vol.reset()
-      lane.vol.integrate(pr["proj_label"].to(torch.float32) * 65536.0, pr["range_image"], pr["proj_remissions"])
+      lane.vol.integrate(lane.color_im, pr["range_image"], pr["proj_remissions"])
       lane.ctx = lane.vol.extract_mesh_begin()
       lane.tag = tag
 
   def _back(self, lane):
     """triangle count -> mesh -> cast -> results on their way to pinned host memory"""
     with torch.cuda.stream(lane.stream):
-      m = lane.vol.extract_mesh_finish(lane.ctx, want_norms=False)
-      engine.cast(self.beams, m["verts"], m["faces"], m["colors"], m["rem"], self.origin, out=lane.outs, want_ids=False,
-                  zero_misses=True, check_mesh=False)
+      m = lane.vol.extract_mesh_finish(lane.ctx, want_norms=False, buffers=lane.mesh_buf, want_faces=False)   # a soup: no index array
+      n_faces = m["n_tris"]
+      if lane.cast_ws is None or lane.cast_ws.numel() < lib().vl_cast_workspace_bytes(self.n_rays, n_faces):
+        lane.cast_ws = self.beams.workspace(n_faces + n_faces // 4)
+      engine.cast(self.beams, m["verts"], None, m["colors"], m["rem"], self.origin, out=lane.outs, want_ids=False,
+                  zero_misses=True, check_mesh=False, workspace=lane.cast_ws)
       lane.h_out.copy_(lane.packed, non_blocking=True)
       lane.done.record(lane.stream)
       lane.mesh, lane.ctx = m, None

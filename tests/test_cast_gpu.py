@@ -530,3 +530,32 @@ def test_ctrace_arrays_that_do_not_fit_the_wire_formats_travel_raw(engine, oracl
   want = np.where(ref_c["tri_id"] >= 0, ids[np.maximum(ref_c["tri_id"], 0)], -1)
   assert np.array_equal(tri, want) and np.array_equal(out["range"].view(np.int32), ref_c["range"].view(np.int32))
   engine.ctrace_host(rays, origin, verts.reshape(-1), faces.reshape(-1), sc["colors"].reshape(-1), rem, H)   # and the library carries on
+
+
+def test_cast_takes_a_triangle_soup_without_an_index_array(engine, oracle):
+  """faces=None: face f = vertices (3f, 3f+1, 3f+2), the layout the mesh extraction produces -- same bits as the explicit
+  index array 0 .. 3T-1 and as the oracle, uint8 colours included; a vertex count that is not a multiple of three leaves
+  the last vertices unused."""
+  import torch
+  sc = synth.make_scene(61, n_side=70, n_boxes=6)
+  tri = sc["verts"][sc["faces"].reshape(-1)]                       # [3T, 3]
+  col = sc["colors"][sc["faces"].reshape(-1)]
+  rem = sc["rem"][sc["faces"].reshape(-1)]
+  T = tri.shape[0] // 3
+  faces = np.arange(3 * T, dtype=np.int32).reshape(T, 3)
+  H, W = 32, 256
+  rays = oracle.create_rays(5.0, -25.0, H, W)
+  origin = np.array([0.25, 0.5, 0.1], np.float32)
+  ref = oracle.trace(rays, origin, tri, faces, col, rem, H, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE)
+  beams = engine.Beams(rays, H)
+  a = _np(engine.cast(beams, tri, faces, col, rem, origin, check_mesh=True))
+  b = _np(engine.cast(beams, tri, None, col, rem, origin, check_mesh=True))
+  _same(a, ref, what="explicit faces")
+  _same(b, ref, what="soup")
+  assert b["n_bad_faces"] == 0 and (b["tri_id"] >= 0).mean() > 0.5
+  c8 = torch.from_numpy((col & 255).astype(np.uint8)).cuda()
+  c = _np(engine.cast(beams, tri, None, c8, rem, origin))
+  _same(c, ref, what="soup, uint8 colours")
+  pad = np.concatenate([tri, np.full((2, 3), 1e3, np.float32)])
+  d = _np(engine.cast(beams, pad, None, np.concatenate([col, np.zeros((2, 3), np.int32)]), np.concatenate([rem, np.zeros(2, np.float32)]), origin))
+  _same(d, ref, what="soup, two spare vertices")
