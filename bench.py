@@ -260,8 +260,8 @@ def pipeline_chain(L, dev, scans, src_fov, bnds, vox, target, reps=3):
       pr = engine.project(p64, rem, lab, src_fov[0], src_fov[1], H, W, workspace=ws)
       ws = pr["workspace"]
       vol.integrate(pr["proj_label"].to(torch.float32) * 65536.0, pr["range_image"], pr["proj_remissions"])
-    m = vol.extract_mesh(want_norms=False)
-    out = engine.cast(beams, m["verts"], m["faces"], m["colors"], m["rem"], origin, zero_misses=True, check_mesh=False)
+    m = vol.extract_mesh(want_norms=False, want_faces=False)   # a triangle soup: its index array is implicit
+    out = engine.cast(beams, m["verts"], None, m["colors"], m["rem"], origin, zero_misses=True, check_mesh=False)
     e1.record()
     torch.cuda.synchronize()
     wall = e0.elapsed_time(e1)
@@ -269,7 +269,7 @@ def pipeline_chain(L, dev, scans, src_fov, bnds, vox, target, reps=3):
       L.vl_profile_enable(0)
       stages = {k: round(1e3 * v[0], 1) for k, v in _collect_stages(L).items()}   # us per chain (all launches of a stage summed)
   return {"n_scans_fused": len(scans), "n_points": [int(p.shape[0]) for p, _ in scans], "voxel_size": vox,
-          "volume": "%d x %d x %d" % tuple(dim), "n_voxels": int(np.prod(dim)), "n_tris": int(m["faces"].shape[0]),
+          "volume": "%d x %d x %d" % tuple(dim), "n_voxels": int(np.prod(dim)), "n_tris": int(m["n_tris"]),
           "target": "%dx%d fov +%g/%g" % (tH, tW, tfu, tfd), "hit_fraction": float((out["range"] > 0).float().mean()),
           "stage_us": stages, "kernel_ms_per_chain": round(sum(stages.values()) / 1e3, 3), "ms_per_chain_incl_host": round(wall, 3)}
 

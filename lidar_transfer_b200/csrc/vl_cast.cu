@@ -542,6 +542,19 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const float*
   int it = 0;
   for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
     const int cb = it % 3, qb = it & 1;
+#ifndef VL_NO_SETUP_PREFETCH
+    {   // the faces (a soup: the vertices) of this CTA's NEXT batch start their way from DRAM to L2 now: one line per thread
+      const int nb = batch + gridDim.x;
+      if (nb < n_batches) {
+        const size_t per = faces ? 12 : 36;
+        const char* p = faces ? reinterpret_cast<const char*>(faces) + (size_t)nb * kBatch * 12
+                              : reinterpret_cast<const char*>(verts) + (size_t)nb * kBatch * 36;
+        const size_t bytes = (size_t)min(kBatch, n_faces - nb * kBatch) * per;
+        for (size_t o = (size_t)threadIdx.x * 128; o < bytes; o += (size_t)kCastThreads * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+      }
+    }
+#endif
     // ---- cull
     int idx[kBatch / kCastThreads][3];
 #pragma unroll
