@@ -203,7 +203,8 @@ int vl_trace_bruteforce(const float* d_verts, const int* d_faces, const int* d_c
 /* ------------------------------------------------------------------------------------
  * (iii) spherical range-image projection (atomicMin-on-depth scatter).
  *
- * Replaces: LaserScan.do_range_projection_new(method="depth") auxiliary/laserscan.py:294-391
+ * Replaces: LaserScan.do_range_projection_new auxiliary/laserscan.py:294-442 (method="depth" :369-391; the other two
+ * methods through vl_project_select)
  * and SemLaserScan.do_label_projection_new :672-676.
  * d_points float64[3*n] (the reference holds float64 after the pose round trip),
  * d_remissions float32[n], d_labels uint32[n].  fov in degrees.  remove != 0 applies the
@@ -228,6 +229,27 @@ int vl_project_snap(const double* d_points, const float* d_remissions, const uin
                     float* d_range, int32_t* d_index, int32_t* d_label, float* d_rem,
                     uint8_t* d_keep, int* d_n_kept, void* d_workspace, size_t workspace_bytes,
                     vl_stream stream);
+/* The same with the reference's `method` argument (auxiliary/laserscan.py:294-295):
+ *   VL_PROJECT_DEPTH      'depth'     :369-391  the nearest point per pixel (what deform() uses; = vl_project_snap);
+ *   VL_PROJECT_PDIST      'pdist'     :392-416  the point whose image position (proj_y, proj_x) is nearest to the pixel
+ *                                     centre -- like 'depth' a float64 quantity compared with the float32 image it was last
+ *                                     stored in, so the same single atomicMin key reproduces the sequential loop; d_range holds the
+ *                                     winner's DEPTH (:405).  d_rem holds the winner's remission (the reference's 'pdist'
+ *                                     never writes proj_remissions; the Python mirror leaves it at -1);
+ *   VL_PROJECT_DEPTHFAST  'depthfast' :418-437  the nearest point per pixel by descending argsort + fancy-index assignment:
+ *                                     float64 depths compared exactly, empty pixels of d_range are -1 (proj_range's initial
+ *                                     value); among EQUAL depths the reference's winner is whatever numpy's unstable
+ *                                     argsort leaves last -- here the smallest index.
+ * Pinned by tests/golden/golden_methods_v1.npz (the reference's own Python on the fixture scan). */
+#define VL_PROJECT_DEPTH     0
+#define VL_PROJECT_PDIST     1
+#define VL_PROJECT_DEPTHFAST 2
+int vl_project_select(const double* d_points, const float* d_remissions, const uint32_t* d_labels,
+                      long n_points, double fov_up_deg, double fov_down_deg, int H, int W, int remove,
+                      const double* d_beam_angles, int n_beam_angles, int method,
+                      float* d_range, int32_t* d_index, int32_t* d_label, float* d_rem,
+                      uint8_t* d_keep, int* d_n_kept, void* d_workspace, size_t workspace_bytes,
+                      vl_stream stream);
 
 /* Axis-aligned bounds of the points the projection kept: replaces SemLaserScan.get_bnds (auxiliary/laserscan.py:
  * np.amin / np.amax over the points after remove_points), which `mergemesh` clips the volume to (laserscan.py:957-962).

@@ -59,6 +59,7 @@ SIGNATURES = {
     "vl_project_workspace_bytes": (_sz, [_l, _i, _i]),
     "vl_project": (_i, [_vp, _vp, _vp, _l, _d, _d, _i, _i, _i] + [_vp] * 7 + [_sz, _vp]),
     "vl_project_snap": (_i, [_vp, _vp, _vp, _l, _d, _d, _i, _i, _i, _vp, _i] + [_vp] * 7 + [_sz, _vp]),
+    "vl_project_select": (_i, [_vp, _vp, _vp, _l, _d, _d, _i, _i, _i, _vp, _i, _i] + [_vp] * 7 + [_sz, _vp]),
     "vl_points_bounds": (_i, [_vp, _vp, _l, _vp, _vp]),
     "vl_reverse_project": (_i, [_vp, _vp, _vp, _i, _i, _d, _d, _vp, _vp]),
     "vl_tsdf_init": (_i, [_vp] * 4 + [_ll, _vp]),

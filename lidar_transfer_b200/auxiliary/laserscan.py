@@ -212,12 +212,13 @@ class LaserScan(_LazyAttrs):
     """Nearest-point-per-pixel projection (laserscan.py:294-391) as one atomicMin scatter on the device.  The images
     stay on the device (`_proj_dev`, what deform() feeds to the TSDF integration); every host attribute the reference
     sets here is a thunk with the reference's value."""
-    if method != "depth":
-      raise NotImplementedError("only method='depth' (the one deform() uses, laserscan.py:952) runs on the device")
+    if method not in engine.PROJECT_METHODS:
+      quit()   # laserscan.py:441-442
     pts = np.ascontiguousarray(self.points, np.float64)
     out = engine.project(pts, np.ascontiguousarray(self.remissions, np.float32),
                          np.ascontiguousarray(self.label).astype(np.uint32), fov_up, fov_down, self.proj_H, self.proj_W,
-                         remove=remove, beam_angles=self.beam_angles if self.beam_angles else None, want_bounds=True)
+                         remove=remove, beam_angles=self.beam_angles if self.beam_angles else None, want_bounds=True,
+                         method=method)
     meta = out["meta"].cpu().numpy()            # one 64-byte copy: bounds of the kept points + their number
     if int(meta[48:52].view(np.int32)[0]) == 0:  # the reference fails the same way at :384 (fancy index into an empty array)
       raise IndexError("do_range_projection_new: no point left after the depth / field-of-view filters")
@@ -231,9 +232,41 @@ class LaserScan(_LazyAttrs):
       keep_fn = _once(lambda: np.linalg.norm(pts, 2, axis=1) != 0)
       self._bnds = None
     self._remove_points_deferred(keep_fn)
+    if method == "depthfast":
+      # :418-437: the winners go into proj_range / proj_xyz / proj_remissions / proj_idx (which start at -1, :88-100 of this
+      # file), index / range_image / label images keep their initial values except range_image = proj_range (:433)
+      self._lazy_set("proj_idx", lambda: out["index"].cpu().numpy())
+      self._lazy_set("proj_range", lambda: out["range_image"].cpu().numpy())
+      self._lazy_set("proj_remissions", lambda: out["proj_remissions"].cpu().numpy())
+      self._lazy_set("range_image", lambda: self.proj_range)
+      self._lazy_set("index", lambda: np.full((H, W), -1, dtype=np.int32))
+      self._lazy_set("label_image", lambda: np.zeros((H, W, 1)))
+      self._lazy_set("label_color_image", lambda: np.zeros((H, W, 3)))
+
+      def proj_xyz():
+        im = np.full((H, W, 3), -1, dtype=np.float32)
+        mask = self.proj_idx >= 0
+        im[mask] = self.points[self.proj_idx[mask]]
+        return im
+      self._lazy_set("proj_xyz", proj_xyz)
+
+      def sorted_coords():   # per-POINT arrays in the reference's order (:420-421, numpy's own unstable argsort)
+        depth = np.linalg.norm(self.points, 2, axis=1)
+        fu, fd = fov_up / 180.0 * np.pi, fov_down / 180.0 * np.pi
+        xf = 0.5 * (-np.arctan2(self.points[:, 1], self.points[:, 0]) / np.pi + 1.0) * W
+        yf = (1.0 - (np.arcsin(self.points[:, 2] / depth) + abs(fd)) / (abs(fd) + abs(fu))) * H
+        order = np.argsort(depth)[::-1]
+        px, py = self._clamp(xf, yf)
+        return xf[order], yf[order], px[order], py[order]
+      sorted_coords = _once(sorted_coords)
+      for k, name in enumerate(("proj_x_float", "proj_y_float", "proj_x2", "proj_y2")):
+        self._lazy_set(name, (lambda k: lambda: sorted_coords()[k])(k))
+      return
     self._lazy_set("index", lambda: out["index"].cpu().numpy())
     self._lazy_set("range_image", lambda: out["range_image"].cpu().numpy())
-    self._lazy_set("proj_remissions", lambda: out["proj_remissions"].cpu().numpy())
+    # 'pdist' never writes proj_remissions (:392-416): it keeps the -1 of :366-367
+    self._lazy_set("proj_remissions", (lambda: np.full((H, W), -1, dtype=np.float32)) if method == "pdist"
+                   else (lambda: out["proj_remissions"].cpu().numpy()))
     self._lazy_set("proj_range", lambda: self.range_image)
 
     def label_image():
@@ -249,7 +282,8 @@ class LaserScan(_LazyAttrs):
       return im
     self._lazy_set("label_image", label_image)
     self._lazy_set("label_color_image", label_color_image)
-    self._lazy_set("unproj_range", lambda: np.linalg.norm(self.points, 2, axis=1))
+    if method == "depth":
+      self._lazy_set("unproj_range", lambda: np.linalg.norm(self.points, 2, axis=1))
 
     # per-pixel image coordinates of the winning point (float and clamped), laserscan.py:384-388
     def coords():
@@ -267,6 +301,13 @@ class LaserScan(_LazyAttrs):
     coords = _once(coords)
     for k, name in enumerate(("proj_x_float", "proj_y_float", "proj_x", "proj_y")):
       self._lazy_set(name, (lambda k: lambda: coords()[k])(k))
+    if method == "pdist":   # :393-401 distance of the winner's image position from its pixel centre, 1000 where no point fell
+      def dist_image():
+        xf, yf, px, py = coords()
+        with np.errstate(invalid="ignore"):
+          d = np.sqrt((yf - (py + 0.5)) ** 2 + (xf - (px + 0.5)) ** 2)
+        return np.where(self.index >= 0, d, 1000).astype(np.float32)
+      self._lazy_set("dist_image", dist_image)
 
   def do_reverse_projection_new(self, fov_up, fov_down, preserve_float=False, host=False):
     """Pixel + depth -> xyz (laserscan.py:475-501), the `cp` adaption's back projection, on the device

@@ -21,7 +21,51 @@ constexpr int kThreads = 256;
 struct ProjParams {
   double fov_down_abs, fov, pi;
   int H, W, remove;
+  int method;   // VL_PROJECT_DEPTH (laserscan.py:369-391), VL_PROJECT_PDIST (:392-416), VL_PROJECT_DEPTHFAST (:418-437)
 };
+
+// One point through laserscan.py:304-360: kept or not, its pixel, its depth and the quantity the method orders by --
+// the depth, or ('pdist', :399-400) the distance of its image position from the pixel centre,
+// np.linalg.norm([proj_y, proj_x] - [py + 0.5, px + 0.5]) = sqrt(a * a + b * b) in float64.
+struct PointPix { bool keep; int pix; double depth, q; };
+
+__device__ __forceinline__ PointPix point_pixel(const double* __restrict__ pts, long i, const ProjParams& P,
+                                                const double* __restrict__ beam_angles, int n_beam_angles) {
+  PointPix r;
+  r.keep = false; r.pix = 0; r.q = 0.0;
+  const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+  const double depth = sqrt((x * x + y * y) + z * z);  // np.linalg.norm(points, 2, axis=1), :304
+  r.depth = depth;
+  if (depth != 0.0) {                                   // :307-309
+    const double yaw = -atan2(y, x);
+    double pitch = asin(z / depth);
+    if (n_beam_angles > 0) {  // :321-327  pitch <- the list entry nearest to it (argmin: first minimum)
+      int best = 0;
+      double best_d = fabs(pitch - __ldg(beam_angles));
+      for (int k = 1; k < n_beam_angles; ++k) {
+        const double d = fabs(pitch - __ldg(beam_angles + k));
+        if (d < best_d) { best_d = d; best = k; }
+      }
+      pitch = __ldg(beam_angles + best);
+    }
+    double proj_x = 0.5 * (yaw / P.pi + 1.0);           // :329-330
+    double proj_y = 1.0 - (pitch + P.fov_down_abs) / P.fov;
+    if (!P.remove || (proj_y >= 0.0 && proj_y <= 1.0)) {  // :337-345
+      proj_x *= P.W;
+      proj_y *= P.H;
+      const double fx = fmax(0.0, fmin((double)(P.W - 1), floor(proj_x)));  // :355-360
+      const double fy = fmax(0.0, fmin((double)(P.H - 1), floor(proj_y)));
+      r.pix = (int)fy * P.W + (int)fx;
+      r.keep = true;
+      r.q = depth;
+      if (P.method == VL_PROJECT_PDIST) {
+        const double a = proj_y - ((double)(int)fy + 0.5), b = proj_x - ((double)(int)fx + 0.5);
+        r.q = sqrt(a * a + b * b);
+      }
+    }
+  }
+  return r;
+}
 
 __global__ void __launch_bounds__(kThreads)
 k_project_scatter(const double* __restrict__ pts, long n, ProjParams P, const double* __restrict__ beam_angles,
@@ -30,32 +74,18 @@ k_project_scatter(const double* __restrict__ pts, long n, ProjParams P, const do
   const long i = (long)blockIdx.x * kThreads + threadIdx.x;
   bool keep = false;
   if (i < n) {
-    const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
-    const double depth = sqrt((x * x + y * y) + z * z);  // np.linalg.norm(points, 2, axis=1), :304
-    if (depth != 0.0) {                                   // :307-309
-      const double yaw = -atan2(y, x);
-      double pitch = asin(z / depth);
-      if (n_beam_angles > 0) {  // :321-327  pitch <- the list entry nearest to it (argmin: first minimum)
-        int best = 0;
-        double best_d = fabs(pitch - __ldg(beam_angles));
-        for (int k = 1; k < n_beam_angles; ++k) {
-          const double d = fabs(pitch - __ldg(beam_angles + k));
-          if (d < best_d) { best_d = d; best = k; }
-        }
-        pitch = __ldg(beam_angles + best);
-      }
-      double proj_x = 0.5 * (yaw / P.pi + 1.0);           // :329-330
-      double proj_y = 1.0 - (pitch + P.fov_down_abs) / P.fov;
-      if (!P.remove || (proj_y >= 0.0 && proj_y <= 1.0)) {  // :337-345
-        proj_x *= P.W;
-        proj_y *= P.H;
-        double fx = fmax(0.0, fmin((double)(P.W - 1), floor(proj_x)));  // :355-360
-        double fy = fmax(0.0, fmin((double)(P.H - 1), floor(proj_y)));
-        const int pix = (int)fy * P.W + (int)fx;
-        const float R = (float)depth;
-        const unsigned int lo = (depth < (double)R) ? (0x7fffffffu - (unsigned int)i) : (0x80000000u | (unsigned int)i);
-        atomicMin(keys + pix, ((unsigned long long)__float_as_uint(R) << 32) | lo);
-        keep = true;
+    const PointPix pp = point_pixel(pts, i, P, beam_angles, n_beam_angles);
+    keep = pp.keep;
+    if (keep) {
+      if (P.method == VL_PROJECT_DEPTHFAST) {
+        // the smallest float64 depth per pixel (bits of a positive double order like its value); the index follows in
+        // k_project_select
+        atomicMin(keys + pp.pix, (unsigned long long)__double_as_longlong(pp.depth));
+      } else {
+        // 'depth' and 'pdist' both compare a float64 quantity against the float32 image it was last stored in
+        const float R = (float)pp.q;
+        const unsigned int lo = (pp.q < (double)R) ? (0x7fffffffu - (unsigned int)i) : (0x80000000u | (unsigned int)i);
+        atomicMin(keys + pp.pix, ((unsigned long long)__float_as_uint(R) << 32) | lo);
       }
     }
     if (keep_out) keep_out[i] = keep ? 1 : 0;
@@ -65,6 +95,17 @@ k_project_scatter(const double* __restrict__ pts, long n, ProjParams P, const do
     const long w = i >> 5;
     if (w * 32 < n) { masks[w] = m; warp_counts[w] = __popc(m); }
   }
+}
+
+// 'depthfast', second pass: among the points whose depth IS the pixel's minimum the smallest index (the reference's
+// winner among equal depths is whatever numpy's unstable argsort leaves last: unspecified)
+__global__ void __launch_bounds__(kThreads)
+k_project_select(const double* __restrict__ pts, long n, ProjParams P, const double* __restrict__ beam_angles,
+                 int n_beam_angles, const unsigned long long* __restrict__ keys, unsigned int* __restrict__ winner) {
+  const long i = (long)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const PointPix pp = point_pixel(pts, i, P, beam_angles, n_beam_angles);
+  if (pp.keep && (unsigned long long)__double_as_longlong(pp.depth) == keys[pp.pix]) atomicMin(winner + pp.pix, (unsigned int)i);
 }
 
 // single-CTA exclusive scan of the per-warp kept counts (n/32 entries); total -> n_kept
@@ -120,17 +161,29 @@ __global__ void __launch_bounds__(kThreads)
 k_project_gather(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ masks,
                  const unsigned int* __restrict__ warp_prefix, const float* __restrict__ remissions,
                  const uint32_t* __restrict__ labels, int n_pix, float* __restrict__ range, int32_t* __restrict__ index,
-                 int32_t* __restrict__ label, float* __restrict__ rem) {
+                 int32_t* __restrict__ label, float* __restrict__ rem, int method, const double* __restrict__ pts,
+                 const unsigned int* __restrict__ winner) {
   const int p = blockIdx.x * kThreads + threadIdx.x;
   if (p >= n_pix) return;
   const unsigned long long key = keys[p];
-  if (key == ~0ull) {  // :362-367 initial values
-    range[p] = 0.0f; index[p] = -1; label[p] = 0; rem[p] = -1.0f;
+  if (key == ~0ull) {  // :362-367 initial values ('depthfast' writes into proj_range, which starts at -1)
+    range[p] = method == VL_PROJECT_DEPTHFAST ? -1.0f : 0.0f; index[p] = -1; label[p] = 0; rem[p] = -1.0f;
     return;
   }
-  const unsigned int lo = (unsigned int)key;
-  const unsigned int i = (lo & 0x80000000u) ? (lo & 0x7fffffffu) : (0x7fffffffu - lo);
-  range[p] = __uint_as_float((unsigned int)(key >> 32));
+  unsigned int i;
+  if (method == VL_PROJECT_DEPTHFAST) {
+    i = winner[p];
+    range[p] = (float)__longlong_as_double((long long)key);   // :428 float64 depth stored into the float32 image
+  } else {
+    const unsigned int lo = (unsigned int)key;
+    i = (lo & 0x80000000u) ? (lo & 0x7fffffffu) : (0x7fffffffu - lo);
+    if (method == VL_PROJECT_PDIST) {   // the key holds the distance to the pixel centre; the image gets the point's depth (:405)
+      const double x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
+      range[p] = (float)sqrt((x * x + y * y) + z * z);
+    } else {
+      range[p] = __uint_as_float((unsigned int)(key >> 32));
+    }
+  }
   index[p] = (int)(warp_prefix[i >> 5] + __popc(masks[i >> 5] & ((1u << (i & 31)) - 1u)));
   label[p] = (int32_t)labels[i];   // :672-676
   rem[p] = remissions[i];
@@ -225,15 +278,19 @@ extern "C" int vl_reverse_project(const float* d_depth_im, const double* d_proj_
 
 extern "C" size_t vl_project_workspace_bytes(long n_points, int H, int W) {
   size_t nw = (size_t)((n_points + 31) / 32) + 1;
-  return vl_align256(8 * (size_t)H * W) + 2 * vl_align256(4 * nw);
+  return vl_align256(8 * (size_t)H * W) + 2 * vl_align256(4 * nw) + vl_align256(4 * (size_t)H * W);   // keys, masks, counts, 'depthfast' winners
 }
 
-extern "C" int vl_project_snap(const double* d_points, const float* d_remissions, const uint32_t* d_labels,
-                               long n_points, double fov_up_deg, double fov_down_deg, int H, int W, int remove,
-                               const double* d_beam_angles, int n_beam_angles, float* d_range, int32_t* d_index,
-                               int32_t* d_label, float* d_rem, uint8_t* d_keep, int* d_n_kept, void* d_workspace,
-                               size_t workspace_bytes, vl_stream stream_) {
+extern "C" int vl_project_select(const double* d_points, const float* d_remissions, const uint32_t* d_labels,
+                                 long n_points, double fov_up_deg, double fov_down_deg, int H, int W, int remove,
+                                 const double* d_beam_angles, int n_beam_angles, int method, float* d_range, int32_t* d_index,
+                                 int32_t* d_label, float* d_rem, uint8_t* d_keep, int* d_n_kept, void* d_workspace,
+                                 size_t workspace_bytes, vl_stream stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (method != VL_PROJECT_DEPTH && method != VL_PROJECT_PDIST && method != VL_PROJECT_DEPTHFAST) {
+    vl_set_error("vl_project: unknown method %d", method);
+    return VL_EINVAL;
+  }
   if (H <= 0 || W <= 0 || n_points < 0 || n_points >= 0x7fffffffL || !d_range || !d_index || !d_label || !d_rem ||
       !d_workspace || (n_points > 0 && (!d_points || !d_remissions || !d_labels)) || n_beam_angles < 0 ||
       (n_beam_angles > 0 && !d_beam_angles)) {
@@ -249,12 +306,13 @@ extern "C" int vl_project_snap(const double* d_points, const float* d_remissions
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws);
   unsigned int* masks = reinterpret_cast<unsigned int*>(ws + vl_align256(8 * (size_t)H * W));
   unsigned int* counts = reinterpret_cast<unsigned int*>(ws + vl_align256(8 * (size_t)H * W) + vl_align256(4 * (nw + 1)));
+  unsigned int* winner = reinterpret_cast<unsigned int*>(ws + vl_align256(8 * (size_t)H * W) + 2 * vl_align256(4 * (nw + 1)));
   ProjParams P;
   P.pi = 3.141592653589793;  // np.pi
   const double fov_up = fov_up_deg / 180.0 * P.pi, fov_down = fov_down_deg / 180.0 * P.pi;  // :299-301
   P.fov_down_abs = fabs(fov_down);
   P.fov = fabs(fov_down) + fabs(fov_up);
-  P.H = H; P.W = W; P.remove = remove;
+  P.H = H; P.W = W; P.remove = remove; P.method = method;
   VL_CUDA_CHECK(cudaMemsetAsync(keys, 0xff, 8 * (size_t)H * W, stream));
   if (n_points > 0) {
     const int nb = (int)((n_points + kThreads - 1) / kThreads);
@@ -262,15 +320,31 @@ extern "C" int vl_project_snap(const double* d_points, const float* d_remissions
     k_project_scatter<<<nb, kThreads, 0, stream>>>(d_points, n_points, P, d_beam_angles, n_beam_angles, keys, masks, counts,
                                                    d_keep);
     VL_LAUNCH_CHECK("k_project_scatter");
+    if (method == VL_PROJECT_DEPTHFAST) {
+      VL_CUDA_CHECK(cudaMemsetAsync(winner, 0xff, 4 * (size_t)H * W, stream));
+      k_project_select<<<nb, kThreads, 0, stream>>>(d_points, n_points, P, d_beam_angles, n_beam_angles, keys, winner);
+      VL_LAUNCH_CHECK("k_project_select");
+    }
   }
   k_scan_counts<<<1, 1024, 0, stream>>>(counts, (long)nw, d_n_kept);
   VL_LAUNCH_CHECK("k_scan_counts");
   const int n_pix = H * W;
   VlProfScope ps(VL_ST_PROJECT_GATHER, stream);
   k_project_gather<<<(n_pix + kThreads - 1) / kThreads, kThreads, 0, stream>>>(keys, masks, counts, d_remissions, d_labels,
-                                                                             n_pix, d_range, d_index, d_label, d_rem);
+                                                                             n_pix, d_range, d_index, d_label, d_rem, method, d_points,
+                                                                             winner);
   VL_LAUNCH_CHECK("k_project_gather");
   return VL_OK;
+}
+
+extern "C" int vl_project_snap(const double* d_points, const float* d_remissions, const uint32_t* d_labels,
+                               long n_points, double fov_up_deg, double fov_down_deg, int H, int W, int remove,
+                               const double* d_beam_angles, int n_beam_angles, float* d_range, int32_t* d_index,
+                               int32_t* d_label, float* d_rem, uint8_t* d_keep, int* d_n_kept, void* d_workspace,
+                               size_t workspace_bytes, vl_stream stream) {
+  return vl_project_select(d_points, d_remissions, d_labels, n_points, fov_up_deg, fov_down_deg, H, W, remove, d_beam_angles,
+                           n_beam_angles, VL_PROJECT_DEPTH, d_range, d_index, d_label, d_rem, d_keep, d_n_kept, d_workspace,
+                           workspace_bytes, stream);
 }
 
 extern "C" int vl_project(const double* d_points, const float* d_remissions, const uint32_t* d_labels, long n_points,

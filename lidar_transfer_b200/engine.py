@@ -236,8 +236,11 @@ def trace_bruteforce(verts, faces, colors, rem, rays, origin, height, out=None, 
   return out
 
 
+PROJECT_METHODS = {"depth": 0, "pdist": 1, "depthfast": 2}   # VL_PROJECT_* of include/vlidar.h
+
+
 def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, workspace=None, beam_angles=None,
-            want_bounds=False, out=None, want_keep=True):
+            want_bounds=False, out=None, want_keep=True, method="depth"):
   """(iii) spherical range-image projection, the device equivalent of
   LaserScan.do_range_projection_new('depth') + do_label_projection_new
   (auxiliary/laserscan.py:294-391, 672-676).
@@ -248,6 +251,8 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, wor
   beam_angles (non-empty sequence): the pitch snapping of laserscan.py:321-327 (vl_project_snap).
   want_bounds: also `bounds` f64[6] = min xyz, max xyz of the kept points (SemLaserScan.get_bnds on the device,
   vl_points_bounds); `bounds` and `n_kept` then share one 64-byte buffer `meta` (a single small D2H for both).
+  method: 'depth' (default, :369-391), 'pdist' (:392-416: range_image / index / proj_label of the point nearest to the
+  pixel centre) or 'depthfast' (:418-437: range_image starts at -1) -- vl_project_select.
   out: the dict of an earlier call with the same H, W -- its tensors are written again instead of allocating new ones
   (pipeline.ScanPipeline: no allocation per scan); want_keep=False leaves `keep` as the raw uint8 buffer."""
   require_cuda()
@@ -287,9 +292,9 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, wor
     meta = torch.zeros(64, dtype=torch.uint8, device=dev)
     out["meta"], out["bounds"], out["n_kept"] = meta, meta[:48].view(torch.float64), meta[48:52].view(torch.int32)
   with torch.cuda.device(dev):
-    check(lib().vl_project_snap(_ptr(points), _ptr(remissions), _ptr(labels), n, float(fov_up), float(fov_down), H, W,
+    check(lib().vl_project_select(_ptr(points), _ptr(remissions), _ptr(labels), n, float(fov_up), float(fov_down), H, W,
                                 1 if remove else 0, _ptr(ba) if ba is not None else None,
-                                ba.numel() if ba is not None else 0, _ptr(out["range_image"]), _ptr(out["index"]),
+                                ba.numel() if ba is not None else 0, PROJECT_METHODS[method], _ptr(out["range_image"]), _ptr(out["index"]),
                                 _ptr(out["proj_label"]), _ptr(out["proj_remissions"]), _ptr(out["keep"]),
                                 _ptr(out["n_kept"]), _ptr(workspace), workspace.numel(), _stream()))
     if want_bounds:

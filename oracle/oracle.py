@@ -173,9 +173,13 @@ def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, bea
   return out
 
 
-def project_numpy(points, remissions, labels, fov_up, fov_down, H, W, remove=True, beam_angles=None):
+def project_numpy(points, remissions, labels, fov_up, fov_down, H, W, remove=True, beam_angles=None, method="depth"):
   """Pure-numpy/Python-loop restatement of the same projection (small inputs only);
-  line-for-line semantics of auxiliary/laserscan.py:294-391 used to cross-check vlo_project."""
+  line-for-line semantics of auxiliary/laserscan.py:294-391 used to cross-check vlo_project.
+  method: 'depth' (:369-391), 'pdist' (:392-416: the point nearest to the pixel centre, compared against a float32
+  image like 'depth'; proj_remissions is never written) or 'depthfast' (:418-437: descending argsort + fancy-index
+  assignment, last write wins = the smallest depth; images start at -1; among EQUAL depths the reference's winner is
+  whatever numpy's unstable argsort leaves last -- here the smallest index).  Pinned by tests/golden/golden_methods_v1.npz."""
   points = np.asarray(points, np.float64).reshape(-1, 3)
   remissions = np.asarray(remissions, np.float32)
   labels = np.asarray(labels, np.uint32)
@@ -205,11 +209,28 @@ def project_numpy(points, remissions, labels, fov_up, fov_down, H, W, remove=Tru
   index = np.full((H, W), -1, np.int32)
   range_image = np.zeros((H, W), np.float32)
   proj_rem = np.full((H, W), -1, np.float32)
-  for i in range(len(depth)):
-    if depth[i] < range_image[py[i], px[i]] or index[py[i], px[i]] == -1:
-      range_image[py[i], px[i]] = depth[i]
-      index[py[i], px[i]] = i
-      proj_rem[py[i], px[i]] = remissions[i]
+  if method == "depth":
+    for i in range(len(depth)):
+      if depth[i] < range_image[py[i], px[i]] or index[py[i], px[i]] == -1:
+        range_image[py[i], px[i]] = depth[i]
+        index[py[i], px[i]] = i
+        proj_rem[py[i], px[i]] = remissions[i]
+  elif method == "pdist":
+    dist_image = np.full((H, W), 1000, np.float32)
+    for i in range(len(depth)):
+      dist = np.linalg.norm(np.array([proj_y[i], proj_x[i]]) - np.array([py[i] + 0.5, px[i] + 0.5]))
+      if dist < dist_image[py[i], px[i]]:
+        dist_image[py[i], px[i]] = dist
+        range_image[py[i], px[i]] = depth[i]
+        index[py[i], px[i]] = i
+  elif method == "depthfast":
+    range_image[:] = -1
+    order = np.lexsort((np.arange(len(depth)), depth))[::-1]   # depth descending; equal depths: the smaller index is written last
+    range_image[py[order], px[order]] = depth[order]
+    proj_rem[py[order], px[order]] = remissions[order]
+    index[py[order], px[order]] = np.arange(len(depth))[order]
+  else:
+    raise ValueError(method)
   proj_label = np.zeros((H, W), np.int32)
   mask = index >= 0
   proj_label[mask] = labels[index[mask]]

@@ -161,3 +161,23 @@ def test_compare_restatement_matches_reference_golden(oracle):
     m_iou, m_acc, mse = G["cmp_%s_scalars" % tag]
     assert r["m_iou"] == m_iou and r["m_acc"] == m_acc and np.float64(r["mse"]) == mse, (tag, r["m_iou"], r["m_acc"], r["mse"])
     assert r["conf"].sum() == a["source_label"].size
+
+
+@pytest.mark.parametrize("method", ["pdist", "depthfast"])
+@pytest.mark.parametrize("remove", [1, 0])
+def test_projection_methods_pdist_and_depthfast_match_the_reference(oracle, method, remove):
+  """The two projection methods no caller of the reference selects (laserscan.py:392-437), restated in
+  oracle.project_numpy and pinned to the reference's own Python (tests/golden/make_golden_methods.py)."""
+  M = np.load(os.path.join(os.path.dirname(GOLDEN), "golden_methods_v1.npz"))
+  fu, fd, H, W = M["args"]
+  o = oracle.project_numpy(M["points_f32"].astype(np.float64), M["rem"], M["label"], fu, fd, int(H), int(W), remove=bool(remove),
+                           method=method)
+  k = "%s_%d_" % (method, remove)
+  assert o["n_kept"] == int(M[k + "n_kept"][0])
+  assert np.array_equal(o["index"], M[k + "index"]) and (o["index"] >= 0).sum() > 1500
+  assert np.array_equal(o["range_image"].view(np.int32), M[k + "range"].view(np.int32))
+  assert np.array_equal(o["proj_remissions"], M[k + "rem"])
+  if method == "pdist":
+    assert np.array_equal(o["proj_label"], M[k + "label"].astype(np.int32)) and (M[k + "rem"] == -1).all()
+  else:
+    assert (M[k + "range"][M[k + "index"] < 0] == -1).all()

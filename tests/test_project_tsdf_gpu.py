@@ -266,3 +266,68 @@ def test_reverse_projection_on_device_matches_reference_golden(engine):
       assert s.back_points.shape == ref.shape and np.allclose(s.back_points, ref, rtol=0, atol=1e-9), (tag, pf)
       s.do_reverse_projection_new(fu, fd, preserve_float=pf, host=True)
       assert np.allclose(s.back_points, ref, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("method", ["pdist", "depthfast"])
+@pytest.mark.parametrize("remove", [True, False])
+def test_projection_methods_pdist_and_depthfast(engine, oracle, method, remove):
+  """vl_project_select against the reference's own Python (golden_methods_v1.npz: fixture scan, 16 x 128 image, ~16 points
+  per pixel) and against the oracle restatement on a random cloud with exact duplicates (equal depths, equal image
+  positions): range / index / label (/ remission) images bit for bit."""
+  import os
+  M = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_methods_v1.npz"))
+  fu, fd, H, W = M["args"]
+  H, W = int(H), int(W)
+  k = "%s_%d_" % (method, int(remove))
+  g = engine.project(M["points_f32"].astype(np.float64), M["rem"], M["label"], fu, fd, H, W, remove=remove, method=method)
+  assert int(g["n_kept"].item()) == int(M[k + "n_kept"][0])
+  assert np.array_equal(g["index"].cpu().numpy(), M[k + "index"])
+  assert np.array_equal(g["range_image"].cpu().numpy().view(np.int32), M[k + "range"].view(np.int32))
+  if method == "pdist":
+    assert np.array_equal(g["proj_label"].cpu().numpy(), M[k + "label"].astype(np.int32))
+  else:
+    assert np.array_equal(g["proj_remissions"].cpu().numpy(), M[k + "rem"])
+  # random cloud, every fifth point repeated later on (ties in depth and in image position)
+  rng = np.random.default_rng(17)
+  pts = rng.normal(size=(6000, 3)) * np.array([20.0, 20.0, 2.0])
+  pts = np.concatenate([pts, pts[::5], np.zeros((3, 3))])
+  rem = rng.random(pts.shape[0], dtype=np.float32)
+  lab = rng.integers(0, 300, pts.shape[0]).astype(np.uint32)
+  o = oracle.project_numpy(pts, rem, lab, 10.0, -30.0, 24, 96, remove=remove, method=method)
+  g = engine.project(pts, rem, lab, 10.0, -30.0, 24, 96, remove=remove, method=method)
+  assert int(g["n_kept"].item()) == o["n_kept"]
+  assert np.array_equal(g["index"].cpu().numpy(), o["index"])
+  assert np.array_equal(g["range_image"].cpu().numpy().view(np.int32), o["range_image"].view(np.int32))
+  assert np.array_equal(g["proj_label"].cpu().numpy(), o["proj_label"])
+  if method == "depthfast":
+    assert np.array_equal(g["proj_remissions"].cpu().numpy(), o["proj_remissions"])
+
+
+def test_shim_projection_methods_set_the_reference_attributes(engine):
+  """SemLaserScan.do_range_projection_new(method=...) of the drop-in package leaves the attributes the reference's
+  methods leave (laserscan.py:392-437), values from the reference's own run."""
+  import os
+  from lidar_transfer_b200.auxiliary import laserscan as ls
+  M = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_methods_v1.npz"))
+  fu, fd, H, W = M["args"]
+  lut = {int(v): [int(v) % 255, 3, 7] for v in np.unique(M["label"])}
+  for method in ("pdist", "depthfast"):
+    s = ls.SemLaserScan(int(H), int(W), max(lut) + 1, color_dict=lut)
+    s.points, s.remissions, s.label = M["points_f32"].astype(np.float64), M["rem"].copy(), M["label"].copy()
+    s.colorize()
+    s.do_range_projection_new(fu, fd, remove=True, method=method)
+    k = method + "_1_"
+    assert s.points.shape[0] == int(M[k + "n_kept"][0])
+    if method == "pdist":
+      assert np.array_equal(s.index, M[k + "index"]) and np.array_equal(s.range_image, M[k + "range"])
+      assert np.array_equal(s.label_image[..., 0], M[k + "label"]) and (s.proj_remissions == -1).all()
+      assert s.proj_range is s.range_image or np.array_equal(s.proj_range, s.range_image)
+      assert np.allclose(s.dist_image, M[k + "dist"], rtol=0, atol=1e-6)
+      filled = s.index >= 0
+      assert np.array_equal(np.asarray(s.proj_y_float)[filled], M[k + "proj_y_float"][filled])
+    else:
+      assert np.array_equal(s.proj_idx, M[k + "index"]) and np.array_equal(s.proj_range, M[k + "range"])
+      assert np.array_equal(s.proj_remissions, M[k + "rem"]) and np.array_equal(s.proj_xyz, M[k + "xyz"])
+      assert np.array_equal(s.range_image, s.proj_range) and (s.index == -1).all()
+  with pytest.raises(SystemExit):
+    s.do_range_projection_new(fu, fd, method="nearest")
