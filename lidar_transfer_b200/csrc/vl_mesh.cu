@@ -44,7 +44,19 @@ constexpr int kEmitTris = 256;                   // triangles per k_mesh_emit CT
 struct MeshParams {
   int dx, dy, dz;
   float level, voxel_size, ox, oy, oz;
+  unsigned long long m_yz, m_dz;   // floor(2^64 / d) + 1 for d = dy * dz, dz (0 when d == 1): vi / d = umul64hi(vi, m), see fast_div
 };
+
+// n / d for n < 2^32 by one 64 x 64 -> high 64 multiplication: with m = floor(2^64 / d) + 1 the product n * m / 2^64 exceeds
+// n / d by less than 2^-32 < 1 / d, so the floor is exact (d = 1 is passed as m = 0).
+__host__ inline unsigned long long fast_div_magic(unsigned int d) {
+  if (d <= 1u) return 0ull;
+  const unsigned long long q = ~0ull / d;                 // floor((2^64 - 1) / d)
+  return ((d & (d - 1u)) == 0u ? q + 1ull : q) + 1ull;    // a power of two divides 2^64: floor(2^64 / d) = q + 1
+}
+__device__ __forceinline__ int fast_div(int n, unsigned long long m) {
+  return m ? (int)__umul64hi((unsigned long long)(unsigned int)n, m) : n;
+}
 
 // Unit u of plane x (x = blockIdx.y) covers voxels j = y * dz + z in [u * kUnit, (u + 1) * kUnit) of that plane; the
 // linear unit id x * units_per_plane + u increases with the voxel index, so everything stays in cube order.
@@ -639,7 +651,7 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
     for (int step = kEmitTris / 2; step > 0; step >>= 1)
       if (s_first[lo + step] <= T) lo += step;
     const int vi = (int)s_vi[lo], t = (int)(T - s_first[lo]), yz = P.dy * P.dz;
-    const int x = vi / yz, jj = vi - x * yz, y = jj / P.dz, z = jj - y * P.dz;
+    const int x = fast_div(vi, P.m_yz), jj = vi - x * yz, y = fast_div(jj, P.m_dz), z = jj - y * P.dz;
     const float* cube0 = tsdf + vi;
     float v[8];
     int mc = 0;   // case index: bit c set when corner c (bit 0 x, bit 1 y, bit 2 z) is below the level
@@ -682,8 +694,9 @@ k_mesh_emit(const float* __restrict__ tsdf, const float* __restrict__ color_vol,
       }
       const float rgb = exists ? __ldg(color_vol + ni) : 0.f;
       // fusion_lidar.py:417-423 (float32 arithmetic, then astype(uint8) wraps modulo 256)
-      const float cb_ = floorf(__fdiv_rn(rgb, 65536.0f));
-      const float cg_ = floorf(__fdiv_rn(__fsub_rn(rgb, __fmul_rn(cb_, 65536.0f)), 256.0f));
+      // x / 2^k and x * 2^-k are the same correctly rounded number: the two divisions of :417-420 as multiplications
+      const float cb_ = floorf(__fmul_rn(rgb, 1.0f / 65536.0f));
+      const float cg_ = floorf(__fmul_rn(__fsub_rn(rgb, __fmul_rn(cb_, 65536.0f)), 1.0f / 256.0f));
       const float cr_ = __fsub_rn(__fsub_rn(rgb, __fmul_rn(cb_, 65536.0f)), __fmul_rn(cg_, 256.0f));
       const int vtx = 3 * tid + k;                             // vertex slot within the CTA
       s_c[3 * vtx + 0] = (unsigned char)((long long)floorf(cr_) & 255);
@@ -811,6 +824,7 @@ static int mesh_args(const char* who, const float* d_tsdf, int dx, int dy, int d
   }
   P->dx = dx; P->dy = dy; P->dz = dz; P->level = level; P->voxel_size = voxel_size;
   P->ox = origin ? origin[0] : 0.f; P->oy = origin ? origin[1] : 0.f; P->oz = origin ? origin[2] : 0.f;
+  P->m_yz = fast_div_magic((unsigned int)((long long)dy * dz)); P->m_dz = fast_div_magic((unsigned int)dz);
   return VL_OK;
 }
 
