@@ -311,19 +311,24 @@ void vl_debug_tsdf_shell(int mode);
  * the interval [z_lo, z_hi] of voxels that are materialised in the four arrays (z_lo | z_hi << 16; 1 | 0 << 16 = none);
  * a voxel outside its column's hull is in the initial state by definition (tsdf 1, weight / colour / remission 0) and
  * its memory is never read or written.  vl_tsdf_sparse_integrate: the integration of vl_tsdf_integrate into such a
- * volume -- fresh != 0: a NEW volume (the arrays' and d_hull's previous content is ignored: no reset pass at all);
+ * volume -- flags & VL_TSDF_FRESH: a NEW volume (the arrays' and d_hull's previous content is ignored: no reset pass at all);
+ * flags & VL_TSDF_TABLES_VALID: the caller's promise that d_workspace still holds the geometry tables (pixel column per
+ * z column, tangents per image row) an earlier call with the SAME dims, origin, voxel size, field of view and image size
+ * left there -- they depend on nothing else and are not rebuilt (20 us per integration at 2000 x 1420 columns);
  * the hull of a column grows to cover every voxel the reference kernel could change (a conservative interval derived
  * from the range image), voxels entering a hull are written (initial or integrated value), voxels already in it are
  * integrated like a later scan, nothing else is touched.  Same values as the dense calls for every voxel, bit for bit
  * (vl_tsdf_densify materialises the rest: afterwards the arrays are the dense volumes and every hull is the whole
  * column).  Outside the sweep's limits (see vl_tsdf_fresh_workspace_bytes; also dz <= 32767, fov_up >= 0 >= fov_down)
  * the call densifies and takes the dense path.  vl_mesh_count_sparse / vl_mesh_emit_sparse read sparse volumes. */
+#define VL_TSDF_FRESH        1
+#define VL_TSDF_TABLES_VALID 2
 size_t vl_tsdf_sparse_workspace_bytes(int dx, int dy, int im_h, int im_w);
 int vl_tsdf_sparse_integrate(float* d_tsdf, float* d_weight, float* d_color, float* d_rem,
                              int dx, int dy, int dz, const float vol_origin[3], float voxel_size,
                              float trunc_margin, float obs_weight, float fov_up_deg, float fov_down_deg,
                              const float* d_color_im, const float* d_depth_im, const float* d_rem_im,
-                             int im_h, int im_w, int* d_hull, int fresh, void* d_workspace, size_t workspace_bytes,
+                             int im_h, int im_w, int* d_hull, int flags /* VL_TSDF_* */, void* d_workspace, size_t workspace_bytes,
                              vl_stream stream);
 int vl_tsdf_densify(float* d_tsdf, float* d_weight, float* d_color, float* d_rem, int dx, int dy, int dz,
                     int* d_hull, vl_stream stream);

@@ -486,7 +486,7 @@ k_mesh_compact_bits(const unsigned int* __restrict__ bits, const MeshParams P, i
 // exclusive scans of both unit totals in three steps: every CTA scans 8192 units locally (8 consecutive units per
 // thread) and leaves its totals, one CTA scans the block totals, every unit adds its block's offset;
 // totals[0] = triangles, totals[1] = active cubes
-constexpr int kScanPer = 8;
+constexpr int kScanPer = 1;   // units per thread of k_mesh_scan_local: 1 = coalesced loads, one CTA per 1024 units (8: 17 CTAs for 139 k units, 15 us; 1: see profiles/r02_experiments.md)
 constexpr int kScanBlockUnits = 1024 * kScanPer;
 
 __device__ __forceinline__ void block_excl2_1024(long long v0, long long v1, long long (*warp_sums)[32], long long* e0,

@@ -812,8 +812,12 @@ extern "C" int vl_tsdf_sparse_integrate(float* d_tsdf, float* d_weight, float* d
                                         const float vol_origin[3], float voxel_size, float trunc_margin, float obs_weight,
                                         float fov_up_deg, float fov_down_deg, const float* d_color_im,
                                         const float* d_depth_im, const float* d_rem_im, int im_h, int im_w, int* d_hull,
-                                        int fresh, void* d_workspace, size_t workspace_bytes, vl_stream stream_) {
+                                        int flags, void* d_workspace, size_t workspace_bytes, vl_stream stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int fresh = flags & VL_TSDF_FRESH;
+  // VL_TSDF_TABLES_VALID: the caller's promise that this workspace still holds the per-column pixel table and the per-row
+  // tangents of an earlier call with the same volume geometry, field of view and image size (they depend on nothing else)
+  const bool tables_valid = (flags & VL_TSDF_TABLES_VALID) != 0;
   const long long n_vox = (long long)dx * dy * dz;
   if (dx <= 0 || dy <= 0 || dz <= 0 || n_vox > 0x7fffffffLL || im_h <= 0 || im_w <= 0 || !vol_origin || !d_tsdf ||
       !d_weight || !d_color || !d_rem || !d_color_im || !d_depth_im || !d_rem_im || !d_hull || !d_workspace || dz > 32767) {
@@ -862,14 +866,18 @@ extern "C" int vl_tsdf_sparse_integrate(float* d_tsdf, float* d_weight, float* d
   int* rmin = reinterpret_cast<int*>(ws + rows_off + vl_align256(sizeof(float4) * (size_t)im_h));
   int* rmax1 = reinterpret_cast<int*>(reinterpret_cast<char*>(rmin) + tab_bytes);
   VlProfScope ps(VL_ST_TSDF_INTEGRATE, stream);
-  k_tsdf_columns<<<(n_cols + kThreads - 1) / kThreads, kThreads, 0, stream>>>(col_px, P);
-  VL_LAUNCH_CHECK("k_tsdf_columns");
+  if (!tables_valid) {
+    k_tsdf_columns<<<(n_cols + kThreads - 1) / kThreads, kThreads, 0, stream>>>(col_px, P);
+    VL_LAUNCH_CHECK("k_tsdf_columns");
+  }
   k_tsdf_shell<<<(im_h * im_w + kThreads - 1) / kThreads, kThreads, 0, stream>>>(d_depth_im, d_color_im, im_h, im_w, trunc_margin, shell);
   VL_LAUNCH_CHECK("k_tsdf_shell");
   // pitch slack of a row boundary: the sweep's row tolerance (eps_row rows) as an angle, plus rounding
   const double e_p = (eps_row + 1e-2) * fov_rad / im_h + 2e-5;
-  k_tsdf_rows<<<(im_h + 127) / 128, 128, 0, stream>>>(rows, im_h, (double)(fabsf(P.fov_up) + fabsf(P.fov_down)), fabs((double)P.fov_down), e_p);
-  VL_LAUNCH_CHECK("k_tsdf_rows");
+  if (!tables_valid) {
+    k_tsdf_rows<<<(im_h + 127) / 128, 128, 0, stream>>>(rows, im_h, (double)(fabsf(P.fov_up) + fabsf(P.fov_down)), fabs((double)P.fov_down), e_p);
+    VL_LAUNCH_CHECK("k_tsdf_rows");
+  }
   // largest horizontal distance of a column from the sensor axis -> bin width
   const double xm = fmax(fabs((double)P.ox), fabs((double)P.ox + dx * (double)voxel_size));
   const double ym = fmax(fabs((double)P.oy), fabs((double)P.oy + dy * (double)voxel_size));

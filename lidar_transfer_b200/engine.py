@@ -237,6 +237,7 @@ def trace_bruteforce(verts, faces, colors, rem, rays, origin, height, out=None, 
 
 
 PROJECT_METHODS = {"depth": 0, "pdist": 1, "depthfast": 2}   # VL_PROJECT_* of include/vlidar.h
+TSDF_FRESH, TSDF_TABLES_VALID = 1, 2                          # VL_TSDF_* of include/vlidar.h
 
 
 def project(points, remissions, labels, fov_up, fov_down, H, W, remove=True, workspace=None, beam_angles=None,
@@ -433,15 +434,23 @@ class TsdfDevice:
       # sparse volume: no reset pass, only the voxels inside the columns' hulls exist (vl_tsdf_sparse_integrate)
       need = lib().vl_tsdf_sparse_workspace_bytes(self.dim[0], self.dim[1], int(im_h), int(im_w))
       ws = self._workspace("columns", need, dev)
+      # the geometry tables in the workspace (pixel column per z column, tangents per image row) depend on the volume
+      # geometry, the field of view and the image size only: rebuilt when any of those -- or the workspace -- changes
+      key = (ws.data_ptr(), self.dim, self.origin.tobytes(), self.voxel_size, self.fov_up, self.fov_down, int(im_h), int(im_w),
+             torch.cuda.current_stream(dev).cuda_stream)
+      flags = (TSDF_FRESH if self._fresh else 0) | (TSDF_TABLES_VALID if self._store.get("tables_key") == key else 0)
+      self._store["tables_key"] = None
       with torch.cuda.device(dev):
         check(lib().vl_tsdf_sparse_integrate(_ptr(self._vols[0]), _ptr(self._vols[1]), _ptr(self._vols[2]), _ptr(self._vols[3]),
                                              self.dim[0], self.dim[1], self.dim[2], origin, self.voxel_size, self.trunc_margin,
                                              float(np.float32(obs_weight)), self.fov_up, self.fov_down, _ptr(color_im),
                                              _ptr(depth_im), _ptr(rem_im), int(im_h), int(im_w), _ptr(self._hull()),
-                                             1 if self._fresh else 0, _ptr(ws), ws.numel(), _stream()))
+                                             flags, _ptr(ws), ws.numel(), _stream()))
+      self._store["tables_key"] = key
       if self._fresh:
         self._fresh, self._dense = False, False
       return
+    self._store["tables_key"] = None   # the dense calls lay the workspace out their own way
     fused = self._fresh and use_column_table   # first integration into a fresh volume: one pass
     if not fused:
       self._materialise()
