@@ -487,8 +487,11 @@ k_tsdf_hull(const TsdfParams P, const int* __restrict__ col_px, const float2* __
 // written); the others are integrated like a later scan.
 constexpr int kHullCols = 256;   // columns per CTA (= kThreads)
 
+#ifndef VL_HULL_MINB
+#define VL_HULL_MINB 6   // 40 registers instead of 53: later integrations (which read the volumes) 641 -> 586 us per five scans, a first integration unchanged
+#endif
 template <int kVec>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, VL_HULL_MINB)
 k_tsdf_hull_sweep(float* __restrict__ tsdf_vol, float* __restrict__ weight_vol, float* __restrict__ color_vol,
                   float* __restrict__ rem_vol, const TsdfParams P, const ShellParams S,
                   const float* __restrict__ color_im, const float* __restrict__ depth_im,
