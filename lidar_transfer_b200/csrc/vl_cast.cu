@@ -15,7 +15,7 @@
 // atomicMin on (t bits << 32 | face index).  No per-scan sort, no per-scan tree, no divergent traversal.
 //
 // Per scan: k_cast_init resets the per-beam keys; k_cast_setup streams the faces in batches of
-// 1024 per CTA -- a cheap cull (sine interval vs the beam rows) that ~70 % of a LiDAR scene's triangles do not
+// 512 per CTA -- a cheap cull (sine interval vs the beam rows) that ~70 % of a LiDAR scene's triangles do not
 // survive, then on dense warps the full rectangle, a 64-byte record and one work unit per run of <= 8 cells of a
 // cell row; k_cast_units pools the beams of 32 units per warp and tests them 32 at a time; k_cast_resolve writes the
 // outputs of RayTracer.cpp:73-90 for the winning triangle of each beam.  Records and units live in L2 between the
@@ -41,7 +41,10 @@ constexpr int kSegShift = 3;        // an item is one run of <= 8 cells of one c
 constexpr int kSegShiftWide = 6;    // ... or of <= 64 cells for a triangle wider than kWideCols (bounds the unit count)
 constexpr int kWideCols = 128;
 constexpr int kUnitItems = 1;       // items per work unit (one lane of k_cast_units)
-constexpr int kBatch = 4 * kCastThreads;   // faces per culling batch of k_cast_setup
+#ifndef VL_SETUP_FPT
+#define VL_SETUP_FPT 2   // measured (8 scans in flight): 1 / 2 / 4 / 8 faces per thread and batch -> 41.0 / 36.0 / 36.9 / 37.6 us per scan
+#endif
+constexpr int kBatch = VL_SETUP_FPT * kCastThreads;   // faces per culling batch of k_cast_setup
 constexpr int kUnitBits = 36;       // packed reservation counter: [records : 28][units : 36]
 constexpr float kPad0 = 2e-5f;      // angular slack (rad): >> fp32 rounding of azimuth / sine / Moller-Trumbore edges
 
@@ -507,7 +510,7 @@ __global__ void k_cast_init(unsigned long long* __restrict__ best, int n, VlCast
   if (blockIdx.x == 0 && threadIdx.x == 0) { hdr->n_bad_faces = 0; hdr->overflow = 0; hdr->reserved = 0ull; }
 }
 
-// Step 1: stream the faces once, in batches of 1024 per CTA.
+// Step 1: stream the faces once, in batches of 512 per CTA.
 //   cull:  every face gets the cheap test (sine interval vs the beam rows); ~70 % of a LiDAR scene's triangles lie
 //          between two beam rows or outside the vertical field of view and stop here.  Survivors are queued in
 //          shared memory, so that
