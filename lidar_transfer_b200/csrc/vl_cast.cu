@@ -37,7 +37,10 @@ namespace {
 constexpr int kCastThreads = 256;
 constexpr int kCastWarps = kCastThreads / 32;
 constexpr int kFineBins = 4096;     // fine sin(elevation) bins of the next-beam-sine table (the arithmetic early-out)
-constexpr int kSegShift = 3;        // an item is one run of <= 8 cells of one cell row ...
+#ifndef VL_SEG_SHIFT
+#define VL_SEG_SHIFT 3
+#endif
+constexpr int kSegShift = VL_SEG_SHIFT;   // an item is one run of <= 8 cells of one cell row ...
 constexpr int kSegShiftWide = 6;    // ... or of <= 64 cells for a triangle wider than kWideCols (bounds the unit count)
 constexpr int kWideCols = 128;
 constexpr int kUnitItems = 1;       // items per work unit (one lane of k_cast_units)

@@ -559,3 +559,37 @@ def test_cast_takes_a_triangle_soup_without_an_index_array(engine, oracle):
   pad = np.concatenate([tri, np.full((2, 3), 1e3, np.float32)])
   d = _np(engine.cast(beams, pad, None, np.concatenate([col, np.zeros((2, 3), np.int32)]), np.concatenate([rem, np.zeros(2, np.float32)]), origin))
   _same(d, ref, what="soup, two spare vertices")
+
+
+@pytest.mark.parametrize("n_faces", [0, 1, 3, 1025])
+@pytest.mark.parametrize("method", ["cast", "lbvh"])
+def test_ctrace_tiny_and_empty_meshes(engine, oracle, vl, n_faces, method):
+  """The host entry point on meshes smaller than one staging item, odd face counts (the packed face words are written two at
+  a time) and no faces at all (the reference: every ray misses, nothing is written)."""
+  rng = np.random.default_rng(100 + n_faces)
+  sc = synth.make_scene(9, n_side=24, n_boxes=0)
+  faces = np.ascontiguousarray(sc["faces"][rng.permutation(sc["faces"].shape[0])[:n_faces]])
+  H, W = 8, 64
+  rays = oracle.create_rays(-5.0, -40.0, H, W)
+  origin = np.zeros(3, np.float32)
+  out = _ctrace_out(H * W, 5)
+  if n_faces == 0:
+    tri = np.empty(H * W, np.int32)
+    p = lambda a: a.ctypes.data
+    z = np.zeros(3, np.int32)
+    vl.vl_ctrace_method({"cast": 0, "lbvh": 1}[method])
+    rc = vl.vl_ctrace_ids(p(rays), p(origin), p(sc["verts"]), p(z), p(sc["colors"]), p(sc["rem"]), H * W, sc["verts"].shape[0], 0, H,
+                          p(out["endpoints"]), p(out["endcolors"]), p(out["range"]), p(out["endrem"]), p(tri))
+    vl.vl_ctrace_method(0)
+    assert rc == 0 and (tri == -1).all() and (out["range"] == 5).all() and (out["endcolors"] == 5).all()
+    return
+  ref = oracle.trace(rays, origin, sc["verts"], faces, sc["colors"], sc["rem"], H, oracle.MIN_ID_TIES | oracle.NORMALIZE_SSE)
+  got = engine.ctrace_host(rays, origin, sc["verts"].reshape(-1), faces.reshape(-1), sc["colors"].reshape(-1), sc["rem"], H,
+                           outputs=out, want_ids=True, method=method)
+  engine.ctrace_host(rays, origin, sc["verts"].reshape(-1), faces.reshape(-1), sc["colors"].reshape(-1), sc["rem"], H, method="cast")
+  hit = ref["tri_id"] >= 0
+  assert np.array_equal(got["tri_id"], ref["tri_id"])
+  for k, c in (("range", 1), ("endrem", 1), ("endpoints", 3), ("endcolors", 3)):
+    x, y = got[k].reshape(-1, c).view(np.int32), np.asarray(ref[k]).reshape(-1, c).view(np.int32)
+    assert np.array_equal(x[hit], y[hit]), k
+    assert (got[k].reshape(-1, c)[~hit] == 5).all(), k
