@@ -418,6 +418,9 @@ void        vl_debug_cast_rearm(int on);
 /* Debug: 1 (default) = a triangle's rectangle drops the cell rows at both ends none of whose beams lies inside its sine
  * interval (exact: the comparison k_cast_units makes per beam), 0 = every cell row the interval touches (A/B aid). */
 void        vl_debug_cast_row_trim(int on);
+/* Debug: 1 = the cast's cull and setup run as two kernels (k_cast_cull at 6 CTAs per SM + k_cast_setup2 on the survivors' list),
+ * 0 = one kernel with a shared-memory queue (k_cast_setup).  Same results. */
+void        vl_debug_cast_split(int on);
 /* Debug: persistent CTAs per SM of the item kernel (default 4). */
 void        vl_debug_cast_ctas(int ctas_per_sm);
 /* Debug: persistent CTAs per SM of the setup kernel (default 4). */

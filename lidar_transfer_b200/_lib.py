@@ -54,6 +54,7 @@ SIGNATURES = {
     "vl_debug_cast_rearm": (None, [_i]),
     "vl_debug_cast_ctas": (None, [_i]),
     "vl_debug_cast_row_trim": (None, [_i]),
+    "vl_debug_cast_split": (None, [_i]),
     "vl_debug_cast_setup_ctas": (None, [_i]),
     "vl_trace_bruteforce": (_i, [_vp] * 4 + [_i, _i, _vp, _vp, _i, _i] + [_vp] * 5 + [_i, _vp]),
     "vl_project_workspace_bytes": (_sz, [_l, _i, _i]),

@@ -25,6 +25,7 @@
 // reference arithmetic; exact-t ties go to the smaller face index (that is what the packed key orders by).
 // The cell rectangle may only over-select: every bound below is conservative (padded by kPad0 plus the
 // rounding of v - o), so a beam the triangle test would accept is always among the candidates.
+#include <stdlib.h>
 #include "vl_common.cuh"
 
 #ifndef VL_SETUP_MINB
@@ -96,6 +97,8 @@ int g_cells_per_row = 1;   // cell rows per beam row (vl_debug_cast_cells)
 // step is 15 % slower (2720 vs 3136 Mrays/s at 8 streams, A/B on one box) -- kept as a switch, off.
 int g_graph_rearm = 0;
 int g_items_ctas_per_sm = 4;
+// vl_debug_cast_split / VLIDAR_CAST_SPLIT: 1 = cull and setup as two kernels (k_cast_cull + k_cast_setup2)
+int g_cast_split = getenv("VLIDAR_CAST_SPLIT") ? atoi(getenv("VLIDAR_CAST_SPLIT")) : 0;
 int g_row_trim = 1;          // vl_debug_cast_row_trim: 0 = rectangles keep every cell row their sine interval touches (A/B aid)
 int g_setup_ctas_per_sm = VL_SETUP_MINB_DEFAULT;
 
@@ -643,6 +646,143 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const float*
   if (n_bad) atomicAdd(&chdr->n_bad_faces, n_bad);
 }
 
+// The same step as TWO kernels (vl_debug_cast_split(1)): the cull alone needs ~40 registers and runs at 6 CTAs per SM instead of
+// 4 -- half as many again warps to hide the face -> vertex gathers behind --, the survivors' setup (64 registers) then runs
+// on a dense list.  No shared-memory queue and no barrier in the cull: every CTA appends its survivors to its OWN segment
+// of a global list (a warp-aggregated shared-memory counter; capacity = the faces the CTA's batches hold), k_cast_setup2 is
+// launched with the same grid and CTA c sets up segment c, a warp per 32 entries.
+#ifndef VL_CULL_MINB
+#define VL_CULL_MINB 6
+#endif
+constexpr int kSegCounts = 4096;   // ints at the head of the list: survivors per CTA (grids are <= 148 x 8 CTAs)
+
+__device__ __forceinline__ int cast_seg_cap(int n_faces, int grid) {
+  const int n_batches = (n_faces + kBatch - 1) / kBatch;
+  return ((n_batches + grid - 1) / grid) * kBatch;
+}
+
+template <bool kDescPtr>
+__global__ void __launch_bounds__(kCastThreads, VL_CULL_MINB)
+k_cast_cull(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const float* __restrict__ nxt, const VlMeshDesc mesh_val,
+            const VlMeshDesc* __restrict__ mesh_ptr, const float* __restrict__ origin, VlCastHeader* chdr,
+            int* __restrict__ list) {
+  const float* __restrict__ verts = kDescPtr ? mesh_ptr->verts : mesh_val.verts;
+  const int* __restrict__ faces = kDescPtr ? mesh_ptr->faces : mesh_val.faces;
+  const int n_verts = kDescPtr ? mesh_ptr->n_verts : mesh_val.n_verts;
+  const int n_faces = kDescPtr ? mesh_ptr->n_faces : mesh_val.n_faces;
+  __shared__ int s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  const BeamParams P = beam_params(bhdr, cw, ch);
+  const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
+  const float o_max = fmaxf(fabsf(o.x), fmaxf(fabsf(o.y), fabsf(o.z)));
+  const int lane = threadIdx.x & 31;
+  const int n_batches = (n_faces + kBatch - 1) / kBatch;
+  int* __restrict__ seg = list + kSegCounts + (size_t)blockIdx.x * cast_seg_cap(n_faces, gridDim.x);
+  int n_bad = 0;
+  for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+    {   // the faces (a soup: the vertices) of this CTA's NEXT batch start their way from DRAM to L2 now: one line per thread
+      const int nb = batch + gridDim.x;
+      if (nb < n_batches) {
+        const size_t per = faces ? 12 : 36;
+        const char* p = faces ? reinterpret_cast<const char*>(faces) + (size_t)nb * kBatch * 12
+                              : reinterpret_cast<const char*>(verts) + (size_t)nb * kBatch * 36;
+        const size_t bytes = (size_t)min(kBatch, n_faces - nb * kBatch) * per;
+        for (size_t o2 = (size_t)threadIdx.x * 128; o2 < bytes; o2 += (size_t)kCastThreads * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o2));
+      }
+    }
+    int idx[kBatch / kCastThreads][3];
+#pragma unroll
+    for (int k = 0; k < kBatch / kCastThreads; ++k) {   // all index loads first: faces -> verts is a dependent gather
+      const int f = batch * kBatch + k * kCastThreads + threadIdx.x;
+      if (f < n_faces) {
+        if (faces) { idx[k][0] = __ldg(faces + 3 * (size_t)f); idx[k][1] = __ldg(faces + 3 * (size_t)f + 1); idx[k][2] = __ldg(faces + 3 * (size_t)f + 2); }
+        else { idx[k][0] = 3 * f; idx[k][1] = 3 * f + 1; idx[k][2] = 3 * f + 2; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kBatch / kCastThreads; ++k) {
+      const int f = batch * kBatch + k * kCastThreads + threadIdx.x;
+      bool keep = false;
+      if (f < n_faces) {
+        if ((unsigned)idx[k][0] >= (unsigned)n_verts || (unsigned)idx[k][1] >= (unsigned)n_verts || (unsigned)idx[k][2] >= (unsigned)n_verts) {
+          ++n_bad;
+        } else {
+          keep = tri_cull(idx[k][0], idx[k][1], idx[k][2], verts, o, o_max, P, nxt);
+        }
+      }
+      const unsigned int m = __ballot_sync(0xffffffffu, keep);
+      if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) seg[base + __popc(m & ((1u << lane) - 1u))] = f;
+      }
+    }
+  }
+  if (n_bad) atomicAdd(&chdr->n_bad_faces, n_bad);
+  __syncthreads();
+  if (threadIdx.x == 0) list[blockIdx.x] = s_count;
+}
+
+template <bool kDescPtr>
+__global__ void __launch_bounds__(kCastThreads, VL_SETUP_MINB)
+k_cast_setup2(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const float* __restrict__ nxt, const VlMeshDesc mesh_val,
+              const VlMeshDesc* __restrict__ mesh_ptr, const float* __restrict__ origin, VlCastHeader* chdr,
+              float4* __restrict__ recs, int rec_cap, int2* __restrict__ units, unsigned long long unit_cap,
+              const float2* __restrict__ row_lim, const int* __restrict__ list) {
+  const float* __restrict__ verts = kDescPtr ? mesh_ptr->verts : mesh_val.verts;
+  const int* __restrict__ faces = kDescPtr ? mesh_ptr->faces : mesh_val.faces;
+  const int n_faces = kDescPtr ? mesh_ptr->n_faces : mesh_val.n_faces;
+  const BeamParams P = beam_params(bhdr, cw, ch);
+  const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned long long units_mask = (1ull << kUnitBits) - 1ull;
+  const int nq = __ldg(list + blockIdx.x);
+  const int* __restrict__ seg = list + kSegCounts + (size_t)blockIdx.x * cast_seg_cap(n_faces, gridDim.x);
+  for (int start = w * 32; start < nq; start += kCastWarps * 32) {
+    const int j = start + lane;
+    TriRec T;
+    int n_i = 0;
+    if (j < nq) {
+      const int f = __ldg(seg + j);
+      const int i0 = faces ? __ldg(faces + 3 * (size_t)f) : 3 * f, i1 = faces ? __ldg(faces + 3 * (size_t)f + 1) : 3 * f + 1,
+                i2 = faces ? __ldg(faces + 3 * (size_t)f + 2) : 3 * f + 2;
+      n_i = tri_setup<true>(f, i0, i1, i2, verts, o, P, nxt, row_lim, T);
+    }
+    const int n_u = (n_i + kUnitItems - 1) / kUnitItems;
+    const unsigned long long mine = n_i > 0 ? ((1ull << kUnitBits) | (unsigned long long)n_u) : 0ull;
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += u;
+    }
+    const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0ull;
+    if (lane == 0 && total) {
+      base = atomicAdd(&chdr->reserved, total);
+      if ((base & units_mask) + (total & units_mask) > unit_cap) chdr->overflow = 1;
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (n_i > 0) {
+      const unsigned long long at = base + incl - mine;
+      const int pos = (int)(at >> kUnitBits);
+      const unsigned long long u0 = at & units_mask;
+      if (pos < rec_cap && u0 + (unsigned long long)n_u <= unit_cap) {   // always, unless the unit list overflowed
+        float4* r = recs + 4 * (size_t)pos;
+        r[0] = make_float4(T.v0x, T.v0y, T.v0z, T.e1x);
+        r[1] = make_float4(T.e1y, T.e1z, T.e2x, T.e2y);
+        r[2] = make_float4(T.e2z, __int_as_float(T.orig), T.ymid, T.yhalf);
+        r[3] = make_float4(T.slo, T.shi, __int_as_float(T.ca | (T.ncx << 16) | (T.ncx > kWideCols ? (1 << 30) : 0)),
+                           __int_as_float(T.ra | (T.ncy << 16)));
+        for (int k = 0; k < n_u; ++k) units[u0 + k] = make_int2(pos, k * kUnitItems);
+      }
+    }
+  }
+}
+
 // Step 2: a warp per 32 work units.  A unit is one item: a run of <= 8 (64 for very wide triangles) cells of one cell row of a triangle's
 // rectangle; the beams of consecutive cells are consecutive in the sorted beam list, so a run is one contiguous
 // range of it (two when it wraps at the azimuth seam).  Each lane decodes its unit and parks the triangle in shared
@@ -789,13 +929,14 @@ k_cast_resolve(unsigned long long* best, int n, const float4* __restrict__ dir,
 
 extern "C" void vl_debug_cast_rearm(int on) { g_graph_rearm = on ? 1 : 0; }
 extern "C" void vl_debug_cast_cells(int cells_per_beam_row) { g_cells_per_row = cells_per_beam_row < 1 ? 1 : cells_per_beam_row; }
+extern "C" void vl_debug_cast_split(int on) { g_cast_split = on ? 1 : 0; }
 extern "C" void vl_debug_cast_row_trim(int on) { g_row_trim = on ? 1 : 0; }
 extern "C" void vl_debug_cast_ctas(int ctas_per_sm) { g_items_ctas_per_sm = ctas_per_sm < 1 ? 1 : ctas_per_sm; }
 extern "C" void vl_debug_cast_setup_ctas(int ctas_per_sm) { g_setup_ctas_per_sm = ctas_per_sm < 1 ? 1 : ctas_per_sm; }
 
 size_t vl_beams_bytes_impl(int n_rays, int height) { return beam_layout(n_rays, height).total; }
 
-struct CastLayout { size_t off_best, off_units, off_recs, total; unsigned long long unit_cap; };
+struct CastLayout { size_t off_best, off_units, off_recs, off_list, total; unsigned long long unit_cap; };
 
 CastLayout cast_layout(int n_rays, int n_faces) {
   CastLayout C;
@@ -805,6 +946,8 @@ CastLayout cast_layout(int n_rays, int n_faces) {
   C.unit_cap = 4 * nf + (1ull << 20);   // a unit is a run of <= 8 (64) cells of one cell row; LiDAR meshes need ~0.6 nf
   C.off_units = off;      off = vl_align256(off + 8 * (size_t)C.unit_cap);
   C.off_recs = off;       off = vl_align256(off + 64 * nf);
+  // survivors of the cull per CTA (vl_debug_cast_split(1)): counts + one segment per CTA, each a whole number of batches
+  C.off_list = off;       off = vl_align256(off + 4 * (kSegCounts + nf + (size_t)kSegCounts * kBatch));
   C.total = off;
   return C;
 }
@@ -887,6 +1030,24 @@ static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr
       const int n_batches = ((by_ptr ? cap_faces : mesh.n_faces) + kBatch - 1) / kBatch;
       const int cap = vl_sm_count() * g_setup_ctas_per_sm;
       const int nb = n_batches < cap ? (n_batches > 0 ? n_batches : 1) : cap;
+      int* list = reinterpret_cast<int*>(Wk + C.off_list);
+      if (g_cast_split) {
+        int nc = vl_sm_count() * VL_CULL_MINB;
+        if (nc > kSegCounts) nc = kSegCounts;
+        if (n_batches < nc) nc = n_batches > 0 ? n_batches : 1;
+        if (by_ptr) {
+          k_cast_cull<true><<<nc, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, mesh, d_desc, d_origin, chdr, list);
+          VL_LAUNCH_CHECK("k_cast_cull");
+          k_cast_setup2<true><<<nc, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, mesh, d_desc, d_origin, chdr, recs, rec_cap,
+                                                              units, C.unit_cap, row_lim, list);
+        } else {
+          k_cast_cull<false><<<nc, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, mesh, d_desc, d_origin, chdr, list);
+          VL_LAUNCH_CHECK("k_cast_cull");
+          k_cast_setup2<false><<<nc, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, mesh, d_desc, d_origin, chdr, recs, rec_cap,
+                                                               units, C.unit_cap, row_lim, list);
+        }
+        VL_LAUNCH_CHECK("k_cast_setup2");
+      } else
       if (by_ptr)
         k_cast_setup<true><<<nb, kCastThreads, 0, stream>>>(bhdr, L.cw, L.ch, fine_mask, mesh, d_desc, d_origin, chdr, recs,
                                                            rec_cap, units, C.unit_cap, row_lim);

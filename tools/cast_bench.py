@@ -11,6 +11,8 @@ L = _lib.lib()
 n_side = int(sys.argv[1]) if len(sys.argv) > 1 else 710
 if len(sys.argv) > 2:
   L.vl_debug_cast_cells(int(sys.argv[2]))
+if os.environ.get("VL_CAST_SPLIT") is not None:
+  L.vl_debug_cast_split(int(os.environ["VL_CAST_SPLIT"]))
 if os.environ.get("VL_ROW_TRIM") is not None:
   L.vl_debug_cast_row_trim(int(os.environ["VL_ROW_TRIM"]))
 sensor = sys.argv[3] if len(sys.argv) > 3 else "HDL-64E"
