@@ -211,7 +211,10 @@ class LaserScan(_LazyAttrs):
   def do_range_projection_new(self, fov_up, fov_down, remove=False, method="depth"):
     """Nearest-point-per-pixel projection (laserscan.py:294-391) as one atomicMin scatter on the device.  The images
     stay on the device (`_proj_dev`, what deform() feeds to the TSDF integration); every host attribute the reference
-    sets here is a thunk with the reference's value."""
+    sets here is a thunk with the reference's value.  The device works in float64 -- the dtype the points have after the
+    pose round trip (apply_pose / apply_inv_pose), i.e. on every path deform() takes; points still in float32 (open_scan
+    without a pose applied) are promoted, where the reference would compute depth / yaw / pitch in float32: bit parity is
+    stated for float64 points only (the golden vectors'), a float32 cloud can differ by an ulp of range or a pixel at a border."""
     if method not in engine.PROJECT_METHODS:
       quit()   # laserscan.py:441-442
     pts = np.ascontiguousarray(self.points, np.float64)
