@@ -311,7 +311,7 @@ def sharded_pipeline_leg(rank, world, dev, n_manifest, barrier, reduce_max):
   R = H * W
   n_lanes = int(os.environ.get("VL_PIPE_LANES", "3"))   # measured: 1 / 2 / 3 / 4 / 6 scans in flight -> 1064 / 1211 / 1717 / 1676 / 447 scans per second
   pipe = pipeline.ScanPipeline(create_rays(FOV_UP, FOV_DOWN, H, W), H, FOV_UP, FOV_DOWN, bnds, 0.05, H, W, n_lanes=n_lanes, device=dev)
-  for _ in pipe.run(clouds[k % P] for k in range(3)):
+  for _ in pipe.run(clouds[k % P] for k in range(120)):   # warm-up: every lane has seen every cloud (grow-only buffers at their final size)
     pass
   barrier()
   t0 = time.perf_counter()
