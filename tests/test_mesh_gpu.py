@@ -90,3 +90,22 @@ def test_topology_ambiguity_is_bounded_on_the_real_scan(engine):
   assert r["triangles"] > 500000 and r["active_cubes"] > 200000
   assert r["ambiguous_cube_fraction"] < 0.10 and r["beam_fraction"] < 0.15, r
   assert mod.ambiguous_cases().sum() == 128
+
+
+def test_independent_torch_emitter_and_the_asymptotic_decider_on_the_real_scan(engine):
+  """tools/mesh_sensitivity.py at voxel 0.1 on the fixture's scan 0: (1) a torch restatement of the emit (table lookup,
+  edge interpolation, nearest-voxel colour / remission) reproduces vl_mesh.cu's mesh bit for bit; (2) every ambiguous face
+  of this TSDF has a never-written outside corner and the asymptotic decider -- what Lewiner's tables follow,
+  fusion_lidar.py:407 -- resolves ALL of them the way vl_mesh.cu's table does (inside corners separated), so face ambiguity
+  changes no beam; (3) the triangulation of the same polygons alone does change ranges (the polygons are not planar)."""
+  import os, sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+  import mesh_sensitivity
+  r = mesh_sensitivity.run(0.1)
+  assert r["self_check_torch_emitter_equals_vl_mesh_bit_for_bit"] is True
+  assert r["ambiguous_cubes"] > 10000 and r["ambiguous_faces_with_an_untouched_outside_corner"] == r["ambiguous_faces"]
+  assert r["ambiguous_cubes_the_decider_resolves_the_other_way"] == 0
+  assert r["decider_margin_inside_product_over_outside_product"]["max"] < 1.0
+  t = r["topology"]
+  assert t["hit_mask_flips"] == 0 and t["label_flips"] == 0 and t["range_changed_at_all"] == 0
+  assert r["triangulation"]["range_changed_by_more_than_1cm"] > 1000 and r["topology_worst_case"]["range_changed_by_more_than_1cm"] > 1000
