@@ -544,7 +544,7 @@ k_cast_setup(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const float*
   const BeamParams P = beam_params(bhdr, cw, ch);
   const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
   const float o_max = fmaxf(fabsf(o.x), fmaxf(fabsf(o.y), fabsf(o.z)));
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int n_batches = (n_faces + kBatch - 1) / kBatch;
   const unsigned long long units_mask = (1ull << kUnitBits) - 1ull;
   int n_bad = 0;

@@ -91,7 +91,6 @@ class WorkPool {
     static WorkPool* p = new WorkPool();   // never destroyed: the workers are detached and outlive static destructors
     return *p;
   }
-  int workers() const { return n_workers_; }
   // lend: the calling thread takes items too while it waits; without, it only watches for finished runs of items and
   // reports them at once (the staging copy: a finished run has to leave for the device NOW, not after the caller's own
   // next megabyte)
