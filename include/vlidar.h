@@ -190,6 +190,11 @@ void vl_ctrace_timing(double* ms4);
  * of the results the end points stay on the device and are recomputed on the host as o + d * t from the unit directions
  * the host made itself, BVH.cpp:106-107), 0 = every array as the caller holds it.  Same results either way.  Process-wide. */
 void vl_ctrace_wire(int packed);
+/* Test hook, host code only (no device needed): the packing loops of the staging copy on caller-provided host buffers --
+ * packed_faces u64[n_faces] (three 21-bit indices per word), packed_colors u8[n_components]; seen2[0] / seen2[1] = OR of every
+ * face index / colour component (bits above 2^21 / 2^8 set: the array does not fit and ctrace sends it raw). */
+int vl_debug_pack(const int* faces, long long n_faces, unsigned long long* packed_faces, const int* colors, long long n_components,
+                  unsigned char* packed_colors, unsigned int* seen2);
 /* Bytes the most recent ctrace moved host->device / device->host. */
 void vl_ctrace_traffic(long long* h2d_bytes, long long* d2h_bytes);
 

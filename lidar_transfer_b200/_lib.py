@@ -41,6 +41,7 @@ SIGNATURES = {
     "vl_ctrace_timing": (None, [_vp]),
     "vl_ctrace_wire": (None, [_i]),
     "vl_ctrace_traffic": (None, [_vp, _vp]),
+    "vl_debug_pack": (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _vp]),
     "vl_cast_workspace_bytes": (_sz, [_i, _i]),
     "vl_cast": (_i, [_vp] * 5 + [_i, _i, _vp, _i, _i] + [_vp] * 5 + [_i, _vp, _sz, _vp]),
     "vl_cast_status": (_i, [_vp, _vp, _vp]),

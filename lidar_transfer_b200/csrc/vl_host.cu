@@ -213,6 +213,49 @@ __global__ void k_unpack_colors(const unsigned char* __restrict__ c8, size_t n3,
 // DMA engine only; lines left dirty in the caches of several cores make the host->device copy that follows markedly
 // slower (measured: profiles/r02_experiments.md section 8).
 // returns the OR of every index (bits above 2^21 or the sign bit set = does not fit); dst is 16-byte aligned
+#if defined(VL_HAVE_SSE) && defined(__GNUC__)
+#include <immintrin.h>
+#define VL_HAVE_AVX2_DISPATCH 1
+// Eight faces per iteration with AVX2 (selected at run time by __builtin_cpu_supports): three 256-bit loads hold
+// a0 b0 c0 a1 b1 c1 ... c7; the stride-3 de-interleave is three lane permutes + two blends per component; the 21-bit
+// fields are assembled in 64-bit lanes and leave as 32-byte non-temporal stores.  Returns the number of faces packed
+// (a multiple of 8); dst must be 32-byte aligned.
+__attribute__((target("avx2"))) static size_t pack_faces_avx2(unsigned long long* dst, const int* src, size_t n_faces,
+                                                              unsigned int* seen_out) {
+  const __m256i ia0 = _mm256_setr_epi32(0, 3, 6, 0, 0, 0, 0, 0), ia1 = _mm256_setr_epi32(0, 0, 0, 1, 4, 7, 0, 0), ia2 = _mm256_setr_epi32(0, 0, 0, 0, 0, 0, 2, 5);
+  const __m256i ib0 = _mm256_setr_epi32(1, 4, 7, 0, 0, 0, 0, 0), ib1 = _mm256_setr_epi32(0, 0, 0, 2, 5, 0, 0, 0), ib2 = _mm256_setr_epi32(0, 0, 0, 0, 0, 0, 3, 6);
+  const __m256i ic0 = _mm256_setr_epi32(2, 5, 0, 0, 0, 0, 0, 0), ic1 = _mm256_setr_epi32(0, 0, 0, 3, 6, 0, 0, 0), ic2 = _mm256_setr_epi32(0, 0, 0, 0, 0, 1, 4, 7);
+  __m256i acc = _mm256_setzero_si256();
+  size_t f = 0;
+  for (; f + 8 <= n_faces; f += 8) {
+    const __m256i v0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + 3 * f));
+    const __m256i v1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + 3 * f + 8));
+    const __m256i v2 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + 3 * f + 16));
+    acc = _mm256_or_si256(acc, _mm256_or_si256(v0, _mm256_or_si256(v1, v2)));
+    // a_i = int 3i: v0[0,3,6] v1[1,4,7] v2[2,5];  b_i = int 3i+1: v0[1,4,7] v1[2,5] v2[0,3,6];  c_i: v0[2,5] v1[0,3,6] v2[1,4,7]
+    const __m256i A = _mm256_blend_epi32(_mm256_blend_epi32(_mm256_permutevar8x32_epi32(v0, ia0), _mm256_permutevar8x32_epi32(v1, ia1), 0x38),
+                                         _mm256_permutevar8x32_epi32(v2, ia2), 0xC0);
+    const __m256i B = _mm256_blend_epi32(_mm256_blend_epi32(_mm256_permutevar8x32_epi32(v0, ib0), _mm256_permutevar8x32_epi32(v1, ib1), 0x18),
+                                         _mm256_permutevar8x32_epi32(v2, ib2), 0xE0);
+    const __m256i C = _mm256_blend_epi32(_mm256_blend_epi32(_mm256_permutevar8x32_epi32(v0, ic0), _mm256_permutevar8x32_epi32(v1, ic1), 0x1C),
+                                         _mm256_permutevar8x32_epi32(v2, ic2), 0xE0);
+    const __m256i w0 = _mm256_or_si256(_mm256_cvtepu32_epi64(_mm256_castsi256_si128(A)),
+                                       _mm256_or_si256(_mm256_slli_epi64(_mm256_cvtepu32_epi64(_mm256_castsi256_si128(B)), kIdxBits),
+                                                       _mm256_slli_epi64(_mm256_cvtepu32_epi64(_mm256_castsi256_si128(C)), 2 * kIdxBits)));
+    const __m256i w1 = _mm256_or_si256(_mm256_cvtepu32_epi64(_mm256_extracti128_si256(A, 1)),
+                                       _mm256_or_si256(_mm256_slli_epi64(_mm256_cvtepu32_epi64(_mm256_extracti128_si256(B, 1)), kIdxBits),
+                                                       _mm256_slli_epi64(_mm256_cvtepu32_epi64(_mm256_extracti128_si256(C, 1)), 2 * kIdxBits)));
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + f), w0);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + f + 4), w1);
+  }
+  _mm_sfence();
+  alignas(32) unsigned int lanes[8];
+  _mm256_store_si256(reinterpret_cast<__m256i*>(lanes), acc);
+  *seen_out = lanes[0] | lanes[1] | lanes[2] | lanes[3] | lanes[4] | lanes[5] | lanes[6] | lanes[7];
+  return f;
+}
+#endif
+
 inline unsigned int pack_faces(unsigned long long* dst, const int* src, size_t n_faces) {
   unsigned int seen = 0;
   auto word = [&](size_t f) {
@@ -221,8 +264,16 @@ inline unsigned int pack_faces(unsigned long long* dst, const int* src, size_t n
     return (unsigned long long)a | ((unsigned long long)b << kIdxBits) | ((unsigned long long)c << (2 * kIdxBits));
   };
   size_t f = 0;
+#ifdef VL_HAVE_AVX2_DISPATCH
+  static const bool avx2 = __builtin_cpu_supports("avx2") && getenv("VLIDAR_NO_AVX2") == nullptr;
+  if (avx2 && (((uintptr_t)dst) & 31) == 0) {
+    unsigned int s8 = 0;
+    f = pack_faces_avx2(dst, src, n_faces, &s8);
+    seen |= s8;
+  }
+#endif
 #ifdef VL_HAVE_SSE
-  if ((((uintptr_t)dst) & 15) == 0) {
+  if ((((uintptr_t)(dst + f)) & 15) == 0) {
     for (; f + 2 <= n_faces; f += 2) {
       const unsigned long long w0 = word(f), w1 = word(f + 1);
       _mm_stream_si128(reinterpret_cast<__m128i*>(dst + f), _mm_set_epi64x((long long)w1, (long long)w0));
@@ -396,7 +447,7 @@ int ctrace_locked(HostCtx& c, const float* rays, const float* origin, const floa
   add_copy(o_origin, origin, 12);
   add_copy(o_verts, verts, 12 * nv);
   if (pack_f) {
-    const size_t per = (kChunk / 12) & ~(size_t)1;   // even: every item's first word is 16-byte aligned
+    const size_t per = (kChunk / 12) & ~(size_t)3;   // a multiple of four: every item's first word is 32-byte aligned
     for (size_t f = 0; f < nf; f += per) {
       const size_t n = nf - f < per ? nf - f : per;
       end = o_wf + 8 * (f + n);
@@ -615,6 +666,15 @@ int ctrace_locked(HostCtx& c, const float* rays, const float* origin, const floa
 }
 
 }  // namespace
+
+// test hook (host code only, no device needed): the staging copy's packing loops on caller-provided buffers
+extern "C" int vl_debug_pack(const int* faces, long long n_faces, unsigned long long* packed_faces, const int* colors, long long n_components,
+                             unsigned char* packed_colors, unsigned int* seen2) {
+  if (n_faces < 0 || n_components < 0 || !seen2) { vl_set_error("vl_debug_pack: invalid argument"); return VL_EINVAL; }
+  seen2[0] = n_faces > 0 ? pack_faces(packed_faces, faces, (size_t)n_faces) : 0u;
+  seen2[1] = n_components > 0 ? pack_colors(packed_colors, colors, (size_t)n_components) : 0u;
+  return VL_OK;
+}
 
 extern "C" void vl_ctrace_method(int method) { g_ctrace_method.store(method == 1 ? 1 : 0); }
 extern "C" void vl_ctrace_normalize(int mode) { g_ctrace_normalize.store(mode == 1 ? 1 : 0); }

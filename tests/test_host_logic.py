@@ -258,3 +258,40 @@ def test_host_normaliser_is_the_reference_normalize_bit_for_bit(vl, oracle):
   ieee = oracle.normalize_rays(sets[0], 0)
   ulp = np.abs(ieee.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))
   assert 0 < ulp.max() <= 4
+
+
+def test_staging_pack_loops_match_numpy():
+  """The packing loops of ctrace's staging copy (faces 3 x 21 bit per 64-bit word -- AVX2 eight at a time where the CPU has
+  it, SSE2 / scalar otherwise --, colours one byte per component) against numpy, for every length 0 .. 40 and a long odd
+  one, aligned and unaligned destinations, and the 'does not fit' detection."""
+  import ctypes
+  from lidar_transfer_b200 import _lib
+  vl = _lib.lib()
+  rng = np.random.default_rng(3)
+  for n in list(range(0, 41)) + [87381, 100003]:
+    faces = rng.integers(0, 1 << 21, 3 * n).astype(np.int32)
+    colors = rng.integers(0, 256, 3 * n + 5).astype(np.int32)
+    for shift in (0, 1):                                      # 32-byte aligned / 8-byte aligned destination
+      buf = np.zeros(n + 8, np.uint64)
+      base = (-buf.ctypes.data // 8) % 4
+      out = buf[base + shift: base + shift + n]
+      c8 = np.zeros(colors.size + 32, np.uint8)
+      seen = np.zeros(2, np.uint32)
+      assert vl.vl_debug_pack(faces.ctypes.data, n, out.ctypes.data, colors.ctypes.data, colors.size, c8.ctypes.data + shift, seen.ctypes.data) == 0
+      f = faces.reshape(-1, 3).astype(np.uint64)
+      want = f[:, 0] | (f[:, 1] << np.uint64(21)) | (f[:, 2] << np.uint64(42))
+      assert np.array_equal(out, want), (n, shift)
+      assert np.array_equal(c8[shift:shift + colors.size], colors.astype(np.uint8)) and not c8[shift + colors.size:].any()
+      assert seen[0] >> 21 == 0 and seen[1] >> 8 == 0
+  for bad in (1 << 21, -1, (1 << 31) - 1):                     # an index that no 21-bit field holds, anywhere in the array
+    for pos in (0, 7, 24, 3 * 1000 - 1):
+      faces = rng.integers(0, 1 << 21, 3 * 1000).astype(np.int32)
+      faces[pos] = bad
+      seen = np.zeros(2, np.uint32)
+      out = np.zeros(1000, np.uint64)
+      vl.vl_debug_pack(faces.ctypes.data, 1000, out.ctypes.data, None, 0, None, seen.ctypes.data)
+      assert seen[0] >> 21 != 0, (bad, pos)
+  colors = np.array([0, 255, 256, 3], np.int32)
+  seen = np.zeros(2, np.uint32)
+  vl.vl_debug_pack(None, 0, None, colors.ctypes.data, 4, np.zeros(4, np.uint8).ctypes.data, seen.ctypes.data)
+  assert seen[1] >> 8 != 0
