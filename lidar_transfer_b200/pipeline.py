@@ -287,7 +287,10 @@ class ScanPipeline:
 
   Scans are independent, so a multi-GPU job gives each rank its own ScanPipeline over its shard (sharding.py)."""
 
-  def __init__(self, rays, height, fov_up, fov_down, vol_bnds, voxel_size, im_h, im_w, n_lanes=3, device=None, origin=None):
+  def __init__(self, rays, height, fov_up, fov_down, vol_bnds, voxel_size, im_h, im_w, n_lanes=3, device=None, origin=None,
+               expect_tris=0):
+    """expect_tris: size every lane's mesh arrays and cast workspace for this many triangles up front (they grow by
+    reallocation otherwise: the first ~100 scans of a process then run at half speed while the buffers find their size)."""
     engine.require_cuda()
     self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     self.fov_up, self.fov_down = float(fov_up), float(fov_down)
@@ -301,7 +304,15 @@ class ScanPipeline:
     self.n_rays = self.beams.n_rays
     self.origin = torch.zeros(3, device=self.dev) if origin is None else engine._dev(origin, torch.float32, self.dev).reshape(-1)
     self.lanes = [_Lane(self) for _ in range(max(1, int(n_lanes)))]
-    torch.cuda.current_stream(self.dev).synchronize()
+    if expect_tris > 0:
+      cap = int(expect_tris)
+      for lane in self.lanes:
+        with torch.cuda.stream(lane.stream):
+          lane.mesh_buf.update(cap_t=cap, verts=torch.empty((3 * cap, 3), dtype=torch.float32, device=self.dev), faces=None, norms=None,
+                               colors=torch.empty((3 * cap, 3), dtype=torch.uint8, device=self.dev),
+                               rem=torch.empty(3 * cap, dtype=torch.float32, device=self.dev))
+          lane.cast_ws = self.beams.workspace(cap)
+    torch.cuda.synchronize(self.dev)
 
   def _front(self, lane, tag, cloud):
     """points -> range / label / remission image -> TSDF -> triangle count on its way to the host"""
