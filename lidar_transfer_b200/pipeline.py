@@ -346,6 +346,8 @@ class ScanPipeline:
     """Generator over (tag, pinned result buffer) in submission order; `clouds` yields (points, remission, label) or
     (tag, points, remission, label).  A yielded buffer is valid until its lane is reused, n_lanes scans later."""
     n = len(self.lanes)
+    for lane in self.lanes:   # a previous run that was abandoned half way (an exception in the consumer) leaves no trace
+      lane.ctx = None
     waiting = []   # lanes in flight, oldest first (round robin: a lane that is needed again is always the oldest)
     k = 0
 
