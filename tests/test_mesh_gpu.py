@@ -109,3 +109,6 @@ def test_independent_torch_emitter_and_the_asymptotic_decider_on_the_real_scan(e
   t = r["topology"]
   assert t["hit_mask_flips"] == 0 and t["label_flips"] == 0 and t["range_changed_at_all"] == 0
   assert r["triangulation"]["range_changed_by_more_than_1cm"] > 1000 and r["topology_worst_case"]["range_changed_by_more_than_1cm"] > 1000
+  # Lewiner's interior test where it stands alone (MC33 case 4): a tunnel in a few hundred of ~half a million active cubes
+  assert 500 < r["body_diagonal_only_cubes_mc33_case_4"] < 5000
+  assert r["of_those_the_interior_test_joins_by_a_tunnel"] < 0.001 * r["active_cubes"]

@@ -168,6 +168,34 @@ def run(vox=0.05):
   res["ambiguous_cubes_the_decider_resolves_the_other_way"] = n_flip
   res["topology"] = compare(*emit(tsdf, color, rem, cube_idx, inv, rows2, dim, vox, origin),
                             "ambiguous faces resolved by the asymptotic decider (inside corners connected where their product is the larger)")
+  # Lewiner's INTERIOR test for the one configuration where it stands alone (MC33 case 4: exactly two like-signed corners, on
+  # a body diagonal): the two corners are joined by a tunnel iff, at the height t* where g(t) = At Ct - Bt Dt is extremal
+  # (At .. Dt: the trilinear interpolant on the four vertical edges, A / C the edges through the two corners), t* lies in
+  # (0, 1), At* and Ct* still have the corners' sign and g(t*) > 0 (their regions touch in that slice).  vl_mesh.cu's table
+  # always emits the two separate caps.
+  diag_pairs = [(0, 7), (1, 6), (2, 5), (3, 4)]
+  n_case4 = n_tunnel = 0
+  for lo_c, hi_c in diag_pairs:                      # lo_c has z = 0, hi_c = lo_c ^ 7 has z = 1
+    for sign in (-1.0, 1.0):                         # the pair is inside (negative) / the pair is outside (complement case)
+      mask = (1 << lo_c) | (1 << hi_c)
+      want = mask if sign < 0 else (255 ^ mask)
+      sel = torch.nonzero(cases == want).reshape(-1)
+      if sel.numel() == 0:
+        continue
+      ci = cube_idx[sel]
+      val = lambda c: flat[ci + off(c)]
+      xa, ya = lo_c & 1, (lo_c >> 1) & 1             # column of corner lo_c; hi_c sits in the opposite column
+      col = lambda x, y: (val(x | (y << 1)), val(x | (y << 1) | 4))    # (bottom, top) value of the vertical edge at (x, y)
+      A0, A1 = col(xa, ya); C0, C1 = col(1 - xa, 1 - ya); B0, B1 = col(xa, 1 - ya); D0, D1 = col(1 - xa, ya)
+      dA, dB, dC, dD = A1 - A0, B1 - B0, C1 - C0, D1 - D0
+      qa = dA * dC - dB * dD
+      qb = A0 * dC + C0 * dA - B0 * dD - D0 * dB
+      t = -qb / (2 * qa)
+      At, Bt, Ct, Dt = A0 + dA * t, B0 + dB * t, C0 + dC * t, D0 + dD * t
+      tunnel = (qa != 0) & (t > 0) & (t < 1) & (sign * At > 0) & (sign * Ct > 0) & (At * Ct - Bt * Dt > 0)
+      n_case4 += int(sel.numel()); n_tunnel += int(tunnel.sum())
+  res["body_diagonal_only_cubes_mc33_case_4"] = n_case4
+  res["of_those_the_interior_test_joins_by_a_tunnel"] = n_tunnel
   # the opposite rule everywhere (every ambiguous face connected): the largest effect ANY face decider could have
   bits_all = torch.zeros_like(cases)
   for f in range(6):
