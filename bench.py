@@ -292,9 +292,9 @@ def pipelines(L, dev):
 
 def sharded_pipeline_leg(rank, world, dev, n_manifest, barrier, reduce_max):
   """BASELINE.json configs[4] as the REAL pipeline: a manifest of n_manifest scans sharded round-robin over the ranks
-  (sharding.scans_for_rank), every scan through points (pinned host, 2.9 MB + 1 MB up) -> range image -> 284 M-voxel TSDF
+  (sharding.scans_for_rank), every scan through points (pinned host, float32 as in the scan file: 1.5 MB + 1 MB up) -> range image -> 284 M-voxel TSDF
   -> mesh -> 64x2048 cast -> results (4.2 MB packed, down to pinned host memory), no collective.  The mesh is born on
-  the device, so a scan moves 4 MB up instead of the 27 MB of the host-mesh interface.  Returns (scans, max-over-ranks ms)."""
+  the device, so a scan moves 2.5 MB up instead of the 27 MB of the host-mesh interface.  Returns (scans, max-over-ranks ms)."""
   import torch
   from lidar_transfer_b200 import pipeline, sharding, synth
   from lidar_transfer_b200.rays import create_rays
@@ -304,7 +304,8 @@ def sharded_pipeline_leg(rank, world, dev, n_manifest, barrier, reduce_max):
   for k in range(P):
     real = _fixture_scan(k % 3) if k < 3 else None
     pts, lab = real if real is not None else synth.make_scan_points(100 + rank * P + k, 124668)
-    clouds.append((torch.from_numpy(pts[:, :3].astype(np.float64)).pin_memory(), torch.from_numpy(pts[:, 3].copy()).pin_memory(),
+    # the scan file's own float32 coordinates (widened to float64 on the device: exact), remissions, labels
+    clouds.append((torch.from_numpy(np.ascontiguousarray(pts[:, :3], np.float32)).pin_memory(), torch.from_numpy(pts[:, 3].copy()).pin_memory(),
                    torch.from_numpy(lab.view(np.int32).copy()).pin_memory()))
   bnds = np.array([[-50, 50], [-31, 40], [-3, 2]], np.float64)
   dim = np.ceil((bnds[:, 1] - bnds[:, 0]) / 0.05).astype(int)

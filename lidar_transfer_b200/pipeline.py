@@ -282,7 +282,7 @@ class ScanPipeline:
   stream.  Same kernels, same bits as the sequential engine calls (tests/test_chain_gpu.py).
 
       pipe = ScanPipeline(rays, height, src_fov, vol_bnds, voxel_size, im_h, im_w)
-      for tag, h_out in pipe.run(clouds):      # clouds: iterable of (points f64[N,3], remission f32[N], label i32[N])
+      for tag, h_out in pipe.run(clouds):      # clouds: iterable of (points f64[N,3] or f32[N,3], remission f32[N], label i32[N])
         ...                                    # h_out: pinned uint8[32 R] = endpoints | endcolors | range | endrem
 
   Scans are independent, so a multi-GPU job gives each rank its own ScanPipeline over its shard (sharding.py)."""
@@ -318,6 +318,8 @@ class ScanPipeline:
     """points -> range / label / remission image -> TSDF -> triangle count on its way to the host"""
     with torch.cuda.stream(lane.stream):
       p64, rem, lab = (t.to(self.dev, non_blocking=True) if torch.is_tensor(t) else t for t in cloud)
+      if torch.is_tensor(p64) and p64.dtype == torch.float32:
+        p64 = p64.to(torch.float64)   # a scan file's float32 coordinates travel as they are (half the bytes) and are widened here: exact
       lane.inputs = (p64, rem, lab)
       pr = lane.proj = engine.project(p64, rem, lab, self.fov_up, self.fov_down, self.im_h, self.im_w, workspace=lane.ws,
                                       out=lane.proj, want_keep=False)

@@ -110,6 +110,11 @@ def test_scan_pipeline_equals_the_sequential_chain(engine, n_lanes):
   # tagged items, a second run on the same pipeline
   got2 = [(tag, h.clone()) for tag, h in pipe.run([("s%d" % k,) + c for k, c in enumerate(clouds[:3])])]
   assert [t for t, _ in got2] == ["s0", "s1", "s2"] and all(torch.equal(h, w) for (_, h), w in zip(got2, want))
+  if n_lanes == 3:   # float32 coordinates (a scan file's own dtype) are widened on the device: the same bytes as float64 input
+    got4 = [h.clone() for _, h in pipe.run([(c[0].to(torch.float32),) + c[1:] for c in clouds[:4]])]
+    c32 = [(c[0].to(torch.float32).to(torch.float64),) + c[1:] for c in clouds[:4]]
+    ref4 = [h.clone() for _, h in pipe.run(c32)]
+    assert all(torch.equal(a, b) for a, b in zip(got4, ref4))
   if n_lanes == 2:   # buffers sized up front (too small on purpose for some of the meshes: they still grow)
     pipe2 = pipeline.ScanPipeline(rays, H, fu, fd, bnds, vox, H, W, n_lanes=2, expect_tris=20000)
     got3 = [h.clone() for _, h in pipe2.run(clouds)]
