@@ -802,7 +802,6 @@ k_cast_units(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const int* _
              unsigned long long* __restrict__ best, const VlCastHeader* __restrict__ chdr,
              const float4* __restrict__ recs, const int2* __restrict__ units) {
   __shared__ UnitRec s_rec[kCastWarps][32];
-  __shared__ int s_off[kCastWarps][33];
   if (chdr->overflow) return;
   const unsigned long long n_units = chdr->reserved & ((1ull << kUnitBits) - 1ull);
   const float3 o = make_float3(__ldg(origin), __ldg(origin + 1), __ldg(origin + 2));
@@ -812,10 +811,14 @@ k_cast_units(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const int* _
   for (unsigned long long g = (unsigned long long)blockIdx.x * kCastWarps + w; g < n_groups; g += g_stride) {
     const unsigned long long u = g * 32 + lane;
     int n_r = 0;
+    const float4* rec = recs;
+    float slo = 0.f, shi = 0.f;
+    int ka0 = 0, ka1 = 0, kb0 = 0, kb1 = 0;
     if (u < n_units) {
       const int2 unit = __ldg(units + u);
-      const float4* rec = recs + 4 * (size_t)unit.x;
+      rec = recs + 4 * (size_t)unit.x;
       const float4 q3 = __ldg(rec + 3);
+      slo = q3.x; shi = q3.y;
       const int pk0 = __float_as_int(q3.z), pk1 = __float_as_int(q3.w);
       const int ca = pk0 & 0xffff, ncx = (pk0 >> 16) & 0x1fff, ra = pk1 & 0xffff;
       const int sh = (pk0 >> 30) & 1 ? kSegShiftWide : kSegShift;
@@ -827,44 +830,47 @@ k_cast_units(const VlBeamHeader* __restrict__ bhdr, int cw, int ch, const int* _
       if (c_begin >= cw) c_begin -= cw;
       const int len_a = min(len, cw - c_begin), len_b = len - len_a;
       const int* row = cell_start + (size_t)(ra + yy) * cw;
-      const int ka0 = __ldg(row + c_begin), ka1 = __ldg(row + c_begin + len_a);
-      int kb0 = 0, kb1 = 0;
+      ka0 = __ldg(row + c_begin); ka1 = __ldg(row + c_begin + len_a);
       if (len_b > 0) { kb0 = __ldg(row); kb1 = __ldg(row + len_b); }
       n_r = ka1 - ka0 + kb1 - kb0;
-      if (n_r > 0) {
-        const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
-        UnitRec& R = s_rec[w][lane];
-        R.v0x = q0.x; R.v0y = q0.y; R.v0z = q0.z; R.e1x = q0.w; R.e1y = q1.x; R.e1z = q1.y; R.e2x = q1.z; R.e2y = q1.w; R.e2z = q2.x;
-        R.orig = (unsigned int)__float_as_int(q2.y); R.ymid = q2.z; R.yhalf = q2.w; R.slo = q3.x; R.shi = q3.y;
-        R.ka0 = ka0; R.ka1 = ka1; R.kb0 = kb0; R.kb1 = kb1;
-      }
     }
     int incl = n_r;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     if (total == 0) continue;   // warp-uniform
-    s_off[w][lane] = incl - n_r;
-    if (lane == 31) s_off[w][32] = total;
+    const int off = incl - n_r;                                     // first pooled candidate of this lane's unit
+    const unsigned int nz = __ballot_sync(0xffffffffu, n_r > 0);
+    if (n_r > 0) {   // the units that have beams at all, parked densely: slot = rank among them (their offsets are strictly increasing)
+      const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+      UnitRec& R = s_rec[w][__popc(nz & ((1u << lane) - 1u))];
+      R.v0x = q0.x; R.v0y = q0.y; R.v0z = q0.z; R.e1x = q0.w; R.e1y = q1.x; R.e1z = q1.y; R.e2x = q1.z; R.e2y = q1.w; R.e2z = q2.x;
+      R.orig = (unsigned int)__float_as_int(q2.y); R.ymid = q2.z; R.yhalf = q2.w; R.slo = slo; R.shi = shi;
+      R.ka0 = ka0 - off; R.ka1 = ka1; R.kb0 = kb0; R.kb1 = kb1;      // candidate number -> sorted-beam index: ka0 - off + it
+    }
     __syncwarp();
-    for (int it = lane; it < total; it += 32) {
-      int j = 0;
-#pragma unroll
-      for (int step = 16; step > 0; step >>= 1) if (s_off[w][j + step] <= it) j += step;
-      const UnitRec& R = s_rec[w][j];
-      int k = R.ka0 + (it - s_off[w][j]);
-      if (k >= R.ka1) k = R.kb0 + (k - R.ka1);
-      const float4 rd = __ldg(sorted + k);
-      if (rd.z < R.slo || rd.z > R.shi) continue;
-#ifdef VL_CAST_YAW_FILTER   // measured: rejects 12 % of what the sine filter lets through and costs more than their triangle tests
-      if (R.yhalf >= 0.f && fabsf(wrap_2(rd.w - R.ymid)) > R.yhalf) continue;
-#endif
-      float t;
-      if (vl_tri_hit(make_float4(R.v0x, R.v0y, R.v0z, 0.f), make_float4(R.e1x, R.e1y, R.e1z, 0.f),
-                     make_float4(R.e2x, R.e2y, R.e2z, 0.f), o, make_float3(rd.x, rd.y, rd.z), &t)) {
-        // a NaN t orders above the initial key and never wins; no value is read back (RED, not ATOM)
-        atomicMin(best + k, ((unsigned long long)__float_as_uint(t) << 32) | R.orig);
+    int jb = 0;   // parked units that start before `base`
+    for (int base = 0; base < total; base += 32) {
+      // candidate -> unit without a search: the units that START inside this stretch of 32 candidates mark their first
+      // candidate in one word (one warp-wide OR); a candidate's unit is the number of marks at or below it
+      const int rel = off - base;
+      const unsigned int M = __reduce_or_sync(0xffffffffu, (n_r > 0 && rel >= 0 && rel < 32) ? (1u << rel) : 0u);
+      const int it = base + lane;
+      if (it < total) {
+        const UnitRec& R = s_rec[w][jb + __popc(M & (0xffffffffu >> (31 - lane))) - 1];
+        int k = R.ka0 + it;
+        if (k >= R.ka1) k = R.kb0 + (k - R.ka1);
+        const float4 rd = __ldg(sorted + k);
+        if (!(rd.z < R.slo || rd.z > R.shi)) {
+          float t;
+          if (vl_tri_hit(make_float4(R.v0x, R.v0y, R.v0z, 0.f), make_float4(R.e1x, R.e1y, R.e1z, 0.f),
+                         make_float4(R.e2x, R.e2y, R.e2z, 0.f), o, make_float3(rd.x, rd.y, rd.z), &t)) {
+            // a NaN t orders above the initial key and never wins; no value is read back (RED, not ATOM)
+            atomicMin(best + k, ((unsigned long long)__float_as_uint(t) << 32) | R.orig);
+          }
+        }
       }
+      jb += __popc(M);
     }
     __syncwarp();
   }
