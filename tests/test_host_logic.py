@@ -295,3 +295,53 @@ def test_staging_pack_loops_match_numpy():
   seen = np.zeros(2, np.uint32)
   vl.vl_debug_pack(None, 0, None, colors.ctypes.data, 4, np.zeros(4, np.uint8).ctypes.data, seen.ctypes.data)
   assert seen[1] >> 8 != 0
+
+
+def test_scan_pipeline_schedule_without_a_device():
+  """The software pipelining of pipeline.ScanPipeline.run, with the device work replaced by a log: results come out in
+  submission order; a lane is reused only after its previous scan has been handed out; with two or more lanes the second
+  half of scan k (the one that waits for the triangle count) is issued AFTER the first half of scan k + 1, so the device
+  has work while the host waits; an abandoned run leaves no state behind."""
+  from lidar_transfer_b200 import pipeline
+
+  class Ev:
+    def synchronize(self):
+      pass
+
+  class Lane:
+    def __init__(self, i):
+      self.i, self.ctx, self.tag, self.done, self.h_out = i, None, None, Ev(), "out%d" % i
+
+  for n_lanes in (1, 2, 3, 5):
+    pipe = object.__new__(pipeline.ScanPipeline)
+    pipe.lanes = [Lane(i) for i in range(n_lanes)]
+    log = []
+
+    def front(lane, tag, cloud):
+      assert lane.ctx is None, "lane reused before its scan was finished"
+      lane.ctx, lane.tag = ("count of", tag), tag
+      log.append(("front", tag, lane.i))
+
+    def back(lane):
+      assert lane.ctx is not None
+      log.append(("back", lane.tag, lane.i))
+      lane.ctx = None
+    pipe._front, pipe._back = front, back
+    clouds = [("p%d" % k, "r", "l") for k in range(11)]
+    out = list(pipe.run(clouds))
+    assert [t for t, _ in out] == list(range(11)) and [h for _, h in out] == ["out%d" % (k % n_lanes) for k in range(11)]
+    fronts = [e[1] for e in log if e[0] == "front"]
+    backs = [e[1] for e in log if e[0] == "back"]
+    assert fronts == list(range(11)) and backs == list(range(11))
+    pos = {(e[0], e[1]): i for i, e in enumerate(log)}
+    for k in range(10):
+      if n_lanes >= 2:
+        assert pos[("front", k + 1)] < pos[("back", k)], (n_lanes, k)      # the next scan's kernels are queued first
+      assert pos[("back", k)] < pos[("front", k + n_lanes)] if k + n_lanes < 11 else True
+    # a consumer that stops half way, then a fresh run on the same object
+    gen = pipe.run(clouds)
+    next(gen)
+    gen.close()
+    log.clear()
+    out = list(pipe.run([("tag%d" % k,) + c for k, c in enumerate(clouds[:4])]))
+    assert [t for t, _ in out] == ["tag0", "tag1", "tag2", "tag3"]
