@@ -711,7 +711,13 @@ extern "C" int vl_ctrace_ids(const float* rays, const float* origin, const float
   std::lock_guard<std::mutex> lock(g_ctx.mu);
   const int rc = ctrace_locked(g_ctx, rays, origin, verts, faces, colors, rem, n_rays, n_verts, n_faces, height, endpoints,
                                endcolors, range, endrem, tri_id);
-  if (rc != VL_OK && rc != VL_EBADMESH) g_ctx.cache_valid = false;
+  if (rc != VL_OK && rc != VL_EBADMESH) {
+    g_ctx.cache_valid = false;
+    // a call that failed half way may have copies in flight out of the staging buffers the next call will overwrite
+    if (g_ctx.stream) cudaStreamSynchronize(g_ctx.stream);
+    if (g_ctx.stream2) cudaStreamSynchronize(g_ctx.stream2);
+    cudaGetLastError();
+  }
   return rc;
 }
 
