@@ -1008,7 +1008,10 @@ static int cast_enqueue(const void* d_beams, const VlMeshDesc& mesh, bool by_ptr
   const bool front = (phases & VL_CAST_PHASE_FRONT) != 0, back = (phases & VL_CAST_PHASE_RESOLVE) != 0;
   if (back && d_tri_id && n_rays > L.n)   // rays beyond width * height are never cast (RayTracer.cpp:56)
     VL_CUDA_CHECK(cudaMemsetAsync(d_tri_id + L.n, 0xff, sizeof(int) * (size_t)(n_rays - L.n), stream));
-  if (L.n <= 0) return VL_OK;
+  if (L.n <= 0) {   // no ray is cast (fewer rays than rows): no kernel runs, but vl_cast_status must not read a stale header
+    if (d_ws) VL_CUDA_CHECK(cudaMemsetAsync(d_ws, 0, sizeof(VlCastHeader), stream));
+    return VL_OK;
+  }
   const char* B = static_cast<const char*>(d_beams);
   const VlBeamHeader* bhdr = reinterpret_cast<const VlBeamHeader*>(B);
   const float4* dir = reinterpret_cast<const float4*>(B + L.off_dir);
