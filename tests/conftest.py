@@ -37,3 +37,18 @@ def engine(vl):
     pytest.skip("no CUDA device")
   from lidar_transfer_b200 import engine as E
   return E
+
+
+@pytest.fixture(autouse=True)
+def _poison_recycled_device_memory(request):
+  """VL_POISON=1 (stress aid): before every GPU test a large block of device memory is filled with 0xCD and handed back
+  to torch's caching allocator, so that every `torch.empty` the test makes comes out of memory full of garbage -- a
+  kernel or a status read that relies on memory it never initialised then fails here instead of once in a while."""
+  if os.environ.get("VL_POISON") and request.node.get_closest_marker("gpu") is not None:
+    import torch
+    if torch.cuda.is_available():
+      torch.cuda.empty_cache()
+      junk = [torch.full((1 << 30,), 0xCD, dtype=torch.uint8, device="cuda") for _ in range(6)]
+      del junk
+      torch.cuda.synchronize()
+  yield
